@@ -1,0 +1,273 @@
+"""Batched device API over libagt.so: one ``AgtContext`` per GPU (one process per GPU).
+
+torch is plumbing only here: it owns the device allocations (frames, pyramids,
+points, poses) and the stream; every kernel that runs is hand-written CUDA
+launched through the C ABI on ``torch.cuda.current_stream()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib, synth
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device visible: the AprilGroup tracking path has no CPU fallback")
+    return torch
+
+
+@dataclass
+class Pyramid:
+    """Device pyramid batch: levels[l] is a uint8 tensor [B, h_l, pitch_l]."""
+    levels: List["object"]
+    widths: List[int]
+    heights: List[int]
+    desc: _lib.AgtPyramid
+    batch: int
+
+    @property
+    def frames(self):
+        """Level-0 view [B, H, W]."""
+        return self.levels[0][:, :, : self.widths[0]]
+
+    def level(self, l: int):
+        return self.levels[l][:, :, : self.widths[l]]
+
+
+class AgtContext:
+    def __init__(self, device: int = 0, mtx: Optional[np.ndarray] = None, dist: Optional[np.ndarray] = None):
+        self.lib = _lib.load()
+        self.torch = _torch()
+        self.device = int(device)
+        self.tdev = self.torch.device("cuda", self.device)
+        h = C.c_void_p()
+        rc = self.lib.agt_create(self.device, C.byref(h))
+        if rc != _lib.AGT_OK:
+            msg = self.lib.agt_last_error(None)
+            raise RuntimeError(f"agt_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.h = h
+        self._model = None
+        if mtx is not None:
+            self.set_camera(mtx, dist)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.agt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing -----------------------------------------------------------------
+    def _check(self, rc, what=""):
+        _lib.check(self.h, rc, what)
+
+    def _use_current_stream(self):
+        s = self.torch.cuda.current_stream(self.tdev).cuda_stream
+        self._check(self.lib.agt_set_stream(self.h, C.c_void_p(s)))
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _dev(self, arr, dtype):
+        t = self.torch
+        if isinstance(arr, t.Tensor):
+            return arr.to(device=self.tdev, dtype=dtype).contiguous()
+        return t.as_tensor(np.ascontiguousarray(arr), dtype=dtype, device=self.tdev).contiguous()
+
+    def launch_count(self) -> int:
+        return int(self.lib.agt_launch_count(self.h))
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.tdev)
+
+    # -- configuration --------------------------------------------------------------
+    def set_camera(self, mtx: np.ndarray, dist: Optional[np.ndarray] = None):
+        k = np.ascontiguousarray(np.asarray(mtx, dtype=np.float64).reshape(9))
+        if dist is None:
+            d, nd = None, 0
+        else:
+            d = np.ascontiguousarray(np.asarray(dist, dtype=np.float64).reshape(-1))
+            nd = int(d.size)
+        self._check(self.lib.agt_set_camera(self.h, k.ctypes.data_as(C.POINTER(C.c_double)),
+                                            d.ctypes.data_as(C.POINTER(C.c_double)) if d is not None else None, nd))
+        self.mtx = np.asarray(mtx, dtype=np.float64).reshape(3, 3).copy()
+        self.dist = None if dist is None else d.copy()
+
+    def set_model(self, samples: np.ndarray, sample_tag: np.ndarray, normals: np.ndarray, centres: np.ndarray, pitch: float):
+        s = np.ascontiguousarray(samples, dtype=np.float32)
+        tg = np.ascontiguousarray(sample_tag, dtype=np.uint8)
+        n = np.ascontiguousarray(normals, dtype=np.float32)
+        c = np.ascontiguousarray(centres, dtype=np.float32)
+        self._check(self.lib.agt_set_model(self.h, s.ctypes.data, tg.ctypes.data, int(s.shape[0]), n.ctypes.data,
+                                           c.ctypes.data, int(n.shape[0]), float(pitch)))
+        self._model = (s, tg, n, c, float(pitch))
+
+    def set_synthetic_model(self):
+        s, tg, n, c = synth.surface_model()
+        self.set_model(s, tg, n, c, synth.model_pitch())
+
+    # -- pyramids -------------------------------------------------------------------
+    def alloc_pyramid(self, batch: int, width: int, height: int, levels: int = 4) -> Pyramid:
+        t = self.torch
+        desc = _lib.AgtPyramid()
+        desc.levels = levels
+        lv, ws, hs = [], [], []
+        w, h = width, height
+        for l in range(levels):
+            pitch = (w + 15) // 16 * 16
+            buf = t.empty((batch, h, pitch), dtype=t.uint8, device=self.tdev)
+            lv.append(buf); ws.append(w); hs.append(h)
+            desc.width[l], desc.height[l] = w, h
+            desc.pitch[l], desc.frame_stride[l] = pitch, pitch * h
+            desc.data[l] = buf.data_ptr()
+            w, h = (w + 1) // 2, (h + 1) // 2
+        return Pyramid(lv, ws, hs, desc, batch)
+
+    def upload_frames(self, pyr: Pyramid, frames) -> None:
+        """frames: [B,H,W] uint8 numpy array or tensor -> level 0."""
+        t = self.torch
+        src = frames if isinstance(frames, t.Tensor) else t.from_numpy(np.ascontiguousarray(frames))
+        pyr.frames.copy_(src.to(self.tdev, non_blocking=True))
+
+    def build_pyramid(self, pyr: Pyramid, batch: Optional[int] = None) -> None:
+        self._use_current_stream()
+        self._check(self.lib.agt_build_pyramid(self.h, C.byref(pyr.desc), int(pyr.batch if batch is None else batch)))
+
+    def scharr(self, pyr: Pyramid, level: int = 0):
+        """-> int16 tensor [B, h, w, 2] (dx, dy) of one level."""
+        t = self.torch
+        w, h = pyr.widths[level], pyr.heights[level]
+        out = t.empty((pyr.batch, h, w, 2), dtype=t.int16, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_scharr(self.h, self._p(pyr.levels[level]), w, h, pyr.desc.pitch[level],
+                                        pyr.desc.frame_stride[level], self._p(out), pyr.batch))
+        return out
+
+    # -- K2 ---------------------------------------------------------------------------
+    def lk(self, prev: Pyramid, nxt: Pyramid, prev_pts):
+        """prev_pts [B,P,2] float32 -> (next_pts [B,P,2] f32, status [B,P] u8, err [B,P] f32)."""
+        t = self.torch
+        pts = self._dev(prev_pts, t.float32)
+        b, p = int(pts.shape[0]), int(pts.shape[1])
+        out = t.empty_like(pts)
+        st = t.empty((b, p), dtype=t.uint8, device=self.tdev)
+        err = t.empty((b, p), dtype=t.float32, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_lk(self.h, C.byref(prev.desc), C.byref(nxt.desc), self._p(pts), self._p(out), self._p(st),
+                                    self._p(err), b, p))
+        return out, st, err
+
+    # -- K3 ---------------------------------------------------------------------------
+    def pnp(self, obj_pts, img_pts, valid=None, guess=None, use_guess=None):
+        """obj [P,3] f32 shared, img [B,P,2] f32, valid [B,P] u8, guess [B,6] f64, use_guess [B] u8
+        -> (pose [B,6] f64, ok [B] u8, reproj_err [B] f32, iters [B] i32)."""
+        t = self.torch
+        obj = self._dev(obj_pts, t.float32)
+        img = self._dev(img_pts, t.float32)
+        b, p = int(img.shape[0]), int(img.shape[1])
+        if obj.shape[0] != p:
+            raise ValueError("obj_pts and img_pts disagree on the number of points")
+        v = self._dev(valid, t.uint8) if valid is not None else None
+        g = self._dev(guess, t.float64) if guess is not None else None
+        ug = self._dev(use_guess, t.uint8) if use_guess is not None else (
+            t.ones(b, dtype=t.uint8, device=self.tdev) if g is not None else None)
+        pose = t.empty((b, 6), dtype=t.float64, device=self.tdev)
+        ok = t.empty(b, dtype=t.uint8, device=self.tdev)
+        err = t.empty(b, dtype=t.float32, device=self.tdev)
+        iters = t.empty(b, dtype=t.int32, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_pnp(self.h, self._p(obj), self._p(img), self._p(v), self._p(g), self._p(ug), self._p(pose),
+                                     self._p(ok), self._p(err), self._p(iters), b, p))
+        return pose, ok, err, iters
+
+    def project(self, obj_pts, poses):
+        t = self.torch
+        obj = self._dev(obj_pts, t.float32)
+        ps = self._dev(poses, t.float64).reshape(-1, 6)
+        out = t.empty((ps.shape[0], obj.shape[0], 2), dtype=t.float64, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_project(self.h, self._p(obj), self._p(ps), self._p(out), int(ps.shape[0]), int(obj.shape[0])))
+        return out
+
+    # -- K0 ---------------------------------------------------------------------------
+    def new_stream_state(self, n_streams: int):
+        t = self.torch
+        return t.zeros((n_streams, _lib.AGT_STREAM_STATE_DOUBLES), dtype=t.float64, device=self.tdev)
+
+    def ape_prepare(self, state, enhance_ape: bool = True):
+        t = self.torch
+        b = int(state.shape[0])
+        guess = t.empty((b, 6), dtype=t.float64, device=self.tdev)
+        use = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_ape_prepare(self.h, self._p(state), self._p(guess), self._p(use), b, int(enhance_ape)))
+        return guess, use
+
+    def ape_update(self, state, n_tags, pose, ok, err, enhance_ape: bool = True):
+        t = self.torch
+        b = int(state.shape[0])
+        nt = self._dev(n_tags, t.int32)
+        acc = t.empty(b, dtype=t.uint8, device=self.tdev)
+        flag = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_ape_update(self.h, self._p(state), self._p(nt), self._p(pose), self._p(ok), self._p(err),
+                                            self._p(acc), self._p(flag), b, int(enhance_ape)))
+        return acc, flag
+
+    # -- K4 ---------------------------------------------------------------------------
+    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
+        """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status)."""
+        t = self.torch
+        b = int(pyr.batch if batch is None else batch)
+        ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
+        pose = t.empty_like(ini)
+        cost = t.empty((b, n_hyp), dtype=t.float32, device=self.tdev)
+        nv = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
+        ev = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
+        st = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(pose), self._p(cost),
+                                        self._p(nv), self._p(ev), self._p(st), b))
+        return {"pose": pose, "cost": cost, "n_valid": nv, "evals": ev, "status": st}
+
+    def select_best(self, res):
+        t = self.torch
+        b, h = int(res["pose"].shape[0]), int(res["pose"].shape[1])
+        best = t.empty(b, dtype=t.int32, device=self.tdev)
+        bp = t.empty((b, 6), dtype=t.float64, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_select_best(self.h, self._p(res["pose"]), self._p(res["cost"]), self._p(res["n_valid"]), h,
+                                             self._p(best), self._p(bp), b))
+        return best, bp
+
+    # -- synthetic frames ---------------------------------------------------------------
+    def render(self, pyr: Pyramid, poses, seeds, noise: bool = True, batch: Optional[int] = None, offset: int = 0) -> None:
+        """Render the synthetic dodecahedron into level 0 of frames [offset, offset+batch)."""
+        t = self.torch
+        ps = self._dev(poses, t.float64).reshape(-1, 6)
+        b = int(ps.shape[0] if batch is None else batch)
+        if isinstance(seeds, t.Tensor):
+            seeds = seeds.detach().cpu().numpy()
+        sd32 = self._dev((np.asarray(seeds).astype(np.int64) & 0xFFFFFFFF).astype(np.uint32).view(np.int32), t.int32)
+        if not hasattr(self, "_render_consts"):
+            rk, tk = synth.group_transforms_f32()
+            rt = np.concatenate([rk.reshape(12, 9), tk.reshape(12, 3)], axis=1)
+            cells = synth.all_tag_cells().astype(np.uint8).reshape(12, 100)
+            self._render_consts = (self._dev(rt, t.float64), self._dev(cells, t.uint8))
+        rt, cells = self._render_consts
+        base = pyr.levels[0].data_ptr() + offset * pyr.desc.frame_stride[0]
+        self._use_current_stream()
+        self._check(self.lib.agt_render(self.h, self._p(ps), self._p(sd32), C.c_void_p(base), pyr.widths[0], pyr.heights[0],
+                                        pyr.desc.pitch[0], pyr.desc.frame_stride[0], self._p(rt), self._p(cells), 12,
+                                        synth.INRADIUS, synth.CELL, int(noise), b))

@@ -1,0 +1,381 @@
+// Context lifecycle, configuration and the host-buffer entry points of libagt.so.
+#include <new>
+
+#include "agt_common.cuh"
+
+char g_agt_create_error[512] = "";
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Describe a pyramid for `batch` frames packed into one allocation; returns bytes.
+int64_t layout_pyramid(agt_pyramid* p, uint8_t* base, int w, int h, int levels, int batch) {
+  memset(p, 0, sizeof(*p));
+  p->levels = levels;
+  int64_t off = 0;
+  for (int l = 0; l < levels; ++l) {
+    p->width[l] = w; p->height[l] = h;
+    p->pitch[l] = align_up(w, 16);
+    p->frame_stride[l] = p->pitch[l] * h;
+    p->data[l] = base ? base + off : nullptr;
+    off += align_up(p->frame_stride[l] * batch, 256);
+    w = (w + 1) / 2; h = (h + 1) / 2;
+  }
+  return off;
+}
+
+}  // namespace
+
+int agt_scratch(agt_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      AGT_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+      ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+    }
+    AGT_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], bytes));
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  *out = ctx->scratch[slot];
+  return AGT_OK;
+}
+
+extern "C" int agt_version(void) { return AGT_VERSION; }
+
+extern "C" int agt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char* agt_last_error(const agt_ctx* ctx) { return ctx ? ctx->err : g_agt_create_error; }
+
+extern "C" int agt_create(int device, agt_ctx** out) {
+  if (!out) { snprintf(g_agt_create_error, sizeof(g_agt_create_error), "agt_create: out is NULL"); return AGT_ERR_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    snprintf(g_agt_create_error, sizeof(g_agt_create_error),
+             "agt_create: no CUDA device available (%s); this library has no CPU fallback",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return AGT_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    snprintf(g_agt_create_error, sizeof(g_agt_create_error), "agt_create: device %d out of range (0..%d)", device, n - 1);
+    return AGT_ERR_INVALID;
+  }
+  agt_ctx* ctx = new (std::nothrow) agt_ctx();
+  if (!ctx) { snprintf(g_agt_create_error, sizeof(g_agt_create_error), "agt_create: out of host memory"); return AGT_ERR_INVALID; }
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    snprintf(g_agt_create_error, sizeof(g_agt_create_error), "agt_create: %s", cudaGetErrorString(e));
+    delete ctx;
+    return AGT_ERR_CUDA;
+  }
+  if (prop.major < 10) {
+    snprintf(g_agt_create_error, sizeof(g_agt_create_error),
+             "agt_create: device %d is sm_%d%d; libagt.so is built for sm_100a only", device, prop.major, prop.minor);
+    cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return AGT_ERR_NO_DEVICE;
+  }
+  for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return AGT_OK;
+}
+
+extern "C" int agt_destroy(agt_ctx* ctx) {
+  if (!ctx) return AGT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  for (int i = 0; i < 8; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->model.samples) cudaFree(ctx->model.samples);
+  for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return AGT_OK;
+}
+
+extern "C" int agt_set_stream(agt_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return AGT_ERR_INVALID;
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);   // 0 = the legacy default stream
+  return AGT_OK;
+}
+
+extern "C" int agt_sync(agt_ctx* ctx) {
+  if (!ctx) return AGT_ERR_INVALID;
+  AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return AGT_OK;
+}
+
+extern "C" int64_t agt_launch_count(const agt_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int agt_set_camera(agt_ctx* ctx, const double k[9], const double* dist, int ndist) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!k) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_camera: K is NULL");
+  if (ndist != 0 && ndist != 4 && ndist != 5) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_camera: ndist must be 0, 4 or 5 (got %d)", ndist);
+  if (ndist && !dist) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_camera: dist is NULL");
+  if (!(k[0] > 0.0) || !(k[4] > 0.0)) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_camera: focal lengths must be positive");
+  agt_camera c;
+  memset(&c, 0, sizeof(c));
+  c.fx = k[0]; c.fy = k[4]; c.cx = k[2]; c.cy = k[5];
+  if (ndist) {
+    c.k1 = dist[0]; c.k2 = dist[1]; c.p1 = dist[2]; c.p2 = dist[3]; c.k3 = ndist == 5 ? dist[4] : 0.0;
+    c.has_dist = (c.k1 != 0.0 || c.k2 != 0.0 || c.p1 != 0.0 || c.p2 != 0.0 || c.k3 != 0.0);
+  }
+  ctx->cam = c;
+  ctx->camera_set = 1;
+  return AGT_OK;
+}
+
+extern "C" int agt_set_model(agt_ctx* ctx, const float* h_samples, const uint8_t* h_sample_tag, int n_samples,
+                             const float* h_tag_normals, const float* h_tag_centres, int n_tags, double pitch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_samples || !h_sample_tag || !h_tag_normals || !h_tag_centres || n_samples < 1 || n_tags < 1 || n_tags > AGT_MAX_TAGS ||
+      !(pitch > 0.0))
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_model: bad arguments (n_samples=%d n_tags=%d)", n_samples, n_tags);
+  agt_model m;
+  memset(&m, 0, sizeof(m));
+  int tag = 0;
+  m.tag_begin[0] = 0;
+  for (int i = 0; i < n_samples; ++i) {
+    int t = h_sample_tag[i];
+    if (t >= n_tags || t < tag) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_model: samples must be tag-major with tags < n_tags (sample %d)", i);
+    while (tag < t) m.tag_begin[++tag] = i;
+  }
+  while (tag < n_tags) m.tag_begin[++tag] = n_samples;
+  for (int k = 0; k < n_tags; ++k)
+    for (int i = 0; i < 3; ++i) { m.normals[k][i] = h_tag_normals[k * 3 + i]; m.centres[k][i] = h_tag_centres[k * 3 + i]; }
+  m.n_samples = n_samples; m.n_tags = n_tags; m.pitch = pitch;
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->model.samples) { AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->model.samples); ctx->model.samples = nullptr; }
+  AGT_CUDA(ctx, cudaMalloc(&m.samples, sizeof(float4) * (size_t)n_samples));
+  AGT_CUDA(ctx, cudaMemcpy(m.samples, h_samples, sizeof(float4) * (size_t)n_samples, cudaMemcpyHostToDevice));
+  ctx->model = m;
+  ctx->model_set = 1;
+  return AGT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------
+extern "C" int agt_solve_pnp_host(agt_ctx* ctx, const float* h_obj, const float* h_img, int n_pts, int use_guess,
+                                  double h_pose[6], int* ok, float* reproj_err) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_obj || !h_img || !h_pose || n_pts < 1 || n_pts > AGT_MAX_POINTS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_solve_pnp_host: bad arguments (n_pts=%d, max %d)", n_pts, AGT_MAX_POINTS);
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t* d;
+  size_t o_obj = 0, o_img = o_obj + 768, o_guess = o_img + 512, o_pose = o_guess + 64, o_err = o_pose + 64, o_ok = o_err + 16,
+         o_ug = o_ok + 16, total = o_ug + 16;
+  int rc = agt_scratch(ctx, 7, total, reinterpret_cast<void**>(&d));
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  uint8_t ug = use_guess ? 1 : 0;
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_obj, h_obj, sizeof(float) * 3 * n_pts, cudaMemcpyHostToDevice, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_img, h_img, sizeof(float) * 2 * n_pts, cudaMemcpyHostToDevice, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_guess, h_pose, sizeof(double) * 6, cudaMemcpyHostToDevice, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_ug, &ug, 1, cudaMemcpyHostToDevice, st));
+  rc = agt_pnp(ctx, reinterpret_cast<float*>(d + o_obj), reinterpret_cast<float*>(d + o_img), nullptr,
+               reinterpret_cast<double*>(d + o_guess), d + o_ug, reinterpret_cast<double*>(d + o_pose), d + o_ok,
+               reinterpret_cast<float*>(d + o_err), nullptr, 1, n_pts);
+  if (rc) return rc;
+  uint8_t okb = 0;
+  float e = 0.f;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_pose, d + o_pose, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(&okb, d + o_ok, 1, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(&e, d + o_err, sizeof(float), cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  if (ok) *ok = okb;
+  if (reproj_err) *reproj_err = e;
+  return AGT_OK;
+}
+
+extern "C" int agt_project_host(agt_ctx* ctx, const float* h_obj, int n_pts, const double h_pose[6], double* h_out) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_obj || !h_pose || !h_out || n_pts < 1) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_project_host: bad arguments");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t* d;
+  size_t o_obj = 0, o_pose = align_up(sizeof(float) * 3 * n_pts, 64), o_out = o_pose + 64, total = o_out + sizeof(double) * 2 * n_pts;
+  int rc = agt_scratch(ctx, 7, total, reinterpret_cast<void**>(&d));
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_obj, h_obj, sizeof(float) * 3 * n_pts, cudaMemcpyHostToDevice, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(d + o_pose, h_pose, sizeof(double) * 6, cudaMemcpyHostToDevice, st));
+  rc = agt_project(ctx, reinterpret_cast<float*>(d + o_obj), reinterpret_cast<double*>(d + o_pose),
+                   reinterpret_cast<double*>(d + o_out), 1, n_pts);
+  if (rc) return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_out, d + o_out, sizeof(double) * 2 * n_pts, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}
+
+// upload a tightly packed host image into level 0 of a (batch 1) pyramid
+static int upload_level0(agt_ctx* ctx, const agt_pyramid& p, const uint8_t* h_img, cudaStream_t st) {
+  AGT_CUDA(ctx, cudaMemcpy2DAsync(p.data[0], (size_t)p.pitch[0], h_img, (size_t)p.width[0], (size_t)p.width[0],
+                                  (size_t)p.height[0], cudaMemcpyHostToDevice, st));
+  return AGT_OK;
+}
+
+extern "C" int agt_pyramid_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int levels, uint8_t* const* h_levels) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_img || !h_levels || w < 1 || h < 1 || levels < 1 || levels > AGT_MAX_LEVELS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pyramid_host: bad arguments");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  agt_pyramid p;
+  int64_t bytes = layout_pyramid(&p, nullptr, w, h, levels, 1);
+  uint8_t* d;
+  int rc = agt_scratch(ctx, 0, (size_t)bytes, reinterpret_cast<void**>(&d));
+  if (rc) return rc;
+  layout_pyramid(&p, d, w, h, levels, 1);
+  cudaStream_t st = ctx->stream;
+  if ((rc = upload_level0(ctx, p, h_img, st))) return rc;
+  if ((rc = agt_build_pyramid(ctx, &p, 1))) return rc;
+  for (int l = 1; l < levels; ++l)
+    if (h_levels[l])
+      AGT_CUDA(ctx, cudaMemcpy2DAsync(h_levels[l], (size_t)p.width[l], p.data[l], (size_t)p.pitch[l], (size_t)p.width[l],
+                                      (size_t)p.height[l], cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}
+
+extern "C" int agt_scharr_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int16_t* h_out) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_img || !h_out || w < 1 || h < 1) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_scharr_host: bad arguments");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  agt_pyramid p;
+  int64_t bytes = layout_pyramid(&p, nullptr, w, h, 1, 1);
+  uint8_t *d, *dout;
+  int rc = agt_scratch(ctx, 0, (size_t)bytes, reinterpret_cast<void**>(&d));
+  if (rc) return rc;
+  if ((rc = agt_scratch(ctx, 1, sizeof(int16_t) * 2 * (size_t)w * h, reinterpret_cast<void**>(&dout)))) return rc;
+  layout_pyramid(&p, d, w, h, 1, 1);
+  cudaStream_t st = ctx->stream;
+  if ((rc = upload_level0(ctx, p, h_img, st))) return rc;
+  if ((rc = agt_scharr(ctx, p.data[0], w, h, p.pitch[0], p.frame_stride[0], reinterpret_cast<int16_t*>(dout), 1))) return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_out, dout, sizeof(int16_t) * 2 * (size_t)w * h, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}
+
+extern "C" int agt_lk_host(agt_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int w, int h, int levels,
+                           const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_prev || !h_next || !h_prev_pts || !h_next_pts || !h_status || !h_err || w < 1 || h < 1 || levels < 1 ||
+      levels > AGT_MAX_LEVELS || n_pts < 0)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_host: bad arguments");
+  if (n_pts == 0) return AGT_OK;
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  // cv::calcOpticalFlowPyrLK lowers maxLevel until the top level is larger than the window
+  agt_pyramid pa, pb;
+  int64_t bytes = layout_pyramid(&pa, nullptr, w, h, levels, 1);
+  uint8_t *da, *db, *dp;
+  int rc;
+  if ((rc = agt_scratch(ctx, 0, (size_t)bytes, reinterpret_cast<void**>(&da)))) return rc;
+  if ((rc = agt_scratch(ctx, 1, (size_t)bytes, reinterpret_cast<void**>(&db)))) return rc;
+  size_t o_prev = 0, o_next = align_up(sizeof(float) * 2 * n_pts, 64), o_err = o_next * 2, o_st = o_err + align_up(sizeof(float) * n_pts, 64),
+         total = o_st + align_up(n_pts, 64);
+  if ((rc = agt_scratch(ctx, 2, total, reinterpret_cast<void**>(&dp)))) return rc;
+  layout_pyramid(&pa, da, w, h, levels, 1);
+  layout_pyramid(&pb, db, w, h, levels, 1);
+  cudaStream_t st = ctx->stream;
+  if ((rc = upload_level0(ctx, pa, h_prev, st))) return rc;
+  if ((rc = upload_level0(ctx, pb, h_next, st))) return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(dp + o_prev, h_prev_pts, sizeof(float) * 2 * n_pts, cudaMemcpyHostToDevice, st));
+  if ((rc = agt_build_pyramid(ctx, &pa, 1))) return rc;
+  if ((rc = agt_build_pyramid(ctx, &pb, 1))) return rc;
+  if ((rc = agt_lk(ctx, &pa, &pb, reinterpret_cast<float*>(dp + o_prev), reinterpret_cast<float*>(dp + o_next), dp + o_st,
+                   reinterpret_cast<float*>(dp + o_err), 1, n_pts)))
+    return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_next_pts, dp + o_next, sizeof(float) * 2 * n_pts, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_status, dp + o_st, n_pts, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_err, dp + o_err, sizeof(float) * n_pts, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}
+
+extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, int batch,
+                               const double* h_init, int n_hyp, double* h_pose, float* h_cost, int32_t* h_n_valid,
+                               int32_t* h_evals, uint8_t* h_status, int32_t* h_best) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine_host: camera and surface model must be set");
+  if (!h_frames || !h_init || !h_pose || w < 1 || h < 1 || levels < 1 || levels > AGT_MAX_LEVELS || batch < 0 || n_hyp < 1)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine_host: bad arguments");
+  if (batch == 0) return AGT_OK;
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  // chunked, double-buffered: H2D of chunk i+1 on the copy stream overlaps pyramid + refinement of chunk i
+  agt_pyramid one;
+  int64_t per_frame = layout_pyramid(&one, nullptr, w, h, levels, 1);
+  int chunk = (int)((256LL << 20) / per_frame);
+  if (chunk < 1) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  int64_t chunk_bytes = layout_pyramid(&one, nullptr, w, h, levels, chunk);
+  uint8_t* buf[2];
+  int rc;
+  if ((rc = agt_scratch(ctx, 0, (size_t)chunk_bytes, reinterpret_cast<void**>(&buf[0])))) return rc;
+  if ((rc = agt_scratch(ctx, 1, (size_t)chunk_bytes, reinterpret_cast<void**>(&buf[1])))) return rc;
+  int64_t jobs = (int64_t)batch * n_hyp;
+  uint8_t* dr;
+  size_t o_init = 0, o_pose = o_init + align_up(sizeof(double) * 6 * jobs, 256), o_cost = o_pose + align_up(sizeof(double) * 6 * jobs, 256),
+         o_nv = o_cost + align_up(sizeof(float) * jobs, 256), o_ev = o_nv + align_up(sizeof(int32_t) * jobs, 256),
+         o_st = o_ev + align_up(sizeof(int32_t) * jobs, 256), o_best = o_st + align_up(jobs, 256),
+         total = o_best + align_up(sizeof(int32_t) * batch, 256);
+  if ((rc = agt_scratch(ctx, 2, total, reinterpret_cast<void**>(&dr)))) return rc;
+  cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
+  AGT_CUDA(ctx, cudaMemcpyAsync(dr + o_init, h_init, sizeof(double) * 6 * jobs, cudaMemcpyHostToDevice, st));
+  // the copy stream must not overwrite a buffer an earlier call on `st` may still read
+  AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+  AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[2], 0));
+  const bool tight = one.pitch[0] == w;
+  int n_chunks = (batch + chunk - 1) / chunk;
+  for (int c = 0; c < n_chunks; ++c) {
+    int b0 = c * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk;
+    int s = c & 1;
+    agt_pyramid p;
+    layout_pyramid(&p, buf[s], w, h, levels, chunk);
+    if (c >= 2) AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[s], 0));       // compute on this buffer finished
+    const uint8_t* src = h_frames + (int64_t)b0 * w * h;
+    if (tight) {
+      AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], src, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
+    } else {
+      AGT_CUDA(ctx, cudaMemcpy2DAsync(p.data[0], (size_t)p.pitch[0], src, (size_t)w, (size_t)w, (size_t)nb * h,
+                                      cudaMemcpyHostToDevice, cp));
+    }
+    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], cp));
+    AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
+    if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
+    int64_t j0 = (int64_t)b0 * n_hyp;
+    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp,
+                         reinterpret_cast<double*>(dr + o_pose) + j0 * 6, reinterpret_cast<float*>(dr + o_cost) + j0,
+                         reinterpret_cast<int32_t*>(dr + o_nv) + j0, reinterpret_cast<int32_t*>(dr + o_ev) + j0,
+                         dr + o_st + j0, nb)))
+      return rc;
+    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[s], st));
+  }
+  if (n_hyp > 1 && h_best) {
+    if ((rc = agt_select_best(ctx, reinterpret_cast<double*>(dr + o_pose), reinterpret_cast<float*>(dr + o_cost),
+                              reinterpret_cast<int32_t*>(dr + o_nv), n_hyp, reinterpret_cast<int32_t*>(dr + o_best), nullptr,
+                              batch)))
+      return rc;
+    AGT_CUDA(ctx, cudaMemcpyAsync(h_best, dr + o_best, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost, st));
+  }
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_pose, dr + o_pose, sizeof(double) * 6 * jobs, cudaMemcpyDeviceToHost, st));
+  if (h_cost) AGT_CUDA(ctx, cudaMemcpyAsync(h_cost, dr + o_cost, sizeof(float) * jobs, cudaMemcpyDeviceToHost, st));
+  if (h_n_valid) AGT_CUDA(ctx, cudaMemcpyAsync(h_n_valid, dr + o_nv, sizeof(int32_t) * jobs, cudaMemcpyDeviceToHost, st));
+  if (h_evals) AGT_CUDA(ctx, cudaMemcpyAsync(h_evals, dr + o_ev, sizeof(int32_t) * jobs, cudaMemcpyDeviceToHost, st));
+  if (h_status) AGT_CUDA(ctx, cudaMemcpyAsync(h_status, dr + o_st, jobs, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}

@@ -1,0 +1,411 @@
+// K4: dense pose refinement - batched photometric Levenberg-Marquardt that never
+// leaves the device.  One CTA per (frame, hypothesis).
+//
+// No reference code exists for this stage (README.md:20 names it as future work);
+// the executable specification is oracle/dpr_oracle.py:
+// visibility and pyramid level frozen at the initial pose; per sample a pinhole
+// projection, bilinear intensity and bilinear Scharr gradient of level l, residual
+// r = I - O, 1x6 Jacobian [Y x g, g] for the left perturbation R <- exp(w) R;
+// H = J^T J (21), b = J^T r (6), c = 1/2 sum r^2; LM with lambda*diag(H), accept
+// iff the cost decreases, stop rules as in the oracle.
+//
+// B200 mapping: the level-l region of interest (<= 272x272 u8, the projected
+// bounding sphere plus a drift margin) is staged ONCE per CTA into shared memory
+// with 128-bit loads and reused by every LM evaluation, so HBM sees each ROI byte
+// once per refinement; no gradient plane is materialised - the 4x4 u8 footprint of
+// a sample is fetched with two aligned 32-bit shared loads + a byte permute per
+// row and the four Scharr values come from 16 dp4a.  Samples are evaluated in
+// float32; the 28 sums are reduced by warp shuffles and across warps in float64
+// (the cost in float64 from the start); one thread runs the 6x6 Cholesky / LM
+// bookkeeping in float64.  Samples whose footprint leaves the staged tile fall
+// back to global loads, so results do not depend on the tile size.
+#include "agt_common.cuh"
+
+namespace {
+
+constexpr int DPR_THREADS = 256;
+constexpr int DPR_WARPS = DPR_THREADS / 32;
+constexpr int TILE_ROWS = 272;
+constexpr int TILE_PITCH = 288;            // 272 + 16 B alignment slack
+constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH + 16;   // +16: the unaligned fetch reads one word past its window
+constexpr int NSUM = 28;                   // 21 H + 6 b + (cost kept separately in double) + count
+constexpr double COS_VISIBLE = 0.25881904510252074;   // cos 75 deg
+constexpr double LAMBDA0 = 1e-3, LAMBDA_MIN = 1e-9, LAMBDA_MAX = 1e6;
+constexpr int MAX_EVALS = 50;
+constexpr double TOL_ROT = 1e-6, TOL_TRANS = 1e-6, REJ_TOL_ROT = 5e-5, REJ_TOL_TRANS = 5e-6;
+constexpr double BOUND_RADIUS_FACTOR = 1.30;   // bounding sphere radius / max |sample|, + drift margin below
+constexpr int DRIFT_MARGIN = 8;
+
+struct DprShared {
+  // trial pose (float32 view used by the sample loop)
+  float R[9], t[3];
+  float fx, fy, cx, cy;
+  float inv_scale;       // 2^-level
+  float gscale;          // 2^-level / 32
+  int level, lw, lh;
+  int64_t lpitch;
+  const uint8_t* limg;   // level image of this frame
+  int tx0, ty0, tw, th;  // staged tile: origin (level px), size
+  int n_active;
+  int act_begin[AGT_MAX_TAGS];   // first sample of each active tag
+  int act_prefix[AGT_MAX_TAGS + 1];
+  int stop;
+  double wsum[DPR_WARPS][NSUM + 2];
+  double tot[NSUM + 2];
+  // LM state, touched by thread 0 only (kept out of registers)
+  double Rc[9], tc[3], Hc[21], bc[6], cc, lam;
+  double Rt[9], tt[3], dstep[6];
+  int nc, evals, status;
+};
+
+__device__ __forceinline__ uint32_t ld4_unaligned_smem(const uint8_t* base, int off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (off & ~3));
+  return __byte_perm(w[0], w[1], 0x3210 + 0x1111 * (off & 3));
+}
+
+__device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
+  return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+}
+
+__device__ __forceinline__ int dp4(uint32_t px, int coef) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(coef), "r"(0));
+  return d;
+}
+
+// packed signed-byte coefficient words (little endian: byte 0 multiplies the left-most pixel)
+constexpr int C_DX0 = (int)0x000100FF;   // (-1, 0, 1, 0)
+constexpr int C_DX1 = (int)0x0100FF00;   // ( 0,-1, 0, 1)
+constexpr int C_SM0 = (int)0x00030A03;   // ( 3,10, 3, 0)
+constexpr int C_SM1 = (int)0x030A0300;   // ( 0, 3,10, 3)
+
+__global__ void __launch_bounds__(DPR_THREADS)
+dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
+           const double* __restrict__ init, int n_hyp, double* __restrict__ pose_out, float* __restrict__ cost_out,
+           int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out) {
+  extern __shared__ __align__(16) uint8_t s_tile[];
+  __shared__ DprShared S;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t job = blockIdx.x;
+  const int64_t frame = job / n_hyp;
+
+  double* const Rc = S.Rc; double* const tc = S.tc; double* const Hc = S.Hc; double* const bc = S.bc;
+  double* const Rt = S.Rt; double* const tt = S.tt; double* const dstep = S.dstep;
+
+  if (tid == 0) {
+    S.cc = 0.0; S.lam = LAMBDA0; S.nc = 0; S.evals = 0; S.status = AGT_DPR_MAX_EVALS;
+    const double* p0 = init + job * 6;
+    double r0[3] = {p0[0], p0[1], p0[2]};
+    agt_rodrigues(r0, Rc);
+    tc[0] = p0[3]; tc[1] = p0[4]; tc[2] = p0[5];
+    // level
+    double q = cam.fx * model.pitch / tc[2];
+    int lvl = q < 2.0 ? 0 : (q < 4.0 ? 1 : (q < 8.0 ? 2 : 3));
+    if (!(tc[2] > 0.0)) lvl = 0;
+    if (lvl > pyr.levels - 1) lvl = pyr.levels - 1;
+    S.level = lvl;
+    S.lw = pyr.width[lvl]; S.lh = pyr.height[lvl]; S.lpitch = pyr.pitch[lvl];
+    S.limg = pyr.data[lvl] + frame * pyr.frame_stride[lvl];
+    double sc = 1.0 / (double)(1 << lvl);
+    S.inv_scale = (float)sc;
+    S.gscale = (float)(sc / 32.0);
+    S.fx = (float)cam.fx; S.fy = (float)cam.fy; S.cx = (float)cam.cx; S.cy = (float)cam.cy;
+    // active tags
+    int na = 0, pre = 0;
+    double rmax2 = 0.0;
+    for (int k = 0; k < model.n_tags; ++k) {
+      double c[3], n[3];
+      for (int i = 0; i < 3; ++i) {
+        c[i] = Rc[i * 3] * model.centres[k][0] + Rc[i * 3 + 1] * model.centres[k][1] + Rc[i * 3 + 2] * model.centres[k][2] + tc[i];
+        n[i] = Rc[i * 3] * model.normals[k][0] + Rc[i * 3 + 1] * model.normals[k][1] + Rc[i * 3 + 2] * model.normals[k][2];
+      }
+      double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+      double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
+      double m2 = model.centres[k][0] * model.centres[k][0] + model.centres[k][1] * model.centres[k][1] +
+                  model.centres[k][2] * model.centres[k][2];
+      rmax2 = fmax(rmax2, m2);
+      if (d > COS_VISIBLE) {
+        S.act_begin[na] = model.tag_begin[k];
+        S.act_prefix[na] = pre;
+        pre += model.tag_begin[k + 1] - model.tag_begin[k];
+        ++na;
+      }
+    }
+    S.act_prefix[na] = pre;
+    S.n_active = na;
+    // staged tile: projected bounding sphere (+ margin), clipped to the level and to the tile capacity
+    double rad_m = sqrt(rmax2) * BOUND_RADIUS_FACTOR;
+    double zc = tc[2] > 1e-6 ? tc[2] : 1e-6;
+    double uc = (cam.fx * tc[0] / zc + cam.cx) * sc, vc = (cam.fy * tc[1] / zc + cam.cy) * sc;
+    double zr = zc - rad_m > 0.05 * zc ? zc - rad_m : 0.05 * zc;
+    double rad_px = fmax(cam.fx, cam.fy) * rad_m / zr * sc + DRIFT_MARGIN + 2;
+    double fx0 = floor(uc - rad_px), fy0 = floor(vc - rad_px);
+    fx0 = fmin(fmax(fx0, -1e6), 1e6); fy0 = fmin(fmax(fy0, -1e6), 1e6);
+    int x0 = (int)fx0, y0 = (int)fy0;
+    int x1 = (int)fmin(ceil(uc + rad_px) + 1, 1e6), y1 = (int)fmin(ceil(vc + rad_px) + 1, 1e6);
+    x0 = max(x0, 0) & ~15; y0 = max(y0, 0);
+    x1 = min(x1, S.lw); y1 = min(y1, S.lh);
+    int tw = x1 - x0, th = y1 - y0;
+    if (tw > TILE_PITCH) { int cut = (tw - TILE_PITCH + 31) / 32 * 16; x0 += cut; tw = min(TILE_PITCH, S.lw - x0); }
+    if (th > TILE_ROWS) { y0 += (th - TILE_ROWS) / 2; th = TILE_ROWS; }
+    if (tw < 0) tw = 0;
+    if (th < 0) th = 0;
+    S.tx0 = x0; S.ty0 = y0; S.tw = tw; S.th = th;
+    for (int i = 0; i < 9; ++i) S.R[i] = (float)Rc[i];
+    for (int i = 0; i < 3; ++i) S.t[i] = (float)tc[i];
+    S.stop = 0;
+  }
+  __syncthreads();
+
+  // ---- stage the ROI tile (128-bit loads; the level rows are 16 B aligned) ----------
+  {
+    const int tw = S.tw, th = S.th;
+    const uint8_t* src = S.limg + (int64_t)S.ty0 * S.lpitch + S.tx0;
+    const bool vec = ((S.lpitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(S.limg) & 15) == 0);
+    const int chunks = (tw + 15) >> 4;
+    for (int i = tid; i < th * chunks; i += DPR_THREADS) {
+      int r = i / chunks, c = i - r * chunks;
+      const uint8_t* g = src + (int64_t)r * S.lpitch + 16 * c;
+      uint4 v;
+      if (vec && S.tx0 + 16 * c + 16 <= (int)S.lpitch) {
+        v = __ldg(reinterpret_cast<const uint4*>(g));
+      } else {
+        uint32_t w4[4] = {0, 0, 0, 0};
+        for (int b = 0; b < 16; ++b)
+          if (S.tx0 + 16 * c + b < S.lw) w4[b >> 2] |= (uint32_t)__ldg(g + b) << (8 * (b & 3));
+        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      *reinterpret_cast<uint4*>(s_tile + r * TILE_PITCH + 16 * c) = v;
+    }
+  }
+  __syncthreads();
+
+  const int n_act_samples = S.act_prefix[S.n_active];
+  const float fx = S.fx, fy = S.fy, cx = S.cx, cy = S.cy, isc = S.inv_scale, gsc = S.gscale;
+  const int lw = S.lw, lh = S.lh, tx0 = S.tx0, ty0 = S.ty0, tw = S.tw, th = S.th;
+  const int64_t lpitch = S.lpitch;
+  const uint8_t* limg = S.limg;
+
+  while (true) {
+    // ================= evaluate cost + normal equations at the trial pose =================
+    const float R0 = S.R[0], R1 = S.R[1], R2 = S.R[2], R3 = S.R[3], R4 = S.R[4], R5 = S.R[5], R6 = S.R[6], R7 = S.R[7],
+                R8 = S.R[8], t0 = S.t[0], t1 = S.t[1], t2 = S.t[2];
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    double cost = 0.0;
+    int cnt = 0;
+    int seg = 0;
+    for (int j = tid; j < n_act_samples; j += DPR_THREADS) {
+      while (j >= S.act_prefix[seg + 1]) ++seg;
+      const float4 sm = __ldg(&samples[S.act_begin[seg] + (j - S.act_prefix[seg])]);
+      const float Yx = R0 * sm.x + R1 * sm.y + R2 * sm.z;
+      const float Yy = R3 * sm.x + R4 * sm.y + R5 * sm.z;
+      const float Yz = R6 * sm.x + R7 * sm.y + R8 * sm.z;
+      const float X = Yx + t0, Y = Yy + t1, Z = Yz + t2;
+      if (!(Z > 1e-6f)) continue;
+      const float iz = 1.f / Z;
+      const float ul = (fx * X * iz + cx) * isc, vl = (fy * Y * iz + cy) * isc;
+      const float fxl = floorf(ul), fyl = floorf(vl);
+      if (!(fxl >= 1.f && fxl <= (float)(lw - 3) && fyl >= 1.f && fyl <= (float)(lh - 3))) continue;
+      const int x0 = (int)fxl, y0 = (int)fyl;
+      const float a = ul - fxl, b = vl - fyl;
+      // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
+      uint32_t row[4];
+      const int lx = x0 - 1 - tx0, ly = y0 - 1 - ty0;
+      if (lx >= 0 && ly >= 0 && lx + 4 <= tw && ly + 4 <= th) {
+        const int off = ly * TILE_PITCH + lx;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[r] = ld4_unaligned_smem(s_tile, off + r * TILE_PITCH);
+      } else {
+        const uint8_t* g = limg + (int64_t)(y0 - 1) * lpitch + (x0 - 1);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) row[r] = ld4_global(g + r * lpitch);
+      }
+      int dx0[4], dx1[4], s0[4], s1[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        dx0[r] = dp4(row[r], C_DX0); dx1[r] = dp4(row[r], C_DX1);
+        s0[r] = dp4(row[r], C_SM0);  s1[r] = dp4(row[r], C_SM1);
+      }
+      // Scharr at (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1)
+      const float gx00 = (float)(3 * (dx0[0] + dx0[2]) + 10 * dx0[1]), gx01 = (float)(3 * (dx1[0] + dx1[2]) + 10 * dx1[1]);
+      const float gx10 = (float)(3 * (dx0[1] + dx0[3]) + 10 * dx0[2]), gx11 = (float)(3 * (dx1[1] + dx1[3]) + 10 * dx1[2]);
+      const float gy00 = (float)(s0[2] - s0[0]), gy01 = (float)(s1[2] - s1[0]);
+      const float gy10 = (float)(s0[3] - s0[1]), gy11 = (float)(s1[3] - s1[1]);
+      const float i00 = (float)((row[1] >> 8) & 0xff), i01 = (float)((row[1] >> 16) & 0xff);
+      const float i10 = (float)((row[2] >> 8) & 0xff), i11 = (float)((row[2] >> 16) & 0xff);
+      const float w11 = a * b, w01 = a - w11, w10 = b - w11, w00 = 1.f - a - b + w11;
+      const float I = w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11;
+      const float Gx = (w00 * gx00 + w01 * gx01 + w10 * gx10 + w11 * gx11) * gsc;
+      const float Gy = (w00 * gy00 + w01 * gy01 + w10 * gy10 + w11 * gy11) * gsc;
+      const float r = I - sm.w;
+      const float g0 = Gx * fx * iz, g1 = Gy * fy * iz;
+      const float g2 = -(g0 * X + g1 * Y) * iz;
+      float J[6];
+      J[0] = Yy * g2 - Yz * g1;
+      J[1] = Yz * g0 - Yx * g2;
+      J[2] = Yx * g1 - Yy * g0;
+      J[3] = g0; J[4] = g1; J[5] = g2;
+      int k = 0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = p; q < 6; ++q) acc[k++] += J[p] * J[q];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc[21 + p] += J[p] * r;
+      cost += (double)r * (double)r;
+      ++cnt;
+    }
+    // ---- reduce: shuffles within the warp, float64 across warps ------------------------
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = agt_warp_sum(acc[k]);
+    cost = agt_warp_sum(cost);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 27; ++k) S.wsum[wid][k] = (double)acc[k];
+      S.wsum[wid][27] = cost;
+      S.wsum[wid][28] = (double)cnt;
+    }
+    __syncthreads();
+    if (tid < 29) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < DPR_WARPS; ++w) s += S.wsum[w][tid];
+      S.tot[tid] = s;
+    }
+    __syncthreads();
+
+    // ================= LM bookkeeping (one thread, float64) ================================
+    if (tid == 0) {
+      double Hn[21], bn[6];
+      for (int k = 0; k < 21; ++k) Hn[k] = S.tot[k];
+      for (int k = 0; k < 6; ++k) bn[k] = S.tot[21 + k];
+      double cn = 0.5 * S.tot[27];
+      int nn = (int)S.tot[28];
+      double cc = S.cc, lam = S.lam;
+      int nc = S.nc, evals = S.evals + 1, status = S.status;
+      bool need_step = false;
+      if (evals == 1) {
+        for (int k = 0; k < 21; ++k) Hc[k] = Hn[k];
+        for (int k = 0; k < 6; ++k) bc[k] = bn[k];
+        cc = cn; nc = nn;
+        if (nn == 0) status = AGT_DPR_NONE; else need_step = true;
+      } else {
+        double nw = sqrt(dstep[0] * dstep[0] + dstep[1] * dstep[1] + dstep[2] * dstep[2]);
+        double nt = sqrt(dstep[3] * dstep[3] + dstep[4] * dstep[4] + dstep[5] * dstep[5]);
+        if (nn > 0 && cn < cc) {
+          for (int k = 0; k < 9; ++k) Rc[k] = Rt[k];
+          for (int k = 0; k < 3; ++k) tc[k] = tt[k];
+          for (int k = 0; k < 21; ++k) Hc[k] = Hn[k];
+          for (int k = 0; k < 6; ++k) bc[k] = bn[k];
+          cc = cn; nc = nn;
+          lam = fmax(lam / 10.0, LAMBDA_MIN);
+          if (nw < TOL_ROT && nt < TOL_TRANS) status = AGT_DPR_CONVERGED; else need_step = true;
+        } else {
+          lam *= 10.0;
+          if (nw < REJ_TOL_ROT && nt < REJ_TOL_TRANS) status = AGT_DPR_CONVERGED;
+          else if (lam > LAMBDA_MAX) status = AGT_DPR_LAMBDA;
+          else need_step = true;
+        }
+      }
+      if (need_step && evals >= MAX_EVALS) need_step = false;     // status stays MAX_EVALS
+      while (need_step) {
+        double A[36], d[6];
+        int k = 0;
+        for (int p = 0; p < 6; ++p)
+          for (int q = p; q < 6; ++q) { A[p * 6 + q] = Hc[k]; A[q * 6 + p] = Hc[k]; ++k; }
+        for (int p = 0; p < 6; ++p) { A[p * 6 + p] += lam * A[p * 6 + p]; d[p] = -bc[p]; }
+        if (agt_chol6_solve(A, d)) {
+          for (int p = 0; p < 6; ++p) dstep[p] = d[p];
+          double E[9];
+          agt_rodrigues(d, E);
+          for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
+          for (int p = 0; p < 3; ++p) tt[p] = tc[p] + d[3 + p];
+          for (int p = 0; p < 9; ++p) S.R[p] = (float)Rt[p];
+          for (int p = 0; p < 3; ++p) S.t[p] = (float)tt[p];
+          break;
+        }
+        lam *= 10.0;
+        if (lam > LAMBDA_MAX) { status = AGT_DPR_LAMBDA; need_step = false; }
+      }
+      S.stop = need_step ? 0 : 1;
+      S.cc = cc; S.lam = lam; S.nc = nc; S.evals = evals; S.status = status;
+    }
+    __syncthreads();
+    if (S.stop) break;
+  }
+
+  if (tid == 0) {
+    double rv[3];
+    agt_log_rotation(Rc, rv);
+    double* po = pose_out + job * 6;
+    po[0] = rv[0]; po[1] = rv[1]; po[2] = rv[2]; po[3] = tc[0]; po[4] = tc[1]; po[5] = tc[2];
+    if (cost_out) cost_out[job] = (float)S.cc;
+    if (nvalid_out) nvalid_out[job] = S.nc;
+    if (evals_out) evals_out[job] = S.evals;
+    if (status_out) status_out[job] = (uint8_t)S.status;
+  }
+}
+
+__global__ void select_best_kernel(const double* __restrict__ pose, const float* __restrict__ cost,
+                                   const int32_t* __restrict__ nvalid, int n_hyp, int32_t* __restrict__ best,
+                                   double* __restrict__ best_pose, int batch) {
+  // one warp per frame: argmin of 2c/n, ties -> lowest index
+  int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (f >= batch) return;
+  double bs = INFINITY;
+  int bi = 0x7fffffff;
+  for (int h = lane; h < n_hyp; h += 32) {
+    int n = nvalid[(int64_t)f * n_hyp + h];
+    double s = n > 0 ? 2.0 * (double)cost[(int64_t)f * n_hyp + h] / (double)n : INFINITY;
+    if (s < bs || (s == bs && h < bi)) { bs = s; bi = h; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double os = __shfl_xor_sync(0xffffffffu, bs, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+  }
+  if (bi == 0x7fffffff) bi = 0;
+  if (lane == 0) best[f] = bi;
+  if (best_pose && lane < 6) best_pose[(int64_t)f * 6 + lane] = pose[((int64_t)f * n_hyp + bi) * 6 + lane];
+}
+
+}  // namespace
+
+extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, double* d_pose,
+                          float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine: camera and surface model must be set");
+  if (!pyr || !d_init || !d_pose || n_hyp < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad arguments");
+  if (pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad pyramid descriptor");
+  if (ctx->cam.has_dist) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: lens distortion is not supported; undistort the frame first (detect_pose.py:611-619)");
+  int64_t jobs = (int64_t)batch * n_hyp;
+  if (jobs == 0) return AGT_OK;
+  if (jobs > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: batch*n_hyp too large");
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    attr_set[ctx->device & 63] = true;
+  }
+  dpr_kernel<<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
+                                                                      n_hyp, d_pose, d_cost, d_n_valid, d_evals, d_status);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,
+                               int n_hyp, int32_t* d_best, double* d_best_pose, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_pose || !d_cost || !d_n_valid || !d_best || n_hyp < 1 || batch < 0)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_select_best: bad arguments");
+  if (batch == 0) return AGT_OK;
+  int threads = 128;
+  int blocks = (int)(((int64_t)batch * 32 + threads - 1) / threads);
+  select_best_kernel<<<blocks, threads, 0, ctx->stream>>>(d_pose, d_cost, d_n_valid, n_hyp, d_best, d_best_pose, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}

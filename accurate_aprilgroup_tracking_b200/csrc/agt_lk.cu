@@ -1,0 +1,255 @@
+// K2: pyramidal Lucas-Kanade corner tracking, one warp per tracked corner.
+//
+// The reference snapshot has no optical-flow code; the frozen semantics are
+// cv::calcOpticalFlowPyrLK(prev, next, prevPts, None) with its defaults
+// (restated in oracle/lk_oracle.py:lk_np): 21x21
+// window, fixed-point bilinear weights (W_BITS 14), int16 template (x32) and
+// int16 interpolated Scharr derivatives, float 2x2 structure tensor with the
+// minEig 1e-4 gate, <= 30 iterations, |delta|^2 <= 1e-4 stop and the
+// oscillation rule.  Outside the image the intensity is BORDER_REFLECT_101 and
+// the derivative is zero, exactly as OpenCV's padded pyramids behave.
+//
+// Per corner and level the warp stages the 24x24 u8 template footprint in shared
+// memory, derives the 22x22 Scharr values from it (no gradient plane is ever
+// materialised in HBM), builds the 21x21 template, reduces the structure tensor
+// with warp shuffles, then iterates against a 32x32 u8 search region staged
+// from the next image (re-staged only if the window drifts out of it).  All sums
+// are exact integers; they are rounded to float once, where OpenCV accumulates
+// in float, so results agree with OpenCV to ~1e-3 px (tolerance 0.01 px).
+#include "agt_common.cuh"
+
+namespace {
+
+constexpr int WIN = 21;
+constexpr int NPIX = WIN * WIN;            // 441
+constexpr int PATCH = WIN + 3;             // 24: template footprint incl. bilinear + Scharr halo
+constexpr int DER = WIN + 1;               // 22
+constexpr int REG = 32;                    // staged search region
+constexpr int REG_MARGIN = 5;              // window offset inside a freshly staged region
+constexpr int WARPS_PER_CTA = 4;
+constexpr int W_BITS = 14;
+constexpr int MAX_ITERS = 30;
+
+struct WarpSmem {
+  union {
+    struct {
+      uint8_t patch[PATCH][PATCH];         // prev level, origin (ix-1, iy-1)
+      short2 der[DER][DER];                // Scharr at (ix..ix+21, iy..iy+21)
+    } t;
+    uint8_t region[REG][REG];              // next level search region
+  } u;
+  short tmpl[NPIX + 7];                    // template intensity * 32
+  short2 dtmpl[NPIX + 3];                  // template derivative
+};
+
+struct Weights { int w00, w01, w10, w11; };
+
+__device__ __forceinline__ Weights make_weights(float a, float b) {
+  Weights w;
+  float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
+  w.w00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), 16384.f));
+  w.w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), 16384.f));
+  w.w10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), 16384.f));
+  w.w11 = (1 << W_BITS) - w.w00 - w.w01 - w.w10;
+  return w;
+}
+
+__device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8_t* __restrict__ img, int cols, int rows,
+                                             int64_t pitch, int rx0, int ry0, int lane) {
+  int gx = agt_reflect101(rx0 + lane, cols);
+#pragma unroll 4
+  for (int r = 0; r < REG; ++r) {
+    int gy = agt_reflect101(ry0 + r, rows);
+    region[r][lane] = __ldg(img + (int64_t)gy * pitch + gx);
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total) {
+  __shared__ WarpSmem smem[WARPS_PER_CTA];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int64_t gid = (int64_t)blockIdx.x * WARPS_PER_CTA + wid;
+  if (gid >= total) return;
+  WarpSmem& S = smem[wid];
+  const int frame = (int)(gid / n_pts);
+  const float ptx = prev_pts[gid * 2], pty = prev_pts[gid * 2 + 1];
+
+  float outx = 0.f, outy = 0.f;
+  int status = 1;
+  float err = 0.f;
+  const int top = prev.levels - 1;
+
+  for (int level = top; level >= 0; --level) {
+    const int cols = prev.width[level], rows = prev.height[level];
+    const uint8_t* imgI = prev.data[level] + (int64_t)frame * prev.frame_stride[level];
+    const uint8_t* imgJ = next.data[level] + (int64_t)frame * next.frame_stride[level];
+    const int64_t pitchI = prev.pitch[level], pitchJ = next.pitch[level];
+    const float sc = (float)(1.0 / (double)(1 << level));
+    float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
+    float nx, ny;
+    if (level == top) { nx = px; ny = py; } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
+    outx = nx; outy = ny;
+    px = __fsub_rn(px, 10.f); py = __fsub_rn(py, 10.f);
+    const int ix = (int)floorf(px), iy = (int)floorf(py);
+    // also rejects NaN / huge coordinates (the float->int conversion saturates)
+    if (!(px == px) || !(py == py) || ix < -WIN || ix >= cols || iy < -WIN || iy >= rows) {
+      if (level == 0) { status = 0; err = 0.f; }
+      continue;
+    }
+    __syncwarp();
+    // ---- stage the 24x24 template footprint (reflect-101 intensity) -------------
+    for (int i = lane; i < PATCH * PATCH; i += 32) {
+      int r = i / PATCH, c = i - r * PATCH;
+      int gy = agt_reflect101(iy - 1 + r, rows), gx = agt_reflect101(ix - 1 + c, cols);
+      S.u.t.patch[r][c] = __ldg(imgI + (int64_t)gy * pitchI + gx);
+    }
+    __syncwarp();
+    // ---- Scharr at the 22x22 integer positions; zero outside the image -------------
+    for (int i = lane; i < DER * DER; i += 32) {
+      int r = i / DER, c = i - r * DER;
+      int gx = ix + c, gy = iy + r;
+      short2 d = make_short2(0, 0);
+      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+        const uint8_t(*p)[PATCH] = S.u.t.patch;
+        int a00 = p[r][c], a01 = p[r][c + 1], a02 = p[r][c + 2];
+        int a10 = p[r + 1][c], a12 = p[r + 1][c + 2];
+        int a20 = p[r + 2][c], a21 = p[r + 2][c + 1], a22 = p[r + 2][c + 2];
+        d.x = (short)(3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+        d.y = (short)(3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+      }
+      S.u.t.der[r][c] = d;
+    }
+    __syncwarp();
+    // ---- template + structure tensor ------------------------------------------
+    Weights w = make_weights(__fsub_rn(px, (float)ix), __fsub_rn(py, (float)iy));
+    int s11 = 0, s12 = 0, s22 = 0;
+    for (int i = lane; i < NPIX; i += 32) {
+      int y = i / WIN, x = i - y * WIN;
+      const uint8_t(*p)[PATCH] = S.u.t.patch;
+      int iv = descale(p[y + 1][x + 1] * w.w00 + p[y + 1][x + 2] * w.w01 + p[y + 2][x + 1] * w.w10 + p[y + 2][x + 2] * w.w11,
+                       W_BITS - 5);
+      short2 d00 = S.u.t.der[y][x], d01 = S.u.t.der[y][x + 1], d10 = S.u.t.der[y + 1][x], d11 = S.u.t.der[y + 1][x + 1];
+      int dxv = descale(d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11, W_BITS);
+      int dyv = descale(d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11, W_BITS);
+      S.tmpl[i] = (short)iv;
+      S.dtmpl[i] = make_short2((short)dxv, (short)dyv);
+      s11 += dxv * dxv; s12 += dxv * dyv; s22 += dyv * dyv;
+    }
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    float A11 = __fmul_rn((float)agt_warp_sum((long long)s11), FLT_SCALE);
+    float A12 = __fmul_rn((float)agt_warp_sum((long long)s12), FLT_SCALE);
+    float A22 = __fmul_rn((float)agt_warp_sum((long long)s22), FLT_SCALE);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    float dif = __fsub_rn(A11, A22);
+    float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WIN * WIN));
+    if ((double)minEig < 1e-4 || D < 1.1920928955078125e-7f) {
+      if (level == 0) status = 0;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+    __syncwarp();      // template footprint no longer needed: the region buffer may overwrite it
+
+    nx = __fsub_rn(nx, 10.f); ny = __fsub_rn(ny, 10.f);
+    float pdx = 0.f, pdy = 0.f;
+    int rx0 = 0, ry0 = 0;
+    bool staged = false;
+    for (int j = 0; j < MAX_ITERS; ++j) {
+      int jx = (int)floorf(nx), jy = (int)floorf(ny);
+      if (!(nx == nx) || !(ny == ny) || jx < -WIN || jx >= cols || jy < -WIN || jy >= rows) {
+        if (level == 0) status = 0;
+        break;
+      }
+      if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
+        __syncwarp();
+        rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+        stage_region(S.u.region, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+        staged = true;
+        __syncwarp();
+      }
+      Weights wj = make_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
+      const int ox = jx - rx0, oy = jy - ry0;
+      int sb1 = 0, sb2 = 0;
+      for (int i = lane; i < NPIX; i += 32) {
+        int y = i / WIN, x = i - y * WIN;
+        const uint8_t* r0 = &S.u.region[oy + y][ox + x];
+        int jv = descale(r0[0] * wj.w00 + r0[1] * wj.w01 + r0[REG] * wj.w10 + r0[REG + 1] * wj.w11, W_BITS - 5);
+        int diff = jv - S.tmpl[i];
+        short2 d = S.dtmpl[i];
+        sb1 += diff * d.x; sb2 += diff * d.y;
+      }
+      float b1 = __fmul_rn((float)agt_warp_sum((long long)sb1), FLT_SCALE);
+      float b2 = __fmul_rn((float)agt_warp_sum((long long)sb2), FLT_SCALE);
+      float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+      outx = __fadd_rn(nx, 10.f); outy = __fadd_rn(ny, 10.f);
+      if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+      if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+        outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
+        outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+        break;
+      }
+      pdx = dx; pdy = dy;
+    }
+
+    if (status && level == 0) {
+      float ex = __fsub_rn(outx, 10.f), ey = __fsub_rn(outy, 10.f);
+      int jx = (int)floorf(ex), jy = (int)floorf(ey);
+      if (!(ex == ex) || !(ey == ey) || jx < -WIN || jx >= cols || jy < -WIN || jy >= rows) {
+        status = 0;
+      } else {
+        if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
+          __syncwarp();
+          rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+          stage_region(S.u.region, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+          __syncwarp();
+        }
+        Weights wj = make_weights(__fsub_rn(ex, (float)jx), __fsub_rn(ey, (float)jy));
+        const int ox = jx - rx0, oy = jy - ry0;
+        int sabs = 0;
+        for (int i = lane; i < NPIX; i += 32) {
+          int y = i / WIN, x = i - y * WIN;
+          const uint8_t* r0 = &S.u.region[oy + y][ox + x];
+          int jv = descale(r0[0] * wj.w00 + r0[1] * wj.w01 + r0[REG] * wj.w10 + r0[REG + 1] * wj.w11, W_BITS - 5);
+          int diff = jv - S.tmpl[i];
+          sabs += diff < 0 ? -diff : diff;
+        }
+        err = __fmul_rn((float)agt_warp_sum((long long)sabs), 1.f / (float)(32 * WIN * WIN));
+      }
+    }
+  }
+  if (lane == 0) {
+    next_pts[gid * 2] = outx;
+    next_pts[gid * 2 + 1] = outy;
+    status_out[gid] = (uint8_t)status;
+    err_out[gid] = status ? err : 0.f;
+  }
+}
+
+}  // namespace
+
+extern "C" int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
+                      float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!prev || !next || batch < 0 || n_pts < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null pyramid or negative size");
+  if ((int64_t)batch * n_pts > 0 && (!d_prev_pts || !d_next_pts || !d_status || !d_err))
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null point / status / err buffer");
+  if (prev->levels < 1 || prev->levels > AGT_MAX_LEVELS || prev->levels != next->levels)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: pyramids must have the same 1..%d levels", AGT_MAX_LEVELS);
+  for (int l = 0; l < prev->levels; ++l)
+    if (prev->width[l] != next->width[l] || prev->height[l] != next->height[l])
+      AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: prev/next level %d sizes differ", l);
+  int64_t total = (int64_t)batch * n_pts;
+  if (total == 0) return AGT_OK;
+  int64_t blocks = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: batch too large");
+  lk_kernel<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status,
+                                                                       d_err, n_pts, total);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}

@@ -1,0 +1,454 @@
+// K3: batched PnP, one warp per frame (stands in for cv::solvePnP
+// SOLVEPNP_ITERATIVE at detect_pose.py:509-526 and for the reprojection gate of
+// transform_helper.py:98-121).
+//
+// Minimises sum_i |pi(K, dist, R(r) X_i + t) - u_i|^2 over (r,t) with
+// Levenberg-Marquardt in float64: analytic Rodrigues derivative, 27 normal-
+// equation sums reduced with warp shuffles, 6x6 Cholesky solve on the device.
+// Frames without an extrinsic guess start from a normalised DLT (smallest
+// eigenvector of the 12x12 A^T A by inverse iteration, then polar
+// orthonormalisation), the same initialisation family OpenCV uses for
+// non-planar point sets.  OpenCV lands on the least-squares minimiser (SURVEY.md
+// section 6: <1e-9 rad from scipy), so parity is "converge to the minimiser".
+// The epilogue reproduces the reference's mean L2 reprojection error in float32.
+#include "agt_common.cuh"
+
+namespace {
+
+constexpr int PNP_WARPS = 4;
+constexpr int PNP_MAX_ITERS = 60;
+
+struct Proj {
+  double u, v;          // projected pixel
+  double j[2][3];       // d(u,v)/d(Xc)
+  bool ok;
+};
+
+__device__ __forceinline__ Proj project_point(const agt_camera& cam, double X, double Y, double Z) {
+  Proj p;
+  p.ok = Z > 1e-9;
+  double iz = p.ok ? 1.0 / Z : 1.0;
+  double x = X * iz, y = Y * iz;
+  double dxx = 1.0, dxy = 0.0, dyx = 0.0, dyy = 1.0, xd = x, yd = y;
+  if (cam.has_dist) {
+    double r2 = x * x + y * y;
+    double rad = 1.0 + r2 * (cam.k1 + r2 * (cam.k2 + r2 * cam.k3));
+    double drad = cam.k1 + r2 * (2.0 * cam.k2 + r2 * 3.0 * cam.k3);   // d rad / d r2
+    xd = x * rad + 2.0 * cam.p1 * x * y + cam.p2 * (r2 + 2.0 * x * x);
+    yd = y * rad + cam.p1 * (r2 + 2.0 * y * y) + 2.0 * cam.p2 * x * y;
+    dxx = rad + x * drad * 2.0 * x + 2.0 * cam.p1 * y + cam.p2 * 6.0 * x;
+    dxy = x * drad * 2.0 * y + 2.0 * cam.p1 * x + cam.p2 * 2.0 * y;
+    dyx = y * drad * 2.0 * x + cam.p1 * 2.0 * x + 2.0 * cam.p2 * y;
+    dyy = rad + y * drad * 2.0 * y + cam.p1 * 6.0 * y + 2.0 * cam.p2 * x;
+  }
+  p.u = cam.fx * xd + cam.cx;
+  p.v = cam.fy * yd + cam.cy;
+  // d(x,y)/d(X,Y,Z) = [[iz,0,-x iz],[0,iz,-y iz]]
+  p.j[0][0] = cam.fx * dxx * iz; p.j[0][1] = cam.fx * dxy * iz; p.j[0][2] = -cam.fx * (dxx * x + dxy * y) * iz;
+  p.j[1][0] = cam.fy * dyx * iz; p.j[1][1] = cam.fy * dyy * iz; p.j[1][2] = -cam.fy * (dyx * x + dyy * y) * iz;
+  return p;
+}
+
+// dR/dr_i for i=0..2 (row-major 3x3 each): (r_i [r]x + [r x (I-R) e_i]x) R / theta^2
+__device__ inline void rodrigues_jacobian(const double r[3], const double R[9], double dR[3][9]) {
+  double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  for (int i = 0; i < 3; ++i) {
+    double a[3];
+    if (th2 < 1e-20) {
+      a[0] = i == 0; a[1] = i == 1; a[2] = i == 2;          // dR/dr_i = [e_i]x
+      double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+      for (int k = 0; k < 9; ++k) dR[i][k] = K[k];
+      continue;
+    }
+    // v = (I - R) e_i
+    double v[3] = {(i == 0) - R[0 + i], (i == 1) - R[3 + i], (i == 2) - R[6 + i]};
+    double c[3] = {r[1] * v[2] - r[2] * v[1], r[2] * v[0] - r[0] * v[2], r[0] * v[1] - r[1] * v[0]};
+    a[0] = (r[i] * r[0] + c[0]) / th2; a[1] = (r[i] * r[1] + c[1]) / th2; a[2] = (r[i] * r[2] + c[2]) / th2;
+    double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    for (int rr = 0; rr < 3; ++rr)
+      for (int cc = 0; cc < 3; ++cc)
+        dR[i][rr * 3 + cc] = K[rr * 3 + 0] * R[0 + cc] + K[rr * 3 + 1] * R[3 + cc] + K[rr * 3 + 2] * R[6 + cc];
+  }
+}
+
+struct Normal {
+  double H[21];
+  double g[6];
+  double c;
+};
+
+// Evaluate cost and normal equations at pose p for this lane's (<= 2) points and reduce over the warp.
+__device__ inline void evaluate(const agt_camera& cam, const double p[6], const double X[2][3], const double U[2][2],
+                                const bool have[2], Normal& out, bool& all_in_front) {
+  double R[9], dR[3][9];
+  agt_rodrigues(p, R);
+  rodrigues_jacobian(p, R, dR);
+  double acc[28];
+#pragma unroll
+  for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+  bool front = true;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!have[s]) continue;
+    const double* x = X[s];
+    double Xc = R[0] * x[0] + R[1] * x[1] + R[2] * x[2] + p[3];
+    double Yc = R[3] * x[0] + R[4] * x[1] + R[5] * x[2] + p[4];
+    double Zc = R[6] * x[0] + R[7] * x[1] + R[8] * x[2] + p[5];
+    Proj pr = project_point(cam, Xc, Yc, Zc);
+    front = front && pr.ok;
+    double e[2] = {pr.u - U[s][0], pr.v - U[s][1]};
+    double J[2][6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double d0 = dR[i][0] * x[0] + dR[i][1] * x[1] + dR[i][2] * x[2];
+      double d1 = dR[i][3] * x[0] + dR[i][4] * x[1] + dR[i][5] * x[2];
+      double d2 = dR[i][6] * x[0] + dR[i][7] * x[1] + dR[i][8] * x[2];
+      J[0][i] = pr.j[0][0] * d0 + pr.j[0][1] * d1 + pr.j[0][2] * d2;
+      J[1][i] = pr.j[1][0] * d0 + pr.j[1][1] * d1 + pr.j[1][2] * d2;
+      J[0][3 + i] = pr.j[0][i];
+      J[1][3 + i] = pr.j[1][i];
+    }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[k++] += J[0][a] * J[0][b] + J[1][a] * J[1][b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * e[0] + J[1][a] * e[1];
+    acc[27] += e[0] * e[0] + e[1] * e[1];
+  }
+#pragma unroll
+  for (int k = 0; k < 28; ++k) acc[k] = agt_warp_sum(acc[k]);
+#pragma unroll
+  for (int k = 0; k < 21; ++k) out.H[k] = acc[k];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) out.g[k] = acc[21 + k];
+  out.c = acc[27];
+  all_in_front = __all_sync(0xffffffffu, front);
+}
+
+// Smallest eigenvector of the symmetric 12x12 matrix M (PSD) by inverse iteration
+// on M + eps I (Cholesky).  Executed redundantly by every lane.
+__device__ inline bool smallest_eigvec12(double* M, double* v) {
+  double tr = 0.0;
+  for (int i = 0; i < 12; ++i) tr += M[i * 12 + i];
+  double eps = 1e-13 * tr + 1e-300;
+  for (int i = 0; i < 12; ++i) M[i * 12 + i] += eps;
+  for (int j = 0; j < 12; ++j) {
+    double d = M[j * 12 + j];
+    for (int k = 0; k < j; ++k) d -= M[j * 12 + k] * M[j * 12 + k];
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    M[j * 12 + j] = d;
+    for (int i = j + 1; i < 12; ++i) {
+      double s = M[i * 12 + j];
+      for (int k = 0; k < j; ++k) s -= M[i * 12 + k] * M[j * 12 + k];
+      M[i * 12 + j] = s / d;
+    }
+  }
+  for (int i = 0; i < 12; ++i) v[i] = 1.0 / sqrt(12.0) * ((i * 7 + 3) % 5 + 1);   // generic start vector
+  for (int it = 0; it < 12; ++it) {
+    for (int i = 0; i < 12; ++i) {
+      double s = v[i];
+      for (int k = 0; k < i; ++k) s -= M[i * 12 + k] * v[k];
+      v[i] = s / M[i * 12 + i];
+    }
+    for (int i = 11; i >= 0; --i) {
+      double s = v[i];
+      for (int k = i + 1; k < 12; ++k) s -= M[k * 12 + i] * v[k];
+      v[i] = s / M[i * 12 + i];
+    }
+    double n = 0.0;
+    for (int i = 0; i < 12; ++i) n += v[i] * v[i];
+    n = 1.0 / sqrt(n);
+    for (int i = 0; i < 12; ++i) v[i] *= n;
+  }
+  return true;
+}
+
+__device__ inline double det3(const double* m) {
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+// R <- nearest rotation (polar factor) by Newton iteration R <- (R + R^-T)/2.
+__device__ inline void orthonormalise(double* R) {
+  for (int it = 0; it < 12; ++it) {
+    double d = det3(R);
+    if (fabs(d) < 1e-300) return;
+    double id = 1.0 / d;
+    // inverse transpose = cofactor matrix / det
+    double C[9] = {(R[4] * R[8] - R[5] * R[7]) * id, (R[5] * R[6] - R[3] * R[8]) * id, (R[3] * R[7] - R[4] * R[6]) * id,
+                   (R[2] * R[7] - R[1] * R[8]) * id, (R[0] * R[8] - R[2] * R[6]) * id, (R[1] * R[6] - R[0] * R[7]) * id,
+                   (R[1] * R[5] - R[2] * R[4]) * id, (R[2] * R[3] - R[0] * R[5]) * id, (R[0] * R[4] - R[1] * R[3]) * id};
+    double diff = 0.0;
+    for (int k = 0; k < 9; ++k) {
+      double n = 0.5 * (R[k] + C[k]);
+      diff += fabs(n - R[k]);
+      R[k] = n;
+    }
+    if (diff < 1e-15) break;
+  }
+}
+
+__global__ void __launch_bounds__(PNP_WARPS * 32)
+pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restrict__ img, const uint8_t* __restrict__ valid,
+           const double* __restrict__ guess, const uint8_t* __restrict__ use_guess, double* __restrict__ pose_out,
+           uint8_t* __restrict__ ok_out, float* __restrict__ err_out, int32_t* __restrict__ iters_out, int n_pts, int batch) {
+  __shared__ double s_M[PNP_WARPS][144];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int f = blockIdx.x * PNP_WARPS + wid;
+  if (f >= batch) return;
+
+  double X[2][3], U[2][2];
+  bool have[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int p = lane + 32 * s;
+    have[s] = p < n_pts && (valid == nullptr || valid[(int64_t)f * n_pts + p] != 0);
+    if (have[s]) {
+      X[s][0] = obj[p * 3]; X[s][1] = obj[p * 3 + 1]; X[s][2] = obj[p * 3 + 2];
+      U[s][0] = img[((int64_t)f * n_pts + p) * 2]; U[s][1] = img[((int64_t)f * n_pts + p) * 2 + 1];
+      bool fin = isfinite(U[s][0]) && isfinite(U[s][1]);
+      have[s] = fin;
+    }
+    if (!have[s]) { X[s][0] = X[s][1] = X[s][2] = 0.0; U[s][0] = U[s][1] = 0.0; }
+  }
+  int n = __popc(__ballot_sync(0xffffffffu, have[0])) + __popc(__ballot_sync(0xffffffffu, have[1]));
+
+  double p[6];
+  bool ok = n >= 4;
+  bool guessed = use_guess != nullptr && guess != nullptr && use_guess[f] != 0;
+  if (guessed) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = guess[(int64_t)f * 6 + k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ok = ok && isfinite(p[k]);
+  } else if (ok) {
+    // ---------------- DLT initialisation (needs >= 6 points) -----------------------
+    ok = n >= 6;
+    // normalisation statistics
+    double sum[5] = {0, 0, 0, 0, 0};
+    double xn[2][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      xn[s][0] = (U[s][0] - cam.cx) / cam.fx; xn[s][1] = (U[s][1] - cam.cy) / cam.fy;
+      if (have[s]) { sum[0] += X[s][0]; sum[1] += X[s][1]; sum[2] += X[s][2]; sum[3] += xn[s][0]; sum[4] += xn[s][1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sum[k] = agt_warp_sum(sum[k]) / (n > 0 ? n : 1);
+    double so = 0.0, si = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (have[s]) {
+        double a = X[s][0] - sum[0], b = X[s][1] - sum[1], c = X[s][2] - sum[2];
+        so += a * a + b * b + c * c;
+        double d = xn[s][0] - sum[3], e = xn[s][1] - sum[4];
+        si += d * d + e * e;
+      }
+    so = agt_warp_sum(so); si = agt_warp_sum(si);
+    ok = ok && so > 0.0 && si > 0.0;
+    double sco = ok ? sqrt(3.0 * n / so) : 1.0, sci = ok ? sqrt(2.0 * n / si) : 1.0;
+    // 4 symmetric 4x4 moment matrices: S, Sx, Sy, Sq
+    double mom[40];
+#pragma unroll
+    for (int k = 0; k < 40; ++k) mom[k] = 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (have[s]) {
+        double h[4] = {sco * (X[s][0] - sum[0]), sco * (X[s][1] - sum[1]), sco * (X[s][2] - sum[2]), 1.0};
+        double x = sci * (xn[s][0] - sum[3]), y = sci * (xn[s][1] - sum[4]);
+        double q = x * x + y * y;
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = a; b < 4; ++b) {
+            double hh = h[a] * h[b];
+            mom[k] += hh; mom[10 + k] += x * hh; mom[20 + k] += y * hh; mom[30 + k] += q * hh;
+            ++k;
+          }
+      }
+#pragma unroll
+    for (int k = 0; k < 40; ++k) mom[k] = agt_warp_sum(mom[k]);
+    double* M = s_M[wid];
+    __syncwarp();
+    if (lane == 0) {
+      for (int k = 0; k < 144; ++k) M[k] = 0.0;
+      int k = 0;
+      for (int a = 0; a < 4; ++a)
+        for (int b = a; b < 4; ++b) {
+          double s0 = mom[k], sx = mom[10 + k], sy = mom[20 + k], sq = mom[30 + k];
+          ++k;
+          // blocks: (0,0)=S (1,1)=S (0,2)=-Sx (1,2)=-Sy (2,2)=Sq, symmetric
+          M[(a)*12 + b] = M[(b)*12 + a] = s0;
+          M[(4 + a) * 12 + 4 + b] = M[(4 + b) * 12 + 4 + a] = s0;
+          M[(a)*12 + 8 + b] = M[(b)*12 + 8 + a] = -sx;
+          M[(8 + b) * 12 + a] = M[(8 + a) * 12 + b] = -sx;
+          M[(4 + a) * 12 + 8 + b] = M[(4 + b) * 12 + 8 + a] = -sy;
+          M[(8 + b) * 12 + 4 + a] = M[(8 + a) * 12 + 4 + b] = -sy;
+          M[(8 + a) * 12 + 8 + b] = M[(8 + b) * 12 + 8 + a] = sq;
+        }
+    }
+    __syncwarp();
+    double v[12];
+    bool eig_ok = true;
+    if (lane == 0) eig_ok = smallest_eigvec12(M, v);
+    eig_ok = __shfl_sync(0xffffffffu, (int)eig_ok, 0) != 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = __shfl_sync(0xffffffffu, v[k], 0);
+    ok = ok && eig_ok;
+    // denormalise: P = Ti^-1 P' To ; Ti^-1 = [[1/sci,0,mx],[0,1/sci,my],[0,0,1]] ; To = [[sco I, -sco c],[0,1]]
+    double Pn[12];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      Pn[0 + c] = v[0 + c] / sci + sum[3] * v[8 + c];
+      Pn[4 + c] = v[4 + c] / sci + sum[4] * v[8 + c];
+      Pn[8 + c] = v[8 + c];
+    }
+    double Rm[9], tt[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      Rm[r * 3 + 0] = Pn[r * 4 + 0] * sco; Rm[r * 3 + 1] = Pn[r * 4 + 1] * sco; Rm[r * 3 + 2] = Pn[r * 4 + 2] * sco;
+      tt[r] = Pn[r * 4 + 3] - sco * (Pn[r * 4 + 0] * sum[0] + Pn[r * 4 + 1] * sum[1] + Pn[r * 4 + 2] * sum[2]);
+    }
+    double d = det3(Rm);
+    ok = ok && fabs(d) > 1e-300 && isfinite(d);
+    double sc = ok ? (d < 0 ? -1.0 : 1.0) / cbrt(fabs(d)) : 1.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rm[k] *= sc;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tt[k] *= sc;
+    orthonormalise(Rm);
+    agt_log_rotation(Rm, p);
+    p[3] = tt[0]; p[4] = tt[1]; p[5] = tt[2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ok = ok && isfinite(p[k]);
+  }
+
+  // ---------------- Levenberg-Marquardt ---------------------------------------------
+  int iters = 0;
+  if (ok) {
+    Normal cur, tri;
+    bool front;
+    evaluate(cam, p, X, U, have, cur, front);
+    double lam = 1e-3;
+    for (iters = 0; iters < PNP_MAX_ITERS; ++iters) {
+      double A[36], b[6];
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = a; c < 6; ++c) { A[a * 6 + c] = cur.H[k]; A[c * 6 + a] = cur.H[k]; ++k; }
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { A[a * 6 + a] *= (1.0 + lam); b[a] = -cur.g[a]; }
+      if (!agt_chol6_solve(A, b)) {
+        lam *= 10.0;
+        if (lam > 1e12) { ok = false; break; }
+        continue;
+      }
+      double q[6], dmax = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) { q[a] = p[a] + b[a]; dmax = fmax(dmax, fabs(b[a])); }
+      evaluate(cam, q, X, U, have, tri, front);
+      if (front && tri.c < cur.c) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) p[a] = q[a];
+        cur = tri;
+        lam = fmax(lam * 0.1, 1e-15);
+        if (dmax < 1e-11) { ++iters; break; }
+      } else {
+        lam *= 10.0;
+        if (dmax < 1e-10 || lam > 1e12) { ++iters; break; }
+      }
+    }
+    // keep the rotation vector in OpenCV's range (angle <= pi)
+    double th = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+    if (th > 3.14159265358979323846) {
+      double R[9];
+      agt_rodrigues(p, R);
+      agt_log_rotation(R, p);
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) ok = ok && isfinite(p[a]);
+  }
+
+  // ---------------- epilogue: mean reprojection error as transform_helper.py:106-119 ----
+  float nrm[2] = {0.f, 0.f};
+  if (ok) {
+    double R[9];
+    agt_rodrigues(p, R);
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (have[s]) {
+        double Xc = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + p[3];
+        double Yc = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + p[4];
+        double Zc = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + p[5];
+        Proj pr = project_point(cam, Xc, Yc, Zc);
+        float du = __fsub_rn((float)U[s][0], (float)pr.u), dv = __fsub_rn((float)U[s][1], (float)pr.v);
+        nrm[s] = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+      }
+  }
+  float total = 0.f;
+  for (int q = 0; q < n_pts; ++q) {
+    float v0 = __shfl_sync(0xffffffffu, q < 32 ? nrm[0] : nrm[1], q & 31);
+    int hv = __shfl_sync(0xffffffffu, (int)(q < 32 ? have[0] : have[1]), q & 31);
+    if (hv) total = __fadd_rn(total, v0);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) pose_out[(int64_t)f * 6 + a] = ok ? p[a] : 0.0;
+    ok_out[f] = ok ? 1 : 0;
+    err_out[f] = ok && n > 0 ? __fdiv_rn(total, (float)n) : 0.f;
+    if (iters_out) iters_out[f] = iters;
+  }
+}
+
+__global__ void project_kernel(agt_camera cam, const float* __restrict__ obj, const double* __restrict__ pose,
+                               double* __restrict__ out, int n_pts, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t f = i / n_pts;
+  int p = (int)(i - f * n_pts);
+  double R[9];
+  const double* ps = pose + f * 6;
+  double r[3] = {ps[0], ps[1], ps[2]};
+  agt_rodrigues(r, R);
+  double x = obj[p * 3], y = obj[p * 3 + 1], z = obj[p * 3 + 2];
+  double Xc = R[0] * x + R[1] * y + R[2] * z + ps[3];
+  double Yc = R[3] * x + R[4] * y + R[5] * z + ps[4];
+  double Zc = R[6] * x + R[7] * y + R[8] * z + ps[5];
+  // cv::projectPoints divides by z without a cheirality test
+  double iz = Zc != 0.0 ? 1.0 / Zc : 1.0;
+  Proj pr = project_point(cam, Xc * iz, Yc * iz, 1.0);
+  out[i * 2] = pr.u;
+  out[i * 2 + 1] = pr.v;
+}
+
+}  // namespace
+
+extern "C" int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_pts, const uint8_t* d_valid,
+                       const double* d_guess, const uint8_t* d_use_guess, double* d_pose, uint8_t* d_ok,
+                       float* d_reproj_err, int32_t* d_iters, int batch, int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_pnp: call agt_set_camera first");
+  if (!d_obj_pts || !d_img_pts || !d_pose || !d_ok || !d_reproj_err || batch < 0)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pnp: null argument or negative batch");
+  if (n_pts < 1 || n_pts > AGT_MAX_POINTS) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pnp: n_pts must be 1..%d", AGT_MAX_POINTS);
+  if (batch == 0) return AGT_OK;
+  int blocks = (batch + PNP_WARPS - 1) / PNP_WARPS;
+  pnp_kernel<<<blocks, PNP_WARPS * 32, 0, ctx->stream>>>(ctx->cam, d_obj_pts, d_img_pts, d_valid, d_guess, d_use_guess,
+                                                         d_pose, d_ok, d_reproj_err, d_iters, n_pts, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_project(agt_ctx* ctx, const float* d_obj_pts, const double* d_pose, double* d_out, int batch, int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_project: call agt_set_camera first");
+  if (!d_obj_pts || !d_pose || !d_out || batch < 0 || n_pts < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_project: bad arguments");
+  int64_t total = (int64_t)batch * n_pts;
+  if (total == 0) return AGT_OK;
+  project_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(ctx->cam, d_obj_pts, d_pose, d_out, n_pts, total);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}

@@ -1,0 +1,192 @@
+// K1: Gaussian pyramid (cv::pyrDown) and Scharr derivatives (cv::Scharr CV_16S),
+// integer-exact.  The reference snapshot has no such code; the frozen semantics
+// are OpenCV's: 5x5 [1 4 6 4 1]^2, (sum+128)>>8,
+// BORDER_REFLECT_101, output ((w+1)/2, (h+1)/2); Scharr [3 10 3] x [-1 0 1],
+// unnormalised int16, BORDER_REFLECT_101.
+//
+// pyrDown is a pure streaming stencil (HBM-bound): each CTA stages a
+// (2*128+32) x (2*16+3) u8 input tile in shared memory with 128-bit coalesced
+// loads, runs the horizontal 5-tap pass into a uint16 tile, then the vertical
+// pass, and stores 8 output bytes per thread.
+#include "agt_common.cuh"
+
+namespace {
+
+constexpr int PD_OW = 128;                 // output tile width
+constexpr int PD_OH = 16;                  // output tile height
+constexpr int PD_IW = 2 * PD_OW + 32;      // staged input width (16 B aligned start, 16 B slack each side)
+constexpr int PD_IH = 2 * PD_OH + 3;
+constexpr int PD_THREADS = 256;
+
+__global__ void __launch_bounds__(PD_THREADS)
+pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
+                uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride, int vec_ok) {
+  __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
+  __shared__ __align__(16) uint16_t s_h[PD_IH][PD_OW];
+
+  const int x0 = blockIdx.x * PD_OW;       // first output column of the tile
+  const int y0 = blockIdx.y * PD_OH;
+  const uint8_t* img = src + (int64_t)blockIdx.z * sstride;
+  uint8_t* out = dst + (int64_t)blockIdx.z * dstride;
+  const int gx_base = 2 * x0 - 16;         // global column of s_in[.][0]
+  const int gy_base = 2 * y0 - 2;
+
+  // ---- stage the input tile --------------------------------------------------
+  constexpr int CHUNKS = PD_IW / 16;
+  for (int i = threadIdx.x; i < PD_IH * CHUNKS; i += PD_THREADS) {
+    int r = i / CHUNKS, c = i - r * CHUNKS;
+    int gy = agt_reflect101(gy_base + r, h);
+    int gx = gx_base + 16 * c;
+    const uint8_t* row = img + (int64_t)gy * spitch;
+    uint4 v;
+    if (vec_ok && gx >= 0 && gx + 16 <= w) {
+      v = __ldg(reinterpret_cast<const uint4*>(row + gx));
+    } else {
+      uint32_t word[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          int xx = gx + 4 * k + b;
+          uint32_t px = row[agt_reflect101(xx, w)];
+          acc |= px << (8 * b);
+        }
+        word[k] = acc;
+      }
+      v = make_uint4(word[0], word[1], word[2], word[3]);
+    }
+    *reinterpret_cast<uint4*>(&s_in[r][16 * c]) = v;
+  }
+  __syncthreads();
+
+  // ---- horizontal pass: 4 outputs per work item ---------------------------------
+  // output column x (tile-local, multiple of 4) needs staged bytes 2x+14 .. 2x+24
+  constexpr int HGROUPS = PD_OW / 4;
+  for (int i = threadIdx.x; i < PD_IH * HGROUPS; i += PD_THREADS) {
+    int r = i / HGROUPS, g = i - r * HGROUPS;
+    const uint2* p = reinterpret_cast<const uint2*>(&s_in[r][8 * g + 8]);   // bytes 2x+8 .. 2x+31
+    uint2 a = p[0], b = p[1], c = p[2];
+    // byte k of the 24-byte window = staged byte 2x+8+k ; tap j of output q is byte 6+2q+j
+    uint32_t wv[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+    auto byte_at = [&](int k) -> uint32_t { return (wv[k >> 2] >> (8 * (k & 3))) & 0xffu; };
+    uint16_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      int k = 6 + 2 * q;
+      uint32_t s = byte_at(k) + 4u * byte_at(k + 1) + 6u * byte_at(k + 2) + 4u * byte_at(k + 3) + byte_at(k + 4);
+      o[q] = (uint16_t)s;
+    }
+    uint2 packed = make_uint2((uint32_t)o[0] | ((uint32_t)o[1] << 16), (uint32_t)o[2] | ((uint32_t)o[3] << 16));
+    *reinterpret_cast<uint2*>(&s_h[r][4 * g]) = packed;
+  }
+  __syncthreads();
+
+  // ---- vertical pass: 8 outputs per thread --------------------------------------
+  {
+    int ty = threadIdx.x / (PD_OW / 8);
+    int tx = (threadIdx.x % (PD_OW / 8)) * 8;
+    int oy = y0 + ty, ox = x0 + tx;
+    if (oy < oh && ox < ow) {
+      uint32_t acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 128u;
+      const uint32_t wgt[5] = {1u, 4u, 6u, 4u, 1u};
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        uint4 v = *reinterpret_cast<const uint4*>(&s_h[2 * ty + j][tx]);
+        uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[2 * k] += wgt[j] * (vv[k] & 0xffffu);
+          acc[2 * k + 1] += wgt[j] * (vv[k] >> 16);
+        }
+      }
+      uint8_t* orow = out + (int64_t)oy * dpitch + ox;
+      if (vec_ok && ox + 8 <= ow && ((dpitch & 7) == 0)) {
+        uint2 pk;
+        pk.x = (acc[0] >> 8) | ((acc[1] >> 8) << 8) | ((acc[2] >> 8) << 16) | ((acc[3] >> 8) << 24);
+        pk.y = (acc[4] >> 8) | ((acc[5] >> 8) << 8) | ((acc[6] >> 8) << 16) | ((acc[7] >> 8) << 24);
+        *reinterpret_cast<uint2*>(orow) = pk;
+      } else {
+        for (int k = 0; k < 8 && ox + k < ow; ++k) orow[k] = (uint8_t)(acc[k] >> 8);
+      }
+    }
+  }
+}
+
+// Scharr: one thread per pixel pair; loads go through L1.  Not on the hot path
+// (the LK and refinement kernels derive gradients on the fly from the u8 levels);
+// exported so the derivative planes themselves can be checked bit-exactly.
+__global__ void scharr_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
+                              int16_t* __restrict__ dst) {
+  int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const uint8_t* img = src + (int64_t)blockIdx.z * sstride;
+  int xm = agt_reflect101(x - 1, w), xp = agt_reflect101(x + 1, w);
+  int ym = agt_reflect101(y - 1, h), yp = agt_reflect101(y + 1, h);
+  const uint8_t* r0 = img + (int64_t)ym * spitch;
+  const uint8_t* r1 = img + (int64_t)y * spitch;
+  const uint8_t* r2 = img + (int64_t)yp * spitch;
+  int a00 = r0[xm], a01 = r0[x], a02 = r0[xp];
+  int a10 = r1[xm], a12 = r1[xp];
+  int a20 = r2[xm], a21 = r2[x], a22 = r2[xp];
+  int dx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
+  int dy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
+  int16_t* o = dst + ((int64_t)blockIdx.z * h * w + (int64_t)y * w + x) * 2;
+  *reinterpret_cast<short2*>(o) = make_short2((short)dx, (short)dy);
+}
+
+}  // namespace
+
+extern "C" int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+                            uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_src || !d_dst || w < 1 || h < 1 || batch < 0 || src_pitch < w || dst_pitch < (w + 1) / 2)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pyr_down: bad arguments (w=%d h=%d batch=%d)", w, h, batch);
+  if (batch == 0) return AGT_OK;
+  int ow = (w + 1) / 2, oh = (h + 1) / 2;
+  int vec_ok = ((reinterpret_cast<uintptr_t>(d_src) & 15) == 0) && ((src_pitch & 15) == 0) && ((src_stride & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(d_dst) & 7) == 0) && ((dst_stride & 7) == 0);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid((ow + PD_OW - 1) / PD_OW, (oh + PD_OH - 1) / PD_OH, nb);
+    pyr_down_kernel<<<grid, PD_THREADS, 0, ctx->stream>>>(d_src + (int64_t)b0 * src_stride, w, h, src_pitch, src_stride,
+                                                          d_dst + (int64_t)b0 * dst_stride, ow, oh, dst_pitch,
+                                                          dst_stride, vec_ok);
+    AGT_LAUNCH_CHECK(ctx);
+  }
+  return AGT_OK;
+}
+
+extern "C" int agt_build_pyramid(agt_ctx* ctx, const agt_pyramid* pyr, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!pyr || pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: bad pyramid descriptor");
+  for (int l = 1; l < pyr->levels; ++l) {
+    if (pyr->width[l] != (pyr->width[l - 1] + 1) / 2 || pyr->height[l] != (pyr->height[l - 1] + 1) / 2)
+      AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: level %d is not ((w+1)/2,(h+1)/2) of level %d", l, l - 1);
+    int rc = agt_pyr_down(ctx, pyr->data[l - 1], pyr->width[l - 1], pyr->height[l - 1], pyr->pitch[l - 1],
+                          pyr->frame_stride[l - 1], pyr->data[l], pyr->pitch[l], pyr->frame_stride[l], batch);
+    if (rc != AGT_OK) return rc;
+  }
+  return AGT_OK;
+}
+
+extern "C" int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+                          int16_t* d_dst, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_src || !d_dst || w < 1 || h < 1 || batch < 0 || src_pitch < w)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_scharr: bad arguments");
+  if (batch == 0) return AGT_OK;
+  dim3 block(32, 8);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid((w + 31) / 32, (h + 7) / 8, nb);
+    scharr_kernel<<<grid, block, 0, ctx->stream>>>(d_src + (int64_t)b0 * src_stride, w, h, src_pitch, src_stride,
+                                                   d_dst + (int64_t)b0 * h * w * 2);
+    AGT_LAUNCH_CHECK(ctx);
+  }
+  return AGT_OK;
+}

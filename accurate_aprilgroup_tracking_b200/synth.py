@@ -192,6 +192,11 @@ def _gauss_blur_sep(img: np.ndarray, sigma: float) -> np.ndarray:
     return sum(k[i] * tmp[i:i + img.shape[0], :] for i in range(2 * rad + 1))
 
 
+def model_pitch() -> float:
+    """Metric spacing of neighbouring surface samples."""
+    return 2.0 * MODEL_HALF_EXTENT * TAG_SIZE / (MODEL_GRID - 1)
+
+
 def surface_model() -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
     """Dense-refinement surface model.
 

@@ -1,0 +1,179 @@
+/*
+ * agt.h - C ABI of the B200-native AprilGroup tracking hot path (libagt.so).
+ *
+ * The reference (Virtana/accurate-aprilgroup-tracking) has no FFI of its own: its
+ * hot path is Python calling OpenCV.  Every entry point below therefore names
+ * the reference call site / OpenCV call it stands in for.  A maintainer binds
+ * these with ctypes; nothing here uses torch or C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative agt_status; it never
+ *     throws or aborts.  agt_last_error() returns a message for the last failure.
+ *   - per-item failures (a corner lost by LK, a PnP that did not converge) are
+ *     reported in status arrays, not as error codes.
+ *   - "d_" pointers are device pointers on the context's device, "h_" pointers
+ *     are host pointers.  Device entry points are asynchronous on the context's
+ *     stream (agt_set_stream); host entry points copy, run and synchronise.
+ *   - a pose is 6 doubles: rvec (axis-angle, OpenCV convention) then tvec,
+ *     X_cam = R(rvec) X_group + tvec  (detect_pose.py:528).
+ *   - a context is bound to one CUDA device and is not re-entrant; use one
+ *     context (and one process) per GPU.
+ */
+#ifndef AGT_H_
+#define AGT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGT_VERSION 100
+#define AGT_MAX_LEVELS 4
+#define AGT_MAX_TAGS 16
+#define AGT_MAX_POINTS 64 /* 4 corners x AGT_MAX_TAGS */
+
+typedef enum agt_status {
+  AGT_OK = 0,
+  AGT_ERR_INVALID = -1,   /* bad argument (maps to ValueError) */
+  AGT_ERR_CUDA = -2,      /* CUDA runtime failure (maps to RuntimeError) */
+  AGT_ERR_NOT_READY = -3, /* camera / group / model not set */
+  AGT_ERR_NO_DEVICE = -4  /* no usable CUDA device: there is no CPU fallback */
+} agt_status;
+
+typedef struct agt_ctx agt_ctx;
+
+/* A batch of gray image pyramids resident in device memory.  Level l of frame
+ * b starts at data[l] + b*frame_stride[l]; rows are pitch[l] bytes apart.
+ * Level 0 is the input frame; levels 1.. are cv::pyrDown chains of it. */
+typedef struct agt_pyramid {
+  int32_t levels;
+  int32_t width[AGT_MAX_LEVELS];
+  int32_t height[AGT_MAX_LEVELS];
+  int64_t pitch[AGT_MAX_LEVELS];
+  int64_t frame_stride[AGT_MAX_LEVELS];
+  uint8_t* data[AGT_MAX_LEVELS];
+} agt_pyramid;
+
+/* per-refinement status (dense pose refinement) */
+enum { AGT_DPR_NONE = 0, AGT_DPR_CONVERGED = 1, AGT_DPR_MAX_EVALS = 2, AGT_DPR_LAMBDA = 3 };
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int agt_version(void);
+int agt_device_count(void);
+int agt_create(int device, agt_ctx** out);
+int agt_destroy(agt_ctx* ctx);
+const char* agt_last_error(const agt_ctx* ctx); /* ctx may be NULL: last create() error */
+/* Run all subsequent device work of this context on `cuda_stream` (a
+ * cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream; 0/NULL is the
+ * CUDA legacy default stream, which is what torch uses unless told otherwise).
+ * A fresh context runs on its own non-blocking stream until this is called. */
+int agt_set_stream(agt_ctx* ctx, void* cuda_stream);
+int agt_sync(agt_ctx* ctx);
+/* number of kernel launches issued by this context since creation */
+int64_t agt_launch_count(const agt_ctx* ctx);
+
+/* ---- configuration --------------------------------------------------------- */
+/* Camera matrix (row-major 3x3) and 0/4/5 distortion coefficients k1 k2 p1 p2 [k3]
+ * - the mtx/dist pair the reference passes to cv.solvePnP / cv.projectPoints
+ * (detect_pose.py:509-526, transform_helper.py:106-111). */
+int agt_set_camera(agt_ctx* ctx, const double k[9], const double* dist, int ndist);
+/* Surface model for dense refinement: samples[S][4] = x,y,z (group frame) and
+ * target intensity; sample_tag[S] in [0,n_tags); samples must be tag-major
+ * (all samples of tag 0, then tag 1, ...).  pitch = metric sample spacing. */
+int agt_set_model(agt_ctx* ctx, const float* h_samples, const uint8_t* h_sample_tag, int n_samples,
+                  const float* h_tag_normals, const float* h_tag_centres, int n_tags, double pitch);
+
+/* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
+/* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
+int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+                 uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch);
+/* Fill levels 1..levels-1 of every frame from level 0. */
+int agt_build_pyramid(agt_ctx* ctx, const agt_pyramid* pyr, int batch);
+/* Interleaved (dx,dy) int16 Scharr planes, d_dst[b][h][w][2] (the layout
+ * cv::buildOpticalFlowPyramid(withDerivatives=true) produces). */
+int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+               int16_t* d_dst, int batch);
+
+/* ---- K2: pyramidal Lucas-Kanade (cv::calcOpticalFlowPyrLK defaults) --------- */
+/* winSize 21x21, pyr->levels levels, criteria (COUNT+EPS, 30, 0.01),
+ * minEigThreshold 1e-4, flags 0.  Points are [batch][n_pts][2] float32. */
+int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
+           float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts);
+
+/* ---- K3: batched PnP (cv::solvePnP SOLVEPNP_ITERATIVE + reprojection gate) --- */
+/* d_obj_pts[n_pts][3] float32 is shared by the batch (group corners, index
+ * 4*tag+corner, detect_pose.py:185-227); d_img_pts[batch][n_pts][2] float32;
+ * d_valid[batch][n_pts] selects the corners present in a frame (NULL = all).
+ * d_guess[batch][6] + d_use_guess[batch] give the extrinsic guess
+ * (detect_pose.py:516-526); frames without a guess start from a DLT like
+ * cv::solvePnP does (detect_pose.py:508-515).  Outputs: pose[batch][6],
+ * ok[batch] (solver success), reproj_err[batch] = mean L2 pixel error
+ * (transform_helper.py:98-121), iters[batch] (may be NULL). */
+int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_pts, const uint8_t* d_valid,
+            const double* d_guess, const uint8_t* d_use_guess, double* d_pose, uint8_t* d_ok,
+            float* d_reproj_err, int32_t* d_iters, int batch, int n_pts);
+/* cv::projectPoints: d_out[batch][n_pts][2] float64. */
+int agt_project(agt_ctx* ctx, const float* d_obj_pts, const double* d_pose, double* d_out, int batch, int n_pts);
+
+/* ---- K0: per-stream APE state machine + motion predictor --------------------- */
+/* State of one camera stream as detect_pose.py:74-78 keeps it (prev_transform,
+ * extrinsic_guess, 2-deep velocity FIFOs) plus the aliasing flags needed to
+ * reproduce cv::solvePnP's in-place write into the guess arrays. Opaque
+ * 64-double record per stream; zero-initialise for a fresh stream. */
+#define AGT_STREAM_STATE_DOUBLES 64
+/* Before K3: write guess[batch][6]/use_guess[batch] from the states. */
+int agt_ape_prepare(agt_ctx* ctx, const double* d_state, double* d_guess, uint8_t* d_use_guess, int batch,
+                    int enhance_ape);
+/* After K3 (+ optional refinement): apply detect_pose.py:490-574 to each
+ * stream. n_tags[batch] = accepted detections in the frame; pose/ok/err from
+ * agt_pnp.  accepted[batch] (may be NULL) receives 1 where prev_transform was
+ * updated. error_flag[batch] (may be NULL) is set where the reference would
+ * raise ValueError (exact zero in a velocity, detect_pose.py:236-237). */
+int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const double* d_pose,
+                   const uint8_t* d_ok, const float* d_err, uint8_t* d_accepted, uint8_t* d_error_flag,
+                   int batch, int enhance_ape);
+
+/* ---- K4: dense pose refinement (photometric LM; DodecaPen stage 3) ----------- */
+/* d_init[batch][n_hyp][6] -> d_pose[batch][n_hyp][6]; cost = 1/2 sum r^2,
+ * n_valid = samples in the final residual, evals = cost/Jacobian evaluations
+ * run, status = AGT_DPR_*.  Any output except d_pose may be NULL. */
+int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, double* d_pose,
+               float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch);
+/* Multi-hypothesis selection: best[b] = argmin_h 2*cost/n_valid (ties -> lowest
+ * h); d_best_pose[batch][6] may be NULL. */
+int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,
+                    int n_hyp, int32_t* d_best, double* d_best_pose, int batch);
+
+/* ---- synthetic input generator (tests / bench only; not part of the path) ---- */
+/* Ray-casts the 12-tag dodecahedron of SURVEY.md 8d. d_tag_rt[n_tags][12] =
+ * row-major R_k (9) then t_k (3) float64; d_cells[n_tags][100] u8 intensities. */
+int agt_render(agt_ctx* ctx, const double* d_pose, const uint32_t* d_seed, uint8_t* d_frames, int w, int h,
+               int64_t pitch, int64_t stride, const double* d_tag_rt, const uint8_t* d_cells, int n_tags,
+               double inradius, double cell, int noise, int batch);
+
+/* ---- host-buffer entry points (what a ctypes caller with numpy arrays uses) --- */
+/* cv.solvePnP(obj, img, K, dist[, rvec, tvec, True], flags=ITERATIVE) for one frame
+ * (detect_pose.py:509-526).  pose is in/out when use_guess != 0. */
+int agt_solve_pnp_host(agt_ctx* ctx, const float* h_obj, const float* h_img, int n_pts, int use_guess,
+                       double h_pose[6], int* ok, float* reproj_err);
+int agt_project_host(agt_ctx* ctx, const float* h_obj, int n_pts, const double h_pose[6], double* h_out);
+/* cv.calcOpticalFlowPyrLK(prev, next, prevPts, None) on host images. */
+int agt_lk_host(agt_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int w, int h, int levels,
+                const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err);
+/* Pyramid of one host image: h_levels[l] receives level l (l >= 1), tightly packed. */
+int agt_pyramid_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int levels, uint8_t* const* h_levels);
+int agt_scharr_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int16_t* h_out);
+/* End-to-end batched refinement from HOST frames [batch][h][w] (pinned memory
+ * recommended): uploads in chunks overlapped with pyramid construction and
+ * refinement, downloads poses.  h_init[batch][n_hyp][6]; outputs as agt_refine
+ * plus (n_hyp>1) h_best[batch]. */
+int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, int batch,
+                    const double* h_init, int n_hyp, double* h_pose, float* h_cost, int32_t* h_n_valid,
+                    int32_t* h_evals, uint8_t* h_status, int32_t* h_best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGT_H_ */
