@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if verbose:
                 print(r.stderr, file=sys.stderr)
             objs.append(str(obj))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -14,8 +14,9 @@
 // with 128-bit loads and reused by every LM evaluation, so HBM sees each ROI byte
 // once per refinement; no gradient plane is materialised - the 4x4 u8 footprint of
 // a sample is fetched with two aligned 32-bit shared loads + a byte permute per
-// row and the four Scharr values come from 16 dp4a.  Samples are evaluated in
-// float32; the 28 sums are reduced by warp shuffles and across warps in float64
+// row and the four Scharr values come from 16 dp4a.  The projection of a sample
+// runs in float64 (see the note in the sample loop), intensity / gradient /
+// Jacobian in float32; the 28 sums are reduced by warp shuffles and across warps in float64
 // (the cost in float64 from the start); one thread runs the 6x6 Cholesky / LM
 // bookkeeping in float64.  Samples whose footprint leaves the staged tile fall
 // back to global loads, so results do not depend on the tile size.
@@ -37,8 +38,10 @@ constexpr double BOUND_RADIUS_FACTOR = 1.30;   // bounding sphere radius / max |
 constexpr int DRIFT_MARGIN = 8;
 
 struct DprShared {
-  // trial pose (float32 view used by the sample loop)
+  // trial pose (float32 view used by the sample loop, float64 for the projection)
   float R[9], t[3];
+  double Rd[9], td[3];
+  double fxs, fys, ubase, vbase;   // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l
   float fx, fy, cx, cy;
   float inv_scale;       // 2^-level
   float gscale;          // 2^-level / 32
@@ -151,8 +154,10 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     if (tw < 0) tw = 0;
     if (th < 0) th = 0;
     S.tx0 = x0; S.ty0 = y0; S.tw = tw; S.th = th;
-    for (int i = 0; i < 9; ++i) S.R[i] = (float)Rc[i];
-    for (int i = 0; i < 3; ++i) S.t[i] = (float)tc[i];
+    for (int i = 0; i < 9; ++i) { S.R[i] = (float)Rc[i]; S.Rd[i] = Rc[i]; }
+    for (int i = 0; i < 3; ++i) { S.t[i] = (float)tc[i]; S.td[i] = tc[i]; }
+    S.fxs = cam.fx * sc; S.fys = cam.fy * sc;
+    S.ubase = cam.cx * sc; S.vbase = cam.cy * sc;
     S.stop = 0;
   }
   __syncthreads();
@@ -188,8 +193,6 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 
   while (true) {
     // ================= evaluate cost + normal equations at the trial pose =================
-    const float R0 = S.R[0], R1 = S.R[1], R2 = S.R[2], R3 = S.R[3], R4 = S.R[4], R5 = S.R[5], R6 = S.R[6], R7 = S.R[7],
-                R8 = S.R[8], t0 = S.t[0], t1 = S.t[1], t2 = S.t[2];
     float acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0.f;
@@ -199,17 +202,24 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     for (int j = tid; j < n_act_samples; j += DPR_THREADS) {
       while (j >= S.act_prefix[seg + 1]) ++seg;
       const float4 sm = __ldg(&samples[S.act_begin[seg] + (j - S.act_prefix[seg])]);
-      const float Yx = R0 * sm.x + R1 * sm.y + R2 * sm.z;
-      const float Yy = R3 * sm.x + R4 * sm.y + R5 * sm.z;
-      const float Yz = R6 * sm.x + R7 * sm.y + R8 * sm.z;
-      const float X = Yx + t0, Y = Yy + t1, Z = Yz + t2;
-      if (!(Z > 1e-6f)) continue;
-      const float iz = 1.f / Z;
-      const float ul = (fx * X * iz + cx) * isc, vl = (fy * Y * iz + cy) * isc;
-      const float fxl = floorf(ul), fyl = floorf(vl);
-      if (!(fxl >= 1.f && fxl <= (float)(lw - 3) && fyl >= 1.f && fyl <= (float)(lh - 3))) continue;
+      // Projection in float64: the accept/reject decisions of the LM loop compare costs that differ by ~1e-6
+      // relative near convergence; float32 pixel coordinates (ulp 6e-5 px at 1080p) add ~1e-6 of noise to the
+      // cost and flip 20 % of those decisions, float64 leaves 0.2 % (profiles/r01_dpr_precision_sweep.log).
+      const double sx = sm.x, sy = sm.y, sz = sm.z;
+      const double dYx = S.Rd[0] * sx + S.Rd[1] * sy + S.Rd[2] * sz;
+      const double dYy = S.Rd[3] * sx + S.Rd[4] * sy + S.Rd[5] * sz;
+      const double dYz = S.Rd[6] * sx + S.Rd[7] * sy + S.Rd[8] * sz;
+      const double dX = dYx + S.td[0], dY = dYy + S.td[1], dZ = dYz + S.td[2];
+      if (!(dZ > 1e-6)) continue;
+      double r0 = (double)(1.f / (float)dZ);          // MUFU.RCP seed + two Newton steps
+      r0 = r0 * (2.0 - dZ * r0);
+      r0 = r0 * (2.0 - dZ * r0);
+      const double ul = (S.fxs * dX) * r0 + S.ubase, vl = (S.fys * dY) * r0 + S.vbase;
+      const double fxl = floor(ul), fyl = floor(vl);
+      if (!(fxl >= 1.0 && fxl <= (double)(lw - 3) && fyl >= 1.0 && fyl <= (double)(lh - 3))) continue;
       const int x0 = (int)fxl, y0 = (int)fyl;
-      const float a = ul - fxl, b = vl - fyl;
+      const float a = (float)(ul - fxl), b = (float)(vl - fyl);
+      const float Yx = (float)dYx, Yy = (float)dYy, Yz = (float)dYz, X = (float)dX, Y = (float)dY, iz = (float)r0;
       // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
       uint32_t row[4];
       const int lx = x0 - 1 - tx0, ly = y0 - 1 - ty0;
@@ -324,8 +334,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
           for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
           for (int p = 0; p < 3; ++p) tt[p] = tc[p] + d[3 + p];
-          for (int p = 0; p < 9; ++p) S.R[p] = (float)Rt[p];
-          for (int p = 0; p < 3; ++p) S.t[p] = (float)tt[p];
+          for (int p = 0; p < 9; ++p) { S.R[p] = (float)Rt[p]; S.Rd[p] = Rt[p]; }
+          for (int p = 0; p < 3; ++p) { S.t[p] = (float)tt[p]; S.td[p] = tt[p]; }
           break;
         }
         lam *= 10.0;

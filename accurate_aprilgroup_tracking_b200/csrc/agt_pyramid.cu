@@ -115,6 +115,125 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, i
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Streaming pyrDown (the hot variant): no shared memory.  A lane owns 8 output columns = 16 input
+// bytes per row: one coalesced 128-bit load per input row, the 4-byte halos come from the
+// neighbouring lanes by warp shuffle.  The horizontal 5-tap is two dp4a per output, sums are kept
+// as packed 2 x u16 (max 16*255 = 4080), the vertical 5-tap runs on the packed words (max
+// 16*4080+128 < 65536, so the halves never carry into each other) and each lane stores 8 bytes.
+// A warp walks down a strip of PF_STRIP output rows; two new input rows per output row, with the
+// next pair of loads issued before the current pair is consumed.
+// ---------------------------------------------------------------------------------------------
+constexpr int PF_WARPS = 4;
+constexpr int PF_STRIP = 32;
+
+struct RowWords { uint32_t w[6]; };   // w[0] = left halo, w[1..4] = own 16 bytes, w[5] = right halo
+
+// Issue the global loads of one input row; nothing here depends on the loaded values, so several
+// rows can be in flight per warp before expand_row() consumes them.  The kernel is only used for
+// w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly at w; the
+// reflect-101 halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from one
+// aligned word and a byte permute - no per-byte border code on the streaming path.
+struct RawRow { uint4 v; uint32_t edge; };   // edge = left halo for lane 0, right halo for lane 31
+
+__device__ __forceinline__ uint32_t right_reflect_word(const uint8_t* __restrict__ row, int w) {
+  return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(row + w - 4)), 0u, 0x4412);   // (p[w-2], p[w-3], 0, 0)
+}
+
+__device__ __forceinline__ RawRow raw_row(const uint8_t* __restrict__ row, int ix0, int w, int lane) {
+  RawRow r;
+  r.v = make_uint4(0, 0, 0, 0);
+  r.edge = 0;
+  if (ix0 + 16 <= w) r.v = __ldg(reinterpret_cast<const uint4*>(row + ix0));
+  else if (ix0 == w) r.v.x = right_reflect_word(row, w);
+  if (lane == 0)
+    r.edge = ix0 >= 4 ? __ldg(reinterpret_cast<const uint32_t*>(row + ix0 - 4))
+                      : __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(row)), 0u, 0x1244);   // (0, 0, p[2], p[1])
+  if (lane == 31) {
+    if (ix0 + 20 <= w) r.edge = __ldg(reinterpret_cast<const uint32_t*>(row + ix0 + 16));
+    else if (ix0 + 16 == w) r.edge = right_reflect_word(row, w);
+  }
+  return r;
+}
+
+__device__ __forceinline__ RowWords expand_row(const RawRow& q, int lane) {
+  RowWords r;
+  r.w[1] = q.v.x; r.w[2] = q.v.y; r.w[3] = q.v.z; r.w[4] = q.v.w;
+  uint32_t left = __shfl_up_sync(0xffffffffu, q.v.w, 1);
+  uint32_t right = __shfl_down_sync(0xffffffffu, q.v.x, 1);
+  r.w[0] = lane == 0 ? q.edge : left;
+  r.w[5] = lane == 31 ? q.edge : right;
+  return r;
+}
+
+// horizontal [1 4 6 4 1] at 8 even positions -> 4 packed words (2 x u16 each)
+__device__ __forceinline__ void hsum(const RowWords& r, uint32_t h[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t even = __dp4a(r.w[j], 0x04010000u, __dp4a(r.w[j + 1], 0x00010406u, 0u));
+    uint32_t odd = __dp4a(r.w[j + 1], 0x04060401u, __dp4a(r.w[j + 2], 0x00000001u, 0u));
+    h[j] = even | (odd << 16);
+  }
+}
+
+__global__ void __launch_bounds__(PF_WARPS * 32, 6)
+pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
+                       uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride,
+                       int col_blocks, int strips, int64_t total_warps) {
+  const int lane = threadIdx.x & 31;
+  int64_t wg = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
+  if (wg >= total_warps) return;
+  const int cb = (int)(wg % col_blocks);
+  wg /= col_blocks;
+  const int strip = (int)(wg % strips);
+  const int64_t frame = wg / strips;
+  const uint8_t* img = src + frame * sstride;
+  uint8_t* out = dst + frame * dstride;
+  const int ox0 = cb * 256 + lane * 8;
+  const int ix0 = 2 * ox0;
+  const int oy0 = strip * PF_STRIP;
+  const int oy1 = min(oy0 + PF_STRIP, oh);
+
+  // single reflection is enough: rows 2*oy-2 .. 2*oy+2 overshoot by at most 2 and h >= 4
+  auto row_ptr = [&](int r) { int rr = r < 0 ? -r : (r >= h ? 2 * h - 2 - r : r); return img + (int64_t)rr * spitch; };
+  uint32_t a[4], b[4], c[4], d[4], e[4];
+  RawRow q0 = raw_row(row_ptr(2 * oy0 - 2), ix0, w, lane);
+  RawRow q1 = raw_row(row_ptr(2 * oy0 - 1), ix0, w, lane);
+  RawRow q2 = raw_row(row_ptr(2 * oy0), ix0, w, lane);
+  // two output rows (four input rows) of loads stay in flight ahead of the arithmetic
+  RawRow n0 = raw_row(row_ptr(2 * oy0 + 1), ix0, w, lane);
+  RawRow n1 = raw_row(row_ptr(2 * oy0 + 2), ix0, w, lane);
+  RawRow n2 = raw_row(row_ptr(2 * oy0 + 3), ix0, w, lane);
+  RawRow n3 = raw_row(row_ptr(2 * oy0 + 4), ix0, w, lane);
+  hsum(expand_row(q0, lane), a); hsum(expand_row(q1, lane), b); hsum(expand_row(q2, lane), c);
+  for (int oy = oy0; oy < oy1; ++oy) {
+    RawRow c0 = n0, c1 = n1;
+    n0 = n2; n1 = n3;
+    if (oy + 2 < oy1) {
+      n2 = raw_row(row_ptr(2 * oy + 5), ix0, w, lane);
+      n3 = raw_row(row_ptr(2 * oy + 6), ix0, w, lane);
+    }
+    hsum(expand_row(c0, lane), d); hsum(expand_row(c1, lane), e);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t v = a[j] + e[j] + 4u * (b[j] + d[j]) + 6u * c[j] + 0x00800080u;
+      o[j] = (v >> 8) & 0x00ff00ffu;
+      a[j] = c[j]; b[j] = d[j]; c[j] = e[j];
+    }
+    if (ox0 < ow) {
+      uint32_t lo = __byte_perm(o[0], o[1], 0x6420), hi = __byte_perm(o[2], o[3], 0x6420);
+      uint8_t* p = out + (int64_t)oy * dpitch + ox0;
+      if (ox0 + 8 <= ow) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(lo, hi);
+      } else {
+        for (int k = 0; k < 8 && ox0 + k < ow; ++k) p[k] = (uint8_t)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xffu);
+      }
+    }
+  }
+}
+
 // Scharr: one thread per pixel pair; loads go through L1.  Not on the hot path
 // (the LK and refinement kernels derive gradients on the fly from the u8 levels);
 // exported so the derivative planes themselves can be checked bit-exactly.
@@ -149,6 +268,20 @@ extern "C" int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, in
   int ow = (w + 1) / 2, oh = (h + 1) / 2;
   int vec_ok = ((reinterpret_cast<uintptr_t>(d_src) & 15) == 0) && ((src_pitch & 15) == 0) && ((src_stride & 15) == 0) &&
                ((reinterpret_cast<uintptr_t>(d_dst) & 7) == 0) && ((dst_stride & 7) == 0);
+  // streaming kernel: 16 B aligned rows and w % 16 == 0 (every pyramid level of 1080p / VGA); else the tiled kernel
+  const bool stream_ok = vec_ok && ((dst_pitch & 7) == 0) && (w & 15) == 0 && w >= 16 && h >= 4;
+  if (stream_ok) {
+    int col_blocks = (ow + 255) / 256, strips = (oh + PF_STRIP - 1) / PF_STRIP;
+    int64_t total_warps = (int64_t)batch * strips * col_blocks;
+    int64_t blocks = (total_warps + PF_WARPS - 1) / PF_WARPS;
+    if (blocks <= 0x7fffffffLL) {
+      pyr_down_stream_kernel<<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(d_src, w, h, src_pitch, src_stride, d_dst, ow, oh,
+                                                                               dst_pitch, dst_stride, col_blocks, strips,
+                                                                               total_warps);
+      AGT_LAUNCH_CHECK(ctx);
+      return AGT_OK;
+    }
+  }
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     dim3 grid((ow + PD_OW - 1) / PD_OW, (oh + PD_OH - 1) / PD_OH, nb);

@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the AprilGroup tracking hot path (BASELINE.json metric: refined poses/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...    # CPU arm: the oracle on the host cores
+
+Workload (BASELINE.json configs[1]): batched dense pose refinement of 4096 independent
+synthetic 1080p frames per GPU (12-tag dodecahedron, 20 172 surface samples), one
+hypothesis per frame, initial pose = truth + N(0, 0.01 rad) + N(0, 0.5 mm).  One step =
+build the Gaussian pyramid of every frame (K1) + refine every frame (K4); frames are
+resident in HBM for ``value`` and in pinned host memory for ``e2e`` (which goes through
+the host-buffer C-ABI entry point agt_refine_host: H2D of every frame, D2H of every pose).
+Other workloads of BASELINE.json (--workload lk / multihyp) are secondary lines.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from accurate_aprilgroup_tracking_b200 import synth  # noqa: E402
+
+CAM = synth.CAMERA_1080P
+BYTES_PER_SAMPLE_EVAL = 36          # 16 B model record + 4 B intensity taps + 16 B gradient taps
+BYTES_PER_POSE_FIXED = 156
+LK_BYTES_PER_CORNER = 5008
+PYR_BYTES_PER_1080P = 2754000
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_poses(n: int, seed: int):
+    rng = np.random.default_rng(seed)
+    truth = np.array([synth.random_pose(rng) for _ in range(n)])
+    init = truth + np.concatenate([rng.normal(0, 0.01, (n, 3)), rng.normal(0, 0.0005, (n, 3))], axis=1)
+    return truth, init
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle (there is no reference implementation of dense refinement, see oracle/)
+# ------------------------------------------------------------------------------------------
+def _cpu_refine_one(args):
+    frame, init = args
+    import cv2
+    from oracle import dpr_oracle, lk_oracle
+    cv2.setNumThreads(1)
+    model = _cpu_refine_one.model
+    t0 = time.perf_counter()
+    pyr = lk_oracle.pyramid_cv(frame)
+    out = dpr_oracle.refine(pyr, model, CAM.mtx, init)
+    return time.perf_counter() - t0, out["pose"], out["evals"]
+
+
+def _cpu_worker_init():
+    from oracle import dpr_oracle
+    s, tg, n, c = synth.surface_model()
+    _cpu_refine_one.model = dpr_oracle.Model(s, tg, n, c, synth.model_pitch())
+
+
+def cpu_refine(frames: np.ndarray, init: np.ndarray, workers: int):
+    """Refine frames with the oracle on `workers` processes; returns (wall seconds, poses)."""
+    jobs = [(frames[i], init[i]) for i in range(len(frames))]
+    if workers <= 1:
+        _cpu_worker_init()
+        t0 = time.perf_counter()
+        res = [_cpu_refine_one(j) for j in jobs]
+        return time.perf_counter() - t0, np.array([r[1] for r in res])
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers, initializer=_cpu_worker_init) as pool:
+        pool.map(_cpu_refine_one, jobs[:workers])                  # warm the workers (imports, model)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_refine_one, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    return wall, np.array([r[1] for r in res])
+
+
+def sample_frames_for_cpu(n: int, seed: int):
+    """Frames for the CPU arm: rendered by the CUDA generator when a GPU is visible (same
+    inputs as the GPU arm), else by the numpy specification of the same renderer."""
+    truth, init = make_poses(n, seed)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        from accurate_aprilgroup_tracking_b200.context import AgtContext
+        ctx = AgtContext(0, CAM.mtx, None)
+        pyr = ctx.alloc_pyramid(n, CAM.width, CAM.height, 1)
+        ctx.render(pyr, truth, np.arange(n) + seed)
+        frames = pyr.frames.cpu().numpy()
+        ctx.close()
+    else:
+        frames = np.stack([synth.render(truth[i], CAM, seed + i) for i in range(n)])
+    return frames, truth, init
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    per_step = max(workers * 2, 16)
+    n = per_step
+    frames, truth, init = sample_frames_for_cpu(n, 2000)
+    times = []
+    for it in range(args.warmup + args.steps):
+        wall, _ = cpu_refine(frames, init, workers)
+        if it >= args.warmup:
+            times.append(wall)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": "refined poses/sec", "value": value, "unit": "poses/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched dense pose refinement, 1080p, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
+                   "frames_per_step": n, "note": "CPU oracle (numpy/OpenCV pyramid + LM); no reference code exists for this stage"},
+        "cpu_baseline": {"value": value, "unit": "poses/s", "cores": workers, "kind": "port",
+                         "sample": f"{n} frames per step, {workers} processes, cv2.pyrDown pyramid + oracle/dpr_oracle.py"},
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    from accurate_aprilgroup_tracking_b200.cv_compat import HostContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the tracking path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B = args.frames
+    ctx = AgtContext(local, CAM.mtx, None)
+    ctx.set_synthetic_model()
+    truth, init = make_poses(B, 2000 + 7919 * rank)
+    pyr = ctx.alloc_pyramid(B, CAM.width, CAM.height, 4)
+    for b0 in range(0, B, 512):                                   # synthetic frames, generated on device
+        nb = min(512, B - b0)
+        ctx.render(pyr, truth[b0:b0 + nb], np.arange(b0, b0 + nb) + 2000 + 7919 * rank, offset=b0, batch=nb)
+    d_init = torch.as_tensor(init, dtype=torch.float64, device=ctx.tdev).reshape(B, 1, 6)
+    gathered = torch.empty((world * B, 6), dtype=torch.float64, device=ctx.tdev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.build_pyramid(pyr)
+        res = ctx.refine(pyr, d_init, 1)
+        if world > 1:                                             # the only collective: gather final poses
+            dist.all_gather_into_tensor(gathered, res["pose"].reshape(B, 6))
+        return res
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # sampled from the warm-up on, so short timed regions still see clocks under load
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    l0 = ctx.launch_count()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_begin.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        ctx.build_pyramid(pyr)
+        ev[k][1].record()
+        res = ctx.refine(pyr, d_init, 1)
+        ev[k][2].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res["pose"].reshape(B, 6))
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=ctx.tdev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    pyr_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    dpr_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+
+    # parity guard on the measured batch: the refined poses must sit near the truth they were rendered from
+    pose = res["pose"].reshape(B, 6).cpu().numpy()
+    evals = res["evals"].reshape(B).cpu().numpy().astype(np.int64)
+    nvalid = res["n_valid"].reshape(B).cpu().numpy().astype(np.int64)
+    status = res["status"].reshape(B).cpu().numpy()
+    dt = np.linalg.norm(pose[:, 3:] - truth[:, 3:], axis=1)
+    algo_bytes = float((BYTES_PER_SAMPLE_EVAL * nvalid * evals).sum() + BYTES_PER_POSE_FIXED * B)
+    peak, peak_kind = measured_peaks()
+    achieved = algo_bytes / (dpr_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- e2e through the host-buffer C-ABI entry point (rank 0 device; every rank would do the same) ----
+    e2e = None
+    if not args.no_e2e:
+        hctx = HostContext(local)
+        s, tg, n, c = synth.surface_model()
+        hctx.set_model(s, tg, n, c, synth.model_pitch())
+        host_frames = torch.empty((B, CAM.height, CAM.width), dtype=torch.uint8, pin_memory=True)
+        host_frames.copy_(pyr.frames)
+        torch.cuda.synchronize()
+        hf = host_frames.numpy()
+        e2e_steps = max(2, min(args.steps, 3))
+        out = hctx.refine_poses(hf, init, CAM.mtx)                  # warm-up (allocates device staging)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = hctx.refine_poses(hf, init, CAM.mtx)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        same = float(np.abs(out["pose"].reshape(B, 6) - pose).max())
+        e2e = {"value": B * world / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": int(B * CAM.width * CAM.height + B * 48),
+               "d2h_bytes_per_step": int(B * (48 + 4 + 4 + 4 + 1)), "ms_per_step": 1e3 * e2e_s,
+               "max_abs_diff_vs_device_path": same,
+               "note": "rank-0 measurement through agt_refine_host with pinned host frames; scaled by n_gpus (ranks are independent)"}
+        hctx.close()
+        del host_frames
+
+    # ---- CPU baseline on a bounded sample of the same frames (rank 0, one core) ----
+    cpu = None
+    if not args.no_cpu:
+        ns = args.cpu_sample
+        frames_s = pyr.frames[:ns].cpu().numpy()
+        wall, cpu_pose = cpu_refine(frames_s, init[:ns], 1)
+        dr = [2 * math.asin(min(1.0, 0.5 * np.linalg.norm(synth.rodrigues(cpu_pose[i, :3]) - synth.rodrigues(pose[i, :3]))))
+              for i in range(ns)]
+        cpu = {"value": ns / wall, "unit": "poses/s", "cores": 1, "kind": "port",
+               "sample": f"first {ns} frames of the batch: cv2.pyrDown pyramid + oracle/dpr_oracle.py (numpy, float64), 1 process",
+               "max_rot_diff_vs_gpu_rad": float(max(dr)),
+               "max_trans_diff_vs_gpu_m": float(np.abs(cpu_pose[:, 3:] - pose[:ns, 3:]).max())}
+
+    value = B * world * args.steps / (elapsed_ms * 1e-3)
+    line = {
+        "metric": "refined poses/sec", "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batched dense pose refinement: 1080p frames, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
+                   "frames_per_gpu": B, "step": "K1 pyramid (3 pyrDown levels) + K4 LM refinement to convergence",
+                   "l2": "inputs (%.1f GB of frames per GPU) are larger than L2; no flush needed" % (B * CAM.width * CAM.height / 1e9),
+                   "parallelism": f"frames sharded over {world} GPU(s), no collective on the path; NCCL all-gather of final poses"},
+        "gpu_launches": int(launches),
+        "kernel_ms": {"pyramid": pyr_ms, "dense_refinement": dpr_ms},
+        "lm": {"mean_evals": float(evals.mean()), "max_evals": int(evals.max()), "mean_samples": float(nvalid.mean()),
+               "converged_frac": float((status == 1).mean()), "median_trans_err_vs_truth_m": float(np.median(dt))},
+        "roofline": {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_kind": peak_kind,
+                     "note": "algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); the kernel keeps "
+                             "the ROI in shared memory, so DRAM traffic is far below this figure (see profiles/)"},
+        "pyramid_roofline": {"achieved": PYR_BYTES_PER_1080P * B / (pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": PYR_BYTES_PER_1080P * B / (pyr_ms * 1e-3) / 1e9 / peak},
+        "clocks": clocks,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=96)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
