@@ -130,40 +130,56 @@ constexpr int PF_STRIP = 32;
 
 struct RowWords { uint32_t w[6]; };   // w[0] = left halo, w[1..4] = own 16 bytes, w[5] = right halo
 
-// Issue the global loads of one input row; nothing here depends on the loaded values, so several
-// rows can be in flight per warp before expand_row() consumes them.  The kernel is only used for
-// w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly at w; the
-// reflect-101 halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from one
-// aligned word and a byte permute - no per-byte border code on the streaming path.
+// Per-lane, loop-invariant description of what a lane loads from every input row.  The kernel is
+// only used for w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly
+// at w; the reflect-101 halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from
+// one aligned word and a byte permute.  Loads (raw_row) and permutes/shuffles (expand_row) are
+// split so that nothing consumes a loaded value while later rows are still being requested.
+struct LanePlan {
+  int main_off;        // byte offset of the 16-byte load, or of the 4-byte reflect source
+  int edge_off;        // byte offset of the halo word lanes 0 / 31 fetch themselves
+  uint32_t main_sel;   // byte_perm selector applied to word 0 (identity unless reflecting)
+  uint32_t edge_sel;
+  bool main16, main4, edge;
+};
 struct RawRow { uint4 v; uint32_t edge; };   // edge = left halo for lane 0, right halo for lane 31
 
-__device__ __forceinline__ uint32_t right_reflect_word(const uint8_t* __restrict__ row, int w) {
-  return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(row + w - 4)), 0u, 0x4412);   // (p[w-2], p[w-3], 0, 0)
+__device__ __forceinline__ LanePlan make_plan(int ix0, int w, int lane) {
+  LanePlan p;
+  p.main16 = ix0 + 16 <= w;
+  p.main4 = ix0 == w;                         // first lane past the right border: (p[w-2], p[w-3], -, -)
+  p.main_off = p.main16 ? ix0 : w - 4;
+  p.main_sel = p.main4 ? 0x4412u : 0x3210u;
+  p.edge = false; p.edge_off = 0; p.edge_sel = 0x3210u;
+  if (lane == 0) {
+    p.edge = true;
+    if (ix0 >= 4) p.edge_off = ix0 - 4; else { p.edge_off = 0; p.edge_sel = 0x1244u; }   // (-, -, p[2], p[1])
+  } else if (lane == 31) {
+    if (ix0 + 20 <= w) { p.edge = true; p.edge_off = ix0 + 16; }
+    else if (ix0 + 16 == w) { p.edge = true; p.edge_off = w - 4; p.edge_sel = 0x4412u; }
+  }
+  return p;
 }
 
-__device__ __forceinline__ RawRow raw_row(const uint8_t* __restrict__ row, int ix0, int w, int lane) {
+__device__ __forceinline__ RawRow raw_row(const uint8_t* __restrict__ row, const LanePlan& p) {
   RawRow r;
   r.v = make_uint4(0, 0, 0, 0);
   r.edge = 0;
-  if (ix0 + 16 <= w) r.v = __ldg(reinterpret_cast<const uint4*>(row + ix0));
-  else if (ix0 == w) r.v.x = right_reflect_word(row, w);
-  if (lane == 0)
-    r.edge = ix0 >= 4 ? __ldg(reinterpret_cast<const uint32_t*>(row + ix0 - 4))
-                      : __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(row)), 0u, 0x1244);   // (0, 0, p[2], p[1])
-  if (lane == 31) {
-    if (ix0 + 20 <= w) r.edge = __ldg(reinterpret_cast<const uint32_t*>(row + ix0 + 16));
-    else if (ix0 + 16 == w) r.edge = right_reflect_word(row, w);
-  }
+  if (p.main16) r.v = __ldg(reinterpret_cast<const uint4*>(row + p.main_off));
+  if (p.main4) r.v.x = __ldg(reinterpret_cast<const uint32_t*>(row + p.main_off));
+  if (p.edge) r.edge = __ldg(reinterpret_cast<const uint32_t*>(row + p.edge_off));
   return r;
 }
 
-__device__ __forceinline__ RowWords expand_row(const RawRow& q, int lane) {
+__device__ __forceinline__ RowWords expand_row(const RawRow& q, const LanePlan& p, int lane) {
   RowWords r;
-  r.w[1] = q.v.x; r.w[2] = q.v.y; r.w[3] = q.v.z; r.w[4] = q.v.w;
+  r.w[1] = __byte_perm(q.v.x, 0u, p.main_sel);
+  r.w[2] = q.v.y; r.w[3] = q.v.z; r.w[4] = q.v.w;
   uint32_t left = __shfl_up_sync(0xffffffffu, q.v.w, 1);
-  uint32_t right = __shfl_down_sync(0xffffffffu, q.v.x, 1);
-  r.w[0] = lane == 0 ? q.edge : left;
-  r.w[5] = lane == 31 ? q.edge : right;
+  uint32_t right = __shfl_down_sync(0xffffffffu, r.w[1], 1);
+  uint32_t edge = __byte_perm(q.edge, 0u, p.edge_sel);
+  r.w[0] = lane == 0 ? edge : left;
+  r.w[5] = lane == 31 ? edge : right;
   return r;
 }
 
@@ -197,24 +213,25 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
 
   // single reflection is enough: rows 2*oy-2 .. 2*oy+2 overshoot by at most 2 and h >= 4
   auto row_ptr = [&](int r) { int rr = r < 0 ? -r : (r >= h ? 2 * h - 2 - r : r); return img + (int64_t)rr * spitch; };
+  const LanePlan plan = make_plan(ix0, w, lane);
   uint32_t a[4], b[4], c[4], d[4], e[4];
-  RawRow q0 = raw_row(row_ptr(2 * oy0 - 2), ix0, w, lane);
-  RawRow q1 = raw_row(row_ptr(2 * oy0 - 1), ix0, w, lane);
-  RawRow q2 = raw_row(row_ptr(2 * oy0), ix0, w, lane);
+  RawRow q0 = raw_row(row_ptr(2 * oy0 - 2), plan);
+  RawRow q1 = raw_row(row_ptr(2 * oy0 - 1), plan);
+  RawRow q2 = raw_row(row_ptr(2 * oy0), plan);
   // two output rows (four input rows) of loads stay in flight ahead of the arithmetic
-  RawRow n0 = raw_row(row_ptr(2 * oy0 + 1), ix0, w, lane);
-  RawRow n1 = raw_row(row_ptr(2 * oy0 + 2), ix0, w, lane);
-  RawRow n2 = raw_row(row_ptr(2 * oy0 + 3), ix0, w, lane);
-  RawRow n3 = raw_row(row_ptr(2 * oy0 + 4), ix0, w, lane);
-  hsum(expand_row(q0, lane), a); hsum(expand_row(q1, lane), b); hsum(expand_row(q2, lane), c);
+  RawRow n0 = raw_row(row_ptr(2 * oy0 + 1), plan);
+  RawRow n1 = raw_row(row_ptr(2 * oy0 + 2), plan);
+  RawRow n2 = raw_row(row_ptr(2 * oy0 + 3), plan);
+  RawRow n3 = raw_row(row_ptr(2 * oy0 + 4), plan);
+  hsum(expand_row(q0, plan, lane), a); hsum(expand_row(q1, plan, lane), b); hsum(expand_row(q2, plan, lane), c);
   for (int oy = oy0; oy < oy1; ++oy) {
     RawRow c0 = n0, c1 = n1;
     n0 = n2; n1 = n3;
     if (oy + 2 < oy1) {
-      n2 = raw_row(row_ptr(2 * oy + 5), ix0, w, lane);
-      n3 = raw_row(row_ptr(2 * oy + 6), ix0, w, lane);
+      n2 = raw_row(row_ptr(2 * oy + 5), plan);
+      n3 = raw_row(row_ptr(2 * oy + 6), plan);
     }
-    hsum(expand_row(c0, lane), d); hsum(expand_row(c1, lane), e);
+    hsum(expand_row(c0, plan, lane), d); hsum(expand_row(c1, plan, lane), e);
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
