@@ -168,6 +168,13 @@ class AgtContext:
                                     self._p(err), b, p))
         return out, st, err
 
+    def lk_merge(self, tracked, status, prev_valid, img_pts, valid, n_tags):
+        """In place: re-admit fully tracked tags into img_pts/valid for frames with < 2 detected tags."""
+        b, p = int(img_pts.shape[0]), int(img_pts.shape[1])
+        self._use_current_stream()
+        self._check(self.lib.agt_lk_merge(self.h, self._p(tracked), self._p(status), self._p(prev_valid), self._p(img_pts),
+                                          self._p(valid), self._p(n_tags), b, p))
+
     # -- K3 ---------------------------------------------------------------------------
     def pnp(self, obj_pts, img_pts, valid=None, guess=None, use_guess=None):
         """obj [P,3] f32 shared, img [B,P,2] f32, valid [B,P] u8, guess [B,6] f64, use_guess [B] u8
@@ -226,8 +233,8 @@ class AgtContext:
         return acc, flag
 
     # -- K4 ---------------------------------------------------------------------------
-    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
-        """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status)."""
+    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None):
+        """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status); mask [B] u8 skips frames."""
         t = self.torch
         b = int(pyr.batch if batch is None else batch)
         ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
@@ -237,7 +244,8 @@ class AgtContext:
         ev = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
         st = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
         self._use_current_stream()
-        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(pose), self._p(cost),
+        msk = self._dev(mask, t.uint8) if mask is not None else None
+        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(pose), self._p(cost),
                                         self._p(nv), self._p(ev), self._p(st), b))
         return {"pose": pose, "cost": cost, "n_valid": nv, "evals": ev, "status": st}
 

@@ -357,7 +357,7 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
     AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
     if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
     int64_t j0 = (int64_t)b0 * n_hyp;
-    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp,
+    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,
                          reinterpret_cast<double*>(dr + o_pose) + j0 * 6, reinterpret_cast<float*>(dr + o_cost) + j0,
                          reinterpret_cast<int32_t*>(dr + o_nv) + j0, reinterpret_cast<int32_t*>(dr + o_ev) + j0,
                          dr + o_st + j0, nb)))

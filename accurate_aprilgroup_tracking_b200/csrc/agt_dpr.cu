@@ -27,7 +27,7 @@ namespace {
 constexpr int DPR_THREADS = 256;
 constexpr int DPR_WARPS = DPR_THREADS / 32;
 constexpr int TILE_ROWS = 272;
-constexpr int TILE_PITCH = 288;            // 272 + 16 B alignment slack
+constexpr int TILE_PITCH = 288;            // 272 + 16 B alignment slack; 2 CTAs of 76.5 KB per SM
 constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH + 16;   // +16: the unaligned fetch reads one word past its window
 constexpr int NSUM = 28;                   // 21 H + 6 b + (cost kept separately in double) + count
 constexpr double COS_VISIBLE = 0.25881904510252074;   // cos 75 deg
@@ -70,6 +70,9 @@ __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
   return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
 }
 
+// exact int -> float for |i| < 2^22 on the integer + FP32 add pipes (I2F runs on the quarter-rate XU pipe)
+__device__ __forceinline__ float i2f_small(int i) { return __int_as_float(i + 0x4B400000) - 12582912.f; }
+
 __device__ __forceinline__ int dp4(uint32_t px, int coef) {
   int d;
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(coef), "r"(0));
@@ -82,15 +85,25 @@ constexpr int C_DX1 = (int)0x0100FF00;   // ( 0,-1, 0, 1)
 constexpr int C_SM0 = (int)0x00030A03;   // ( 3,10, 3, 0)
 constexpr int C_SM1 = (int)0x030A0300;   // ( 0, 3,10, 3)
 
-__global__ void __launch_bounds__(DPR_THREADS)
+__global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
-           const double* __restrict__ init, int n_hyp, double* __restrict__ pose_out, float* __restrict__ cost_out,
+           const double* __restrict__ init, int n_hyp, const uint8_t* __restrict__ mask, double* __restrict__ pose_out, float* __restrict__ cost_out,
            int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out) {
   extern __shared__ __align__(16) uint8_t s_tile[];
   __shared__ DprShared S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t job = blockIdx.x;
   const int64_t frame = job / n_hyp;
+  if (mask != nullptr && mask[frame] == 0) {          // skipped frame: pass the pose through
+    if (tid < 6) pose_out[job * 6 + tid] = init[job * 6 + tid];
+    if (tid == 0) {
+      if (cost_out) cost_out[job] = 0.f;
+      if (nvalid_out) nvalid_out[job] = 0;
+      if (evals_out) evals_out[job] = 0;
+      if (status_out) status_out[job] = AGT_DPR_NONE;
+    }
+    return;
+  }
 
   double* const Rc = S.Rc; double* const tc = S.tc; double* const Hc = S.Hc; double* const bc = S.bc;
   double* const Rt = S.Rt; double* const tt = S.tt; double* const dstep = S.dstep;
@@ -198,28 +211,50 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     for (int k = 0; k < 27; ++k) acc[k] = 0.f;
     double cost = 0.0;
     int cnt = 0;
+    // rotation / translation of the trial pose: float64 copies for the projection, float32 for the Jacobian
+    const float R0 = S.R[0], R1 = S.R[1], R2 = S.R[2], R3 = S.R[3], R4 = S.R[4], R5 = S.R[5], R6 = S.R[6], R7 = S.R[7],
+                R8 = S.R[8], t0 = S.t[0], t1 = S.t[1];
     int seg = 0;
+    // software pipeline: the model record of the next sample is requested before this one is consumed
+    float4 sm_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < n_act_samples) {
+      while (tid >= S.act_prefix[seg + 1]) ++seg;
+      sm_next = __ldg(&samples[S.act_begin[seg] + (tid - S.act_prefix[seg])]);
+    }
     for (int j = tid; j < n_act_samples; j += DPR_THREADS) {
-      while (j >= S.act_prefix[seg + 1]) ++seg;
-      const float4 sm = __ldg(&samples[S.act_begin[seg] + (j - S.act_prefix[seg])]);
+      const float4 sm = sm_next;
+      const int jn = j + DPR_THREADS;
+      if (jn < n_act_samples) {
+        while (jn >= S.act_prefix[seg + 1]) ++seg;
+        sm_next = __ldg(&samples[S.act_begin[seg] + (jn - S.act_prefix[seg])]);
+      }
       // Projection in float64: the accept/reject decisions of the LM loop compare costs that differ by ~1e-6
       // relative near convergence; float32 pixel coordinates (ulp 6e-5 px at 1080p) add ~1e-6 of noise to the
       // cost and flip 20 % of those decisions, float64 leaves 0.2 % (profiles/r01_dpr_precision_sweep.log).
       const double sx = sm.x, sy = sm.y, sz = sm.z;
-      const double dYx = S.Rd[0] * sx + S.Rd[1] * sy + S.Rd[2] * sz;
-      const double dYy = S.Rd[3] * sx + S.Rd[4] * sy + S.Rd[5] * sz;
-      const double dYz = S.Rd[6] * sx + S.Rd[7] * sy + S.Rd[8] * sz;
-      const double dX = dYx + S.td[0], dY = dYy + S.td[1], dZ = dYz + S.td[2];
+      // (the float64 pose is read from shared memory with broadcast loads: 24 registers less per thread)
+      const double dX = S.Rd[0] * sx + S.Rd[1] * sy + S.Rd[2] * sz + S.td[0];
+      const double dY = S.Rd[3] * sx + S.Rd[4] * sy + S.Rd[5] * sz + S.td[1];
+      const double dZ = S.Rd[6] * sx + S.Rd[7] * sy + S.Rd[8] * sz + S.td[2];
       if (!(dZ > 1e-6)) continue;
-      double r0 = (double)(1.f / (float)dZ);          // MUFU.RCP seed + two Newton steps
+      float iz;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dZ));       // MUFU.RCP: Jacobian + Newton seed
+      double r0 = (double)iz;
       r0 = r0 * (2.0 - dZ * r0);
       r0 = r0 * (2.0 - dZ * r0);
       const double ul = (S.fxs * dX) * r0 + S.ubase, vl = (S.fys * dY) * r0 + S.vbase;
-      const double fxl = floor(ul), fyl = floor(vl);
-      if (!(fxl >= 1.0 && fxl <= (double)(lw - 3) && fyl >= 1.0 && fyl <= (double)(lh - 3))) continue;
-      const int x0 = (int)fxl, y0 = (int)fyl;
-      const float a = (float)(ul - fxl), b = (float)(vl - fyl);
-      const float Yx = (float)dYx, Yy = (float)dYy, Yz = (float)dYz, X = (float)dX, Y = (float)dY, iz = (float)r0;
+      // valid <=> 1 <= floor(ul) <= lw-3  <=>  1 <= ul < lw-2   (NaN fails both)
+      if (!(ul >= 1.0 && ul < (double)(lw - 2) && vl >= 1.0 && vl < (double)(lh - 2))) continue;
+      // floor + fraction without conversions: adding 2^52+2^51 rounding down leaves floor(ul) in the low mantissa word
+      const double kMagic = 6755399441055744.0;
+      const double tu = __dadd_rd(ul, kMagic), tv = __dadd_rd(vl, kMagic);
+      const int x0 = __double2loint(tu), y0 = __double2loint(tv);
+      const float a = (float)(ul - (tu - kMagic)), b = (float)(vl - (tv - kMagic));
+      // float32 copies for the Jacobian (rounding of these only perturbs the LM step, not the cost)
+      const float Yx = R0 * sm.x + R1 * sm.y + R2 * sm.z;
+      const float Yy = R3 * sm.x + R4 * sm.y + R5 * sm.z;
+      const float Yz = R6 * sm.x + R7 * sm.y + R8 * sm.z;
+      const float X = Yx + t0, Y = Yy + t1;
       // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
       uint32_t row[4];
       const int lx = x0 - 1 - tx0, ly = y0 - 1 - ty0;
@@ -239,12 +274,12 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
         s0[r] = dp4(row[r], C_SM0);  s1[r] = dp4(row[r], C_SM1);
       }
       // Scharr at (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1)
-      const float gx00 = (float)(3 * (dx0[0] + dx0[2]) + 10 * dx0[1]), gx01 = (float)(3 * (dx1[0] + dx1[2]) + 10 * dx1[1]);
-      const float gx10 = (float)(3 * (dx0[1] + dx0[3]) + 10 * dx0[2]), gx11 = (float)(3 * (dx1[1] + dx1[3]) + 10 * dx1[2]);
-      const float gy00 = (float)(s0[2] - s0[0]), gy01 = (float)(s1[2] - s1[0]);
-      const float gy10 = (float)(s0[3] - s0[1]), gy11 = (float)(s1[3] - s1[1]);
-      const float i00 = (float)((row[1] >> 8) & 0xff), i01 = (float)((row[1] >> 16) & 0xff);
-      const float i10 = (float)((row[2] >> 8) & 0xff), i11 = (float)((row[2] >> 16) & 0xff);
+      const float gx00 = i2f_small(3 * (dx0[0] + dx0[2]) + 10 * dx0[1]), gx01 = i2f_small(3 * (dx1[0] + dx1[2]) + 10 * dx1[1]);
+      const float gx10 = i2f_small(3 * (dx0[1] + dx0[3]) + 10 * dx0[2]), gx11 = i2f_small(3 * (dx1[1] + dx1[3]) + 10 * dx1[2]);
+      const float gy00 = i2f_small(s0[2] - s0[0]), gy01 = i2f_small(s1[2] - s1[0]);
+      const float gy10 = i2f_small(s0[3] - s0[1]), gy11 = i2f_small(s1[3] - s1[1]);
+      const float i00 = i2f_small((row[1] >> 8) & 0xff), i01 = i2f_small((row[1] >> 16) & 0xff);
+      const float i10 = i2f_small((row[2] >> 8) & 0xff), i11 = i2f_small((row[2] >> 16) & 0xff);
       const float w11 = a * b, w01 = a - w11, w10 = b - w11, w00 = 1.f - a - b + w11;
       const float I = w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11;
       const float Gx = (w00 * gx00 + w01 * gx01 + w10 * gx10 + w11 * gx11) * gsc;
@@ -386,8 +421,8 @@ __global__ void select_best_kernel(const double* __restrict__ pose, const float*
 
 }  // namespace
 
-extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, double* d_pose,
-                          float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch) {
+extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+                          double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine: camera and surface model must be set");
   if (!pyr || !d_init || !d_pose || n_hyp < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad arguments");
@@ -401,8 +436,9 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
     AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
     attr_set[ctx->device & 63] = true;
   }
+  // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower
   dpr_kernel<<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
-                                                                      n_hyp, d_pose, d_cost, d_n_valid, d_evals, d_status);
+                                                                      n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

@@ -231,7 +231,52 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
   }
 }
 
+// Stage-2 integration: one thread per (frame, tag).
+__global__ void lk_merge_kernel(const float* __restrict__ tracked, const uint8_t* __restrict__ status,
+                                const uint8_t* __restrict__ prev_valid, float* __restrict__ img, uint8_t* __restrict__ valid,
+                                int32_t* __restrict__ n_tags, int batch, int tags) {
+  int f = blockIdx.x;
+  if (f >= batch) return;
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  const int need = n_tags[f] < 2;
+  int t = threadIdx.x;
+  if (t < tags) {
+    int64_t base = ((int64_t)f * tags + t) * 4;
+    bool det = valid[base] && valid[base + 1] && valid[base + 2] && valid[base + 3];
+    if (!det && need) {
+      bool ok = true;
+      for (int j = 0; j < 4; ++j) ok = ok && prev_valid[base + j] != 0 && status[base + j] == 1;
+      if (ok) {
+        for (int j = 0; j < 4; ++j) {
+          img[(base + j) * 2] = tracked[(base + j) * 2];
+          img[(base + j) * 2 + 1] = tracked[(base + j) * 2 + 1];
+          valid[base + j] = 1;
+        }
+        det = true;
+      }
+    }
+    if (det) atomicAdd(&s_cnt, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) n_tags[f] = s_cnt;
+}
+
 }  // namespace
+
+extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
+                            float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int batch, int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_tracked_pts || !d_status || !d_prev_valid || !d_img_pts || !d_valid || !d_n_tags || batch < 0 || n_pts < 4 ||
+      (n_pts & 3) || n_pts > AGT_MAX_POINTS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_merge: bad arguments");
+  if (batch == 0) return AGT_OK;
+  lk_merge_kernel<<<batch, 32, 0, ctx->stream>>>(d_tracked_pts, d_status, d_prev_valid, d_img_pts, d_valid, d_n_tags, batch,
+                                                 n_pts / 4);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
 
 extern "C" int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
                       float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts) {

@@ -102,6 +102,13 @@ int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pit
 int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
            float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts);
 
+/* Stage-2 integration rule: for every frame with fewer than 2 detected tags, re-admit each
+ * tag that was accepted in the previous frame (d_prev_valid) and whose four corners were all tracked
+ * (d_status == 1): its tracked corners are copied into d_img_pts and its d_valid entries set.
+ * d_n_tags[batch] is recomputed (tags with 4 valid corners).  n_pts = 4 * n_tags_total. */
+int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
+                 float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int batch, int n_pts);
+
 /* ---- K3: batched PnP (cv::solvePnP SOLVEPNP_ITERATIVE + reprojection gate) --- */
 /* d_obj_pts[n_pts][3] float32 is shared by the batch (group corners, index
  * 4*tag+corner, detect_pose.py:185-227); d_img_pts[batch][n_pts][2] float32;
@@ -138,9 +145,11 @@ int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const
 /* ---- K4: dense pose refinement (photometric LM; DodecaPen stage 3) ----------- */
 /* d_init[batch][n_hyp][6] -> d_pose[batch][n_hyp][6]; cost = 1/2 sum r^2,
  * n_valid = samples in the final residual, evals = cost/Jacobian evaluations
- * run, status = AGT_DPR_*.  Any output except d_pose may be NULL. */
-int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, double* d_pose,
-               float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch);
+ * run, status = AGT_DPR_*.  Any output except d_pose may be NULL.  d_mask[batch]
+ * (may be NULL) skips frames whose entry is 0: their pose is copied through,
+ * status AGT_DPR_NONE, evals 0. */
+int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+               double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch);
 /* Multi-hypothesis selection: best[b] = argmin_h 2*cost/n_valid (ties -> lowest
  * h); d_best_pose[batch][6] may be NULL. */
 int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,
