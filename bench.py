@@ -343,6 +343,195 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs 3-5); the driver's contract line is --workload dpr
+# ------------------------------------------------------------------------------------------
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the tracking path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, dist, world, rank, local
+
+
+def _timed(torch, dist, world, fn, steps, warmup):
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_lk(args):
+    """Config 3: pyramidal LK, 4 levels, 21x21, 48 corners per frame pair."""
+    torch, dist, world, rank, local = _dist_setup()
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    ctx = AgtContext(local, CAM.mtx, None)
+    B = args.frames
+    traj = np.array([synth.trajectory(3000 + 7919 * rank + i, 2) for i in range(B)])
+    pa, pb = ctx.alloc_pyramid(B, CAM.width, CAM.height, 4), ctx.alloc_pyramid(B, CAM.width, CAM.height, 4)
+    for b0 in range(0, B, 512):
+        nb = min(512, B - b0)
+        ctx.render(pa, traj[b0:b0 + nb, 0], np.arange(nb) + b0, offset=b0, batch=nb)
+        ctx.render(pb, traj[b0:b0 + nb, 1], np.arange(nb) + b0 + 1, offset=b0, batch=nb)
+    ctx.build_pyramid(pa)
+    obj = synth.object_points()
+    pts = torch.as_tensor(np.stack([synth.project(obj, traj[i, 0], CAM) for i in range(B)]).astype(np.float32), device=ctx.tdev)
+    holder = {}
+
+    def step():
+        ctx.build_pyramid(pb)                       # pyramid of the new frames (the previous one is reused)
+        holder["out"] = ctx.lk(pa, pb, pts)
+
+    l0 = ctx.launch_count()
+    ms = _timed(torch, dist, world, step, args.steps, args.warmup)
+    launches = ctx.launch_count() - l0
+    lk_ms = _timed(torch, dist, world, lambda: holder.__setitem__("out", ctx.lk(pa, pb, pts)), args.steps, 3) / args.steps
+    if rank == 0:
+        out, st, err = holder["out"]
+        peak, kind = measured_peaks()
+        corners = B * 48
+        ach = LK_BYTES_PER_CORNER * corners / (lk_ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "tracked corners/sec", "value": corners * world * args.steps / (ms * 1e-3), "unit": "corners/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32", "data": "synthetic",
+            "config": {"workload": "pyramidal LK: 4 levels, 21x21 window, 48 corners per 1080p frame pair", "frame_pairs_per_gpu": B,
+                       "step": "K1 pyramid of the new frames + K2 LK", "l2": "inputs larger than L2"},
+            "gpu_launches": int(launches), "kernel_ms": {"lk": lk_ms}, "tracked_frac": float(st.float().mean()),
+            "roofline": {"bound": "hbm", "kernel": "lk_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_kind": kind, "note": "5008 B per corner (SURVEY.md 8d); latency-bound by design"}}), flush=True)
+
+
+def run_multihyp(args):
+    """Config 4: 64 perturbed hypotheses per frame, LM to convergence, arg-min selection."""
+    torch, dist, world, rank, local = _dist_setup()
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    ctx = AgtContext(local, CAM.mtx, None)
+    ctx.set_synthetic_model()
+    H = 64
+    B = max(1, args.frames // H)
+    rng = np.random.default_rng(4000 + rank)
+    truth = np.array([synth.random_pose(rng) for _ in range(B)])
+    init = truth[:, None, :] + np.concatenate([rng.normal(0, 0.03, (B, H, 3)), rng.normal(0, 0.002, (B, H, 3))], axis=2)
+    pyr = ctx.alloc_pyramid(B, CAM.width, CAM.height, 4)
+    ctx.render(pyr, truth, np.arange(B) + 4000)
+    d_init = torch.as_tensor(init, device=ctx.tdev)
+    holder = {}
+
+    def step():
+        ctx.build_pyramid(pyr)
+        res = ctx.refine(pyr, d_init, H)
+        holder["res"], holder["best"] = res, ctx.select_best(res)
+
+    l0 = ctx.launch_count()
+    ms = _timed(torch, dist, world, step, args.steps, args.warmup)
+    launches = ctx.launch_count() - l0
+    if rank == 0:
+        res, (best, bp) = holder["res"], holder["best"]
+        bp = bp.cpu().numpy()
+        ev, nv = res["evals"].double(), res["n_valid"].double()
+        dt = np.linalg.norm(bp[:, 3:] - truth[:, 3:], axis=1)
+        print(json.dumps({
+            "metric": "refined poses/sec (64 hypotheses per frame)", "value": B * world * args.steps / (ms * 1e-3), "unit": "poses/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "multi-hypothesis dense refinement: 64 inits per 1080p frame (0.03 rad, 2 mm), LM to convergence",
+                       "frames_per_gpu": B, "hypotheses": H},
+            "gpu_launches": int(launches), "hypothesis_refinements_per_s": B * H * world * args.steps / (ms * 1e-3),
+            "lm": {"mean_evals": float(ev.mean()), "median_trans_err_vs_truth_m": float(np.median(dt)),
+                   "algorithmic_GBps": float((BYTES_PER_SAMPLE_EVAL * ev * nv).sum()) * args.steps / (ms * 1e-3) / 1e9}}), flush=True)
+
+
+def run_streams(args):
+    """Config 5: 64 concurrent 1080p streams, full APE + LK + DPR per frame, streams sharded s mod G."""
+    torch, dist, world, rank, local = _dist_setup()
+    from accurate_aprilgroup_tracking_b200 import sharding
+    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector, pack_detections
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    ctx = AgtContext(local, CAM.mtx, None)
+    ctx.set_synthetic_model()
+    S_total, F = args.streams, args.stream_frames
+    mine = sharding.local_streams(S_total, rank, world)
+    S = len(mine)
+    trajs = [synth.trajectory(5000 + s, F) for s in mine]
+    rngs = [np.random.default_rng(5000 + s) for s in mine]
+    bank = ctx.alloc_pyramid(S * F, CAM.width, CAM.height, 1)           # pre-rendered frames [F][S]
+    for f in range(F):
+        ctx.render(bank, np.array([trajs[i][f] for i in range(S)]), np.array([1000 * s + f for s in mine]), offset=f * S, batch=S)
+    det_img, det_valid, det_n = [], [], []
+    for f in range(F):
+        dets = []
+        for i in range(S):
+            d = synth.detections(trajs[i][f], CAM, rngs[i])
+            if (f + 3 * i) % 17 == 16:
+                d = d[:1]                                               # periodic detector dropouts exercise the LK path
+            dets.append(d)
+        a, b, c = pack_detections(dets)
+        det_img.append(torch.as_tensor(a, device=ctx.tdev)); det_valid.append(torch.as_tensor(b, device=ctx.tdev))
+        det_n.append(torch.as_tensor(c, device=ctx.tdev))
+    bank_frames = bank.frames.reshape(F, S, CAM.height, CAM.width)
+    gathered = torch.empty((S_total, 6), dtype=torch.float64, device=ctx.tdev)
+
+    def run_sequence():
+        bpd = BatchedPoseDetector(ctx, S, CAM.width, CAM.height, synth.object_points())
+        acc = 0
+        for f in range(F):
+            bpd.frames.copy_(bank_frames[f])                            # frame ingest (device to device)
+            out = bpd.step(det_img[f], det_valid[f], det_n[f])
+            if world > 1:
+                sharding.gather_stream_poses(out["pose"], S_total)      # NCCL: final poses only
+            acc = out
+        return acc
+
+    run_sequence()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = run_sequence()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.tdev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = ctx.launch_count() - l0
+    pose = out["pose"].cpu().numpy()
+    dt = np.array([np.linalg.norm(pose[i, 3:] - trajs[i][F - 1][3:]) for i in range(S)])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "refined poses/sec (full APE+LK+DPR pipeline)", "value": S_total * F * args.steps / (ms * 1e-3), "unit": "poses/s",
+            "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": "64 concurrent 1080p camera streams, predictor -> PnP / LK fallback -> dense refinement per frame",
+                       "streams": S_total, "frames_per_stream": F, "step": "one pass over all frames of all streams",
+                       "parallelism": f"streams s mod {world} -> GPU; per-frame NCCL all-gather of poses"},
+            "gpu_launches": int(launches), "ms_per_frame_step": ms / args.steps / F,
+            "final_frame_median_trans_err_m": float(np.median(dt)), "accepted_frac_last": float(out["accepted"].float().mean())}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -353,9 +542,18 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="dpr", choices=["dpr", "lk", "multihyp", "streams"])
+    ap.add_argument("--streams", type=int, default=64)
+    ap.add_argument("--stream-frames", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "lk":
+        run_lk(args)
+    elif args.workload == "multihyp":
+        run_multihyp(args)
+    elif args.workload == "streams":
+        run_streams(args)
     else:
         run_gpu(args)
 
