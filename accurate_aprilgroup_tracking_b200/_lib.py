@@ -58,7 +58,7 @@ PROTOTYPES = {
     "agt_project": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_prepare": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_update": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
-    "agt_refine": (_I, [_VP, _PYR, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I]),
+    "agt_refine": (_I, [_VP, _PYR, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I]),
     "agt_lk_merge": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
     "agt_select_best": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I]),
     "agt_render": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _I, _D, _D, _I, _I]),
@@ -67,6 +67,8 @@ PROTOTYPES = {
     "agt_lk_host": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _I, _VP, _VP, _VP]),
     "agt_pyramid_host": (_I, [_VP, _VP, _I, _I, _I, C.POINTER(_VP)]),
     "agt_scharr_host": (_I, [_VP, _VP, _I, _I, _VP]),
+    "agt_set_roi_upload": (_I, [_VP, _I]),
+    "agt_last_h2d_bytes": (_I64, [_VP]),
     "agt_refine_host": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
 }
 

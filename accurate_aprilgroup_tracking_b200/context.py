@@ -243,11 +243,12 @@ class AgtContext:
         nv = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
         ev = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
         st = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
+        left = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
         self._use_current_stream()
         msk = self._dev(mask, t.uint8) if mask is not None else None
         self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(pose), self._p(cost),
-                                        self._p(nv), self._p(ev), self._p(st), b))
-        return {"pose": pose, "cost": cost, "n_valid": nv, "evals": ev, "status": st}
+                                        self._p(nv), self._p(ev), self._p(st), self._p(left), b))
+        return {"pose": pose, "cost": cost, "n_valid": nv, "evals": ev, "status": st, "left_roi": left}
 
     def select_best(self, res):
         t = self.torch

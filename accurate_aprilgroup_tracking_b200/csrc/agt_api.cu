@@ -1,7 +1,10 @@
 // Context lifecycle, configuration and the host-buffer entry points of libagt.so.
 #include <new>
 
-#include "agt_common.cuh"
+#include <stdlib.h>
+#include <chrono>
+
+#include "agt_dpr_plan.cuh"
 
 char g_agt_create_error[512] = "";
 
@@ -90,6 +93,7 @@ extern "C" int agt_create(int device, agt_ctx** out) {
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
   ctx->sm_count = prop.multiProcessorCount;
   ctx->stream = ctx->own_stream;
+  ctx->roi_upload = 1;
   *out = ctx;
   return AGT_OK;
 }
@@ -101,6 +105,7 @@ extern "C" int agt_destroy(agt_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   for (int i = 0; i < 8; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->model.samples) cudaFree(ctx->model.samples);
+  if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -159,6 +164,12 @@ extern "C" int agt_set_model(agt_ctx* ctx, const float* h_samples, const uint8_t
   for (int k = 0; k < n_tags; ++k)
     for (int i = 0; i < 3; ++i) { m.normals[k][i] = h_tag_normals[k * 3 + i]; m.centres[k][i] = h_tag_centres[k * 3 + i]; }
   m.n_samples = n_samples; m.n_tags = n_tags; m.pitch = pitch;
+  m.radius = 0.0;                                  // bounding sphere of the surface samples (about the group origin)
+  for (int i = 0; i < n_samples; ++i) {
+    const float* q = h_samples + 4 * (size_t)i;
+    double r = sqrt((double)q[0] * q[0] + (double)q[1] * q[1] + (double)q[2] * q[2]);
+    if (r > m.radius) m.radius = r;
+  }
   AGT_CUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->model.samples) { AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->model.samples); ctx->model.samples = nullptr; }
   AGT_CUDA(ctx, cudaMalloc(&m.samples, sizeof(float4) * (size_t)n_samples));
@@ -306,6 +317,134 @@ extern "C" int agt_lk_host(agt_ctx* ctx, const uint8_t* h_prev, const uint8_t* h
   return AGT_OK;
 }
 
+// One launch copies the ROI rectangle of every frame of a chunk straight out of pinned (device-mapped) host
+// memory: 4096 cudaMemcpy2DAsync calls cost ~7 us of driver time each, a gather kernel costs one launch and
+// keeps thousands of 16-byte PCIe reads in flight.  rect = (x0, y0, x1, y1, host frame index), x0/x1 % 16 == 0.
+struct agt_roi_rect { int x0, y0, x1, y1, src; };
+
+__global__ void __launch_bounds__(256)
+roi_gather_kernel(const uint8_t* __restrict__ host_frames, int w, int h, const agt_roi_rect* __restrict__ rects,
+                  uint8_t* __restrict__ dst, int64_t dst_pitch, int64_t dst_stride, int n_rects) {
+  // a small persistent grid: the CTAs mostly wait on PCIe reads, so they must not fill the SMs' thread
+  // slots - the pyramid / refinement kernels of the previous chunk run next to them
+  for (int ri = blockIdx.x; ri < n_rects; ri += gridDim.x) {
+  const agt_roi_rect r = rects[ri];
+  const int cw = (r.x1 - r.x0) >> 4, rows = r.y1 - r.y0;
+  if (cw <= 0 || rows <= 0) continue;
+  const uint8_t* src = host_frames + (int64_t)r.src * w * h + (int64_t)r.y0 * w + r.x0;
+  uint8_t* out = dst + (int64_t)ri * dst_stride + (int64_t)r.y0 * dst_pitch + r.x0;
+  const int total = cw * rows;
+  for (int i = threadIdx.x; i < total; i += 4 * blockDim.x) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = i + k * blockDim.x;
+      if (j < total) { int y = j / cw, c = j - y * cw; v[k] = *reinterpret_cast<const uint4*>(src + (int64_t)y * w + 16 * c); }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = i + k * blockDim.x;
+      if (j < total) { int y = j / cw, c = j - y * cw; *reinterpret_cast<uint4*>(out + (int64_t)y * dst_pitch + 16 * c) = v[k]; }
+    }
+  }
+  }
+}
+
+// L0 rectangle the refinement of `frame` can read: union over its hypotheses of the predicted ROI
+// (agt_dpr_plan) scaled to level 0 plus the pyrDown halo.  Returns false if empty.
+static bool roi_rect_l0(const agt_ctx* ctx, const agt_pyramid& one, const double* init, int n_hyp, int* X0, int* Y0, int* X1,
+                        int* Y1) {
+  const int W = one.width[0], H = one.height[0];
+  int x0 = W, y0 = H, x1 = 0, y1 = 0;
+  for (int hyp = 0; hyp < n_hyp; ++hyp) {
+    const double* p = init + hyp * 6;
+    agt_dpr_plan plan = agt_make_dpr_plan(ctx->cam, ctx->model.pitch, ctx->model.radius, p + 3, one.width, one.height, one.levels);
+    if (plan.rx1 <= plan.rx0 || plan.ry1 <= plan.ry0) continue;
+    const int l = plan.level, pad = 2 << l;          // pyrDown halo of the chain down to level l
+    int a = (plan.rx0 << l) - pad, b = (plan.ry0 << l) - pad;
+    int c = ((plan.rx1 - 1) << l) + pad + 1, d = ((plan.ry1 - 1) << l) + pad + 1;
+    x0 = a < x0 ? a : x0; y0 = b < y0 ? b : y0; x1 = c > x1 ? c : x1; y1 = d > y1 ? d : y1;
+  }
+  x0 = (x0 > 0 ? x0 : 0) & ~15; y0 = y0 > 0 ? y0 : 0;
+  x1 = (x1 + 15) & ~15; x1 = x1 < W ? x1 : W; y1 = y1 < H ? y1 : H;
+  *X0 = x0; *Y0 = y0; *X1 = x1; *Y1 = y1;
+  return x1 > x0 && y1 > y0;
+}
+
+extern "C" int agt_set_roi_upload(agt_ctx* ctx, int enable) {
+  if (!ctx) return AGT_ERR_INVALID;
+  ctx->roi_upload = enable ? 1 : 0;
+  return AGT_OK;
+}
+
+extern "C" int64_t agt_last_h2d_bytes(const agt_ctx* ctx) { return ctx ? ctx->last_h2d_bytes : -1; }
+
+// One pass of chunked, double-buffered refinement over the frames listed in `ids` (NULL = 0..count-1).
+// roi != 0 uploads only the rectangle each refinement can touch.
+static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, const int* ids, int count,
+                       int n_hyp, int roi, const double* h_init, uint8_t* dr, size_t o_init, size_t o_pose, size_t o_cost,
+                       size_t o_nv, size_t o_ev, size_t o_st, size_t o_left, int chunk, uint8_t* const buf[2]) {
+  cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
+  agt_pyramid one;
+  layout_pyramid(&one, nullptr, w, h, levels, 1);
+  const bool tight = one.pitch[0] == w;
+  int rc;
+  int n_chunks = (count + chunk - 1) / chunk;
+  for (int c = 0; c < n_chunks; ++c) {
+    int b0 = c * chunk, nb = count - b0 < chunk ? count - b0 : chunk;
+    int s = c & 1;
+    agt_pyramid p;
+    layout_pyramid(&p, buf[s], w, h, levels, chunk);
+    if (c >= 2) AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[s], 0));       // compute on this buffer finished
+    const bool contiguous_ids = ids == nullptr;
+    if (roi && ctx->host_frames_dev && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx->host_frames_dev) & 15) == 0) {
+      // rectangles of this chunk -> device, then one gather launch on the copy stream
+      agt_roi_rect* hr = ctx->h_rects + b0;        // pinned; one slot per frame of the pass, so the CPU never
+      agt_roi_rect* drc = ctx->d_rects + b0;       // overwrites a list whose asynchronous upload is still pending
+      for (int i = 0; i < nb; ++i) {
+        int f = ids ? ids[b0 + i] : b0 + i;
+        agt_roi_rect r = {0, 0, 0, 0, f};
+        if (roi_rect_l0(ctx, one, h_init + (int64_t)f * n_hyp * 6, n_hyp, &r.x0, &r.y0, &r.x1, &r.y1))
+          ctx->last_h2d_bytes += (int64_t)(r.x1 - r.x0) * (r.y1 - r.y0);
+        else
+          r.x0 = r.x1 = r.y0 = r.y1 = 0;
+        hr[i] = r;
+      }
+      AGT_CUDA(ctx, cudaMemcpyAsync(drc, hr, sizeof(agt_roi_rect) * nb, cudaMemcpyHostToDevice, cp));
+      int gctas = 64;
+      if (const char* e = getenv("AGT_GATHER_CTAS")) { int v = atoi(e); if (v > 0) gctas = v; }
+      roi_gather_kernel<<<nb < gctas ? nb : gctas, 256, 0, cp>>>(ctx->host_frames_dev, w, h, drc, p.data[0], p.pitch[0], p.frame_stride[0], nb);
+      AGT_LAUNCH_CHECK(ctx);
+    } else if (!roi && contiguous_ids && tight) {
+      AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], h_frames + (int64_t)b0 * w * h, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
+      ctx->last_h2d_bytes += (int64_t)nb * w * h;
+    } else {
+      for (int i = 0; i < nb; ++i) {
+        int f = ids ? ids[b0 + i] : b0 + i;
+        const uint8_t* src = h_frames + (int64_t)f * w * h;
+        uint8_t* dst = p.data[0] + (int64_t)i * p.frame_stride[0];
+        int X0 = 0, Y0 = 0, X1 = w, Y1 = h;
+        if (roi && !roi_rect_l0(ctx, one, h_init + (int64_t)f * n_hyp * 6, n_hyp, &X0, &Y0, &X1, &Y1)) continue;
+        AGT_CUDA(ctx, cudaMemcpy2DAsync(dst + (int64_t)Y0 * p.pitch[0] + X0, (size_t)p.pitch[0], src + (int64_t)Y0 * w + X0, (size_t)w,
+                                        (size_t)(X1 - X0), (size_t)(Y1 - Y0), cudaMemcpyHostToDevice, cp));
+        ctx->last_h2d_bytes += (int64_t)(X1 - X0) * (Y1 - Y0);
+      }
+    }
+    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], cp));
+    AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
+    if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
+    // jobs of this chunk are contiguous in the compacted device arrays [b0*n_hyp, (b0+nb)*n_hyp)
+    int64_t j0 = (int64_t)b0 * n_hyp;
+    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,
+                         reinterpret_cast<double*>(dr + o_pose) + j0 * 6, reinterpret_cast<float*>(dr + o_cost) + j0,
+                         reinterpret_cast<int32_t*>(dr + o_nv) + j0, reinterpret_cast<int32_t*>(dr + o_ev) + j0,
+                         dr + o_st + j0, dr + o_left + j0, nb)))
+      return rc;
+    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[s], st));
+  }
+  return AGT_OK;
+}
+
 extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, int batch,
                                const double* h_init, int n_hyp, double* h_pose, float* h_cost, int32_t* h_n_valid,
                                int32_t* h_evals, uint8_t* h_status, int32_t* h_best) {
@@ -313,12 +452,19 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine_host: camera and surface model must be set");
   if (!h_frames || !h_init || !h_pose || w < 1 || h < 1 || levels < 1 || levels > AGT_MAX_LEVELS || batch < 0 || n_hyp < 1)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine_host: bad arguments");
+  ctx->last_h2d_bytes = 0;
   if (batch == 0) return AGT_OK;
   AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool trace = getenv("AGT_TRACE") != nullptr;
+  auto t_start = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   // chunked, double-buffered: H2D of chunk i+1 on the copy stream overlaps pyramid + refinement of chunk i
   agt_pyramid one;
   int64_t per_frame = layout_pyramid(&one, nullptr, w, h, levels, 1);
-  int chunk = (int)((256LL << 20) / per_frame);
+  // chunks of up to 1024 frames (<= 3 GiB per buffer): large enough that one refinement launch fills the GPU
+  int chunk = (int)((3LL << 30) / per_frame);
+  if (chunk > 1024) chunk = 1024;
+  if (const char* e = getenv("AGT_E2E_CHUNK")) { int v = atoi(e); if (v > 0 && v < chunk) chunk = v; }
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   int64_t chunk_bytes = layout_pyramid(&one, nullptr, w, h, levels, chunk);
@@ -330,39 +476,85 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
   uint8_t* dr;
   size_t o_init = 0, o_pose = o_init + align_up(sizeof(double) * 6 * jobs, 256), o_cost = o_pose + align_up(sizeof(double) * 6 * jobs, 256),
          o_nv = o_cost + align_up(sizeof(float) * jobs, 256), o_ev = o_nv + align_up(sizeof(int32_t) * jobs, 256),
-         o_st = o_ev + align_up(sizeof(int32_t) * jobs, 256), o_best = o_st + align_up(jobs, 256),
-         total = o_best + align_up(sizeof(int32_t) * batch, 256);
+         o_st = o_ev + align_up(sizeof(int32_t) * jobs, 256), o_left = o_st + align_up(jobs, 256),
+         o_best = o_left + align_up(jobs, 256), total = o_best + align_up(sizeof(int32_t) * batch, 256);
   if ((rc = agt_scratch(ctx, 2, total, reinterpret_cast<void**>(&dr)))) return rc;
   cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
   AGT_CUDA(ctx, cudaMemcpyAsync(dr + o_init, h_init, sizeof(double) * 6 * jobs, cudaMemcpyHostToDevice, st));
+  ctx->last_h2d_bytes += (int64_t)sizeof(double) * 6 * jobs;
   // the copy stream must not overwrite a buffer an earlier call on `st` may still read
-  AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-  AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[2], 0));
-  const bool tight = one.pitch[0] == w;
-  int n_chunks = (batch + chunk - 1) / chunk;
-  for (int c = 0; c < n_chunks; ++c) {
-    int b0 = c * chunk, nb = batch - b0 < chunk ? batch - b0 : chunk;
-    int s = c & 1;
-    agt_pyramid p;
-    layout_pyramid(&p, buf[s], w, h, levels, chunk);
-    if (c >= 2) AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[s], 0));       // compute on this buffer finished
-    const uint8_t* src = h_frames + (int64_t)b0 * w * h;
-    if (tight) {
-      AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], src, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
-    } else {
-      AGT_CUDA(ctx, cudaMemcpy2DAsync(p.data[0], (size_t)p.pitch[0], src, (size_t)w, (size_t)w, (size_t)nb * h,
-                                      cudaMemcpyHostToDevice, cp));
+  AGT_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+  AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[3], 0));
+  const int roi = ctx->roi_upload && !ctx->cam.has_dist;
+  ctx->host_frames_dev = nullptr;
+  if (roi) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+      ctx->host_frames_dev = static_cast<const uint8_t*>(attr.devicePointer);     // pinned + mapped: gather by kernel
+    else
+      cudaGetLastError();                                                          // pageable: per-frame 2-D copies
+    if (ctx->host_frames_dev) {
+      if (ctx->rect_capacity < batch) {
+        if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
+        ctx->h_rects = nullptr; ctx->rect_capacity = 0;
+        AGT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_rects), sizeof(agt_roi_rect) * (size_t)batch));
+        ctx->rect_capacity = batch;
+      }
+      void* dtmp;
+      if ((rc = agt_scratch(ctx, 4, sizeof(agt_roi_rect) * (size_t)batch, &dtmp))) return rc;
+      ctx->d_rects = static_cast<agt_roi_rect*>(dtmp);
     }
-    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], cp));
-    AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
-    if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
-    int64_t j0 = (int64_t)b0 * n_hyp;
-    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,
-                         reinterpret_cast<double*>(dr + o_pose) + j0 * 6, reinterpret_cast<float*>(dr + o_cost) + j0,
-                         reinterpret_cast<int32_t*>(dr + o_nv) + j0, reinterpret_cast<int32_t*>(dr + o_ev) + j0,
-                         dr + o_st + j0, nb)))
-      return rc;
-    AGT_CUDA(ctx, cudaEventRecord(ctx->ev[s], st));
+  }
+  if ((rc = refine_pass(ctx, h_frames, w, h, levels, nullptr, batch, n_hyp, roi, h_init, dr, o_init, o_pose, o_cost, o_nv, o_ev, o_st,
+                        o_left, chunk, buf)))
+    return rc;
+  if (trace) fprintf(stderr, "[agt] refine_host: first pass enqueued at %.3f ms (chunk %d, roi %d, gather %d)\n", since(), chunk, roi,
+                     ctx->host_frames_dev != nullptr);
+  if (roi) {
+    // frames whose refinement read pixels outside the uploaded rectangle are redone from the whole frame,
+    // so the result never depends on the ROI prediction
+    uint8_t* left = static_cast<uint8_t*>(malloc((size_t)jobs));
+    if (!left) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine_host: out of host memory");
+    cudaError_t e = cudaMemcpyAsync(left, dr + o_left, (size_t)jobs, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { free(left); AGT_FAIL(ctx, AGT_ERR_CUDA, "agt_refine_host: %s", cudaGetErrorString(e)); }
+    int n_redo = 0;
+    int* ids = static_cast<int*>(malloc(sizeof(int) * (size_t)batch));
+    for (int f = 0; f < batch; ++f) {
+      bool any = false;
+      for (int k = 0; k < n_hyp; ++k) any = any || left[(int64_t)f * n_hyp + k];
+      if (any) ids[n_redo++] = f;
+    }
+    free(left);
+    ctx->last_redo_frames = n_redo;
+    if (trace) fprintf(stderr, "[agt] refine_host: first pass done at %.3f ms, %d frames to redo\n", since(), n_redo);
+    if (n_redo > 0) {
+      // compact the initial poses of the redo frames behind the main arrays and scatter the results back
+      uint8_t* dr2;
+      int64_t j2 = (int64_t)n_redo * n_hyp;
+      size_t p_init = 0, p_pose = p_init + align_up(sizeof(double) * 6 * j2, 256), p_cost = p_pose + align_up(sizeof(double) * 6 * j2, 256),
+             p_nv = p_cost + align_up(sizeof(float) * j2, 256), p_ev = p_nv + align_up(sizeof(int32_t) * j2, 256),
+             p_st = p_ev + align_up(sizeof(int32_t) * j2, 256), p_left = p_st + align_up(j2, 256), tot2 = p_left + align_up(j2, 256);
+      if ((rc = agt_scratch(ctx, 3, tot2, reinterpret_cast<void**>(&dr2)))) { free(ids); return rc; }
+      for (int i = 0; i < n_redo; ++i)
+        cudaMemcpyAsync(dr2 + p_init + sizeof(double) * 6 * (size_t)i * n_hyp, h_init + (int64_t)ids[i] * n_hyp * 6,
+                        sizeof(double) * 6 * n_hyp, cudaMemcpyHostToDevice, st);
+      cudaEventRecord(ctx->ev[3], st);
+      cudaStreamWaitEvent(cp, ctx->ev[3], 0);
+      int chunk2 = chunk < n_redo ? chunk : n_redo;
+      rc = refine_pass(ctx, h_frames, w, h, levels, ids, n_redo, n_hyp, 0, h_init, dr2, p_init, p_pose, p_cost, p_nv, p_ev, p_st, p_left,
+                       chunk2, buf);
+      if (rc) { free(ids); return rc; }
+      for (int i = 0; i < n_redo; ++i) {
+        int64_t src = (int64_t)i * n_hyp, dst = (int64_t)ids[i] * n_hyp;
+        cudaMemcpyAsync(dr + o_pose + sizeof(double) * 6 * dst, dr2 + p_pose + sizeof(double) * 6 * src, sizeof(double) * 6 * n_hyp, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dr + o_cost + sizeof(float) * dst, dr2 + p_cost + sizeof(float) * src, sizeof(float) * n_hyp, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dr + o_nv + sizeof(int32_t) * dst, dr2 + p_nv + sizeof(int32_t) * src, sizeof(int32_t) * n_hyp, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dr + o_ev + sizeof(int32_t) * dst, dr2 + p_ev + sizeof(int32_t) * src, sizeof(int32_t) * n_hyp, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dr + o_st + dst, dr2 + p_st + src, (size_t)n_hyp, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+    free(ids);
   }
   if (n_hyp > 1 && h_best) {
     if ((rc = agt_select_best(ctx, reinterpret_cast<double*>(dr + o_pose), reinterpret_cast<float*>(dr + o_cost),
@@ -377,5 +569,6 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
   if (h_evals) AGT_CUDA(ctx, cudaMemcpyAsync(h_evals, dr + o_ev, sizeof(int32_t) * jobs, cudaMemcpyDeviceToHost, st));
   if (h_status) AGT_CUDA(ctx, cudaMemcpyAsync(h_status, dr + o_st, jobs, cudaMemcpyDeviceToHost, st));
   AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  if (trace) fprintf(stderr, "[agt] refine_host: done at %.3f ms\n", since());
   return AGT_OK;
 }

@@ -21,6 +21,7 @@ struct agt_model {
   float normals[AGT_MAX_TAGS][3];
   float centres[AGT_MAX_TAGS][3];
   double pitch;
+  double radius;                     // max |sample position|
 };
 
 struct agt_ctx {
@@ -34,6 +35,13 @@ struct agt_ctx {
   agt_camera cam;
   agt_model model;
   int64_t launches;
+  int roi_upload;                // agt_refine_host uploads only the rectangle a refinement can read
+  int64_t last_h2d_bytes;        // host->device bytes of the last agt_refine_host call
+  int last_redo_frames;          // frames the last agt_refine_host call redid from the full frame
+  const uint8_t* host_frames_dev; // device alias of pinned host frames (NULL: pageable memory)
+  struct agt_roi_rect* h_rects;  // pinned ROI rectangle lists (double-buffered)
+  struct agt_roi_rect* d_rects;
+  int rect_capacity;
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];

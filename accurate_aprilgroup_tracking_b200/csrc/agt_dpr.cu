@@ -20,22 +20,20 @@
 // (the cost in float64 from the start); one thread runs the 6x6 Cholesky / LM
 // bookkeeping in float64.  Samples whose footprint leaves the staged tile fall
 // back to global loads, so results do not depend on the tile size.
-#include "agt_common.cuh"
+#include "agt_dpr_plan.cuh"
 
 namespace {
 
 constexpr int DPR_THREADS = 256;
 constexpr int DPR_WARPS = DPR_THREADS / 32;
-constexpr int TILE_ROWS = 272;
-constexpr int TILE_PITCH = 288;            // 272 + 16 B alignment slack; 2 CTAs of 76.5 KB per SM
+constexpr int TILE_ROWS = AGT_DPR_TILE_ROWS;
+constexpr int TILE_PITCH = AGT_DPR_TILE_PITCH;
 constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH + 16;   // +16: the unaligned fetch reads one word past its window
 constexpr int NSUM = 28;                   // 21 H + 6 b + (cost kept separately in double) + count
 constexpr double COS_VISIBLE = 0.25881904510252074;   // cos 75 deg
 constexpr double LAMBDA0 = 1e-3, LAMBDA_MIN = 1e-9, LAMBDA_MAX = 1e6;
 constexpr int MAX_EVALS = 50;
 constexpr double TOL_ROT = 1e-6, TOL_TRANS = 1e-6, REJ_TOL_ROT = 5e-5, REJ_TOL_TRANS = 5e-6;
-constexpr double BOUND_RADIUS_FACTOR = 1.30;   // bounding sphere radius / max |sample|, + drift margin below
-constexpr int DRIFT_MARGIN = 8;
 
 struct DprShared {
   // trial pose (float32 view used by the sample loop, float64 for the projection)
@@ -49,6 +47,8 @@ struct DprShared {
   int64_t lpitch;
   const uint8_t* limg;   // level image of this frame
   int tx0, ty0, tw, th;  // staged tile: origin (level px), size
+  int rx0, ry0, rx1, ry1;   // predicted ROI (see agt_dpr_plan)
+  int left_roi;          // a sample footprint left the predicted ROI at some evaluation
   int n_active;
   int act_begin[AGT_MAX_TAGS];   // first sample of each active tag
   int act_prefix[AGT_MAX_TAGS + 1];
@@ -88,7 +88,8 @@ constexpr int C_SM1 = (int)0x030A0300;   // ( 0, 3,10, 3)
 __global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
            const double* __restrict__ init, int n_hyp, const uint8_t* __restrict__ mask, double* __restrict__ pose_out, float* __restrict__ cost_out,
-           int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out) {
+           int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out,
+           uint8_t* __restrict__ left_roi_out) {
   extern __shared__ __align__(16) uint8_t s_tile[];
   __shared__ DprShared S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -101,6 +102,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       if (nvalid_out) nvalid_out[job] = 0;
       if (evals_out) evals_out[job] = 0;
       if (status_out) status_out[job] = AGT_DPR_NONE;
+      if (left_roi_out) left_roi_out[job] = 0;
     }
     return;
   }
@@ -114,21 +116,20 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     double r0[3] = {p0[0], p0[1], p0[2]};
     agt_rodrigues(r0, Rc);
     tc[0] = p0[3]; tc[1] = p0[4]; tc[2] = p0[5];
-    // level
-    double q = cam.fx * model.pitch / tc[2];
-    int lvl = q < 2.0 ? 0 : (q < 4.0 ? 1 : (q < 8.0 ? 2 : 3));
-    if (!(tc[2] > 0.0)) lvl = 0;
-    if (lvl > pyr.levels - 1) lvl = pyr.levels - 1;
+    const agt_dpr_plan plan = agt_make_dpr_plan(cam, model.pitch, model.radius, tc, pyr.width, pyr.height, pyr.levels);
+    const int lvl = plan.level;
     S.level = lvl;
     S.lw = pyr.width[lvl]; S.lh = pyr.height[lvl]; S.lpitch = pyr.pitch[lvl];
     S.limg = pyr.data[lvl] + frame * pyr.frame_stride[lvl];
+    S.rx0 = plan.rx0; S.ry0 = plan.ry0; S.rx1 = plan.rx1; S.ry1 = plan.ry1;
+    S.tx0 = plan.tx0; S.ty0 = plan.ty0; S.tw = plan.tw; S.th = plan.th;
+    S.left_roi = 0;
     double sc = 1.0 / (double)(1 << lvl);
     S.inv_scale = (float)sc;
     S.gscale = (float)(sc / 32.0);
     S.fx = (float)cam.fx; S.fy = (float)cam.fy; S.cx = (float)cam.cx; S.cy = (float)cam.cy;
     // active tags
     int na = 0, pre = 0;
-    double rmax2 = 0.0;
     for (int k = 0; k < model.n_tags; ++k) {
       double c[3], n[3];
       for (int i = 0; i < 3; ++i) {
@@ -137,9 +138,6 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       }
       double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
       double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
-      double m2 = model.centres[k][0] * model.centres[k][0] + model.centres[k][1] * model.centres[k][1] +
-                  model.centres[k][2] * model.centres[k][2];
-      rmax2 = fmax(rmax2, m2);
       if (d > COS_VISIBLE) {
         S.act_begin[na] = model.tag_begin[k];
         S.act_prefix[na] = pre;
@@ -149,24 +147,6 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     }
     S.act_prefix[na] = pre;
     S.n_active = na;
-    // staged tile: projected bounding sphere (+ margin), clipped to the level and to the tile capacity
-    double rad_m = sqrt(rmax2) * BOUND_RADIUS_FACTOR;
-    double zc = tc[2] > 1e-6 ? tc[2] : 1e-6;
-    double uc = (cam.fx * tc[0] / zc + cam.cx) * sc, vc = (cam.fy * tc[1] / zc + cam.cy) * sc;
-    double zr = zc - rad_m > 0.05 * zc ? zc - rad_m : 0.05 * zc;
-    double rad_px = fmax(cam.fx, cam.fy) * rad_m / zr * sc + DRIFT_MARGIN + 2;
-    double fx0 = floor(uc - rad_px), fy0 = floor(vc - rad_px);
-    fx0 = fmin(fmax(fx0, -1e6), 1e6); fy0 = fmin(fmax(fy0, -1e6), 1e6);
-    int x0 = (int)fx0, y0 = (int)fy0;
-    int x1 = (int)fmin(ceil(uc + rad_px) + 1, 1e6), y1 = (int)fmin(ceil(vc + rad_px) + 1, 1e6);
-    x0 = max(x0, 0) & ~15; y0 = max(y0, 0);
-    x1 = min(x1, S.lw); y1 = min(y1, S.lh);
-    int tw = x1 - x0, th = y1 - y0;
-    if (tw > TILE_PITCH) { int cut = (tw - TILE_PITCH + 31) / 32 * 16; x0 += cut; tw = min(TILE_PITCH, S.lw - x0); }
-    if (th > TILE_ROWS) { y0 += (th - TILE_ROWS) / 2; th = TILE_ROWS; }
-    if (tw < 0) tw = 0;
-    if (th < 0) th = 0;
-    S.tx0 = x0; S.ty0 = y0; S.tw = tw; S.th = th;
     for (int i = 0; i < 9; ++i) { S.R[i] = (float)Rc[i]; S.Rd[i] = Rc[i]; }
     for (int i = 0; i < 3; ++i) { S.t[i] = (float)tc[i]; S.td[i] = tc[i]; }
     S.fxs = cam.fx * sc; S.fys = cam.fy * sc;
@@ -263,6 +243,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 #pragma unroll
         for (int r = 0; r < 4; ++r) row[r] = ld4_unaligned_smem(s_tile, off + r * TILE_PITCH);
       } else {
+        if (x0 - 1 < S.rx0 || y0 - 1 < S.ry0 || x0 + 3 > S.rx1 || y0 + 3 > S.ry1) S.left_roi = 1;   // benign race: all write 1
         const uint8_t* g = limg + (int64_t)(y0 - 1) * lpitch + (x0 - 1);
 #pragma unroll
         for (int r = 0; r < 4; ++r) row[r] = ld4_global(g + r * lpitch);
@@ -392,6 +373,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     if (nvalid_out) nvalid_out[job] = S.nc;
     if (evals_out) evals_out[job] = S.evals;
     if (status_out) status_out[job] = (uint8_t)S.status;
+    if (left_roi_out) left_roi_out[job] = (uint8_t)S.left_roi;
   }
 }
 
@@ -422,7 +404,8 @@ __global__ void select_best_kernel(const double* __restrict__ pose, const float*
 }  // namespace
 
 extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
-                          double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch) {
+                          double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+                          uint8_t* d_left_roi, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine: camera and surface model must be set");
   if (!pyr || !d_init || !d_pose || n_hyp < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad arguments");
@@ -438,7 +421,7 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
   }
   // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower
   dpr_kernel<<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
-                                                                      n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status);
+                                                                      n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

@@ -186,6 +186,12 @@ class HostContext:
                 out.append(self.Scharr(l))
         return levels - 1, out
 
+    def set_roi_upload(self, enable: bool) -> None:
+        self._check(self.lib.agt_set_roi_upload(self.h, int(bool(enable))))
+
+    def last_h2d_bytes(self) -> int:
+        return int(self.lib.agt_last_h2d_bytes(self.h))
+
     # -- stage 3 ------------------------------------------------------------------------
     def refine_poses(self, frames, init, cameraMatrix, n_hyp: int = 1, levels: int = 4):
         """frames [B,H,W] u8 (host; pinned memory recommended), init [B,n_hyp,6] f64.

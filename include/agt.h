@@ -147,9 +147,12 @@ int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const
  * n_valid = samples in the final residual, evals = cost/Jacobian evaluations
  * run, status = AGT_DPR_*.  Any output except d_pose may be NULL.  d_mask[batch]
  * (may be NULL) skips frames whose entry is 0: their pose is copied through,
- * status AGT_DPR_NONE, evals 0. */
+ * status AGT_DPR_NONE, evals 0.  d_left_roi[batch][n_hyp] (may be NULL) is set
+ * to 1 when a sample ever read pixels outside the region of interest predicted
+ * from the initial pose (projected bounding sphere + 8 px drift margin). */
 int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
-               double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status, int batch);
+               double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+               uint8_t* d_left_roi, int batch);
 /* Multi-hypothesis selection: best[b] = argmin_h 2*cost/n_valid (ties -> lowest
  * h); d_best_pose[batch][6] may be NULL. */
 int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,
@@ -178,6 +181,12 @@ int agt_scharr_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int16_t* h
  * recommended): uploads in chunks overlapped with pyramid construction and
  * refinement, downloads poses.  h_init[batch][n_hyp][6]; outputs as agt_refine
  * plus (n_hyp>1) h_best[batch]. */
+/* agt_refine_host uploads, per frame, only the level-0 rectangle its refinement can read (the ROI
+ * predicted from the initial pose + pyramid halo) and redoes from the whole frame every frame whose
+ * refinement touched pixels outside it, so results are identical to a full upload.  enable = 0
+ * always uploads whole frames.  agt_last_h2d_bytes reports what the last call transferred. */
+int agt_set_roi_upload(agt_ctx* ctx, int enable);
+int64_t agt_last_h2d_bytes(const agt_ctx* ctx);
 int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, int batch,
                     const double* h_init, int n_hyp, double* h_pose, float* h_cost, int32_t* h_n_valid,
                     int32_t* h_evals, uint8_t* h_status, int32_t* h_best);

@@ -128,6 +128,42 @@ def test_refine_host_chunked_equals_device_path(host, ctxvga):
     assert np.array_equal(out3["best"], np.argmin(score, axis=1))
 
 
+def test_refine_host_roi_upload_is_exact(host, ctxvga):
+    """ROI-only upload (default) returns the same bits as uploading whole frames, moves far fewer bytes,
+    and frames whose refinement leaves the predicted ROI are transparently redone from the full frame."""
+    cam = synth.CAMERA_VGA
+    rng = np.random.default_rng(99)
+    n = 24
+    truth = np.array([synth.random_pose(rng) for _ in range(n)])
+    pyr = ctxvga.alloc_pyramid(n, cam.width, cam.height, 1)
+    ctxvga.render(pyr, truth, np.arange(n) + 700)
+    frames = pyr.frames.cpu().numpy()
+    init = truth + np.concatenate([rng.normal(0, 0.008, (n, 3)), rng.normal(0, 0.0004, (n, 3))], axis=1)
+    init[3, 3] += 0.012            # 12 mm off: the LM run starts (and wanders) outside the predicted ROI
+    init[7, :3] += 0.25
+    host.set_roi_upload(False)
+    full = host.refine_poses(frames, init, cam.mtx)
+    full_bytes = host.last_h2d_bytes()
+    host.set_roi_upload(True)
+    # poison the device staging buffers so stale pixels outside the ROI cannot help by accident
+    host.refine_poses(np.full_like(frames, 255), init, cam.mtx)
+    roi = host.refine_poses(frames, init, cam.mtx)
+    roi_bytes = host.last_h2d_bytes()
+    for key in ("pose", "cost", "n_valid", "evals", "status"):
+        assert np.array_equal(roi[key], full[key]), key
+    assert roi_bytes < 0.6 * full_bytes, (roi_bytes, full_bytes)
+    # pinned host frames take the gather-kernel path (one launch per chunk instead of one 2-D copy per frame)
+    import torch
+    pinned = torch.from_numpy(frames).pin_memory()
+    host.refine_poses(np.full_like(frames, 255), init, cam.mtx)
+    l0 = host.launch_count()
+    pin = host.refine_poses(pinned.numpy(), init, cam.mtx)
+    assert host.launch_count() - l0 >= 5          # gather + 3 pyrDown + refinement (+ redo pass)
+    for key in ("pose", "cost", "n_valid", "evals", "status"):
+        assert np.array_equal(pin[key], full[key]), key
+    assert host.last_h2d_bytes() == roi_bytes
+
+
 def test_pose_detector_matches_reference_golden_sequence(detector_factory):
     """The drop-in class over the sequence the UNMODIFIED reference produced the golden states for:
     accept / reset decisions identical, poses within tolerance, aliasing quirks included."""
