@@ -52,6 +52,10 @@ PROTOTYPES = {
     "agt_set_model": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _D]),
     "agt_pyr_down": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
     "agt_build_pyramid": (_I, [_VP, _PYR, _I]),
+    "agt_build_pyramid_roi": (_I, [_VP, _PYR, _VP, _I, _I]),
+    "agt_build_pyramid_masked": (_I, [_VP, _PYR, _VP, _I, _I]),
+    "agt_dpr_rects": (_I, [_VP, _PYR, _VP, _I, _VP, _I]),
+    "agt_any_flag": (_I, [_VP, _VP, _I, _VP, _I]),
     "agt_scharr": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _I]),
     "agt_lk": (_I, [_VP, _PYR, _PYR, _VP, _VP, _VP, _VP, _I, _I]),
     "agt_pnp": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),

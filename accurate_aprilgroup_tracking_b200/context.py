@@ -233,22 +233,66 @@ class AgtContext:
         return acc, flag
 
     # -- K4 ---------------------------------------------------------------------------
-    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None):
-        """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status); mask [B] u8 skips frames."""
+    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None, out=None):
+        """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status, left_roi).
+        mask [B] u8: frames with 0 are skipped and none of their outputs is written; ``out`` (a previous result
+        dict) receives the outputs in place, otherwise skipped frames read pose = init, everything else 0."""
         t = self.torch
         b = int(pyr.batch if batch is None else batch)
         ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
-        pose = t.empty_like(ini)
-        cost = t.empty((b, n_hyp), dtype=t.float32, device=self.tdev)
-        nv = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
-        ev = t.empty((b, n_hyp), dtype=t.int32, device=self.tdev)
-        st = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
-        left = t.empty((b, n_hyp), dtype=t.uint8, device=self.tdev)
-        self._use_current_stream()
+        if out is None:
+            fresh = t.zeros if mask is not None else t.empty
+            out = {"pose": ini.clone() if mask is not None else t.empty_like(ini),
+                   "cost": fresh((b, n_hyp), dtype=t.float32, device=self.tdev),
+                   "n_valid": fresh((b, n_hyp), dtype=t.int32, device=self.tdev),
+                   "evals": fresh((b, n_hyp), dtype=t.int32, device=self.tdev),
+                   "status": fresh((b, n_hyp), dtype=t.uint8, device=self.tdev),
+                   "left_roi": fresh((b, n_hyp), dtype=t.uint8, device=self.tdev)}
         msk = self._dev(mask, t.uint8) if mask is not None else None
-        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(pose), self._p(cost),
-                                        self._p(nv), self._p(ev), self._p(st), self._p(left), b))
-        return {"pose": pose, "cost": cost, "n_valid": nv, "evals": ev, "status": st, "left_roi": left}
+        self._use_current_stream()
+        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(out["pose"]),
+                                        self._p(out["cost"]), self._p(out["n_valid"]), self._p(out["evals"]), self._p(out["status"]),
+                                        self._p(out["left_roi"]), b))
+        return out
+
+    def dpr_rects(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
+        """Level-0 rectangle [B,4] i32 (x0,y0,x1,y1) each frame's refinements can read."""
+        t = self.torch
+        b = int(pyr.batch if batch is None else batch)
+        ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
+        rects = t.empty((b, 4), dtype=t.int32, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_dpr_rects(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(rects), b))
+        return rects
+
+    def build_pyramid_roi(self, pyr: Pyramid, rects, batch: Optional[int] = None) -> None:
+        self._use_current_stream()
+        self._check(self.lib.agt_build_pyramid_roi(self.h, C.byref(pyr.desc), self._p(rects), int(rects.shape[1]),
+                                                   int(pyr.batch if batch is None else batch)))
+
+    def build_pyramid_masked(self, pyr: Pyramid, mask, batch: Optional[int] = None) -> None:
+        stride = int(mask.shape[1]) if mask.dim() > 1 else 1
+        self._use_current_stream()
+        self._check(self.lib.agt_build_pyramid_masked(self.h, C.byref(pyr.desc), self._p(mask), stride,
+                                                      int(pyr.batch if batch is None else batch)))
+
+    def refine_roi(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
+        """Pyramid + refinement restricted to the region of interest, exact by construction:
+        rectangles from the initial poses -> ROI pyramid -> refinement; frames whose refinement read outside
+        their rectangle (``left_roi``) get the full pyramid and are refined again, all without leaving the device
+        (the two redo launches exit immediately for frames that stayed inside)."""
+        t = self.torch
+        b = int(pyr.batch if batch is None else batch)
+        ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
+        rects = self.dpr_rects(pyr, ini, n_hyp, b)
+        self.build_pyramid_roi(pyr, rects, b)
+        res = self.refine(pyr, ini, n_hyp, b)
+        redo = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._check(self.lib.agt_any_flag(self.h, self._p(res["left_roi"]), n_hyp, self._p(redo), b))
+        self.build_pyramid_masked(pyr, redo, b)
+        self.refine(pyr, ini, n_hyp, b, mask=redo, out=res)
+        res["redo"] = redo
+        return res
 
     def select_best(self, res):
         t = self.torch

@@ -350,25 +350,12 @@ roi_gather_kernel(const uint8_t* __restrict__ host_frames, int w, int h, const a
   }
 }
 
-// L0 rectangle the refinement of `frame` can read: union over its hypotheses of the predicted ROI
-// (agt_dpr_plan) scaled to level 0 plus the pyrDown halo.  Returns false if empty.
 static bool roi_rect_l0(const agt_ctx* ctx, const agt_pyramid& one, const double* init, int n_hyp, int* X0, int* Y0, int* X1,
                         int* Y1) {
-  const int W = one.width[0], H = one.height[0];
-  int x0 = W, y0 = H, x1 = 0, y1 = 0;
-  for (int hyp = 0; hyp < n_hyp; ++hyp) {
-    const double* p = init + hyp * 6;
-    agt_dpr_plan plan = agt_make_dpr_plan(ctx->cam, ctx->model.pitch, ctx->model.radius, p + 3, one.width, one.height, one.levels);
-    if (plan.rx1 <= plan.rx0 || plan.ry1 <= plan.ry0) continue;
-    const int l = plan.level, pad = 2 << l;          // pyrDown halo of the chain down to level l
-    int a = (plan.rx0 << l) - pad, b = (plan.ry0 << l) - pad;
-    int c = ((plan.rx1 - 1) << l) + pad + 1, d = ((plan.ry1 - 1) << l) + pad + 1;
-    x0 = a < x0 ? a : x0; y0 = b < y0 ? b : y0; x1 = c > x1 ? c : x1; y1 = d > y1 ? d : y1;
-  }
-  x0 = (x0 > 0 ? x0 : 0) & ~15; y0 = y0 > 0 ? y0 : 0;
-  x1 = (x1 + 15) & ~15; x1 = x1 < W ? x1 : W; y1 = y1 < H ? y1 : H;
-  *X0 = x0; *Y0 = y0; *X1 = x1; *Y1 = y1;
-  return x1 > x0 && y1 > y0;
+  int32_t r[4];
+  bool ok = agt_dpr_rect_l0(ctx->cam, ctx->model.pitch, ctx->model.radius, init, n_hyp, one.width, one.height, one.levels, r);
+  *X0 = r[0]; *Y0 = r[1]; *X1 = r[2]; *Y1 = r[3];
+  return ok;
 }
 
 extern "C" int agt_set_roi_upload(agt_ctx* ctx, int enable) {
@@ -397,6 +384,7 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
     layout_pyramid(&p, buf[s], w, h, levels, chunk);
     if (c >= 2) AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[s], 0));       // compute on this buffer finished
     const bool contiguous_ids = ids == nullptr;
+    bool gathered = false;
     if (roi && ctx->host_frames_dev && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx->host_frames_dev) & 15) == 0) {
       // rectangles of this chunk -> device, then one gather launch on the copy stream
       agt_roi_rect* hr = ctx->h_rects + b0;        // pinned; one slot per frame of the pass, so the CPU never
@@ -415,6 +403,7 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
       if (const char* e = getenv("AGT_GATHER_CTAS")) { int v = atoi(e); if (v > 0) gctas = v; }
       roi_gather_kernel<<<nb < gctas ? nb : gctas, 256, 0, cp>>>(ctx->host_frames_dev, w, h, drc, p.data[0], p.pitch[0], p.frame_stride[0], nb);
       AGT_LAUNCH_CHECK(ctx);
+      gathered = true;
     } else if (!roi && contiguous_ids && tight) {
       AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], h_frames + (int64_t)b0 * w * h, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
       ctx->last_h2d_bytes += (int64_t)nb * w * h;
@@ -432,7 +421,11 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
     }
     AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], cp));
     AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
-    if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
+    if (gathered) {        // the rectangle list is on the device: build the pyramid below the rectangles only
+      if ((rc = agt_build_pyramid_roi(ctx, &p, reinterpret_cast<const int32_t*>(ctx->d_rects + b0), 5, nb))) return rc;
+    } else {
+      if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
+    }
     // jobs of this chunk are contiguous in the compacted device arrays [b0*n_hyp, (b0+nb)*n_hyp)
     int64_t j0 = (int64_t)b0 * n_hyp;
     if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,

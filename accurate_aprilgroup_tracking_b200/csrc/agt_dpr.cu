@@ -95,17 +95,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t job = blockIdx.x;
   const int64_t frame = job / n_hyp;
-  if (mask != nullptr && mask[frame] == 0) {          // skipped frame: pass the pose through
-    if (tid < 6) pose_out[job * 6 + tid] = init[job * 6 + tid];
-    if (tid == 0) {
-      if (cost_out) cost_out[job] = 0.f;
-      if (nvalid_out) nvalid_out[job] = 0;
-      if (evals_out) evals_out[job] = 0;
-      if (status_out) status_out[job] = AGT_DPR_NONE;
-      if (left_roi_out) left_roi_out[job] = 0;
-    }
-    return;
-  }
+  if (mask != nullptr && mask[frame] == 0) return;     // skipped frame: none of its outputs is written
 
   double* const Rc = S.Rc; double* const tc = S.tc; double* const Hc = S.Hc; double* const bc = S.bc;
   double* const Rt = S.Rt; double* const tt = S.tt; double* const dstep = S.dstep;
@@ -377,6 +367,23 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   }
 }
 
+__global__ void dpr_rects_kernel(agt_pyramid pyr, agt_camera cam, double pitch, double radius, const double* __restrict__ init,
+                                 int n_hyp, int32_t* __restrict__ rects, int batch) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= batch) return;
+  int32_t r[4];
+  agt_dpr_rect_l0(cam, pitch, radius, init + (int64_t)f * n_hyp * 6, n_hyp, pyr.width, pyr.height, pyr.levels, r);
+  *reinterpret_cast<int4*>(rects + (int64_t)f * 4) = make_int4(r[0], r[1], r[2], r[3]);
+}
+
+__global__ void any_flag_kernel(const uint8_t* __restrict__ flags, int stride, uint8_t* __restrict__ out, int batch) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= batch) return;
+  uint8_t any = 0;
+  for (int k = 0; k < stride; ++k) any |= flags[(int64_t)f * stride + k];
+  out[f] = any ? 1 : 0;
+}
+
 __global__ void select_best_kernel(const double* __restrict__ pose, const float* __restrict__ cost,
                                    const int32_t* __restrict__ nvalid, int n_hyp, int32_t* __restrict__ best,
                                    double* __restrict__ best_pose, int batch) {
@@ -435,6 +442,27 @@ extern "C" int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* 
   int threads = 128;
   int blocks = (int)(((int64_t)batch * 32 + threads - 1) / threads);
   select_best_kernel<<<blocks, threads, 0, ctx->stream>>>(d_pose, d_cost, d_n_valid, n_hyp, d_best, d_best_pose, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_dpr_rects(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, int32_t* d_rects, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_dpr_rects: camera and surface model must be set");
+  if (!pyr || !d_init || !d_rects || n_hyp < 1 || batch < 0 || (reinterpret_cast<uintptr_t>(d_rects) & 15))
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_dpr_rects: bad arguments (d_rects must be 16-byte aligned)");
+  if (batch == 0) return AGT_OK;
+  dpr_rects_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(*pyr, ctx->cam, ctx->model.pitch, ctx->model.radius, d_init, n_hyp,
+                                                                d_rects, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_any_flag(agt_ctx* ctx, const uint8_t* d_flags, int stride, uint8_t* d_out, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_flags || !d_out || stride < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_any_flag: bad arguments");
+  if (batch == 0) return AGT_OK;
+  any_flag_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d_flags, stride, d_out, batch);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

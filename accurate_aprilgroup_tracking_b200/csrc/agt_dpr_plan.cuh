@@ -65,3 +65,27 @@ __host__ __device__ inline agt_dpr_plan agt_make_dpr_plan(const agt_camera& cam,
   p.tx0 = x0; p.ty0 = y0; p.tw = tw > 0 ? tw : 0; p.th = th > 0 ? th : 0;
   return p;
 }
+
+// Level-0 rectangle (x0,y0,x1,y1; x multiples of 16) the refinements of one frame can read: union over its
+// hypotheses of the predicted ROI scaled to level 0 plus the pyrDown halo of the chain down to the level used.
+// Returns false (and an empty rectangle) if no hypothesis projects into the frame.
+__host__ __device__ inline bool agt_dpr_rect_l0(const agt_camera& cam, double pitch, double radius, const double* init,
+                                                int n_hyp, const int32_t* widths, const int32_t* heights, int levels,
+                                                int32_t rect[4]) {
+  const int W = widths[0], H = heights[0];
+  int x0 = W, y0 = H, x1 = 0, y1 = 0;
+  for (int hyp = 0; hyp < n_hyp; ++hyp) {
+    const double* p = init + hyp * 6;
+    agt_dpr_plan plan = agt_make_dpr_plan(cam, pitch, radius, p + 3, widths, heights, levels);
+    if (plan.rx1 <= plan.rx0 || plan.ry1 <= plan.ry0) continue;
+    const int l = plan.level, pad = 2 << l;
+    int a = (plan.rx0 << l) - pad, b = (plan.ry0 << l) - pad;
+    int c = ((plan.rx1 - 1) << l) + pad + 1, d = ((plan.ry1 - 1) << l) + pad + 1;
+    x0 = a < x0 ? a : x0; y0 = b < y0 ? b : y0; x1 = c > x1 ? c : x1; y1 = d > y1 ? d : y1;
+  }
+  x0 = (x0 > 0 ? x0 : 0) & ~15; y0 = y0 > 0 ? y0 : 0;
+  x1 = (x1 + 15) & ~15; x1 = x1 < W ? x1 : W; y1 = y1 < H ? y1 : H;
+  bool ok = x1 > x0 && y1 > y0;
+  rect[0] = ok ? x0 : 0; rect[1] = ok ? y0 : 0; rect[2] = ok ? x1 : 0; rect[3] = ok ? y1 : 0;
+  return ok;
+}

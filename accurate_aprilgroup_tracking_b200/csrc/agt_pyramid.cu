@@ -20,7 +20,13 @@ constexpr int PD_THREADS = 256;
 
 __global__ void __launch_bounds__(PD_THREADS)
 pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
-                uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride, int vec_ok) {
+                uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride, int vec_ok,
+                const uint8_t* __restrict__ mask, int mask_stride) {
+  if (mask != nullptr) {
+    bool any = false;
+    for (int k = 0; k < mask_stride; ++k) any = any || mask[(int64_t)blockIdx.z * mask_stride + k] != 0;
+    if (!any) return;
+  }
   __shared__ __align__(16) uint8_t s_in[PD_IH][PD_IW];
   __shared__ __align__(16) uint16_t s_h[PD_IH][PD_OW];
 
@@ -196,7 +202,8 @@ __device__ __forceinline__ void hsum(const RowWords& r, uint32_t h[4]) {
 __global__ void __launch_bounds__(PF_WARPS * 32, 6)
 pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
                        uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride,
-                       int col_blocks, int strips, int64_t total_warps) {
+                       int col_blocks, int strips, int64_t total_warps, const int32_t* __restrict__ rects, int rect_stride,
+                       int src_level, const uint8_t* __restrict__ mask, int mask_stride) {
   const int lane = threadIdx.x & 31;
   int64_t wg = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
   if (wg >= total_warps) return;
@@ -204,12 +211,29 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   wg /= col_blocks;
   const int strip = (int)(wg % strips);
   const int64_t frame = wg / strips;
+  if (mask != nullptr) {                      // only frames with a set flag (any of mask_stride entries)
+    bool any = false;
+    for (int k = 0; k < mask_stride; ++k) any = any || mask[frame * mask_stride + k] != 0;
+    if (!any) return;
+  }
+  // output window of this frame: the whole level, or the part of it below the frame's level-0 rectangle
+  int xo0 = 0, yo0 = 0, xo1 = ow, yo1 = oh;
+  if (rects != nullptr) {
+    const int32_t* r = rects + frame * rect_stride;
+    const int sh = src_level + 1, rnd = (1 << sh) - 1;
+    xo0 = max(0, (r[0] >> sh) - 2) & ~7;
+    yo0 = max(0, (r[1] >> sh) - 2);
+    xo1 = min(ow, (((r[2] + rnd) >> sh) + 2 + 7) & ~7);
+    yo1 = min(oh, ((r[3] + rnd) >> sh) + 2);
+    if (r[2] <= r[0] || r[3] <= r[1]) return;
+  }
   const uint8_t* img = src + frame * sstride;
   uint8_t* out = dst + frame * dstride;
-  const int ox0 = cb * 256 + lane * 8;
+  const int ox0 = xo0 + cb * 256 + lane * 8;
   const int ix0 = 2 * ox0;
-  const int oy0 = strip * PF_STRIP;
-  const int oy1 = min(oy0 + PF_STRIP, oh);
+  const int oy0 = yo0 + strip * PF_STRIP;
+  const int oy1 = min(oy0 + PF_STRIP, yo1);
+  if (oy0 >= yo1 || xo0 + cb * 256 >= xo1) return;      // warp-uniform
 
   // single reflection is enough: rows 2*oy-2 .. 2*oy+2 overshoot by at most 2 and h >= 4
   auto row_ptr = [&](int r) { int rr = r < 0 ? -r : (r >= h ? 2 * h - 2 - r : r); return img + (int64_t)rr * spitch; };
@@ -239,7 +263,7 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
       o[j] = (v >> 8) & 0x00ff00ffu;
       a[j] = c[j]; b[j] = d[j]; c[j] = e[j];
     }
-    if (ox0 < ow) {
+    if (ox0 < xo1) {
       uint32_t lo = __byte_perm(o[0], o[1], 0x6420), hi = __byte_perm(o[2], o[3], 0x6420);
       uint8_t* p = out + (int64_t)oy * dpitch + ox0;
       if (ox0 + 8 <= ow) {
@@ -276,9 +300,9 @@ __global__ void scharr_kernel(const uint8_t* __restrict__ src, int w, int h, int
 
 }  // namespace
 
-extern "C" int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
-                            uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch) {
-  if (!ctx) return AGT_ERR_INVALID;
+static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+                         uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch, const int32_t* d_rects,
+                         int rect_stride, int src_level, const uint8_t* d_mask, int mask_stride) {
   if (!d_src || !d_dst || w < 1 || h < 1 || batch < 0 || src_pitch < w || dst_pitch < (w + 1) / 2)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pyr_down: bad arguments (w=%d h=%d batch=%d)", w, h, batch);
   if (batch == 0) return AGT_OK;
@@ -294,34 +318,61 @@ extern "C" int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, in
     if (blocks <= 0x7fffffffLL) {
       pyr_down_stream_kernel<<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(d_src, w, h, src_pitch, src_stride, d_dst, ow, oh,
                                                                                dst_pitch, dst_stride, col_blocks, strips,
-                                                                               total_warps);
+                                                                               total_warps, d_rects, rect_stride, src_level, d_mask,
+                                                                               mask_stride);
       AGT_LAUNCH_CHECK(ctx);
       return AGT_OK;
     }
   }
+  // tiled kernel (any size / alignment): computes whole frames, which is a superset of any ROI
   for (int b0 = 0; b0 < batch; b0 += 65535) {
     int nb = batch - b0 < 65535 ? batch - b0 : 65535;
     dim3 grid((ow + PD_OW - 1) / PD_OW, (oh + PD_OH - 1) / PD_OH, nb);
     pyr_down_kernel<<<grid, PD_THREADS, 0, ctx->stream>>>(d_src + (int64_t)b0 * src_stride, w, h, src_pitch, src_stride,
                                                           d_dst + (int64_t)b0 * dst_stride, ow, oh, dst_pitch,
-                                                          dst_stride, vec_ok);
+                                                          dst_stride, vec_ok, d_mask ? d_mask + (int64_t)b0 * mask_stride : nullptr,
+                                                          mask_stride);
     AGT_LAUNCH_CHECK(ctx);
+  }
+  return AGT_OK;
+}
+
+extern "C" int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
+                            uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  return pyr_down_impl(ctx, d_src, w, h, src_pitch, src_stride, d_dst, dst_pitch, dst_stride, batch, nullptr, 0, 0, nullptr, 0);
+}
+
+static int build_pyramid_impl(agt_ctx* ctx, const agt_pyramid* pyr, int batch, const int32_t* d_rects, int rect_stride,
+                              const uint8_t* d_mask, int mask_stride) {
+  if (!pyr || pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: bad pyramid descriptor");
+  for (int l = 1; l < pyr->levels; ++l) {
+    if (pyr->width[l] != (pyr->width[l - 1] + 1) / 2 || pyr->height[l] != (pyr->height[l - 1] + 1) / 2)
+      AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: level %d is not ((w+1)/2,(h+1)/2) of level %d", l, l - 1);
+    int rc = pyr_down_impl(ctx, pyr->data[l - 1], pyr->width[l - 1], pyr->height[l - 1], pyr->pitch[l - 1],
+                           pyr->frame_stride[l - 1], pyr->data[l], pyr->pitch[l], pyr->frame_stride[l], batch, d_rects,
+                           rect_stride, l - 1, d_mask, mask_stride);
+    if (rc != AGT_OK) return rc;
   }
   return AGT_OK;
 }
 
 extern "C" int agt_build_pyramid(agt_ctx* ctx, const agt_pyramid* pyr, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
-  if (!pyr || pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS)
-    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: bad pyramid descriptor");
-  for (int l = 1; l < pyr->levels; ++l) {
-    if (pyr->width[l] != (pyr->width[l - 1] + 1) / 2 || pyr->height[l] != (pyr->height[l - 1] + 1) / 2)
-      AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: level %d is not ((w+1)/2,(h+1)/2) of level %d", l, l - 1);
-    int rc = agt_pyr_down(ctx, pyr->data[l - 1], pyr->width[l - 1], pyr->height[l - 1], pyr->pitch[l - 1],
-                          pyr->frame_stride[l - 1], pyr->data[l], pyr->pitch[l], pyr->frame_stride[l], batch);
-    if (rc != AGT_OK) return rc;
-  }
-  return AGT_OK;
+  return build_pyramid_impl(ctx, pyr, batch, nullptr, 0, nullptr, 0);
+}
+
+extern "C" int agt_build_pyramid_roi(agt_ctx* ctx, const agt_pyramid* pyr, const int32_t* d_rects, int rect_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_rects || rect_stride < 4) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid_roi: rects missing or rect_stride < 4");
+  return build_pyramid_impl(ctx, pyr, batch, d_rects, rect_stride, nullptr, 0);
+}
+
+extern "C" int agt_build_pyramid_masked(agt_ctx* ctx, const agt_pyramid* pyr, const uint8_t* d_mask, int mask_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_mask || mask_stride < 1) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid_masked: mask missing");
+  return build_pyramid_impl(ctx, pyr, batch, nullptr, 0, d_mask, mask_stride);
 }
 
 extern "C" int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,

@@ -91,6 +91,13 @@ int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_p
                  uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch);
 /* Fill levels 1..levels-1 of every frame from level 0. */
 int agt_build_pyramid(agt_ctx* ctx, const agt_pyramid* pyr, int batch);
+/* Region-of-interest variants (the three stages only ever read the neighbourhood of the tracked object):
+ * _roi fills, per frame, only the part of levels 1.. that lies below its level-0 rectangle
+ * d_rects[b*rect_stride + 0..3] = x0,y0,x1,y1 (x multiples of 16; pixels whose 5x5 support chain lies inside
+ * the rectangle are bit-identical to the full pyramid, the rest of the level is left untouched);
+ * _masked rebuilds the full pyramid of the frames with any non-zero entry in d_mask[b*mask_stride ..]. */
+int agt_build_pyramid_roi(agt_ctx* ctx, const agt_pyramid* pyr, const int32_t* d_rects, int rect_stride, int batch);
+int agt_build_pyramid_masked(agt_ctx* ctx, const agt_pyramid* pyr, const uint8_t* d_mask, int mask_stride, int batch);
 /* Interleaved (dx,dy) int16 Scharr planes, d_dst[b][h][w][2] (the layout
  * cv::buildOpticalFlowPyramid(withDerivatives=true) produces). */
 int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
@@ -146,13 +153,19 @@ int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const
 /* d_init[batch][n_hyp][6] -> d_pose[batch][n_hyp][6]; cost = 1/2 sum r^2,
  * n_valid = samples in the final residual, evals = cost/Jacobian evaluations
  * run, status = AGT_DPR_*.  Any output except d_pose may be NULL.  d_mask[batch]
- * (may be NULL) skips frames whose entry is 0: their pose is copied through,
- * status AGT_DPR_NONE, evals 0.  d_left_roi[batch][n_hyp] (may be NULL) is set
+ * (may be NULL) skips frames whose entry is 0: none of their outputs is
+ * written.  d_left_roi[batch][n_hyp] (may be NULL) is set
  * to 1 when a sample ever read pixels outside the region of interest predicted
  * from the initial pose (projected bounding sphere + 8 px drift margin). */
 int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
                double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
                uint8_t* d_left_roi, int batch);
+/* d_rects[batch][4] (16-byte aligned) = the level-0 rectangle x0,y0,x1,y1 the refinements of each frame can
+ * read (predicted ROI of every hypothesis + pyramid halo); feed it to agt_build_pyramid_roi.  A frame whose
+ * refinement reports left_roi must be redone on a full pyramid (agt_build_pyramid_masked + masked agt_refine). */
+int agt_dpr_rects(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, int32_t* d_rects, int batch);
+/* d_out[b] = any(d_flags[b*stride .. b*stride+stride-1]) */
+int agt_any_flag(agt_ctx* ctx, const uint8_t* d_flags, int stride, uint8_t* d_out, int batch);
 /* Multi-hypothesis selection: best[b] = argmin_h 2*cost/n_valid (ties -> lowest
  * h); d_best_pose[batch][6] may be NULL. */
 int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,

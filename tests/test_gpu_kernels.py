@@ -358,3 +358,47 @@ def test_dpr_object_outside_image(ctx1080):
     res = ctx1080.refine(pyr, init, 1)
     assert int(res["status"][0, 0]) == 0 and int(res["n_valid"][0, 0]) == 0
     util.assert_pose_close(res["pose"][0, 0].cpu().numpy(), init[0, 0])
+
+
+# ------------------------------------------------------------------------------------------
+# region-of-interest pyramid + refinement: identical to the full-frame path
+# ------------------------------------------------------------------------------------------
+def test_roi_pyramid_and_refinement_are_exact(ctx1080):
+    import cv2
+    cam = synth.CAMERA_1080P
+    torch = ctx1080.torch
+    rng = np.random.default_rng(2500)
+    n = 20
+    truth = np.array([synth.random_pose(rng) for _ in range(n)])
+    truth[0, 3:] = (0.16, 0.09, 0.27)         # object cut by the image corner
+    truth[1, 3:] = (0.0, 0.0, 0.2505)         # largest ROI of the working volume
+    init = truth + np.concatenate([rng.normal(0, 0.01, (n, 3)), rng.normal(0, 0.0005, (n, 3))], axis=1)
+    init[2, 3] += 0.010                       # starts 10 mm off: the LM run leaves its predicted ROI -> redone on the full pyramid
+    full = ctx1080.alloc_pyramid(n, cam.width, cam.height, 4)
+    ctx1080.render(full, truth, np.arange(n) + 2500)
+    roi = ctx1080.alloc_pyramid(n, cam.width, cam.height, 4)
+    roi.levels[0].copy_(full.levels[0])
+    for l in (1, 2, 3):
+        roi.levels[l].fill_(255)              # poison: anything the ROI path does not compute stays visibly wrong
+    ctx1080.build_pyramid(full)
+    want = ctx1080.refine(full, init.reshape(n, 1, 6), 1)
+    got = ctx1080.refine_roi(roi, init.reshape(n, 1, 6), 1)
+    for key in ("pose", "cost", "n_valid", "evals", "status"):
+        assert torch.equal(got[key], want[key]), key
+    redo = got["redo"].cpu().numpy()
+    assert redo[2] == 1 and redo.sum() <= 3
+    # inside the rectangle (minus the pyrDown halo) the ROI levels equal cv2.pyrDown of the frame
+    rects = ctx1080.dpr_rects(roi, init.reshape(n, 1, 6), 1).cpu().numpy()
+    for b in (0, 1, 5):
+        x0, y0, x1, y1 = rects[b]
+        assert x0 % 16 == 0 and 0 <= x0 < x1 <= cam.width and 0 <= y0 < y1 <= cam.height
+        ref = full.frames[b].cpu().numpy()
+        for l in (1, 2, 3):
+            ref = cv2.pyrDown(ref)
+            pad = (2 << l) >> l
+            sl = (slice((y0 >> l) + pad + 1, (y1 >> l) - pad - 1), slice((x0 >> l) + pad + 1, (x1 >> l) - pad - 1))
+            if redo[b] or sl[0].stop <= sl[0].start:
+                continue
+            assert np.array_equal(roi.level(l)[b].cpu().numpy()[sl], ref[sl]), (b, l)
+    # the ROI path touched only a small part of the levels
+    assert float((roi.level(1)[5] == 255).float().mean()) > 0.5
