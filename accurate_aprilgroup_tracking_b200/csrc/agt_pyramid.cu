@@ -132,61 +132,51 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, i
 // next pair of loads issued before the current pair is consumed.
 // ---------------------------------------------------------------------------------------------
 constexpr int PF_WARPS = 4;
-constexpr int PF_STRIP = 32;
 
 struct RowWords { uint32_t w[6]; };   // w[0] = left halo, w[1..4] = own 16 bytes, w[5] = right halo
 
-// Per-lane, loop-invariant description of what a lane loads from every input row.  The kernel is
-// only used for w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly
-// at w; the reflect-101 halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from
-// one aligned word and a byte permute.  Loads (raw_row) and permutes/shuffles (expand_row) are
-// split so that nothing consumes a loaded value while later rows are still being requested.
+// Per-lane, loop-invariant description of what a lane requests from every input row.  The kernel is only used
+// for w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly at w; the reflect-101
+// halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from one aligned word and a byte permute.
+//
+// Rows travel global -> shared with cp.async (LDGSTS) into a per-warp ring, PF_Q rows ahead of the row being
+// consumed: no registers are tied up by loads in flight, so ~40 warps/SM each keep ~4 KB on the wire - enough
+// to cover the HBM latency-bandwidth product - and the halo words of a lane are simply its neighbours' words
+// in the ring.  Ring row layout: [12 pad][4 left halo][32 x 16 B main][4 right halo][12 pad][16 dummy] = 560 B.
+constexpr int PF_RPITCH = 16 * 35;        // + one 16 B dummy target for zero-size requests
+
 struct LanePlan {
-  int main_off;        // byte offset of the 16-byte load, or of the 4-byte reflect source
-  int edge_off;        // byte offset of the halo word lanes 0 / 31 fetch themselves
-  uint32_t main_sel;   // byte_perm selector applied to word 0 (identity unless reflecting)
-  uint32_t edge_sel;
-  bool main16, main4, edge;
+  // every lane executes the same three (predicated) requests per row; size 0 masks the lane off
+  int main_off, main_size, main_dst;   // 16-byte request
+  int word_off, word_size, word_dst;   // 4-byte request of the lane that starts exactly at w (reflect source p[w-4..w-1])
+  int edge_off, edge_size, edge_dst;   // 4-byte halo request of lanes 0 / 31
+  uint32_t left_sel, right_sel;   // byte_perm selectors for the halo words (identity unless reflecting)
 };
-struct RawRow { uint4 v; uint32_t edge; };   // edge = left halo for lane 0, right halo for lane 31
 
 __device__ __forceinline__ LanePlan make_plan(int ix0, int w, int lane) {
   LanePlan p;
-  p.main16 = ix0 + 16 <= w;
-  p.main4 = ix0 == w;                         // first lane past the right border: (p[w-2], p[w-3], -, -)
-  p.main_off = p.main16 ? ix0 : w - 4;
-  p.main_sel = p.main4 ? 0x4412u : 0x3210u;
-  p.edge = false; p.edge_off = 0; p.edge_sel = 0x3210u;
+  const bool main16 = ix0 + 16 <= w, main4 = ix0 == w;
+  p.main_off = main16 ? ix0 : 0; p.main_size = main16 ? 16 : 0; p.main_dst = main16 ? 16 * (lane + 1) : 16 * 34;
+  p.word_off = w - 4; p.word_size = main4 ? 4 : 0; p.word_dst = main4 ? 16 * (lane + 1) : 0;
+  p.left_sel = ix0 == 0 ? 0x1244u : 0x3210u;          // (-, -, p[2], p[1]) from p[0..3]
+  p.right_sel = ix0 + 16 == w ? 0x4412u : 0x3210u;     // (p[w-2], p[w-3], -, -) from p[w-4..w-1]
+  p.edge_off = 0; p.edge_size = 0; p.edge_dst = 4;     // bytes 0..11 of a ring row are padding
   if (lane == 0) {
-    p.edge = true;
-    if (ix0 >= 4) p.edge_off = ix0 - 4; else { p.edge_off = 0; p.edge_sel = 0x1244u; }   // (-, -, p[2], p[1])
-  } else if (lane == 31) {
-    if (ix0 + 20 <= w) { p.edge = true; p.edge_off = ix0 + 16; }
-    else if (ix0 + 16 == w) { p.edge = true; p.edge_off = w - 4; p.edge_sel = 0x4412u; }
+    p.edge_size = 4; p.edge_dst = 12;
+    p.edge_off = ix0 >= 4 ? ix0 - 4 : 0;
+  } else if (lane == 31 && ix0 + 16 <= w) {
+    p.edge_size = 4; p.edge_dst = 16 * 33;
+    p.edge_off = ix0 + 20 <= w ? ix0 + 16 : w - 4;
   }
   return p;
 }
 
-__device__ __forceinline__ RawRow raw_row(const uint8_t* __restrict__ row, const LanePlan& p) {
-  RawRow r;
-  r.v = make_uint4(0, 0, 0, 0);
-  r.edge = 0;
-  if (p.main16) r.v = __ldg(reinterpret_cast<const uint4*>(row + p.main_off));
-  if (p.main4) r.v.x = __ldg(reinterpret_cast<const uint32_t*>(row + p.main_off));
-  if (p.edge) r.edge = __ldg(reinterpret_cast<const uint32_t*>(row + p.edge_off));
-  return r;
+// predicated cp.async: lanes whose request does not apply are masked off (no divergent branch, no smem write)
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem, int size) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(smem), "l"(gmem), "r"(size));
 }
-
-__device__ __forceinline__ RowWords expand_row(const RawRow& q, const LanePlan& p, int lane) {
-  RowWords r;
-  r.w[1] = __byte_perm(q.v.x, 0u, p.main_sel);
-  r.w[2] = q.v.y; r.w[3] = q.v.z; r.w[4] = q.v.w;
-  uint32_t left = __shfl_up_sync(0xffffffffu, q.v.w, 1);
-  uint32_t right = __shfl_down_sync(0xffffffffu, r.w[1], 1);
-  uint32_t edge = __byte_perm(q.edge, 0u, p.edge_sel);
-  r.w[0] = lane == 0 ? edge : left;
-  r.w[5] = lane == 31 ? edge : right;
-  return r;
+__device__ __forceinline__ void cp_async4(uint32_t smem, const void* gmem, int size) {
+  asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 4; }" ::"r"(smem), "l"(gmem), "r"(size));
 }
 
 // horizontal [1 4 6 4 1] at 8 even positions -> 4 packed words (2 x u16 each)
@@ -195,10 +185,11 @@ __device__ __forceinline__ void hsum(const RowWords& r, uint32_t h[4]) {
   for (int j = 0; j < 4; ++j) {
     uint32_t even = __dp4a(r.w[j], 0x04010000u, __dp4a(r.w[j + 1], 0x00010406u, 0u));
     uint32_t odd = __dp4a(r.w[j + 1], 0x04060401u, __dp4a(r.w[j + 2], 0x00000001u, 0u));
-    h[j] = even | (odd << 16);
+    h[j] = __byte_perm(even, odd, 0x5410);              // even | odd << 16 (both < 65536)
   }
 }
 
+template <int PF_Q, int PF_STRIP>
 __global__ void __launch_bounds__(PF_WARPS * 32, 6)
 pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
                        uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride,
@@ -235,42 +226,74 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   const int oy1 = min(oy0 + PF_STRIP, yo1);
   if (oy0 >= yo1 || xo0 + cb * 256 >= xo1) return;      // warp-uniform
 
-  // single reflection is enough: rows 2*oy-2 .. 2*oy+2 overshoot by at most 2 and h >= 4
-  auto row_ptr = [&](int r) { int rr = r < 0 ? -r : (r >= h ? 2 * h - 2 - r : r); return img + (int64_t)rr * spitch; };
+  constexpr int PF_RING = PF_Q + 4;
+  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][PF_RING][PF_RPITCH];
   const LanePlan plan = make_plan(ix0, w, lane);
-  uint32_t a[4], b[4], c[4], d[4], e[4];
-  RawRow q0 = raw_row(row_ptr(2 * oy0 - 2), plan);
-  RawRow q1 = raw_row(row_ptr(2 * oy0 - 1), plan);
-  RawRow q2 = raw_row(row_ptr(2 * oy0), plan);
-  // two output rows (four input rows) of loads stay in flight ahead of the arithmetic
-  RawRow n0 = raw_row(row_ptr(2 * oy0 + 1), plan);
-  RawRow n1 = raw_row(row_ptr(2 * oy0 + 2), plan);
-  RawRow n2 = raw_row(row_ptr(2 * oy0 + 3), plan);
-  RawRow n3 = raw_row(row_ptr(2 * oy0 + 4), plan);
-  hsum(expand_row(q0, plan, lane), a); hsum(expand_row(q1, plan, lane), b); hsum(expand_row(q2, plan, lane), c);
-  for (int oy = oy0; oy < oy1; ++oy) {
-    RawRow c0 = n0, c1 = n1;
-    n0 = n2; n1 = n3;
-    if (oy + 2 < oy1) {
-      n2 = raw_row(row_ptr(2 * oy + 5), plan);
-      n3 = raw_row(row_ptr(2 * oy + 6), plan);
-    }
-    hsum(expand_row(c0, plan, lane), d); hsum(expand_row(c1, plan, lane), e);
-    uint32_t o[4];
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]);
+  const uint32_t ring_end = ring0 + PF_RING * PF_RPITCH;
+  const uint32_t lane_main = 16 * (lane + 1);
+  const int n_in = 2 * (oy1 - oy0) + 3;            // input rows the strip consumes
+  int r_next = 2 * oy0 - 2, issued = 0;            // next input row to request
+  uint32_t req_slot = ring0, take_slot = ring0;
+
+  // request one input row (sizes forced to 0 past the end of the strip) and close the group
+  auto request = [&]() {
+    // BORDER_REFLECT_101 with a single fold: rows overshoot by at most 2 and h >= 4
+    int rr = h - 1 - abs(h - 1 - abs(r_next));
+    const uint8_t* row = img + (int64_t)rr * spitch;
+    const bool live = issued < n_in;
+    cp_async16(req_slot + plan.main_dst, row + plan.main_off, live ? plan.main_size : 0);
+    cp_async4(req_slot + plan.word_dst, row + plan.word_off, live ? plan.word_size : 0);
+    cp_async4(req_slot + plan.edge_dst, row + plan.edge_off, live ? plan.edge_size : 0);
+    asm volatile("cp.async.commit_group;");
+    ++r_next; ++issued;
+    req_slot += PF_RPITCH;
+    if (req_slot == ring_end) req_slot = ring0;
+  };
+  // wait for the oldest outstanding row, read own 16 bytes + the neighbours' halo words, horizontal pass
+  auto take = [&](uint32_t hrow[4]) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PF_Q));
+    __syncwarp();
+    RowWords r;
+    uint32_t left, right;
+    const uint32_t at = take_slot + lane_main;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]) : "r"(at));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(left) : "r"(at - 4));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(right) : "r"(at + 16));
+    r.w[0] = __byte_perm(left, 0u, plan.left_sel);
+    r.w[5] = __byte_perm(right, 0u, plan.right_sel);
+    hsum(r, hrow);
+    take_slot += PF_RPITCH;
+    if (take_slot == ring_end) take_slot = ring0;
+  };
+  // vertical [1 4 6 4 1] on packed u16 pairs, +128, >>8, and the four result bytes of two words in one permute
+  auto emit = [&](int oy, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, const uint32_t* e) {
+    uint32_t v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t v = a[j] + e[j] + 4u * (b[j] + d[j]) + 6u * c[j] + 0x00800080u;
-      o[j] = (v >> 8) & 0x00ff00ffu;
-      a[j] = c[j]; b[j] = d[j]; c[j] = e[j];
-    }
+    for (int j = 0; j < 4; ++j) v[j] = (a[j] + 4u * (b[j] + d[j])) + (e[j] + 6u * c[j]) + 0x00800080u;
     if (ox0 < xo1) {
-      uint32_t lo = __byte_perm(o[0], o[1], 0x6420), hi = __byte_perm(o[2], o[3], 0x6420);
-      uint8_t* p = out + (int64_t)oy * dpitch + ox0;
-      if (ox0 + 8 <= ow) {
-        *reinterpret_cast<uint2*>(p) = make_uint2(lo, hi);
-      } else {
-        for (int k = 0; k < 8 && ox0 + k < ow; ++k) p[k] = (uint8_t)((k < 4 ? lo >> (8 * k) : hi >> (8 * (k - 4))) & 0xffu);
-      }
+      uint2 px = make_uint2(__byte_perm(v[0], v[1], 0x7531), __byte_perm(v[2], v[3], 0x7531));
+      *reinterpret_cast<uint2*>(out + (int64_t)oy * dpitch + ox0) = px;      // ow % 8 == 0 on this path
+    }
+  };
+
+#pragma unroll
+  for (int k = 0; k < PF_Q + 1; ++k) request();
+  // six row registers rotate with period three output rows, so no value is ever moved between registers
+  uint32_t h0[4], h1[4], h2[4], h3[4], h4[4], h5[4];
+  take(h0); request();
+  take(h1); request();
+  take(h2); request();
+  for (int oy = oy0; oy < oy1; oy += 3) {
+    take(h3); request(); take(h4); request();
+    emit(oy, h0, h1, h2, h3, h4);
+    if (oy + 1 < oy1) {
+      take(h5); request(); take(h0); request();
+      emit(oy + 1, h2, h3, h4, h5, h0);
+    }
+    if (oy + 2 < oy1) {
+      take(h1); request(); take(h2); request();
+      emit(oy + 2, h4, h5, h0, h1, h2);
     }
   }
 }
@@ -312,14 +335,14 @@ static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64
   // streaming kernel: 16 B aligned rows and w % 16 == 0 (every pyramid level of 1080p / VGA); else the tiled kernel
   const bool stream_ok = vec_ok && ((dst_pitch & 7) == 0) && (w & 15) == 0 && w >= 16 && h >= 4;
   if (stream_ok) {
-    int col_blocks = (ow + 255) / 256, strips = (oh + PF_STRIP - 1) / PF_STRIP;
+    constexpr int kQ = 8, kStrip = 32;     // measured best of {8,12,16} x {32,64} (profiles/r01_pyrdown_variants.log)
+    int col_blocks = (ow + 255) / 256, strips = (oh + kStrip - 1) / kStrip;
     int64_t total_warps = (int64_t)batch * strips * col_blocks;
     int64_t blocks = (total_warps + PF_WARPS - 1) / PF_WARPS;
     if (blocks <= 0x7fffffffLL) {
-      pyr_down_stream_kernel<<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(d_src, w, h, src_pitch, src_stride, d_dst, ow, oh,
-                                                                               dst_pitch, dst_stride, col_blocks, strips,
-                                                                               total_warps, d_rects, rect_stride, src_level, d_mask,
-                                                                               mask_stride);
+      pyr_down_stream_kernel<kQ, kStrip><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
+          d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
+          rect_stride, src_level, d_mask, mask_stride);
       AGT_LAUNCH_CHECK(ctx);
       return AGT_OK;
     }
