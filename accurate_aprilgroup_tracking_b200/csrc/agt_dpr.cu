@@ -79,6 +79,63 @@ __device__ __forceinline__ int dp4(uint32_t px, int coef) {
   return d;
 }
 
+// ---- serial LM phase helpers (one thread per CTA runs them while 255 wait: keep the dependency chains short) ----
+// 1/sqrt(d) in float64 from the MUFU.RSQ seed + two Newton steps (a sqrt + a division cost ~70 dependent instructions)
+__device__ __forceinline__ double rsqrt_f64(double d) {
+  double y = (double)rsqrtf((float)d);
+  y = y * (1.5 - 0.5 * d * y * y);
+  y = y * (1.5 - 0.5 * d * y * y);
+  return y;
+}
+
+// Cholesky solve of the SPD 6x6 system A x = b (A full, row-major), multiplications by 1/L_jj instead of divisions.
+__device__ inline bool chol6_solve_fast(double A[36], double b[6]) {
+  double inv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+    if (!(d > 1e-30 && d < 1e30)) return agt_chol6_solve(A, b) && false;   // out of the float seed's range: not PD for our purposes
+    const double y = rsqrt_f64(d);
+    inv[j] = y;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = v * y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= A[i * 6 + k] * b[k];
+    b[i] = v * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= A[k * 6 + i] * b[k];
+    b[i] = v * inv[i];
+  }
+  return true;
+}
+
+// exp([w]x) for an LM step: series for |w| < 0.5 (truncation < 1e-16), libm sincos otherwise
+__device__ inline void rodrigues_step(const double w[3], double R[9]) {
+  const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  if (t2 >= 0.25) { agt_rodrigues(w, R); return; }
+  const double a = 1.0 - t2 / 6.0 * (1.0 - t2 / 20.0 * (1.0 - t2 / 42.0 * (1.0 - t2 / 72.0 * (1.0 - t2 / 110.0 * (1.0 - t2 / 156.0)))));
+  const double b = 0.5 * (1.0 - t2 / 12.0 * (1.0 - t2 / 30.0 * (1.0 - t2 / 56.0 * (1.0 - t2 / 90.0 * (1.0 - t2 / 132.0 * (1.0 - t2 / 182.0))))));
+  const double c = 1.0 - b * t2;
+  R[0] = c + b * w[0] * w[0];        R[1] = b * w[0] * w[1] - a * w[2]; R[2] = b * w[0] * w[2] + a * w[1];
+  R[3] = b * w[1] * w[0] + a * w[2]; R[4] = c + b * w[1] * w[1];        R[5] = b * w[1] * w[2] - a * w[0];
+  R[6] = b * w[2] * w[0] - a * w[1]; R[7] = b * w[2] * w[1] + a * w[0]; R[8] = c + b * w[2] * w[2];
+}
+
 // packed signed-byte coefficient words (little endian: byte 0 multiplies the left-most pixel)
 constexpr int C_DX0 = (int)0x000100FF;   // (-1, 0, 1, 0)
 constexpr int C_DX1 = (int)0x0100FF00;   // ( 0,-1, 0, 1)
@@ -285,13 +342,15 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       S.wsum[wid][28] = (double)cnt;
     }
     __syncthreads();
-    if (tid < 29) {
-      double s = 0.0;
+    if (wid == 0) {
+      if (lane < 29) {
+        double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < DPR_WARPS; ++w) s += S.wsum[w][tid];
-      S.tot[tid] = s;
+        for (int w = 0; w < DPR_WARPS; ++w) s += S.wsum[w][lane];
+        S.tot[lane] = s;
+      }
+      __syncwarp();
     }
-    __syncthreads();
 
     // ================= LM bookkeeping (one thread, float64) ================================
     if (tid == 0) {
@@ -333,10 +392,10 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
         for (int p = 0; p < 6; ++p)
           for (int q = p; q < 6; ++q) { A[p * 6 + q] = Hc[k]; A[q * 6 + p] = Hc[k]; ++k; }
         for (int p = 0; p < 6; ++p) { A[p * 6 + p] += lam * A[p * 6 + p]; d[p] = -bc[p]; }
-        if (agt_chol6_solve(A, d)) {
+        if (chol6_solve_fast(A, d)) {
           for (int p = 0; p < 6; ++p) dstep[p] = d[p];
           double E[9];
-          agt_rodrigues(d, E);
+          rodrigues_step(d, E);
           for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
           for (int p = 0; p < 3; ++p) tt[p] = tc[p] + d[3 + p];

@@ -25,8 +25,7 @@ t0 = time.time()
 with mp.get_context("fork").Pool(min(32, os.cpu_count())) as pool:
     ref = pool.map(work, range(N))
 print("oracle time", time.time() - t0, "cpus", os.cpu_count())
-for mode in ("2", "3"):
-    os.environ["AGT_DPR_MINB"] = mode
+for mode in ("current",):
     for _ in range(2):
         res = ctx.refine(pyr, init.reshape(N, 1, 6), 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
