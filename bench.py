@@ -37,6 +37,9 @@ BYTES_PER_SAMPLE_EVAL = 36          # 16 B model record + 4 B inte
 BYTES_PER_POSE_FIXED = 156
 LK_BYTES_PER_CORNER = 5008
 PYR_BYTES_PER_1080P = 2754000
+# dram__bytes_read.sum + dram__bytes_write.sum of one dpr_kernel launch, per pose, from the ncu --set full capture
+# summarised in profiles/r01_ncu_dpr_kernel.txt (67.19 MB for 1024 poses of this workload)
+DPR_NCU_DRAM_BYTES_PER_POSE = 67.19e6 / 1024
 
 
 def measured_peaks():
@@ -104,39 +107,41 @@ def make_poses(n: int, seed: int):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle (there is no reference implementation of dense refinement, see oracle/)
 # ------------------------------------------------------------------------------------------
-def _cpu_refine_one(args):
-    frame, init = args
+_CPU = {}
+
+
+def _cpu_refine_one(i):
     import cv2
     from oracle import dpr_oracle, lk_oracle
     cv2.setNumThreads(1)
-    model = _cpu_refine_one.model
     t0 = time.perf_counter()
-    pyr = lk_oracle.pyramid_cv(frame)
-    out = dpr_oracle.refine(pyr, model, CAM.mtx, init)
+    pyr = lk_oracle.pyramid_cv(_CPU["frames"][i])
+    out = dpr_oracle.refine(pyr, _CPU["model"], CAM.mtx, _CPU["init"][i])
     return time.perf_counter() - t0, out["pose"], out["evals"]
 
 
-def _cpu_worker_init():
+def cpu_refine(frames: np.ndarray, init: np.ndarray, workers: int, repeats: int = 1):
+    """Refine frames with the oracle on `workers` processes (forked: frames and model are inherited, not pickled).
+    Returns (list of wall seconds per repeat, poses)."""
     from oracle import dpr_oracle
     s, tg, n, c = synth.surface_model()
-    _cpu_refine_one.model = dpr_oracle.Model(s, tg, n, c, synth.model_pitch())
-
-
-def cpu_refine(frames: np.ndarray, init: np.ndarray, workers: int):
-    """Refine frames with the oracle on `workers` processes; returns (wall seconds, poses)."""
-    jobs = [(frames[i], init[i]) for i in range(len(frames))]
+    _CPU.update(frames=frames, init=init, model=dpr_oracle.Model(s, tg, n, c, synth.model_pitch()))
+    idx = list(range(len(frames)))
+    walls = []
     if workers <= 1:
-        _cpu_worker_init()
-        t0 = time.perf_counter()
-        res = [_cpu_refine_one(j) for j in jobs]
-        return time.perf_counter() - t0, np.array([r[1] for r in res])
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            res = [_cpu_refine_one(i) for i in idx]
+            walls.append(time.perf_counter() - t0)
+        return walls, np.array([r[1] for r in res])
     import multiprocessing as mp
-    with mp.get_context("fork").Pool(workers, initializer=_cpu_worker_init) as pool:
-        pool.map(_cpu_refine_one, jobs[:workers])                  # warm the workers (imports, model)
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_refine_one, jobs, chunksize=1)
-        wall = time.perf_counter() - t0
-    return wall, np.array([r[1] for r in res])
+    with mp.get_context("fork").Pool(workers) as pool:
+        pool.map(_cpu_refine_one, idx[:workers])                   # warm the workers (imports)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_refine_one, idx, chunksize=1)
+            walls.append(time.perf_counter() - t0)
+    return walls, np.array([r[1] for r in res])
 
 
 def sample_frames_for_cpu(n: int, seed: int):
@@ -166,19 +171,16 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    per_step = max(workers * 2, 16)
-    n = per_step
+    n = max(workers * 8, 32)                       # frames per step: a bounded sample of the 4096-frame workload
     frames, truth, init = sample_frames_for_cpu(n, 2000)
-    times = []
-    for it in range(args.warmup + args.steps):
-        wall, _ = cpu_refine(frames, init, workers)
-        if it >= args.warmup:
-            times.append(wall)
+    steps = min(args.steps, 10)                    # keep the whole run within a couple of minutes
+    walls, _ = cpu_refine(frames, init, workers, repeats=args.warmup + steps)
+    times = walls[args.warmup:]
     total = sum(times)
     value = n * len(times) / total
     line = {
         "impl": "reference", "metric": "refined poses/sec", "value": value, "unit": "poses/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "batched dense pose refinement, 1080p, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
                    "frames_per_step": n, "note": "CPU oracle (numpy/OpenCV pyramid + LM); no reference code exists for this stage"},
@@ -334,7 +336,8 @@ def run_gpu(args):
     if not args.no_cpu:
         ns = args.cpu_sample
         frames_s = pyr.frames[:ns].cpu().numpy()
-        wall, cpu_pose = cpu_refine(frames_s, init[:ns], 1)
+        walls, cpu_pose = cpu_refine(frames_s, init[:ns], 1)
+        wall = walls[0]
         dr = [2 * math.asin(min(1.0, 0.5 * np.linalg.norm(synth.rodrigues(cpu_pose[i, :3]) - synth.rodrigues(pose[i, :3]))))
               for i in range(ns)]
         cpu = {"value": ns / wall, "unit": "poses/s", "cores": 1, "kind": "port",
@@ -357,9 +360,10 @@ def run_gpu(args):
         "lm": {"mean_evals": float(evals.mean()), "max_evals": int(evals.max()), "mean_samples": float(nvalid.mean()),
                "converged_frac": float((status == 1).mean()), "median_trans_err_vs_truth_m": float(np.median(dt))},
         "roofline": {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind,
-                     "note": "algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); the kernel keeps "
-                             "the ROI in shared memory, so DRAM traffic is far below this figure (see profiles/)"},
+                     "traffic": DPR_NCU_DRAM_BYTES_PER_POSE * B, "peak_kind": peak_kind, "algorithmic_bytes": algo_bytes,
+                     "note": "per launch; algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); "
+                             "traffic = ncu dram bytes (profiles/r01_ncu_dpr_kernel.txt): the ROI is staged once in shared memory and "
+                             "reused by every LM evaluation, so the kernel is FP32/shared-memory issue bound, not HBM bound"},
         "pyramid_roofline": {"kernel": "pyr_down_stream_kernel (full frames, 3 levels)", "bound": "hbm",
                              "achieved": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9 / peak},
