@@ -62,7 +62,7 @@ class BatchedPoseDetector:
         ctx.build_pyramid(cur)                                                   # K1
         tracked_tags = None
         if self.use_lk and self.have_prev_frame:
-            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts)                          # K2
+            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntg)              # K2 (frames with < 2 tags only)
             before = ntg.clone()
             ctx.lk_merge(nxt, st, self.prev_valid, img, val, ntg)
             tracked_tags = ntg - before

@@ -155,8 +155,9 @@ class AgtContext:
         return out
 
     # -- K2 ---------------------------------------------------------------------------
-    def lk(self, prev: Pyramid, nxt: Pyramid, prev_pts):
-        """prev_pts [B,P,2] float32 -> (next_pts [B,P,2] f32, status [B,P] u8, err [B,P] f32)."""
+    def lk(self, prev: Pyramid, nxt: Pyramid, prev_pts, n_tags=None):
+        """prev_pts [B,P,2] float32 -> (next_pts [B,P,2] f32, status [B,P] u8, err [B,P] f32).
+        n_tags [B] i32: frames with >= 2 detected tags are skipped (pipeline fallback rule)."""
         t = self.torch
         pts = self._dev(prev_pts, t.float32)
         b, p = int(pts.shape[0]), int(pts.shape[1])
@@ -164,8 +165,12 @@ class AgtContext:
         st = t.empty((b, p), dtype=t.uint8, device=self.tdev)
         err = t.empty((b, p), dtype=t.float32, device=self.tdev)
         self._use_current_stream()
-        self._check(self.lib.agt_lk(self.h, C.byref(prev.desc), C.byref(nxt.desc), self._p(pts), self._p(out), self._p(st),
-                                    self._p(err), b, p))
+        if n_tags is None:
+            self._check(self.lib.agt_lk(self.h, C.byref(prev.desc), C.byref(nxt.desc), self._p(pts), self._p(out), self._p(st),
+                                        self._p(err), b, p))
+        else:
+            self._check(self.lib.agt_lk_fallback(self.h, C.byref(prev.desc), C.byref(nxt.desc), self._p(pts), self._p(out),
+                                                 self._p(st), self._p(err), self._p(n_tags), b, p))
         return out, st, err
 
     def lk_merge(self, tracked, status, prev_valid, img_pts, valid, n_tags):

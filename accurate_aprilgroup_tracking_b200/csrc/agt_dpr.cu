@@ -20,7 +20,11 @@
 // (the cost in float64 from the start); one thread runs the 6x6 Cholesky / LM
 // bookkeeping in float64.  Samples whose footprint leaves the staged tile fall
 // back to global loads, so results do not depend on the tile size.
+#include <cooperative_groups.h>
+
 #include "agt_dpr_plan.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -142,6 +146,11 @@ constexpr int C_DX1 = (int)0x0100FF00;   // ( 0,-1, 0, 1)
 constexpr int C_SM0 = (int)0x00030A03;   // ( 3,10, 3, 0)
 constexpr int C_SM1 = (int)0x030A0300;   // ( 0, 3,10, 3)
 
+// kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
+// the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
+// slice of the samples, the partial sums meet in CTA 0 through distributed shared memory, CTA 0 runs the LM step
+// and the others read the new trial pose back over DSMEM.  Two cluster barriers per evaluation.
+template <int kCluster>
 __global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
            const double* __restrict__ init, int n_hyp, const uint8_t* __restrict__ mask, double* __restrict__ pose_out, float* __restrict__ cost_out,
@@ -150,9 +159,10 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   extern __shared__ __align__(16) uint8_t s_tile[];
   __shared__ DprShared S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t job = blockIdx.x;
+  const int64_t job = blockIdx.x / kCluster;
+  const int crank = kCluster > 1 ? (int)(blockIdx.x % kCluster) : 0;     // == cluster.block_rank() for (kCluster,1,1) clusters
   const int64_t frame = job / n_hyp;
-  if (mask != nullptr && mask[frame] == 0) return;     // skipped frame: none of its outputs is written
+  if (mask != nullptr && mask[frame] == 0) return;     // skipped frame: none of its outputs is written (whole cluster)
 
   double* const Rc = S.Rc; double* const tc = S.tc; double* const Hc = S.Hc; double* const bc = S.bc;
   double* const Rt = S.Rt; double* const tt = S.tt; double* const dstep = S.dstep;
@@ -244,13 +254,14 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     int seg = 0;
     // software pipeline: the model record of the next sample is requested before this one is consumed
     float4 sm_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < n_act_samples) {
-      while (tid >= S.act_prefix[seg + 1]) ++seg;
-      sm_next = __ldg(&samples[S.act_begin[seg] + (tid - S.act_prefix[seg])]);
+    const int j0 = crank * DPR_THREADS + tid;
+    if (j0 < n_act_samples) {
+      while (j0 >= S.act_prefix[seg + 1]) ++seg;
+      sm_next = __ldg(&samples[S.act_begin[seg] + (j0 - S.act_prefix[seg])]);
     }
-    for (int j = tid; j < n_act_samples; j += DPR_THREADS) {
+    for (int j = j0; j < n_act_samples; j += kCluster * DPR_THREADS) {
       const float4 sm = sm_next;
-      const int jn = j + DPR_THREADS;
+      const int jn = j + kCluster * DPR_THREADS;
       if (jn < n_act_samples) {
         while (jn >= S.act_prefix[seg + 1]) ++seg;
         sm_next = __ldg(&samples[S.act_begin[seg] + (jn - S.act_prefix[seg])]);
@@ -351,9 +362,21 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       }
       __syncwarp();
     }
+    if (kCluster > 1) {
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();                                   // every CTA's partial sums are in its S.tot
+      if (crank == 0 && wid == 0) {
+        if (lane < 29) {
+          double s = S.tot[lane];
+          for (int r = 1; r < kCluster; ++r) s += cluster.map_shared_rank(&S, r)->tot[lane];
+          S.tot[lane] = s;
+        }
+        __syncwarp();
+      }
+    }
 
     // ================= LM bookkeeping (one thread, float64) ================================
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
       double Hn[21], bn[6];
       for (int k = 0; k < 21; ++k) Hn[k] = S.tot[k];
       for (int k = 0; k < 6; ++k) bn[k] = S.tot[21 + k];
@@ -409,8 +432,26 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       S.stop = need_step ? 0 : 1;
       S.cc = cc; S.lam = lam; S.nc = nc; S.evals = evals; S.status = status;
     }
+    if (kCluster > 1) {
+      cg::cluster_group cluster = cg::this_cluster();
+      cluster.sync();                                   // CTA 0 has published the next trial pose (or stop)
+      if (crank != 0) {
+        const DprShared* S0 = cluster.map_shared_rank(&S, 0);
+        if (tid < 9) { S.R[tid] = S0->R[tid]; S.Rd[tid] = S0->Rd[tid]; }
+        if (tid < 3) { S.t[tid] = S0->t[tid]; S.td[tid] = S0->td[tid]; }
+        if (tid == 0) S.stop = S0->stop;
+      }
+    }
     __syncthreads();
     if (S.stop) break;
+  }
+  if (kCluster > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (crank == 0 && tid == 0)
+      for (int r = 1; r < kCluster; ++r) S.left_roi |= cluster.map_shared_rank(&S, r)->left_roi;
+    cluster.sync();                                     // keep every CTA's shared memory alive until CTA 0 has read it
+    if (crank != 0) return;
   }
 
   if (tid == 0) {
@@ -482,12 +523,42 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
   if (jobs > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: batch*n_hyp too large");
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
     attr_set[ctx->device & 63] = true;
   }
-  // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower
-  dpr_kernel<<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
-                                                                      n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+  // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower.
+  // Small batches (fewer refinements than 2 CTA slots per SM) are spread over clusters of 2 / 4 / 8 CTAs.
+  int cluster = 1;
+  const int64_t slots = 2LL * ctx->sm_count;
+  while (cluster < 8 && jobs * (cluster * 2) <= slots) cluster *= 2;
+  if (cluster == 1) {
+    dpr_kernel<1><<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
+                                                                         n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status,
+                                                                         d_left_roi);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(jobs * cluster));
+    cfg.blockDim = dim3(DPR_THREADS);
+    cfg.dynamicSmemBytes = TILE_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    agt_pyramid pv = *pyr;
+    const float4* smp = ctx->model.samples;
+    cudaError_t e;
+    if (cluster == 2)
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<2>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+    else if (cluster == 4)
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<4>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+    else
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<8>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+    if (e != cudaSuccess) AGT_FAIL(ctx, AGT_ERR_CUDA, "agt_refine: cluster launch failed: %s", cudaGetErrorString(e));
+  }
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

@@ -68,7 +68,8 @@ __device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
-          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total) {
+          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total,
+          const int32_t* __restrict__ skip_if_tags_ge2) {
   __shared__ WarpSmem smem[WARPS_PER_CTA];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -76,6 +77,10 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
   if (gid >= total) return;
   WarpSmem& S = smem[wid];
   const int frame = (int)(gid / n_pts);
+  if (skip_if_tags_ge2 != nullptr && skip_if_tags_ge2[frame] >= 2) {     // stage-2 rule: tracking only backs up frames with < 2 tags
+    if (lane == 0) { next_pts[gid * 2] = prev_pts[gid * 2]; next_pts[gid * 2 + 1] = prev_pts[gid * 2 + 1]; status_out[gid] = 0; err_out[gid] = 0.f; }
+    return;
+  }
   const float ptx = prev_pts[gid * 2], pty = prev_pts[gid * 2 + 1];
 
   float outx = 0.f, outy = 0.f;
@@ -278,9 +283,24 @@ extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint
   return AGT_OK;
 }
 
+static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts, float* d_next_pts,
+                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags);
+
 extern "C" int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
                       float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts) {
   if (!ctx) return AGT_ERR_INVALID;
+  return lk_impl(ctx, prev, next, d_prev_pts, d_next_pts, d_status, d_err, batch, n_pts, nullptr);
+}
+
+extern "C" int agt_lk_fallback(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
+                               float* d_next_pts, uint8_t* d_status, float* d_err, const int32_t* d_n_tags, int batch, int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_n_tags) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_fallback: d_n_tags is NULL");
+  return lk_impl(ctx, prev, next, d_prev_pts, d_next_pts, d_status, d_err, batch, n_pts, d_n_tags);
+}
+
+static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts, float* d_next_pts,
+                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags) {
   if (!prev || !next || batch < 0 || n_pts < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null pyramid or negative size");
   if ((int64_t)batch * n_pts > 0 && (!d_prev_pts || !d_next_pts || !d_status || !d_err))
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null point / status / err buffer");
@@ -294,7 +314,7 @@ extern "C" int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* 
   int64_t blocks = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: batch too large");
   lk_kernel<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status,
-                                                                       d_err, n_pts, total);
+                                                                       d_err, n_pts, total, d_n_tags);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

@@ -109,6 +109,10 @@ int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pit
 int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
            float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts);
 
+/* Same, but frames with d_n_tags[b] >= 2 are skipped (status 0, points copied through): in the pipeline tracking
+ * only backs up frames in which fewer than two tags were detected. */
+int agt_lk_fallback(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
+                    float* d_next_pts, uint8_t* d_status, float* d_err, const int32_t* d_n_tags, int batch, int n_pts);
 /* Stage-2 integration rule: for every frame with fewer than 2 detected tags, re-admit each
  * tag that was accepted in the previous frame (d_prev_valid) and whose four corners were all tracked
  * (d_status == 1): its tracked corners are copied into d_img_pts and its d_valid entries set.
