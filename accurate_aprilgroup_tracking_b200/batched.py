@@ -27,7 +27,8 @@ from .context import AgtContext
 
 class BatchedPoseDetector:
     def __init__(self, ctx: AgtContext, n_streams: int, width: int, height: int, obj_pts: np.ndarray,
-                 enhance_ape: bool = True, use_lk: bool = True, use_dense_refine: bool = True, levels: int = 4):
+                 enhance_ape: bool = True, use_lk: bool = True, use_dense_refine: bool = True, levels: int = 4,
+                 use_graphs: bool = True):
         t = ctx.torch
         self.ctx, self.n, self.enhance_ape = ctx, int(n_streams), enhance_ape
         self.use_lk, self.use_dense_refine = use_lk, use_dense_refine
@@ -37,32 +38,42 @@ class BatchedPoseDetector:
         self.cur = 0
         self.state = ctx.new_stream_state(self.n)
         dev = ctx.tdev
+        # static buffers: the per-step work is a fixed launch sequence, captured once per pyramid slot into a CUDA graph
+        self.in_img = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
+        self.in_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
+        self.in_ntags = t.zeros(self.n, dtype=t.int32, device=dev)
         self.prev_pts = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
         self.prev_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
-        self.have_prev_frame = False
+        self.use_graphs = use_graphs
+        self._graphs = [None, None]
+        self._outs = [None, None]
+        self._steps = 0
+        self.kernels_per_step = 0
         if use_dense_refine and ctx._model is None:
             ctx.set_synthetic_model()
+
+    def reset(self):
+        """Forget all stream state (fresh streams); captured graphs stay valid because the buffers are reused."""
+        self.state.zero_()
+        self.prev_pts.zero_()
+        self.prev_valid.zero_()
 
     @property
     def frames(self):
         """Level-0 buffer [S,H,W] the caller fills (or renders into) before ``step``."""
         return self.pyr[self.cur].frames
 
-    def step(self, img_pts, valid, n_tags, frames=None):
-        """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),
-        n_tags [S] i32 accepted detections.  ``frames`` [S,H,W] u8 is copied into the current slot
-        unless the caller wrote ``self.frames`` directly.  Returns a dict of device tensors."""
+    def _body(self, slot: int):
+        """One frame of every stream: fixed launch sequence over static buffers (graph-capturable)."""
         ctx, t = self.ctx, self.ctx.torch
-        cur, prv = self.pyr[self.cur], self.pyr[1 - self.cur]
-        if frames is not None:
-            ctx.upload_frames(cur, frames)
-        img = ctx._dev(img_pts, t.float32).clone()
-        val = ctx._dev(valid, t.uint8).clone()
-        ntg = ctx._dev(n_tags, t.int32).clone()
+        cur, prv = self.pyr[slot], self.pyr[1 - slot]
+        img, val, ntg = self.in_img.clone(), self.in_valid.clone(), self.in_ntags.clone()
         ctx.build_pyramid(cur)                                                   # K1
         tracked_tags = None
-        if self.use_lk and self.have_prev_frame:
-            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntg)              # K2 (frames with < 2 tags only)
+        if self.use_lk:
+            # K2: only frames with < 2 detected tags are tracked; on the very first frame prev_valid is all zero,
+            # so nothing can be re-admitted from the (not yet written) previous slot
+            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntg)
             before = ntg.clone()
             ctx.lk_merge(nxt, st, self.prev_valid, img, val, ntg)
             tracked_tags = ntg - before
@@ -76,12 +87,41 @@ class BatchedPoseDetector:
             pose = t.where(good, refined["pose"].reshape(self.n, 6), pose)
         accepted, flag = ctx.ape_update(self.state, ntg, pose, ok, err, self.enhance_ape)   # K0
         # corners of the accepted frame feed the next LK step (PoseDetector._prev_corners)
-        self.prev_pts = img
-        self.prev_valid = val * accepted.unsqueeze(1)
-        self.have_prev_frame = True
-        self.cur = 1 - self.cur
+        self.prev_pts.copy_(img)
+        self.prev_valid.copy_(val * accepted.unsqueeze(1))
         return {"pose": self.state[:, 1:7].clone(), "accepted": accepted, "error_flag": flag, "reproj_err": err,
                 "n_tags": ntg, "tracked_tags": tracked_tags, "refine": refined}
+
+    def step(self, img_pts, valid, n_tags, frames=None):
+        """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),
+        n_tags [S] i32 accepted detections.  ``frames`` [S,H,W] u8 is copied into the current slot
+        unless the caller wrote ``self.frames`` directly.  Returns a dict of device tensors (valid until the
+        step after next when CUDA graphs are in use: the graph of a slot reuses its output buffers)."""
+        ctx, t = self.ctx, self.ctx.torch
+        slot = self.cur
+        if frames is not None:
+            ctx.upload_frames(self.pyr[slot], frames)
+        self.in_img.copy_(ctx._dev(img_pts, t.float32))
+        self.in_valid.copy_(ctx._dev(valid, t.uint8))
+        self.in_ntags.copy_(ctx._dev(n_tags, t.int32))
+        if self.use_graphs and self._graphs[slot] is not None:
+            self._graphs[slot].replay()
+            out = self._outs[slot]
+        elif self.use_graphs and self._steps >= 2:
+            # both slots have run eagerly once (lazy one-time setup is done): capture this slot and replay it
+            g = t.cuda.CUDAGraph()
+            t.cuda.synchronize(ctx.tdev)
+            with t.cuda.graph(g):
+                out = self._body(slot)
+            g.replay()
+            self._graphs[slot], self._outs[slot] = g, out
+        else:
+            l0 = ctx.launch_count()
+            out = self._body(slot)
+            self.kernels_per_step = ctx.launch_count() - l0     # what a graph replay launches, too
+        self._steps += 1
+        self.cur = 1 - slot
+        return out
 
 
 def pack_detections(dets_per_stream, n_tags_total: int = synth.NUM_TAGS):
