@@ -133,40 +133,44 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, i
 // ---------------------------------------------------------------------------------------------
 constexpr int PF_WARPS = 4;
 
-struct RowWords { uint32_t w[6]; };   // w[0] = left halo, w[1..4] = own 16 bytes, w[5] = right halo
-
-// Per-lane, loop-invariant description of what a lane requests from every input row.  The kernel is only used
-// for w % 16 == 0, so a lane's 16 bytes are either fully inside the row or start exactly at w; the reflect-101
-// halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3]) come from one aligned word and a byte permute.
+// Per-lane, loop-invariant description of what a lane requests from every input row.  A lane owns NW units of
+// 16 input bytes (= 8*NW output pixels).  The kernel is only used for w % 16 == 0, so a unit is either fully inside
+// the row or starts exactly at w; the reflect-101 halo bytes (p[-1]=p[1], p[-2]=p[2], p[w]=p[w-2], p[w+1]=p[w-3])
+// come from one aligned word and a byte permute.
 //
 // Rows travel global -> shared with cp.async (LDGSTS) into a per-warp ring, PF_Q rows ahead of the row being
-// consumed: no registers are tied up by loads in flight, so ~40 warps/SM each keep ~4 KB on the wire - enough
-// to cover the HBM latency-bandwidth product - and the halo words of a lane are simply its neighbours' words
-// in the ring.  Ring row layout: [12 pad][4 left halo][32 x 16 B main][4 right halo][12 pad][16 dummy] = 560 B.
-constexpr int PF_RPITCH = 16 * 35;        // + one 16 B dummy target for zero-size requests
-
+// consumed: no registers are tied up by loads in flight, and the halo words of a lane are simply its neighbours'
+// words in the ring.  Ring row: [12 pad][4 left halo][32 lanes x 16*NW B][4 right halo][12 pad].
+// Every lane executes the same (predicated) requests per row; a size of 0 masks the lane off.
+template <int NW>
 struct LanePlan {
-  // every lane executes the same three (predicated) requests per row; size 0 masks the lane off
-  int main_off, main_size, main_dst;   // 16-byte request
-  int word_off, word_size, word_dst;   // 4-byte request of the lane that starts exactly at w (reflect source p[w-4..w-1])
+  int unit_size[NW];         // 16-byte request of unit k is live
+  int refl_size, refl_dst;   // the unit that starts exactly at w receives p[w-4..w-1] in its first word
   int edge_off, edge_size, edge_dst;   // 4-byte halo request of lanes 0 / 31
-  uint32_t left_sel, right_sel;   // byte_perm selectors for the halo words (identity unless reflecting)
+  uint32_t left_sel, right_sel;        // byte_perm selectors of the halo words (identity unless reflecting)
+  uint32_t unit_sel[NW];               // selector of the first word of unit k >= 1 (it is unit k-1's right neighbour)
 };
 
-__device__ __forceinline__ LanePlan make_plan(int ix0, int w, int lane) {
-  LanePlan p;
-  const bool main16 = ix0 + 16 <= w, main4 = ix0 == w;
-  p.main_off = main16 ? ix0 : 0; p.main_size = main16 ? 16 : 0; p.main_dst = main16 ? 16 * (lane + 1) : 16 * 34;
-  p.word_off = w - 4; p.word_size = main4 ? 4 : 0; p.word_dst = main4 ? 16 * (lane + 1) : 0;
-  p.left_sel = ix0 == 0 ? 0x1244u : 0x3210u;          // (-, -, p[2], p[1]) from p[0..3]
-  p.right_sel = ix0 + 16 == w ? 0x4412u : 0x3210u;     // (p[w-2], p[w-3], -, -) from p[w-4..w-1]
+template <int NW>
+__device__ __forceinline__ LanePlan<NW> make_plan(int ix0, int w, int lane) {
+  LanePlan<NW> p;
+  p.refl_size = 0; p.refl_dst = 0;
+#pragma unroll
+  for (int k = 0; k < NW; ++k) {
+    const int ux = ix0 + 16 * k;
+    p.unit_size[k] = ux + 16 <= w ? 16 : 0;
+    p.unit_sel[k] = ux == w ? 0x4412u : 0x3210u;       // (p[w-2], p[w-3], -, -) from p[w-4..w-1]
+    if (ux == w) { p.refl_size = 4; p.refl_dst = 16 + 16 * NW * lane + 16 * k; }
+  }
+  p.left_sel = ix0 == 0 ? 0x1244u : 0x3210u;           // (-, -, p[2], p[1]) from p[0..3]
+  p.right_sel = ix0 + 16 * NW == w ? 0x4412u : 0x3210u;
   p.edge_off = 0; p.edge_size = 0; p.edge_dst = 4;     // bytes 0..11 of a ring row are padding
   if (lane == 0) {
     p.edge_size = 4; p.edge_dst = 12;
     p.edge_off = ix0 >= 4 ? ix0 - 4 : 0;
-  } else if (lane == 31 && ix0 + 16 <= w) {
-    p.edge_size = 4; p.edge_dst = 16 * 33;
-    p.edge_off = ix0 + 20 <= w ? ix0 + 16 : w - 4;
+  } else if (lane == 31 && ix0 + 16 * NW <= w) {
+    p.edge_size = 4; p.edge_dst = 16 + 16 * NW * 32;
+    p.edge_off = ix0 + 16 * NW + 4 <= w ? ix0 + 16 * NW : w - 4;
   }
   return p;
 }
@@ -179,22 +183,20 @@ __device__ __forceinline__ void cp_async4(uint32_t smem, const void* gmem, int s
   asm volatile("{ .reg .pred p; setp.ne.s32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 4; }" ::"r"(smem), "l"(gmem), "r"(size));
 }
 
-// horizontal [1 4 6 4 1] at 8 even positions -> 4 packed words (2 x u16 each)
-__device__ __forceinline__ void hsum(const RowWords& r, uint32_t h[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t even = __dp4a(r.w[j], 0x04010000u, __dp4a(r.w[j + 1], 0x00010406u, 0u));
-    uint32_t odd = __dp4a(r.w[j + 1], 0x04060401u, __dp4a(r.w[j + 2], 0x00000001u, 0u));
-    h[j] = __byte_perm(even, odd, 0x5410);              // even | odd << 16 (both < 65536)
-  }
-}
-
-template <int PF_Q, int PF_STRIP>
-__global__ void __launch_bounds__(PF_WARPS * 32, 6)
+// Streaming pyrDown.  Lane = 8*NW output pixels; horizontal 5-tap = two dp4a per output into packed 2 x u16
+// (max 16*255 = 4080); vertical 5-tap on the packed words (max 16*4080+128 < 65536, the halves never carry into each
+// other); +128, >>8 and byte packing in one permute per two words; 8*NW-byte stores.  A warp walks down a strip of
+// PF_STRIP output rows; six packed row registers rotate with period three output rows, so nothing is ever moved.
+template <int PF_Q, int PF_STRIP, int NW>
+__global__ void __launch_bounds__(PF_WARPS * 32, NW == 1 ? 6 : 4)
 pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
                        uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride,
                        int col_blocks, int strips, int64_t total_warps, const int32_t* __restrict__ rects, int rect_stride,
                        int src_level, const uint8_t* __restrict__ mask, int mask_stride) {
+  constexpr int OUTS = 8 * NW;                 // output pixels per lane
+  constexpr int NWORD = 4 * NW;                // own 32-bit words per lane and row
+  constexpr int RPITCH = 16 + 16 * NW * 32 + 16;
+  constexpr int PF_RING = PF_Q + 4;
   const int lane = threadIdx.x & 31;
   int64_t wg = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
   if (wg >= total_warps) return;
@@ -212,7 +214,7 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   if (rects != nullptr) {
     const int32_t* r = rects + frame * rect_stride;
     const int sh = src_level + 1, rnd = (1 << sh) - 1;
-    xo0 = max(0, (r[0] >> sh) - 2) & ~7;
+    xo0 = max(0, (r[0] >> sh) - 2) & ~(OUTS - 1);
     yo0 = max(0, (r[1] >> sh) - 2);
     xo1 = min(ow, (((r[2] + rnd) >> sh) + 2 + 7) & ~7);
     yo1 = min(oh, ((r[3] + rnd) >> sh) + 2);
@@ -220,18 +222,17 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   }
   const uint8_t* img = src + frame * sstride;
   uint8_t* out = dst + frame * dstride;
-  const int ox0 = xo0 + cb * 256 + lane * 8;
+  const int ox0 = xo0 + cb * (32 * OUTS) + lane * OUTS;
   const int ix0 = 2 * ox0;
   const int oy0 = yo0 + strip * PF_STRIP;
   const int oy1 = min(oy0 + PF_STRIP, yo1);
-  if (oy0 >= yo1 || xo0 + cb * 256 >= xo1) return;      // warp-uniform
+  if (oy0 >= yo1 || xo0 + cb * (32 * OUTS) >= xo1) return;      // warp-uniform
 
-  constexpr int PF_RING = PF_Q + 4;
-  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][PF_RING][PF_RPITCH];
-  const LanePlan plan = make_plan(ix0, w, lane);
+  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][PF_RING][RPITCH];
+  const LanePlan<NW> plan = make_plan<NW>(ix0, w, lane);
   const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]);
-  const uint32_t ring_end = ring0 + PF_RING * PF_RPITCH;
-  const uint32_t lane_main = 16 * (lane + 1);
+  const uint32_t ring_end = ring0 + PF_RING * RPITCH;
+  const uint32_t lane_main = 16 + 16 * NW * lane;
   const int n_in = 2 * (oy1 - oy0) + 3;            // input rows the strip consumes
   int r_next = 2 * oy0 - 2, issued = 0;            // next input row to request
   uint32_t req_slot = ring0, take_slot = ring0;
@@ -242,45 +243,62 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
     int rr = h - 1 - abs(h - 1 - abs(r_next));
     const uint8_t* row = img + (int64_t)rr * spitch;
     const bool live = issued < n_in;
-    cp_async16(req_slot + plan.main_dst, row + plan.main_off, live ? plan.main_size : 0);
-    cp_async4(req_slot + plan.word_dst, row + plan.word_off, live ? plan.word_size : 0);
+#pragma unroll
+    for (int k = 0; k < NW; ++k) cp_async16(req_slot + lane_main + 16 * k, row + ix0 + 16 * k, live ? plan.unit_size[k] : 0);
+    cp_async4(req_slot + plan.refl_dst, row + w - 4, live ? plan.refl_size : 0);
     cp_async4(req_slot + plan.edge_dst, row + plan.edge_off, live ? plan.edge_size : 0);
     asm volatile("cp.async.commit_group;");
     ++r_next; ++issued;
-    req_slot += PF_RPITCH;
+    req_slot += RPITCH;
     if (req_slot == ring_end) req_slot = ring0;
   };
-  // wait for the oldest outstanding row, read own 16 bytes + the neighbours' halo words, horizontal pass
-  auto take = [&](uint32_t hrow[4]) {
+  // wait for the oldest outstanding row, read own bytes + the neighbours' halo words, horizontal pass
+  auto take = [&](uint32_t hrow[NWORD]) {
     asm volatile("cp.async.wait_group %0;" ::"n"(PF_Q));
     __syncwarp();
-    RowWords r;
-    uint32_t left, right;
+    uint32_t wv[NWORD + 2];
     const uint32_t at = take_slot + lane_main;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]) : "r"(at));
+#pragma unroll
+    for (int k = 0; k < NW; ++k)
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(wv[1 + 4 * k]), "=r"(wv[2 + 4 * k]), "=r"(wv[3 + 4 * k]), "=r"(wv[4 + 4 * k]) : "r"(at + 16 * k));
+    uint32_t left, right;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(left) : "r"(at - 4));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(right) : "r"(at + 16));
-    r.w[0] = __byte_perm(left, 0u, plan.left_sel);
-    r.w[5] = __byte_perm(right, 0u, plan.right_sel);
-    hsum(r, hrow);
-    take_slot += PF_RPITCH;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(right) : "r"(at + 16 * NW));
+    wv[0] = __byte_perm(left, 0u, plan.left_sel);
+    wv[NWORD + 1] = __byte_perm(right, 0u, plan.right_sel);
+#pragma unroll
+    for (int k = 1; k < NW; ++k) wv[1 + 4 * k] = __byte_perm(wv[1 + 4 * k], 0u, plan.unit_sel[k]);
+#pragma unroll
+    for (int j = 0; j < NWORD; ++j) {
+      uint32_t even = __dp4a(wv[j], 0x04010000u, __dp4a(wv[j + 1], 0x00010406u, 0u));
+      uint32_t odd = __dp4a(wv[j + 1], 0x04060401u, __dp4a(wv[j + 2], 0x00000001u, 0u));
+      hrow[j] = __byte_perm(even, odd, 0x5410);            // even | odd << 16 (both < 65536)
+    }
+    take_slot += RPITCH;
     if (take_slot == ring_end) take_slot = ring0;
   };
   // vertical [1 4 6 4 1] on packed u16 pairs, +128, >>8, and the four result bytes of two words in one permute
   auto emit = [&](int oy, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, const uint32_t* e) {
-    uint32_t v[4];
+    uint32_t px[NWORD / 2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (a[j] + 4u * (b[j] + d[j])) + (e[j] + 6u * c[j]) + 0x00800080u;
-    if (ox0 < xo1) {
-      uint2 px = make_uint2(__byte_perm(v[0], v[1], 0x7531), __byte_perm(v[2], v[3], 0x7531));
-      *reinterpret_cast<uint2*>(out + (int64_t)oy * dpitch + ox0) = px;      // ow % 8 == 0 on this path
+    for (int j = 0; j < NWORD; j += 2) {
+      uint32_t v0 = (a[j] + 4u * (b[j] + d[j])) + (e[j] + 6u * c[j]) + 0x00800080u;
+      uint32_t v1 = (a[j + 1] + 4u * (b[j + 1] + d[j + 1])) + (e[j + 1] + 6u * c[j + 1]) + 0x00800080u;
+      px[j / 2] = __byte_perm(v0, v1, 0x7531);
+    }
+    uint8_t* o = out + (int64_t)oy * dpitch + ox0;
+    if (NW == 2) {
+      if (ox0 + 16 <= xo1) *reinterpret_cast<uint4*>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+      else if (ox0 + 8 <= xo1) *reinterpret_cast<uint2*>(o) = make_uint2(px[0], px[1]);
+    } else {
+      if (ox0 < xo1) *reinterpret_cast<uint2*>(o) = make_uint2(px[0], px[1]);      // xo1 % 8 == 0 on this path
     }
   };
 
 #pragma unroll
   for (int k = 0; k < PF_Q + 1; ++k) request();
-  // six row registers rotate with period three output rows, so no value is ever moved between registers
-  uint32_t h0[4], h1[4], h2[4], h3[4], h4[4], h5[4];
+  uint32_t h0[NWORD], h1[NWORD], h2[NWORD], h3[NWORD], h4[NWORD], h5[NWORD];
   take(h0); request();
   take(h1); request();
   take(h2); request();
@@ -335,14 +353,22 @@ static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64
   // streaming kernel: 16 B aligned rows and w % 16 == 0 (every pyramid level of 1080p / VGA); else the tiled kernel
   const bool stream_ok = vec_ok && ((dst_pitch & 7) == 0) && (w & 15) == 0 && w >= 16 && h >= 4;
   if (stream_ok) {
-    constexpr int kQ = 8, kStrip = 32;     // measured best of {8,12,16} x {32,64} (profiles/r01_pyrdown_variants.log)
-    int col_blocks = (ow + 255) / 256, strips = (oh + kStrip - 1) / kStrip;
+    // wide levels use 16 output pixels per lane (half the per-byte instruction overhead), narrow ones 8
+    const bool wide = ow >= 320 && ((dst_pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_dst) & 15) == 0) && ((dst_stride & 15) == 0);
+    constexpr int kStrip = 32;
+    const int lane_outs = wide ? 16 : 8;
+    int col_blocks = (ow + 32 * lane_outs - 1) / (32 * lane_outs), strips = (oh + kStrip - 1) / kStrip;
     int64_t total_warps = (int64_t)batch * strips * col_blocks;
     int64_t blocks = (total_warps + PF_WARPS - 1) / PF_WARPS;
     if (blocks <= 0x7fffffffLL) {
-      pyr_down_stream_kernel<kQ, kStrip><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
-          d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
-          rect_stride, src_level, d_mask, mask_stride);
+      if (wide)
+        pyr_down_stream_kernel<6, kStrip, 2><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
+            d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
+            rect_stride, src_level, d_mask, mask_stride);
+      else
+        pyr_down_stream_kernel<8, kStrip, 1><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
+            d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
+            rect_stride, src_level, d_mask, mask_stride);
       AGT_LAUNCH_CHECK(ctx);
       return AGT_OK;
     }
