@@ -42,7 +42,8 @@ constexpr double TOL_ROT = 1e-6, TOL_TRANS = 1e-6, REJ_TOL_ROT = 5e-5, REJ_TOL_T
 struct DprShared {
   // trial pose (float32 view used by the sample loop, float64 for the projection)
   float R[9], t[3];
-  double Rd[9], td[3];
+  __align__(16) double Rd[12];   // trial rotation (row-major) followed by the translation: six 128-bit broadcast loads
+  double td_unused_[1];
   double fxs, fys, ubase, vbase;   // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l
   float fx, fy, cx, cy;
   float inv_scale;       // 2^-level
@@ -74,12 +75,10 @@ __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
   return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
 }
 
-// exact int -> float for |i| < 2^22 on the integer + FP32 add pipes (I2F runs on the quarter-rate XU pipe)
-__device__ __forceinline__ float i2f_small(int i) { return __int_as_float(i + 0x4B400000) - 12582912.f; }
-
-__device__ __forceinline__ int dp4(uint32_t px, int coef) {
+// d = acc + sum_k px.byte[k] (unsigned) * coef.byte[k] (signed)
+__device__ __forceinline__ int dp4c(uint32_t px, int coef, int acc) {
   int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(coef), "r"(0));
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(coef), "r"(acc));
   return d;
 }
 
@@ -141,10 +140,14 @@ __device__ inline void rodrigues_step(const double w[3], double R[9]) {
 }
 
 // packed signed-byte coefficient words (little endian: byte 0 multiplies the left-most pixel)
-constexpr int C_DX0 = (int)0x000100FF;   // (-1, 0, 1, 0)
-constexpr int C_DX1 = (int)0x0100FF00;   // ( 0,-1, 0, 1)
-constexpr int C_SM0 = (int)0x00030A03;   // ( 3,10, 3, 0)
-constexpr int C_SM1 = (int)0x030A0300;   // ( 0, 3,10, 3)
+constexpr int C_DX0_3 = (int)0x000300FD;    // ( -3,  0,  3,  0)   horizontal difference at x0, row weight 3
+constexpr int C_DX0_10 = (int)0x000A00F6;   // (-10,  0, 10,  0)   ... row weight 10
+constexpr int C_DX1_3 = (int)0x0300FD00;    // (  0, -3,  0,  3)   horizontal difference at x0+1
+constexpr int C_DX1_10 = (int)0x0A00F600;   // (  0,-10,  0, 10)
+constexpr int C_SM0 = (int)0x00030A03;      // (  3, 10,  3,  0)   horizontal smoothing at x0
+constexpr int C_SM1 = (int)0x030A0300;      // (  0,  3, 10,  3)   horizontal smoothing at x0+1
+constexpr int C_SM0_NEG = (int)0x00FDF6FD;  // ( -3,-10, -3,  0)
+constexpr int C_SM1_NEG = (int)0xFDF6FD00;  // (  0, -3,-10, -3)
 
 // kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
 // the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
@@ -205,7 +208,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     S.act_prefix[na] = pre;
     S.n_active = na;
     for (int i = 0; i < 9; ++i) { S.R[i] = (float)Rc[i]; S.Rd[i] = Rc[i]; }
-    for (int i = 0; i < 3; ++i) { S.t[i] = (float)tc[i]; S.td[i] = tc[i]; }
+    for (int i = 0; i < 3; ++i) { S.t[i] = (float)tc[i]; S.Rd[9 + i] = tc[i]; }
     S.fxs = cam.fx * sc; S.fys = cam.fy * sc;
     S.ubase = cam.cx * sc; S.vbase = cam.cy * sc;
     S.stop = 0;
@@ -271,14 +274,15 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       // cost and flip 20 % of those decisions, float64 leaves 0.2 % (profiles/r01_dpr_precision_sweep.log).
       const double sx = sm.x, sy = sm.y, sz = sm.z;
       // (the float64 pose is read from shared memory with broadcast loads: 24 registers less per thread)
-      const double dX = S.Rd[0] * sx + S.Rd[1] * sy + S.Rd[2] * sz + S.td[0];
-      const double dY = S.Rd[3] * sx + S.Rd[4] * sy + S.Rd[5] * sz + S.td[1];
-      const double dZ = S.Rd[6] * sx + S.Rd[7] * sy + S.Rd[8] * sz + S.td[2];
+      const double2* P = reinterpret_cast<const double2*>(S.Rd);
+      const double2 p01 = P[0], p23 = P[1], p45 = P[2], p67 = P[3], p8t = P[4], ptt = P[5];
+      const double dX = p01.x * sx + p01.y * sy + p23.x * sz + p8t.y;
+      const double dY = p23.y * sx + p45.x * sy + p45.y * sz + ptt.x;
+      const double dZ = p67.x * sx + p67.y * sy + p8t.x * sz + ptt.y;
       if (!(dZ > 1e-6)) continue;
       float iz;
       asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dZ));       // MUFU.RCP: Jacobian + Newton seed
-      double r0 = (double)iz;
-      r0 = r0 * (2.0 - dZ * r0);
+      double r0 = (double)iz;                         // 2^-23 relative; one Newton step -> 2^-46 (1e-11 px at 1080p)
       r0 = r0 * (2.0 - dZ * r0);
       const double ul = (S.fxs * dX) * r0 + S.ubase, vl = (S.fys * dY) * r0 + S.vbase;
       // valid <=> 1 <= floor(ul) <= lw-3  <=>  1 <= ul < lw-2   (NaN fails both)
@@ -306,19 +310,18 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 #pragma unroll
         for (int r = 0; r < 4; ++r) row[r] = ld4_global(g + r * lpitch);
       }
-      int dx0[4], dx1[4], s0[4], s1[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        dx0[r] = dp4(row[r], C_DX0); dx1[r] = dp4(row[r], C_DX1);
-        s0[r] = dp4(row[r], C_SM0);  s1[r] = dp4(row[r], C_SM1);
-      }
-      // Scharr at (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1)
-      const float gx00 = i2f_small(3 * (dx0[0] + dx0[2]) + 10 * dx0[1]), gx01 = i2f_small(3 * (dx1[0] + dx1[2]) + 10 * dx1[1]);
-      const float gx10 = i2f_small(3 * (dx0[1] + dx0[3]) + 10 * dx0[2]), gx11 = i2f_small(3 * (dx1[1] + dx1[3]) + 10 * dx1[2]);
-      const float gy00 = i2f_small(s0[2] - s0[0]), gy01 = i2f_small(s1[2] - s1[0]);
-      const float gy10 = i2f_small(s0[3] - s0[1]), gy11 = i2f_small(s1[3] - s1[1]);
-      const float i00 = i2f_small((row[1] >> 8) & 0xff), i01 = i2f_small((row[1] >> 16) & 0xff);
-      const float i10 = i2f_small((row[2] >> 8) & 0xff), i11 = i2f_small((row[2] >> 16) & 0xff);
+      // Scharr at (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1): the [3 10 3] row weights are folded into the byte
+      // coefficients and the three rows are chained through the dp4a accumulator - no integer combine afterwards
+      const float gx00 = (float)dp4c(row[2], C_DX0_3, dp4c(row[1], C_DX0_10, dp4c(row[0], C_DX0_3, 0)));
+      const float gx01 = (float)dp4c(row[2], C_DX1_3, dp4c(row[1], C_DX1_10, dp4c(row[0], C_DX1_3, 0)));
+      const float gx10 = (float)dp4c(row[3], C_DX0_3, dp4c(row[2], C_DX0_10, dp4c(row[1], C_DX0_3, 0)));
+      const float gx11 = (float)dp4c(row[3], C_DX1_3, dp4c(row[2], C_DX1_10, dp4c(row[1], C_DX1_3, 0)));
+      const float gy00 = (float)dp4c(row[2], C_SM0, dp4c(row[0], C_SM0_NEG, 0));
+      const float gy01 = (float)dp4c(row[2], C_SM1, dp4c(row[0], C_SM1_NEG, 0));
+      const float gy10 = (float)dp4c(row[3], C_SM0, dp4c(row[1], C_SM0_NEG, 0));
+      const float gy11 = (float)dp4c(row[3], C_SM1, dp4c(row[1], C_SM1_NEG, 0));
+      const float i00 = (float)((row[1] >> 8) & 0xffu), i01 = (float)((row[1] >> 16) & 0xffu);
+      const float i10 = (float)((row[2] >> 8) & 0xffu), i11 = (float)((row[2] >> 16) & 0xffu);
       const float w11 = a * b, w01 = a - w11, w10 = b - w11, w00 = 1.f - a - b + w11;
       const float I = w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11;
       const float Gx = (w00 * gx00 + w01 * gx01 + w10 * gx10 + w11 * gx11) * gsc;
@@ -423,7 +426,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
             for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
           for (int p = 0; p < 3; ++p) tt[p] = tc[p] + d[3 + p];
           for (int p = 0; p < 9; ++p) { S.R[p] = (float)Rt[p]; S.Rd[p] = Rt[p]; }
-          for (int p = 0; p < 3; ++p) { S.t[p] = (float)tt[p]; S.td[p] = tt[p]; }
+          for (int p = 0; p < 3; ++p) { S.t[p] = (float)tt[p]; S.Rd[9 + p] = tt[p]; }
           break;
         }
         lam *= 10.0;
@@ -438,7 +441,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       if (crank != 0) {
         const DprShared* S0 = cluster.map_shared_rank(&S, 0);
         if (tid < 9) { S.R[tid] = S0->R[tid]; S.Rd[tid] = S0->Rd[tid]; }
-        if (tid < 3) { S.t[tid] = S0->t[tid]; S.td[tid] = S0->td[tid]; }
+        if (tid < 3) { S.t[tid] = S0->t[tid]; S.Rd[9 + tid] = S0->Rd[9 + tid]; }
         if (tid == 0) S.stop = S0->stop;
       }
     }
