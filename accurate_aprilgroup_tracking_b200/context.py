@@ -140,6 +140,15 @@ class AgtContext:
         src = frames if isinstance(frames, t.Tensor) else t.from_numpy(np.ascontiguousarray(frames))
         pyr.frames.copy_(src.to(self.tdev, non_blocking=True))
 
+    def ingest_bgr(self, pyr: Pyramid, bgr) -> None:
+        """bgr [B,H,W,3] uint8 (device tensor or numpy) -> level 0 of ``pyr`` as cv.cvtColor(BGR2GRAY) would give it."""
+        t = self.torch
+        src = self._dev(bgr, t.uint8)
+        b, h, w = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+        self._use_current_stream()
+        self._check(self.lib.agt_bgr_to_gray(self.h, self._p(src), w, h, 3 * w, 3 * w * h, self._p(pyr.levels[0]),
+                                             pyr.desc.pitch[0], pyr.desc.frame_stride[0], b))
+
     def build_pyramid(self, pyr: Pyramid, batch: Optional[int] = None) -> None:
         self._use_current_stream()
         self._check(self.lib.agt_build_pyramid(self.h, C.byref(pyr.desc), int(pyr.batch if batch is None else batch)))

@@ -339,7 +339,62 @@ __global__ void scharr_kernel(const uint8_t* __restrict__ src, int w, int h, int
   *reinterpret_cast<short2*>(o) = make_short2((short)dx, (short)dy);
 }
 
+// Frame ingest: cv::cvtColor(BGR2GRAY) for 8-bit images in OpenCV's fixed-point form,
+// gray = (B*3735 + G*19235 + R*9798 + 16384) >> 15, written straight into level 0 of a pyramid.
+// 16 pixels per thread: three 128-bit loads of interleaved BGR, one 128-bit store.
+__global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, int w, int h, int64_t spitch, int64_t sstride,
+                                   uint8_t* __restrict__ gray, int64_t dpitch, int64_t dstride, int vec_ok) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int y = blockIdx.y;
+  if (x0 >= w) return;
+  const uint8_t* src = bgr + (int64_t)blockIdx.z * sstride + (int64_t)y * spitch + 3 * x0;
+  uint8_t* dst = gray + (int64_t)blockIdx.z * dstride + (int64_t)y * dpitch + x0;
+  if (vec_ok && x0 + 16 <= w) {
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+    uint4 q[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+    const uint32_t* wds = reinterpret_cast<const uint32_t*>(q);
+    uint32_t o[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {            // 4 pixels = 12 bytes = words 3g .. 3g+2
+      const uint32_t a = wds[3 * g], b = wds[3 * g + 1], c = wds[3 * g + 2];
+      // pixel 0: a.b0 a.b1 a.b2 | pixel 1: a.b3 b.b0 b.b1 | pixel 2: b.b2 b.b3 c.b0 | pixel 3: c.b1 c.b2 c.b3
+      const uint32_t px[4] = {a & 0xffffffu, (a >> 24) | ((b & 0xffffu) << 8), (b >> 16) | ((c & 0xffu) << 16), c >> 8};
+      uint32_t out = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t B = px[k] & 0xffu, G = (px[k] >> 8) & 0xffu, R = (px[k] >> 16) & 0xffu;
+        out |= ((B * 3735u + G * 19235u + R * 9798u + 16384u) >> 15) << (8 * k);
+      }
+      o[g] = out;
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+  } else {
+    for (int k = 0; k < 16 && x0 + k < w; ++k) {
+      const uint32_t B = src[3 * k], G = src[3 * k + 1], R = src[3 * k + 2];
+      dst[k] = (uint8_t)((B * 3735u + G * 19235u + R * 9798u + 16384u) >> 15);
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int agt_bgr_to_gray(agt_ctx* ctx, const uint8_t* d_bgr, int w, int h, int64_t src_pitch, int64_t src_stride,
+                               uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!d_bgr || !d_gray || w < 1 || h < 1 || batch < 0 || src_pitch < 3 * (int64_t)w || dst_pitch < w)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_bgr_to_gray: bad arguments");
+  if (batch == 0) return AGT_OK;
+  int vec_ok = ((reinterpret_cast<uintptr_t>(d_bgr) & 15) == 0) && ((src_pitch & 15) == 0) && ((src_stride & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(d_gray) & 15) == 0) && ((dst_pitch & 15) == 0) && ((dst_stride & 15) == 0);
+  for (int b0 = 0; b0 < batch; b0 += 65535) {
+    int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    dim3 grid(((w + 15) / 16 + 127) / 128, h, nb);
+    bgr_to_gray_kernel<<<grid, 128, 0, ctx->stream>>>(d_bgr + (int64_t)b0 * src_stride, w, h, src_pitch, src_stride,
+                                                      d_gray + (int64_t)b0 * dst_stride, dst_pitch, dst_stride, vec_ok);
+    AGT_LAUNCH_CHECK(ctx);
+  }
+  return AGT_OK;
+}
 
 static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
                          uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch, const int32_t* d_rects,

@@ -85,6 +85,11 @@ int agt_set_camera(agt_ctx* ctx, const double k[9], const double* dist, int ndis
 int agt_set_model(agt_ctx* ctx, const float* h_samples, const uint8_t* h_sample_tag, int n_samples,
                   const float* h_tag_normals, const float* h_tag_centres, int n_tags, double pitch);
 
+/* ---- frame ingest: cv::cvtColor(frame, COLOR_BGR2GRAY) (detect_pose.py:602), bit-exact for 8-bit images ---- */
+/* d_bgr[batch][h][src_pitch] interleaved B,G,R -> d_gray[batch][h][dst_pitch] (e.g. level 0 of a pyramid). */
+int agt_bgr_to_gray(agt_ctx* ctx, const uint8_t* d_bgr, int w, int h, int64_t src_pitch, int64_t src_stride,
+                    uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch);
+
 /* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
 /* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
 int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,

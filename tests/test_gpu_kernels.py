@@ -402,3 +402,15 @@ def test_roi_pyramid_and_refinement_are_exact(ctx1080):
             assert np.array_equal(roi.level(l)[b].cpu().numpy()[sl], ref[sl]), (b, l)
     # the ROI path touched only a small part of the levels
     assert float((roi.level(1)[5] == 255).float().mean()) > 0.5
+
+
+def test_bgr_to_gray_bit_exact(ctxvga):
+    import cv2
+    rng = np.random.default_rng(3)
+    for (w, h) in [(640, 480), (1920, 1080), (333, 77)]:
+        bgr = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        pyr = ctxvga.alloc_pyramid(2, w, h, 1)
+        ctxvga.ingest_bgr(pyr, bgr)
+        got = pyr.frames.cpu().numpy()
+        for b in range(2):
+            assert np.array_equal(got[b], cv2.cvtColor(bgr[b], cv2.COLOR_BGR2GRAY)), (w, h, b)
