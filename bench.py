@@ -570,6 +570,22 @@ def run_streams(args):
             "final_frame_median_trans_err_m": float(np.median(dt)), "accepted_frac_last": float(out["accepted"].float().mean())}), flush=True)
 
 
+def ensure_library():
+    """libagt.so normally travels with the tree; if it is absent build it once (local rank 0) and let the others wait."""
+    from accurate_aprilgroup_tracking_b200 import _build, _lib
+    if _lib.LIB_PATH.exists():
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build()
+        return
+    for _ in range(600):
+        if _lib.LIB_PATH.exists():
+            time.sleep(1.0)
+            return
+        time.sleep(0.5)
+    raise RuntimeError("libagt.so was not built")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -584,6 +600,7 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     args = ap.parse_args()
+    ensure_library()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "lk":

@@ -182,3 +182,34 @@ def test_dpr_multi_hypothesis_tie_breaks_to_lowest_index():
     score = [2 * r["cost"] / r["n_valid"] for r in runs]
     assert best == int(np.argmin(score))
     assert score[0] == score[1] and (best != 1)
+
+
+# ---------------------------------------------------------------------------- whole path (BASELINE config 1 shape)
+def test_pipeline_oracle_reduces_to_ape_and_tracks_through_dropout():
+    from oracle import pipeline_oracle
+    g = np.load(GOLDEN / "ape_sequence.npz")
+    group = ape_oracle.group_from_json(synth.april_group_dict())
+    # with both extra stages off the composition is exactly the reference's APE state machine
+    po = pipeline_oracle.PipelineOracle(group, g["mtx"], util.dpr_model(), use_lk=False, use_dense_refine=False)
+    for f in range(40):
+        po.frame(np.zeros((8, 8), np.uint8), make_golden.unpack_detections(g["ids"], g["corners"], f))
+        snap = po.snapshot()
+        want = g["prev"][f]
+        assert (snap["prev"] is None) == bool(np.isnan(want[0]))
+        if snap["prev"] is not None:
+            assert np.array_equal(np.concatenate(snap["prev"]), want)
+    # full path on a short rendered VGA sequence with a detector dropout: LK carries the tags, refinement runs
+    cam = synth.CAMERA_VGA
+    po = pipeline_oracle.PipelineOracle(group, cam.mtx, util.dpr_model())
+    traj = synth.trajectory(777, 6)
+    rng = np.random.default_rng(777)
+    for f in range(6):
+        dets = synth.detections(traj[f], cam, rng)
+        if f == 4:
+            dets = dets[:1]
+        po.frame(synth.render(traj[f], cam, seed=f), dets)
+        assert po.last_accepted, f
+        dr, dt = util.pose_diff(np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)]), traj[f])
+        assert dr < 0.02 and dt < 2e-3, (f, dr, dt)
+        if f == 4:
+            assert po.tracked >= 1

@@ -221,3 +221,42 @@ def test_pose_detector_full_pipeline_with_lk_and_dense_refinement(detector_facto
     finally:
         sys.path.remove(stub_dir)
         sys.modules.pop("apriltag", None)
+
+
+def test_full_pipeline_matches_pipeline_oracle_config1(detector_factory, ctxvga):
+    """BASELINE config 1 shape (640x480 synthetic sequence, APE + LK + dense refinement): the drop-in detector
+    against the CPU composition of the three stage oracles, frame by frame, including detector dropouts."""
+    from oracle import ape_oracle, pipeline_oracle
+    cam = synth.CAMERA_VGA
+    n = 40
+    traj = synth.trajectory(1000, n)
+    rng = np.random.default_rng(1000)
+    pyr = ctxvga.alloc_pyramid(n, cam.width, cam.height, 1)
+    ctxvga.render(pyr, traj, np.arange(n) + 1000)
+    frames = pyr.frames.cpu().numpy()
+    det = detector_factory(cam.mtx, use_lk=True, use_dense_refine=True)
+    po = pipeline_oracle.PipelineOracle(ape_oracle.group_from_json(synth.april_group_dict()), cam.mtx, util.dpr_model())
+    tracked = 0
+    for f in range(n):
+        dets = synth.detections(traj[f], cam, rng)
+        if f in (12, 13, 27):
+            dets = dets[:1]
+        if f == 20:
+            dets = []
+        po.frame(frames[f], dets)
+        det.img = None
+        det._prev_gray, det._gray = det._gray, frames[f]
+        lists = det._lists_from_detections([_Det(t, c) for t, c in dets])
+        before = len(lists[0])
+        if len(lists[0]) < 2:
+            lists = det._track_lost_tags(*lists)
+        assert len(lists[0]) - before == po.tracked, f          # LK inlier set (all-four-corners rule) identical
+        tracked += po.tracked
+        det._estimate_pose(lists[0], lists[1])
+        assert bool(det._prev_corners) == po.last_accepted, f
+        assert (det.extrinsic_guess[0] is None) == (po.guess[0] is None), f
+        if po.prev[0] is not None:
+            got = np.concatenate([det.prev_transform[0].ravel(), det.prev_transform[1].ravel().astype(np.float64)])
+            want = np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
+            util.assert_pose_close(got, want, f"frame {f}")
+    assert tracked >= 3
