@@ -142,6 +142,7 @@ __global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __r
 extern "C" int agt_ape_prepare(agt_ctx* ctx, const double* d_state, double* d_guess, uint8_t* d_use_guess, int batch,
                                int enhance_ape) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_state || !d_guess || !d_use_guess || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_ape_prepare: bad arguments");
   if (batch == 0) return AGT_OK;
   ape_prepare_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d_state, d_guess, d_use_guess, batch, enhance_ape);
@@ -153,6 +154,7 @@ extern "C" int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_
                               const uint8_t* d_ok, const float* d_err, uint8_t* d_accepted, uint8_t* d_error_flag,
                               int batch, int enhance_ape) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_state || !d_n_tags || !d_pose || !d_ok || !d_err || batch < 0)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_ape_update: bad arguments");
   if (batch == 0) return AGT_OK;

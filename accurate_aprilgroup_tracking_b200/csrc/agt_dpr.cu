@@ -517,6 +517,7 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
                           double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
                           uint8_t* d_left_roi, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine: camera and surface model must be set");
   if (!pyr || !d_init || !d_pose || n_hyp < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad arguments");
   if (pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: bad pyramid descriptor");
@@ -569,6 +570,7 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
 extern "C" int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,
                                int n_hyp, int32_t* d_best, double* d_best_pose, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_pose || !d_cost || !d_n_valid || !d_best || n_hyp < 1 || batch < 0)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_select_best: bad arguments");
   if (batch == 0) return AGT_OK;
@@ -581,6 +583,7 @@ extern "C" int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* 
 
 extern "C" int agt_dpr_rects(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, int32_t* d_rects, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_dpr_rects: camera and surface model must be set");
   if (!pyr || !d_init || !d_rects || n_hyp < 1 || batch < 0 || (reinterpret_cast<uintptr_t>(d_rects) & 15))
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_dpr_rects: bad arguments (d_rects must be 16-byte aligned)");
@@ -593,6 +596,7 @@ extern "C" int agt_dpr_rects(agt_ctx* ctx, const agt_pyramid* pyr, const double*
 
 extern "C" int agt_any_flag(agt_ctx* ctx, const uint8_t* d_flags, int stride, uint8_t* d_out, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_flags || !d_out || stride < 1 || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_any_flag: bad arguments");
   if (batch == 0) return AGT_OK;
   any_flag_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d_flags, stride, d_out, batch);

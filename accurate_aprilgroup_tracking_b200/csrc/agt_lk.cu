@@ -273,6 +273,7 @@ __global__ void lk_merge_kernel(const float* __restrict__ tracked, const uint8_t
 extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
                             float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int batch, int n_pts) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_tracked_pts || !d_status || !d_prev_valid || !d_img_pts || !d_valid || !d_n_tags || batch < 0 || n_pts < 4 ||
       (n_pts & 3) || n_pts > AGT_MAX_POINTS)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_merge: bad arguments");

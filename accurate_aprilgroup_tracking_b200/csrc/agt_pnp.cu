@@ -430,6 +430,7 @@ extern "C" int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_
                        const double* d_guess, const uint8_t* d_use_guess, double* d_pose, uint8_t* d_ok,
                        float* d_reproj_err, int32_t* d_iters, int batch, int n_pts) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_pnp: call agt_set_camera first");
   if (!d_obj_pts || !d_img_pts || !d_pose || !d_ok || !d_reproj_err || batch < 0)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pnp: null argument or negative batch");
@@ -444,6 +445,7 @@ extern "C" int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_
 
 extern "C" int agt_project(agt_ctx* ctx, const float* d_obj_pts, const double* d_pose, double* d_out, int batch, int n_pts) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_project: call agt_set_camera first");
   if (!d_obj_pts || !d_pose || !d_out || batch < 0 || n_pts < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_project: bad arguments");
   int64_t total = (int64_t)batch * n_pts;

@@ -381,6 +381,7 @@ __global__ void bgr_to_gray_kernel(const uint8_t* __restrict__ bgr, int w, int h
 extern "C" int agt_bgr_to_gray(agt_ctx* ctx, const uint8_t* d_bgr, int w, int h, int64_t src_pitch, int64_t src_stride,
                                uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_bgr || !d_gray || w < 1 || h < 1 || batch < 0 || src_pitch < 3 * (int64_t)w || dst_pitch < w)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_bgr_to_gray: bad arguments");
   if (batch == 0) return AGT_OK;
@@ -399,6 +400,7 @@ extern "C" int agt_bgr_to_gray(agt_ctx* ctx, const uint8_t* d_bgr, int w, int h,
 static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
                          uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch, const int32_t* d_rects,
                          int rect_stride, int src_level, const uint8_t* d_mask, int mask_stride) {
+  if (batch == 0) return AGT_OK;
   if (!d_src || !d_dst || w < 1 || h < 1 || batch < 0 || src_pitch < w || dst_pitch < (w + 1) / 2)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pyr_down: bad arguments (w=%d h=%d batch=%d)", w, h, batch);
   if (batch == 0) return AGT_OK;
@@ -482,6 +484,7 @@ extern "C" int agt_build_pyramid_masked(agt_ctx* ctx, const agt_pyramid* pyr, co
 extern "C" int agt_scharr(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,
                           int16_t* d_dst, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_src || !d_dst || w < 1 || h < 1 || batch < 0 || src_pitch < w)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_scharr: bad arguments");
   if (batch == 0) return AGT_OK;

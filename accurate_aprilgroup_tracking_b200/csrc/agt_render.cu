@@ -110,6 +110,7 @@ extern "C" int agt_render(agt_ctx* ctx, const double* d_pose, const uint32_t* d_
                           int64_t pitch, int64_t stride, const double* d_tag_rt, const uint8_t* d_cells, int n_tags,
                           double inradius, double cell, int noise, int batch) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_render: call agt_set_camera first");
   if (!d_pose || !d_seed || !d_frames || !d_tag_rt || !d_cells || n_tags < 1 || n_tags > AGT_MAX_TAGS || batch < 0 || w < 1 || h < 1)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_render: bad arguments");
