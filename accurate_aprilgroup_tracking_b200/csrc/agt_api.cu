@@ -399,9 +399,9 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
         hr[i] = r;
       }
       AGT_CUDA(ctx, cudaMemcpyAsync(drc, hr, sizeof(agt_roi_rect) * nb, cudaMemcpyHostToDevice, cp));
-      int gctas = 64;
-      if (const char* e = getenv("AGT_GATHER_CTAS")) { int v = atoi(e); if (v > 0) gctas = v; }
-      roi_gather_kernel<<<nb < gctas ? nb : gctas, 256, 0, cp>>>(ctx->host_frames_dev, w, h, drc, p.data[0], p.pitch[0], p.frame_stride[0], nb);
+      // 64 CTAs: enough 16-byte reads in flight to fill PCIe, few enough to leave the SMs to the compute stream
+      // (measured 32 / 64 / 128 / 256 CTAs x chunk 128..1024 frames: profiles/r01_e2e_sweep.log)
+      roi_gather_kernel<<<nb < 64 ? nb : 64, 256, 0, cp>>>(ctx->host_frames_dev, w, h, drc, p.data[0], p.pitch[0], p.frame_stride[0], nb);
       AGT_LAUNCH_CHECK(ctx);
       gathered = true;
     } else if (!roi && contiguous_ids && tight) {
@@ -448,7 +448,7 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
   ctx->last_h2d_bytes = 0;
   if (batch == 0) return AGT_OK;
   AGT_CUDA(ctx, cudaSetDevice(ctx->device));
-  const bool trace = getenv("AGT_TRACE") != nullptr;
+  const bool trace = getenv("AGT_TRACE") != nullptr;      // debug aid: phase timestamps on stderr
   auto t_start = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   // chunked, double-buffered: H2D of chunk i+1 on the copy stream overlaps pyramid + refinement of chunk i
@@ -457,7 +457,6 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
   // chunks of up to 1024 frames (<= 3 GiB per buffer): large enough that one refinement launch fills the GPU
   int chunk = (int)((3LL << 30) / per_frame);
   if (chunk > 1024) chunk = 1024;
-  if (const char* e = getenv("AGT_E2E_CHUNK")) { int v = atoi(e); if (v > 0 && v < chunk) chunk = v; }
   if (chunk < 1) chunk = 1;
   if (chunk > batch) chunk = batch;
   int64_t chunk_bytes = layout_pyramid(&one, nullptr, w, h, levels, chunk);
