@@ -40,10 +40,9 @@ constexpr int MAX_EVALS = 50;
 constexpr double TOL_ROT = 1e-6, TOL_TRANS = 1e-6, REJ_TOL_ROT = 5e-5, REJ_TOL_TRANS = 5e-6;
 
 struct DprShared {
-  // trial pose (float32 view used by the sample loop, float64 for the projection)
-  float R[9], t[3];
+  // trial pose: float64 for the projection, float32 for the Jacobian
   __align__(16) double Rd[12];   // trial rotation (row-major) followed by the translation: six 128-bit broadcast loads
-  double td_unused_[1];
+  __align__(16) float Rf[12];    // (R0,R3) (R1,R4) (R2,R5) (t0,t1) as pairs for the packed float32 ops, then R6 R7 R8 t2
   double fxs, fys, ubase, vbase;   // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l
   float fx, fy, cx, cy;
   float inv_scale;       // 2^-level
@@ -52,6 +51,8 @@ struct DprShared {
   int64_t lpitch;
   const uint8_t* limg;   // level image of this frame
   int tx0, ty0, tw, th;  // staged tile: origin (level px), size
+  int xbias, ybias;      // high word of (1.5 * 2^20 + tile origin + 1): see the sample loop
+  uint32_t tw_m3, th_m3; // tile size - 3 (0 for a tile smaller than one footprint)
   int rx0, ry0, rx1, ry1;   // predicted ROI (see agt_dpr_plan)
   int left_roi;          // a sample footprint left the predicted ROI at some evaluation
   int n_active;
@@ -59,10 +60,11 @@ struct DprShared {
   int act_prefix[AGT_MAX_TAGS + 1];
   int stop;
   double wsum[DPR_WARPS][NSUM + 2];
-  double tot[NSUM + 2];
-  // LM state, touched by thread 0 only (kept out of registers)
-  double Rc[9], tc[3], Hc[21], bc[6], cc, lam;
-  double Rt[9], tt[3], dstep[6];
+  double tot[NSUM + 2];  // cluster exchange only
+  // LM state, touched by warp 0 only (kept out of registers)
+  double Pc[12];         // accepted pose: rotation (row-major) + translation
+  double Hb[27];         // normal equations at the accepted pose: H (21, packed upper triangle by rows) + b (6)
+  double dstep[6], cc, lam;
   int nc, evals, status;
 };
 
@@ -75,6 +77,21 @@ __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
   return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
 }
 
+// ---- packed float32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per issue slot) --------------------------
+// The sample loop is bound by instruction issue, not by any one pipe, so everything that comes in (x, y)
+// pairs - the rotated lever arm, the (gx, gy) gradient taps, the normal-equation products - runs packed.
+// ptxas folds scalar broadcasts and lane swaps into the operand modifiers (R.F32, R.F32x2.LO_HI).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk2(int lo, int hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ f32x2 swap2(f32x2 v) { return pk2(hi2(v), lo2(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // d = acc + sum_k px.byte[k] (unsigned) * coef.byte[k] (signed)
 __device__ __forceinline__ int dp4c(uint32_t px, int coef, int acc) {
   int d;
@@ -83,60 +100,83 @@ __device__ __forceinline__ int dp4c(uint32_t px, int coef, int acc) {
 }
 
 // ---- serial LM phase helpers (one thread per CTA runs them while 255 wait: keep the dependency chains short) ----
-// 1/sqrt(d) in float64 from the MUFU.RSQ seed + two Newton steps (a sqrt + a division cost ~70 dependent instructions)
-__device__ __forceinline__ double rsqrt_f64(double d) {
-  double y = (double)rsqrtf((float)d);
-  y = y * (1.5 - 0.5 * d * y * y);
-  y = y * (1.5 - 0.5 * d * y * y);
+// 1/sqrt(d) in float64: MUFU.RSQ64H seed (2^-22) + two Newton steps, each three dependent operations deep
+__device__ __forceinline__ double rsqrt_newton(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
   return y;
 }
 
-// Cholesky solve of the SPD 6x6 system A x = b (A full, row-major), multiplications by 1/L_jj instead of divisions.
-__device__ inline bool chol6_solve_fast(double A[36], double b[6]) {
+// index of H(p, q), p <= q, in the packed upper triangle stored by rows
+__host__ __device__ constexpr int hk(int p, int q) { return p * 6 - p * (p - 1) / 2 + (q - p); }
+
+// Cholesky solve of the SPD system A x = b, A packed as above, everything in registers (all indices are compile-time
+// constants).  Right-looking: after the column scale the trailing updates are independent, so the critical path per
+// column is one reciprocal square root, one multiplication and one FMA.  L(i, j) overwrites A(j, i).
+__device__ __forceinline__ bool chol6_packed(double (&A)[21], double (&b)[6]) {
   double inv[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double d = A[j * 6 + j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
-    if (!(d > 1e-30 && d < 1e30)) return agt_chol6_solve(A, b) && false;   // out of the float seed's range: not PD for our purposes
-    const double y = rsqrt_f64(d);
+    const double d = A[hk(j, j)];
+    if (!(d > 1e-30 && d < 1e30)) return false;          // not positive definite for our purposes
+    const double y = rsqrt_newton(d);
     inv[j] = y;
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double v = A[i * 6 + j];
+    for (int i = j + 1; i < 6; ++i) A[hk(j, i)] *= y;
 #pragma unroll
-      for (int k = 0; k < j; ++k) v -= A[i * 6 + k] * A[j * 6 + k];
-      A[i * 6 + j] = v * y;
-    }
+    for (int k = j + 1; k < 6; ++k)
+#pragma unroll
+      for (int i = k; i < 6; ++i) A[hk(k, i)] = fma(-A[hk(j, i)], A[hk(j, k)], A[hk(k, i)]);
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     double v = b[i];
 #pragma unroll
-    for (int k = 0; k < i; ++k) v -= A[i * 6 + k] * b[k];
+    for (int k = 0; k < i; ++k) v = fma(-A[hk(k, i)], b[k], v);
     b[i] = v * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     double v = b[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; ++k) v -= A[k * 6 + i] * b[k];
+    for (int k = i + 1; k < 6; ++k) v = fma(-A[hk(i, k)], b[k], v);
     b[i] = v * inv[i];
   }
   return true;
 }
 
-// exp([w]x) for an LM step: series for |w| < 0.5 (truncation < 1e-16), libm sincos otherwise
-__device__ inline void rodrigues_step(const double w[3], double R[9]) {
+// exp([w]x) for an LM step: Taylor series of sin(t)/t and (1-cos t)/t^2 in t^2 for |w| < 0.5 (truncation < 1e-16),
+// libm sincos otherwise
+__device__ __forceinline__ void rodrigues_step(const double w[3], double R[9]) {
   const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   if (t2 >= 0.25) { agt_rodrigues(w, R); return; }
-  const double a = 1.0 - t2 / 6.0 * (1.0 - t2 / 20.0 * (1.0 - t2 / 42.0 * (1.0 - t2 / 72.0 * (1.0 - t2 / 110.0 * (1.0 - t2 / 156.0)))));
-  const double b = 0.5 * (1.0 - t2 / 12.0 * (1.0 - t2 / 30.0 * (1.0 - t2 / 56.0 * (1.0 - t2 / 90.0 * (1.0 - t2 / 132.0 * (1.0 - t2 / 182.0))))));
+  double a = 1.0 / 6227020800.0, b = 1.0 / 87178291200.0;
+  a = fma(a, t2, -1.0 / 39916800.0); b = fma(b, t2, -1.0 / 479001600.0);
+  a = fma(a, t2, 1.0 / 362880.0);    b = fma(b, t2, 1.0 / 3628800.0);
+  a = fma(a, t2, -1.0 / 5040.0);     b = fma(b, t2, -1.0 / 40320.0);
+  a = fma(a, t2, 1.0 / 120.0);       b = fma(b, t2, 1.0 / 720.0);
+  a = fma(a, t2, -1.0 / 6.0);        b = fma(b, t2, -1.0 / 24.0);
+  a = fma(a, t2, 1.0);               b = fma(b, t2, 0.5);
   const double c = 1.0 - b * t2;
   R[0] = c + b * w[0] * w[0];        R[1] = b * w[0] * w[1] - a * w[2]; R[2] = b * w[0] * w[2] + a * w[1];
   R[3] = b * w[1] * w[0] + a * w[2]; R[4] = c + b * w[1] * w[1];        R[5] = b * w[1] * w[2] - a * w[0];
   R[6] = b * w[2] * w[0] - a * w[1]; R[7] = b * w[2] * w[1] + a * w[0]; R[8] = c + b * w[2] * w[2];
+}
+
+// thread 0 publishes a trial pose to the sample loop
+__device__ __forceinline__ void publish_pose(DprShared& S, const double* R, const double* t) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) S.Rd[i] = R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.Rd[9 + i] = t[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { S.Rf[2 * c] = (float)R[c]; S.Rf[2 * c + 1] = (float)R[3 + c]; S.Rf[8 + c] = (float)R[6 + c]; }
+  S.Rf[6] = (float)t[0]; S.Rf[7] = (float)t[1]; S.Rf[11] = (float)t[2];
 }
 
 // packed signed-byte coefficient words (little endian: byte 0 multiplies the left-most pixel)
@@ -167,8 +207,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int64_t frame = job / n_hyp;
   if (mask != nullptr && mask[frame] == 0) return;     // skipped frame: none of its outputs is written (whole cluster)
 
-  double* const Rc = S.Rc; double* const tc = S.tc; double* const Hc = S.Hc; double* const bc = S.bc;
-  double* const Rt = S.Rt; double* const tt = S.tt; double* const dstep = S.dstep;
+  double* const Rc = S.Pc; double* const tc = S.Pc + 9;
 
   if (tid == 0) {
     S.cc = 0.0; S.lam = LAMBDA0; S.nc = 0; S.evals = 0; S.status = AGT_DPR_MAX_EVALS;
@@ -207,8 +246,9 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     }
     S.act_prefix[na] = pre;
     S.n_active = na;
-    for (int i = 0; i < 9; ++i) { S.R[i] = (float)Rc[i]; S.Rd[i] = Rc[i]; }
-    for (int i = 0; i < 3; ++i) { S.t[i] = (float)tc[i]; S.Rd[9 + i] = tc[i]; }
+    publish_pose(S, Rc, tc);
+    S.xbias = 0x41380000 + plan.tx0 + 1; S.ybias = 0x41380000 + plan.ty0 + 1;
+    S.tw_m3 = plan.tw >= 4 ? (uint32_t)(plan.tw - 3) : 0u; S.th_m3 = plan.th >= 4 ? (uint32_t)(plan.th - 3) : 0u;
     S.fxs = cam.fx * sc; S.fys = cam.fy * sc;
     S.ubase = cam.cx * sc; S.vbase = cam.cy * sc;
     S.stop = 0;
@@ -239,36 +279,55 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   __syncthreads();
 
   const int n_act_samples = S.act_prefix[S.n_active];
-  const float fx = S.fx, fy = S.fy, cx = S.cx, cy = S.cy, isc = S.inv_scale, gsc = S.gscale;
+  const float fx = S.fx, fy = S.fy, gsc = S.gscale;
   const int lw = S.lw, lh = S.lh, tx0 = S.tx0, ty0 = S.ty0, tw = S.tw, th = S.th;
   const int64_t lpitch = S.lpitch;
   const uint8_t* limg = S.limg;
+  // footprint origin relative to the tile straight from the high word of ul + 1.5 * 2^20 (see the sample loop)
+  const int xbias = S.xbias, ybias = S.ybias;
+  const uint32_t tw_m3 = S.tw_m3, th_m3 = S.th_m3;
+  const f32x2 fg = pk2(fx * gsc, fy * gsc);
 
   while (true) {
     // ================= evaluate cost + normal equations at the trial pose =================
-    float acc[27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
-    double cost = 0.0;
+    // Internal order of the six Jacobian columns: q = (J0, -J1, J3, J4, J2, J5) in three pairs QA QB QC, chosen so that
+    // every pair is produced as a pair (no register moves); signs and order are undone when the sums are unpacked.
+    f32x2 p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, p8 = 0, p9 = 0, p10 = 0, p11 = 0;
+    float s11 = 0.f, s44 = 0.f, s55 = 0.f, scost = 0.f;
     int cnt = 0;
-    // rotation / translation of the trial pose: float64 copies for the projection, float32 for the Jacobian
-    const float R0 = S.R[0], R1 = S.R[1], R2 = S.R[2], R3 = S.R[3], R4 = S.R[4], R5 = S.R[5], R6 = S.R[6], R7 = S.R[7],
-                R8 = S.R[8], t0 = S.t[0], t1 = S.t[1];
-    int seg = 0;
+    // rotation / translation of the trial pose: float64 copy (shared memory) for the projection, float32 for the Jacobian
+    const f32x2* Rp = reinterpret_cast<const f32x2*>(S.Rf);
+    const f32x2 R03 = Rp[0], R14 = Rp[1], R25 = Rp[2], t01 = Rp[3];
+    const float R6 = S.Rf[8], R7 = S.Rf[9], R8 = S.Rf[10], t2 = S.Rf[11];
     // software pipeline: the model record of the next sample is requested before this one is consumed
     float4 sm_next = make_float4(0.f, 0.f, 0.f, 0.f);
     const int j0 = crank * DPR_THREADS + tid;
+    int seg = 0, sidx = 0, seg_end = 0;
     if (j0 < n_act_samples) {
       while (j0 >= S.act_prefix[seg + 1]) ++seg;
-      sm_next = __ldg(&samples[S.act_begin[seg] + (j0 - S.act_prefix[seg])]);
+      sidx = S.act_begin[seg] + (j0 - S.act_prefix[seg]);
+      seg_end = S.act_prefix[seg + 1];
+      sm_next = __ldg(&samples[sidx]);
     }
+#pragma unroll 1
     for (int j = j0; j < n_act_samples; j += kCluster * DPR_THREADS) {
       const float4 sm = sm_next;
       const int jn = j + kCluster * DPR_THREADS;
       if (jn < n_act_samples) {
-        while (jn >= S.act_prefix[seg + 1]) ++seg;
-        sm_next = __ldg(&samples[S.act_begin[seg] + (jn - S.act_prefix[seg])]);
+        sidx += kCluster * DPR_THREADS;
+        if (jn >= seg_end) {                       // crossed into the next active tag (rare)
+          do { ++seg; } while (jn >= S.act_prefix[seg + 1]);
+          sidx = S.act_begin[seg] + (jn - S.act_prefix[seg]);
+          seg_end = S.act_prefix[seg + 1];
+        }
       }
+      sm_next = __ldg(&samples[sidx]);             // (the last iteration re-reads its own record)
+      // float32 lever arm Y = R x for the Jacobian and the reciprocal-depth seed (rounding of these only perturbs
+      // the LM step, not the cost)
+      const f32x2 Yxy = fma2(R25, bc2(sm.z), fma2(R14, bc2(sm.y), mul2(R03, bc2(sm.x))));
+      const float Yz = fmaf(R8, sm.z, fmaf(R7, sm.y, R6 * sm.x));
+      float iz;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(Yz + t2));         // MUFU.RCP: Jacobian + Newton seed
       // Projection in float64: the accept/reject decisions of the LM loop compare costs that differ by ~1e-6
       // relative near convergence; float32 pixel coordinates (ulp 6e-5 px at 1080p) add ~1e-6 of noise to the
       // cost and flip 20 % of those decisions, float64 leaves 0.2 % (profiles/r01_dpr_precision_sweep.log).
@@ -279,169 +338,186 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       const double dX = p01.x * sx + p01.y * sy + p23.x * sz + p8t.y;
       const double dY = p23.y * sx + p45.x * sy + p45.y * sz + ptt.x;
       const double dZ = p67.x * sx + p67.y * sy + p8t.x * sz + ptt.y;
-      if (!(dZ > 1e-6)) continue;
-      float iz;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"((float)dZ));       // MUFU.RCP: Jacobian + Newton seed
-      double r0 = (double)iz;                         // 2^-23 relative; one Newton step -> 2^-46 (1e-11 px at 1080p)
+      double r0 = (double)iz;                         // 2^-22 relative; one Newton step -> 2^-44 (4e-11 px at 1080p)
       r0 = r0 * (2.0 - dZ * r0);
       const double ul = (S.fxs * dX) * r0 + S.ubase, vl = (S.fys * dY) * r0 + S.vbase;
-      // valid <=> 1 <= floor(ul) <= lw-3  <=>  1 <= ul < lw-2   (NaN fails both)
-      if (!(ul >= 1.0 && ul < (double)(lw - 2) && vl >= 1.0 && vl < (double)(lh - 2))) continue;
-      // floor + fraction without conversions: adding 2^52+2^51 rounding down leaves floor(ul) in the low mantissa word
-      const double kMagic = 6755399441055744.0;
+      // floor + fraction without conversions or float64 compares: adding 1.5 * 2^20 (rounding down) leaves floor(ul)
+      // in the low bits of the high mantissa word and the fraction, scaled by 2^32, in the low word; NaN / Inf /
+      // |ul| >= 2^19 give a high word far outside any image
+      const double kMagic = 1572864.0;
       const double tu = __dadd_rd(ul, kMagic), tv = __dadd_rd(vl, kMagic);
-      const int x0 = __double2loint(tu), y0 = __double2loint(tv);
-      const float a = (float)(ul - (tu - kMagic)), b = (float)(vl - (tv - kMagic));
-      // float32 copies for the Jacobian (rounding of these only perturbs the LM step, not the cost)
-      const float Yx = R0 * sm.x + R1 * sm.y + R2 * sm.z;
-      const float Yy = R3 * sm.x + R4 * sm.y + R5 * sm.z;
-      const float Yz = R6 * sm.x + R7 * sm.y + R8 * sm.z;
-      const float X = Yx + t0, Y = Yy + t1;
+      const int lx = __double2hiint(tu) - xbias, ly = __double2hiint(tv) - ybias;     // footprint origin in the tile
+      const bool zok = dZ > 1e-6;
       // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
       uint32_t row[4];
-      const int lx = x0 - 1 - tx0, ly = y0 - 1 - ty0;
-      if (lx >= 0 && ly >= 0 && lx + 4 <= tw && ly + 4 <= th) {
-        const int off = ly * TILE_PITCH + lx;
+      if (zok && (uint32_t)lx < tw_m3 && (uint32_t)ly < th_m3) {
+        // the tile lies inside the level image, so a footprint inside the tile is a valid sample
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s_tile + ly * TILE_PITCH + (lx & ~3));
+        const uint32_t sel = 0x3210 + 0x1111 * (lx & 3);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) row[r] = ld4_unaligned_smem(s_tile, off + r * TILE_PITCH);
+        for (int r = 0; r < 4; ++r) row[r] = __byte_perm(w[r * (TILE_PITCH / 4)], w[r * (TILE_PITCH / 4) + 1], sel);
       } else {
+        const int x0 = lx + tx0 + 1, y0 = ly + ty0 + 1;
+        // valid <=> z > 1e-6 and 1 <= floor(ul) <= lw-3 and 1 <= floor(vl) <= lh-3
+        if (!zok || x0 < 1 || x0 > lw - 3 || y0 < 1 || y0 > lh - 3) continue;
         if (x0 - 1 < S.rx0 || y0 - 1 < S.ry0 || x0 + 3 > S.rx1 || y0 + 3 > S.ry1) S.left_roi = 1;   // benign race: all write 1
         const uint8_t* g = limg + (int64_t)(y0 - 1) * lpitch + (x0 - 1);
 #pragma unroll
         for (int r = 0; r < 4; ++r) row[r] = ld4_global(g + r * lpitch);
       }
+      // bilinear weights; (a, b) = fractions of (ul, vl)
+      const f32x2 ab = mul2(pk2((float)(uint32_t)__double2loint(tu), (float)(uint32_t)__double2loint(tv)), bc2(2.3283064365386963e-10f));
+      const f32x2 omab = fma2(ab, bc2(-1.f), bc2(1.f));                     // (1-a, 1-b)
+      const f32x2 wx = mul2(ab, swap2(omab));                               // (w01, w10) = (a (1-b), b (1-a))
+      const float w00 = lo2(omab) * hi2(omab), w11 = lo2(ab) * hi2(ab), w01 = lo2(wx), w10 = hi2(wx);
       // Scharr at (x0,y0) (x0+1,y0) (x0,y0+1) (x0+1,y0+1): the [3 10 3] row weights are folded into the byte
-      // coefficients and the three rows are chained through the dp4a accumulator - no integer combine afterwards
-      const float gx00 = (float)dp4c(row[2], C_DX0_3, dp4c(row[1], C_DX0_10, dp4c(row[0], C_DX0_3, 0)));
-      const float gx01 = (float)dp4c(row[2], C_DX1_3, dp4c(row[1], C_DX1_10, dp4c(row[0], C_DX1_3, 0)));
-      const float gx10 = (float)dp4c(row[3], C_DX0_3, dp4c(row[2], C_DX0_10, dp4c(row[1], C_DX0_3, 0)));
-      const float gx11 = (float)dp4c(row[3], C_DX1_3, dp4c(row[2], C_DX1_10, dp4c(row[1], C_DX1_3, 0)));
-      const float gy00 = (float)dp4c(row[2], C_SM0, dp4c(row[0], C_SM0_NEG, 0));
-      const float gy01 = (float)dp4c(row[2], C_SM1, dp4c(row[0], C_SM1_NEG, 0));
-      const float gy10 = (float)dp4c(row[3], C_SM0, dp4c(row[1], C_SM0_NEG, 0));
-      const float gy11 = (float)dp4c(row[3], C_SM1, dp4c(row[1], C_SM1_NEG, 0));
+      // coefficients and the three rows are chained through the dp4a accumulator, which starts at the bit pattern of
+      // 1.5 * 2^23: the integer sum lands in the mantissa and one packed subtraction turns two taps into floats
+      const int kB = 0x4B400000;
+      const f32x2 kNegBias = bc2(-12582912.f);
+      const f32x2 g00 = add2(pk2(dp4c(row[2], C_DX0_3, dp4c(row[1], C_DX0_10, dp4c(row[0], C_DX0_3, kB))),
+                                 dp4c(row[2], C_SM0, dp4c(row[0], C_SM0_NEG, kB))), kNegBias);
+      const f32x2 g01 = add2(pk2(dp4c(row[2], C_DX1_3, dp4c(row[1], C_DX1_10, dp4c(row[0], C_DX1_3, kB))),
+                                 dp4c(row[2], C_SM1, dp4c(row[0], C_SM1_NEG, kB))), kNegBias);
+      const f32x2 g10 = add2(pk2(dp4c(row[3], C_DX0_3, dp4c(row[2], C_DX0_10, dp4c(row[1], C_DX0_3, kB))),
+                                 dp4c(row[3], C_SM0, dp4c(row[1], C_SM0_NEG, kB))), kNegBias);
+      const f32x2 g11 = add2(pk2(dp4c(row[3], C_DX1_3, dp4c(row[2], C_DX1_10, dp4c(row[1], C_DX1_3, kB))),
+                                 dp4c(row[3], C_SM1, dp4c(row[1], C_SM1_NEG, kB))), kNegBias);
       const float i00 = (float)((row[1] >> 8) & 0xffu), i01 = (float)((row[1] >> 16) & 0xffu);
       const float i10 = (float)((row[2] >> 8) & 0xffu), i11 = (float)((row[2] >> 16) & 0xffu);
-      const float w11 = a * b, w01 = a - w11, w10 = b - w11, w00 = 1.f - a - b + w11;
       const float I = w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11;
-      const float Gx = (w00 * gx00 + w01 * gx01 + w10 * gx10 + w11 * gx11) * gsc;
-      const float Gy = (w00 * gy00 + w01 * gy01 + w10 * gy10 + w11 * gy11) * gsc;
+      const f32x2 G = fma2(bc2(w11), g11, fma2(bc2(w10), g10, fma2(bc2(w01), g01, mul2(bc2(w00), g00))));   // (Gx, Gy) * 32 * 2^l
       const float r = I - sm.w;
-      const float g0 = Gx * fx * iz, g1 = Gy * fy * iz;
-      const float g2 = -(g0 * X + g1 * Y) * iz;
-      float J[6];
-      J[0] = Yy * g2 - Yz * g1;
-      J[1] = Yz * g0 - Yx * g2;
-      J[2] = Yx * g1 - Yy * g0;
-      J[3] = g0; J[4] = g1; J[5] = g2;
-      int k = 0;
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = p; q < 6; ++q) acc[k++] += J[p] * J[q];
-#pragma unroll
-      for (int p = 0; p < 6; ++p) acc[21 + p] += J[p] * r;
-      cost += (double)r * (double)r;
+      const f32x2 QB = mul2(mul2(G, fg), bc2(iz));                          // (g0, g1) = (J3, J4)
+      const f32x2 XY = add2(Yxy, t01);
+      const float g0 = lo2(QB), g1 = hi2(QB);
+      const float g2 = -(g0 * lo2(XY) + g1 * hi2(XY)) * iz;
+      // (J0, -J1) = g2 (Yy, Yx) - Yz (g1, g0);  J2 = Yx g1 - Yy g0
+      const f32x2 QA = fma2(bc2(g2), swap2(Yxy), mul2(bc2(-Yz), swap2(QB)));
+      const f32x2 QC = pk2(lo2(Yxy) * g1 - hi2(Yxy) * g0, g2);             // (J2, J5)
+      const float q0 = lo2(QA), q1 = hi2(QA), q4 = lo2(QC);
+      p0 = fma2(bc2(q0), QA, p0); p1 = fma2(bc2(q0), QB, p1); p2 = fma2(bc2(q0), QC, p2);
+      p3 = fma2(bc2(q1), QB, p3); p4 = fma2(bc2(q1), QC, p4);
+      p5 = fma2(bc2(g0), QB, p5); p6 = fma2(bc2(g0), QC, p6);
+      p7 = fma2(bc2(g1), QC, p7); p8 = fma2(bc2(q4), QC, p8);
+      p9 = fma2(bc2(r), QA, p9); p10 = fma2(bc2(r), QB, p10); p11 = fma2(bc2(r), QC, p11);
+      s11 = fmaf(q1, q1, s11); s44 = fmaf(g1, g1, s44); s55 = fmaf(g2, g2, s55);
+      // the per-thread cost (<= ~30 terms) in float32: its rounding (1e-8 relative) is below that of the
+      // float32 interpolation feeding it; across threads it is summed in float64
+      scost = fmaf(r, r, scost);
       ++cnt;
     }
-    // ---- reduce: shuffles within the warp, float64 across warps ------------------------
+    // ---- reduce: one transposing butterfly over the 27 sums, float64 across warps --------------------
+    // After the step with offset h a lane keeps the half of the values whose index has bit h equal to its own lane
+    // bit, so 31 shuffles (instead of 27 x 5) leave the total of sum k on lane k - the same summation tree as a
+    // butterfly all-reduce.
+    {
+      float v[32];
+      v[0] = lo2(p0);   v[1] = -hi2(p0);  v[2] = lo2(p2);   v[3] = lo2(p1);   v[4] = hi2(p1);   v[5] = hi2(p2);
+      v[6] = s11;       v[7] = -lo2(p4);  v[8] = -lo2(p3);  v[9] = -hi2(p3);  v[10] = -hi2(p4);
+      v[11] = lo2(p8);  v[12] = lo2(p6);  v[13] = lo2(p7);  v[14] = hi2(p8);
+      v[15] = lo2(p5);  v[16] = hi2(p5);  v[17] = hi2(p6);  v[18] = s44;      v[19] = hi2(p7);  v[20] = s55;
+      v[21] = lo2(p9);  v[22] = -hi2(p9); v[23] = lo2(p11); v[24] = lo2(p10); v[25] = hi2(p10); v[26] = hi2(p11);
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = agt_warp_sum(acc[k]);
-    cost = agt_warp_sum(cost);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) {
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 27; ++k) S.wsum[wid][k] = (double)acc[k];
-      S.wsum[wid][27] = cost;
-      S.wsum[wid][28] = (double)cnt;
+      for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+          const float keep = up ? v[k + h] : v[k], send = up ? v[k] : v[k + h];
+          v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+      }
+      const double cost = agt_warp_sum((double)scost);
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      double o = (double)v[0];
+      if (lane == 27) o = cost;
+      if (lane == 28) o = (double)cnt;
+      if (lane < 29) S.wsum[wid][lane] = o;
     }
     __syncthreads();
-    if (wid == 0) {
-      if (lane < 29) {
-        double s = 0.0;
+    double tot = 0.0;                                     // lane k of warp 0: sum k over the CTA (then the cluster)
+    if (wid == 0 && lane < 29) {
 #pragma unroll
-        for (int w = 0; w < DPR_WARPS; ++w) s += S.wsum[w][lane];
-        S.tot[lane] = s;
-      }
-      __syncwarp();
+      for (int w = 0; w < DPR_WARPS; ++w) tot += S.wsum[w][lane];
     }
     if (kCluster > 1) {
       cg::cluster_group cluster = cg::this_cluster();
+      if (wid == 0 && lane < 29) S.tot[lane] = tot;
       cluster.sync();                                   // every CTA's partial sums are in its S.tot
-      if (crank == 0 && wid == 0) {
-        if (lane < 29) {
-          double s = S.tot[lane];
-          for (int r = 1; r < kCluster; ++r) s += cluster.map_shared_rank(&S, r)->tot[lane];
-          S.tot[lane] = s;
-        }
-        __syncwarp();
-      }
+      if (crank == 0 && wid == 0 && lane < 29)
+        for (int r = 1; r < kCluster; ++r) tot += cluster.map_shared_rank(&S, r)->tot[lane];
     }
 
-    // ================= LM bookkeeping (one thread, float64) ================================
-    if (tid == 0 && crank == 0) {
-      double Hn[21], bn[6];
-      for (int k = 0; k < 21; ++k) Hn[k] = S.tot[k];
-      for (int k = 0; k < 6; ++k) bn[k] = S.tot[21 + k];
-      double cn = 0.5 * S.tot[27];
-      int nn = (int)S.tot[28];
+    // ================= LM bookkeeping (warp 0: decisions in every lane, the 6x6 solve in lane 0) ==========
+    if (wid == 0 && crank == 0) {
+      const double cn = 0.5 * __shfl_sync(0xffffffffu, tot, 27);
+      const int nn = (int)__shfl_sync(0xffffffffu, tot, 28);
       double cc = S.cc, lam = S.lam;
-      int nc = S.nc, evals = S.evals + 1, status = S.status;
-      bool need_step = false;
+      const int evals = S.evals + 1;
+      int status = S.status;
+      bool need_step = false, accept = false;
       if (evals == 1) {
-        for (int k = 0; k < 21; ++k) Hc[k] = Hn[k];
-        for (int k = 0; k < 6; ++k) bc[k] = bn[k];
-        cc = cn; nc = nn;
+        accept = true;
         if (nn == 0) status = AGT_DPR_NONE; else need_step = true;
       } else {
-        double nw = sqrt(dstep[0] * dstep[0] + dstep[1] * dstep[1] + dstep[2] * dstep[2]);
-        double nt = sqrt(dstep[3] * dstep[3] + dstep[4] * dstep[4] + dstep[5] * dstep[5]);
+        // |step| against the tolerances, squared on both sides (no square root on the critical path)
+        const double* ds = S.dstep;
+        const double nw2 = ds[0] * ds[0] + ds[1] * ds[1] + ds[2] * ds[2], nt2 = ds[3] * ds[3] + ds[4] * ds[4] + ds[5] * ds[5];
         if (nn > 0 && cn < cc) {
-          for (int k = 0; k < 9; ++k) Rc[k] = Rt[k];
-          for (int k = 0; k < 3; ++k) tc[k] = tt[k];
-          for (int k = 0; k < 21; ++k) Hc[k] = Hn[k];
-          for (int k = 0; k < 6; ++k) bc[k] = bn[k];
-          cc = cn; nc = nn;
-          lam = fmax(lam / 10.0, LAMBDA_MIN);
-          if (nw < TOL_ROT && nt < TOL_TRANS) status = AGT_DPR_CONVERGED; else need_step = true;
+          accept = true;
+          lam = fmax(lam * 0.1, LAMBDA_MIN);
+          if (nw2 < TOL_ROT * TOL_ROT && nt2 < TOL_TRANS * TOL_TRANS) status = AGT_DPR_CONVERGED; else need_step = true;
         } else {
           lam *= 10.0;
-          if (nw < REJ_TOL_ROT && nt < REJ_TOL_TRANS) status = AGT_DPR_CONVERGED;
+          if (nw2 < REJ_TOL_ROT * REJ_TOL_ROT && nt2 < REJ_TOL_TRANS * REJ_TOL_TRANS) status = AGT_DPR_CONVERGED;
           else if (lam > LAMBDA_MAX) status = AGT_DPR_LAMBDA;
           else need_step = true;
         }
       }
-      if (need_step && evals >= MAX_EVALS) need_step = false;     // status stays MAX_EVALS
-      while (need_step) {
-        double A[36], d[6];
-        int k = 0;
-        for (int p = 0; p < 6; ++p)
-          for (int q = p; q < 6; ++q) { A[p * 6 + q] = Hc[k]; A[q * 6 + p] = Hc[k]; ++k; }
-        for (int p = 0; p < 6; ++p) { A[p * 6 + p] += lam * A[p * 6 + p]; d[p] = -bc[p]; }
-        if (chol6_solve_fast(A, d)) {
-          for (int p = 0; p < 6; ++p) dstep[p] = d[p];
-          double E[9];
-          rodrigues_step(d, E);
-          for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
-          for (int p = 0; p < 3; ++p) tt[p] = tc[p] + d[3 + p];
-          for (int p = 0; p < 9; ++p) { S.R[p] = (float)Rt[p]; S.Rd[p] = Rt[p]; }
-          for (int p = 0; p < 3; ++p) { S.t[p] = (float)tt[p]; S.Rd[9 + p] = tt[p]; }
-          break;
-        }
-        lam *= 10.0;
-        if (lam > LAMBDA_MAX) { status = AGT_DPR_LAMBDA; need_step = false; }
+      if (accept) {                                       // the trial pose and its normal equations become current
+        if (lane < 27) S.Hb[lane] = tot;
+        if (lane < 12) S.Pc[lane] = S.Rd[lane];
+        cc = cn;
       }
-      S.stop = need_step ? 0 : 1;
-      S.cc = cc; S.lam = lam; S.nc = nc; S.evals = evals; S.status = status;
+      if (need_step && evals >= MAX_EVALS) need_step = false;     // status stays MAX_EVALS
+      __syncwarp();
+      if (lane == 0) {
+        while (need_step) {
+          double A[21], d[6];
+#pragma unroll
+          for (int k = 0; k < 21; ++k) A[k] = S.Hb[k];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { A[hk(q, q)] = fma(lam, A[hk(q, q)], A[hk(q, q)]); d[q] = -S.Hb[21 + q]; }
+          if (chol6_packed(A, d)) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) S.dstep[q] = d[q];
+            double E[9], Rt[9], tt[3];
+            rodrigues_step(d, E);
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) Rt[r * 3 + c] = E[r * 3] * Rc[c] + E[r * 3 + 1] * Rc[3 + c] + E[r * 3 + 2] * Rc[6 + c];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) tt[q] = tc[q] + d[3 + q];
+            publish_pose(S, Rt, tt);
+            break;
+          }
+          lam *= 10.0;
+          if (lam > LAMBDA_MAX) { status = AGT_DPR_LAMBDA; need_step = false; }
+        }
+        S.stop = need_step ? 0 : 1;
+        S.cc = cc; S.lam = lam; S.evals = evals; S.status = status;
+        if (accept) S.nc = nn;
+      }
     }
     if (kCluster > 1) {
       cg::cluster_group cluster = cg::this_cluster();
       cluster.sync();                                   // CTA 0 has published the next trial pose (or stop)
       if (crank != 0) {
         const DprShared* S0 = cluster.map_shared_rank(&S, 0);
-        if (tid < 9) { S.R[tid] = S0->R[tid]; S.Rd[tid] = S0->Rd[tid]; }
-        if (tid < 3) { S.t[tid] = S0->t[tid]; S.Rd[9 + tid] = S0->Rd[9 + tid]; }
+        if (tid < 12) { S.Rd[tid] = S0->Rd[tid]; S.Rf[tid] = S0->Rf[tid]; }
         if (tid == 0) S.stop = S0->stop;
       }
     }
