@@ -21,6 +21,7 @@
 // bookkeeping in float64.  Samples whose footprint leaves the staged tile fall
 // back to global loads, so results do not depend on the tile size.
 #include <cooperative_groups.h>
+#include <cstddef>
 
 #include "agt_dpr_plan.cuh"
 
@@ -43,7 +44,7 @@ struct DprShared {
   // trial pose: float64 for the projection, float32 for the Jacobian
   __align__(16) double Rd[12];   // trial rotation (row-major) followed by the translation: six 128-bit broadcast loads
   __align__(16) float Rf[12];    // (R0,R3) (R1,R4) (R2,R5) (t0,t1) as pairs for the packed float32 ops, then R6 R7 R8 t2
-  double fxs, fys, ubase, vbase;   // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l
+  __align__(16) double proj[4];  // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l (two 128-bit loads)
   float fx, fy, cx, cy;
   float inv_scale;       // 2^-level
   float gscale;          // 2^-level / 32
@@ -168,6 +169,24 @@ __device__ __forceinline__ void rodrigues_step(const double w[3], double R[9]) {
   R[6] = b * w[2] * w[0] - a * w[1]; R[7] = b * w[2] * w[1] + a * w[0]; R[8] = c + b * w[2] * w[2];
 }
 
+// shared-window address kept opaque so that it stays in one register instead of being re-derived in the loop;
+// the loads below carry a memory clobber so that the compiler keeps (and orders) the C++ stores they read
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), o;
+  asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(a));
+  return o;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
 // thread 0 publishes a trial pose to the sample loop
 __device__ __forceinline__ void publish_pose(DprShared& S, const double* R, const double* t) {
 #pragma unroll
@@ -188,6 +207,7 @@ constexpr int C_SM0 = (int)0x00030A03;      // (  3, 10,  3,  0)   horizontal sm
 constexpr int C_SM1 = (int)0x030A0300;      // (  0,  3, 10,  3)   horizontal smoothing at x0+1
 constexpr int C_SM0_NEG = (int)0x00FDF6FD;  // ( -3,-10, -3,  0)
 constexpr int C_SM1_NEG = (int)0xFDF6FD00;  // (  0, -3,-10, -3)
+__constant__ int kCoef[8] = {C_DX0_3, C_DX0_10, C_DX1_3, C_DX1_10, C_SM0, C_SM1, C_SM0_NEG, C_SM1_NEG};
 
 // kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
 // the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
@@ -249,8 +269,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     publish_pose(S, Rc, tc);
     S.xbias = 0x41380000 + plan.tx0 + 1; S.ybias = 0x41380000 + plan.ty0 + 1;
     S.tw_m3 = plan.tw >= 4 ? (uint32_t)(plan.tw - 3) : 0u; S.th_m3 = plan.th >= 4 ? (uint32_t)(plan.th - 3) : 0u;
-    S.fxs = cam.fx * sc; S.fys = cam.fy * sc;
-    S.ubase = cam.cx * sc; S.vbase = cam.cy * sc;
+    S.proj[0] = cam.fx * sc; S.proj[1] = cam.fy * sc;
+    S.proj[2] = cam.cx * sc; S.proj[3] = cam.cy * sc;
     S.stop = 0;
   }
   __syncthreads();
@@ -287,6 +307,11 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int xbias = S.xbias, ybias = S.ybias;
   const uint32_t tw_m3 = S.tw_m3, th_m3 = S.th_m3;
   const f32x2 fg = pk2(fx * gsc, fy * gsc);
+  const uint32_t sP = smem_addr(S.Rd), sT = smem_addr(s_tile);
+  constexpr uint32_t kOffFxs = (uint32_t)(offsetof(DprShared, proj) - offsetof(DprShared, Rd));
+  // dp4a coefficient words from constant memory: they stay in uniform registers across the loop
+  const int cDX0_3 = kCoef[0], cDX0_10 = kCoef[1], cDX1_3 = kCoef[2], cDX1_10 = kCoef[3], cSM0 = kCoef[4], cSM1 = kCoef[5],
+            cSM0_NEG = kCoef[6], cSM1_NEG = kCoef[7];
 
   while (true) {
     // ================= evaluate cost + normal equations at the trial pose =================
@@ -299,67 +324,48 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     const f32x2* Rp = reinterpret_cast<const f32x2*>(S.Rf);
     const f32x2 R03 = Rp[0], R14 = Rp[1], R25 = Rp[2], t01 = Rp[3];
     const float R6 = S.Rf[8], R7 = S.Rf[9], R8 = S.Rf[10], t2 = S.Rf[11];
-    // software pipeline: the model record of the next sample is requested before this one is consumed
-    float4 sm_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int j0 = crank * DPR_THREADS + tid;
-    int seg = 0, sidx = 0, seg_end = 0;
-    if (j0 < n_act_samples) {
-      while (j0 >= S.act_prefix[seg + 1]) ++seg;
-      sidx = S.act_begin[seg] + (j0 - S.act_prefix[seg]);
-      seg_end = S.act_prefix[seg + 1];
-      sm_next = __ldg(&samples[sidx]);
-    }
-#pragma unroll 1
-    for (int j = j0; j < n_act_samples; j += kCluster * DPR_THREADS) {
-      const float4 sm = sm_next;
-      const int jn = j + kCluster * DPR_THREADS;
-      if (jn < n_act_samples) {
-        sidx += kCluster * DPR_THREADS;
-        if (jn >= seg_end) {                       // crossed into the next active tag (rare)
-          do { ++seg; } while (jn >= S.act_prefix[seg + 1]);
-          sidx = S.act_begin[seg] + (jn - S.act_prefix[seg]);
-          seg_end = S.act_prefix[seg + 1];
-        }
-      }
-      sm_next = __ldg(&samples[sidx]);             // (the last iteration re-reads its own record)
+    // One sample: projection, footprint fetch, Scharr taps, residual, Jacobian, normal-equation products.
+    auto eval_sample = [&](const float4 sm) {
       // float32 lever arm Y = R x for the Jacobian and the reciprocal-depth seed (rounding of these only perturbs
       // the LM step, not the cost)
       const f32x2 Yxy = fma2(R25, bc2(sm.z), fma2(R14, bc2(sm.y), mul2(R03, bc2(sm.x))));
       const float Yz = fmaf(R8, sm.z, fmaf(R7, sm.y, R6 * sm.x));
+      const float Z32 = Yz + t2;
       float iz;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(Yz + t2));         // MUFU.RCP: Jacobian + Newton seed
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(Z32));             // MUFU.RCP: Jacobian + Newton seed
       // Projection in float64: the accept/reject decisions of the LM loop compare costs that differ by ~1e-6
       // relative near convergence; float32 pixel coordinates (ulp 6e-5 px at 1080p) add ~1e-6 of noise to the
       // cost and flip 20 % of those decisions, float64 leaves 0.2 % (profiles/r01_dpr_precision_sweep.log).
       const double sx = sm.x, sy = sm.y, sz = sm.z;
       // (the float64 pose is read from shared memory with broadcast loads: 24 registers less per thread)
-      const double2* P = reinterpret_cast<const double2*>(S.Rd);
-      const double2 p01 = P[0], p23 = P[1], p45 = P[2], p67 = P[3], p8t = P[4], ptt = P[5];
+      const double2 p01 = lds_f64x2(sP), p23 = lds_f64x2(sP + 16), p45 = lds_f64x2(sP + 32), p67 = lds_f64x2(sP + 48),
+                    p8t = lds_f64x2(sP + 64), ptt = lds_f64x2(sP + 80);
+      const double2 fxy = lds_f64x2(sP + kOffFxs), uvb = lds_f64x2(sP + kOffFxs + 16);    // (fxs, fys) (ubase, vbase)
       const double dX = p01.x * sx + p01.y * sy + p23.x * sz + p8t.y;
       const double dY = p23.y * sx + p45.x * sy + p45.y * sz + ptt.x;
       const double dZ = p67.x * sx + p67.y * sy + p8t.x * sz + ptt.y;
       double r0 = (double)iz;                         // 2^-22 relative; one Newton step -> 2^-44 (4e-11 px at 1080p)
       r0 = r0 * (2.0 - dZ * r0);
-      const double ul = (S.fxs * dX) * r0 + S.ubase, vl = (S.fys * dY) * r0 + S.vbase;
+      const double ul = (fxy.x * dX) * r0 + uvb.x, vl = (fxy.y * dY) * r0 + uvb.y;
       // floor + fraction without conversions or float64 compares: adding 1.5 * 2^20 (rounding down) leaves floor(ul)
       // in the low bits of the high mantissa word and the fraction, scaled by 2^32, in the low word; NaN / Inf /
       // |ul| >= 2^19 give a high word far outside any image
       const double kMagic = 1572864.0;
       const double tu = __dadd_rd(ul, kMagic), tv = __dadd_rd(vl, kMagic);
       const int lx = __double2hiint(tu) - xbias, ly = __double2hiint(tv) - ybias;     // footprint origin in the tile
-      const bool zok = dZ > 1e-6;
       // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
       uint32_t row[4];
-      if (zok && (uint32_t)lx < tw_m3 && (uint32_t)ly < th_m3) {
-        // the tile lies inside the level image, so a footprint inside the tile is a valid sample
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(s_tile + ly * TILE_PITCH + (lx & ~3));
+      if (Z32 > 2e-6f && (uint32_t)lx < tw_m3 && (uint32_t)ly < th_m3) {
+        // (float32 depth above 2e-6 implies float64 depth above 1e-6; the tile lies inside the level image, so a
+        // footprint inside the tile is a valid sample)
+        const uint32_t a0 = sT + ly * TILE_PITCH + (lx & ~3);
         const uint32_t sel = 0x3210 + 0x1111 * (lx & 3);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) row[r] = __byte_perm(w[r * (TILE_PITCH / 4)], w[r * (TILE_PITCH / 4) + 1], sel);
+        for (int r = 0; r < 4; ++r) row[r] = __byte_perm(lds_u32(a0 + r * TILE_PITCH), lds_u32(a0 + r * TILE_PITCH + 4), sel);
       } else {
         const int x0 = lx + tx0 + 1, y0 = ly + ty0 + 1;
         // valid <=> z > 1e-6 and 1 <= floor(ul) <= lw-3 and 1 <= floor(vl) <= lh-3
-        if (!zok || x0 < 1 || x0 > lw - 3 || y0 < 1 || y0 > lh - 3) continue;
+        if (!(dZ > 1e-6) || x0 < 1 || x0 > lw - 3 || y0 < 1 || y0 > lh - 3) return;
         if (x0 - 1 < S.rx0 || y0 - 1 < S.ry0 || x0 + 3 > S.rx1 || y0 + 3 > S.ry1) S.left_roi = 1;   // benign race: all write 1
         const uint8_t* g = limg + (int64_t)(y0 - 1) * lpitch + (x0 - 1);
 #pragma unroll
@@ -375,14 +381,14 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       // 1.5 * 2^23: the integer sum lands in the mantissa and one packed subtraction turns two taps into floats
       const int kB = 0x4B400000;
       const f32x2 kNegBias = bc2(-12582912.f);
-      const f32x2 g00 = add2(pk2(dp4c(row[2], C_DX0_3, dp4c(row[1], C_DX0_10, dp4c(row[0], C_DX0_3, kB))),
-                                 dp4c(row[2], C_SM0, dp4c(row[0], C_SM0_NEG, kB))), kNegBias);
-      const f32x2 g01 = add2(pk2(dp4c(row[2], C_DX1_3, dp4c(row[1], C_DX1_10, dp4c(row[0], C_DX1_3, kB))),
-                                 dp4c(row[2], C_SM1, dp4c(row[0], C_SM1_NEG, kB))), kNegBias);
-      const f32x2 g10 = add2(pk2(dp4c(row[3], C_DX0_3, dp4c(row[2], C_DX0_10, dp4c(row[1], C_DX0_3, kB))),
-                                 dp4c(row[3], C_SM0, dp4c(row[1], C_SM0_NEG, kB))), kNegBias);
-      const f32x2 g11 = add2(pk2(dp4c(row[3], C_DX1_3, dp4c(row[2], C_DX1_10, dp4c(row[1], C_DX1_3, kB))),
-                                 dp4c(row[3], C_SM1, dp4c(row[1], C_SM1_NEG, kB))), kNegBias);
+      const f32x2 g00 = add2(pk2(dp4c(row[2], cDX0_3, dp4c(row[1], cDX0_10, dp4c(row[0], cDX0_3, kB))),
+                                 dp4c(row[2], cSM0, dp4c(row[0], cSM0_NEG, kB))), kNegBias);
+      const f32x2 g01 = add2(pk2(dp4c(row[2], cDX1_3, dp4c(row[1], cDX1_10, dp4c(row[0], cDX1_3, kB))),
+                                 dp4c(row[2], cSM1, dp4c(row[0], cSM1_NEG, kB))), kNegBias);
+      const f32x2 g10 = add2(pk2(dp4c(row[3], cDX0_3, dp4c(row[2], cDX0_10, dp4c(row[1], cDX0_3, kB))),
+                                 dp4c(row[3], cSM0, dp4c(row[1], cSM0_NEG, kB))), kNegBias);
+      const f32x2 g11 = add2(pk2(dp4c(row[3], cDX1_3, dp4c(row[2], cDX1_10, dp4c(row[1], cDX1_3, kB))),
+                                 dp4c(row[3], cSM1, dp4c(row[1], cSM1_NEG, kB))), kNegBias);
       const float i00 = (float)((row[1] >> 8) & 0xffu), i01 = (float)((row[1] >> 16) & 0xffu);
       const float i10 = (float)((row[2] >> 8) & 0xffu), i11 = (float)((row[2] >> 16) & 0xffu);
       const float I = w00 * i00 + w01 * i01 + w10 * i10 + w11 * i11;
@@ -406,6 +412,42 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       // float32 interpolation feeding it; across threads it is summed in float64
       scost = fmaf(r, r, scost);
       ++cnt;
+    };
+    // This thread's samples are j0, j0 + step, ... of the concatenated active tags.  Software pipeline: the model
+    // record of the next sample is requested before the current one is consumed; two copies of the body alternate
+    // between two record registers so that nothing has to be moved.
+    const int step = kCluster * DPR_THREADS;
+    const int j0 = crank * DPR_THREADS + tid;
+    int left = j0 < n_act_samples ? (n_act_samples - j0 + step - 1) / step : 0;
+    if (left > 0) {
+      int seg = 0;
+      while (j0 >= S.act_prefix[seg + 1]) ++seg;
+      int sidx = S.act_begin[seg] + (j0 - S.act_prefix[seg]);               // record index of the current sample
+      int seg_last = S.act_begin[seg] + (S.act_prefix[seg + 1] - S.act_prefix[seg]);   // end of this tag's records
+      auto advance = [&]() {
+        sidx += step;
+        if (sidx >= seg_last) {                        // crossed into the next active tag (rare)
+          int j = S.act_prefix[seg + 1] + (sidx - seg_last);
+          do { ++seg; } while (j >= S.act_prefix[seg + 1]);
+          sidx = S.act_begin[seg] + (j - S.act_prefix[seg]);
+          seg_last = S.act_begin[seg] + (S.act_prefix[seg + 1] - S.act_prefix[seg]);
+        }
+      };
+      float4 smA = __ldg(&samples[sidx]), smB;
+#pragma unroll 1
+      while (true) {
+        const bool moreA = left > 1;
+        if (moreA) advance();
+        smB = __ldg(&samples[sidx]);                   // (the last sample re-reads its own record)
+        eval_sample(smA);
+        if (!moreA) break;
+        const bool moreB = left > 2;
+        if (moreB) advance();
+        smA = __ldg(&samples[sidx]);
+        eval_sample(smB);
+        if (!moreB) break;
+        left -= 2;
+      }
     }
     // ---- reduce: one transposing butterfly over the 27 sums, float64 across warps --------------------
     // After the step with offset h a lane keeps the half of the values whose index has bit h equal to its own lane
