@@ -42,7 +42,9 @@ constexpr double TOL_ROT = 1e-6, TOL_TRANS = 1e-6, REJ_TOL_ROT = 5e-5, REJ_TOL_T
 
 struct DprShared {
   // trial pose: float64 for the projection, float32 for the Jacobian
-  __align__(16) double Rd[12];   // trial rotation (row-major) followed by the translation: six 128-bit broadcast loads
+  __align__(16) double Rd[12];   // level-l projection matrix of the trial pose, K_l [R | t] with K_l = [[fx_l 0 cx_l] [0 fy_l cy_l] [0 0 1]]:
+                                 // rows as R-part (9, row-major) then t-part (3); six 128-bit broadcast loads per sample
+  double Pt[12];                 // trial pose itself: rotation (row-major) + translation
   __align__(16) float Rf[12];    // (R0,R3) (R1,R4) (R2,R5) (t0,t1) as pairs for the packed float32 ops, then R6 R7 R8 t2
   __align__(16) double proj[4];  // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l (two 128-bit loads)
   float fx, fy, cx, cy;
@@ -60,6 +62,7 @@ struct DprShared {
   int act_begin[AGT_MAX_TAGS];   // first sample of each active tag
   int act_prefix[AGT_MAX_TAGS + 1];
   int stop;
+  int zero;              // 0, read at run time (an ordering dependency the compiler cannot fold away)
   double wsum[DPR_WARPS][NSUM + 2];
   double tot[NSUM + 2];  // cluster exchange only
   // LM state, touched by warp 0 only (kept out of registers)
@@ -189,10 +192,20 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 
 // thread 0 publishes a trial pose to the sample loop
 __device__ __forceinline__ void publish_pose(DprShared& S, const double* R, const double* t) {
+  const double fxl = S.proj[0], fyl = S.proj[1], cxl = S.proj[2], cyl = S.proj[3];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) S.Rd[i] = R[i];
+  for (int c = 0; c < 3; ++c) {
+    S.Rd[c] = fma(fxl, R[c], cxl * R[6 + c]);
+    S.Rd[3 + c] = fma(fyl, R[3 + c], cyl * R[6 + c]);
+    S.Rd[6 + c] = R[6 + c];
+  }
+  S.Rd[9] = fma(fxl, t[0], cxl * t[2]);
+  S.Rd[10] = fma(fyl, t[1], cyl * t[2]);
+  S.Rd[11] = t[2];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) S.Rd[9 + i] = t[i];
+  for (int i = 0; i < 9; ++i) S.Pt[i] = R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S.Pt[9 + i] = t[i];
 #pragma unroll
   for (int c = 0; c < 3; ++c) { S.Rf[2 * c] = (float)R[c]; S.Rf[2 * c + 1] = (float)R[3 + c]; S.Rf[8 + c] = (float)R[6 + c]; }
   S.Rf[6] = (float)t[0]; S.Rf[7] = (float)t[1]; S.Rf[11] = (float)t[2];
@@ -266,11 +279,12 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     }
     S.act_prefix[na] = pre;
     S.n_active = na;
+    S.proj[0] = cam.fx * sc; S.proj[1] = cam.fy * sc;
+    S.proj[2] = cam.cx * sc; S.proj[3] = cam.cy * sc;
+    S.zero = 0;
     publish_pose(S, Rc, tc);
     S.xbias = 0x41380000 + plan.tx0 + 1; S.ybias = 0x41380000 + plan.ty0 + 1;
     S.tw_m3 = plan.tw >= 4 ? (uint32_t)(plan.tw - 3) : 0u; S.th_m3 = plan.th >= 4 ? (uint32_t)(plan.th - 3) : 0u;
-    S.proj[0] = cam.fx * sc; S.proj[1] = cam.fy * sc;
-    S.proj[2] = cam.cx * sc; S.proj[3] = cam.cy * sc;
     S.stop = 0;
   }
   __syncthreads();
@@ -308,7 +322,6 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const uint32_t tw_m3 = S.tw_m3, th_m3 = S.th_m3;
   const f32x2 fg = pk2(fx * gsc, fy * gsc);
   const uint32_t sP = smem_addr(S.Rd), sT = smem_addr(s_tile);
-  constexpr uint32_t kOffFxs = (uint32_t)(offsetof(DprShared, proj) - offsetof(DprShared, Rd));
   // dp4a coefficient words from constant memory: they stay in uniform registers across the loop
   const int cDX0_3 = kCoef[0], cDX0_10 = kCoef[1], cDX1_3 = kCoef[2], cDX1_10 = kCoef[3], cSM0 = kCoef[4], cSM1 = kCoef[5],
             cSM0_NEG = kCoef[6], cSM1_NEG = kCoef[7];
@@ -340,18 +353,17 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       // (the float64 pose is read from shared memory with broadcast loads: 24 registers less per thread)
       const double2 p01 = lds_f64x2(sP), p23 = lds_f64x2(sP + 16), p45 = lds_f64x2(sP + 32), p67 = lds_f64x2(sP + 48),
                     p8t = lds_f64x2(sP + 64), ptt = lds_f64x2(sP + 80);
-      const double2 fxy = lds_f64x2(sP + kOffFxs), uvb = lds_f64x2(sP + kOffFxs + 16);    // (fxs, fys) (ubase, vbase)
-      const double dX = p01.x * sx + p01.y * sy + p23.x * sz + p8t.y;
-      const double dY = p23.y * sx + p45.x * sy + p45.y * sz + ptt.x;
-      const double dZ = p67.x * sx + p67.y * sy + p8t.x * sz + ptt.y;
+      // homogeneous level-l pixel coordinates (K_l folded into the pose by the LM thread): (ul dZ, vl dZ, dZ)
+      const double dX = fma(p01.x, sx, fma(p01.y, sy, fma(p23.x, sz, p8t.y)));
+      const double dY = fma(p23.y, sx, fma(p45.x, sy, fma(p45.y, sz, ptt.x)));
+      const double dZ = fma(p67.x, sx, fma(p67.y, sy, fma(p8t.x, sz, ptt.y)));
       double r0 = (double)iz;                         // 2^-22 relative; one Newton step -> 2^-44 (4e-11 px at 1080p)
       r0 = r0 * (2.0 - dZ * r0);
-      const double ul = (fxy.x * dX) * r0 + uvb.x, vl = (fxy.y * dY) * r0 + uvb.y;
-      // floor + fraction without conversions or float64 compares: adding 1.5 * 2^20 (rounding down) leaves floor(ul)
-      // in the low bits of the high mantissa word and the fraction, scaled by 2^32, in the low word; NaN / Inf /
-      // |ul| >= 2^19 give a high word far outside any image
+      // floor + fraction without conversions or float64 compares: ul + 1.5 * 2^20 (one FMA rounding down) leaves
+      // floor(ul) in the low bits of the high mantissa word and the fraction, scaled by 2^32, in the low word;
+      // NaN / Inf / |ul| >= 2^19 give a high word far outside any image
       const double kMagic = 1572864.0;
-      const double tu = __dadd_rd(ul, kMagic), tv = __dadd_rd(vl, kMagic);
+      const double tu = __fma_rd(dX, r0, kMagic), tv = __fma_rd(dY, r0, kMagic);
       const int lx = __double2hiint(tu) - xbias, ly = __double2hiint(tv) - ybias;     // footprint origin in the tile
       // 4x4 footprint rows y0-1..y0+2, columns x0-1..x0+2
       uint32_t row[4];
@@ -433,17 +445,21 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
           seg_last = S.act_begin[seg] + (S.act_prefix[seg + 1] - S.act_prefix[seg]);
         }
       };
+      // The address of each request is made to depend on the record about to be consumed: the scoreboards count
+      // outstanding loads, so a request issued just before the first use of the previous record would make that use
+      // wait for the new request as well (seen as 11 % of all stall samples on one instruction).
+      const int zero = S.zero;
       float4 smA = __ldg(&samples[sidx]), smB;
 #pragma unroll 1
       while (true) {
         const bool moreA = left > 1;
         if (moreA) advance();
-        smB = __ldg(&samples[sidx]);                   // (the last sample re-reads its own record)
+        smB = __ldg(&samples[sidx + (__float_as_int(smA.w) & zero)]);     // (the last sample re-reads its own record)
         eval_sample(smA);
         if (!moreA) break;
         const bool moreB = left > 2;
         if (moreB) advance();
-        smA = __ldg(&samples[sidx]);
+        smA = __ldg(&samples[sidx + (__float_as_int(smB.w) & zero)]);
         eval_sample(smB);
         if (!moreB) break;
         left -= 2;
@@ -520,7 +536,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       }
       if (accept) {                                       // the trial pose and its normal equations become current
         if (lane < 27) S.Hb[lane] = tot;
-        if (lane < 12) S.Pc[lane] = S.Rd[lane];
+        if (lane < 12) S.Pc[lane] = S.Pt[lane];
         cc = cn;
       }
       if (need_step && evals >= MAX_EVALS) need_step = false;     // status stays MAX_EVALS
