@@ -222,6 +222,49 @@ constexpr int C_SM0_NEG = (int)0x00FDF6FD;  // ( -3,-10, -3,  0)
 constexpr int C_SM1_NEG = (int)0xFDF6FD00;  // (  0, -3,-10, -3)
 __constant__ int kCoef[8] = {C_DX0_3, C_DX0_10, C_DX1_3, C_DX1_10, C_SM0, C_SM1, C_SM0_NEG, C_SM1_NEG};
 
+// Per-refinement setup that depends only on the initial pose, computed by one thread per refinement in a launch of its
+// own (dpr_prep_kernel) instead of by thread 0 of every CTA while 255 threads wait: pyramid level and ROI plan
+// (atan / asin / tan), rotation matrix of the initial pose (sincos) and the visibility test of each tag.
+struct __align__(16) DprJob {
+  int32_t level, rx0, ry0, rx1;       // 16-byte words read by every thread of the CTA
+  int32_t ry1, tx0, ty0, tw;
+  int32_t th;
+  uint32_t active;                    // bit k: tag k passes the visibility test at the initial pose
+  int32_t pad[2];
+  double R[9];                        // rotation of the initial pose, row-major
+  double pad2;
+};
+static_assert(sizeof(DprJob) == 128, "DprJob layout");
+
+__global__ void dpr_prep_kernel(agt_pyramid pyr, agt_camera cam, agt_model model, const double* __restrict__ init, int n_hyp,
+                                const uint8_t* __restrict__ mask, DprJob* __restrict__ jobs, int64_t n_jobs) {
+  const int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (job >= n_jobs) return;
+  if (mask != nullptr && mask[job / n_hyp] == 0) return;
+  const double* p0 = init + job * 6;
+  const double r0[3] = {p0[0], p0[1], p0[2]}, tc[3] = {p0[3], p0[4], p0[5]};
+  double Rc[9];
+  agt_rodrigues(r0, Rc);
+  const agt_dpr_plan plan = agt_make_dpr_plan(cam, model.pitch, model.radius, tc, pyr.width, pyr.height, pyr.levels);
+  uint32_t active = 0;
+  for (int k = 0; k < model.n_tags; ++k) {
+    double c[3], n[3];
+    for (int i = 0; i < 3; ++i) {
+      c[i] = Rc[i * 3] * model.centres[k][0] + Rc[i * 3 + 1] * model.centres[k][1] + Rc[i * 3 + 2] * model.centres[k][2] + tc[i];
+      n[i] = Rc[i * 3] * model.normals[k][0] + Rc[i * 3 + 1] * model.normals[k][1] + Rc[i * 3 + 2] * model.normals[k][2];
+    }
+    const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
+    if (d > COS_VISIBLE) active |= 1u << k;
+  }
+  DprJob j;
+  j.level = plan.level; j.rx0 = plan.rx0; j.ry0 = plan.ry0; j.rx1 = plan.rx1; j.ry1 = plan.ry1;
+  j.tx0 = plan.tx0; j.ty0 = plan.ty0; j.tw = plan.tw; j.th = plan.th; j.active = active; j.pad[0] = j.pad[1] = 0;
+  for (int i = 0; i < 9; ++i) j.R[i] = Rc[i];
+  j.pad2 = 0.0;
+  jobs[job] = j;
+}
+
 // kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
 // the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
 // slice of the samples, the partial sums meet in CTA 0 through distributed shared memory, CTA 0 runs the LM step
@@ -231,7 +274,7 @@ __global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
            const double* __restrict__ init, int n_hyp, const uint8_t* __restrict__ mask, double* __restrict__ pose_out, float* __restrict__ cost_out,
            int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out,
-           uint8_t* __restrict__ left_roi_out) {
+           uint8_t* __restrict__ left_roi_out, const DprJob* __restrict__ jobs) {
   extern __shared__ __align__(16) uint8_t s_tile[];
   __shared__ DprShared S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -242,35 +285,62 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 
   double* const Rc = S.Pc; double* const tc = S.Pc + 9;
 
+  // ---- the plan of this refinement (dpr_prep_kernel), read by every thread so that staging starts at once --------
+  const int4* jw = reinterpret_cast<const int4*>(jobs + job);
+  const int4 ja = __ldg(jw), jb = __ldg(jw + 1), jc = __ldg(jw + 2);
+  const int lvl = ja.x;
+  {
+    // stage the ROI tile with 16-byte asynchronous copies (LDGSTS): every chunk of a thread is in flight at once and
+    // thread 0 sets up the LM state underneath them
+    const int tx0 = jb.y, ty0 = jb.z, tw = jb.w, th = jc.x;
+    const int lw = pyr.width[lvl];
+    const int64_t lpitch = pyr.pitch[lvl];
+    const uint8_t* limg = pyr.data[lvl] + frame * pyr.frame_stride[lvl];
+    const uint8_t* src = limg + (int64_t)ty0 * lpitch + tx0;
+    const bool vec = ((lpitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(limg) & 15) == 0);
+    const int chunks = tw > 0 ? (tw + 15) >> 4 : 1;
+    const int rows = tw > 0 ? th : 0;                     // (an empty ROI stages nothing)
+    const uint32_t sT0 = (uint32_t)__cvta_generic_to_shared(s_tile);
+    int r = tid / chunks, c = tid - r * chunks;           // chunks <= 18: a step of 256 chunks is dr rows + dc columns
+    const int dr = DPR_THREADS / chunks, dc = DPR_THREADS - dr * chunks;
+    for (; r < rows; ) {
+      const uint8_t* g = src + (int64_t)r * lpitch + 16 * c;
+      if (vec && tx0 + 16 * c + 16 <= (int)lpitch) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sT0 + r * TILE_PITCH + 16 * c), "l"(g) : "memory");
+      } else {
+        uint32_t w4[4] = {0, 0, 0, 0};
+        for (int b = 0; b < 16; ++b)
+          if (tx0 + 16 * c + b < lw) w4[b >> 2] |= (uint32_t)__ldg(g + b) << (8 * (b & 3));
+        *reinterpret_cast<uint4*>(s_tile + r * TILE_PITCH + 16 * c) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+      r += dr; c += dc;
+      if (c >= chunks) { c -= chunks; ++r; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
   if (tid == 0) {
     S.cc = 0.0; S.lam = LAMBDA0; S.nc = 0; S.evals = 0; S.status = AGT_DPR_MAX_EVALS;
     const double* p0 = init + job * 6;
-    double r0[3] = {p0[0], p0[1], p0[2]};
-    agt_rodrigues(r0, Rc);
+    const DprJob* J = jobs + job;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rc[i] = J->R[i];
     tc[0] = p0[3]; tc[1] = p0[4]; tc[2] = p0[5];
-    const agt_dpr_plan plan = agt_make_dpr_plan(cam, model.pitch, model.radius, tc, pyr.width, pyr.height, pyr.levels);
-    const int lvl = plan.level;
     S.level = lvl;
     S.lw = pyr.width[lvl]; S.lh = pyr.height[lvl]; S.lpitch = pyr.pitch[lvl];
     S.limg = pyr.data[lvl] + frame * pyr.frame_stride[lvl];
-    S.rx0 = plan.rx0; S.ry0 = plan.ry0; S.rx1 = plan.rx1; S.ry1 = plan.ry1;
-    S.tx0 = plan.tx0; S.ty0 = plan.ty0; S.tw = plan.tw; S.th = plan.th;
+    S.rx0 = ja.y; S.ry0 = ja.z; S.rx1 = ja.w; S.ry1 = jb.x;
+    S.tx0 = jb.y; S.ty0 = jb.z; S.tw = jb.w; S.th = jc.x;
     S.left_roi = 0;
     double sc = 1.0 / (double)(1 << lvl);
     S.inv_scale = (float)sc;
     S.gscale = (float)(sc / 32.0);
     S.fx = (float)cam.fx; S.fy = (float)cam.fy; S.cx = (float)cam.cx; S.cy = (float)cam.cy;
-    // active tags
+    // active tags (visibility frozen at the initial pose)
+    const uint32_t active = (uint32_t)jc.y;
     int na = 0, pre = 0;
     for (int k = 0; k < model.n_tags; ++k) {
-      double c[3], n[3];
-      for (int i = 0; i < 3; ++i) {
-        c[i] = Rc[i * 3] * model.centres[k][0] + Rc[i * 3 + 1] * model.centres[k][1] + Rc[i * 3 + 2] * model.centres[k][2] + tc[i];
-        n[i] = Rc[i * 3] * model.normals[k][0] + Rc[i * 3 + 1] * model.normals[k][1] + Rc[i * 3 + 2] * model.normals[k][2];
-      }
-      double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-      double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
-      if (d > COS_VISIBLE) {
+      if (active >> k & 1u) {
         S.act_begin[na] = model.tag_begin[k];
         S.act_prefix[na] = pre;
         pre += model.tag_begin[k + 1] - model.tag_begin[k];
@@ -283,33 +353,11 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     S.proj[2] = cam.cx * sc; S.proj[3] = cam.cy * sc;
     S.zero = 0;
     publish_pose(S, Rc, tc);
-    S.xbias = 0x41380000 + plan.tx0 + 1; S.ybias = 0x41380000 + plan.ty0 + 1;
-    S.tw_m3 = plan.tw >= 4 ? (uint32_t)(plan.tw - 3) : 0u; S.th_m3 = plan.th >= 4 ? (uint32_t)(plan.th - 3) : 0u;
+    S.xbias = 0x41380000 + jb.y + 1; S.ybias = 0x41380000 + jb.z + 1;
+    S.tw_m3 = jb.w >= 4 ? (uint32_t)(jb.w - 3) : 0u; S.th_m3 = jc.x >= 4 ? (uint32_t)(jc.x - 3) : 0u;
     S.stop = 0;
   }
-  __syncthreads();
-
-  // ---- stage the ROI tile (128-bit loads; the level rows are 16 B aligned) ----------
-  {
-    const int tw = S.tw, th = S.th;
-    const uint8_t* src = S.limg + (int64_t)S.ty0 * S.lpitch + S.tx0;
-    const bool vec = ((S.lpitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(S.limg) & 15) == 0);
-    const int chunks = (tw + 15) >> 4;
-    for (int i = tid; i < th * chunks; i += DPR_THREADS) {
-      int r = i / chunks, c = i - r * chunks;
-      const uint8_t* g = src + (int64_t)r * S.lpitch + 16 * c;
-      uint4 v;
-      if (vec && S.tx0 + 16 * c + 16 <= (int)S.lpitch) {
-        v = __ldg(reinterpret_cast<const uint4*>(g));
-      } else {
-        uint32_t w4[4] = {0, 0, 0, 0};
-        for (int b = 0; b < 16; ++b)
-          if (S.tx0 + 16 * c + b < S.lw) w4[b >> 2] |= (uint32_t)__ldg(g + b) << (8 * (b & 3));
-        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-      }
-      *reinterpret_cast<uint4*>(s_tile + r * TILE_PITCH + 16 * c) = v;
-    }
-  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   const int n_act_samples = S.act_prefix[S.n_active];
@@ -669,13 +717,22 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
   }
   // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower.
   // Small batches (fewer refinements than 2 CTA slots per SM) are spread over clusters of 2 / 4 / 8 CTAs.
+  DprJob* d_jobs = nullptr;
+  {
+    void* pj = nullptr;
+    int rc = agt_scratch(ctx, 5, sizeof(DprJob) * (size_t)jobs, &pj);
+    if (rc) return rc;
+    d_jobs = static_cast<DprJob*>(pj);
+  }
+  dpr_prep_kernel<<<(unsigned)((jobs + 127) / 128), 128, 0, ctx->stream>>>(*pyr, ctx->cam, ctx->model, d_init, n_hyp, d_mask, d_jobs, jobs);
+  AGT_LAUNCH_CHECK(ctx);
   int cluster = 1;
   const int64_t slots = 2LL * ctx->sm_count;
   while (cluster < 8 && jobs * (cluster * 2) <= slots) cluster *= 2;
   if (cluster == 1) {
     dpr_kernel<1><<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
                                                                          n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status,
-                                                                         d_left_roi);
+                                                                         d_left_roi, d_jobs);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(jobs * cluster));
@@ -690,11 +747,11 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
     const float4* smp = ctx->model.samples;
     cudaError_t e;
     if (cluster == 2)
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<2>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<2>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
     else if (cluster == 4)
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<4>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<4>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
     else
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<8>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<8>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
     if (e != cudaSuccess) AGT_FAIL(ctx, AGT_ERR_CUDA, "agt_refine: cluster launch failed: %s", cudaGetErrorString(e));
   }
   AGT_LAUNCH_CHECK(ctx);
