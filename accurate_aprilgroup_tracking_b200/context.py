@@ -247,10 +247,12 @@ class AgtContext:
         return acc, flag
 
     # -- K4 ---------------------------------------------------------------------------
-    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None, out=None):
+    def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None, out=None, fused: bool = False):
         """init [B,H,6] f64 -> dict(pose [B,H,6], cost [B,H], n_valid, evals, status, left_roi).
         mask [B] u8: frames with 0 are skipped and none of their outputs is written; ``out`` (a previous result
-        dict) receives the outputs in place, otherwise skipped frames read pose = init, everything else 0."""
+        dict) receives the outputs in place, otherwise skipped frames read pose = init, everything else 0.
+        fused: only level 0 of ``pyr`` holds the frames; every refinement builds the part of its level it reads
+        inside the kernel (agt_refine_fused)."""
         t = self.torch
         b = int(pyr.batch if batch is None else batch)
         ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
@@ -264,9 +266,10 @@ class AgtContext:
                    "left_roi": fresh((b, n_hyp), dtype=t.uint8, device=self.tdev)}
         msk = self._dev(mask, t.uint8) if mask is not None else None
         self._use_current_stream()
-        self._check(self.lib.agt_refine(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(out["pose"]),
-                                        self._p(out["cost"]), self._p(out["n_valid"]), self._p(out["evals"]), self._p(out["status"]),
-                                        self._p(out["left_roi"]), b))
+        fn = self.lib.agt_refine_fused if fused else self.lib.agt_refine
+        self._check(fn(self.h, C.byref(pyr.desc), self._p(ini), n_hyp, self._p(msk), self._p(out["pose"]),
+                       self._p(out["cost"]), self._p(out["n_valid"]), self._p(out["evals"]), self._p(out["status"]),
+                       self._p(out["left_roi"]), b))
         return out
 
     def dpr_rects(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
@@ -301,6 +304,21 @@ class AgtContext:
         rects = self.dpr_rects(pyr, ini, n_hyp, b)
         self.build_pyramid_roi(pyr, rects, b)
         res = self.refine(pyr, ini, n_hyp, b)
+        redo = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._check(self.lib.agt_any_flag(self.h, self._p(res["left_roi"]), n_hyp, self._p(redo), b))
+        self.build_pyramid_masked(pyr, redo, b)
+        self.refine(pyr, ini, n_hyp, b, mask=redo, out=res)
+        res["redo"] = redo
+        return res
+
+    def refine_fused(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None):
+        """Refinement from level 0 alone (K1 fused into K4), exact by construction: every refinement builds the
+        region of interest of its own pyramid level inside the kernel; frames whose refinement read outside that
+        region (``left_roi``) get the full pyramid and are refined again, all without leaving the device."""
+        t = self.torch
+        b = int(pyr.batch if batch is None else batch)
+        ini = self._dev(init, t.float64).reshape(b, n_hyp, 6)
+        res = self.refine(pyr, ini, n_hyp, b, fused=True)
         redo = t.empty(b, dtype=t.uint8, device=self.tdev)
         self._check(self.lib.agt_any_flag(self.h, self._p(res["left_roi"]), n_hyp, self._p(redo), b))
         self.build_pyramid_masked(pyr, redo, b)

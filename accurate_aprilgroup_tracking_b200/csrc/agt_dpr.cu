@@ -34,6 +34,13 @@ constexpr int DPR_WARPS = DPR_THREADS / 32;
 constexpr int TILE_ROWS = AGT_DPR_TILE_ROWS;
 constexpr int TILE_PITCH = AGT_DPR_TILE_PITCH;
 constexpr int TILE_BYTES = TILE_ROWS * TILE_PITCH + 16;   // +16: the unaligned fetch reads one word past its window
+// fused K1: scratch of the CTA-level pyrDown that builds the level-l ROI inside the refinement kernel
+constexpr int PB_ROWS = 8;                        // output rows per band
+constexpr int PB_IN_ROWS = 2 * PB_ROWS + 3;       // input rows a band reads
+constexpr int PB_OUT_W = 288;                     // output columns per panel (the widest tile)
+constexpr int PB_IN_PITCH = 2 * PB_OUT_W + 32;    // staged input row: 16 B of halo room on each side
+constexpr int PB_H_PITCH = PB_OUT_W;              // horizontal-pass row, uint16 elements
+constexpr int PB_BYTES = 2 * PB_IN_ROWS * PB_IN_PITCH + PB_IN_ROWS * PB_H_PITCH * 2;   // two input buffers (the next band is prefetched)
 constexpr int NSUM = 28;                   // 21 H + 6 b + (cost kept separately in double) + count
 constexpr double COS_VISIBLE = 0.25881904510252074;   // cos 75 deg
 constexpr double LAMBDA0 = 1e-3, LAMBDA_MIN = 1e-9, LAMBDA_MAX = 1e6;
@@ -77,8 +84,9 @@ __device__ __forceinline__ uint32_t ld4_unaligned_smem(const uint8_t* base, int 
   return __byte_perm(w[0], w[1], 0x3210 + 0x1111 * (off & 3));
 }
 
+// (L2-coherent loads: with K1 fused the level image is written by this very launch, so the read-only path is out)
 __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
-  return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+  return (uint32_t)__ldcg(p) | ((uint32_t)__ldcg(p + 1) << 8) | ((uint32_t)__ldcg(p + 2) << 16) | ((uint32_t)__ldcg(p + 3) << 24);
 }
 
 // ---- packed float32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per issue slot) --------------------------
@@ -265,6 +273,111 @@ __global__ void dpr_prep_kernel(agt_pyramid pyr, agt_camera cam, agt_model model
   jobs[job] = j;
 }
 
+// BORDER_REFLECT_101 index (single fold; |overshoot| < n)
+__device__ __forceinline__ int reflect101(int i, int n) { return n - 1 - abs(n - 1 - abs(i)); }
+
+// cv2.pyrDown of one rectangle of a level, by the whole CTA: out = (sum 5x5 [1 4 6 4 1]^2 in + 128) >> 8, integer, so the
+// result is bit-identical to K1 whatever the order.  Output rectangle [x0,x1) x [y0,y1) in destination pixels, x0 % 16 == 0,
+// inside the destination level.  Bands of PB_ROWS output rows: the 2*rows+3 input rows are staged with 16-byte asynchronous
+// copies (reflected borders patched in shared memory), a horizontal pass leaves packed uint16 sums (8 dp4a per 4 outputs),
+// a vertical pass on uint16 pairs (16 * 4080 + 128 fits) writes 4 output bytes per thread to the global level and, where it
+// overlaps, to the shared-memory tile of the refinement.
+__device__ void cta_pyr_down_region(const uint8_t* __restrict__ src, int sw, int sh, int64_t spitch, uint8_t* __restrict__ dst,
+                                    int64_t dpitch, uint8_t* tile, int tx0, int ty0, int tw, int th, int x0, int y0, int x1,
+                                    int y1, uint8_t* s_in, uint16_t* s_h) {
+  const int tid = threadIdx.x;
+  const bool vec = ((spitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const bool dvec = ((dpitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
+  const uint32_t s_in_a = (uint32_t)__cvta_generic_to_shared(s_in);
+  const int n_bands = (y1 - y0 + PB_ROWS - 1) / PB_ROWS, n_panels = (x1 - x0 + PB_OUT_W - 1) / PB_OUT_W;
+  const int n_items = n_bands * n_panels;
+  // geometry of work item i (a band of a panel) and the request for its input rows into buffer i & 1
+  auto stage = [&](int i) {
+    if (i < n_items) {
+      const int px0 = x0 + (i / n_bands) * PB_OUT_W, oy0 = y0 + (i % n_bands) * PB_ROWS;
+      const int pw = min(PB_OUT_W, (x1 - px0 + 3) & ~3);
+      const int in_c0 = 2 * px0 - 16, in_chunks = (2 * pw + 32) >> 4;      // source column of staged offset 0 (16 B aligned)
+      const int in_rows = 2 * min(PB_ROWS, y1 - oy0) + 3, iy0 = 2 * oy0 - 2;
+      uint8_t* buf = s_in + (i & 1) * (PB_IN_ROWS * PB_IN_PITCH);
+      const uint32_t buf_a = s_in_a + (i & 1) * (PB_IN_ROWS * PB_IN_PITCH);
+      for (int r = tid >> 5; r < in_rows; r += DPR_WARPS)
+      for (int c = tid & 31; c < in_chunks; c += 32) {      // a warp per row, a lane per 16-byte chunk (no divisions)
+        const int col = in_c0 + 16 * c;
+        const uint8_t* g = src + (int64_t)reflect101(iy0 + r, sh) * spitch + col;
+        if (col >= 0 && col + 16 <= (int)spitch) {
+          if (vec) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(buf_a + r * PB_IN_PITCH + 16 * c), "l"(g) : "memory");
+          } else {
+            for (int q = 0; q < 16; ++q) buf[r * PB_IN_PITCH + 16 * c + q] = __ldcg(g + q);
+          }
+        } else {
+          for (int q = 0; q < 16; ++q) {
+            const int cc = col + q;
+            buf[r * PB_IN_PITCH + 16 * c + q] = (cc >= 0 && cc < sw) ? __ldcg(g + q) : (uint8_t)0;
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0);
+  for (int i = 0; i < n_items; ++i) {
+    stage(i + 1);                                        // the next band travels while this one is computed
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const int px0 = x0 + (i / n_bands) * PB_OUT_W, oy0 = y0 + (i % n_bands) * PB_ROWS;
+    const int pw = min(PB_OUT_W, (x1 - px0 + 3) & ~3), quads = pw >> 2;
+    const int in_c0 = 2 * px0 - 16;
+    const int rows = min(PB_ROWS, y1 - oy0), in_rows = 2 * rows + 3;
+    uint8_t* buf = s_in + (i & 1) * (PB_IN_ROWS * PB_IN_PITCH);
+    // ---- reflected columns: -2, -1 on the left edge of the level, sw .. on the right edge ----
+    {
+      const int c_lo = 2 * px0 - 2, c_hi = 2 * (px0 + pw - 1) + 2;        // tap range of this panel
+      const int n_left = c_lo < 0 ? -c_lo : 0, n_right = c_hi >= sw ? c_hi - sw + 1 : 0;
+      if (n_left + n_right > 0) {
+        for (int k = tid; k < in_rows * (n_left + n_right); k += DPR_THREADS) {
+          const int r = k / (n_left + n_right), q = k - r * (n_left + n_right);
+          const int cc = q < n_left ? c_lo + q : sw + (q - n_left);
+          buf[r * PB_IN_PITCH + (cc - in_c0)] = buf[r * PB_IN_PITCH + (reflect101(cc, sw) - in_c0)];
+        }
+        __syncthreads();
+      }
+    }
+    // ---- horizontal pass: 4 outputs from 4 words ----
+    for (int r = tid >> 5; r < in_rows; r += DPR_WARPS)
+    for (int q = tid & 31; q < quads; q += 32) {
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(buf + r * PB_IN_PITCH + 12 + 8 * q);      // bytes 2*ox-4 ..
+      const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      const int h0 = dp4c(w1, 0x00010406, dp4c(w0, 0x04010000, 0));      // taps at bytes 2..6
+      const int h1 = dp4c(w2, 0x00000001, dp4c(w1, 0x04060401, 0));      // bytes 4..8
+      const int h2 = dp4c(w2, 0x00010406, dp4c(w1, 0x04010000, 0));      // bytes 6..10
+      const int h3 = dp4c(w3, 0x00000001, dp4c(w2, 0x04060401, 0));      // bytes 8..12
+      *reinterpret_cast<uint2*>(s_h + r * PB_H_PITCH + 4 * q) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+    }
+    __syncthreads();
+    // ---- vertical pass on uint16 pairs ----
+    for (int r = tid >> 5; r < rows; r += DPR_WARPS)
+    for (int q = tid & 31; q < quads; q += 32) {
+      const uint2* hp = reinterpret_cast<const uint2*>(s_h + (2 * r) * PB_H_PITCH + 4 * q);
+      const uint2 a = hp[0], b = hp[PB_H_PITCH / 4], c = hp[2 * (PB_H_PITCH / 4)], d = hp[3 * (PB_H_PITCH / 4)], e = hp[4 * (PB_H_PITCH / 4)];
+      const uint32_t v0 = a.x + e.x + 4u * (b.x + d.x) + 6u * c.x + 0x00800080u;
+      const uint32_t v1 = a.y + e.y + 4u * (b.y + d.y) + 6u * c.y + 0x00800080u;
+      const uint32_t out = __byte_perm(v0, v1, 0x7531);                  // the high byte of each uint16
+      const int ox = px0 + 4 * q, oy = oy0 + r;
+      if (dvec && ox + 4 <= (int)dpitch) {
+        *reinterpret_cast<uint32_t*>(dst + (int64_t)oy * dpitch + ox) = out;
+      } else {
+        for (int m = 0; m < 4; ++m)
+          if (ox + m < (int)dpitch) dst[(int64_t)oy * dpitch + ox + m] = (uint8_t)(out >> (8 * m));
+      }
+      if (tile != nullptr && oy >= ty0 && oy < ty0 + th && ox >= tx0 && ox < tx0 + tw)
+        *reinterpret_cast<uint32_t*>(tile + (oy - ty0) * TILE_PITCH + (ox - tx0)) = out;
+    }
+    __syncthreads();                                     // s_h and buffer i & 1 are free again
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
 // the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
 // slice of the samples, the partial sums meet in CTA 0 through distributed shared memory, CTA 0 runs the LM step
@@ -274,7 +387,7 @@ __global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
            const double* __restrict__ init, int n_hyp, const uint8_t* __restrict__ mask, double* __restrict__ pose_out, float* __restrict__ cost_out,
            int32_t* __restrict__ nvalid_out, int32_t* __restrict__ evals_out, uint8_t* __restrict__ status_out,
-           uint8_t* __restrict__ left_roi_out, const DprJob* __restrict__ jobs) {
+           uint8_t* __restrict__ left_roi_out, const DprJob* __restrict__ jobs, int fuse_pyramid) {
   extern __shared__ __align__(16) uint8_t s_tile[];
   __shared__ DprShared S;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -289,7 +402,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int4* jw = reinterpret_cast<const int4*>(jobs + job);
   const int4 ja = __ldg(jw), jb = __ldg(jw + 1), jc = __ldg(jw + 2);
   const int lvl = ja.x;
-  {
+  const bool build_level = fuse_pyramid != 0 && lvl > 0;
+  if (!build_level) {
     // stage the ROI tile with 16-byte asynchronous copies (LDGSTS): every chunk of a thread is in flight at once and
     // thread 0 sets up the LM state underneath them
     const int tx0 = jb.y, ty0 = jb.z, tw = jb.w, th = jc.x;
@@ -359,6 +473,25 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  if (build_level) {
+    // K1 fused: only level 0 of the pyramid holds the frame.  Build the ROI of levels 1..l from it (intermediate levels
+    // through the pyramid's own global buffers, which stay in L2), the last one also into the tile.
+    uint8_t* s_in = s_tile + TILE_BYTES;
+    uint16_t* s_h = reinterpret_cast<uint16_t*>(s_in + 2 * PB_IN_ROWS * PB_IN_PITCH);
+    for (int L = 1; L <= lvl; ++L) {
+      // rectangle needed at level L: the ROI at level l grown by the 5x5 support of every pyrDown above it
+      int x0 = S.rx0, y0 = S.ry0, x1 = S.rx1, y1 = S.ry1;
+      for (int m = lvl; m > L; --m) {
+        x0 = max(0, 2 * x0 - 2) & ~15; y0 = max(0, 2 * y0 - 2);
+        x1 = min(pyr.width[m - 1], 2 * ((x1 + 3) & ~3) + 2); y1 = min(pyr.height[m - 1], 2 * y1 + 2);
+      }
+      if (x1 > x0 && y1 > y0)
+        cta_pyr_down_region(pyr.data[L - 1] + frame * pyr.frame_stride[L - 1], pyr.width[L - 1], pyr.height[L - 1], pyr.pitch[L - 1],
+                            pyr.data[L] + frame * pyr.frame_stride[L], pyr.pitch[L], L == lvl ? s_tile : nullptr, S.tx0, S.ty0,
+                            S.tw, S.th, x0, y0, x1, y1, s_in, s_h);
+      __syncthreads();
+    }
+  }
 
   const int n_act_samples = S.act_prefix[S.n_active];
   const float fx = S.fx, fy = S.fy, gsc = S.gscale;
@@ -695,9 +828,9 @@ __global__ void select_best_kernel(const double* __restrict__ pose, const float*
 
 }  // namespace
 
-extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
-                          double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
-                          uint8_t* d_left_roi, int batch) {
+static int refine_impl(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+                       double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+                       uint8_t* d_left_roi, int batch, int fuse_pyramid) {
   if (!ctx) return AGT_ERR_INVALID;
   if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!ctx->camera_set || !ctx->model_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_refine: camera and surface model must be set");
@@ -709,10 +842,10 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
   if (jobs > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine: batch*n_hyp too large");
   static bool attr_set[64] = {false};
   if (!attr_set[ctx->device & 63]) {
-    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
-    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
-    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
-    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + PB_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + PB_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + PB_BYTES));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(dpr_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + PB_BYTES));
     attr_set[ctx->device & 63] = true;
   }
   // 2 CTAs/SM at 128 registers: a 3-CTA build (80 registers) spills in the sample loop and measured 20 % slower.
@@ -730,14 +863,14 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
   const int64_t slots = 2LL * ctx->sm_count;
   while (cluster < 8 && jobs * (cluster * 2) <= slots) cluster *= 2;
   if (cluster == 1) {
-    dpr_kernel<1><<<(unsigned)jobs, DPR_THREADS, TILE_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
+    dpr_kernel<1><<<(unsigned)jobs, DPR_THREADS, TILE_BYTES + PB_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
                                                                          n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status,
-                                                                         d_left_roi, d_jobs);
+                                                                         d_left_roi, d_jobs, fuse_pyramid);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(jobs * cluster));
     cfg.blockDim = dim3(DPR_THREADS);
-    cfg.dynamicSmemBytes = TILE_BYTES;
+    cfg.dynamicSmemBytes = TILE_BYTES + PB_BYTES;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -747,15 +880,27 @@ extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_
     const float4* smp = ctx->model.samples;
     cudaError_t e;
     if (cluster == 2)
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<2>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<2>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs, fuse_pyramid);
     else if (cluster == 4)
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<4>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<4>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs, fuse_pyramid);
     else
-      e = cudaLaunchKernelEx(&cfg, dpr_kernel<8>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs);
+      e = cudaLaunchKernelEx(&cfg, dpr_kernel<8>, pv, ctx->cam, smp, ctx->model, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, (const DprJob*)d_jobs, fuse_pyramid);
     if (e != cudaSuccess) AGT_FAIL(ctx, AGT_ERR_CUDA, "agt_refine: cluster launch failed: %s", cudaGetErrorString(e));
   }
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
+}
+
+extern "C" int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+                          double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+                          uint8_t* d_left_roi, int batch) {
+  return refine_impl(ctx, pyr, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, batch, 0);
+}
+
+extern "C" int agt_refine_fused(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+                                double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+                                uint8_t* d_left_roi, int batch) {
+  return refine_impl(ctx, pyr, d_init, n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status, d_left_roi, batch, 1);
 }
 
 extern "C" int agt_select_best(agt_ctx* ctx, const double* d_pose, const float* d_cost, const int32_t* d_n_valid,

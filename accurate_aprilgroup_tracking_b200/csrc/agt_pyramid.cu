@@ -187,7 +187,7 @@ __device__ __forceinline__ void cp_async4(uint32_t smem, const void* gmem, int s
 // (max 16*255 = 4080); vertical 5-tap on the packed words (max 16*4080+128 < 65536, the halves never carry into each
 // other); +128, >>8 and byte packing in one permute per two words; 8*NW-byte stores.  A warp walks down a strip of
 // PF_STRIP output rows; six packed row registers rotate with period three output rows, so nothing is ever moved.
-template <int PF_Q, int PF_STRIP, int NW>
+template <int PF_Q, int PF_STRIP, int NW, bool kStride>
 __global__ void __launch_bounds__(PF_WARPS * 32, NW == 1 ? 6 : 4)
 pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t spitch, int64_t sstride,
                        uint8_t* __restrict__ dst, int ow, int oh, int64_t dpitch, int64_t dstride,
@@ -198,8 +198,14 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   constexpr int RPITCH = 16 + 16 * NW * 32 + 16;
   constexpr int PF_RING = PF_Q + 4;
   const int lane = threadIdx.x & 31;
-  int64_t wg = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);
-  if (wg >= total_warps) return;
+  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][PF_RING][RPITCH];
+  // One work item = one strip of one column block of one frame.  Full-frame and ROI launches have one warp per item;
+  // masked launches (few frames flagged, usually none) use a small grid whose warps stride over the items, so that
+  // a batch with nothing to redo costs a scan of the mask instead of tens of thousands of empty CTAs.
+#define AGT_ITEM_DONE { if (kStride) { wi += (int64_t)gridDim.x * PF_WARPS; __syncwarp(); continue; } else return; }
+  for (int64_t wi = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);;) {
+  if (wi >= total_warps) return;
+  int64_t wg = wi;
   const int cb = (int)(wg % col_blocks);
   wg /= col_blocks;
   const int strip = (int)(wg % strips);
@@ -207,7 +213,7 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   if (mask != nullptr) {                      // only frames with a set flag (any of mask_stride entries)
     bool any = false;
     for (int k = 0; k < mask_stride; ++k) any = any || mask[frame * mask_stride + k] != 0;
-    if (!any) return;
+    if (!any) AGT_ITEM_DONE;
   }
   // output window of this frame: the whole level, or the part of it below the frame's level-0 rectangle
   int xo0 = 0, yo0 = 0, xo1 = ow, yo1 = oh;
@@ -218,7 +224,7 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
     yo0 = max(0, (r[1] >> sh) - 2);
     xo1 = min(ow, (((r[2] + rnd) >> sh) + 2 + 7) & ~7);
     yo1 = min(oh, ((r[3] + rnd) >> sh) + 2);
-    if (r[2] <= r[0] || r[3] <= r[1]) return;
+    if (r[2] <= r[0] || r[3] <= r[1]) AGT_ITEM_DONE;
   }
   const uint8_t* img = src + frame * sstride;
   uint8_t* out = dst + frame * dstride;
@@ -226,9 +232,8 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   const int ix0 = 2 * ox0;
   const int oy0 = yo0 + strip * PF_STRIP;
   const int oy1 = min(oy0 + PF_STRIP, yo1);
-  if (oy0 >= yo1 || xo0 + cb * (32 * OUTS) >= xo1) return;      // warp-uniform
+  if (oy0 >= yo1 || xo0 + cb * (32 * OUTS) >= xo1) AGT_ITEM_DONE;      // warp-uniform
 
-  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][PF_RING][RPITCH];
   const LanePlan<NW> plan = make_plan<NW>(ix0, w, lane);
   const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]);
   const uint32_t ring_end = ring0 + PF_RING * RPITCH;
@@ -314,6 +319,9 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
       emit(oy + 2, h4, h5, h0, h1, h2);
     }
   }
+  AGT_ITEM_DONE;
+  }
+#undef AGT_ITEM_DONE
 }
 
 // Scharr: one thread per pixel pair; loads go through L1.  Not on the hot path
@@ -417,15 +425,16 @@ static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64
     int col_blocks = (ow + 32 * lane_outs - 1) / (32 * lane_outs), strips = (oh + kStrip - 1) / kStrip;
     int64_t total_warps = (int64_t)batch * strips * col_blocks;
     int64_t blocks = (total_warps + PF_WARPS - 1) / PF_WARPS;
+    const bool stride_items = d_mask != nullptr && blocks > 8LL * ctx->sm_count;
+    if (stride_items) blocks = 8LL * ctx->sm_count;                    // warps stride over the items
     if (blocks <= 0x7fffffffLL) {
-      if (wide)
-        pyr_down_stream_kernel<6, kStrip, 2><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
-            d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
-            rect_stride, src_level, d_mask, mask_stride);
-      else
-        pyr_down_stream_kernel<8, kStrip, 1><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(
-            d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects,
-            rect_stride, src_level, d_mask, mask_stride);
+#define AGT_PYR_LAUNCH(Q, NWv, ST)                                                                                        \
+  pyr_down_stream_kernel<Q, kStrip, NWv, ST><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(                          \
+      d_src, w, h, src_pitch, src_stride, d_dst, ow, oh, dst_pitch, dst_stride, col_blocks, strips, total_warps, d_rects, \
+      rect_stride, src_level, d_mask, mask_stride)
+      if (wide) { if (stride_items) AGT_PYR_LAUNCH(6, 2, true); else AGT_PYR_LAUNCH(6, 2, false); }
+      else      { if (stride_items) AGT_PYR_LAUNCH(8, 1, true); else AGT_PYR_LAUNCH(8, 1, false); }
+#undef AGT_PYR_LAUNCH
       AGT_LAUNCH_CHECK(ctx);
       return AGT_OK;
     }

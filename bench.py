@@ -223,18 +223,16 @@ def run_gpu(args):
     redo = torch.empty(B, dtype=torch.uint8, device=ctx.tdev)
 
     def step(ev=None):
-        # K1 restricted to the region of interest of each frame, K4, then the exactness net: frames whose refinement
-        # read outside their rectangle get the full pyramid and are refined again (both launches exit at once otherwise)
+        # K4 with K1 fused into it (every refinement builds the region of interest of its own pyramid level from the
+        # frame), then the exactness net: frames whose refinement read outside that region get the full pyramid and
+        # are refined again (both launches exit at once otherwise)
         if ev: ev[0].record()
-        rects = ctx.dpr_rects(pyr, d_init, 1)
-        ctx.build_pyramid_roi(pyr, rects)
+        res = ctx.refine(pyr, d_init, 1, fused=True)
         if ev: ev[1].record()
-        res = ctx.refine(pyr, d_init, 1)
-        if ev: ev[2].record()
         ctx._check(ctx.lib.agt_any_flag(ctx.h, ctx._p(res["left_roi"]), 1, ctx._p(redo), B))
         ctx.build_pyramid_masked(pyr, redo)
         ctx.refine(pyr, d_init, 1, mask=redo, out=res)
-        if ev: ev[3].record()
+        if ev: ev[2].record()
         if world > 1:                                             # the only collective: gather final poses
             dist.all_gather_into_tensor(gathered, res["pose"].reshape(B, 6))
         return res
@@ -247,7 +245,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     l0 = ctx.launch_count()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
@@ -266,9 +264,8 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    pyr_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    dpr_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    redo_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / args.steps
+    dpr_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    redo_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     n_redo = int(redo.sum().item())
     # the full-frame pyramid kernel (what the LK stage consumes), timed on the same batch outside the step
     fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,6 +276,17 @@ def run_gpu(args):
     fe1.record()
     torch.cuda.synchronize()
     full_pyr_ms = fe0.elapsed_time(fe1) / 5
+    # K4 alone on the pyramid just built (no K1 inside), for comparison with the fused launch of the step
+    ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    plain = ctx.refine(pyr, d_init, 1)
+    ke0.record()
+    for _ in range(5):
+        plain = ctx.refine(pyr, d_init, 1)
+    ke1.record()
+    torch.cuda.synchronize()
+    k4_only_ms = ke0.elapsed_time(ke1) / 5
+    inside = res["left_roi"] == 0
+    fused_equals_plain = bool(all(torch.equal(res[k][inside], plain[k][inside]) for k in ("pose", "cost", "n_valid", "evals", "status")))
 
     # parity guard on the measured batch: the refined poses must sit near the truth they were rendered from
     pose = res["pose"].reshape(B, 6).cpu().numpy()
@@ -351,17 +359,19 @@ def run_gpu(args):
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batched dense pose refinement: 1080p frames, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
-                   "frames_per_gpu": B, "step": "ROI rectangles + K1 pyramid below them (3 pyrDown levels) + K4 LM refinement to convergence + exact redo of frames that left their ROI",
+                   "frames_per_gpu": B, "step": "K4 LM refinement to convergence with K1 fused into it (each refinement builds the region of interest of its own pyramid level from the frame, cv2.pyrDown arithmetic) + exact redo on a full pyramid of frames that left their ROI",
                    "l2": "inputs (%.1f GB of frames per GPU) are larger than L2; no flush needed" % (B * CAM.width * CAM.height / 1e9),
                    "parallelism": f"frames sharded over {world} GPU(s), no collective on the path; NCCL all-gather of final poses"},
         "gpu_launches": int(launches),
-        "kernel_ms": {"roi_pyramid": pyr_ms, "dense_refinement": dpr_ms, "redo_pass": redo_ms, "full_frame_pyramid": full_pyr_ms},
+        "kernel_ms": {"dense_refinement_with_fused_pyramid": dpr_ms, "redo_pass": redo_ms,
+                      "dense_refinement_on_built_pyramid": k4_only_ms, "full_frame_pyramid": full_pyr_ms},
+        "fused_equals_built_pyramid_path": fused_equals_plain,
         "frames_redone_on_full_pyramid": n_redo,
         "lm": {"mean_evals": float(evals.mean()), "max_evals": int(evals.max()), "mean_samples": float(nvalid.mean()),
                "converged_frac": float((status == 1).mean()), "median_trans_err_vs_truth_m": float(np.median(dt))},
         "roofline": {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": DPR_NCU_DRAM_BYTES_PER_POSE * B, "peak_kind": peak_kind, "algorithmic_bytes": algo_bytes,
-                     "note": "per launch; algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); "
+                     "note": "per launch of the step (setup launch + dpr_kernel including its fused pyrDown); algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); "
                              "traffic = ncu dram bytes (profiles/r01_ncu_dpr_kernel.txt): the ROI is staged once in shared memory and "
                              "reused by every LM evaluation, so the kernel is FP32/shared-memory issue bound, not HBM bound"},
         "pyramid_roofline": {"kernel": "pyr_down_stream_kernel (full frames, 3 levels)", "bound": "hbm",

@@ -169,6 +169,15 @@ int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const
 int agt_refine(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
                double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
                uint8_t* d_left_roi, int batch);
+/* As agt_refine, with K1 fused into K4: only level 0 of `pyr` has to hold the frames.  Each refinement builds the
+ * part of levels 1..l it reads (its predicted ROI, grown by the 5x5 support of every pyrDown above it) from
+ * level 0 inside the kernel - cv2.pyrDown arithmetic, bit-identical to agt_build_pyramid - and writes it into
+ * the pyramid's buffers; everything else in levels >= 1 is left untouched.  Results are identical to
+ * agt_build_pyramid + agt_refine unless left_roi is set; such frames must be redone on a full pyramid
+ * (agt_build_pyramid_masked + masked agt_refine), exactly as after agt_build_pyramid_roi. */
+int agt_refine_fused(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_init, int n_hyp, const uint8_t* d_mask,
+                     double* d_pose, float* d_cost, int32_t* d_n_valid, int32_t* d_evals, uint8_t* d_status,
+                     uint8_t* d_left_roi, int batch);
 /* d_rects[batch][4] (16-byte aligned) = the level-0 rectangle x0,y0,x1,y1 the refinements of each frame can
  * read (predicted ROI of every hypothesis + pyramid halo); feed it to agt_build_pyramid_roi.  A frame whose
  * refinement reports left_roi must be redone on a full pyramid (agt_build_pyramid_masked + masked agt_refine). */

@@ -414,3 +414,58 @@ def test_bgr_to_gray_bit_exact(ctxvga):
         got = pyr.frames.cpu().numpy()
         for b in range(2):
             assert np.array_equal(got[b], cv2.cvtColor(bgr[b], cv2.COLOR_BGR2GRAY)), (w, h, b)
+
+
+# ------------------------------------------------------------------------------------------
+# K1 fused into K4
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_hyp", [1, 3])
+def test_fused_pyramid_refinement_is_exact(ctx1080, n_hyp):
+    # K1 fused into K4: only level 0 given, every refinement builds its own level ROI; identical to pyramid + refine.
+    # Depths chosen to hit every pyramid level (q = fx * pitch / z: level 0 above 0.42 m, 1, 2, and 3 below 0.105 m),
+    # objects cut by the image border (reflected taps), a large batch (one CTA per pose) and small ones (clusters).
+    cam = synth.CAMERA_1080P
+    torch = ctx1080.torch
+    rng = np.random.default_rng(2600 + n_hyp)
+    for n in (40, 3):
+        truth = np.array([synth.random_pose(rng) for _ in range(n)])
+        truth[0, 3:] = (0.16, 0.09, 0.27)          # cut by the image corner, level 1
+        truth[1, 3:] = (-0.20, -0.11, 0.30)        # cut by the opposite corner
+        truth[2, 3:] = (0.01, -0.02, 0.16)         # level 2
+        if n > 3:
+            truth[3, 3:] = (0.0, 0.0, 0.50)        # level 0: nothing to build
+            truth[4, 3:] = (0.005, 0.004, 0.10)    # level 3
+            truth[5, 3:] = (0.06, 0.03, 0.12)      # level 2/3 boundary, cut by the border
+            truth[6, 3:] = (0.0, 0.0, 0.2505)
+        init = truth[:, None, :] + np.concatenate([rng.normal(0, 0.01, (n, n_hyp, 3)), rng.normal(0, 0.0005, (n, n_hyp, 3))], axis=2)
+        full = ctx1080.alloc_pyramid(n, cam.width, cam.height, 4)
+        ctx1080.render(full, truth, np.arange(n) + 2600)
+        base = ctx1080.alloc_pyramid(n, cam.width, cam.height, 4)
+        base.levels[0].copy_(full.levels[0])
+        for l in (1, 2, 3):
+            base.levels[l].fill_(255)             # poison: a refinement that reads what it did not build goes visibly wrong
+        ctx1080.build_pyramid(full)
+        want = ctx1080.refine(full, init, n_hyp)
+        got = ctx1080.refine(base, init, n_hyp, fused=True)
+        inside = (got["left_roi"] == 0)
+        assert float(inside.float().mean()) > 0.9
+        assert torch.equal(got["left_roi"], want["left_roi"])
+        for key in ("pose", "cost", "n_valid", "evals", "status"):
+            a, b = got[key][inside], want[key][inside]
+            assert torch.equal(a, b), (key, n, n_hyp)
+        levels_used = set()
+        for b in range(n):
+            q = cam.mtx[0, 0] * synth.model_pitch() / init[b, 0, 5]
+            levels_used.add(0 if q < 2 else 1 if q < 4 else 2 if q < 8 else 3)
+        if n > 3:
+            assert levels_used == {0, 1, 2, 3}
+            # what was built equals the full pyramid there, and most of every level was never touched
+            for b, l in ((0, 1), (2, 2), (4, 3)):
+                built = base.level(l)[b] != 255
+                assert bool(built.any())
+                assert torch.equal(base.level(l)[b][built], full.level(l)[b][built])
+            assert float((base.level(1)[3] == 255).float().mean()) == 1.0      # level-0 refinement builds nothing
+        # the exactness net (redo of frames that left their ROI) gives the full-pyramid result everywhere
+        got2 = ctx1080.refine_fused(base, init, n_hyp)
+        for key in ("pose", "cost", "n_valid", "evals", "status"):
+            assert torch.equal(got2[key], want[key]), (key, "after redo")
