@@ -202,6 +202,20 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
   // One work item = one strip of one column block of one frame.  Full-frame and ROI launches have one warp per item;
   // masked launches (few frames flagged, usually none) use a small grid whose warps stride over the items, so that
   // a batch with nothing to redo costs a scan of the mask instead of tens of thousands of empty CTAs.
+  if (kStride && mask != nullptr) {
+    // nothing flagged in the whole batch (the usual case of the exactness net): leave after one pass over the mask
+    const int64_t n_flags = total_warps / ((int64_t)col_blocks * strips) * mask_stride;
+    uint32_t acc = 0;
+    if ((reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+      const uint4* m4 = reinterpret_cast<const uint4*>(mask);
+#pragma unroll 4
+      for (int64_t i = threadIdx.x; i < n_flags / 16; i += blockDim.x) { const uint4 v = __ldg(m4 + i); acc |= v.x | v.y | v.z | v.w; }
+      for (int64_t i = (n_flags & ~15LL) + threadIdx.x; i < n_flags; i += blockDim.x) acc |= mask[i];
+    } else {
+      for (int64_t i = threadIdx.x; i < n_flags; i += blockDim.x) acc |= mask[i];
+    }
+    if (!__syncthreads_or(acc != 0)) return;
+  }
 #define AGT_ITEM_DONE { if (kStride) { wi += (int64_t)gridDim.x * PF_WARPS; __syncwarp(); continue; } else return; }
   for (int64_t wi = (int64_t)blockIdx.x * PF_WARPS + (threadIdx.x >> 5);;) {
   if (wi >= total_warps) return;

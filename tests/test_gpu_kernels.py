@@ -64,6 +64,31 @@ def test_pyramid_bit_exact(ctxvga, w, h):
             assert np.array_equal(sch[b, :, :, 1], cv2.Scharr(lvl, cv2.CV_16S, 0, 1))
 
 
+def test_masked_pyramid_large_batch(ctxvga):
+    # masked builds of a large batch run on a small grid whose warps stride over the flagged frames' strips
+    # (and leave at once when nothing is flagged): flagged frames equal the full pyramid, the others are untouched
+    import cv2
+    torch = ctxvga.torch
+    n, w, h = 400, 640, 480
+    pyr = ctxvga.alloc_pyramid(n, w, h, 4)
+    pyr.levels[0].random_(0, 256)
+    for l in (1, 2, 3):
+        pyr.levels[l].fill_(255)
+    mask = torch.zeros(n, dtype=torch.uint8, device=pyr.levels[0].device)
+    ctxvga.build_pyramid_masked(pyr, mask)
+    assert all(bool((pyr.levels[l] == 255).all()) for l in (1, 2, 3))
+    flagged = [0, 7, 131, 399]
+    mask[flagged] = 1
+    ctxvga.build_pyramid_masked(pyr, mask)
+    for b in flagged:
+        ref = pyr.frames[b].cpu().numpy()
+        for l in (1, 2, 3):
+            ref = cv2.pyrDown(ref)
+            assert np.array_equal(pyr.level(l)[b].cpu().numpy(), ref), (b, l)
+    for b in (1, 6, 8, 130, 398):
+        assert all(bool((pyr.level(l)[b] == 255).all()) for l in (1, 2, 3)), b
+
+
 def test_pyramid_idempotent_constant(ctxvga):
     # size-independent property: a constant image stays constant at every level
     pyr = ctxvga.alloc_pyramid(2, 1920, 1080, 4)
