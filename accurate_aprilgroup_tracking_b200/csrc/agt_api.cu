@@ -421,14 +421,15 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
     }
     AGT_CUDA(ctx, cudaEventRecord(ctx->ev[2], cp));
     AGT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev[2], 0));
-    if (gathered) {        // the rectangle list is on the device: build the pyramid below the rectangles only
-      if ((rc = agt_build_pyramid_roi(ctx, &p, reinterpret_cast<const int32_t*>(ctx->d_rects + b0), 5, nb))) return rc;
-    } else {
+    // ROI pass: only the rectangle of level 0 each refinement can read is on the device, and the refinement builds
+    // the part of its pyramid level it needs itself (K1 fused into K4).  Redo pass (roi == 0): whole frames, full
+    // pyramid, plain refinement - the result then cannot depend on any ROI prediction.
+    if (!roi) {
       if ((rc = agt_build_pyramid(ctx, &p, nb))) return rc;
     }
     // jobs of this chunk are contiguous in the compacted device arrays [b0*n_hyp, (b0+nb)*n_hyp)
     int64_t j0 = (int64_t)b0 * n_hyp;
-    if ((rc = agt_refine(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,
+    if ((rc = (roi ? agt_refine_fused : agt_refine)(ctx, &p, reinterpret_cast<double*>(dr + o_init) + j0 * 6, n_hyp, nullptr,
                          reinterpret_cast<double*>(dr + o_pose) + j0 * 6, reinterpret_cast<float*>(dr + o_cost) + j0,
                          reinterpret_cast<int32_t*>(dr + o_nv) + j0, reinterpret_cast<int32_t*>(dr + o_ev) + j0,
                          dr + o_st + j0, dr + o_left + j0, nb)))

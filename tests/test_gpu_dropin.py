@@ -158,7 +158,7 @@ def test_refine_host_roi_upload_is_exact(host, ctxvga):
     host.refine_poses(np.full_like(frames, 255), init, cam.mtx)
     l0 = host.launch_count()
     pin = host.refine_poses(pinned.numpy(), init, cam.mtx)
-    assert host.launch_count() - l0 >= 5          # gather + 3 pyrDown + refinement (+ redo pass)
+    assert host.launch_count() - l0 >= 3          # gather + setup + refinement with its fused pyrDown (+ redo pass)
     for key in ("pose", "cost", "n_valid", "evals", "status"):
         assert np.array_equal(pin[key], full[key]), key
     assert host.last_h2d_bytes() == roi_bytes
