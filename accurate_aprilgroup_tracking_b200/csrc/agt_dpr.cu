@@ -273,8 +273,8 @@ __global__ void dpr_prep_kernel(agt_pyramid pyr, agt_camera cam, agt_model model
   jobs[job] = j;
 }
 
-// BORDER_REFLECT_101 index (single fold; |overshoot| < n)
-__device__ __forceinline__ int reflect101(int i, int n) { return n - 1 - abs(n - 1 - abs(i)); }
+// BORDER_REFLECT_101 index: in range almost always, the general fold otherwise
+__device__ __forceinline__ int reflect101(int i, int n) { return (unsigned)i < (unsigned)n ? i : agt_reflect101(i, n); }
 
 // cv2.pyrDown of one rectangle of a level, by the whole CTA: out = (sum 5x5 [1 4 6 4 1]^2 in + 128) >> 8, integer, so the
 // result is bit-identical to K1 whatever the order.  Output rectangle [x0,x1) x [y0,y1) in destination pixels, x0 % 16 == 0,

@@ -494,3 +494,36 @@ def test_fused_pyramid_refinement_is_exact(ctx1080, n_hyp):
         got2 = ctx1080.refine_fused(base, init, n_hyp)
         for key in ("pose", "cost", "n_valid", "evals", "status"):
             assert torch.equal(got2[key], want[key]), (key, "after redo")
+
+
+@pytest.mark.parametrize("w,h,f", [(637, 479, 600.0), (333, 201, 300.0), (161, 121, 150.0)])
+def test_fused_pyramid_odd_sizes(lib_built, w, h, f):
+    # odd widths (unaligned rows: no 16-byte copies), odd heights and levels only a few pixels wide
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    cam = synth.Camera(w, h, f, f, w / 2.0, h / 2.0)
+    ctx = AgtContext(0, cam.mtx, None)
+    ctx.set_synthetic_model()
+    try:
+        torch = ctx.torch
+        rng = np.random.default_rng(w)
+        pitch = synth.model_pitch()
+        depths = [f * pitch / q for q in (1.5, 3.0, 6.0, 8.5)]           # one pose per pyramid level (the last: lens almost on the tag)
+        n = len(depths)
+        truth = np.array([synth.random_pose(rng) for _ in range(n)])
+        for b, z in enumerate(depths):
+            truth[b, 3:] = (0.2 * z * (b - 1.5) / 1.5 * w / (2 * f), 0.0, z)
+        init = truth + np.concatenate([rng.normal(0, 0.005, (n, 3)), rng.normal(0, 0.0002, (n, 3))], axis=1)
+        full = ctx.alloc_pyramid(n, w, h, 4)
+        ctx.render(full, truth, np.arange(n) + w)
+        base = ctx.alloc_pyramid(n, w, h, 4)
+        base.levels[0].copy_(full.levels[0])
+        for l in (1, 2, 3):
+            base.levels[l].fill_(255)
+        ctx.build_pyramid(full)
+        want = ctx.refine(full, init.reshape(n, 1, 6), 1)
+        got = ctx.refine_fused(base, init.reshape(n, 1, 6), 1)
+        assert int(want["n_valid"][0]) > 0          # (short focal lengths put the deeper-level poses inside the object)
+        for key in ("pose", "cost", "n_valid", "evals", "status"):
+            assert torch.equal(got[key], want[key]), (key, w, h)
+    finally:
+        ctx.close()
