@@ -38,8 +38,9 @@ BYTES_PER_POSE_FIXED = 156
 LK_BYTES_PER_CORNER = 5008
 PYR_BYTES_PER_1080P = 2754000
 # dram__bytes_read.sum + dram__bytes_write.sum of one dpr_kernel launch, per pose, from the ncu --set full capture
-# summarised in profiles/r01_ncu_dpr_kernel.txt (67.19 MB for 1024 poses of this workload)
-DPR_NCU_DRAM_BYTES_PER_POSE = 67.19e6 / 1024
+# summarised in profiles/r01_ncu_dpr_kernel.txt (132.67 MB read + 12.67 MB written for 1024 poses of this workload with K1
+# fused into the kernel: the level-0 ROI is read from HBM, the level-1..3 ROIs it builds are written back)
+DPR_NCU_DRAM_BYTES_PER_POSE = 145.34e6 / 1024
 
 
 def measured_peaks():
@@ -217,7 +218,8 @@ def run_gpu(args):
         nb = min(512, B - b0)
         ctx.render(pyr, truth[b0:b0 + nb], np.arange(b0, b0 + nb) + 2000 + 7919 * rank, offset=b0, batch=nb)
     d_init = torch.as_tensor(init, dtype=torch.float64, device=ctx.tdev).reshape(B, 1, 6)
-    gathered = torch.empty((world * B, 6), dtype=torch.float64, device=ctx.tdev) if world > 1 else None
+    gathered = [torch.empty((world * B, 6), dtype=torch.float64, device=ctx.tdev) for _ in range(2)] if world > 1 else None
+    pending, step_no, keep = [None], [0], [None, None]
     torch.cuda.synchronize()
 
     redo = torch.empty(B, dtype=torch.uint8, device=ctx.tdev)
@@ -233,15 +235,29 @@ def run_gpu(args):
         ctx.build_pyramid_masked(pyr, redo)
         ctx.refine(pyr, d_init, 1, mask=redo, out=res)
         if ev: ev[2].record()
-        if world > 1:                                             # the only collective: gather final poses
-            dist.all_gather_into_tensor(gathered, res["pose"].reshape(B, 6))
+        if world > 1:
+            # the only collective: gather the final poses.  Issued asynchronously (NCCL's own stream waits for this
+            # step's kernels) into one of two buffers, so that it travels while the next step computes; the handle of
+            # the previous step is waited for first, and the last one before the timed region ends.
+            if pending[0] is not None:
+                pending[0].wait()
+            k = step_no[0] & 1
+            step_no[0] += 1
+            keep[k] = res["pose"]                                 # keep the source alive until its gather has run
+            pending[0] = dist.all_gather_into_tensor(gathered[k], res["pose"].reshape(B, 6), async_op=True)
         return res
+
+    def drain():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # sampled from the warm-up on, so short timed regions still see clocks under load
     for _ in range(max(args.warmup, 3)):
         res = step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -253,6 +269,7 @@ def run_gpu(args):
     t_begin.record()
     for k in range(args.steps):
         res = step(ev[k])
+    drain()                                                       # the last gather is inside the timed region
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -372,8 +389,8 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": DPR_NCU_DRAM_BYTES_PER_POSE * B, "peak_kind": peak_kind, "algorithmic_bytes": algo_bytes,
                      "note": "per launch of the step (setup launch + dpr_kernel including its fused pyrDown); algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); "
-                             "traffic = ncu dram bytes (profiles/r01_ncu_dpr_kernel.txt): the ROI is staged once in shared memory and "
-                             "reused by every LM evaluation, so the kernel is FP32/shared-memory issue bound, not HBM bound"},
+                             "traffic = ncu dram bytes (profiles/r01_ncu_dpr_kernel.txt): the ROI is read once (and its pyramid level built) into shared memory and "
+                             "reused by every LM evaluation, so the kernel is instruction-issue / latency bound, not HBM bound"},
         "pyramid_roofline": {"kernel": "pyr_down_stream_kernel (full frames, 3 levels)", "bound": "hbm",
                              "achieved": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9 / peak},
