@@ -333,20 +333,21 @@ roi_gather_kernel(const uint8_t* __restrict__ host_frames, int w, int h, const a
   if (cw <= 0 || rows <= 0) continue;
   const uint8_t* src = host_frames + (int64_t)r.src * w * h + (int64_t)r.y0 * w + r.x0;
   uint8_t* out = dst + (int64_t)ri * dst_stride + (int64_t)r.y0 * dst_pitch + r.x0;
-  const int total = cw * rows;
-  for (int i = threadIdx.x; i < total; i += 4 * blockDim.x) {
-    uint4 v[4];
+  // a warp per row, four rows of it in flight: every row is one contiguous run of 16-byte reads, i.e. the fewest
+  // 128-byte lines on the bus (host memory is fetched in whole lines: a rectangle padded to 128 B costs the same
+  // time as the 16 B aligned one, scripts/gather_probe.cu)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int y = wid; y < rows; y += 32)
+    for (int c0 = 0; c0 < cw; c0 += 32) {
+      const int c = c0 + lane;
+      uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int j = i + k * blockDim.x;
-      if (j < total) { int y = j / cw, c = j - y * cw; v[k] = *reinterpret_cast<const uint4*>(src + (int64_t)y * w + 16 * c); }
-    }
+      for (int k = 0; k < 4; ++k)
+        if (y + 8 * k < rows && c < cw) v[k] = *reinterpret_cast<const uint4*>(src + (int64_t)(y + 8 * k) * w + 16 * c);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int j = i + k * blockDim.x;
-      if (j < total) { int y = j / cw, c = j - y * cw; *reinterpret_cast<uint4*>(out + (int64_t)y * dst_pitch + 16 * c) = v[k]; }
+      for (int k = 0; k < 4; ++k)
+        if (y + 8 * k < rows && c < cw) *reinterpret_cast<uint4*>(out + (int64_t)(y + 8 * k) * dst_pitch + 16 * c) = v[k];
     }
-  }
   }
 }
 
