@@ -56,12 +56,15 @@ __device__ __forceinline__ Weights make_weights(float a, float b) {
 
 __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 
+// BORDER_REFLECT_101 index: in range for every window that is not cut by the image border (no modulo then)
+__device__ __forceinline__ int reflect_fast(int i, int n) { return (unsigned)i < (unsigned)n ? i : agt_reflect101(i, n); }
+
 __device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8_t* __restrict__ img, int cols, int rows,
                                              int64_t pitch, int rx0, int ry0, int lane) {
-  int gx = agt_reflect101(rx0 + lane, cols);
+  int gx = reflect_fast(rx0 + lane, cols);
 #pragma unroll 4
   for (int r = 0; r < REG; ++r) {
-    int gy = agt_reflect101(ry0 + r, rows);
+    int gy = reflect_fast(ry0 + r, rows);
     region[r][lane] = __ldg(img + (int64_t)gy * pitch + gx);
   }
 }
@@ -109,7 +112,7 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     // ---- stage the 24x24 template footprint (reflect-101 intensity) -------------
     for (int i = lane; i < PATCH * PATCH; i += 32) {
       int r = i / PATCH, c = i - r * PATCH;
-      int gy = agt_reflect101(iy - 1 + r, rows), gx = agt_reflect101(ix - 1 + c, cols);
+      int gy = reflect_fast(iy - 1 + r, rows), gx = reflect_fast(ix - 1 + c, cols);
       S.u.t.patch[r][c] = __ldg(imgI + (int64_t)gy * pitchI + gx);
     }
     __syncwarp();
