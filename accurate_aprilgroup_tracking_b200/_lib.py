@@ -51,6 +51,9 @@ PROTOTYPES = {
     "agt_set_camera": (_I, [_VP, C.POINTER(_D), C.POINTER(_D), _I]),
     "agt_set_model": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _D]),
     "agt_bgr_to_gray": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
+    "agt_set_undistort": (_I, [_VP, C.POINTER(_D), _I, _I, _I, _I, _I, _I]),
+    "agt_undistort_to_gray": (_I, [_VP, _VP, _I, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
+    "agt_undistort_to_gray_host": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "agt_pyr_down": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
     "agt_build_pyramid": (_I, [_VP, _PYR, _I]),
     "agt_build_pyramid_roi": (_I, [_VP, _PYR, _VP, _I, _I]),

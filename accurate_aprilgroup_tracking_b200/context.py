@@ -149,6 +149,24 @@ class AgtContext:
         self._check(self.lib.agt_bgr_to_gray(self.h, self._p(src), w, h, 3 * w, 3 * w * h, self._p(pyr.levels[0]),
                                              pyr.desc.pitch[0], pyr.desc.frame_stride[0], b))
 
+    def set_undistort(self, new_mtx, width: int, height: int, roi) -> None:
+        """New camera matrix and crop (x, y, w, h) as cv.getOptimalNewCameraMatrix returns them (detect_pose.py:167-173)."""
+        k = np.ascontiguousarray(new_mtx, dtype=np.float64).reshape(9)
+        x, y, w, h = (int(v) for v in roi)
+        self._check(self.lib.agt_set_undistort(self.h, k.ctypes.data_as(C.POINTER(C.c_double)), int(width), int(height), x, y, w, h))
+        self._undistort_roi = (x, y, w, h)
+
+    def ingest_undistort(self, pyr: Pyramid, frames) -> None:
+        """frames [B,H,W,3] BGR or [B,H,W] gray, uint8 -> level 0 of ``pyr`` (roi_w x roi_h) as the reference's
+        undistort_frame + BGR2GRAY would give it (detect_pose.py:147-183, 602)."""
+        t = self.torch
+        src = self._dev(frames, t.uint8)
+        b, h, w = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+        ch = int(src.shape[3]) if src.dim() == 4 else 1
+        self._use_current_stream()
+        self._check(self.lib.agt_undistort_to_gray(self.h, self._p(src), w, h, ch, ch * w, ch * w * h, self._p(pyr.levels[0]),
+                                                   pyr.desc.pitch[0], pyr.desc.frame_stride[0], b))
+
     def build_pyramid(self, pyr: Pyramid, batch: Optional[int] = None) -> None:
         self._use_current_stream()
         self._check(self.lib.agt_build_pyramid(self.h, C.byref(pyr.desc), int(pyr.batch if batch is None else batch)))

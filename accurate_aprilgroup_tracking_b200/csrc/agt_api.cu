@@ -105,6 +105,7 @@ extern "C" int agt_destroy(agt_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   for (int i = 0; i < 8; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   if (ctx->model.samples) cudaFree(ctx->model.samples);
+  if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
   if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);

@@ -13,6 +13,15 @@ struct agt_camera {
   int has_dist;
 };
 
+// frame ingest with undistortion (agt_set_undistort): the new camera matrix, the crop and the stripe height of
+// cv::undistort; the distortion itself comes from agt_camera
+struct agt_undistort {
+  double nfx, nskew, ncx, nfy, ncy;   // new camera matrix (upper triangular)
+  int stripe;                         // rows per map stripe: max(1, 4096 / width) of the frame it was set for
+  int width, height;                  // frame size it was set for
+  int roi_x, roi_y, roi_w, roi_h;     // crop (getOptimalNewCameraMatrix ROI)
+};
+
 struct agt_model {
   float4* samples;       // [S] x,y,z,O
   int n_samples;
@@ -31,8 +40,10 @@ struct agt_ctx {
   cudaStream_t copy_stream;
   cudaStream_t stream;           // where kernels are launched
   cudaEvent_t ev[4];
-  int camera_set, model_set;
+  int camera_set, model_set, undistort_set;
   agt_camera cam;
+  agt_undistort und;
+  short* d_remap_tab;            // [1024][4] int16 bilinear weights of cv::remap (device)
   agt_model model;
   int64_t launches;
   int roi_upload;                // agt_refine_host uploads only the rectangle a refinement can read

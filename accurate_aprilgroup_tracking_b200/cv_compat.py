@@ -186,6 +186,27 @@ class HostContext:
                 out.append(self.Scharr(l))
         return levels - 1, out
 
+    # -- frame ingest -------------------------------------------------------------------
+    def undistort_gray(self, frame, cameraMatrix, distCoeffs, newCameraMatrix, roi):
+        """cv.cvtColor(cv.undistort(frame, K, dist, None, newK)[y:y+h, x:x+w], COLOR_BGR2GRAY) in one device pass:
+        the reference's undistort_frame (detect_pose.py:147-183) followed by the gray conversion (detect_pose.py:602),
+        bit-exact for 8-bit frames.  frame [H,W,3] BGR or [H,W] gray; roi = (x, y, w, h) of getOptimalNewCameraMatrix."""
+        src = np.ascontiguousarray(frame, dtype=np.uint8)
+        if src.ndim not in (2, 3) or (src.ndim == 3 and src.shape[2] != 3):
+            raise ValueError("frame must be [H,W] or [H,W,3] uint8")
+        self.use_camera(cameraMatrix, distCoeffs)
+        h, w = int(src.shape[0]), int(src.shape[1])
+        x, y, rw, rh = (int(v) for v in roi)
+        k = np.ascontiguousarray(newCameraMatrix, dtype=np.float64).reshape(9)
+        key = (k.tobytes(), w, h, x, y, rw, rh, self._cam_key)
+        if key != getattr(self, "_und_key", None):
+            self._check(self.lib.agt_set_undistort(self.h, k.ctypes.data_as(C.POINTER(C.c_double)), w, h, x, y, rw, rh))
+            self._und_key = key
+        out = np.empty((rh, rw), dtype=np.uint8)
+        self._check(self.lib.agt_undistort_to_gray_host(self.h, C.c_void_p(src.ctypes.data), w, h, 1 if src.ndim == 2 else 3,
+                                                        C.c_void_p(out.ctypes.data)))
+        return out
+
     def set_roi_upload(self, enable: bool) -> None:
         self._check(self.lib.agt_set_roi_upload(self.h, int(bool(enable))))
 

@@ -90,6 +90,21 @@ int agt_set_model(agt_ctx* ctx, const float* h_samples, const uint8_t* h_sample_
 int agt_bgr_to_gray(agt_ctx* ctx, const uint8_t* d_bgr, int w, int h, int64_t src_pitch, int64_t src_stride,
                     uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch);
 
+/* ---- frame ingest with lens undistortion: undistort_frame (detect_pose.py:147-183, called by process_frame,
+ * detect_pose.py:611-619) followed by BGR2GRAY (detect_pose.py:602), bit-exact for 8-bit frames --------------- */
+/* new_K[9] (row-major, [[fx s cx] [0 fy cy] [0 0 1]]) and the crop are what cv.getOptimalNewCameraMatrix returns
+ * for width x height frames; the lens model is the one given to agt_set_camera.  Must be called again when the
+ * camera or the frame size changes. */
+int agt_set_undistort(agt_ctx* ctx, const double* new_K, int width, int height, int roi_x, int roi_y, int roi_w, int roi_h);
+/* d_src[batch][h][src_pitch], 1 (gray) or 3 (B,G,R interleaved) channels -> d_gray[batch][roi_h][dst_pitch] =
+ * cvtColor(undistort(frame, K, dist, None, new_K)[roi], BGR2GRAY), e.g. straight into level 0 of a roi_w x roi_h
+ * pyramid.  cv::undistort arithmetic: float64 maps rounded to 1/32 px, cv::remap's int16 bilinear table,
+ * BORDER_CONSTANT 0. */
+int agt_undistort_to_gray(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int channels, int64_t src_pitch,
+                          int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch);
+/* One frame from host memory: h_src[h][w][channels] -> h_gray[roi_h][roi_w]. */
+int agt_undistort_to_gray_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_gray);
+
 /* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
 /* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
 int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,

@@ -54,3 +54,19 @@ ms = timeit(lambda: ctx.refine(pa if False else pb, init, 1), 5)
 res = ctx.refine(pb, init, 1)
 ev = res["evals"].double(); nv = res["n_valid"].double()
 print(f"refine: {ms:.3f} ms for {B} poses -> {B/ms*1e3:.3e} poses/s; mean evals {float(ev.mean()):.2f}; algorithmic {float((36*ev*nv).sum())/ms/1e6:.0f} GB/s")
+# frame ingest: BGR -> gray, and undistort + crop + BGR -> gray (row N2)
+import cv2
+nb = min(B, 256)
+bgr = torch.randint(0, 256, (nb, cam.height, cam.width, 3), dtype=torch.uint8, device=ctx.tdev)
+pg = ctx.alloc_pyramid(nb, cam.width, cam.height, 1)
+ms = timeit(lambda: ctx.ingest_bgr(pg, bgr))
+byt = nb * cam.width * cam.height * 4
+print(f"bgr_to_gray: {ms:.3f} ms for {nb} 1080p frames -> {byt/ms/1e6:.0f} GB/s ({byt/ms/1e6/6550.1:.2f} of measured HBM peak)")
+dist = np.array([[-0.28, 0.11, 0.0007, -0.0004, -0.02]])
+new_mtx, roi = cv2.getOptimalNewCameraMatrix(cam.mtx, dist, (cam.width, cam.height), 1, (cam.width, cam.height))
+ctxd = AgtContext(0, cam.mtx, dist)
+ctxd.set_undistort(new_mtx, cam.width, cam.height, roi)
+pu = ctxd.alloc_pyramid(nb, roi[2], roi[3], 1)
+ms = timeit(lambda: ctxd.ingest_undistort(pu, bgr))
+byt = nb * (cam.width * cam.height * 3 + roi[2] * roi[3])
+print(f"undistort_to_gray: {ms:.3f} ms for {nb} 1080p BGR frames (roi {roi[2]}x{roi[3]}) -> {nb/ms*1e3:.3e} frames/s, {byt/ms/1e6:.0f} GB/s ({byt/ms/1e6/6550.1:.2f} of measured HBM peak)")

@@ -213,3 +213,34 @@ def test_pipeline_oracle_reduces_to_ape_and_tracks_through_dropout():
         assert dr < 0.02 and dt < 2e-3, (f, dr, dt)
         if f == 4:
             assert po.tracked >= 1
+
+
+# ------------------------------------------------------------------------------------------
+# frame ingest with undistortion (row N2): the restatement of cv::undistort against the installed cv2,
+# i.e. against the very call the reference makes (detect_pose.py:174)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,f", [(333, 201, 300.0), (640, 480, 600.0), (97, 64, 80.0)])
+def test_undistort_oracle_matches_cv2(w, h, f):
+    import cv2
+    from oracle import undistort_oracle as uo
+    rng = np.random.default_rng(w)
+    mtx = np.array([[f, 0, w / 2 + 3.3], [0, f * 1.01, h / 2 - 2.1], [0, 0, 1]])
+    for dist in ([-0.28, 0.11, 0.0007, -0.0004, -0.02], [0.05, -0.1, 0.001, 0.002, 0.03], [0, 0, 0, 0, 0]):
+        dist = np.array(dist, np.float64).reshape(1, 5)
+        new_mtx, roi = cv2.getOptimalNewCameraMatrix(mtx, dist, (w, h), 1, (w, h))
+        x, y, rw, rh = roi
+        for shape in ((h, w, 3), (h, w)):
+            frame = rng.integers(0, 256, shape, dtype=np.uint8)
+            und = cv2.undistort(frame, mtx, dist, None, new_mtx)
+            assert np.array_equal(uo.undistort(frame, mtx, dist, new_mtx), und)
+            want = und[y:y + rh, x:x + rw]
+            want = cv2.cvtColor(want, cv2.COLOR_BGR2GRAY) if want.ndim == 3 else want
+            assert np.array_equal(uo.undistort_frame_gray(frame, mtx, dist, new_mtx, roi), want)
+
+
+def test_remap_table_sums_to_one():
+    from oracle import undistort_oracle as uo
+    tab = uo.bilinear_table()
+    assert tab.shape == (1024, 4) and (tab.sum(axis=1) == 32768).all() and tab.min() >= 0
+    assert tab[0].tolist() == [32767, 0, 0, 1]          # saturation of 1.0 * 2^15 and the remainder fix-up
+

@@ -527,3 +527,40 @@ def test_fused_pyramid_odd_sizes(lib_built, w, h, f):
             assert torch.equal(got[key], want[key]), (key, w, h)
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------
+# frame ingest with undistortion (row N2): cv.undistort + crop + BGR2GRAY in one pass, bit exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,f", [(640, 480, 600.0), (1920, 1080, 1400.0), (333, 201, 300.0)])
+def test_undistort_ingest_bit_exact(lib_built, w, h, f):
+    import cv2
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    from accurate_aprilgroup_tracking_b200.cv_compat import HostContext
+    rng = np.random.default_rng(h)
+    mtx = np.array([[f, 0, w / 2 + 3.3], [0, f * 1.01, h / 2 - 2.1], [0, 0, 1]])
+    for dist in ([-0.28, 0.11, 0.0007, -0.0004, -0.02], [0.05, -0.1, 0.001, 0.002, 0.03]):
+        dist = np.array(dist, np.float64).reshape(1, 5)
+        new_mtx, roi = cv2.getOptimalNewCameraMatrix(mtx, dist, (w, h), 1, (w, h))
+        x, y, rw, rh = roi
+        ctx = AgtContext(0, mtx, dist)
+        try:
+            ctx.set_undistort(new_mtx, w, h, roi)
+            for n, shape in ((11, (h, w, 3)), (3, (h, w))):          # 11 frames: two groups of the per-thread frame loop
+                frames = rng.integers(0, 256, (n,) + shape, dtype=np.uint8)
+                frames[0] = cv2.GaussianBlur(frames[0], (0, 0), 3.0)
+                pyr = ctx.alloc_pyramid(n, rw, rh, 1)
+                ctx.ingest_undistort(pyr, frames)
+                got = pyr.frames.cpu().numpy()
+                for b in range(n):
+                    want = cv2.undistort(frames[b], mtx, dist, None, new_mtx)[y:y + rh, x:x + rw]
+                    want = cv2.cvtColor(want, cv2.COLOR_BGR2GRAY) if want.ndim == 3 else want
+                    assert np.array_equal(got[b], want), (w, h, b, int(np.abs(got[b].astype(int) - want.astype(int)).max()))
+        finally:
+            ctx.close()
+        host = HostContext(0)
+        frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = cv2.cvtColor(cv2.undistort(frame, mtx, dist, None, new_mtx)[y:y + rh, x:x + rw], cv2.COLOR_BGR2GRAY)
+        assert np.array_equal(host.undistort_gray(frame, mtx, dist, new_mtx, roi), want)
+        host.close()
+
