@@ -129,6 +129,13 @@ def cpu_refine(frames: np.ndarray, init: np.ndarray, workers: int, repeats: int 
     _CPU.update(frames=frames, init=init, model=dpr_oracle.Model(s, tg, n, c, synth.model_pitch()))
     idx = list(range(len(frames)))
     walls = []
+    # one BLAS thread per process: `cores` then means what it says, and 16 processes do not fight over 16 x 16 threads
+    # (measured on the GPU box: 265 poses/s with the default pool, 688 with one thread each; scripts/cpu_probe.py)
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["blas_limit"] = threadpool_limits(1)
+    except Exception:
+        pass
     if workers <= 1:
         for _ in range(repeats):
             t0 = time.perf_counter()
