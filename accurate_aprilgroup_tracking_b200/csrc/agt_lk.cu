@@ -30,17 +30,34 @@ constexpr int WARPS_PER_CTA = 4;
 constexpr int W_BITS = 14;
 constexpr int MAX_ITERS = 30;
 
-struct WarpSmem {
+// Window pixels per lane: 14, in two runs of 7 consecutive pixels of one row each ("segments"), so that the search
+// loop reads every run with three aligned 32-bit loads per image row instead of one byte load per tap:
+//   lanes 0..20 : row = lane, columns 0..6 and 7..13          lanes 21..31 : rows 2(l-21), 2(l-21)+1, columns 14..20
+// (lane 31's second segment would be row 21: it is disabled by zero derivatives).  Per-pixel arrays are stored in
+// this order: index = lane * 14 + k.
+constexpr int PIX_PER_LANE = 14;
+constexpr int SEG_LEN = 7;
+constexpr int NSLOT = 32 * PIX_PER_LANE;   // 448 >= 441
+
+struct __align__(16) WarpSmem {
   union {
     struct {
       uint8_t patch[PATCH][PATCH];         // prev level, origin (ix-1, iy-1)
       short2 der[DER][DER];                // Scharr at (ix..ix+21, iy..iy+21)
     } t;
-    uint8_t region[REG][REG];              // next level search region
+    struct {
+      __align__(16) uint8_t px[REG][REG];  // next level search region
+      uint32_t pad[2];                     // the third word of a run in the last row
+    } region;
   } u;
-  short tmpl[NPIX + 7];                    // template intensity * 32
-  short2 dtmpl[NPIX + 3];                  // template derivative
+  __align__(16) int2 dd[NSLOT];            // template derivative (dx, dy), lane-major
+  short tmpl[NSLOT];                       // template intensity * 32, lane-major
 };
+
+__device__ __forceinline__ void segment_of(int lane, int s, int& row, int& col) {
+  if (lane < WIN) { row = lane; col = SEG_LEN * s; }
+  else { row = 2 * (lane - WIN) + s; col = 2 * SEG_LEN; }
+}
 
 struct Weights { int w00, w01, w10, w11; };
 
@@ -59,6 +76,33 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 // BORDER_REFLECT_101 index: in range for every window that is not cut by the image border (no modulo then)
 __device__ __forceinline__ int reflect_fast(int i, int n) { return (unsigned)i < (unsigned)n ? i : agt_reflect101(i, n); }
 
+// The 8 bytes of a run (columns col..col+7 of one staged row) as two words with the run's first byte in bits 0-7, plus
+// the same shifted by one byte: pixel k of the run blends bytes (k, k+1) of two rows, i.e. one half of one of these
+// words per row, which is exactly what dp2a multiplies by a pair of 16-bit weights.
+struct Run { uint32_t e0, e1, o0, o1; };
+__device__ __forceinline__ Run load_run(uint32_t smem_addr) {
+  const uint32_t wa = smem_addr & ~3u, sh = (smem_addr & 3u) * 8u;
+  uint32_t w0, w1, w2;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(wa + 4));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(wa + 8));
+  Run r;
+  r.e0 = __funnelshift_r(w0, w1, sh);
+  r.e1 = __funnelshift_r(w1, w2, sh);
+  r.o0 = __funnelshift_r(r.e0, r.e1, 8);
+  r.o1 = r.e1 >> 8;
+  return r;
+}
+// bilinear value * 32 of pixel k (0..6) of a run: (w00 p00 + w01 p01 + w10 p10 + w11 p11 + 2^8) >> 9, the same integer
+// OpenCV computes; wt = w00 | w01 << 16, wb = w10 | w11 << 16
+template <int K>
+__device__ __forceinline__ int blend(const Run& t, const Run& b, uint32_t wt, uint32_t wb) {
+  const uint32_t tw = (K & 1) ? (K < 4 ? t.o0 : t.o1) : (K < 4 ? t.e0 : t.e1);
+  const uint32_t bw = (K & 1) ? (K < 4 ? b.o0 : b.o1) : (K < 4 ? b.e0 : b.e1);
+  const uint32_t acc = (K & 2) ? __dp2a_hi(wb, bw, __dp2a_hi(wt, tw, 256u)) : __dp2a_lo(wb, bw, __dp2a_lo(wt, tw, 256u));
+  return (int)(acc >> (W_BITS - 5));
+}
+
 __device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8_t* __restrict__ img, int cols, int rows,
                                              int64_t pitch, int rx0, int ry0, int lane) {
   int gx = reflect_fast(rx0 + lane, cols);
@@ -69,7 +113,7 @@ __device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
 lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
           uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total,
           const int32_t* __restrict__ skip_if_tags_ge2) {
@@ -132,25 +176,39 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
       S.u.t.der[r][c] = d;
     }
     __syncwarp();
-    // ---- template + structure tensor ------------------------------------------
+    // ---- template + structure tensor (lane-major pixel order, see WarpSmem) ------------------
     Weights w = make_weights(__fsub_rn(px, (float)ix), __fsub_rn(py, (float)iy));
+    int seg_row[2], seg_col[2];
+    segment_of(lane, 0, seg_row[0], seg_col[0]);
+    segment_of(lane, 1, seg_row[1], seg_col[1]);
     int s11 = 0, s12 = 0, s22 = 0;
-    for (int i = lane; i < NPIX; i += 32) {
-      int y = i / WIN, x = i - y * WIN;
-      const uint8_t(*p)[PATCH] = S.u.t.patch;
-      int iv = descale(p[y + 1][x + 1] * w.w00 + p[y + 1][x + 2] * w.w01 + p[y + 2][x + 1] * w.w10 + p[y + 2][x + 2] * w.w11,
-                       W_BITS - 5);
-      short2 d00 = S.u.t.der[y][x], d01 = S.u.t.der[y][x + 1], d10 = S.u.t.der[y + 1][x], d11 = S.u.t.der[y + 1][x + 1];
-      int dxv = descale(d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11, W_BITS);
-      int dyv = descale(d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11, W_BITS);
-      S.tmpl[i] = (short)iv;
-      S.dtmpl[i] = make_short2((short)dxv, (short)dyv);
-      s11 += dxv * dxv; s12 += dxv * dyv; s22 += dyv * dyv;
+    long long c1 = 0, c2 = 0;                    // sum of template * derivative: lets the search loop skip the template
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+      const bool live = seg_row[sg] < WIN;
+      const int y = live ? seg_row[sg] : WIN - 1;
+#pragma unroll
+      for (int k = 0; k < SEG_LEN; ++k) {
+        const int x = seg_col[sg] + k;
+        const uint8_t(*p)[PATCH] = S.u.t.patch;
+        int iv = descale(p[y + 1][x + 1] * w.w00 + p[y + 1][x + 2] * w.w01 + p[y + 2][x + 1] * w.w10 + p[y + 2][x + 2] * w.w11,
+                         W_BITS - 5);
+        short2 d00 = S.u.t.der[y][x], d01 = S.u.t.der[y][x + 1], d10 = S.u.t.der[y + 1][x], d11 = S.u.t.der[y + 1][x + 1];
+        int dxv = descale(d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11, W_BITS);
+        int dyv = descale(d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11, W_BITS);
+        if (!live) { iv = 0; dxv = 0; dyv = 0; }
+        const int slot = lane * PIX_PER_LANE + sg * SEG_LEN + k;
+        S.tmpl[slot] = (short)iv;
+        S.dd[slot] = make_int2(dxv, dyv);
+        s11 += dxv * dxv; s12 += dxv * dyv; s22 += dyv * dyv;
+        c1 += iv * dxv; c2 += iv * dyv;
+      }
     }
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float A11 = __fmul_rn((float)agt_warp_sum((long long)s11), FLT_SCALE);
     float A12 = __fmul_rn((float)agt_warp_sum((long long)s12), FLT_SCALE);
     float A22 = __fmul_rn((float)agt_warp_sum((long long)s22), FLT_SCALE);
+    const long long C1 = agt_warp_sum(c1), C2 = agt_warp_sum(c2);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     float dif = __fsub_rn(A11, A22);
     float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -161,6 +219,12 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     }
     D = __fdiv_rn(1.f, D);
     __syncwarp();      // template footprint no longer needed: the region buffer may overwrite it
+
+    const uint32_t region_a = (uint32_t)__cvta_generic_to_shared(&S.u.region.px[0][0]);
+    // shared-memory offset of each run inside the region for a window at (0, 0); disabled runs read a valid row
+    const int run_off0 = (seg_row[0] < WIN ? seg_row[0] : WIN - 1) * REG + seg_col[0];
+    const int run_off1 = (seg_row[1] < WIN ? seg_row[1] : WIN - 1) * REG + seg_col[1];
+    const int4* ddp = reinterpret_cast<const int4*>(&S.dd[lane * PIX_PER_LANE]);      // two pixels per 128-bit load
 
     nx = __fsub_rn(nx, 10.f); ny = __fsub_rn(ny, 10.f);
     float pdx = 0.f, pdy = 0.f;
@@ -175,23 +239,33 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
       if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
         __syncwarp();
         rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
-        stage_region(S.u.region, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+        stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
         staged = true;
         __syncwarp();
       }
       Weights wj = make_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
-      const int ox = jx - rx0, oy = jy - ry0;
+      const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
+      const uint32_t win_a = region_a + (jy - ry0) * REG + (jx - rx0);
+      // b = sum (J - I) dI = sum J dI - sum I dI: exact integers, the second sum is C1, C2
       int sb1 = 0, sb2 = 0;
-      for (int i = lane; i < NPIX; i += 32) {
-        int y = i / WIN, x = i - y * WIN;
-        const uint8_t* r0 = &S.u.region[oy + y][ox + x];
-        int jv = descale(r0[0] * wj.w00 + r0[1] * wj.w01 + r0[REG] * wj.w10 + r0[REG + 1] * wj.w11, W_BITS - 5);
-        int diff = jv - S.tmpl[i];
-        short2 d = S.dtmpl[i];
-        sb1 += diff * d.x; sb2 += diff * d.y;
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg) {
+        const uint32_t a = win_a + (sg == 0 ? run_off0 : run_off1);
+        const Run t = load_run(a), bt = load_run(a + REG);
+        int jv[SEG_LEN];
+        jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
+        jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
+        jv[6] = blend<6>(t, bt, wt, wb);
+#pragma unroll
+        for (int k = 0; k < SEG_LEN; ++k) {
+          const int slot = sg * SEG_LEN + k;                      // 0..13: pair slot / 2 of the 128-bit loads
+          const int4 d2 = ddp[slot >> 1];
+          const int dx = (slot & 1) ? d2.z : d2.x, dy = (slot & 1) ? d2.w : d2.y;
+          sb1 += jv[k] * dx; sb2 += jv[k] * dy;
+        }
       }
-      float b1 = __fmul_rn((float)agt_warp_sum((long long)sb1), FLT_SCALE);
-      float b2 = __fmul_rn((float)agt_warp_sum((long long)sb2), FLT_SCALE);
+      float b1 = __fmul_rn((float)(agt_warp_sum((long long)sb1) - C1), FLT_SCALE);
+      float b2 = __fmul_rn((float)(agt_warp_sum((long long)sb2) - C2), FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -214,18 +288,27 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
         if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
           __syncwarp();
           rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
-          stage_region(S.u.region, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+          stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
           __syncwarp();
         }
         Weights wj = make_weights(__fsub_rn(ex, (float)jx), __fsub_rn(ey, (float)jy));
-        const int ox = jx - rx0, oy = jy - ry0;
+        const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
+        const uint32_t win_a = region_a + (jy - ry0) * REG + (jx - rx0);
         int sabs = 0;
-        for (int i = lane; i < NPIX; i += 32) {
-          int y = i / WIN, x = i - y * WIN;
-          const uint8_t* r0 = &S.u.region[oy + y][ox + x];
-          int jv = descale(r0[0] * wj.w00 + r0[1] * wj.w01 + r0[REG] * wj.w10 + r0[REG + 1] * wj.w11, W_BITS - 5);
-          int diff = jv - S.tmpl[i];
-          sabs += diff < 0 ? -diff : diff;
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+          if (seg_row[sg] >= WIN) continue;
+          const uint32_t a = win_a + (sg == 0 ? run_off0 : run_off1);
+          const Run t = load_run(a), bt = load_run(a + REG);
+          int jv[SEG_LEN];
+          jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
+          jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
+          jv[6] = blend<6>(t, bt, wt, wb);
+#pragma unroll
+          for (int k = 0; k < SEG_LEN; ++k) {
+            int diff = jv[k] - S.tmpl[lane * PIX_PER_LANE + sg * SEG_LEN + k];
+            sabs += diff < 0 ? -diff : diff;
+          }
         }
         err = __fmul_rn((float)agt_warp_sum((long long)sabs), 1.f / (float)(32 * WIN * WIN));
       }
