@@ -52,6 +52,32 @@ undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__
   const int64_t o00 = (int64_t)cy0 * spitch + (int64_t)cx0 * channels, o01 = (int64_t)cy0 * spitch + (int64_t)cx1 * channels;
   const int64_t o10 = (int64_t)cy1 * spitch + (int64_t)cx0 * channels, o11 = (int64_t)cy1 * spitch + (int64_t)cx1 * channels;
   const int b0 = blockIdx.z * kFramesPerThread, b1 = min(b0 + kFramesPerThread, batch);
+  if (channels == 3 && cx1 == cx0 + 1 && ((spitch | sstride) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    // interior pixel of a BGR frame: the two taps of a row are six consecutive bytes B0 G0 R0 B1 G1 R1.  Three aligned
+    // word loads + two funnel shifts fetch them (half the cache wavefronts of six byte loads), one permute per channel
+    // puts (p0, p1) side by side and dp2a blends them with the pair of 16-bit weights.
+    const uint32_t wt = (uint32_t)w00 | ((uint32_t)w01 << 16), wb = (uint32_t)w10 | ((uint32_t)w11 << 16);
+    const int64_t a0 = o00 & ~(int64_t)3, a1 = o10 & ~(int64_t)3;
+    const uint32_t sh0 = (uint32_t)(o00 & 3) * 8u, sh1 = (uint32_t)(o10 & 3) * 8u;
+    // the third word may lie past the end of the last row of the last frame: clamp it inside the batch
+    const int64_t last_word = ((int64_t)(batch - 1) * sstride + (int64_t)h * spitch - 4) & ~(int64_t)3;
+#pragma unroll 1
+    for (int b = b0; b < b1; ++b) {
+      const int64_t fo = (int64_t)b * sstride;
+      const uint32_t* t = reinterpret_cast<const uint32_t*>(src + fo + a0);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(src + fo + a1);
+      const bool t2ok = fo + a0 + 8 <= last_word, u2ok = fo + a1 + 8 <= last_word;
+      const uint32_t t0 = __ldg(t), t1 = __ldg(t + 1), t2 = t2ok ? __ldg(t + 2) : 0u;
+      const uint32_t u0 = __ldg(u), u1 = __ldg(u + 1), u2 = u2ok ? __ldg(u + 2) : 0u;
+      const uint32_t tl = __funnelshift_r(t0, t1, sh0), th = __funnelshift_r(t1, t2, sh0);     // B0 G0 R0 B1 | G1 R1 . .
+      const uint32_t ul = __funnelshift_r(u0, u1, sh1), uh = __funnelshift_r(u1, u2, sh1);
+      const uint32_t vb = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0030), __dp2a_lo(wt, __byte_perm(tl, th, 0x0030), 1u << 14)) >> 15;
+      const uint32_t vg = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0041), __dp2a_lo(wt, __byte_perm(tl, th, 0x0041), 1u << 14)) >> 15;
+      const uint32_t vr = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0052), __dp2a_lo(wt, __byte_perm(tl, th, 0x0052), 1u << 14)) >> 15;
+      dst[(int64_t)b * dstride + (int64_t)y * dpitch + x] = (uint8_t)((vb * 3735u + vg * 19235u + vr * 9798u + 16384u) >> 15);
+    }
+    return;
+  }
   for (int b = b0; b < b1; ++b) {
     const uint8_t* f = src + (int64_t)b * sstride;
     int v[3];
