@@ -604,6 +604,99 @@ def run_streams(args):
             "final_frame_median_trans_err_m": float(np.median(dt)), "accepted_frac_last": float(out["accepted"].float().mean())}), flush=True)
 
 
+def run_config1(args):
+    """Config 1: the reference's own shape - one 640x480 camera stream, 300 frames, APE + LK + dense refinement per frame
+    through the drop-in ``PoseDetector`` (host buffers in, attributes out, one frame at a time) - next to the CPU
+    composition of the stage oracles (the reference's ``_estimate_pose`` state machine + OpenCV LK + dense oracle)."""
+    import logging
+    import tempfile
+    import torch
+    from accurate_aprilgroup_tracking_b200.aprilgroup_pose_estimation import PoseDetector
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    cam = synth.CAMERA_VGA
+    n = 300
+    traj = synth.trajectory(1000, n)
+    rng = np.random.default_rng(1000)
+    ctx = AgtContext(0, cam.mtx, None)
+    ctx.set_synthetic_model()
+    pyr = ctx.alloc_pyramid(n, cam.width, cam.height, 1)
+    ctx.render(pyr, traj, np.arange(n) + 1000)
+    frames = pyr.frames.cpu().numpy()
+    ctx.close()
+    dets_all = []
+    for f in range(n):
+        d = synth.detections(traj[f], cam, rng)
+        if f % 17 == 16:
+            d = d[:1]                                   # periodic detector dropouts exercise the LK path
+        dets_all.append(d)
+
+    class _Det:
+        def __init__(self, tag_id, corners):
+            self.tag_id, self.corners, self.decision_margin = int(tag_id), np.asarray(corners, dtype=np.float64), 100.0
+            self.center = self.corners.mean(axis=0)
+
+    lg = logging.getLogger("agt-bench")
+    lg.handlers[:] = [logging.NullHandler()]
+    lg.propagate = False
+    tmp = tempfile.mkdtemp()
+    synth.write_april_group_json(tmp)
+    cls = type("PD", (PoseDetector,), {"DIRPATH": os.path.join(tmp, "aprilgroup_tracking", "aprilgroup_pose_estimation")})
+
+    def run_gpu_sequence():
+        det = cls(lg, cam.mtx, None, True, use_lk=True, use_dense_refine=True)
+        poses, t_frames = [], []
+        for f in range(n):
+            t0 = time.perf_counter()
+            det.img = None
+            det._prev_gray, det._gray = det._gray, frames[f]
+            lists = det._lists_from_detections([_Det(t, c) for t, c in dets_all[f]])
+            if len(lists[0]) < 2:
+                lists = det._track_lost_tags(*lists)
+            det._estimate_pose(lists[0], lists[1])
+            t_frames.append(time.perf_counter() - t0)
+            pt = det.prev_transform
+            poses.append(None if pt[0] is None else np.concatenate([pt[0].ravel(), pt[1].ravel().astype(np.float64)]))
+        return poses, np.array(t_frames)
+
+    run_gpu_sequence()                                   # warm-up: library load, scratch buffers, kernels
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    poses, t_frames = run_gpu_sequence()
+    wall = time.perf_counter() - t0
+
+    cpu = None
+    if not args.no_cpu:
+        from oracle import ape_oracle, dpr_oracle, pipeline_oracle
+        sm, tg, nn, c = synth.surface_model()
+        po = pipeline_oracle.PipelineOracle(ape_oracle.group_from_json(synth.april_group_dict()), cam.mtx,
+                                            dpr_oracle.Model(sm, tg, nn, c, synth.model_pitch()))
+        n_cpu = 60                                       # a bounded sample of the sequence: ~20 ms of oracle per frame
+        worst_r = worst_t = 0.0
+        t0 = time.perf_counter()
+        for f in range(n_cpu):
+            po.frame(frames[f], dets_all[f])
+            if po.prev[0] is not None and poses[f] is not None:
+                want = np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
+                dr = np.linalg.norm(synth.rodrigues(poses[f][:3]) - synth.rodrigues(want[:3]))
+                worst_r, worst_t = max(worst_r, float(dr)), max(worst_t, float(np.abs(poses[f][3:] - want[3:]).max()))
+        cpu_wall = time.perf_counter() - t0
+        cpu = {"value": n_cpu / cpu_wall, "unit": "poses/s", "cores": 1, "kind": "port",
+               "sample": f"first {n_cpu} frames of the sequence: reference APE state machine (cv2.solvePnP) + cv2.calcOpticalFlowPyrLK + oracle/dpr_oracle.py",
+               "max_rot_diff_vs_gpu_rad": worst_r, "max_trans_diff_vs_gpu_m": worst_t}
+    dt = np.array([np.linalg.norm(p[3:] - traj[f][3:]) for f, p in enumerate(poses) if p is not None])
+    line = {"metric": "refined poses/sec (one 640x480 stream through the drop-in PoseDetector)", "value": n / wall, "unit": "poses/s",
+            "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": 1e3 * wall, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 1: 300-frame 640x480 synthetic sequence, APE + LK fallback + dense refinement per frame, "
+                                   "one frame at a time through PoseDetector (host numpy in, attributes out)",
+                       "frames": n},
+            "ms_per_frame": {"median": float(np.median(t_frames) * 1e3), "p95": float(np.percentile(t_frames, 95) * 1e3)},
+            "poses_accepted": int(sum(p is not None for p in poses)), "median_trans_err_vs_truth_m": float(np.median(dt))}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
 def ensure_library():
     """libagt.so normally travels with the tree; if it is absent build it once (local rank 0) and let the others wait."""
     from accurate_aprilgroup_tracking_b200 import _build, _lib
@@ -630,7 +723,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="dpr", choices=["dpr", "lk", "multihyp", "streams"])
+    ap.add_argument("--workload", default="dpr", choices=["dpr", "lk", "multihyp", "streams", "config1"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     args = ap.parse_args()
@@ -643,6 +736,8 @@ def main():
         run_multihyp(args)
     elif args.workload == "streams":
         run_streams(args)
+    elif args.workload == "config1":
+        run_config1(args)
     else:
         run_gpu(args)
 
