@@ -118,3 +118,40 @@ def test_nan_inputs_do_not_poison_the_batch(ctx1080):
     a = ctx1080.pnp(obj, img_bad, v)[0].cpu().numpy()
     b = ctx1080.pnp(obj, img, v2)[0].cpu().numpy()
     assert np.array_equal(a, b)
+
+
+def test_fused_refine_and_undistort_edge_cases(ctxvga, lib_built):
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    torch = ctxvga.torch
+    cam = synth.CAMERA_VGA
+    # empty batch, and a pose whose ROI is empty (object far outside the frame): nothing to build, status NONE
+    pyr0 = ctxvga.alloc_pyramid(0, cam.width, cam.height, 4)
+    assert ctxvga.refine(pyr0, np.zeros((0, 1, 6)), 1, fused=True)["pose"].shape == (0, 1, 6)
+    pyr = ctxvga.alloc_pyramid(2, cam.width, cam.height, 4)
+    pyr.levels[0].fill_(128)
+    for l in (1, 2, 3):
+        pyr.levels[l].fill_(255)
+    init = np.array([[[0.1, 0.2, 0.3, 5.0, 0.0, 0.4]], [[float("nan")] * 6]])
+    res = ctxvga.refine(pyr, init, 1, fused=True)
+    assert res["status"].reshape(-1).tolist() == [0, 0] and res["n_valid"].reshape(-1).tolist() == [0, 0]
+    assert all(bool((pyr.levels[l] == 255).all()) for l in (1, 2, 3))
+    # masked frames are skipped by the fused launch too
+    mask = torch.tensor([0, 1], dtype=torch.uint8, device=pyr.levels[0].device)
+    out = ctxvga.refine(pyr, init, 1, mask=mask, fused=True)
+    assert int(out["evals"][0, 0]) == 0
+    # undistortion: must be configured first, for the frame size it is used with
+    ctx = AgtContext(0, cam.mtx, np.array([-0.2, 0.05, 0.0, 0.0, 0.0]))
+    try:
+        g = ctx.alloc_pyramid(1, cam.width, cam.height, 1)
+        with pytest.raises(RuntimeError):
+            ctx.ingest_undistort(g, np.zeros((1, cam.height, cam.width, 3), np.uint8))
+        with pytest.raises(ValueError):
+            ctx.set_undistort(np.eye(3), cam.width, cam.height, (0, 0, cam.width + 1, cam.height))       # crop outside the frame
+        with pytest.raises(ValueError):
+            ctx.set_undistort(np.array([[600.0, 0, 320], [0.1, 600, 240], [0, 0, 1]]), cam.width, cam.height, (0, 0, 8, 8))
+        ctx.set_undistort(cam.mtx, cam.width, cam.height, (0, 0, cam.width, cam.height))
+        with pytest.raises(ValueError):
+            ctx.ingest_undistort(g, np.zeros((1, cam.height // 2, cam.width, 3), np.uint8))              # another frame size
+        ctx.ingest_undistort(g, np.zeros((0, cam.height, cam.width, 3), np.uint8))                        # empty batch
+    finally:
+        ctx.close()
