@@ -24,6 +24,7 @@
 #include <cstddef>
 
 #include "agt_dpr_plan.cuh"
+#include "agt_pyr_stream.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -403,7 +404,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int4 ja = __ldg(jw), jb = __ldg(jw + 1), jc = __ldg(jw + 2);
   const int lvl = ja.x;
   const bool build_level = fuse_pyramid != 0 && lvl > 0;
-  if (!build_level) {
+  auto stage_tile = [&]() {
     // stage the ROI tile with 16-byte asynchronous copies (LDGSTS): every chunk of a thread is in flight at once and
     // thread 0 sets up the LM state underneath them
     const int tx0 = jb.y, ty0 = jb.z, tw = jb.w, th = jc.x;
@@ -424,14 +425,15 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       } else {
         uint32_t w4[4] = {0, 0, 0, 0};
         for (int b = 0; b < 16; ++b)
-          if (tx0 + 16 * c + b < lw) w4[b >> 2] |= (uint32_t)__ldg(g + b) << (8 * (b & 3));
+          if (tx0 + 16 * c + b < lw) w4[b >> 2] |= (uint32_t)__ldcg(g + b) << (8 * (b & 3));
         *reinterpret_cast<uint4*>(s_tile + r * TILE_PITCH + 16 * c) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
       r += dr; c += dc;
       if (c >= chunks) { c -= chunks; ++r; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  };
+  if (!build_level) stage_tile();
 
   if (tid == 0) {
     S.cc = 0.0; S.lam = LAMBDA0; S.nc = 0; S.evals = 0; S.status = AGT_DPR_MAX_EVALS;
@@ -475,9 +477,11 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   __syncthreads();
   if (build_level) {
     // K1 fused: only level 0 of the pyramid holds the frame.  Build the ROI of levels 1..l from it (intermediate levels
-    // through the pyramid's own global buffers, which stay in L2), the last one also into the tile.
-    uint8_t* s_in = s_tile + TILE_BYTES;
-    uint16_t* s_h = reinterpret_cast<uint16_t*>(s_in + 2 * PB_IN_ROWS * PB_IN_PITCH);
+    // through the pyramid's own global buffers, which stay in L2), then stage the tile from the level just written.
+    // Level 1 of an aligned frame (the usual case) is built by K1's own streaming warp routine, the eight warps
+    // sharing the rows of the ROI; anything else by the generic band routine.
+    uint8_t* s_scratch = s_tile + TILE_BYTES;
+    bool tile_written = false;
     for (int L = 1; L <= lvl; ++L) {
       // rectangle needed at level L: the ROI at level l grown by the 5x5 support of every pyrDown above it
       int x0 = S.rx0, y0 = S.ry0, x1 = S.rx1, y1 = S.ry1;
@@ -485,10 +489,37 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
         x0 = max(0, 2 * x0 - 2) & ~15; y0 = max(0, 2 * y0 - 2);
         x1 = min(pyr.width[m - 1], 2 * ((x1 + 3) & ~3) + 2); y1 = min(pyr.height[m - 1], 2 * y1 + 2);
       }
-      if (x1 > x0 && y1 > y0)
-        cta_pyr_down_region(pyr.data[L - 1] + frame * pyr.frame_stride[L - 1], pyr.width[L - 1], pyr.height[L - 1], pyr.pitch[L - 1],
-                            pyr.data[L] + frame * pyr.frame_stride[L], pyr.pitch[L], L == lvl ? s_tile : nullptr, S.tx0, S.ty0,
-                            S.tw, S.th, x0, y0, x1, y1, s_in, s_h);
+      if (x1 > x0 && y1 > y0) {
+        const uint8_t* simg = pyr.data[L - 1] + frame * pyr.frame_stride[L - 1];
+        uint8_t* dimg = pyr.data[L] + frame * pyr.frame_stride[L];
+        const int sw = pyr.width[L - 1], sh = pyr.height[L - 1], dw = pyr.width[L];
+        const int64_t sp = pyr.pitch[L - 1], dp = pyr.pitch[L];
+        // (only level 0 is read through the streaming routine: its 4-byte halo requests may be served by L1, which is
+        // safe for data this launch never writes)
+        const bool stream = L == 1 && (sw & 15) == 0 && sw >= 16 && sh >= 4 && (dw & 7) == 0 && (sp & 15) == 0 && (dp & 7) == 0 &&
+                            (reinterpret_cast<uintptr_t>(simg) & 15) == 0 && (reinterpret_cast<uintptr_t>(dimg) & 7) == 0;
+        if (stream) {
+          constexpr int kQ = 3;                                        // rows in flight per warp: 8 warps x 7 x 544 B of ring
+          const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_scratch) + wid * ((kQ + 4) * 544);
+          const int xo1 = min(dw, (x1 + 7) & ~7);
+          const int per = (y1 - y0 + DPR_WARPS - 1) / DPR_WARPS;
+          const int oy0 = y0 + wid * per, oy1 = min(oy0 + per, y1);
+          if (oy0 < oy1)
+            for (int xb = x0; xb < xo1; xb += 256)
+              agt_pyr_down_strip<kQ, 1>(simg, sw, sh, sp, dimg, dp, xb + 8 * lane, xo1, oy0, oy1, lane, ring);
+          asm volatile("cp.async.wait_all;" ::: "memory");
+        } else {
+          uint8_t* s_in = s_scratch;
+          uint16_t* s_h = reinterpret_cast<uint16_t*>(s_in + 2 * PB_IN_ROWS * PB_IN_PITCH);
+          cta_pyr_down_region(simg, sw, sh, sp, dimg, dp, L == lvl ? s_tile : nullptr, S.tx0, S.ty0, S.tw, S.th, x0, y0, x1, y1, s_in, s_h);
+          tile_written = tile_written || L == lvl;
+        }
+      }
+      __syncthreads();
+    }
+    if (!tile_written) {                                              // (uniform across the CTA)
+      stage_tile();
+      asm volatile("cp.async.wait_all;" ::: "memory");
       __syncthreads();
     }
   }
