@@ -38,9 +38,9 @@ BYTES_PER_POSE_FIXED = 156
 LK_BYTES_PER_CORNER = 5008
 PYR_BYTES_PER_1080P = 2754000
 # dram__bytes_read.sum + dram__bytes_write.sum of one dpr_kernel launch, per pose, from the ncu --set full capture
-# summarised in profiles/r01_ncu_dpr_kernel.txt (132.67 MB read + 12.67 MB written for 1024 poses of this workload with K1
+# summarised in profiles/r01_ncu_dpr_kernel.txt (166.64 MB read + 13.44 MB written for 1024 poses of this workload with K1
 # fused into the kernel: the level-0 ROI is read from HBM, the level-1..3 ROIs it builds are written back)
-DPR_NCU_DRAM_BYTES_PER_POSE = 145.34e6 / 1024
+DPR_NCU_DRAM_BYTES_PER_POSE = 180.08e6 / 1024
 
 
 def measured_peaks():
