@@ -122,11 +122,32 @@ def make_dpr():
                         source=np.array(["oracle/dpr_oracle.py (executable spec; no reference code exists)"]))
 
 
+def make_undistort():
+    """The reference's frame ingest on a small BGR frame: undistort_frame (detect_pose.py:147-183) + BGR2GRAY (:602),
+    computed by the calls the reference makes (cv2), for two lens models."""
+    import cv2
+    w, h, f = 160, 120, 150.0
+    rng = np.random.default_rng(777)
+    mtx = np.array([[f, 0, w / 2 + 1.7], [0, f * 1.01, h / 2 - 0.9], [0, 0, 1]])
+    frame = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 1.2)
+    dists, news, rois, grays = [], [], [], []
+    for dist in ([-0.28, 0.11, 0.0007, -0.0004, -0.02], [0.05, -0.1, 0.001, 0.002, 0.03]):
+        dist = np.array(dist, np.float64).reshape(1, 5)
+        new_mtx, roi = cv2.getOptimalNewCameraMatrix(mtx, dist, (w, h), 1, (w, h))
+        x, y, rw, rh = roi
+        gray = cv2.cvtColor(cv2.undistort(frame, mtx, dist, None, new_mtx)[y:y + rh, x:x + rw], cv2.COLOR_BGR2GRAY)
+        dists.append(dist); news.append(new_mtx); rois.append(np.array(roi)); grays.append(gray.ravel())
+    np.savez_compressed(GOLDEN / "undistort_case.npz", frame=frame, mtx=mtx, dist=np.array(dists), new_mtx=np.array(news),
+                        roi=np.array(rois), gray0=grays[0], gray1=grays[1], versions=VERSIONS,
+                        source=np.array(["cv2.getOptimalNewCameraMatrix + cv2.undistort + cv2.cvtColor, the calls of detect_pose.py:167-177, 602"]))
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     make_ape()
     make_lk()
     make_dpr()
+    make_undistort()
     for p in sorted(GOLDEN.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

@@ -244,3 +244,12 @@ def test_remap_table_sums_to_one():
     assert tab.shape == (1024, 4) and (tab.sum(axis=1) == 32768).all() and tab.min() >= 0
     assert tab[0].tolist() == [32767, 0, 0, 1]          # saturation of 1.0 * 2^15 and the remainder fix-up
 
+
+def test_undistort_oracle_matches_golden():
+    from oracle import make_golden, undistort_oracle as uo
+    g = np.load(make_golden.GOLDEN / "undistort_case.npz")
+    for k in range(2):
+        x, y, w, h = g["roi"][k]
+        got = uo.undistort_frame_gray(g["frame"], g["mtx"], g["dist"][k], g["new_mtx"][k], g["roi"][k])
+        assert np.array_equal(got.ravel(), g[f"gray{k}"]) and got.shape == (h, w)
+

@@ -260,3 +260,13 @@ def test_full_pipeline_matches_pipeline_oracle_config1(detector_factory, ctxvga)
             want = np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
             util.assert_pose_close(got, want, f"frame {f}")
     assert tracked >= 3
+
+
+def test_undistort_ingest_golden(host):
+    # the reference's frame ingest (cv2 calls of detect_pose.py:167-177, 602) as committed golden vectors
+    g = np.load(GOLDEN / "undistort_case.npz")
+    for k in range(2):
+        x, y, w, h = (int(v) for v in g["roi"][k])
+        got = host.undistort_gray(g["frame"], g["mtx"], g["dist"][k], g["new_mtx"][k], (x, y, w, h))
+        assert got.shape == (h, w) and np.array_equal(got.ravel(), g[f"gray{k}"])
+
