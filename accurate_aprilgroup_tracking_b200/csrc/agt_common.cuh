@@ -180,6 +180,56 @@ __host__ __device__ inline bool agt_chol6_solve(double A[36], double b[6]) {
   return true;
 }
 
+// 1/sqrt(d) in float64: MUFU.RSQ64H seed (2^-22) + two Newton steps, each three dependent operations deep
+__device__ __forceinline__ double agt_rsqrt_newton(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double e = fma(-(d * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
+// index of H(p, q), p <= q, in the packed upper triangle stored by rows
+__host__ __device__ constexpr int agt_hk(int p, int q) { return p * 6 - p * (p - 1) / 2 + (q - p); }
+
+// Cholesky solve of the SPD system A x = b, A packed as above, everything in registers (all indices are compile-time
+// constants).  Right-looking: after the column scale the trailing updates are independent, so the critical path per
+// column is one reciprocal square root, one multiplication and one FMA.  L(i, j) overwrites A(j, i).
+__device__ __forceinline__ bool agt_chol6_packed(double (&A)[21], double (&b)[6]) {
+  double inv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const double d = A[agt_hk(j, j)];
+    if (!(d > 1e-30 && d < 1e30)) return false;          // not positive definite for our purposes
+    const double y = agt_rsqrt_newton(d);
+    inv[j] = y;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) A[agt_hk(j, i)] *= y;
+#pragma unroll
+    for (int k = j + 1; k < 6; ++k)
+#pragma unroll
+      for (int i = k; i < 6; ++i) A[agt_hk(k, i)] = fma(-A[agt_hk(j, i)], A[agt_hk(j, k)], A[agt_hk(k, i)]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v = fma(-A[agt_hk(k, i)], b[k], v);
+    b[i] = v * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v = fma(-A[agt_hk(i, k)], b[k], v);
+    b[i] = v * inv[i];
+  }
+  return true;
+}
+
 __device__ __forceinline__ double agt_warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -113,56 +113,6 @@ __device__ __forceinline__ int dp4c(uint32_t px, int coef, int acc) {
 }
 
 // ---- serial LM phase helpers (one thread per CTA runs them while 255 wait: keep the dependency chains short) ----
-// 1/sqrt(d) in float64: MUFU.RSQ64H seed (2^-22) + two Newton steps, each three dependent operations deep
-__device__ __forceinline__ double rsqrt_newton(double d) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double e = fma(-(d * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-  }
-  return y;
-}
-
-// index of H(p, q), p <= q, in the packed upper triangle stored by rows
-__host__ __device__ constexpr int hk(int p, int q) { return p * 6 - p * (p - 1) / 2 + (q - p); }
-
-// Cholesky solve of the SPD system A x = b, A packed as above, everything in registers (all indices are compile-time
-// constants).  Right-looking: after the column scale the trailing updates are independent, so the critical path per
-// column is one reciprocal square root, one multiplication and one FMA.  L(i, j) overwrites A(j, i).
-__device__ __forceinline__ bool chol6_packed(double (&A)[21], double (&b)[6]) {
-  double inv[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const double d = A[hk(j, j)];
-    if (!(d > 1e-30 && d < 1e30)) return false;          // not positive definite for our purposes
-    const double y = rsqrt_newton(d);
-    inv[j] = y;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) A[hk(j, i)] *= y;
-#pragma unroll
-    for (int k = j + 1; k < 6; ++k)
-#pragma unroll
-      for (int i = k; i < 6; ++i) A[hk(k, i)] = fma(-A[hk(j, i)], A[hk(j, k)], A[hk(k, i)]);
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    double v = b[i];
-#pragma unroll
-    for (int k = 0; k < i; ++k) v = fma(-A[hk(k, i)], b[k], v);
-    b[i] = v * inv[i];
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; --i) {
-    double v = b[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; ++k) v = fma(-A[hk(i, k)], b[k], v);
-    b[i] = v * inv[i];
-  }
-  return true;
-}
-
 // exp([w]x) for an LM step: Taylor series of sin(t)/t and (1-cos t)/t^2 in t^2 for |w| < 0.5 (truncation < 1e-16),
 // libm sincos otherwise
 __device__ __forceinline__ void rodrigues_step(const double w[3], double R[9]) {
@@ -759,8 +709,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 #pragma unroll
           for (int k = 0; k < 21; ++k) A[k] = S.Hb[k];
 #pragma unroll
-          for (int q = 0; q < 6; ++q) { A[hk(q, q)] = fma(lam, A[hk(q, q)], A[hk(q, q)]); d[q] = -S.Hb[21 + q]; }
-          if (chol6_packed(A, d)) {
+          for (int q = 0; q < 6; ++q) { A[agt_hk(q, q)] = fma(lam, A[agt_hk(q, q)], A[agt_hk(q, q)]); d[q] = -S.Hb[21 + q]; }
+          if (agt_chol6_packed(A, d)) {
 #pragma unroll
             for (int q = 0; q < 6; ++q) S.dstep[q] = d[q];
             double E[9], Rt[9], tt[3];

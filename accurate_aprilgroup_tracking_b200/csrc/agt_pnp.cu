@@ -117,8 +117,27 @@ __device__ inline void evaluate(const agt_camera& cam, const double p[6], const 
     for (int a = 0; a < 6; ++a) acc[21 + a] += J[0][a] * e[0] + J[1][a] * e[1];
     acc[27] += e[0] * e[0] + e[1] * e[1];
   }
+  // One transposing butterfly (31 exchanges instead of 28 x 5) leaves the total of sum k on lane k, then every lane
+  // fetches the 28 totals: it solves the 6x6 system itself.
+  {
+    const int lane = threadIdx.x & 31;
+    double v[32];
 #pragma unroll
-  for (int k = 0; k < 28; ++k) acc[k] = agt_warp_sum(acc[k]);
+    for (int k = 0; k < 28; ++k) v[k] = acc[k];
+#pragma unroll
+    for (int k = 28; k < 32; ++k) v[k] = 0.0;
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+      const bool up = (lane & h) != 0;
+#pragma unroll
+      for (int k = 0; k < h; ++k) {
+        const double keep = up ? v[k + h] : v[k], send = up ? v[k] : v[k + h];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = __shfl_sync(0xffffffffu, v[0], k);
+  }
 #pragma unroll
   for (int k = 0; k < 21; ++k) out.H[k] = acc[k];
 #pragma unroll
@@ -333,15 +352,12 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
     evaluate(cam, p, X, U, have, cur, front);
     double lam = 1e-3;
     for (iters = 0; iters < PNP_MAX_ITERS; ++iters) {
-      double A[36], b[6];
-      int k = 0;
+      double A[21], b[6];                          // packed upper triangle, solved in registers
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+      for (int k = 0; k < 21; ++k) A[k] = cur.H[k];
 #pragma unroll
-        for (int c = a; c < 6; ++c) { A[a * 6 + c] = cur.H[k]; A[c * 6 + a] = cur.H[k]; ++k; }
-#pragma unroll
-      for (int a = 0; a < 6; ++a) { A[a * 6 + a] *= (1.0 + lam); b[a] = -cur.g[a]; }
-      if (!agt_chol6_solve(A, b)) {
+      for (int a = 0; a < 6; ++a) { A[agt_hk(a, a)] *= (1.0 + lam); b[a] = -cur.g[a]; }
+      if (!agt_chol6_packed(A, b)) {
         lam *= 10.0;
         if (lam > 1e12) { ok = false; break; }
         continue;
