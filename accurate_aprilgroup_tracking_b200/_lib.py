@@ -67,9 +67,11 @@ PROTOTYPES = {
     "agt_project": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_prepare": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_update": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
+    "agt_accept_gate": (_I, [_VP, _VP, _VP, _VP, _VP, _I]),
+    "agt_ape_commit": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _I]),
     "agt_refine": (_I, [_VP, _PYR, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I]),
     "agt_refine_fused": (_I, [_VP, _PYR, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I]),
-    "agt_lk_merge": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
+    "agt_lk_merge": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
     "agt_select_best": (_I, [_VP, _VP, _VP, _VP, _I, _VP, _VP, _I]),
     "agt_render": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _I, _D, _D, _I, _I]),
     "agt_solve_pnp_host": (_I, [_VP, _VP, _VP, _I, _I, _VP, C.POINTER(_I), C.POINTER(C.c_float)]),

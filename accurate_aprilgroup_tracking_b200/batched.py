@@ -9,8 +9,9 @@ the reference's per-stream state (detect_pose.py:74-78) kept in device memory.  
                            were tracked from the previous frame (the inlier set is LK status == 1)
   K0  agt_ape_prepare      extrinsic guess from the predictor state        (detect_pose.py:508)
   K3  agt_pnp              batched solvePnP + mean reprojection error      (detect_pose.py:509-538)
-  K4  agt_refine           dense refinement of the poses that pass the 2 px gate (masked)
-  K0  agt_ape_update       accept / reset rules, velocity FIFOs, predictor (detect_pose.py:539-574)
+  K4  agt_accept_gate + agt_refine   dense refinement of the poses that pass the 2 px gate (masked)
+  K0  agt_ape_commit       accept / reset rules, velocity FIFOs, predictor (detect_pose.py:539-574) with the refined
+                           pose, and the hand-over of the accepted frame's corners to the next LK step
 
 Frames within a stream are sequential (the predictor needs poses t-1, t-2; LK needs frame t-1), so the
 batch dimension is the number of streams; streams are pinned to GPUs by ``sharding.stream_owner``.
@@ -74,22 +75,22 @@ class BatchedPoseDetector:
             # K2: only frames with < 2 detected tags are tracked; on the very first frame prev_valid is all zero,
             # so nothing can be re-admitted from the (not yet written) previous slot
             nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntg)
-            before = ntg.clone()
-            ctx.lk_merge(nxt, st, self.prev_valid, img, val, ntg)
-            tracked_tags = ntg - before
+            tracked_tags = t.empty(self.n, dtype=t.int32, device=ctx.tdev)
+            ctx.lk_merge(nxt, st, self.prev_valid, img, val, ntg, tracked_tags)
         guess, use = ctx.ape_prepare(self.state, self.enhance_ape)               # K0
         pose, ok, err, iters = ctx.pnp(self.obj, img, val, guess, use)            # K3
         refined = None
         if self.use_dense_refine:
-            gate = ((ok != 0) & (err < 2.0) & (ntg >= 2)).to(t.uint8)             # only poses the reference accepts
-            refined = ctx.refine(cur, pose.reshape(self.n, 1, 6), 1, mask=gate)   # K4
-            good = (refined["status"].reshape(self.n) != 0).unsqueeze(1)
-            pose = t.where(good, refined["pose"].reshape(self.n, 6), pose)
-        accepted, flag = ctx.ape_update(self.state, ntg, pose, ok, err, self.enhance_ape)   # K0
-        # corners of the accepted frame feed the next LK step (PoseDetector._prev_corners)
-        self.prev_pts.copy_(img)
-        self.prev_valid.copy_(val * accepted.unsqueeze(1))
-        return {"pose": self.state[:, 1:7].clone(), "accepted": accepted, "error_flag": flag, "reproj_err": err,
+            gate = ctx.accept_gate(ok, err, ntg)                                  # only poses the reference accepts
+            out = {k: t.empty((self.n, 1) + ((6,) if k == "pose" else ()), dtype=d, device=ctx.tdev)
+                   for k, d in (("pose", t.float64), ("cost", t.float32), ("n_valid", t.int32), ("evals", t.int32),
+                                ("left_roi", t.uint8))}
+            out["status"] = t.zeros((self.n, 1), dtype=t.uint8, device=ctx.tdev)  # masked frames keep status 0: pose unused
+            refined = ctx.refine(cur, pose.reshape(self.n, 1, 6), 1, mask=gate, out=out)   # K4
+        # K0 with the refined pose where there is one; the corners of the accepted frame feed the next LK step
+        accepted, flag, pose_out = ctx.ape_commit(self.state, ntg, pose, ok, err, refined, img, val, self.prev_pts,
+                                                  self.prev_valid, self.enhance_ape)
+        return {"pose": pose_out, "accepted": accepted, "error_flag": flag, "reproj_err": err,
                 "n_tags": ntg, "tracked_tags": tracked_tags, "refine": refined}
 
     def step(self, img_pts, valid, n_tags, frames=None):

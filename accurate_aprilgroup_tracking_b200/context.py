@@ -200,12 +200,13 @@ class AgtContext:
                                                  self._p(st), self._p(err), self._p(n_tags), b, p))
         return out, st, err
 
-    def lk_merge(self, tracked, status, prev_valid, img_pts, valid, n_tags):
-        """In place: re-admit fully tracked tags into img_pts/valid for frames with < 2 detected tags."""
+    def lk_merge(self, tracked, status, prev_valid, img_pts, valid, n_tags, tracked_tags=None):
+        """In place: re-admit fully tracked tags into img_pts/valid for frames with < 2 detected tags;
+        tracked_tags [B] i32 (optional) receives the number of tags re-admitted per frame."""
         b, p = int(img_pts.shape[0]), int(img_pts.shape[1])
         self._use_current_stream()
         self._check(self.lib.agt_lk_merge(self.h, self._p(tracked), self._p(status), self._p(prev_valid), self._p(img_pts),
-                                          self._p(valid), self._p(n_tags), b, p))
+                                          self._p(valid), self._p(n_tags), self._p(tracked_tags), b, p))
 
     # -- K3 ---------------------------------------------------------------------------
     def pnp(self, obj_pts, img_pts, valid=None, guess=None, use_guess=None):
@@ -263,6 +264,34 @@ class AgtContext:
         self._check(self.lib.agt_ape_update(self.h, self._p(state), self._p(nt), self._p(pose), self._p(ok), self._p(err),
                                             self._p(acc), self._p(flag), b, int(enhance_ape)))
         return acc, flag
+
+    def accept_gate(self, ok, err, n_tags):
+        """[B] u8: the reference's acceptance test of a solved frame (>= 2 tags, solvePnP ok, mean error < 2 px)."""
+        t = self.torch
+        b = int(ok.shape[0])
+        gate = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_accept_gate(self.h, self._p(ok), self._p(err), self._p(n_tags), self._p(gate), b))
+        return gate
+
+    def ape_commit(self, state, n_tags, pose, ok, err, refined=None, img_pts=None, valid=None, prev_pts=None, prev_valid=None,
+                   enhance_ape: bool = True):
+        """ape_update with the refined pose where the refinement produced one, plus the hand-over of the frame's corners
+        to the next LK step -> (accepted [B] u8, error_flag [B] u8, pose [B,6] f64 = each stream's prev_transform)."""
+        t = self.torch
+        b = int(state.shape[0])
+        acc = t.empty(b, dtype=t.uint8, device=self.tdev)
+        flag = t.empty(b, dtype=t.uint8, device=self.tdev)
+        out = t.empty((b, 6), dtype=t.float64, device=self.tdev)
+        rp = refined["pose"] if refined is not None else None
+        rs = refined["status"] if refined is not None else None
+        n_pts = int(img_pts.shape[1]) if img_pts is not None else 0
+        self._use_current_stream()
+        self._check(self.lib.agt_ape_commit(self.h, self._p(state), self._p(n_tags), self._p(pose), self._p(ok), self._p(err),
+                                            self._p(rp), self._p(rs), self._p(img_pts), self._p(valid), self._p(prev_pts),
+                                            self._p(prev_valid), n_pts, self._p(acc), self._p(flag), self._p(out), b,
+                                            int(enhance_ape)))
+        return acc, flag, out
 
     # -- K4 ---------------------------------------------------------------------------
     def refine(self, pyr: Pyramid, init, n_hyp: int = 1, batch: Optional[int] = None, mask=None, out=None, fused: bool = False):

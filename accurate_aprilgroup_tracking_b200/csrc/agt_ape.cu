@@ -42,21 +42,16 @@ __global__ void ape_prepare_kernel(const double* __restrict__ state, double* __r
   for (int k = 0; k < 6; ++k) guess[(int64_t)i * 6 + k] = use ? s[S_GUESS + k] : 0.0;
 }
 
-__global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __restrict__ n_tags,
-                                  const double* __restrict__ pose, const uint8_t* __restrict__ ok,
-                                  const float* __restrict__ err, uint8_t* __restrict__ accepted,
-                                  uint8_t* __restrict__ error_flag, int batch, int enhance) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= batch) return;
-  double* s = state + (int64_t)i * AGT_STREAM_STATE_DOUBLES;
-  if (accepted) accepted[i] = 0;
-  if (error_flag) error_flag[i] = 0;
+// detect_pose.py:490-574 for one stream: s = its state record, p_in = the pose solvePnP (or the dense refinement)
+// returned.  Returns accepted; error is set where the reference would raise ValueError.
+__device__ inline bool ape_update_stream(double* s, int n_tags, const double* p_in, bool ok, float err, int enhance, bool& error) {
+  error = false;
   double held[6];
   for (int k = 0; k < 6; ++k) held[k] = s[S_PREV + k];      // deepcopy(prev_transform), detect_pose.py:490
-  if (n_tags[i] < 2) { s[S_HAS_GUESS] = 0.0; return; }      // detect_pose.py:494-496,573-574
+  if (n_tags < 2) { s[S_HAS_GUESS] = 0.0; return false; }   // detect_pose.py:494-496,573-574
   const bool fresh = !(enhance && s[S_HAS_GUESS] != 0.0);
   double p[6];
-  for (int k = 0; k < 6; ++k) p[k] = pose[(int64_t)i * 6 + k];
+  for (int k = 0; k < 6; ++k) p[k] = p_in[k];
   if (!fresh) {
     // solvePnP wrote its result into the guess arrays (dtype preserved)
     if (s[S_T32] != 0.0)
@@ -65,9 +60,8 @@ __global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __r
     if (s[S_ALIAS] != 0.0)
       for (int k = 0; k < 6; ++k) s[S_PREV + k] = p[k];
   }
-  if (!ok[i]) return;                                        // detect_pose.py:533
-  if (!(err[i] < 2.0f)) { s[S_HAS_GUESS] = 0.0; return; }    // detect_pose.py:539,570-572
-  if (accepted) accepted[i] = 1;
+  if (!ok) return false;                                     // detect_pose.py:533
+  if (!(err < 2.0f)) { s[S_HAS_GUESS] = 0.0; return false; } // detect_pose.py:539,570-572
   if (fresh) {
     for (int k = 0; k < 6; ++k) s[S_GUESS + k] = p[k];       // detect_pose.py:551
     s[S_HAS_GUESS] = 1.0; s[S_ALIAS] = 1.0; s[S_T32] = 0.0;
@@ -83,8 +77,8 @@ __global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __r
     for (int k = 0; k < 9; ++k) zero = zero || rv[k] == 0.0;
     for (int k = 0; k < 3; ++k) zero = zero || tv[k] == 0.0;
     if (zero) {                                              // detect_pose.py:236-237 raises ValueError
-      if (error_flag) error_flag[i] = 1;
-      return;
+      error = true;
+      return true;                                           // (the pose passed the gate; the state update is abandoned)
     }
     int nv = (int)s[S_NVEL];
     if (nv >= 2) {                                           // FIFO depth 2: drop the oldest
@@ -135,6 +129,59 @@ __global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __r
   }
   for (int k = 0; k < 6; ++k) s[S_PREV + k] = p[k];          // detect_pose.py:569
   s[S_HAS_PREV] = 1.0;
+  return true;
+}
+
+__global__ void ape_update_kernel(double* __restrict__ state, const int32_t* __restrict__ n_tags,
+                                  const double* __restrict__ pose, const uint8_t* __restrict__ ok,
+                                  const float* __restrict__ err, uint8_t* __restrict__ accepted,
+                                  uint8_t* __restrict__ error_flag, int batch, int enhance) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  bool error;
+  const bool acc = ape_update_stream(state + (int64_t)i * AGT_STREAM_STATE_DOUBLES, n_tags[i], pose + (int64_t)i * 6, ok[i] != 0,
+                                     err[i], enhance, error);
+  if (accepted) accepted[i] = acc ? 1 : 0;
+  if (error_flag) error_flag[i] = error ? 1 : 0;
+}
+
+// The reference's acceptance test of a solved frame (detect_pose.py:494, 533, 539): at least two tags, solvePnP
+// succeeded, mean reprojection error below 2 px.  Used to mask the dense refinement.
+__global__ void accept_gate_kernel(const uint8_t* __restrict__ ok, const float* __restrict__ err, const int32_t* __restrict__ n_tags,
+                                   uint8_t* __restrict__ gate, int batch) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) gate[i] = ok[i] != 0 && err[i] < 2.0f && n_tags[i] >= 2 ? 1 : 0;
+}
+
+// One warp per stream: lane 0 applies the state update with the refined pose where the refinement produced one,
+// then the warp hands the frame's corners over to the next LK step (PoseDetector._prev_corners keeps the corners of
+// accepted frames only) and publishes the stream's pose.
+__global__ void ape_commit_kernel(double* __restrict__ state, const int32_t* __restrict__ n_tags, const double* __restrict__ pose,
+                                  const uint8_t* __restrict__ ok, const float* __restrict__ err,
+                                  const double* __restrict__ refined_pose, const uint8_t* __restrict__ refined_status,
+                                  const float* __restrict__ img, const uint8_t* __restrict__ valid, float* __restrict__ prev_pts,
+                                  uint8_t* __restrict__ prev_valid, int n_pts, uint8_t* __restrict__ accepted,
+                                  uint8_t* __restrict__ error_flag, double* __restrict__ pose_out, int batch, int enhance) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= batch) return;
+  double* s = state + (int64_t)i * AGT_STREAM_STATE_DOUBLES;
+  int acc = 0;
+  if (lane == 0) {
+    const bool use_refined = refined_pose != nullptr && refined_status != nullptr && refined_status[i] != 0;
+    const double* p = use_refined ? refined_pose + (int64_t)i * 6 : pose + (int64_t)i * 6;
+    bool error;
+    const bool a = ape_update_stream(s, n_tags[i], p, ok[i] != 0, err[i], enhance, error);
+    acc = a ? 1 : 0;
+    if (accepted) accepted[i] = (uint8_t)acc;
+    if (error_flag) error_flag[i] = error ? 1 : 0;
+  }
+  acc = __shfl_sync(0xffffffffu, acc, 0);
+  __syncwarp();
+  if (pose_out && lane < 6) pose_out[(int64_t)i * 6 + lane] = s[S_PREV + lane];
+  if (prev_pts && prev_valid && img && valid) {
+    for (int k = lane; k < 2 * n_pts; k += 32) prev_pts[(int64_t)i * 2 * n_pts + k] = img[(int64_t)i * 2 * n_pts + k];
+    for (int k = lane; k < n_pts; k += 32) prev_valid[(int64_t)i * n_pts + k] = acc ? valid[(int64_t)i * n_pts + k] : 0;
+  }
 }
 
 }  // namespace
@@ -163,3 +210,28 @@ extern "C" int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }
+
+extern "C" int agt_accept_gate(agt_ctx* ctx, const uint8_t* d_ok, const float* d_err, const int32_t* d_n_tags, uint8_t* d_gate, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
+  if (!d_ok || !d_err || !d_n_tags || !d_gate || batch < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_accept_gate: bad arguments");
+  accept_gate_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d_ok, d_err, d_n_tags, d_gate, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_ape_commit(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const double* d_pose, const uint8_t* d_ok,
+                              const float* d_err, const double* d_refined_pose, const uint8_t* d_refined_status,
+                              const float* d_img_pts, const uint8_t* d_valid, float* d_prev_pts, uint8_t* d_prev_valid, int n_pts,
+                              uint8_t* d_accepted, uint8_t* d_error_flag, double* d_pose_out, int batch, int enhance_ape) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
+  if (!d_state || !d_n_tags || !d_pose || !d_ok || !d_err || batch < 0 || n_pts < 0 || n_pts > AGT_MAX_POINTS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_ape_commit: bad arguments");
+  ape_commit_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(d_state, d_n_tags, d_pose, d_ok, d_err, d_refined_pose, d_refined_status,
+                                                             d_img_pts, d_valid, d_prev_pts, d_prev_valid, n_pts, d_accepted,
+                                                             d_error_flag, d_pose_out, batch, enhance_ape);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+

@@ -325,13 +325,14 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
 // Stage-2 integration: one thread per (frame, tag).
 __global__ void lk_merge_kernel(const float* __restrict__ tracked, const uint8_t* __restrict__ status,
                                 const uint8_t* __restrict__ prev_valid, float* __restrict__ img, uint8_t* __restrict__ valid,
-                                int32_t* __restrict__ n_tags, int batch, int tags) {
+                                int32_t* __restrict__ n_tags, int32_t* __restrict__ tracked_tags, int batch, int tags) {
   int f = blockIdx.x;
   if (f >= batch) return;
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
-  const int need = n_tags[f] < 2;
+  const int before = n_tags[f];
+  const int need = before < 2;
   int t = threadIdx.x;
   if (t < tags) {
     int64_t base = ((int64_t)f * tags + t) * 4;
@@ -351,20 +352,23 @@ __global__ void lk_merge_kernel(const float* __restrict__ tracked, const uint8_t
     if (det) atomicAdd(&s_cnt, 1);
   }
   __syncthreads();
-  if (threadIdx.x == 0) n_tags[f] = s_cnt;
+  if (threadIdx.x == 0) {
+    n_tags[f] = s_cnt;
+    if (tracked_tags) tracked_tags[f] = s_cnt - before;
+  }
 }
 
 }  // namespace
 
 extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
-                            float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int batch, int n_pts) {
+                            float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int32_t* d_tracked_tags, int batch, int n_pts) {
   if (!ctx) return AGT_ERR_INVALID;
   if (batch == 0) return AGT_OK;          // nothing to do (empty tensors may carry null pointers)
   if (!d_tracked_pts || !d_status || !d_prev_valid || !d_img_pts || !d_valid || !d_n_tags || batch < 0 || n_pts < 4 ||
       (n_pts & 3) || n_pts > AGT_MAX_POINTS)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_merge: bad arguments");
   if (batch == 0) return AGT_OK;
-  lk_merge_kernel<<<batch, 32, 0, ctx->stream>>>(d_tracked_pts, d_status, d_prev_valid, d_img_pts, d_valid, d_n_tags, batch,
+  lk_merge_kernel<<<batch, 32, 0, ctx->stream>>>(d_tracked_pts, d_status, d_prev_valid, d_img_pts, d_valid, d_n_tags, d_tracked_tags, batch,
                                                  n_pts / 4);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;

@@ -136,9 +136,10 @@ int agt_lk_fallback(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* ne
 /* Stage-2 integration rule: for every frame with fewer than 2 detected tags, re-admit each
  * tag that was accepted in the previous frame (d_prev_valid) and whose four corners were all tracked
  * (d_status == 1): its tracked corners are copied into d_img_pts and its d_valid entries set.
- * d_n_tags[batch] is recomputed (tags with 4 valid corners).  n_pts = 4 * n_tags_total. */
+ * d_n_tags[batch] is recomputed (tags with 4 valid corners); d_tracked_tags[batch] (may be NULL) receives how many
+ * tags were re-admitted.  n_pts = 4 * n_tags_total. */
 int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
-                 float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int batch, int n_pts);
+                 float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int32_t* d_tracked_tags, int batch, int n_pts);
 
 /* ---- K3: batched PnP (cv::solvePnP SOLVEPNP_ITERATIVE + reprojection gate) --- */
 /* d_obj_pts[n_pts][3] float32 is shared by the batch (group corners, index
@@ -172,6 +173,18 @@ int agt_ape_prepare(agt_ctx* ctx, const double* d_state, double* d_guess, uint8_
 int agt_ape_update(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const double* d_pose,
                    const uint8_t* d_ok, const float* d_err, uint8_t* d_accepted, uint8_t* d_error_flag,
                    int batch, int enhance_ape);
+/* d_gate[batch] = the reference's acceptance test of a solved frame (detect_pose.py:494, 533, 539): at least two
+ * tags, solvePnP succeeded, mean reprojection error below 2 px.  Masks the dense refinement of a stream step. */
+int agt_accept_gate(agt_ctx* ctx, const uint8_t* d_ok, const float* d_err, const int32_t* d_n_tags, uint8_t* d_gate, int batch);
+/* agt_ape_update for a stream step with dense refinement and LK: where d_refined_status[batch] != 0 the refined
+ * pose d_refined_pose[batch][6] replaces the PnP pose before it becomes prev_transform (both may be NULL); then the
+ * frame's corners are handed to the next LK step (d_prev_pts = d_img_pts, d_prev_valid = d_valid where the frame was
+ * accepted, else 0: PoseDetector keeps the corners of accepted frames only; all four may be NULL) and
+ * d_pose_out[batch][6] (may be NULL) receives each stream's prev_transform. */
+int agt_ape_commit(agt_ctx* ctx, double* d_state, const int32_t* d_n_tags, const double* d_pose, const uint8_t* d_ok,
+                   const float* d_err, const double* d_refined_pose, const uint8_t* d_refined_status,
+                   const float* d_img_pts, const uint8_t* d_valid, float* d_prev_pts, uint8_t* d_prev_valid, int n_pts,
+                   uint8_t* d_accepted, uint8_t* d_error_flag, double* d_pose_out, int batch, int enhance_ape);
 
 /* ---- K4: dense pose refinement (photometric LM; DodecaPen stage 3) ----------- */
 /* d_init[batch][n_hyp][6] -> d_pose[batch][n_hyp][6]; cost = 1/2 sum r^2,
