@@ -386,7 +386,6 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
     layout_pyramid(&p, buf[s], w, h, levels, chunk);
     if (c >= 2) AGT_CUDA(ctx, cudaStreamWaitEvent(cp, ctx->ev[s], 0));       // compute on this buffer finished
     const bool contiguous_ids = ids == nullptr;
-    bool gathered = false;
     if (roi && ctx->host_frames_dev && (w & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx->host_frames_dev) & 15) == 0) {
       // rectangles of this chunk -> device, then one gather launch on the copy stream
       agt_roi_rect* hr = ctx->h_rects + b0;        // pinned; one slot per frame of the pass, so the CPU never
@@ -405,7 +404,6 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
       // (measured 32 / 64 / 128 / 256 CTAs x chunk 128..1024 frames: profiles/r01_e2e_sweep.log)
       roi_gather_kernel<<<nb < 64 ? nb : 64, 256, 0, cp>>>(ctx->host_frames_dev, w, h, drc, p.data[0], p.pitch[0], p.frame_stride[0], nb);
       AGT_LAUNCH_CHECK(ctx);
-      gathered = true;
     } else if (!roi && contiguous_ids && tight) {
       AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], h_frames + (int64_t)b0 * w * h, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
       ctx->last_h2d_bytes += (int64_t)nb * w * h;

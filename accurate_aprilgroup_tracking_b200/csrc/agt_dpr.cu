@@ -55,8 +55,7 @@ struct DprShared {
   double Pt[12];                 // trial pose itself: rotation (row-major) + translation
   __align__(16) float Rf[12];    // (R0,R3) (R1,R4) (R2,R5) (t0,t1) as pairs for the packed float32 ops, then R6 R7 R8 t2
   __align__(16) double proj[4];  // fx*2^-l, fy*2^-l, cx*2^-l, cy*2^-l (two 128-bit loads)
-  float fx, fy, cx, cy;
-  float inv_scale;       // 2^-level
+  float fx, fy;
   float gscale;          // 2^-level / 32
   int level, lw, lh;
   int64_t lpitch;
@@ -80,11 +79,6 @@ struct DprShared {
   int nc, evals, status;
 };
 
-__device__ __forceinline__ uint32_t ld4_unaligned_smem(const uint8_t* base, int off) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (off & ~3));
-  return __byte_perm(w[0], w[1], 0x3210 + 0x1111 * (off & 3));
-}
-
 // (L2-coherent loads: with K1 fused the level image is written by this very launch, so the read-only path is out)
 __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
   return (uint32_t)__ldcg(p) | ((uint32_t)__ldcg(p + 1) << 8) | ((uint32_t)__ldcg(p + 2) << 16) | ((uint32_t)__ldcg(p + 3) << 24);
@@ -97,8 +91,8 @@ __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2 pk2(int lo, int hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a; asm("{ .reg .b32 t; mov.b64 {%0, t}, %1; }" : "=f"(a) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float b; asm("{ .reg .b32 t; mov.b64 {t, %0}, %1; }" : "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
 __device__ __forceinline__ f32x2 swap2(f32x2 v) { return pk2(hi2(v), lo2(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
@@ -399,9 +393,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
     S.tx0 = jb.y; S.ty0 = jb.z; S.tw = jb.w; S.th = jc.x;
     S.left_roi = 0;
     double sc = 1.0 / (double)(1 << lvl);
-    S.inv_scale = (float)sc;
     S.gscale = (float)(sc / 32.0);
-    S.fx = (float)cam.fx; S.fy = (float)cam.fy; S.cx = (float)cam.cx; S.cy = (float)cam.cy;
+    S.fx = (float)cam.fx; S.fy = (float)cam.fy;
     // active tags (visibility frozen at the initial pose)
     const uint32_t active = (uint32_t)jc.y;
     int na = 0, pre = 0;
@@ -476,7 +469,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 
   const int n_act_samples = S.act_prefix[S.n_active];
   const float fx = S.fx, fy = S.fy, gsc = S.gscale;
-  const int lw = S.lw, lh = S.lh, tx0 = S.tx0, ty0 = S.ty0, tw = S.tw, th = S.th;
+  const int lw = S.lw, lh = S.lh, tx0 = S.tx0, ty0 = S.ty0;
   const int64_t lpitch = S.lpitch;
   const uint8_t* limg = S.limg;
   // footprint origin relative to the tile straight from the high word of ul + 1.5 * 2^20 (see the sample loop)

@@ -21,7 +21,6 @@
 namespace {
 
 constexpr int WIN = 21;
-constexpr int NPIX = WIN * WIN;            // 441
 constexpr int PATCH = WIN + 3;             // 24: template footprint incl. bilinear + Scharr halo
 constexpr int DER = WIN + 1;               // 22
 constexpr int REG = 32;                    // staged search region
