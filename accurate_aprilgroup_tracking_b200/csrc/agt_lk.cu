@@ -153,10 +153,14 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     }
     __syncwarp();
     // ---- stage the 24x24 template footprint (reflect-101 intensity) -------------
-    for (int i = lane; i < PATCH * PATCH; i += 32) {
-      int r = i / PATCH, c = i - r * PATCH;
-      int gy = reflect_fast(iy - 1 + r, rows), gx = reflect_fast(ix - 1 + c, cols);
-      S.u.t.patch[r][c] = __ldg(imgI + (int64_t)gy * pitchI + gx);
+    {
+      // a lane per column (its reflected source column is computed once), the row index is warp-uniform
+      const int gx = reflect_fast(ix - 1 + (lane < PATCH ? lane : 0), cols);
+#pragma unroll 6
+      for (int r = 0; r < PATCH; ++r) {
+        const int gy = reflect_fast(iy - 1 + r, rows);
+        if (lane < PATCH) S.u.t.patch[r][lane] = __ldg(imgI + (int64_t)gy * pitchI + gx);
+      }
     }
     __syncwarp();
     // ---- Scharr at the 22x22 integer positions; zero outside the image -------------
@@ -181,33 +185,41 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     segment_of(lane, 0, seg_row[0], seg_col[0]);
     segment_of(lane, 1, seg_row[1], seg_col[1]);
     int s11 = 0, s12 = 0, s22 = 0;
-    long long c1 = 0, c2 = 0;                    // sum of template * derivative: lets the search loop skip the template
+    int c1 = 0, c2 = 0;                          // sum of template * derivative: lets the search loop skip the template
+    const uint32_t patch_a = (uint32_t)__cvta_generic_to_shared(&S.u.t.patch[0][0]);
+    const uint32_t wtI = (uint32_t)w.w00 | ((uint32_t)w.w01 << 16), wbI = (uint32_t)w.w10 | ((uint32_t)w.w11 << 16);
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg) {
       const bool live = seg_row[sg] < WIN;
-      const int y = live ? seg_row[sg] : WIN - 1;
+      const int y = live ? seg_row[sg] : WIN - 1, x0 = seg_col[sg];
+      // the run's template intensities: rows y+1, y+2 of the footprint from column x0+1, blended as in the search loop
+      const Run t = load_run(patch_a + (y + 1) * PATCH + x0 + 1), bt = load_run(patch_a + (y + 2) * PATCH + x0 + 1);
+      int ivs[SEG_LEN];
+      ivs[0] = blend<0>(t, bt, wtI, wbI); ivs[1] = blend<1>(t, bt, wtI, wbI); ivs[2] = blend<2>(t, bt, wtI, wbI);
+      ivs[3] = blend<3>(t, bt, wtI, wbI); ivs[4] = blend<4>(t, bt, wtI, wbI); ivs[5] = blend<5>(t, bt, wtI, wbI);
+      ivs[6] = blend<6>(t, bt, wtI, wbI);
+      // the eight Scharr values of the run's two rows, each used by two neighbouring pixels
+      short2 d0[SEG_LEN + 1], d1[SEG_LEN + 1];
+#pragma unroll
+      for (int k = 0; k <= SEG_LEN; ++k) { d0[k] = S.u.t.der[y][x0 + k]; d1[k] = S.u.t.der[y + 1][x0 + k]; }
 #pragma unroll
       for (int k = 0; k < SEG_LEN; ++k) {
-        const int x = seg_col[sg] + k;
-        const uint8_t(*p)[PATCH] = S.u.t.patch;
-        int iv = descale(p[y + 1][x + 1] * w.w00 + p[y + 1][x + 2] * w.w01 + p[y + 2][x + 1] * w.w10 + p[y + 2][x + 2] * w.w11,
-                         W_BITS - 5);
-        short2 d00 = S.u.t.der[y][x], d01 = S.u.t.der[y][x + 1], d10 = S.u.t.der[y + 1][x], d11 = S.u.t.der[y + 1][x + 1];
-        int dxv = descale(d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11, W_BITS);
-        int dyv = descale(d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11, W_BITS);
+        int iv = ivs[k];
+        int dxv = descale(d0[k].x * w.w00 + d0[k + 1].x * w.w01 + d1[k].x * w.w10 + d1[k + 1].x * w.w11, W_BITS);
+        int dyv = descale(d0[k].y * w.w00 + d0[k + 1].y * w.w01 + d1[k].y * w.w10 + d1[k + 1].y * w.w11, W_BITS);
         if (!live) { iv = 0; dxv = 0; dyv = 0; }
         const int slot = lane * PIX_PER_LANE + sg * SEG_LEN + k;
         S.tmpl[slot] = (short)iv;
         S.dd[slot] = make_int2(dxv, dyv);
         s11 += dxv * dxv; s12 += dxv * dyv; s22 += dyv * dyv;
-        c1 += iv * dxv; c2 += iv * dyv;
+        c1 += iv * dxv; c2 += iv * dyv;          // |iv| <= 8160, |d| <= 4080: 14 terms fit in 32 bits
       }
     }
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     float A11 = __fmul_rn((float)agt_warp_sum((long long)s11), FLT_SCALE);
     float A12 = __fmul_rn((float)agt_warp_sum((long long)s12), FLT_SCALE);
     float A22 = __fmul_rn((float)agt_warp_sum((long long)s22), FLT_SCALE);
-    const long long C1 = agt_warp_sum(c1), C2 = agt_warp_sum(c2);
+    const long long C1 = agt_warp_sum((long long)c1), C2 = agt_warp_sum((long long)c2);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     float dif = __fsub_rn(A11, A22);
     float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
