@@ -75,6 +75,13 @@ __device__ __forceinline__ int descale(int v, int n) { return (v + (1 << (n - 1)
 // BORDER_REFLECT_101 index: in range for every window that is not cut by the image border (no modulo then)
 __device__ __forceinline__ int reflect_fast(int i, int n) { return (unsigned)i < (unsigned)n ? i : agt_reflect101(i, n); }
 
+// acc + sum_k px.byte[k] (unsigned) * coef.byte[k] (signed)
+__device__ __forceinline__ int dp4us(uint32_t px, int coef, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(coef), "r"(acc));
+  return d;
+}
+
 // The 8 bytes of a run (columns col..col+7 of one staged row) as two words with the run's first byte in bits 0-7, plus
 // the same shifted by one byte: pixel k of the run blends bytes (k, k+1) of two rows, i.e. one half of one of these
 // words per row, which is exactly what dp2a multiplies by a pair of 16-bit weights.
@@ -164,6 +171,39 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     }
     __syncwarp();
     // ---- Scharr at the 22x22 integer positions; zero outside the image -------------
+    if (ix >= 0 && iy >= 0 && ix + DER <= cols && iy + DER <= rows) {
+      // window inside the image (warp-uniform): a lane per row reads the three footprint rows as aligned words and
+      // forms every derivative with chained dp4a ([3 10 3] folded into the byte coefficients), no per-tap byte loads
+      if (lane < DER) {
+        uint32_t w[3][PATCH / 4];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          const uint2* src = reinterpret_cast<const uint2*>(&S.u.t.patch[lane + rr][0]);      // 24-byte rows: 8 B aligned
+#pragma unroll
+          for (int q = 0; q < PATCH / 8; ++q) { const uint2 v = src[q]; w[rr][2 * q] = v.x; w[rr][2 * q + 1] = v.y; }
+        }
+#pragma unroll
+        for (int c = 0; c < DER; ++c) {
+          const int j = c >> 2, m = c & 3;              // bytes c..c+2 of a row = bytes m..m+2 of word j (and word j+1)
+          // coefficient words for a tap triple starting at byte m: difference (-k, 0, +k) and smoothing (3, 10, 3)
+          const int d3a = m == 0 ? 0x000300FD : m == 1 ? 0x0300FD00 : m == 2 ? (int)0x00FD0000 : (int)0xFD000000;
+          const int d3b = m == 2 ? 0x00000003 : m == 3 ? 0x00000300 : 0;
+          const int d10a = m == 0 ? 0x000A00F6 : m == 1 ? 0x0A00F600 : m == 2 ? (int)0x00F60000 : (int)0xF6000000;
+          const int d10b = m == 2 ? 0x0000000A : m == 3 ? 0x00000A00 : 0;
+          const int sma = m == 0 ? 0x00030A03 : m == 1 ? 0x030A0300 : m == 2 ? 0x0A030000 : 0x03000000;
+          const int smb = m == 2 ? 0x00000003 : m == 3 ? 0x0000030A : 0;
+          const int nsma = m == 0 ? 0x00FDF6FD : m == 1 ? (int)0xFDF6FD00 : m == 2 ? (int)0xF6FD0000 : (int)0xFD000000;
+          const int nsmb = m == 2 ? 0x000000FD : m == 3 ? 0x0000FDF6 : 0;
+          int dx = dp4us(w[2][j], d3a, dp4us(w[1][j], d10a, dp4us(w[0][j], d3a, 0)));
+          int dy = dp4us(w[2][j], sma, dp4us(w[0][j], nsma, 0));
+          if (m >= 2) {
+            dx = dp4us(w[2][j + 1], d3b, dp4us(w[1][j + 1], d10b, dp4us(w[0][j + 1], d3b, dx)));
+            dy = dp4us(w[2][j + 1], smb, dp4us(w[0][j + 1], nsmb, dy));
+          }
+          S.u.t.der[lane][c] = make_short2((short)dx, (short)dy);
+        }
+      }
+    } else
     for (int i = lane; i < DER * DER; i += 32) {
       int r = i / DER, c = i - r * DER;
       int gx = ix + c, gy = iy + r;
