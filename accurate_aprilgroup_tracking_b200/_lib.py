@@ -63,6 +63,8 @@ PROTOTYPES = {
     "agt_scharr": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _I]),
     "agt_lk": (_I, [_VP, _PYR, _PYR, _VP, _VP, _VP, _VP, _I, _I]),
     "agt_lk_fallback": (_I, [_VP, _PYR, _PYR, _VP, _VP, _VP, _VP, _VP, _I, _I]),
+    "agt_lk_rects": (_I, [_VP, _PYR, _VP, _VP, _I, _I, _VP, _I, _I]),
+    "agt_lk_roi": (_I, [_VP, _PYR, _PYR, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
     "agt_pnp": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
     "agt_project": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_prepare": (_I, [_VP, _VP, _VP, _VP, _I, _I]),

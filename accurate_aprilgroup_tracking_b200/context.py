@@ -200,6 +200,45 @@ class AgtContext:
                                                  self._p(st), self._p(err), self._p(n_tags), b, p))
         return out, st, err
 
+    def lk_rects(self, pyr: Pyramid, pts, valid=None, max_flow: int = 32):
+        """Level-0 rectangle [B,4] i32 that tracking ``pts`` [B,P,2] can read while no corner moves more than max_flow px."""
+        t = self.torch
+        p = self._dev(pts, t.float32)
+        b, n = int(p.shape[0]), int(p.shape[1])
+        rects = t.empty((b, 4), dtype=t.int32, device=self.tdev)
+        v = self._dev(valid, t.uint8) if valid is not None else None
+        self._use_current_stream()
+        self._check(self.lib.agt_lk_rects(self.h, C.byref(pyr.desc), self._p(p), self._p(v), n, int(max_flow), self._p(rects), 4, b))
+        return rects
+
+    def lk_roi(self, prev: Pyramid, nxt: Pyramid, prev_pts, rects_prev=None, n_tags=None, max_flow: int = 32, valid=None):
+        """Tracking with the pyramid of the new frames built only where the corners can look, exact by construction:
+        rectangles from prev_pts -> ROI pyramid of ``nxt`` (level 0 must hold the frames) -> LK; frames in which a corner
+        looked outside what was built (``left_roi``) get complete pyramids and are tracked again, all on the device
+        (the redo launches leave at once when nothing is flagged).  ``rects_prev``: rectangles ``prev`` was built under
+        (None = complete).  -> (next_pts, status, err, rects, redo[B] u8); ``nxt`` is valid under ``rects`` except for
+        the frames flagged in ``redo``, which are complete."""
+        t = self.torch
+        pts = self._dev(prev_pts, t.float32)
+        b, p = int(pts.shape[0]), int(pts.shape[1])
+        rects = self.lk_rects(nxt, pts, valid, max_flow)
+        self.build_pyramid_roi(nxt, rects, b)
+        out = t.empty_like(pts)
+        st = t.empty((b, p), dtype=t.uint8, device=self.tdev)
+        err = t.empty((b, p), dtype=t.float32, device=self.tdev)
+        left = t.empty((b, p), dtype=t.uint8, device=self.tdev)
+        redo = t.empty(b, dtype=t.uint8, device=self.tdev)
+        self._use_current_stream()
+        args = (self._p(pts), self._p(out), self._p(st), self._p(err), self._p(n_tags))
+        self._check(self.lib.agt_lk_roi(self.h, C.byref(prev.desc), C.byref(nxt.desc), *args, self._p(rects_prev), self._p(rects), 4,
+                                        None, self._p(left), b, p))
+        self._check(self.lib.agt_any_flag(self.h, self._p(left), p, self._p(redo), b))
+        self.build_pyramid_masked(nxt, redo, b)
+        if rects_prev is not None:
+            self.build_pyramid_masked(prev, redo, b)
+        self._check(self.lib.agt_lk_roi(self.h, C.byref(prev.desc), C.byref(nxt.desc), *args, None, None, 0, self._p(redo), None, b, p))
+        return out, st, err, rects, redo
+
     def lk_merge(self, tracked, status, prev_valid, img_pts, valid, n_tags, tracked_tags=None):
         """In place: re-admit fully tracked tags into img_pts/valid for frames with < 2 detected tags;
         tracked_tags [B] i32 (optional) receives the number of tags re-admitted per frame."""

@@ -20,6 +20,9 @@
 
 namespace {
 
+// rows of the staging loops that are unrolled (global loads in flight per lane): 6 / 4 measured best under the 64-register
+// cap (profiles/r01_lk_variants.log)
+constexpr int kPatchUnroll = 6, kRegionUnroll = 4;
 constexpr int WIN = 21;
 constexpr int PATCH = WIN + 3;             // 24: template footprint incl. bilinear + Scharr halo
 constexpr int DER = WIN + 1;               // 22
@@ -51,12 +54,21 @@ struct __align__(16) WarpSmem {
   } u;
   __align__(16) int2 dd[NSLOT];            // template derivative (dx, dy), lane-major
   short tmpl[NSLOT];                       // template intensity * 32, lane-major
+  // region-of-interest pyramids only: exact part [x_lo, x_hi) x [y_lo, y_hi) of the current level of the next pyramid and
+  // the "looked outside" flag, kept here rather than in registers that would be live across the search loop
+  __align__(16) int win[4];
+  int left;
 };
 
 __device__ __forceinline__ void segment_of(int lane, int s, int& row, int& col) {
   if (lane < WIN) { row = lane; col = SEG_LEN * s; }
   else { row = 2 * (lane - WIN) + s; col = 2 * SEG_LEN; }
 }
+
+// Exact warp-wide sum of one 32-bit integer per lane (the total needs more than 32 bits).  Five 64-bit shuffle steps; the
+// warp-reduce unit (two REDUX.SUM on the 16-bit halves) was measured 4-14 % slower for the whole kernel
+// (profiles/r01_lk_variants.log).
+__device__ __forceinline__ long long warp_sum_wide(int v) { return agt_warp_sum((long long)v); }
 
 struct Weights { int w00, w01, w10, w11; };
 
@@ -112,26 +124,57 @@ __device__ __forceinline__ int blend(const Run& t, const Run& b, uint32_t wt, ui
 __device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8_t* __restrict__ img, int cols, int rows,
                                              int64_t pitch, int rx0, int ry0, int lane) {
   int gx = reflect_fast(rx0 + lane, cols);
-#pragma unroll 4
+#pragma unroll (kRegionUnroll)
   for (int r = 0; r < REG; ++r) {
     int gy = reflect_fast(ry0 + r, rows);
     region[r][lane] = __ldg(img + (int64_t)gy * pitch + gx);
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
-lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
-          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total,
-          const int32_t* __restrict__ skip_if_tags_ge2) {
-  __shared__ WarpSmem smem[WARPS_PER_CTA];
-  const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-  const int64_t gid = (int64_t)blockIdx.x * WARPS_PER_CTA + wid;
-  if (gid >= total) return;
-  WarpSmem& S = smem[wid];
+// Region-of-interest pyramids (agt_build_pyramid_roi): a pixel of level l >= 1 is exact iff the level-0 support of its
+// pyrDown chain, 2^l x +- (2^(l+1) - 2), lies inside the frame's level-0 rectangle (or is cut by the image border, where
+// the chain reflects back inside).  Level 0 is the frame itself.  -> half-open window [lo, hi) of exact pixels along one axis.
+__device__ __forceinline__ void exact_window(int r_lo, int r_hi, int n0, int n, int level, int& lo, int& hi) {
+  if (level == 0) { lo = 0; hi = n; return; }
+  const int reach = (2 << level) - 2;
+  lo = r_lo <= 0 ? 0 : (r_lo + reach + (1 << level) - 1) >> level;
+  hi = r_hi >= n0 ? n : ((r_hi - 1 - reach) >> level) + 1;
+  if (hi < 0) hi = 0;
+}
+// does the footprint [f0, f1) of an n-pixel axis, read with BORDER_REFLECT_101, stay inside [lo, hi)?
+__device__ __forceinline__ bool footprint_inside(int f0, int f1, int n, int lo, int hi) {
+  int a = max(f0, 0), b = min(f1, n);
+  if (f0 < 0) b = max(b, min(n, 1 - f0));                 // -k reads k
+  if (f1 > n) a = min(a, max(0, 2 * n - 1 - f1));         // n-1+k reads n-1-k
+  return a >= lo && b <= hi;
+}
+
+// rects_prev / rects_next (may be null: every level is complete) are the level-0 rectangles the two pyramids were built
+// under; a corner whose footprints leave the exact part of a level is flagged in left_roi_out (its outputs are then
+// meaningless and the caller redoes the frame on complete pyramids).  mask (may be null): only frames with a non-zero
+// entry are processed, the outputs of the others are left untouched.
+template <bool kRoi>
+__device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int64_t gid, const agt_pyramid& prev, const agt_pyramid& next,
+                                          const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                                          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts,
+                                          const int32_t* __restrict__ skip_if_tags_ge2, const int32_t* __restrict__ rects_prev,
+                                          const int32_t* __restrict__ rects_next, int rect_stride, const uint8_t* __restrict__ mask,
+                                          uint8_t* __restrict__ left_roi_out) {
   const int frame = (int)(gid / n_pts);
+  if (mask != nullptr && mask[frame] == 0) return;
+  // region-of-interest rectangles: element k of the previous / next pyramid's rectangle lives in lane k / 4 + k (one
+  // register, one exposed load latency per corner) and is fetched by shuffle at every level
+  int rect_elem = (lane & 3) < 2 ? 0 : ((lane & 3) == 2 ? prev.width[0] : prev.height[0]);
+  if (kRoi) {
+    if (lane == 0) S.left = 0;
+    if (lane < 4 && rects_prev != nullptr) rect_elem = __ldg(rects_prev + (int64_t)frame * rect_stride + lane);
+    if (lane >= 4 && lane < 8 && rects_next != nullptr) rect_elem = __ldg(rects_next + (int64_t)frame * rect_stride + lane - 4);
+  }
   if (skip_if_tags_ge2 != nullptr && skip_if_tags_ge2[frame] >= 2) {     // stage-2 rule: tracking only backs up frames with < 2 tags
-    if (lane == 0) { next_pts[gid * 2] = prev_pts[gid * 2]; next_pts[gid * 2 + 1] = prev_pts[gid * 2 + 1]; status_out[gid] = 0; err_out[gid] = 0.f; }
+    if (lane == 0) {
+      next_pts[gid * 2] = prev_pts[gid * 2]; next_pts[gid * 2 + 1] = prev_pts[gid * 2 + 1]; status_out[gid] = 0; err_out[gid] = 0.f;
+      if (left_roi_out != nullptr) left_roi_out[gid] = 0;
+    }
     return;
   }
   const float ptx = prev_pts[gid * 2], pty = prev_pts[gid * 2 + 1];
@@ -158,12 +201,25 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
       if (level == 0) { status = 0; err = 0.f; }
       continue;
     }
+    if (kRoi) {
+      int rp[4], rn[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rp[k] = __shfl_sync(0xffffffffu, rect_elem, k); rn[k] = __shfl_sync(0xffffffffu, rect_elem, 4 + k); }
+      int ax, bx, ay, by;
+      exact_window(rp[0], rp[2], prev.width[0], cols, level, ax, bx);
+      exact_window(rp[1], rp[3], prev.height[0], rows, level, ay, by);
+      const bool out = !footprint_inside(ix - 1, ix - 1 + PATCH, cols, ax, bx) || !footprint_inside(iy - 1, iy - 1 + PATCH, rows, ay, by);
+      exact_window(rn[0], rn[2], prev.width[0], cols, level, ax, bx);
+      exact_window(rn[1], rn[3], prev.height[0], rows, level, ay, by);
+      __syncwarp();
+      if (lane == 0) { S.win[0] = ax; S.win[1] = bx; S.win[2] = ay; S.win[3] = by; if (out) S.left = 1; }
+    }
     __syncwarp();
     // ---- stage the 24x24 template footprint (reflect-101 intensity) -------------
     {
       // a lane per column (its reflected source column is computed once), the row index is warp-uniform
       const int gx = reflect_fast(ix - 1 + (lane < PATCH ? lane : 0), cols);
-#pragma unroll 6
+#pragma unroll (kPatchUnroll)
       for (int r = 0; r < PATCH; ++r) {
         const int gy = reflect_fast(iy - 1 + r, rows);
         if (lane < PATCH) S.u.t.patch[r][lane] = __ldg(imgI + (int64_t)gy * pitchI + gx);
@@ -256,10 +312,10 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
       }
     }
     const float FLT_SCALE = 1.f / (float)(1 << 20);
-    float A11 = __fmul_rn((float)agt_warp_sum((long long)s11), FLT_SCALE);
-    float A12 = __fmul_rn((float)agt_warp_sum((long long)s12), FLT_SCALE);
-    float A22 = __fmul_rn((float)agt_warp_sum((long long)s22), FLT_SCALE);
-    const long long C1 = agt_warp_sum((long long)c1), C2 = agt_warp_sum((long long)c2);
+    float A11 = __fmul_rn((float)warp_sum_wide(s11), FLT_SCALE);
+    float A12 = __fmul_rn((float)warp_sum_wide(s12), FLT_SCALE);
+    float A22 = __fmul_rn((float)warp_sum_wide(s22), FLT_SCALE);
+    const long long C1 = warp_sum_wide(c1), C2 = warp_sum_wide(c2);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     float dif = __fsub_rn(A11, A22);
     float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -290,6 +346,10 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
       if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
         __syncwarp();
         rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+        if (kRoi) {
+          const int4 wn = *reinterpret_cast<const int4*>(S.win);
+          if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
+        }
         stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
         staged = true;
         __syncwarp();
@@ -315,8 +375,8 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
           sb1 += jv[k] * dx; sb2 += jv[k] * dy;
         }
       }
-      float b1 = __fmul_rn((float)(agt_warp_sum((long long)sb1) - C1), FLT_SCALE);
-      float b2 = __fmul_rn((float)(agt_warp_sum((long long)sb2) - C2), FLT_SCALE);
+      float b1 = __fmul_rn((float)(warp_sum_wide(sb1) - C1), FLT_SCALE);
+      float b2 = __fmul_rn((float)(warp_sum_wide(sb2) - C2), FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -339,6 +399,10 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
         if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
           __syncwarp();
           rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+          if (kRoi) {
+            const int4 wn = *reinterpret_cast<const int4*>(S.win);
+            if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
+          }
           stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
           __syncwarp();
         }
@@ -361,7 +425,7 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
             sabs += diff < 0 ? -diff : diff;
           }
         }
-        err = __fmul_rn((float)agt_warp_sum((long long)sabs), 1.f / (float)(32 * WIN * WIN));
+        err = __fmul_rn((float)warp_sum_wide(sabs), 1.f / (float)(32 * WIN * WIN));
       }
     }
   }
@@ -370,6 +434,70 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
     next_pts[gid * 2 + 1] = outy;
     status_out[gid] = (uint8_t)status;
     err_out[gid] = status ? err : 0.f;
+    if (kRoi && left_roi_out != nullptr) left_roi_out[gid] = S.left ? 1 : 0;
+  }
+}
+
+// One warp per corner.  Unmasked launches have one corner per warp; masked launches (the redo pass of agt_lk_roi: few
+// frames flagged, usually none) use a small grid whose warps stride over the corners and leave after one pass over the
+// mask when nothing is flagged, instead of launching tens of thousands of CTAs that have nothing to do.
+template <bool kRoi, bool kStride>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+          uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total,
+          const int32_t* __restrict__ skip_if_tags_ge2, const int32_t* __restrict__ rects_prev,
+          const int32_t* __restrict__ rects_next, int rect_stride, const uint8_t* __restrict__ mask,
+          uint8_t* __restrict__ left_roi_out) {
+  __shared__ WarpSmem smem[WARPS_PER_CTA];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  if (!kStride) {
+    const int64_t gid = (int64_t)blockIdx.x * WARPS_PER_CTA + wid;
+    if (gid < total)
+      lk_corner<kRoi>(smem[wid], lane, gid, prev, next, prev_pts, next_pts, status_out, err_out, n_pts, skip_if_tags_ge2, rects_prev,
+                      rects_next, rect_stride, mask, left_roi_out);
+    return;
+  }
+  if (mask != nullptr) {
+    const int64_t n_frames = total / n_pts;
+    uint32_t acc = 0;
+    for (int64_t i = threadIdx.x; i < n_frames; i += blockDim.x) acc |= mask[i];
+    if (!__syncthreads_or(acc != 0)) return;
+  }
+  for (int64_t gid = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; gid < total; gid += (int64_t)gridDim.x * WARPS_PER_CTA) {
+    lk_corner<kRoi>(smem[wid], lane, gid, prev, next, prev_pts, next_pts, status_out, err_out, n_pts, skip_if_tags_ge2, rects_prev,
+                    rects_next, rect_stride, mask, left_roi_out);
+    __syncwarp();
+  }
+}
+
+// Level-0 rectangle (x0,y0,x1,y1; x multiples of 16) that covers what tracking the points of one frame can read when no
+// point moves more than max_flow level-0 pixels: per level the 32-pixel search region around the estimate (+-16 level
+// pixels, which contains the template footprint), the flow, and the pyrDown chain: (16 + 2) * 2^top + max_flow.
+// Points outside the frame are clamped to it (they read the reflected border region at most), NaNs are ignored.
+__global__ void lk_rects_kernel(const float* __restrict__ pts, const uint8_t* __restrict__ valid, int n_pts, int W, int H,
+                                int top, int max_flow, int32_t* __restrict__ rects, int rect_stride, int batch) {
+  const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (frame >= batch) return;
+  int x0 = W, y0 = H, x1 = -1, y1 = -1;
+  for (int k = lane; k < n_pts; k += 32) {
+    if (valid != nullptr && valid[(int64_t)frame * n_pts + k] == 0) continue;
+    const float x = pts[((int64_t)frame * n_pts + k) * 2], y = pts[((int64_t)frame * n_pts + k) * 2 + 1];
+    if (!(x == x) || !(y == y)) continue;
+    const int xi = (int)fminf(fmaxf(x, 0.f), (float)(W - 1)), yi = (int)fminf(fmaxf(y, 0.f), (float)(H - 1));
+    x0 = min(x0, xi); y0 = min(y0, yi); x1 = max(x1, xi); y1 = max(y1, yi);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+    x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+  }
+  if (lane == 0) {
+    int32_t* r = rects + (int64_t)frame * rect_stride;
+    if (x1 < 0) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+    const int pad = (18 << top) + max_flow;
+    x0 = max(0, x0 - pad) & ~15; y0 = max(0, y0 - pad);
+    x1 = min(W, (x1 + 1 + pad + 15) & ~15); y1 = min(H, y1 + 1 + pad);
+    r[0] = x0; r[1] = y0; r[2] = x1; r[3] = y1;
   }
 }
 
@@ -426,7 +554,9 @@ extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint
 }
 
 static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts, float* d_next_pts,
-                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags);
+                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags, const int32_t* d_rects_prev = nullptr,
+                   const int32_t* d_rects_next = nullptr, int rect_stride = 0, const uint8_t* d_mask = nullptr,
+                   uint8_t* d_left_roi = nullptr);
 
 extern "C" int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
                       float* d_next_pts, uint8_t* d_status, float* d_err, int batch, int n_pts) {
@@ -441,8 +571,34 @@ extern "C" int agt_lk_fallback(agt_ctx* ctx, const agt_pyramid* prev, const agt_
   return lk_impl(ctx, prev, next, d_prev_pts, d_next_pts, d_status, d_err, batch, n_pts, d_n_tags);
 }
 
+extern "C" int agt_lk_roi(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
+                          float* d_next_pts, uint8_t* d_status, float* d_err, const int32_t* d_n_tags, const int32_t* d_rects_prev,
+                          const int32_t* d_rects_next, int rect_stride, const uint8_t* d_mask, uint8_t* d_left_roi, int batch,
+                          int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if ((d_rects_prev || d_rects_next) && rect_stride < 4) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_roi: rect_stride < 4");
+  if ((d_rects_prev || d_rects_next) && !d_left_roi && (int64_t)batch * n_pts > 0)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_roi: d_left_roi is required with region-of-interest pyramids");
+  return lk_impl(ctx, prev, next, d_prev_pts, d_next_pts, d_status, d_err, batch, n_pts, d_n_tags, d_rects_prev, d_rects_next,
+                 rect_stride, d_mask, d_left_roi);
+}
+
+extern "C" int agt_lk_rects(agt_ctx* ctx, const agt_pyramid* pyr, const float* d_pts, const uint8_t* d_valid, int n_pts,
+                            int max_flow, int32_t* d_rects, int rect_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!pyr || !d_pts || !d_rects || batch < 0 || n_pts < 1 || rect_stride < 4 || max_flow < 0 || pyr->levels < 1 ||
+      pyr->levels > AGT_MAX_LEVELS)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk_rects: bad arguments");
+  lk_rects_kernel<<<(batch + 3) / 4, 128, 0, ctx->stream>>>(d_pts, d_valid, n_pts, pyr->width[0], pyr->height[0], pyr->levels - 1,
+                                                            max_flow, d_rects, rect_stride, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
 static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts, float* d_next_pts,
-                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags) {
+                   uint8_t* d_status, float* d_err, int batch, int n_pts, const int32_t* d_n_tags, const int32_t* d_rects_prev,
+                   const int32_t* d_rects_next, int rect_stride, const uint8_t* d_mask, uint8_t* d_left_roi) {
   if (!prev || !next || batch < 0 || n_pts < 0) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null pyramid or negative size");
   if ((int64_t)batch * n_pts > 0 && (!d_prev_pts || !d_next_pts || !d_status || !d_err))
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: null point / status / err buffer");
@@ -455,8 +611,16 @@ static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* nex
   if (total == 0) return AGT_OK;
   int64_t blocks = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: batch too large");
-  lk_kernel<<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status,
-                                                                       d_err, n_pts, total, d_n_tags);
+  const bool stride = d_mask != nullptr && blocks > 8LL * ctx->sm_count;
+  if (stride) blocks = 8LL * ctx->sm_count;      // warps stride over the corners
+  const bool roi = d_rects_prev || d_rects_next;
+#define AGT_LK_LAUNCH(R, S)                                                                                                     \
+  lk_kernel<R, S><<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status, d_err, \
+                                                                            n_pts, total, d_n_tags, d_rects_prev, d_rects_next,   \
+                                                                            rect_stride, d_mask, d_left_roi)
+  if (roi) { if (stride) AGT_LK_LAUNCH(true, true); else AGT_LK_LAUNCH(true, false); }
+  else     { if (stride) AGT_LK_LAUNCH(false, true); else AGT_LK_LAUNCH(false, false); }
+#undef AGT_LK_LAUNCH
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

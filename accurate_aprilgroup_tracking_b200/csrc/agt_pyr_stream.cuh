@@ -22,13 +22,13 @@ struct LanePlan {
 };
 
 template <int NW>
-__device__ __forceinline__ LanePlan<NW> make_plan(int ix0, int w, int lane) {
+__device__ __forceinline__ LanePlan<NW> make_plan(int ix0, int w, int lane, int xlim) {
   LanePlan<NW> p;
   p.refl_size = 0; p.refl_dst = 0;
 #pragma unroll
   for (int k = 0; k < NW; ++k) {
     const int ux = ix0 + 16 * k;
-    p.unit_size[k] = ux + 16 <= w ? 16 : 0;
+    p.unit_size[k] = (ux + 16 <= w && ux < xlim) ? 16 : 0;   // units past the last stored column's taps are not fetched
     p.unit_sel[k] = ux == w ? 0x4412u : 0x3210u;       // (p[w-2], p[w-3], -, -) from p[w-4..w-1]
     if (ux == w) { p.refl_size = 4; p.refl_dst = 16 + 16 * NW * lane + 16 * k; }
   }
@@ -64,7 +64,7 @@ __device__ __forceinline__ void agt_pyr_down_strip(const uint8_t* __restrict__ i
   constexpr int RPITCH = 16 + 16 * NW * 32 + 16;
   constexpr int PF_RING = PF_Q + 4;
   const int ix0 = 2 * ox0;
-  const LanePlan<NW> plan = make_plan<NW>(ix0, w, lane);
+  const LanePlan<NW> plan = make_plan<NW>(ix0, w, lane, 2 * xo1 + 4);
   const uint32_t ring_end = ring0 + PF_RING * RPITCH;
   const uint32_t lane_main = 16 + 16 * NW * lane;
   const int n_in = 2 * (oy1 - oy0) + 3;            // input rows the strip consumes

@@ -466,16 +466,25 @@ def run_lk(args):
     pts = torch.as_tensor(np.stack([synth.project(obj, traj[i, 0], CAM) for i in range(B)]).astype(np.float32), device=ctx.tdev)
     holder = {}
 
-    def step():
-        ctx.build_pyramid(pb)                       # pyramid of the new frames (the previous one is reused)
-        holder["out"] = ctx.lk(pa, pb, pts)
+    def step_full():
+        ctx.build_pyramid(pb)                       # complete pyramid of the new frames (the previous one is reused)
+        holder["full"] = ctx.lk(pa, pb, pts)
 
+    def step():
+        # pyramid of the new frames only where the corners can look + LK + exact redo of frames that looked outside
+        holder["out"] = ctx.lk_roi(pa, pb, pts)
+
+    full_ms = _timed(torch, dist, world, step_full, args.steps, 3) / args.steps
     l0 = ctx.launch_count()
     ms = _timed(torch, dist, world, step, args.steps, args.warmup)
-    launches = ctx.launch_count() - l0
-    lk_ms = _timed(torch, dist, world, lambda: holder.__setitem__("out", ctx.lk(pa, pb, pts)), args.steps, 3) / args.steps
+    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    same = all(bool(torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b))
+               for a, b in zip(holder["out"][:3], holder["full"]))
+    redone = int(holder["out"][4].sum())
+    ctx.build_pyramid(pb)
+    lk_ms = _timed(torch, dist, world, lambda: holder.__setitem__("k", ctx.lk(pa, pb, pts)), args.steps, 3) / args.steps
     if rank == 0:
-        out, st, err = holder["out"]
+        out, st, err = holder["out"][:3]
         peak, kind = measured_peaks()
         corners = B * 48
         ach = LK_BYTES_PER_CORNER * corners / (lk_ms * 1e-3) / 1e9
@@ -484,8 +493,11 @@ def run_lk(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32", "data": "synthetic",
             "config": {"workload": "pyramidal LK: 4 levels, 21x21 window, 48 corners per 1080p frame pair", "frame_pairs_per_gpu": B,
-                       "step": "K1 pyramid of the new frames + K2 LK", "l2": "inputs larger than L2"},
-            "gpu_launches": int(launches), "kernel_ms": {"lk": lk_ms}, "tracked_frac": float(st.float().mean()),
+                       "step": "K1 pyramid of the new frames below the rectangles the corners can look at (32 px of flow) + K2 LK + "
+                               "exact redo on complete pyramids of frames that looked outside", "l2": "inputs larger than L2"},
+            "gpu_launches": int(launches), "kernel_ms": {"lk": lk_ms, "step_with_complete_pyramid": full_ms},
+            "roi_equals_complete_pyramid_path": same, "frames_redone_on_complete_pyramid": redone,
+            "tracked_frac": float(st.float().mean()),
             "roofline": {"bound": "hbm", "kernel": "lk_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_kind": kind, "note": "5008 B per corner (SURVEY.md 8d); latency-bound by design"}}), flush=True)
 

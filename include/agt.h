@@ -133,6 +133,21 @@ int agt_lk(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const
  * only backs up frames in which fewer than two tags were detected. */
 int agt_lk_fallback(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts,
                     float* d_next_pts, uint8_t* d_status, float* d_err, const int32_t* d_n_tags, int batch, int n_pts);
+/* Tracking on region-of-interest pyramids (agt_build_pyramid_roi): tracking reads only the neighbourhood of the corners,
+ * so the pyramid of a new frame need not be built anywhere else.
+ * agt_lk_rects: d_rects[b*rect_stride + 0..3] = level-0 rectangle (x0,y0,x1,y1; x multiples of 16) that covers everything
+ * tracking the points of frame b (d_valid[b][n_pts] selects them, NULL = all) can read while no corner moves more than
+ * max_flow pixels: bounding box of the points + (16 + 2) * 2^(levels-1) + max_flow.
+ * agt_lk_roi: agt_lk / agt_lk_fallback (d_n_tags may be NULL) on pyramids built under d_rects_prev / d_rects_next (either
+ * may be NULL: that pyramid is complete).  The results are exact by construction: d_left_roi[b][n_pts] flags every corner
+ * whose template footprint or search region left the part of a level that is bit-identical to the full pyramid; the
+ * caller rebuilds the flagged frames (agt_any_flag + agt_build_pyramid_masked) and calls again with d_mask (NULL = all
+ * frames; otherwise only frames with a non-zero entry are tracked and the outputs of the others are left untouched). */
+int agt_lk_rects(agt_ctx* ctx, const agt_pyramid* pyr, const float* d_pts, const uint8_t* d_valid, int n_pts, int max_flow,
+                 int32_t* d_rects, int rect_stride, int batch);
+int agt_lk_roi(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* next, const float* d_prev_pts, float* d_next_pts,
+               uint8_t* d_status, float* d_err, const int32_t* d_n_tags, const int32_t* d_rects_prev,
+               const int32_t* d_rects_next, int rect_stride, const uint8_t* d_mask, uint8_t* d_left_roi, int batch, int n_pts);
 /* Stage-2 integration rule: for every frame with fewer than 2 detected tags, re-admit each
  * tag that was accepted in the previous frame (d_prev_valid) and whose four corners were all tracked
  * (d_status == 1): its tracked corners are copied into d_img_pts and its d_valid entries set.

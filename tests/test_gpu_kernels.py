@@ -156,6 +156,61 @@ def test_lk_empty_batch(ctxvga):
     assert out.shape == (1, 0, 2)
 
 
+@pytest.mark.parametrize("cam_name,max_flow,extra", [("1080p", 32, False), ("1080p", 0, False), ("vga", 32, True), ("vga", 2, False)])
+def test_lk_on_roi_pyramids_is_exact(ctx1080, ctxvga, cam_name, max_flow, extra):
+    """agt_lk_roi (pyramid of the new frames built only around the corners, frames that looked outside redone on complete
+    pyramids) returns bit for bit what agt_lk returns on complete pyramids - also when the rectangles are too small
+    (max_flow 0 / 2: the exactness net does the work) and with corners on and outside the image border.  Levels 1-3 of the
+    ROI pyramids are poisoned first, so anything read outside what was built would show."""
+    import torch
+    ctx, cam = (ctx1080, synth.CAMERA_1080P) if cam_name == "1080p" else (ctxvga, synth.CAMERA_VGA)
+    n = 12
+    trajs = [synth.trajectory(3300 + i, 6) for i in range(n)]
+    first = np.array([t[0] for t in trajs])
+    second = np.array([t[5 if max_flow < 32 else 1] for t in trajs])        # five frames apart: flows beyond a small max_flow
+    prev = _render(ctx, cam, first, np.arange(n) + 3300)
+    full = _render(ctx, cam, second, np.arange(n) + 3400)
+    obj = synth.object_points()
+    pts = np.stack([synth.project(obj, p, cam) for p in first]).astype(np.float32)
+    if extra:
+        more = np.array([[5, 5], [636.5, 3.2], [-3, 10], [700, 100], [320, 479.5], [0, 0], [639, 479], [-30, -30], [np.nan, 1.0]], np.float32)
+        pts = np.concatenate([pts, np.broadcast_to(more, (n,) + more.shape)], axis=1).astype(np.float32)
+    ref_out, ref_st, ref_err = ctx.lk(prev, full, pts)
+    roi = ctx.alloc_pyramid(n, cam.width, cam.height, 4)
+    roi.levels[0].copy_(full.levels[0])
+    for l in range(1, 4):
+        roi.levels[l].fill_(0xA5)
+    # max_flow 0: the rectangles are computed from the first corner alone, so most other corners look outside them
+    only_first = None
+    if max_flow == 0:
+        only_first = np.zeros(pts.shape[:2], np.uint8)
+        only_first[:, 0] = 1
+    out, st, err, rects, redo = ctx.lk_roi(prev, roi, pts, max_flow=max_flow, valid=only_first)
+    assert torch.equal(st, ref_st)
+    assert torch.equal(out.view(torch.int32), ref_out.view(torch.int32)), "tracked points differ from the complete-pyramid path"
+    assert torch.equal(err.view(torch.int32), ref_err.view(torch.int32))
+    n_redo = int(redo.sum())
+    if max_flow >= 32 and not extra:
+        print("lk roi: frames redone", n_redo, "of", n)
+        assert n_redo <= n // 4, f"{n_redo} of {n} frames left a rectangle sized for 32 px of flow"
+        r = rects.cpu().numpy()
+        assert ((r[:, 2] - r[:, 0]) * (r[:, 3] - r[:, 1])).mean() < 0.5 * cam.width * cam.height or cam_name == "vga"
+    if max_flow == 0:
+        assert n_redo > n // 2, "rectangles around one corner cannot cover the other 47"
+    # the previous pyramid may be a region-of-interest one as well (it is the `next` of the step before)
+    prev_roi = ctx.alloc_pyramid(n, cam.width, cam.height, 4)
+    prev_roi.levels[0].copy_(prev.levels[0])
+    for l in range(1, 4):
+        prev_roi.levels[l].fill_(0x5A)
+    rp = ctx.lk_rects(prev_roi, pts, None, max_flow)
+    ctx.build_pyramid_roi(prev_roi, rp)
+    for l in range(1, 4):
+        roi.levels[l].fill_(0xA5)
+    out2, st2, err2, _, redo2 = ctx.lk_roi(prev_roi, roi, pts, rects_prev=rp, max_flow=max_flow)
+    assert torch.equal(st2, ref_st) and torch.equal(out2.view(torch.int32), ref_out.view(torch.int32))
+    assert torch.equal(err2.view(torch.int32), ref_err.view(torch.int32))
+
+
 # ------------------------------------------------------------------------------------------
 # K3 PnP vs cv2.solvePnP(SOLVEPNP_ITERATIVE)
 # ------------------------------------------------------------------------------------------
