@@ -17,6 +17,7 @@ struct agt_camera {
 // cv::undistort; the distortion itself comes from agt_camera
 struct agt_undistort {
   double nfx, nskew, ncx, nfy, ncy;   // new camera matrix (upper triangular)
+  double inv_ab, ir0, ir1, ir4;       // stripe-independent entries of its inverse: 1/(fx fy), 1/fx, -s/(fx fy), 1/fy (set on the host)
   int stripe;                         // rows per map stripe: max(1, 4096 / width) of the frame it was set for
   int width, height;                  // frame size it was set for
   int roi_x, roi_y, roi_w, roi_h;     // crop (getOptimalNewCameraMatrix ROI)

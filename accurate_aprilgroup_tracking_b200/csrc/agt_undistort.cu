@@ -9,9 +9,16 @@
 // float64, rounded to 1/32 px; bilinear blend with cv::remap's table of int16 weights, (sum + 2^14) >> 15,
 // BORDER_CONSTANT 0; then the 15-bit BGR2GRAY of the three blended channels.
 //
-// One thread per output pixel; the map of a pixel is the same for every frame of the batch, so a thread computes
-// it once (float64, ~40 operations) and applies it to kFramesPerThread frames: the pass is bound by reading the
-// BGR frame once (6.2 MB per 1080p frame) and writing the gray one.
+// The map of a pixel is the same for every frame of the batch, so a thread computes it once (float64, ~40 operations)
+// and applies it to a group of frames; the pass is bound by reading the BGR frame once (6.2 MB per 1080p frame) and
+// writing the gray one.
+//
+// undistort_gray_tiled_kernel (16-byte aligned frames: every real camera format): a CTA owns a 32x32 output tile.  The
+// source pixels the tile reads form a small bounding box (the lens map is smooth), found once by a block-wide min/max over
+// the pixel maps; per frame that box is staged into shared memory with 16-byte asynchronous copies, three frames deep, so
+// that tens of KB per SM are in flight without holding registers, and the four taps of every pixel are gathered from
+// shared memory.  Tiles whose box does not fit a stage (extreme distortion) and unaligned frames take the per-pixel
+// global-memory path (undistort_gray_kernel), which computes the same integers.
 #include <cmath>
 #include <vector>
 
@@ -21,20 +28,17 @@ namespace {
 
 constexpr int kFramesPerThread = 8;
 
-__global__ void __launch_bounds__(128)
-undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__ tab, const uint8_t* __restrict__ src, int w, int h,
-                      int channels, int64_t spitch, int64_t sstride, uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride,
-                      int batch) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= U.roi_w) return;
-  // ---- the map of this pixel (cv::initUndistortRectifyMap on the stripe of cv::undistort that holds the row) ----
+// The map of output pixel (x, y) of the crop (cv::initUndistortRectifyMap on the stripe of cv::undistort that holds the row):
+// integer source position (sx, sy) and the four int16 bilinear weights of cv::remap's table.
+__device__ __forceinline__ void undistort_map(const agt_camera& cam, const agt_undistort& U, const short* __restrict__ tab, int x, int y,
+                                              int& sx, int& sy, short4& wt) {
   const int j = U.roi_x + x, Y = U.roi_y + y;
   const int y0 = (Y / U.stripe) * U.stripe, i = Y - y0;
   const double cy = U.ncy - (double)y0;                       // principal point of the stripe's new camera matrix
   // inverse of the upper-triangular new camera matrix [[fx s cx] [0 fy cy] [0 0 1]]
-  const double inv_ab = 1.0 / (U.nfx * U.nfy);
-  const double ir0 = 1.0 / U.nfx, ir1 = -U.nskew * inv_ab, ir2 = (U.nskew * cy - U.ncx * U.nfy) * inv_ab;
-  const double ir4 = 1.0 / U.nfy, ir5 = -cy / U.nfy;
+  // (the stripe-independent entries are correctly rounded quotients / one product: computed once on the host)
+  const double inv_ab = U.inv_ab, ir0 = U.ir0, ir1 = U.ir1, ir4 = U.ir4;
+  const double ir2 = (U.nskew * cy - U.ncx * U.nfy) * inv_ab, ir5 = -cy / U.nfy;
   const double px = (double)i * ir1 + ir2 + (double)j * ir0;
   const double py = (double)i * ir4 + ir5;
   const double x2 = px * px, y2 = py * py, r2 = x2 + y2, _2xy = 2.0 * px * py;
@@ -42,8 +46,19 @@ undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__
   const double xd = px * kr + cam.p1 * _2xy + cam.p2 * (r2 + 2.0 * x2);
   const double yd = py * kr + cam.p1 * (r2 + 2.0 * y2) + cam.p2 * _2xy;
   const int iu = __double2int_rn((cam.fx * xd + cam.cx) * 32.0), iv = __double2int_rn((cam.fy * yd + cam.cy) * 32.0);
-  const int sx = (int)(short)(iu >> 5), sy = (int)(short)(iv >> 5);       // CV_16SC2 integer part (the cast wraps)
-  const short4 wt = *reinterpret_cast<const short4*>(tab + 4 * ((iv & 31) * 32 + (iu & 31)));
+  sx = (int)(short)(iu >> 5); sy = (int)(short)(iv >> 5);       // CV_16SC2 integer part (the cast wraps)
+  wt = *reinterpret_cast<const short4*>(tab + 4 * ((iv & 31) * 32 + (iu & 31)));
+}
+
+__global__ void __launch_bounds__(128)
+undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__ tab, const uint8_t* __restrict__ src, int w, int h,
+                      int channels, int64_t spitch, int64_t sstride, uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride,
+                      int batch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= U.roi_w) return;
+  int sx, sy;
+  short4 wt;
+  undistort_map(cam, U, tab, x, y, sx, sy, wt);
   // taps outside the frame read the constant border 0: zero their weights instead of branching per load
   const bool x0ok = (unsigned)sx < (unsigned)w, x1ok = (unsigned)(sx + 1) < (unsigned)w;
   const bool y0ok = (unsigned)sy < (unsigned)h, y1ok = (unsigned)(sy + 1) < (unsigned)h;
@@ -86,6 +101,167 @@ undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__
     const int gray = channels == 3 ? (v[0] * 3735 + v[1] * 19235 + v[2] * 9798 + 16384) >> 15 : v[0];
     dst[(int64_t)b * dstride + (int64_t)y * dpitch + x] = (uint8_t)gray;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tiled variant: see the header comment.  256 threads, a 32x32 output tile, 4 pixels per thread (a warp = 32
+// consecutive pixels of one row, rows ty, ty+8, ty+16, ty+24), UT_GROUP frames per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int UT_TILE = 32, UT_THREADS = 256, UT_PX = 4, UT_STAGES = 3, UT_STAGE_BYTES = 8192;
+
+// Every pixel takes the same branch-free path: the top-left tap is clamped into the frame, the tap to its right is the
+// next pixel in memory and the tap row below is `dy` rows further (0 on the last row); taps that fall outside the frame
+// have weight 0 (BORDER_CONSTANT 0), and for sx == -1 (only the right-hand taps are inside) the weights move to the
+// left-hand slots, which then sit on column 0.  Pixels outside the crop keep weight 0 and are not stored.
+template <int CH>
+__global__ void __launch_bounds__(UT_THREADS, 4)
+undistort_gray_tiled_kernel(agt_camera cam, agt_undistort U, const short* __restrict__ tab, const uint8_t* __restrict__ src, int w, int h,
+                            int64_t spitch, int64_t sstride, uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride, int batch,
+                            int group) {
+  __shared__ __align__(16) uint8_t s_buf[UT_STAGES][UT_STAGE_BYTES];
+  __shared__ int s_box[4];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int x = blockIdx.x * UT_TILE + tx;
+  if (tid == 0) { s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1; }
+  __syncthreads();
+  // ---- the maps of this thread's pixels: packed weight pairs, clamped top-left tap, row step ------------------------
+  uint32_t wtop[UT_PX], wbot[UT_PX];
+  int tap[UT_PX];                          // cx0 | cy0 << 14 | dy << 28 | live << 29   (frames up to 16384 x 16384)
+  int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -1, by1 = -1;
+#pragma unroll
+  for (int k = 0; k < UT_PX; ++k) {
+    const int y = blockIdx.y * UT_TILE + ty + 8 * k;
+    tap[k] = 0; wtop[k] = 0; wbot[k] = 0;
+    if (x < U.roi_w && y < U.roi_h) {
+      int sx, sy;
+      short4 wt;
+      undistort_map(cam, U, tab, x, y, sx, sy, wt);
+      const bool x0ok = (unsigned)sx < (unsigned)w, x1ok = (unsigned)(sx + 1) < (unsigned)w;
+      const bool y0ok = (unsigned)sy < (unsigned)h, y1ok = (unsigned)(sy + 1) < (unsigned)h;
+      int w00 = x0ok && y0ok ? wt.x : 0, w01 = x1ok && y0ok ? wt.y : 0, w10 = x0ok && y1ok ? wt.z : 0, w11 = x1ok && y1ok ? wt.w : 0;
+      if (sx == -1) { w00 = w01; w01 = 0; w10 = w11; w11 = 0; }          // column 0 is the right-hand tap
+      const int cx0 = min(max(sx, 0), w - 1), cy0 = min(max(sy, 0), h - 1), cy1 = min(max(sy + 1, 0), h - 1);
+      wtop[k] = (uint32_t)w00 | ((uint32_t)w01 << 16); wbot[k] = (uint32_t)w10 | ((uint32_t)w11 << 16);
+      tap[k] = cx0 | (cy0 << 14) | ((cy1 - cy0) << 28) | (1 << 29);
+      bx0 = min(bx0, cx0); bx1 = max(bx1, min(cx0 + 1, w - 1)); by0 = min(by0, cy0); by1 = max(by1, cy1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bx0 = min(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); by0 = min(by0, __shfl_xor_sync(0xffffffffu, by0, o));
+    bx1 = max(bx1, __shfl_xor_sync(0xffffffffu, bx1, o)); by1 = max(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+  }
+  if (tx == 0) { atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0); atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1); }
+  __syncthreads();
+  bx0 = s_box[0]; by0 = s_box[1]; bx1 = s_box[2]; by1 = s_box[3];
+  if (bx1 < 0) return;                                       // no live pixel in this tile
+  const int b0 = blockIdx.z * group, nb = min(group, batch - b0);
+  const int xb0 = (bx0 * CH) & ~15, xb1 = ((bx1 + 1) * CH + 15) & ~15;      // staged byte range of a source row
+  const int P = xb1 - xb0 + 16, R = by1 - by0 + 1;          // 16 bytes of slack: the fetches below may read past a row's last tap
+  uint8_t* out = dst + (int64_t)b0 * dstride + (int64_t)(blockIdx.y * UT_TILE + ty) * dpitch + x;
+  const int64_t dp8 = 8 * dpitch;
+  if (R * P > UT_STAGE_BYTES) {
+    // the bounding box does not fit a stage (extreme distortion): the same taps from global memory
+    for (int b = 0; b < nb; ++b, out += dstride) {
+      const uint8_t* f = src + (int64_t)(b0 + b) * sstride;
+#pragma unroll
+      for (int k = 0; k < UT_PX; ++k) {
+        if (!(tap[k] >> 29 & 1)) continue;
+        const int cx0 = tap[k] & 0x3fff, cy0 = (tap[k] >> 14) & 0x3fff;
+        const uint8_t* t = f + (int64_t)cy0 * spitch + (int64_t)cx0 * CH;
+        const uint8_t* u = t + ((tap[k] >> 28) & 1) * spitch;
+        const int dxb = cx0 + 1 < w ? CH : 0;                // (the weight of a tap past the last column is 0)
+        const int w00 = wtop[k] & 0xffff, w01 = wtop[k] >> 16, w10 = wbot[k] & 0xffff, w11 = wbot[k] >> 16;
+        int v[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          v[c] = (w00 * __ldg(t + c) + w01 * __ldg(t + dxb + c) + w10 * __ldg(u + c) + w11 * __ldg(u + dxb + c) + (1 << 14)) >> 15;
+        const int gray = CH == 3 ? (v[0] * 3735 + v[1] * 19235 + v[CH - 1] * 9798 + 16384) >> 15 : v[0];
+        out[k * dp8] = (uint8_t)gray;
+      }
+    }
+    return;
+  }
+  // ---- per-pixel offsets inside a stage; staging plan of this thread (<= 2 chunks of 16 bytes per frame) ----------
+  uint32_t off[UT_PX];                     // bits 0-15: offset of the top-left tap, bits 16-31: offset of the tap row below
+  uint32_t live = 0;
+#pragma unroll
+  for (int k = 0; k < UT_PX; ++k) {
+    off[k] = 0;
+    if (tap[k] >> 29 & 1) {
+      const uint32_t o00 = (uint32_t)((((tap[k] >> 14) & 0x3fff) - by0) * P + (tap[k] & 0x3fff) * CH - xb0);
+      off[k] = o00 | ((o00 + ((tap[k] >> 28) & 1) * P) << 16);
+      live |= 1u << k;
+    }
+  }
+  const int cpr = (xb1 - xb0) >> 4, n_chunks = R * cpr;      // <= 512
+  const uint8_t* g_ptr[2];
+  uint32_t s_off[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int j = tid + UT_THREADS * q;
+    const int r = j / cpr, c = j - r * cpr;
+    g_ptr[q] = src + (int64_t)b0 * sstride + (int64_t)(by0 + r) * spitch + xb0 + 16 * c;
+    s_off[q] = j < n_chunks ? (uint32_t)(r * P + 16 * c) : 0xffffffffu;
+  }
+  const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(&s_buf[0][0]);
+  int issued = 0;
+  uint32_t issue_stage = buf0;
+  auto issue = [&]() {
+    if (issued < nb) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (s_off[q] != 0xffffffffu)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(issue_stage + s_off[q]), "l"(g_ptr[q]) : "memory");
+        g_ptr[q] += sstride;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    ++issued;
+    issue_stage = issue_stage == buf0 + (UT_STAGES - 1) * UT_STAGE_BYTES ? buf0 : issue_stage + UT_STAGE_BYTES;
+  };
+  issue();
+  issue();
+  uint32_t stage = buf0;
+  for (int b = 0; b < nb; ++b, out += dstride) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");    // frame b has landed (frame b+1 may still travel)
+    __syncthreads();                                         // ... for every thread; and the stage of frame b-1 is free again
+    issue();                                                 // frame b+2 into it
+#pragma unroll
+    for (int k = 0; k < UT_PX; ++k) {
+      const uint32_t o00 = stage + (off[k] & 0xffffu), o10 = stage + (off[k] >> 16);
+      uint32_t gray;
+      if (CH == 3) {
+        // the two taps of a row are six consecutive bytes B0 G0 R0 B1 G1 R1: three aligned word loads + two funnel shifts
+        // fetch them, one permute per channel puts (p0, p1) side by side and dp2a blends them with the pair of 16-bit weights
+        const uint32_t sh = (o00 & 3u) * 8u;                 // P % 4 == 0: both rows have the same misalignment
+        uint32_t t0, t1, t2, u0, u1, u2;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t0) : "r"(o00 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(t1) : "r"(o00 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(t2) : "r"(o00 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u0) : "r"(o10 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(u1) : "r"(o10 & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(u2) : "r"(o10 & ~3u));
+        const uint32_t tl = __funnelshift_r(t0, t1, sh), th = __funnelshift_r(t1, t2, sh);     // B0 G0 R0 B1 | G1 R1 . .
+        const uint32_t ul = __funnelshift_r(u0, u1, sh), uh = __funnelshift_r(u1, u2, sh);
+        const uint32_t wt = wtop[k], wb = wbot[k];
+        const uint32_t vb = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0030), __dp2a_lo(wt, __byte_perm(tl, th, 0x0030), 1u << 14)) >> 15;
+        const uint32_t vg = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0041), __dp2a_lo(wt, __byte_perm(tl, th, 0x0041), 1u << 14)) >> 15;
+        const uint32_t vr = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0052), __dp2a_lo(wt, __byte_perm(tl, th, 0x0052), 1u << 14)) >> 15;
+        gray = (vb * 3735u + vg * 19235u + vr * 9798u + 16384u) >> 15;
+      } else {
+        uint32_t p00, p01, p10, p11;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p00) : "r"(o00));
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p01) : "r"(o00));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p10) : "r"(o10));
+        asm volatile("ld.shared.u8 %0, [%1+1];" : "=r"(p11) : "r"(o10));
+        gray = (__dp2a_lo(wbot[k], p10 | (p11 << 8), __dp2a_lo(wtop[k], p00 | (p01 << 8), 1u << 14))) >> 15;
+      }
+      if (live >> k & 1) out[k * dp8] = (uint8_t)gray;
+    }
+    stage = stage == buf0 + (UT_STAGES - 1) * UT_STAGE_BYTES ? buf0 : stage + UT_STAGE_BYTES;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // cv::initInterTab2D(INTER_LINEAR, fixed point): float32 products scaled by 2^15, saturated to int16, the rounding
@@ -140,6 +316,7 @@ extern "C" int agt_set_undistort(agt_ctx* ctx, const double* new_K, int width, i
   }
   agt_undistort& U = ctx->und;
   U.nfx = new_K[0]; U.nskew = new_K[1]; U.ncx = new_K[2]; U.nfy = new_K[4]; U.ncy = new_K[5];
+  U.inv_ab = 1.0 / (U.nfx * U.nfy); U.ir0 = 1.0 / U.nfx; U.ir1 = -U.nskew * U.inv_ab; U.ir4 = 1.0 / U.nfy;
   int stripe = (1 << 12) / width;
   if (stripe < 1) stripe = 1;
   if (stripe > height) stripe = height;
@@ -160,6 +337,28 @@ extern "C" int agt_undistort_to_gray(agt_ctx* ctx, const uint8_t* d_src, int w, 
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_undistort_to_gray: frame is %dx%d but agt_set_undistort was given %dx%d", w, h, ctx->und.width, ctx->und.height);
   agt_camera cam = ctx->cam;
   if (!cam.has_dist) { cam.k1 = cam.k2 = cam.p1 = cam.p2 = cam.k3 = 0.0; }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)src_pitch | (uintptr_t)src_stride) & 15) == 0 &&
+                       w <= 16384 && h <= 16384;
+  if (aligned) {
+    // frames per CTA: the float64 pixel maps are computed once per CTA, so large batches amortise them over more frames
+    const int group = batch >= 128 ? 32 : 16;
+    const int groups = (batch + group - 1) / group;
+    for (int g0 = 0; g0 < groups; g0 += 65535) {
+      const int ng = groups - g0 < 65535 ? groups - g0 : 65535;
+      const int64_t f0 = (int64_t)g0 * group;
+      dim3 grid((ctx->und.roi_w + UT_TILE - 1) / UT_TILE, (ctx->und.roi_h + UT_TILE - 1) / UT_TILE, ng);
+      if (channels == 3)
+        undistort_gray_tiled_kernel<3><<<grid, UT_THREADS, 0, ctx->stream>>>(cam, ctx->und, ctx->d_remap_tab, d_src + f0 * src_stride, w, h,
+                                                                             src_pitch, src_stride, d_gray + f0 * dst_stride, dst_pitch,
+                                                                             dst_stride, (int)(batch - f0), group);
+      else
+        undistort_gray_tiled_kernel<1><<<grid, UT_THREADS, 0, ctx->stream>>>(cam, ctx->und, ctx->d_remap_tab, d_src + f0 * src_stride, w, h,
+                                                                             src_pitch, src_stride, d_gray + f0 * dst_stride, dst_pitch,
+                                                                             dst_stride, (int)(batch - f0), group);
+      AGT_LAUNCH_CHECK(ctx);
+    }
+    return AGT_OK;
+  }
   const int groups = (batch + kFramesPerThread - 1) / kFramesPerThread;
   for (int g0 = 0; g0 < groups; g0 += 65535) {
     const int ng = groups - g0 < 65535 ? groups - g0 : 65535;

@@ -601,7 +601,8 @@ def test_undistort_ingest_bit_exact(lib_built, w, h, f):
         ctx = AgtContext(0, mtx, dist)
         try:
             ctx.set_undistort(new_mtx, w, h, roi)
-            for n, shape in ((11, (h, w, 3)), (3, (h, w))):          # 11 frames: two groups of the per-thread frame loop
+            # 11 / 37 frames: a partial group and three groups (the last one partial) of the per-CTA frame loop
+            for n, shape in ((11, (h, w, 3)), (3, (h, w))) + (((37, (h, w, 3)),) if w == 640 else ()):
                 frames = rng.integers(0, 256, (n,) + shape, dtype=np.uint8)
                 frames[0] = cv2.GaussianBlur(frames[0], (0, 0), 3.0)
                 pyr = ctx.alloc_pyramid(n, rw, rh, 1)
@@ -611,6 +612,18 @@ def test_undistort_ingest_bit_exact(lib_built, w, h, f):
                     want = cv2.undistort(frames[b], mtx, dist, None, new_mtx)[y:y + rh, x:x + rw]
                     want = cv2.cvtColor(want, cv2.COLOR_BGR2GRAY) if want.ndim == 3 else want
                     assert np.array_equal(got[b], want), (w, h, b, int(np.abs(got[b].astype(int) - want.astype(int)).max()))
+            # a new camera matrix that zooms out three times: the source box of a 32x32 tile no longer fits a shared-memory
+            # stage, so the tiles take the global-memory path; and one that zooms in (boxes of a few pixels)
+            for zoom in (1.0 / 3.0, 2.5):
+                zk = np.array([[f * zoom, 0, w / 2], [0, f * zoom, h / 2], [0, 0, 1]])
+                ctx.set_undistort(zk, w, h, (0, 0, w, h))
+                frames = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+                pyr = ctx.alloc_pyramid(2, w, h, 1)
+                ctx.ingest_undistort(pyr, frames)
+                got = pyr.frames.cpu().numpy()
+                for b in range(2):
+                    want = cv2.cvtColor(cv2.undistort(frames[b], mtx, dist, None, zk), cv2.COLOR_BGR2GRAY)
+                    assert np.array_equal(got[b], want), (w, h, zoom, b)
         finally:
             ctx.close()
         host = HostContext(0)
