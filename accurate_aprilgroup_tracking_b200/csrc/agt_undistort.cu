@@ -245,8 +245,10 @@ undistort_gray_tiled_kernel(agt_camera cam, agt_undistort U, const short* __rest
         const uint32_t tl = __funnelshift_r(t0, t1, sh), th = __funnelshift_r(t1, t2, sh);     // B0 G0 R0 B1 | G1 R1 . .
         const uint32_t ul = __funnelshift_r(u0, u1, sh), uh = __funnelshift_r(u1, u2, sh);
         const uint32_t wt = wtop[k], wb = wbot[k];
-        const uint32_t vb = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0030), __dp2a_lo(wt, __byte_perm(tl, th, 0x0030), 1u << 14)) >> 15;
-        const uint32_t vg = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0041), __dp2a_lo(wt, __byte_perm(tl, th, 0x0041), 1u << 14)) >> 15;
+        // (B0 B1 G0 G1) in one word serves the blue (low half) and green (high half) blends
+        const uint32_t tbg = __byte_perm(tl, th, 0x4130), ubg = __byte_perm(ul, uh, 0x4130);
+        const uint32_t vb = __dp2a_lo(wb, ubg, __dp2a_lo(wt, tbg, 1u << 14)) >> 15;
+        const uint32_t vg = __dp2a_hi(wb, ubg, __dp2a_hi(wt, tbg, 1u << 14)) >> 15;
         const uint32_t vr = __dp2a_lo(wb, __byte_perm(ul, uh, 0x0052), __dp2a_lo(wt, __byte_perm(tl, th, 0x0052), 1u << 14)) >> 15;
         gray = (vb * 3735u + vg * 19235u + vr * 9798u + 16384u) >> 15;
       } else {

@@ -331,8 +331,11 @@ def run_gpu(args):
         hctx = HostContext(local)
         s, tg, n, c = synth.surface_model()
         hctx.set_model(s, tg, n, c, synth.model_pitch())
-        host_frames = torch.empty((B, CAM.height, CAM.width), dtype=torch.uint8, pin_memory=True)
-        host_frames.copy_(pyr.frames)
+        # the pinned frames of a rank live on the NUMA node of its GPU (one process per GPU: first-touch allocation)
+        from accurate_aprilgroup_tracking_b200 import sharding as _sh
+        with _sh.on_gpu_numa_node(local) as numa:
+            host_frames = torch.empty((B, CAM.height, CAM.width), dtype=torch.uint8, pin_memory=True)
+            host_frames.copy_(pyr.frames)
         torch.cuda.synchronize()
         hf = host_frames.numpy()
         e2e_steps = max(3, min(args.steps, 5))
@@ -353,7 +356,8 @@ def run_gpu(args):
         e2e = {"value": B * world / e2e_s, "unit": "poses/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(B * (48 + 4 + 4 + 4 + 1 + 1)), "ms_per_step": 1e3 * e2e_s,
                "max_abs_diff_vs_device_path": same, "host_frame_bytes_per_step": int(B * CAM.width * CAM.height),
-               "note": "agt_refine_host on pinned host frames, all ranks concurrently, max over ranks; per frame only the "
+               "host_numa_node": numa,
+               "note": "agt_refine_host on pinned host frames (allocated on the NUMA node of the rank's GPU), all ranks concurrently, max over ranks; per frame only the "
                        "rectangle the refinement can read is copied (frames that leave it are redone from the full frame)"}
         hctx.close()
         del host_frames

@@ -189,3 +189,33 @@ def test_gather_poses_gloo_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_numa_binding_helpers(tmp_path, monkeypatch):
+    """sharding.on_gpu_numa_node: sysfs cpulist parsing, the CPU set is restored afterwards, unknown topology is a no-op."""
+    import os
+    import types
+    from accurate_aprilgroup_tracking_b200 import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    # no GPU here: the topology is unknown and nothing changes
+    with sharding.on_gpu_numa_node(0, sysfs=str(tmp_path)) as node:
+        assert node is None and os.sched_getaffinity(0) == before
+    # a fake sysfs tree + device properties: the thread runs on the node's CPUs inside the block only
+    import torch
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    nd = tmp_path / "devices/system/node/node1"
+    nd.mkdir(parents=True)
+    one = min(before)
+    (nd / "cpulist").write_text(f"{one}\n")
+    with sharding.on_gpu_numa_node(0, sysfs=str(tmp_path)) as node:
+        assert node == 1 and os.sched_getaffinity(0) == {one}
+    assert os.sched_getaffinity(0) == before
+    (dev / "numa_node").write_text("-1\n")
+    with sharding.on_gpu_numa_node(0, sysfs=str(tmp_path)) as node:
+        assert node is None
