@@ -357,7 +357,7 @@ def run_gpu(args):
                "d2h_bytes_per_step": int(B * (48 + 4 + 4 + 4 + 1 + 1)), "ms_per_step": 1e3 * e2e_s,
                "max_abs_diff_vs_device_path": same, "host_frame_bytes_per_step": int(B * CAM.width * CAM.height),
                "host_numa_node": numa,
-               "note": "agt_refine_host on pinned host frames (allocated on the NUMA node of the rank's GPU), all ranks concurrently, max over ranks; per frame only the "
+               "note": "agt_refine_host on pinned host frames (allocated on the NUMA node of the rank's GPU when the host exposes one: host_numa_node), all ranks concurrently, max over ranks; per frame only the "
                        "rectangle the refinement can read is copied (frames that leave it are redone from the full frame)"}
         hctx.close()
         del host_frames
@@ -574,9 +574,11 @@ def run_streams(args):
         det_img.append(torch.as_tensor(a, device=ctx.tdev)); det_valid.append(torch.as_tensor(b, device=ctx.tdev))
         det_n.append(torch.as_tensor(c, device=ctx.tdev))
     bank_frames = bank.frames.reshape(F, S, CAM.height, CAM.width)
-    gathered = torch.empty((S_total, 6), dtype=torch.float64, device=ctx.tdev)
+    holder = {}
 
     bpd = BatchedPoseDetector(ctx, S, CAM.width, CAM.height, synth.object_points())
+
+    hist = torch.zeros((S, F, 6), dtype=torch.float64, device=ctx.tdev)     # every stream's poses, frame by frame
 
     def run_sequence():
         bpd.reset()
@@ -584,9 +586,11 @@ def run_streams(args):
         for f in range(F):
             bpd.frames.copy_(bank_frames[f])                            # frame ingest (device to device)
             out = bpd.step(det_img[f], det_valid[f], det_n[f])
-            if world > 1:
-                sharding.gather_stream_poses(out["pose"], S_total)      # NCCL: final poses only
+            hist[:, f].copy_(out["pose"])
             acc = out
+        if world > 1:
+            # NCCL: the final poses only - one all-gather of the whole sequence ([streams, frames x 6]), nothing per frame
+            holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), S_total)
         return acc
 
     run_sequence()
@@ -614,7 +618,7 @@ def run_streams(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
             "config": {"workload": "64 concurrent 1080p camera streams, predictor -> PnP / LK fallback -> dense refinement per frame",
                        "streams": S_total, "frames_per_stream": F, "step": "one pass over all frames of all streams",
-                       "parallelism": f"streams s mod {world} -> GPU; per-frame NCCL all-gather of poses"},
+                       "parallelism": f"streams s mod {world} -> GPU; one NCCL all-gather of all poses at the end of the sequence"},
             "gpu_launches": int(launches), "kernels_per_frame_step": int(bpd.kernels_per_step), "cuda_graphs": True,
             "ms_per_frame_step": ms / args.steps / F,
             "final_frame_median_trans_err_m": float(np.median(dt)), "accepted_frac_last": float(out["accepted"].float().mean())}), flush=True)

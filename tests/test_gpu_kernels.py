@@ -632,3 +632,32 @@ def test_undistort_ingest_bit_exact(lib_built, w, h, f):
         assert np.array_equal(host.undistort_gray(frame, mtx, dist, new_mtx, roi), want)
         host.close()
 
+
+
+def test_undistort_ingest_large_batch(lib_built):
+    """Batches of 128 frames and more use 32 frames per CTA (fewer pixel-map evaluations): same bits as cv2 and as the
+    16-frame grouping of a smaller batch."""
+    import cv2
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    w, h, f = 320, 200, 280.0
+    rng = np.random.default_rng(77)
+    mtx = np.array([[f, 0, w / 2 - 1.7], [0, f, h / 2 + 0.9], [0, 0, 1]])
+    dist = np.array([[-0.31, 0.12, 0.001, -0.0007, -0.03]])
+    new_mtx, roi = cv2.getOptimalNewCameraMatrix(mtx, dist, (w, h), 1, (w, h))
+    x, y, rw, rh = roi
+    ctx = AgtContext(0, mtx, dist)
+    try:
+        ctx.set_undistort(new_mtx, w, h, roi)
+        n = 150                                                    # 4 full groups of 32 + one of 22
+        frames = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        big = ctx.alloc_pyramid(n, rw, rh, 1)
+        ctx.ingest_undistort(big, frames)
+        got = big.frames.cpu().numpy()
+        small = ctx.alloc_pyramid(100, rw, rh, 1)
+        ctx.ingest_undistort(small, frames[:100])
+        assert np.array_equal(small.frames.cpu().numpy(), got[:100])
+        for b in (0, 31, 32, 127, 128, 149):
+            want = cv2.cvtColor(cv2.undistort(frames[b], mtx, dist, None, new_mtx)[y:y + rh, x:x + rw], cv2.COLOR_BGR2GRAY)
+            assert np.array_equal(got[b], want), b
+    finally:
+        ctx.close()
