@@ -20,15 +20,16 @@
 
 namespace {
 
-// rows of the staging loops that are unrolled (global loads in flight per lane): 6 / 4 measured best under the 64-register
-// cap (profiles/r01_lk_variants.log)
-constexpr int kPatchUnroll = 6, kRegionUnroll = 4;
 constexpr int WIN = 21;
 constexpr int PATCH = WIN + 3;             // 24: template footprint incl. bilinear + Scharr halo
 constexpr int DER = WIN + 1;               // 22
 constexpr int REG = 32;                    // staged search region
 constexpr int REG_MARGIN = 5;              // window offset inside a freshly staged region
-constexpr int WARPS_PER_CTA = 4;
+// Shared-memory rows of the two staged footprints hold the aligned 32-bit words that cover the footprint's columns (the
+// footprint starts `x & 3` bytes into the row): 7 words for 24 columns, 9 for 32.  An odd number of words per row also
+// spreads the rows of a window over all banks (rows of 8 words put every fourth row on the same banks).
+constexpr int PATCH_PITCH = 28, REG_PITCH = 36;
+constexpr int WARPS_PER_CTA = 8;          // 4 CTAs of 8 warps fit an SM's shared memory (1 KB is reserved per CTA), 8 of 4 no longer do
 constexpr int W_BITS = 14;
 constexpr int MAX_ITERS = 30;
 
@@ -44,12 +45,11 @@ constexpr int NSLOT = 32 * PIX_PER_LANE;   // 448 >= 441
 struct __align__(16) WarpSmem {
   union {
     struct {
-      uint8_t patch[PATCH][PATCH];         // prev level, origin (ix-1, iy-1)
+      __align__(16) uint8_t patch[PATCH * PATCH_PITCH];       // prev level, origin (ix-1, iy-1) at byte `x offset` of row 0
       short2 der[DER][DER];                // Scharr at (ix..ix+21, iy..iy+21)
     } t;
     struct {
-      __align__(16) uint8_t px[REG][REG];  // next level search region
-      uint32_t pad[2];                     // the third word of a run in the last row
+      __align__(16) uint8_t px[REG * REG_PITCH + 12];       // next level search region (+ the third word of a run in the last row)
     } region;
   } u;
   __align__(16) int2 dd[NSLOT];            // template derivative (dx, dy), lane-major
@@ -121,14 +121,39 @@ __device__ __forceinline__ int blend(const Run& t, const Run& b, uint32_t wt, ui
   return (int)(acc >> (W_BITS - 5));
 }
 
-__device__ __forceinline__ void stage_region(uint8_t (*region)[REG], const uint8_t* __restrict__ img, int cols, int rows,
-                                             int64_t pitch, int rx0, int ry0, int lane) {
-  int gx = reflect_fast(rx0 + lane, cols);
-#pragma unroll (kRegionUnroll)
-  for (int r = 0; r < REG; ++r) {
-    int gy = reflect_fast(ry0 + r, rows);
-    region[r][lane] = __ldg(img + (int64_t)gy * pitch + gx);
+// Stage the footprint [x0, x0 + W) x [y0, y0 + ROWS) of one level into shared memory and return the byte offset of
+// column x0 inside a shared-memory row.  Footprints inside the image (4-byte aligned rows) travel as aligned words by
+// cp.async: every request of the footprint is in flight at once and no register waits for it.  Footprints cut by the
+// image border are gathered byte by byte with BORDER_REFLECT_101 (a lane per column).  The caller waits.
+template <int W, int ROWS, int WORDS, int SPITCH>
+__device__ __forceinline__ int stage_footprint(uint8_t* smem, const uint8_t* __restrict__ img, int cols, int rows, int64_t pitch,
+                                               int x0, int y0, int lane) {
+  static_assert((WORDS == 9 || WORDS == 7) && WORDS * 4 == SPITCH && WORDS * 4 >= W + 3, "row of aligned words");
+  if (x0 >= 0 && y0 >= 0 && x0 + W <= cols && y0 + ROWS <= rows && ((pitch | reinterpret_cast<uintptr_t>(img)) & 3) == 0) {
+    const int xa = x0 & ~3, nw = ((x0 + W - 1) >> 2) - (x0 >> 2) + 1;
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint8_t* src = img + (int64_t)y0 * pitch + xa;
+#pragma unroll
+    for (int q = 0; q < (ROWS * WORDS + 31) / 32; ++q) {
+      const int i = lane + 32 * q;
+      const int r = WORDS == 9 ? (i * 57) >> 9 : (i * 147) >> 10;      // i / WORDS for i < 288 (9) / 192 (7)
+      const int k = i - r * WORDS;
+      if (r < ROWS && k < nw)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + r * SPITCH + 4 * k), "l"(src + (int64_t)r * pitch + 4 * k) : "memory");
+    }
+    return x0 & 3;
   }
+  const int gx = reflect_fast(x0 + (lane < W ? lane : 0), cols);
+#pragma unroll 4
+  for (int r = 0; r < ROWS; ++r) {
+    const int gy = reflect_fast(y0 + r, rows);
+    if (lane < W) smem[r * SPITCH + lane] = __ldg(img + (int64_t)gy * pitch + gx);
+  }
+  return 0;
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 }
 
 // Region-of-interest pyramids (agt_build_pyramid_roi): a pixel of level l >= 1 is exact iff the level-0 support of its
@@ -216,27 +241,23 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
     }
     __syncwarp();
     // ---- stage the 24x24 template footprint (reflect-101 intensity) -------------
-    {
-      // a lane per column (its reflected source column is computed once), the row index is warp-uniform
-      const int gx = reflect_fast(ix - 1 + (lane < PATCH ? lane : 0), cols);
-#pragma unroll (kPatchUnroll)
-      for (int r = 0; r < PATCH; ++r) {
-        const int gy = reflect_fast(iy - 1 + r, rows);
-        if (lane < PATCH) S.u.t.patch[r][lane] = __ldg(imgI + (int64_t)gy * pitchI + gx);
-      }
-    }
-    __syncwarp();
+    const int pxo = stage_footprint<PATCH, PATCH, 7, PATCH_PITCH>(S.u.t.patch, imgI, cols, rows, pitchI, ix - 1, iy - 1, lane);
+    stage_wait();
     // ---- Scharr at the 22x22 integer positions; zero outside the image -------------
     if (ix >= 0 && iy >= 0 && ix + DER <= cols && iy + DER <= rows) {
       // window inside the image (warp-uniform): a lane per row reads the three footprint rows as aligned words and
       // forms every derivative with chained dp4a ([3 10 3] folded into the byte coefficients), no per-tap byte loads
       if (lane < DER) {
         uint32_t w[3][PATCH / 4];
+        const uint32_t psh = (uint32_t)pxo * 8u;
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
-          const uint2* src = reinterpret_cast<const uint2*>(&S.u.t.patch[lane + rr][0]);      // 24-byte rows: 8 B aligned
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.u.t.patch[(lane + rr) * PATCH_PITCH]);      // 7 aligned words
+          uint32_t t[PATCH / 4 + 1];
 #pragma unroll
-          for (int q = 0; q < PATCH / 8; ++q) { const uint2 v = src[q]; w[rr][2 * q] = v.x; w[rr][2 * q + 1] = v.y; }
+          for (int q = 0; q <= PATCH / 4; ++q) t[q] = src[q];
+#pragma unroll
+          for (int q = 0; q < PATCH / 4; ++q) w[rr][q] = __funnelshift_r(t[q], t[q + 1], psh);
         }
 #pragma unroll
         for (int c = 0; c < DER; ++c) {
@@ -265,10 +286,10 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
       int gx = ix + c, gy = iy + r;
       short2 d = make_short2(0, 0);
       if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-        const uint8_t(*p)[PATCH] = S.u.t.patch;
-        int a00 = p[r][c], a01 = p[r][c + 1], a02 = p[r][c + 2];
-        int a10 = p[r + 1][c], a12 = p[r + 1][c + 2];
-        int a20 = p[r + 2][c], a21 = p[r + 2][c + 1], a22 = p[r + 2][c + 2];
+        const uint8_t* p = S.u.t.patch + r * PATCH_PITCH + pxo + c;
+        int a00 = p[0], a01 = p[1], a02 = p[2];
+        int a10 = p[PATCH_PITCH], a12 = p[PATCH_PITCH + 2];
+        int a20 = p[2 * PATCH_PITCH], a21 = p[2 * PATCH_PITCH + 1], a22 = p[2 * PATCH_PITCH + 2];
         d.x = (short)(3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
         d.y = (short)(3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
       }
@@ -282,14 +303,14 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
     segment_of(lane, 1, seg_row[1], seg_col[1]);
     int s11 = 0, s12 = 0, s22 = 0;
     int c1 = 0, c2 = 0;                          // sum of template * derivative: lets the search loop skip the template
-    const uint32_t patch_a = (uint32_t)__cvta_generic_to_shared(&S.u.t.patch[0][0]);
+    const uint32_t patch_a = (uint32_t)__cvta_generic_to_shared(&S.u.t.patch[0]) + pxo;
     const uint32_t wtI = (uint32_t)w.w00 | ((uint32_t)w.w01 << 16), wbI = (uint32_t)w.w10 | ((uint32_t)w.w11 << 16);
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg) {
       const bool live = seg_row[sg] < WIN;
       const int y = live ? seg_row[sg] : WIN - 1, x0 = seg_col[sg];
       // the run's template intensities: rows y+1, y+2 of the footprint from column x0+1, blended as in the search loop
-      const Run t = load_run(patch_a + (y + 1) * PATCH + x0 + 1), bt = load_run(patch_a + (y + 2) * PATCH + x0 + 1);
+      const Run t = load_run(patch_a + (y + 1) * PATCH_PITCH + x0 + 1), bt = load_run(patch_a + (y + 2) * PATCH_PITCH + x0 + 1);
       int ivs[SEG_LEN];
       ivs[0] = blend<0>(t, bt, wtI, wbI); ivs[1] = blend<1>(t, bt, wtI, wbI); ivs[2] = blend<2>(t, bt, wtI, wbI);
       ivs[3] = blend<3>(t, bt, wtI, wbI); ivs[4] = blend<4>(t, bt, wtI, wbI); ivs[5] = blend<5>(t, bt, wtI, wbI);
@@ -327,10 +348,11 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
     D = __fdiv_rn(1.f, D);
     __syncwarp();      // template footprint no longer needed: the region buffer may overwrite it
 
-    const uint32_t region_a = (uint32_t)__cvta_generic_to_shared(&S.u.region.px[0][0]);
+    const uint32_t region_a = (uint32_t)__cvta_generic_to_shared(&S.u.region.px[0]);
+    int rxo = 0;                               // byte offset of column rx0 inside a staged row
     // shared-memory offset of each run inside the region for a window at (0, 0); disabled runs read a valid row
-    const int run_off0 = (seg_row[0] < WIN ? seg_row[0] : WIN - 1) * REG + seg_col[0];
-    const int run_off1 = (seg_row[1] < WIN ? seg_row[1] : WIN - 1) * REG + seg_col[1];
+    const int run_off0 = (seg_row[0] < WIN ? seg_row[0] : WIN - 1) * REG_PITCH + seg_col[0];
+    const int run_off1 = (seg_row[1] < WIN ? seg_row[1] : WIN - 1) * REG_PITCH + seg_col[1];
     const int4* ddp = reinterpret_cast<const int4*>(&S.dd[lane * PIX_PER_LANE]);      // two pixels per 128-bit load
 
     nx = __fsub_rn(nx, 10.f); ny = __fsub_rn(ny, 10.f);
@@ -350,19 +372,19 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
           const int4 wn = *reinterpret_cast<const int4*>(S.win);
           if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
         }
-        stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+        rxo = stage_footprint<REG, REG, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
         staged = true;
-        __syncwarp();
+        stage_wait();
       }
       Weights wj = make_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
       const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
-      const uint32_t win_a = region_a + (jy - ry0) * REG + (jx - rx0);
+      const uint32_t win_a = region_a + (jy - ry0) * REG_PITCH + (jx - rx0) + rxo;
       // b = sum (J - I) dI = sum J dI - sum I dI: exact integers, the second sum is C1, C2
       int sb1 = 0, sb2 = 0;
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {
         const uint32_t a = win_a + (sg == 0 ? run_off0 : run_off1);
-        const Run t = load_run(a), bt = load_run(a + REG);
+        const Run t = load_run(a), bt = load_run(a + REG_PITCH);
         int jv[SEG_LEN];
         jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
         jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
@@ -403,18 +425,18 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
             const int4 wn = *reinterpret_cast<const int4*>(S.win);
             if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
           }
-          stage_region(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
-          __syncwarp();
+          rxo = stage_footprint<REG, REG, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+          stage_wait();
         }
         Weights wj = make_weights(__fsub_rn(ex, (float)jx), __fsub_rn(ey, (float)jy));
         const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
-        const uint32_t win_a = region_a + (jy - ry0) * REG + (jx - rx0);
+        const uint32_t win_a = region_a + (jy - ry0) * REG_PITCH + (jx - rx0) + rxo;
         int sabs = 0;
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
           if (seg_row[sg] >= WIN) continue;
           const uint32_t a = win_a + (sg == 0 ? run_off0 : run_off1);
-          const Run t = load_run(a), bt = load_run(a + REG);
+          const Run t = load_run(a), bt = load_run(a + REG_PITCH);
           int jv[SEG_LEN];
           jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
           jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
@@ -442,13 +464,14 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
 // frames flagged, usually none) use a small grid whose warps stride over the corners and leave after one pass over the
 // mask when nothing is flagged, instead of launching tens of thousands of CTAs that have nothing to do.
 template <bool kRoi, bool kStride>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 8)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
           uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, int64_t total,
           const int32_t* __restrict__ skip_if_tags_ge2, const int32_t* __restrict__ rects_prev,
           const int32_t* __restrict__ rects_next, int rect_stride, const uint8_t* __restrict__ mask,
           uint8_t* __restrict__ left_roi_out) {
-  __shared__ WarpSmem smem[WARPS_PER_CTA];
+  extern __shared__ __align__(16) uint8_t lk_smem_raw[];      // WARPS_PER_CTA x WarpSmem (more than the 48 KB static limit)
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(lk_smem_raw);
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   if (!kStride) {
@@ -614,8 +637,17 @@ static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* nex
   const bool stride = d_mask != nullptr && blocks > 8LL * ctx->sm_count;
   if (stride) blocks = 8LL * ctx->sm_count;      // warps stride over the corners
   const bool roi = d_rects_prev || d_rects_next;
+  constexpr int kSmem = WARPS_PER_CTA * (int)sizeof(WarpSmem);
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    AGT_CUDA(ctx, cudaFuncSetAttribute(lk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(lk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(lk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    AGT_CUDA(ctx, cudaFuncSetAttribute(lk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set[ctx->device & 63] = true;
+  }
 #define AGT_LK_LAUNCH(R, S)                                                                                                     \
-  lk_kernel<R, S><<<(unsigned)blocks, WARPS_PER_CTA * 32, 0, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status, d_err, \
+  lk_kernel<R, S><<<(unsigned)blocks, WARPS_PER_CTA * 32, kSmem, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status, d_err, \
                                                                             n_pts, total, d_n_tags, d_rects_prev, d_rects_next,   \
                                                                             rect_stride, d_mask, d_left_roi)
   if (roi) { if (stride) AGT_LK_LAUNCH(true, true); else AGT_LK_LAUNCH(true, false); }
