@@ -305,8 +305,12 @@ static int pyr_down_impl(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64
     int col_blocks = (ow + 32 * lane_outs - 1) / (32 * lane_outs), strips = (oh + kStrip - 1) / kStrip;
     int64_t total_warps = (int64_t)batch * strips * col_blocks;
     int64_t blocks = (total_warps + PF_WARPS - 1) / PF_WARPS;
-    const bool stride_items = d_mask != nullptr && blocks > 8LL * ctx->sm_count;
-    if (stride_items) blocks = 8LL * ctx->sm_count;                    // warps stride over the items
+    // Masked launches (few frames flagged) and region-of-interest launches (most items of a level lie outside the frame's
+    // rectangle) use a grid that just fills the machine; its warps stride over the items, so every resident warp keeps
+    // finding real strips instead of whole CTAs holding their slots for one live warp.
+    const int64_t fill = (int64_t)(d_mask != nullptr ? 8 : (wide ? 4 : 6)) * ctx->sm_count;
+    const bool stride_items = (d_mask != nullptr || d_rects != nullptr) && blocks > fill;
+    if (stride_items) blocks = fill;
     if (blocks <= 0x7fffffffLL) {
 #define AGT_PYR_LAUNCH(Q, NWv, ST)                                                                                        \
   pyr_down_stream_kernel<Q, kStrip, NWv, ST><<<(unsigned)blocks, PF_WARPS * 32, 0, ctx->stream>>>(                          \
