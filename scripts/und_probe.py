@@ -1,6 +1,10 @@
 """One timed (or profiled) run of the undistort ingest on 256 x 1080p BGR frames."""
 import sys, numpy as np, torch, cv2
 sys.path.insert(0, '.')
+if len(sys.argv) > 1:
+    from pathlib import Path
+    from accurate_aprilgroup_tracking_b200 import _lib
+    _lib.LIB_PATH = Path(sys.argv[1]).resolve()
 from accurate_aprilgroup_tracking_b200 import synth
 from accurate_aprilgroup_tracking_b200.context import AgtContext
 cam = synth.CAMERA_1080P
@@ -18,4 +22,6 @@ for _ in range(10): ctx.ingest_undistort(pu, bgr)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 byt = nb * (cam.width * cam.height * 3 + roi[2] * roi[3])
-print(f"undistort_to_gray: {ms:.3f} ms for {nb} 1080p BGR frames (roi {roi[2]}x{roi[3]}) -> {nb/ms*1e3:.3e} frames/s, {byt/ms/1e6:.0f} GB/s ({byt/ms/1e6/6550.1:.2f} of measured HBM peak)")
+import hashlib
+h = hashlib.sha256(pu.frames.cpu().numpy().tobytes()).hexdigest()[:12]
+print(f"{sys.argv[1] if len(sys.argv) > 1 else 'libagt.so'} [{h}] undistort_to_gray: {ms:.3f} ms for {nb} 1080p BGR frames (roi {roi[2]}x{roi[3]}) -> {nb/ms*1e3:.3e} frames/s, {byt/ms/1e6:.0f} GB/s ({byt/ms/1e6/6550.1:.2f} of measured HBM peak)")
