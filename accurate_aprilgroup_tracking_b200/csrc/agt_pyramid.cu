@@ -204,6 +204,46 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
 #undef AGT_ITEM_DONE
 }
 
+// Region-of-interest pyramid of a batch in ONE launch: a CTA per frame walks down the levels, its four warps share the rows
+// of the frame's window at each level (one strip per warp, so the warps finish together) and meet at a barrier before the
+// next level reads what they wrote (from L2).  Per-level launches leave most of the machine idle on these small windows:
+// a 600 x 580 rectangle is 10 + 5 + 3 strips per frame, three short launches with their tails, each warp striding over a
+// handful of live items (profiles/r01_ncu_pyr_roi.txt).  Same streaming warp routine, same bits.
+template <int Q2, int Q1>
+__global__ void __launch_bounds__(PF_WARPS * 32, 4)
+pyr_roi_chain_kernel(agt_pyramid pyr, const int32_t* __restrict__ rects, int rect_stride, int batch, uint32_t wide_mask) {
+  constexpr int RPITCH2 = 16 + 16 * 2 * 32 + 16, RING2 = Q2 + 4, RPITCH1 = 16 + 16 * 32 + 16, RING1 = Q1 + 4;
+  constexpr int RING_BYTES = RPITCH2 * RING2 > RPITCH1 * RING1 ? RPITCH2 * RING2 : RPITCH1 * RING1;
+  __shared__ __align__(16) uint8_t s_ring[PF_WARPS][RING_BYTES];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&s_ring[wid][0]);
+  for (int frame = blockIdx.x; frame < batch; frame += gridDim.x) {
+    const int32_t* r = rects + (int64_t)frame * rect_stride;
+    const int r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+    if (r2 <= r0 || r3 <= r1) continue;                    // (the whole CTA)
+    for (int l = 1; l < pyr.levels; ++l) {
+      const int w = pyr.width[l - 1], h = pyr.height[l - 1], ow = pyr.width[l], oh = pyr.height[l];
+      const bool wide = (wide_mask >> l) & 1u;
+      const int outs = wide ? 16 : 8, rnd = (1 << l) - 1;
+      // the window of pyr_down_stream_kernel for src_level = l - 1
+      const int xo0 = max(0, (r0 >> l) - 2) & ~(outs - 1), yo0 = max(0, (r1 >> l) - 2);
+      const int xo1 = min(ow, (((r2 + rnd) >> l) + 2 + 7) & ~7), yo1 = min(oh, ((r3 + rnd) >> l) + 2);
+      const uint8_t* img = pyr.data[l - 1] + (int64_t)frame * pyr.frame_stride[l - 1];
+      uint8_t* out = pyr.data[l] + (int64_t)frame * pyr.frame_stride[l];
+      const int per = (yo1 - yo0 + PF_WARPS - 1) / PF_WARPS;
+      const int oy0 = yo0 + wid * per, oy1 = min(oy0 + per, yo1);
+      if (oy0 < oy1) {
+        for (int bx = xo0; bx < xo1; bx += 32 * outs) {
+          if (wide) agt_pyr_down_strip<Q2, 2>(img, w, h, pyr.pitch[l - 1], out, pyr.pitch[l], bx + lane * 16, xo1, oy0, oy1, lane, ring0);
+          else      agt_pyr_down_strip<Q1, 1>(img, w, h, pyr.pitch[l - 1], out, pyr.pitch[l], bx + lane * 8, xo1, oy0, oy1, lane, ring0);
+          __syncwarp();
+        }
+      }
+      __syncthreads();                                     // level l of this frame is complete (and visible) before level l + 1 reads it
+    }
+  }
+}
+
 // Scharr: one thread per pixel pair; loads go through L1.  Not on the hot path
 // (the LK and refinement kernels derive gradients on the fly from the u8 levels);
 // exported so the derivative planes themselves can be checked bit-exactly.
@@ -346,6 +386,27 @@ static int build_pyramid_impl(agt_ctx* ctx, const agt_pyramid* pyr, int batch, c
                               const uint8_t* d_mask, int mask_stride) {
   if (!pyr || pyr->levels < 1 || pyr->levels > AGT_MAX_LEVELS)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: bad pyramid descriptor");
+  // region-of-interest builds of batches that fill the machine: all levels in one launch, a CTA per frame
+  if (d_rects != nullptr && d_mask == nullptr && batch >= 2 * ctx->sm_count && pyr->levels > 1) {
+    bool ok = true;
+    uint32_t wide_mask = 0;
+    for (int l = 1; l < pyr->levels && ok; ++l) {
+      const int w = pyr->width[l - 1], h = pyr->height[l - 1], ow = pyr->width[l];
+      ok = pyr->data[l - 1] && pyr->data[l] && ow == (w + 1) / 2 && pyr->height[l] == (h + 1) / 2 && (w & 15) == 0 && w >= 16 && h >= 4 &&
+           ((reinterpret_cast<uintptr_t>(pyr->data[l - 1]) | (uintptr_t)pyr->pitch[l - 1] | (uintptr_t)pyr->frame_stride[l - 1]) & 15) == 0 &&
+           ((reinterpret_cast<uintptr_t>(pyr->data[l]) | (uintptr_t)pyr->pitch[l] | (uintptr_t)pyr->frame_stride[l]) & 7) == 0 &&
+           pyr->pitch[l - 1] >= w && pyr->pitch[l] >= ow;
+      const bool wide = ow >= 320 && ((reinterpret_cast<uintptr_t>(pyr->data[l]) | (uintptr_t)pyr->pitch[l] | (uintptr_t)pyr->frame_stride[l]) & 15) == 0;
+      if (wide) wide_mask |= 1u << l;
+    }
+    if (ok) {
+      if (batch == 0) return AGT_OK;
+      const int blocks = batch < 4 * ctx->sm_count ? batch : 4 * ctx->sm_count;
+      pyr_roi_chain_kernel<6, 8><<<blocks, PF_WARPS * 32, 0, ctx->stream>>>(*pyr, d_rects, rect_stride, batch, wide_mask);
+      AGT_LAUNCH_CHECK(ctx);
+      return AGT_OK;
+    }
+  }
   for (int l = 1; l < pyr->levels; ++l) {
     if (pyr->width[l] != (pyr->width[l - 1] + 1) / 2 || pyr->height[l] != (pyr->height[l - 1] + 1) / 2)
       AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_build_pyramid: level %d is not ((w+1)/2,(h+1)/2) of level %d", l, l - 1);

@@ -661,3 +661,59 @@ def test_undistort_ingest_large_batch(lib_built):
             assert np.array_equal(got[b], want), b
     finally:
         ctx.close()
+
+
+def _exact_window(lo, hi, n0, n, level):
+    """Exact part [a, b) of a level-`level` axis of a pyramid built under the level-0 interval [lo, hi) (agt.h)."""
+    reach = (2 << level) - 2
+    a = 0 if lo <= 0 else (lo + reach + (1 << level) - 1) >> level
+    b = n if hi >= n0 else ((hi - 1 - reach) >> level) + 1
+    return a, max(b, 0)
+
+
+def test_roi_pyramid_single_launch_chain(ctxvga):
+    """Batches that fill the machine build the region-of-interest pyramid of every frame in one launch (a CTA per frame
+    walks down the levels): inside the window of pixels whose pyrDown support lies in the frame's rectangle it equals
+    the complete pyramid bit for bit, outside the windows K1 would write it leaves the (poisoned) levels untouched;
+    empty rectangles, rectangles on the image border and full-frame rectangles included."""
+    import torch
+    ctx = ctxvga
+    w, h, n = 1280, 128, 320          # more than 2 frames per SM: the single-launch path; 16 px per lane on levels 1-2, 8 on level 3
+    rng = np.random.default_rng(11)
+    frames = torch.as_tensor(rng.integers(0, 256, (n, h, w), dtype=np.uint8), device=ctx.tdev)
+    full = ctx.alloc_pyramid(n, w, h, 4)
+    full.levels[0].copy_(frames)
+    ctx.build_pyramid(full)
+    rects = np.zeros((n, 4), np.int32)
+    for b in range(n):
+        x0, y0 = int(rng.integers(0, w - 48)) & ~15, int(rng.integers(0, h - 40))
+        x1, y1 = min(w, (x0 + int(rng.integers(40, 900)) + 15) & ~15), min(h, y0 + int(rng.integers(30, 128)))
+        rects[b] = (x0, y0, x1, y1)
+    rects[0] = (0, 0, w, h)                                            # whole frame
+    rects[1] = (0, 0, 0, 0)                                            # empty: nothing is built
+    rects[2] = (0, 0, 64, 50)                                          # top-left corner
+    rects[3] = (w - 64, h - 50, w, h)                                  # bottom-right corner
+    roi = ctx.alloc_pyramid(n, w, h, 4)
+    roi.levels[0].copy_(frames)
+    for l in (1, 2, 3):
+        roi.levels[l].fill_(0xA5)
+    ctx.build_pyramid_roi(roi, torch.as_tensor(rects, device=ctx.tdev))
+    small = ctx.alloc_pyramid(24, w, h, 4)                             # the per-level launches on a small batch
+    small.levels[0].copy_(frames[:24])
+    for l in (1, 2, 3):
+        small.levels[l].fill_(0xA5)
+    ctx.build_pyramid_roi(small, torch.as_tensor(rects[:24], device=ctx.tdev))
+    for l in (1, 2, 3):
+        got, want, per_level = roi.level(l).cpu().numpy(), full.level(l).cpu().numpy(), small.level(l).cpu().numpy()
+        assert np.array_equal(got[:24], per_level), f"level {l}: single launch and per-level launches differ"
+        lw, lh = w >> l, h >> l
+        for b in range(n):
+            x0, y0, x1, y1 = rects[b]
+            if x1 <= x0 or y1 <= y0:
+                assert (got[b] == 0xA5).all()
+                continue
+            ax, bx = _exact_window(x0, x1, w, lw, l)
+            ay, by = _exact_window(y0, y1, h, lh, l)
+            if bx > ax and by > ay:
+                assert np.array_equal(got[b, ay:by, ax:bx], want[b, ay:by, ax:bx]), (l, b)
+    assert np.array_equal(roi.level(1)[0].cpu().numpy(), full.level(1)[0].cpu().numpy())
