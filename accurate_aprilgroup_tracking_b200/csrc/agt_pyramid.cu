@@ -209,6 +209,9 @@ pyr_down_stream_kernel(const uint8_t* __restrict__ src, int w, int h, int64_t sp
 // next level reads what they wrote (from L2).  Per-level launches leave most of the machine idle on these small windows:
 // a 600 x 580 rectangle is 10 + 5 + 3 strips per frame, three short launches with their tails, each warp striding over a
 // handful of live items (profiles/r01_ncu_pyr_roi.txt).  Same streaming warp routine, same bits.
+// (Whole frames through this scheme run as fast as the per-level launches, 1.29 against 1.28 ms per 2048 frames, and a
+// 16-warp CTA per SM - fewer frames in flight, so that a level might still be in L2 when the next one reads it - is
+// slower, 1.34 ms: whole-frame builds keep the per-level launches.)
 template <int Q2, int Q1>
 __global__ void __launch_bounds__(PF_WARPS * 32, 4)
 pyr_roi_chain_kernel(agt_pyramid pyr, const int32_t* __restrict__ rects, int rect_stride, int batch, uint32_t wide_mask) {
