@@ -739,7 +739,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=None,
+                    help="frames per GPU per step (default: 4096, BASELINE config 2; 8192 frame pairs for --workload lk, config 3)")
     ap.add_argument("--cpu-sample", type=int, default=96)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -747,6 +748,8 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     args = ap.parse_args()
+    if args.frames is None:
+        args.frames = 8192 if args.workload == "lk" else 4096
     ensure_library()
     if args.impl == "reference":
         run_reference(args)
