@@ -125,6 +125,17 @@ __device__ __forceinline__ int blend(const Run& t, const Run& b, uint32_t wt, ui
 // column x0 inside a shared-memory row.  Footprints inside the image (4-byte aligned rows) travel as aligned words by
 // cp.async: every request of the footprint is in flight at once and no register waits for it.  Footprints cut by the
 // image border are gathered byte by byte with BORDER_REFLECT_101 (a lane per column).  The caller waits.
+// the rare path (a footprint cut by the image border), kept out of line so that it does not sit in the instruction
+// stream of every warp: the kernel is large and the warps of an SM are spread all over it
+__device__ __noinline__ void stage_footprint_bytes(uint8_t* smem, const uint8_t* __restrict__ img, int cols, int rows, int64_t pitch,
+                                                   int x0, int y0, int lane, int w, int n_rows, int spitch) {
+  const int gx = reflect_fast(x0 + (lane < w ? lane : 0), cols);
+  for (int r = 0; r < n_rows; ++r) {
+    const int gy = reflect_fast(y0 + r, rows);
+    if (lane < w) smem[r * spitch + lane] = __ldg(img + (int64_t)gy * pitch + gx);
+  }
+}
+
 template <int W, int ROWS, int WORDS, int SPITCH>
 __device__ __forceinline__ int stage_footprint(uint8_t* smem, const uint8_t* __restrict__ img, int cols, int rows, int64_t pitch,
                                                int x0, int y0, int lane) {
@@ -143,12 +154,7 @@ __device__ __forceinline__ int stage_footprint(uint8_t* smem, const uint8_t* __r
     }
     return x0 & 3;
   }
-  const int gx = reflect_fast(x0 + (lane < W ? lane : 0), cols);
-#pragma unroll 4
-  for (int r = 0; r < ROWS; ++r) {
-    const int gy = reflect_fast(y0 + r, rows);
-    if (lane < W) smem[r * SPITCH + lane] = __ldg(img + (int64_t)gy * pitch + gx);
-  }
+  stage_footprint_bytes(smem, img, cols, rows, pitch, x0, y0, lane, W, ROWS, SPITCH);
   return 0;
 }
 __device__ __forceinline__ void stage_wait() {
@@ -178,6 +184,24 @@ __device__ __forceinline__ bool footprint_inside(int f0, int f1, int n, int lo, 
 // under; a corner whose footprints leave the exact part of a level is flagged in left_roi_out (its outputs are then
 // meaningless and the caller redoes the frame on complete pyramids).  mask (may be null): only frames with a non-zero
 // entry are processed, the outputs of the others are left untouched.
+// Scharr of a window that is cut by the image border: zero outside the image (rare, kept out of line like the byte-wise staging)
+__device__ __noinline__ void scharr_cut_window(WarpSmem& S, int ix, int iy, int cols, int rows, int pxo, int lane) {
+  for (int i = lane; i < DER * DER; i += 32) {
+    int r = i / DER, c = i - r * DER;
+    int gx = ix + c, gy = iy + r;
+    short2 d = make_short2(0, 0);
+    if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+      const uint8_t* p = S.u.t.patch + r * PATCH_PITCH + pxo + c;
+      int a00 = p[0], a01 = p[1], a02 = p[2];
+      int a10 = p[PATCH_PITCH], a12 = p[PATCH_PITCH + 2];
+      int a20 = p[2 * PATCH_PITCH], a21 = p[2 * PATCH_PITCH + 1], a22 = p[2 * PATCH_PITCH + 2];
+      d.x = (short)(3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+      d.y = (short)(3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+    }
+    S.u.t.der[r][c] = d;
+  }
+}
+
 template <bool kRoi>
 __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int64_t gid, const agt_pyramid& prev, const agt_pyramid& next,
                                           const float* __restrict__ prev_pts, float* __restrict__ next_pts,
@@ -282,20 +306,8 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
           S.u.t.der[lane][c] = make_short2((short)dx, (short)dy);
         }
       }
-    } else
-    for (int i = lane; i < DER * DER; i += 32) {
-      int r = i / DER, c = i - r * DER;
-      int gx = ix + c, gy = iy + r;
-      short2 d = make_short2(0, 0);
-      if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-        const uint8_t* p = S.u.t.patch + r * PATCH_PITCH + pxo + c;
-        int a00 = p[0], a01 = p[1], a02 = p[2];
-        int a10 = p[PATCH_PITCH], a12 = p[PATCH_PITCH + 2];
-        int a20 = p[2 * PATCH_PITCH], a21 = p[2 * PATCH_PITCH + 1], a22 = p[2 * PATCH_PITCH + 2];
-        d.x = (short)(3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
-        d.y = (short)(3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
-      }
-      S.u.t.der[r][c] = d;
+    } else {
+      scharr_cut_window(S, ix, iy, cols, rows, pxo, lane);
     }
     __syncwarp();
     // ---- template + structure tensor (lane-major pixel order, see WarpSmem) ------------------
