@@ -717,3 +717,39 @@ def test_roi_pyramid_single_launch_chain(ctxvga):
             if bx > ax and by > ay:
                 assert np.array_equal(got[b, ay:by, ax:bx], want[b, ay:by, ax:bx]), (l, b)
     assert np.array_equal(roi.level(1)[0].cpu().numpy(), full.level(1)[0].cpu().numpy())
+
+
+def test_undistort_ingest_random_cameras(lib_built):
+    """Bit-exactness of the undistort ingest over random lenses, new camera matrices (alpha 0..1, off-centre, skew-free),
+    crops and 16-byte aligned frame sizes, BGR and gray."""
+    import cv2
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for case in range(14):
+        w = int(rng.choice([64, 176, 320, 640, 1008]))
+        h = int(rng.integers(33, 300))
+        f = float(rng.uniform(0.5, 1.6)) * w
+        mtx = np.array([[f, 0, w / 2 + rng.uniform(-9, 9)], [0, f * rng.uniform(0.97, 1.03), h / 2 + rng.uniform(-9, 9)], [0, 0, 1]])
+        dist = np.array([[rng.uniform(-0.35, 0.2), rng.uniform(-0.15, 0.15), rng.uniform(-0.004, 0.004), rng.uniform(-0.004, 0.004),
+                          rng.uniform(-0.05, 0.05)]])
+        new_mtx, roi = cv2.getOptimalNewCameraMatrix(mtx, dist, (w, h), float(rng.uniform(0, 1)), (w, h))
+        x, y, rw, rh = roi
+        if rw < 8 or rh < 8:
+            continue
+        ctx = AgtContext(0, mtx, dist)
+        try:
+            ctx.set_undistort(new_mtx, w, h, roi)
+            for shape in ((5, h, w, 3), (2, h, w)):
+                frames = rng.integers(0, 256, shape, dtype=np.uint8)
+                pyr = ctx.alloc_pyramid(shape[0], rw, rh, 1)
+                ctx.ingest_undistort(pyr, frames)
+                got = pyr.frames.cpu().numpy()
+                for b in range(shape[0]):
+                    want = cv2.undistort(frames[b], mtx, dist, None, new_mtx)[y:y + rh, x:x + rw]
+                    want = cv2.cvtColor(want, cv2.COLOR_BGR2GRAY) if want.ndim == 3 else want
+                    assert np.array_equal(got[b], want), (case, w, h, roi, b, int(np.abs(got[b].astype(int) - want.astype(int)).max()))
+            checked += 1
+        finally:
+            ctx.close()
+    assert checked >= 8
