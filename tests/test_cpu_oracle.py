@@ -253,3 +253,31 @@ def test_undistort_oracle_matches_golden():
         got = uo.undistort_frame_gray(g["frame"], g["mtx"], g["dist"][k], g["new_mtx"][k], g["roi"][k])
         assert np.array_equal(got.ravel(), g[f"gray{k}"]) and got.shape == (h, w)
 
+
+
+def test_roi_exactness_rule_of_the_pyramid_chain():
+    """The rule behind agt_build_pyramid_roi / agt_lk_roi (include/agt.h): a level-l pixel depends only on the level-0
+    pixels 2^l x +- (2^(l+1) - 2) of its pyrDown chain (reflected at the image border).  Checked with cv2.pyrDown itself:
+    randomising everything outside a rectangle leaves the window the kernels treat as exact untouched."""
+    import cv2
+    rng = np.random.default_rng(5)
+    w, h = 208, 144
+    base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+
+    def window(lo, hi, n0, n, level):
+        reach = (2 << level) - 2
+        a = 0 if lo <= 0 else (lo + reach + (1 << level) - 1) >> level
+        b = n if hi >= n0 else ((hi - 1 - reach) >> level) + 1
+        return a, max(b, 0)
+
+    for x0, y0, x1, y1 in ((48, 30, 160, 120), (0, 0, 96, 80), (112, 64, w, h), (0, 40, w, 100)):
+        other = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        other[y0:y1, x0:x1] = base[y0:y1, x0:x1]
+        a, b = base, other
+        for level in (1, 2, 3):
+            a, b = cv2.pyrDown(a), cv2.pyrDown(b)
+            lh, lw = a.shape
+            ax, bx = window(x0, x1, w, lw, level)
+            ay, by = window(y0, y1, h, lh, level)
+            assert bx > ax and by > ay
+            assert np.array_equal(a[ay:by, ax:bx], b[ay:by, ax:bx]), (level, (x0, y0, x1, y1))
