@@ -108,7 +108,7 @@ undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__
 // consecutive pixels of one row, rows ty, ty+8, ty+16, ty+24), UT_GROUP frames per CTA.
 // ---------------------------------------------------------------------------------------------------------------
 // (8 pixels per thread - 32x64 tiles, 14 KB stages - amortise the per-frame overhead over more pixels but measured slower:
-// 2.65e5 frames/s at 64 registers with spills, 3.10e5 at 80 registers and 3 CTAs per SM, against 3.33e5)
+// 2.65e5 frames/s at 64 registers with spills, 3.10e5 at 80 registers and 3 CTAs per SM, against 3.33e5 at 32 frames per CTA)
 constexpr int UT_TILE = 32, UT_THREADS = 256, UT_PX = 4, UT_TILE_H = 8 * UT_PX, UT_STAGES = 3;
 constexpr int UT_STAGE_BYTES = 8192;
 constexpr int UT_CHUNKS = (UT_STAGE_BYTES / 16 + UT_THREADS - 1) / UT_THREADS;      // 16-byte requests per thread and frame
@@ -347,7 +347,7 @@ extern "C" int agt_undistort_to_gray(agt_ctx* ctx, const uint8_t* d_src, int w, 
                        w <= 16384 && h <= 16384;
   if (aligned) {
     // frames per CTA: the float64 pixel maps are computed once per CTA, so large batches amortise them over more frames
-    const int group = batch >= 128 ? 32 : 16;
+    const int group = batch >= 256 ? 64 : (batch >= 128 ? 32 : 16);
     const int groups = (batch + group - 1) / group;
     for (int g0 = 0; g0 < groups; g0 += 65535) {
       const int ng = groups - g0 < 65535 ? groups - g0 : 65535;

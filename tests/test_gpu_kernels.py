@@ -635,8 +635,8 @@ def test_undistort_ingest_bit_exact(lib_built, w, h, f):
 
 
 def test_undistort_ingest_large_batch(lib_built):
-    """Batches of 128 frames and more use 32 frames per CTA (fewer pixel-map evaluations): same bits as cv2 and as the
-    16-frame grouping of a smaller batch."""
+    """Large batches put more frames on a CTA (16 below 128 frames, 32 below 256, 64 from there on: fewer pixel-map
+    evaluations): same bits as cv2 and whatever the grouping."""
     import cv2
     from accurate_aprilgroup_tracking_b200.context import AgtContext
     w, h, f = 320, 200, 280.0
@@ -648,15 +648,16 @@ def test_undistort_ingest_large_batch(lib_built):
     ctx = AgtContext(0, mtx, dist)
     try:
         ctx.set_undistort(new_mtx, w, h, roi)
-        n = 150                                                    # 4 full groups of 32 + one of 22
+        n = 300                                                    # 4 full groups of 64 + one of 44
         frames = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
         big = ctx.alloc_pyramid(n, rw, rh, 1)
         ctx.ingest_undistort(big, frames)
         got = big.frames.cpu().numpy()
-        small = ctx.alloc_pyramid(100, rw, rh, 1)
-        ctx.ingest_undistort(small, frames[:100])
-        assert np.array_equal(small.frames.cpu().numpy(), got[:100])
-        for b in (0, 31, 32, 127, 128, 149):
+        for m in (100, 150):                                       # groups of 16 / of 32
+            part = ctx.alloc_pyramid(m, rw, rh, 1)
+            ctx.ingest_undistort(part, frames[:m])
+            assert np.array_equal(part.frames.cpu().numpy(), got[:m]), m
+        for b in (0, 63, 64, 255, 256, 299):
             want = cv2.cvtColor(cv2.undistort(frames[b], mtx, dist, None, new_mtx)[y:y + rh, x:x + rw], cv2.COLOR_BGR2GRAY)
             assert np.array_equal(got[b], want), b
     finally:
