@@ -706,7 +706,7 @@ def test_roi_pyramid_single_launch_chain(ctxvga):
     ctx.build_pyramid_roi(small, torch.as_tensor(rects[:24], device=ctx.tdev))
     for l in (1, 2, 3):
         got, want, per_level = roi.level(l).cpu().numpy(), full.level(l).cpu().numpy(), small.level(l).cpu().numpy()
-        assert np.array_equal(got[:24], per_level), f"level {l}: single launch and per-level launches differ"
+        # (the two paths may start a window on different 8 / 16 pixel boundaries: compare them where both are exact)
         lw, lh = w >> l, h >> l
         for b in range(n):
             x0, y0, x1, y1 = rects[b]
@@ -717,6 +717,15 @@ def test_roi_pyramid_single_launch_chain(ctxvga):
             ay, by = _exact_window(y0, y1, h, lh, l)
             if bx > ax and by > ay:
                 assert np.array_equal(got[b, ay:by, ax:bx], want[b, ay:by, ax:bx]), (l, b)
+                if b < 24:
+                    assert np.array_equal(per_level[b, ay:by, ax:bx], want[b, ay:by, ax:bx]), (l, b)
+            # nothing is written outside the largest window K1 may touch (16-pixel alignment on the left)
+            sh, rnd = l, (1 << l) - 1
+            mx0, my0 = max(0, (x0 >> sh) - 2) & ~15, max(0, (y0 >> sh) - 2)
+            mx1, my1 = min(lw, (((x1 + rnd) >> sh) + 2 + 7) & ~7), min(lh, ((y1 + rnd) >> sh) + 2)
+            outside = np.ones_like(got[b], bool)
+            outside[my0:my1, mx0:mx1] = False
+            assert (got[b][outside] == 0xA5).all(), (l, b)
     assert np.array_equal(roi.level(1)[0].cpu().numpy(), full.level(1)[0].cpu().numpy())
 
 
