@@ -71,7 +71,7 @@ struct DprShared {
   int stop;
   int zero;              // 0, read at run time (an ordering dependency the compiler cannot fold away)
   double wsum[DPR_WARPS][NSUM + 2];
-  double tot[NSUM + 2];  // cluster exchange only
+  double tot[2][NSUM + 2];  // cluster exchange only, double-buffered by evaluation parity
   // LM state, touched by warp 0 only (kept out of registers)
   double Pc[12];         // accepted pose: rotation (row-major) + translation
   double Hb[27];         // normal equations at the accepted pose: H (21, packed upper triangle by rows) + b (6)
@@ -325,8 +325,8 @@ __device__ void cta_pyr_down_region(const uint8_t* __restrict__ src, int sw, int
 
 // kCluster > 1: a thread-block cluster of kCluster CTAs shares one refinement.  Used when the batch is smaller than
 // the machine (camera streams: one pose per stream per step): every CTA stages the ROI, takes every kCluster-th
-// slice of the samples, the partial sums meet in CTA 0 through distributed shared memory, CTA 0 runs the LM step
-// and the others read the new trial pose back over DSMEM.  Two cluster barriers per evaluation.
+// slice of the samples, every CTA reads every CTA's partial sums through distributed shared memory and takes the
+// (identical) LM step itself.  One cluster barrier per evaluation.
 template <int kCluster>
 __global__ void __launch_bounds__(DPR_THREADS, 2)
 dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, agt_model model,
@@ -481,7 +481,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   const int cDX0_3 = kCoef[0], cDX0_10 = kCoef[1], cDX1_3 = kCoef[2], cDX1_10 = kCoef[3], cSM0 = kCoef[4], cSM1 = kCoef[5],
             cSM0_NEG = kCoef[6], cSM1_NEG = kCoef[7];
 
-  while (true) {
+  for (int it = 0;; ++it) {
     // ================= evaluate cost + normal equations at the trial pose =================
     // Internal order of the six Jacobian columns: q = (J0, -J1, J3, J4, J2, J5) in three pairs QA QB QC, chosen so that
     // every pair is produced as a pair (no register moves); signs and order are undone when the sums are unpacked.
@@ -656,15 +656,22 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
       for (int w = 0; w < DPR_WARPS; ++w) tot += S.wsum[w][lane];
     }
     if (kCluster > 1) {
+      // Every CTA of the cluster adds up every CTA's partial sums, in rank order, and then takes the LM step itself: the
+      // same numbers through the same operations, so all of them arrive at the same decision and the same next pose, and
+      // one cluster barrier per evaluation is enough (nobody waits for CTA 0 to publish the pose).  The exchange buffer is
+      // double-buffered by evaluation parity: a CTA overwrites a buffer only after the barrier of the next evaluation,
+      // which every CTA reaches after it has read this one.
       cg::cluster_group cluster = cg::this_cluster();
-      if (wid == 0 && lane < 29) S.tot[lane] = tot;
+      if (wid == 0 && lane < 29) S.tot[it & 1][lane] = tot;
       cluster.sync();                                   // every CTA's partial sums are in its S.tot
-      if (crank == 0 && wid == 0 && lane < 29)
-        for (int r = 1; r < kCluster; ++r) tot += cluster.map_shared_rank(&S, r)->tot[lane];
+      if (wid == 0 && lane < 29) {
+        tot = 0.0;
+        for (int r = 0; r < kCluster; ++r) tot += cluster.map_shared_rank(&S, r)->tot[it & 1][lane];
+      }
     }
 
     // ================= LM bookkeeping (warp 0: decisions in every lane, the 6x6 solve in lane 0) ==========
-    if (wid == 0 && crank == 0) {
+    if (wid == 0) {
       const double cn = 0.5 * __shfl_sync(0xffffffffu, tot, 27);
       const int nn = (int)__shfl_sync(0xffffffffu, tot, 28);
       double cc = S.cc, lam = S.lam;
@@ -723,15 +730,6 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
         S.stop = need_step ? 0 : 1;
         S.cc = cc; S.lam = lam; S.evals = evals; S.status = status;
         if (accept) S.nc = nn;
-      }
-    }
-    if (kCluster > 1) {
-      cg::cluster_group cluster = cg::this_cluster();
-      cluster.sync();                                   // CTA 0 has published the next trial pose (or stop)
-      if (crank != 0) {
-        const DprShared* S0 = cluster.map_shared_rank(&S, 0);
-        if (tid < 12) { S.Rd[tid] = S0->Rd[tid]; S.Rf[tid] = S0->Rf[tid]; }
-        if (tid == 0) S.stop = S0->stop;
       }
     }
     __syncthreads();

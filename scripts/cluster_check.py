@@ -1,6 +1,10 @@
 """Cluster-split refinement (small batches) vs the single-CTA path and vs the oracle (run on the GPU box)."""
 import sys, numpy as np
 sys.path.insert(0, '.')
+if len(sys.argv) > 1:
+    from pathlib import Path
+    from accurate_aprilgroup_tracking_b200 import _lib
+    _lib.LIB_PATH = Path(sys.argv[1]).resolve()
 import torch
 from accurate_aprilgroup_tracking_b200 import synth
 from accurate_aprilgroup_tracking_b200.context import AgtContext
