@@ -4,7 +4,8 @@ streams at once, one frame per stream per step, entirely on one GPU.
 It is the batched counterpart of ``PoseDetector._detect_and_get_pose`` (detect_pose.py:576-609) with
 the reference's per-stream state (detect_pose.py:74-78) kept in device memory.  Per step:
 
-  K1  agt_build_pyramid    pyramid of the new frames
+  K1  agt_build_pyramid    pyramid of the new frames (outside the captured sequence: ``ingest_next`` lets the caller run
+                           it, with the frame ingest, on a side stream while the previous step refines)
   K2  agt_lk + agt_lk_merge  streams with < 2 detected tags re-admit the tags whose four corners
                            were tracked from the previous frame (the inlier set is LK status == 1)
   K0  agt_ape_prepare      extrinsic guess from the predictor state        (detect_pose.py:508)
@@ -27,6 +28,8 @@ from .context import AgtContext
 
 
 class BatchedPoseDetector:
+    SLOTS = 3
+
     def __init__(self, ctx: AgtContext, n_streams: int, width: int, height: int, obj_pts: np.ndarray,
                  enhance_ape: bool = True, use_lk: bool = True, use_dense_refine: bool = True, levels: int = 4,
                  use_graphs: bool = True):
@@ -35,7 +38,9 @@ class BatchedPoseDetector:
         self.use_lk, self.use_dense_refine = use_lk, use_dense_refine
         self.n_pts = int(obj_pts.shape[0])
         self.obj = ctx._dev(obj_pts, t.float32)
-        self.pyr = [ctx.alloc_pyramid(self.n, width, height, levels) for _ in range(2)]
+        # three frame slots: a step reads the current and the previous one, the third is free to receive the next frame while
+        # the step runs (double-buffered ingest)
+        self.pyr = [ctx.alloc_pyramid(self.n, width, height, levels) for _ in range(self.SLOTS)]
         self.cur = 0
         self.state = ctx.new_stream_state(self.n)
         dev = ctx.tdev
@@ -46,8 +51,9 @@ class BatchedPoseDetector:
         self.prev_pts = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
         self.prev_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
         self.use_graphs = use_graphs
-        self._graphs = [None, None]
-        self._outs = [None, None]
+        self._graphs = [None] * self.SLOTS
+        self._built = [False] * self.SLOTS        # the pyramid of the slot's current frame is already there
+        self._outs = [None] * self.SLOTS
         self._steps = 0
         self.kernels_per_step = 0
         if use_dense_refine and ctx._model is None:
@@ -58,18 +64,33 @@ class BatchedPoseDetector:
         self.state.zero_()
         self.prev_pts.zero_()
         self.prev_valid.zero_()
+        self._built = [False] * self.SLOTS
 
     @property
     def frames(self):
         """Level-0 buffer [S,H,W] the caller fills (or renders into) before ``step``."""
         return self.pyr[self.cur].frames
 
+    @property
+    def next_frames(self):
+        """Level-0 buffer of the step after the coming one: not read by the coming step, so the caller may fill it
+        (on another stream, ordered after the previous step) while that step runs."""
+        return self.pyr[(self.cur + 1) % self.SLOTS].frames
+
+    def ingest_next(self, frames) -> None:
+        """Put the frame of the step after the coming one into its slot and build its pyramid (K1), on the current stream:
+        neither is read by the coming step, so with a side stream (ordered after the previous step; the coming-but-one step
+        ordered after it) the bandwidth-bound ingest runs under the latency-bound refinement of the step in flight."""
+        slot = (self.cur + 1) % self.SLOTS
+        self.ctx.upload_frames(self.pyr[slot], frames)
+        self.ctx.build_pyramid(self.pyr[slot])
+        self._built[slot] = True
+
     def _body(self, slot: int):
         """One frame of every stream: fixed launch sequence over static buffers (graph-capturable)."""
         ctx, t = self.ctx, self.ctx.torch
-        cur, prv = self.pyr[slot], self.pyr[1 - slot]
+        cur, prv = self.pyr[slot], self.pyr[(slot - 1) % self.SLOTS]
         img, val, ntg = self.in_img.clone(), self.in_valid.clone(), self.in_ntags.clone()
-        ctx.build_pyramid(cur)                                                   # K1
         tracked_tags = None
         if self.use_lk:
             # K2: only frames with < 2 detected tags are tracked; on the very first frame prev_valid is all zero,
@@ -96,12 +117,16 @@ class BatchedPoseDetector:
     def step(self, img_pts, valid, n_tags, frames=None):
         """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),
         n_tags [S] i32 accepted detections.  ``frames`` [S,H,W] u8 is copied into the current slot
-        unless the caller wrote ``self.frames`` directly.  Returns a dict of device tensors (valid until the
-        step after next when CUDA graphs are in use: the graph of a slot reuses its output buffers)."""
+        unless the caller wrote ``self.frames`` directly.  Returns a dict of device tensors (valid until the slot
+        comes round again when CUDA graphs are in use: the graph of a slot reuses its output buffers)."""
         ctx, t = self.ctx, self.ctx.torch
         slot = self.cur
         if frames is not None:
             ctx.upload_frames(self.pyr[slot], frames)
+            self._built[slot] = False
+        if not self._built[slot]:
+            ctx.build_pyramid(self.pyr[slot])                # K1 (unless ingest_next built this slot during the last step)
+        self._built[slot] = False                            # the caller writes the next frame into it before it is used again
         self.in_img.copy_(ctx._dev(img_pts, t.float32))
         self.in_valid.copy_(ctx._dev(valid, t.uint8))
         self.in_ntags.copy_(ctx._dev(n_tags, t.int32))
@@ -109,7 +134,7 @@ class BatchedPoseDetector:
             self._graphs[slot].replay()
             out = self._outs[slot]
         elif self.use_graphs and self._steps >= 2:
-            # both slots have run eagerly once (lazy one-time setup is done): capture this slot and replay it
+            # two steps have run eagerly (lazy one-time setup is done): capture this slot and replay it
             g = t.cuda.CUDAGraph()
             t.cuda.synchronize(ctx.tdev)
             with t.cuda.graph(g):
@@ -121,7 +146,7 @@ class BatchedPoseDetector:
             out = self._body(slot)
             self.kernels_per_step = ctx.launch_count() - l0     # what a graph replay launches, too
         self._steps += 1
-        self.cur = 1 - slot
+        self.cur = (slot + 1) % self.SLOTS
         return out
 
 
