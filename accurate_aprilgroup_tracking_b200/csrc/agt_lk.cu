@@ -13,9 +13,18 @@
 // memory, derives the 22x22 Scharr values from it (no gradient plane is ever
 // materialised in HBM), builds the 21x21 template, reduces the structure tensor
 // with warp shuffles, then iterates against a 32x32 u8 search region staged
-// from the next image (re-staged only if the window drifts out of it).  All sums
-// are exact integers; they are rounded to float once, where OpenCV accumulates
-// in float, so results agree with OpenCV to ~1e-3 px (tolerance 0.01 px).
+// from the next image (re-staged only if the window drifts out of it).
+//
+// Bit parity with OpenCV.  cv::calcOpticalFlowPyrLK accumulates the structure tensor and the mismatch vector in
+// float32, in the order of its 128-bit SIMD loop (oracle/lk_oracle.py:_tensor_sum_f32 / _mismatch_sum_f32 restate it
+// and are bit-identical to cv2 on every corner tried): columns 0..15 of a row go to four float lanes (lane k adds
+// columns k, k+4, k+8, k+12; for the mismatch vector the products of columns (k, k+4) are first added as integers),
+// rows top to bottom, the lanes are reduced as (l0+l2)+(l1+l3); columns 16..20 are added one at a time into a scalar
+// float, and the lane sum is added to that scalar last.  The products exceed 2^24, so every one of those additions
+// rounds, and on ill-conditioned windows one rounding decides whether another iteration runs (0.05 px).  This kernel
+// therefore forms the same integer products in parallel, converts them exactly like cvtdq2ps, and adds them up in
+// that very order: the owners write the floats to shared memory chain by chain, ten lanes then run the ten dependent
+// chains (8 x 42 additions, 2 x 105).  Points, status and error come out bit-identical to OpenCV.
 #include "agt_common.cuh"
 
 namespace {
@@ -23,24 +32,35 @@ namespace {
 constexpr int WIN = 21;
 constexpr int PATCH = WIN + 3;             // 24: template footprint incl. bilinear + Scharr halo
 constexpr int DER = WIN + 1;               // 22
-constexpr int REG = 32;                    // staged search region
-constexpr int REG_MARGIN = 5;              // window offset inside a freshly staged region
+constexpr int REG = 32;                    // staged search region: REG columns x REG_H rows
+constexpr int REG_H = 30;
+constexpr int REG_MARGIN = 5;              // window offset inside a freshly staged region (columns / rows)
+constexpr int REG_MARGIN_Y = 4;
 // Shared-memory rows of the two staged footprints hold the aligned 32-bit words that cover the footprint's columns (the
 // footprint starts `x & 3` bytes into the row): 7 words for 24 columns, 9 for 32.  An odd number of words per row also
 // spreads the rows of a window over all banks (rows of 8 words put every fourth row on the same banks).
 constexpr int PATCH_PITCH = 28, REG_PITCH = 36;
-constexpr int WARPS_PER_CTA = 8;          // 4 CTAs of 8 warps fit an SM's shared memory (1 KB is reserved per CTA), 8 of 4 no longer do
+constexpr int WARPS_PER_CTA = 7;          // 4 CTAs of 7 warps: 4 x (7 x 8176 + 1024 reserved) bytes of an SM's 228 KB
 constexpr int W_BITS = 14;
 constexpr int MAX_ITERS = 30;
 
-// Window pixels per lane: 14, in two runs of 7 consecutive pixels of one row each ("segments"), so that the search
-// loop reads every run with three aligned 32-bit loads per image row instead of one byte load per tap:
-//   lanes 0..20 : row = lane, columns 0..6 and 7..13          lanes 21..31 : rows 2(l-21), 2(l-21)+1, columns 14..20
-// (lane 31's second segment would be row 21: it is disabled by zero derivatives).  Per-pixel arrays are stored in
-// this order: index = lane * 14 + k.
-constexpr int PIX_PER_LANE = 14;
-constexpr int SEG_LEN = 7;
-constexpr int NSLOT = 32 * PIX_PER_LANE;   // 448 >= 441
+// Window pixels per lane, in two runs of consecutive pixels of one row each ("segments"), so that the search loop reads
+// every run with three aligned 32-bit loads per image row instead of one byte load per tap:
+//   lanes 0..20  ("row lanes") : row = lane, columns 0..7 and 8..15 - the part OpenCV's SIMD loop handles
+//   lanes 21..31 ("tail lanes"): rows 2(l-21), 2(l-21)+1, columns 16..20 - OpenCV's scalar tail
+// (lane 31's second run would be row 21: it is disabled by zero derivatives; a tail lane computes eight pixels per run
+// like a row lane and uses the first five).  The per-pixel template arrays are lane-interleaved so that no access has a
+// bank conflict: dd holds (dx, dy) of two neighbouring pixels per int4, run s / pixel pair p of lane l at
+// dd[s * DD_RUN + (p < 3 ? 32 p : 96) + l] (pairs 0..2 for all 32 lanes, pair 3 for the row lanes only); tmpl holds the
+// eight int16 template values of run s of lane l in tmpl[s][l].
+constexpr int SEG_LEN = 8;
+constexpr int TAIL_LEN = 5;
+constexpr int DD_RUN = 3 * 32 + WIN;                                  // 117 int4 per run index
+constexpr int REG_BYTES = (REG_H * REG_PITCH + 12 + 15) & ~15;        // + the third word of a run in the last row
+// float scratch of the ordered sums.  Search loop: 8 chains of 42 (x / y, lanes 0..3 of the SIMD loop: element 2 row + group)
+// and 2 chains of 105 (the scalar tail: element 5 row + column - 16), padded with zeros to whole float4s.  Structure tensor
+// (before the region is staged): 84 per lane chain, in two passes (A11 and A12; A22 and the three tails).
+constexpr int CH_SIMD = 44, CH_TAIL = 108, CH_A = 4 * WIN, CH_ATAIL = 112;
 
 struct __align__(16) WarpSmem {
   union {
@@ -49,26 +69,63 @@ struct __align__(16) WarpSmem {
       __align__(16) uint8_t patch[PATCH * PATCH_PITCH];   // prev level, origin (ix-1, iy-1) at byte `x offset` of row 0
     } t;
     struct {
-      __align__(16) uint8_t px[REG * REG_PITCH + 12];       // next level search region (+ the third word of a run in the last row)
+      __align__(16) uint8_t px[REG_BYTES];                  // next level search region
+      __align__(16) float simd[8][CH_SIMD];
+      __align__(16) float tail[2][CH_TAIL];
     } region;
+    struct { __align__(16) float simd[8][CH_A]; } a1;
+    struct { __align__(16) float simd[4][CH_A]; __align__(16) float tail[3][CH_ATAIL]; } a2;
   } u;
-  __align__(16) int2 dd[NSLOT];            // template derivative (dx, dy), lane-major
-  short tmpl[NSLOT];                       // template intensity * 32, lane-major
+  __align__(16) int4 dd[2 * DD_RUN];       // template derivative (dx, dy) of two pixels
+  __align__(16) uint4 tmpl[2][32];         // template intensity * 32, eight int16 per run
   // region-of-interest pyramids only: exact part [x_lo, x_hi) x [y_lo, y_hi) of the current level of the next pyramid and
   // the "looked outside" flag, kept here rather than in registers that would be live across the search loop
   __align__(16) int win[4];
   int left;
 };
+static_assert(sizeof(WarpSmem) <= 8192, "4 CTAs of 7 warps per SM");
 
 __device__ __forceinline__ void segment_of(int lane, int s, int& row, int& col) {
   if (lane < WIN) { row = lane; col = SEG_LEN * s; }
   else { row = 2 * (lane - WIN) + s; col = 2 * SEG_LEN; }
 }
 
+// One dependent float32 chain per lane: acc = (..((acc + p[0].x) + p[0].y) + ..) over N4 float4s, one rounding per
+// addition.  Straight-line code (the callers branch once around a whole chain) so that the loads run ahead of the adds.
+template <int N4>
+__device__ __forceinline__ float ordered_sum(const float4* __restrict__ p, float acc) {
+#pragma unroll
+  for (int i = 0; i < N4; ++i) {
+    const float4 v = p[i];
+    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+  }
+  return acc;
+}
+// v_reduce_sum of the four SIMD lane accumulators held by lanes base..base+3: (l0 + l2) + (l1 + l3), valid in lane base
+__device__ __forceinline__ float reduce_lanes4(float acc) {
+  const float s = __fadd_rn(acc, __shfl_down_sync(0xffffffffu, acc, 2));
+  return __fadd_rn(s, __shfl_down_sync(0xffffffffu, s, 1));
+}
+
 // Exact warp-wide sum of one 32-bit integer per lane (the total needs more than 32 bits).  Five 64-bit shuffle steps; the
 // warp-reduce unit (two REDUX.SUM on the 16-bit halves) was measured 4-14 % slower for the whole kernel
 // (profiles/r01_lk_variants.log).
 __device__ __forceinline__ long long warp_sum_wide(int v) { return agt_warp_sum((long long)v); }
+
+#ifdef AGT_LK_DEBUG
+// debug build only (scripts/lk_debug_probe.py): per-level / per-iteration sums of one corner
+__device__ float g_lk_dbg[8192];
+__device__ int g_lk_dbg_gid = -1, g_lk_dbg_n = 0;
+#define LK_DBG(...)                                                                     \
+  do {                                                                                  \
+    if (gid == g_lk_dbg_gid && lane == 0) {                                             \
+      const float v_[] = {__VA_ARGS__};                                                 \
+      for (unsigned q_ = 0; q_ < sizeof(v_) / 4; ++q_) if (g_lk_dbg_n < 8192) g_lk_dbg[g_lk_dbg_n++] = v_[q_]; \
+    }                                                                                   \
+  } while (0)
+#else
+#define LK_DBG(...) do {} while (0)
+#endif
 
 struct Weights { int w00, w01, w10, w11; };
 
@@ -94,7 +151,7 @@ __device__ __forceinline__ int dp4us(uint32_t px, int coef, int acc) {
   return d;
 }
 
-// The 8 bytes of a run (columns col..col+7 of one staged row) as two words with the run's first byte in bits 0-7, plus
+// The 9 bytes of a run (columns col..col+8 of one staged row) as two words with the run's first byte in bits 0-7, plus
 // the same shifted by one byte: pixel k of the run blends bytes (k, k+1) of two rows, i.e. one half of one of these
 // words per row, which is exactly what dp2a multiplies by a pair of 16-bit weights.
 struct Run { uint32_t e0, e1, o0, o1; };
@@ -108,17 +165,30 @@ __device__ __forceinline__ Run load_run(uint32_t smem_addr) {
   r.e0 = __funnelshift_r(w0, w1, sh);
   r.e1 = __funnelshift_r(w1, w2, sh);
   r.o0 = __funnelshift_r(r.e0, r.e1, 8);
-  r.o1 = r.e1 >> 8;
+  r.o1 = __funnelshift_r(r.e1, w2 >> sh, 8);
   return r;
 }
-// bilinear value * 32 of pixel k (0..6) of a run: (w00 p00 + w01 p01 + w10 p10 + w11 p11 + 2^8) >> 9, the same integer
+// bilinear value * 32 of pixel k (0..7) of a run: (w00 p00 + w01 p01 + w10 p10 + w11 p11 + 2^8) >> 9, the same integer
 // OpenCV computes; wt = w00 | w01 << 16, wb = w10 | w11 << 16
+// d = c + a.lo16 * b.byte[0 | 2] + a.hi16 * b.byte[1 | 3] with SIGNED 16-bit weights and unsigned pixel bytes: the fourth
+// bilinear weight, 2^14 - w00 - w01 - w10, is -1 when the three rounded ones add up to 2^14 + 1 (OpenCV multiplies signed
+// int16 weights, pmaddwd); the all-unsigned dp2a read that as 65535 - the cause of round 1's rare 0.05 px outliers.
+__device__ __forceinline__ int dp2a_lo_su(uint32_t w, uint32_t px, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t w, uint32_t px, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+  return d;
+}
 template <int K>
 __device__ __forceinline__ int blend(const Run& t, const Run& b, uint32_t wt, uint32_t wb) {
   const uint32_t tw = (K & 1) ? (K < 4 ? t.o0 : t.o1) : (K < 4 ? t.e0 : t.e1);
   const uint32_t bw = (K & 1) ? (K < 4 ? b.o0 : b.o1) : (K < 4 ? b.e0 : b.e1);
-  const uint32_t acc = (K & 2) ? __dp2a_hi(wb, bw, __dp2a_hi(wt, tw, 256u)) : __dp2a_lo(wb, bw, __dp2a_lo(wt, tw, 256u));
-  return (int)(acc >> (W_BITS - 5));
+  const int acc = (K & 2) ? dp2a_hi_su(wb, bw, dp2a_hi_su(wt, tw, 256)) : dp2a_lo_su(wb, bw, dp2a_lo_su(wt, tw, 256));
+  return acc >> (W_BITS - 5);
 }
 
 // Stage the footprint [x0, x0 + W) x [y0, y0 + ROWS) of one level into shared memory and return the byte offset of
@@ -312,13 +382,13 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
     __syncwarp();
     // ---- template + structure tensor (lane-major pixel order, see WarpSmem) ------------------
     Weights w = make_weights(__fsub_rn(px, (float)ix), __fsub_rn(py, (float)iy));
+    const bool row_lane = lane < WIN;
     int seg_row[2], seg_col[2];
     segment_of(lane, 0, seg_row[0], seg_col[0]);
     segment_of(lane, 1, seg_row[1], seg_col[1]);
-    int s11 = 0, s12 = 0, s22 = 0;
-    int c1 = 0, c2 = 0;                          // sum of template * derivative: lets the search loop skip the template
     const uint32_t patch_a = (uint32_t)__cvta_generic_to_shared(&S.u.t.patch[0]) + pxo;
-    const uint32_t wtI = (uint32_t)w.w00 | ((uint32_t)w.w01 << 16), wbI = (uint32_t)w.w10 | ((uint32_t)w.w11 << 16);
+    const uint32_t wtI = ((uint32_t)w.w00 & 0xffffu) | ((uint32_t)w.w01 << 16), wbI = ((uint32_t)w.w10 & 0xffffu) | ((uint32_t)w.w11 << 16);
+    int4* const ddl = &S.dd[lane];
 #pragma unroll
     for (int sg = 0; sg < 2; ++sg) {
       const bool live = seg_row[sg] < WIN;
@@ -328,29 +398,89 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
       int ivs[SEG_LEN];
       ivs[0] = blend<0>(t, bt, wtI, wbI); ivs[1] = blend<1>(t, bt, wtI, wbI); ivs[2] = blend<2>(t, bt, wtI, wbI);
       ivs[3] = blend<3>(t, bt, wtI, wbI); ivs[4] = blend<4>(t, bt, wtI, wbI); ivs[5] = blend<5>(t, bt, wtI, wbI);
-      ivs[6] = blend<6>(t, bt, wtI, wbI);
-      // the eight Scharr values of the run's two rows, each used by two neighbouring pixels
+      ivs[6] = blend<6>(t, bt, wtI, wbI); ivs[7] = blend<7>(t, bt, wtI, wbI);
+      // the Scharr values of the run's two rows, each used by two neighbouring pixels (a tail lane needs six per row)
       short2 d0[SEG_LEN + 1], d1[SEG_LEN + 1];
 #pragma unroll
-      for (int k = 0; k <= SEG_LEN; ++k) { d0[k] = S.u.t.der[y][x0 + k]; d1[k] = S.u.t.der[y + 1][x0 + k]; }
+      for (int k = 0; k <= SEG_LEN; ++k) {
+        const int c = row_lane || k <= TAIL_LEN ? x0 + k : x0;
+        d0[k] = S.u.t.der[y][c]; d1[k] = S.u.t.der[y + 1][c];
+      }
+      int dxs[SEG_LEN], dys[SEG_LEN];
 #pragma unroll
       for (int k = 0; k < SEG_LEN; ++k) {
-        int iv = ivs[k];
-        int dxv = descale(d0[k].x * w.w00 + d0[k + 1].x * w.w01 + d1[k].x * w.w10 + d1[k + 1].x * w.w11, W_BITS);
-        int dyv = descale(d0[k].y * w.w00 + d0[k + 1].y * w.w01 + d1[k].y * w.w10 + d1[k + 1].y * w.w11, W_BITS);
-        if (!live) { iv = 0; dxv = 0; dyv = 0; }
-        const int slot = lane * PIX_PER_LANE + sg * SEG_LEN + k;
-        S.tmpl[slot] = (short)iv;
-        S.dd[slot] = make_int2(dxv, dyv);
-        s11 += dxv * dxv; s12 += dxv * dyv; s22 += dyv * dyv;
-        c1 += iv * dxv; c2 += iv * dyv;          // |iv| <= 8160, |d| <= 4080: 14 terms fit in 32 bits
+        dxs[k] = descale(d0[k].x * w.w00 + d0[k + 1].x * w.w01 + d1[k].x * w.w10 + d1[k + 1].x * w.w11, W_BITS);
+        dys[k] = descale(d0[k].y * w.w00 + d0[k + 1].y * w.w01 + d1[k].y * w.w10 + d1[k + 1].y * w.w11, W_BITS);
+        if (!live || !(row_lane || k < TAIL_LEN)) { ivs[k] = 0; dxs[k] = 0; dys[k] = 0; }
+      }
+      S.tmpl[sg][lane] = make_uint4((uint32_t)(ivs[0] & 0xffff) | ((uint32_t)ivs[1] << 16), (uint32_t)(ivs[2] & 0xffff) | ((uint32_t)ivs[3] << 16),
+                                    (uint32_t)(ivs[4] & 0xffff) | ((uint32_t)ivs[5] << 16), (uint32_t)(ivs[6] & 0xffff) | ((uint32_t)ivs[7] << 16));
+#pragma unroll
+      for (int pr = 0; pr < 4; ++pr)
+        if (pr < 3 || row_lane) ddl[sg * DD_RUN + (pr < 3 ? 32 * pr : 96)] = make_int4(dxs[2 * pr], dys[2 * pr], dxs[2 * pr + 1], dys[2 * pr + 1]);
+    }
+    __syncwarp();      // der / patch are dead from here on: the float scratch of the ordered sums overlays them
+    // ---- structure tensor, summed in float32 in OpenCV's order (see the header) -------------------------------------------
+    // (dx, dy) of column c (0..15) of this row lane / of tail pixel i (0..9) of this tail lane
+#define AGT_DD_COL(c) (reinterpret_cast<const int2*>(&ddl[((c) >> 3) * DD_RUN + ((((c) & 7) >> 1) < 3 ? 32 * (((c) & 7) >> 1) : 96)])[(c) & 1])
+#define AGT_DD_TAIL(i) (reinterpret_cast<const int2*>(&ddl[((i) / TAIL_LEN) * DD_RUN + 32 * (((i) % TAIL_LEN) >> 1)])[((i) % TAIL_LEN) & 1])
+    // pass 1: A11 and A12 of columns 0..15 (lanes 0..3 / 4..7 run the SIMD lane chains: 84 additions each)
+    if (row_lane) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float fx[4], fy[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { const int2 d = AGT_DD_COL(4 * m + kk); fx[m] = (float)d.x; fy[m] = (float)d.y; }
+        // |d| <= 4080: the products are below 2^24, i.e. exact
+        *reinterpret_cast<float4*>(&S.u.a1.simd[kk][4 * lane]) = make_float4(fx[0] * fx[0], fx[1] * fx[1], fx[2] * fx[2], fx[3] * fx[3]);
+        *reinterpret_cast<float4*>(&S.u.a1.simd[4 + kk][4 * lane]) = make_float4(fx[0] * fy[0], fx[1] * fy[1], fx[2] * fy[2], fx[3] * fy[3]);
       }
     }
+    __syncwarp();
+    float acc = 0.f;
+    if (lane < 8) acc = ordered_sum<CH_A / 4>(reinterpret_cast<const float4*>(S.u.a1.simd[lane]), 0.f);
+    acc = reduce_lanes4(acc);
+    const float A11s = __shfl_sync(0xffffffffu, acc, 0), A12s = __shfl_sync(0xffffffffu, acc, 4);
+    __syncwarp();
+    // pass 2: A22 of columns 0..15 (lanes 0..3) and the scalar tails of A11, A12, A22 (lanes 4..6: 105 additions each)
+    if (row_lane) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float fy[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) fy[m] = (float)AGT_DD_COL(4 * m + kk).y;
+        *reinterpret_cast<float4*>(&S.u.a2.simd[kk][4 * lane]) = make_float4(fy[0] * fy[0], fy[1] * fy[1], fy[2] * fy[2], fy[3] * fy[3]);
+      }
+    } else {
+      // ten tail pixels: rows 2j, 2j+1 -> elements 10 j .. 10 j + 9 of each tail chain (lane 31's second row is zero: the
+      // zero padding of the chains; CH_ATAIL leaves room for it)
+      float f11[2 * TAIL_LEN], f12[2 * TAIL_LEN], f22[2 * TAIL_LEN];
+#pragma unroll
+      for (int i = 0; i < 2 * TAIL_LEN; ++i) {
+        const int2 d = AGT_DD_TAIL(i);
+        const float fx = (float)d.x, fy = (float)d.y;
+        f11[i] = fx * fx; f12[i] = fx * fy; f22[i] = fy * fy;
+      }
+      const int e = 2 * TAIL_LEN * (lane - WIN);
+#pragma unroll
+      for (int i = 0; i < TAIL_LEN; ++i) {
+        *reinterpret_cast<float2*>(&S.u.a2.tail[0][e + 2 * i]) = make_float2(f11[2 * i], f11[2 * i + 1]);
+        *reinterpret_cast<float2*>(&S.u.a2.tail[1][e + 2 * i]) = make_float2(f12[2 * i], f12[2 * i + 1]);
+        *reinterpret_cast<float2*>(&S.u.a2.tail[2][e + 2 * i]) = make_float2(f22[2 * i], f22[2 * i + 1]);
+      }
+    }
+#undef AGT_DD_COL
+#undef AGT_DD_TAIL
+    __syncwarp();
+    acc = 0.f;
+    if (lane < 4) acc = ordered_sum<CH_A / 4>(reinterpret_cast<const float4*>(S.u.a2.simd[lane]), 0.f);
+    else if (lane < 7) acc = ordered_sum<CH_TAIL / 4>(reinterpret_cast<const float4*>(S.u.a2.tail[lane - 4]), 0.f);
+    const float A22s = __shfl_sync(0xffffffffu, reduce_lanes4(acc), 0);
     const float FLT_SCALE = 1.f / (float)(1 << 20);
-    float A11 = __fmul_rn((float)warp_sum_wide(s11), FLT_SCALE);
-    float A12 = __fmul_rn((float)warp_sum_wide(s12), FLT_SCALE);
-    float A22 = __fmul_rn((float)warp_sum_wide(s22), FLT_SCALE);
-    const long long C1 = warp_sum_wide(c1), C2 = warp_sum_wide(c2);
+    float A11 = __fmul_rn(__fadd_rn(__shfl_sync(0xffffffffu, acc, 4), A11s), FLT_SCALE);
+    float A12 = __fmul_rn(__fadd_rn(__shfl_sync(0xffffffffu, acc, 5), A12s), FLT_SCALE);
+    float A22 = __fmul_rn(__fadd_rn(__shfl_sync(0xffffffffu, acc, 6), A22s), FLT_SCALE);
+    LK_DBG(-1.f, (float)level, A11, A12, A22, px, py);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     float dif = __fsub_rn(A11, A22);
     float disc = __fadd_rn(__fmul_rn(dif, dif), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -360,14 +490,17 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
       continue;
     }
     D = __fdiv_rn(1.f, D);
-    __syncwarp();      // template footprint no longer needed: the region buffer may overwrite it
+    __syncwarp();      // the scratch of the tensor sums is dead: the region buffer and the search scratch may overwrite it
+    // zero padding of the search chains (elements 42, 43 of the eight lane chains; the tail's comes from lane 31's dead row)
+    if (lane < 8) *reinterpret_cast<float2*>(&S.u.region.simd[lane][CH_SIMD - 2]) = make_float2(0.f, 0.f);
 
     const uint32_t region_a = (uint32_t)__cvta_generic_to_shared(&S.u.region.px[0]);
     int rxo = 0;                               // byte offset of column rx0 inside a staged row
     // shared-memory offset of each run inside the region for a window at (0, 0); disabled runs read a valid row
     const int run_off0 = (seg_row[0] < WIN ? seg_row[0] : WIN - 1) * REG_PITCH + seg_col[0];
     const int run_off1 = (seg_row[1] < WIN ? seg_row[1] : WIN - 1) * REG_PITCH + seg_col[1];
-    const int4* ddp = reinterpret_cast<const int4*>(&S.dd[lane * PIX_PER_LANE]);      // two pixels per 128-bit load
+    const float4* chain = lane < 8 ? reinterpret_cast<const float4*>(S.u.region.simd[lane])
+                                   : reinterpret_cast<const float4*>(S.u.region.tail[lane & 1]);
 
     nx = __fsub_rn(nx, 10.f); ny = __fsub_rn(ny, 10.f);
     float pdx = 0.f, pdy = 0.f;
@@ -379,22 +512,23 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
         if (level == 0) status = 0;
         break;
       }
-      if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
+      if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG_H - DER)) {
         __syncwarp();
-        rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+        rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN_Y;
         if (kRoi) {
           const int4 wn = *reinterpret_cast<const int4*>(S.win);
-          if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
+          if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG_H, rows, wn.z, wn.w))) S.left = 1;
         }
-        rxo = stage_footprint<REG, REG, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+        rxo = stage_footprint<REG, REG_H, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
         staged = true;
         stage_wait();
       }
       Weights wj = make_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
-      const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
+      const uint32_t wt = ((uint32_t)wj.w00 & 0xffffu) | ((uint32_t)wj.w01 << 16), wb = ((uint32_t)wj.w10 & 0xffffu) | ((uint32_t)wj.w11 << 16);
       const uint32_t win_a = region_a + (jy - ry0) * REG_PITCH + (jx - rx0) + rxo;
-      // b = sum (J - I) dI = sum J dI - sum I dI: exact integers, the second sum is C1, C2
-      int sb1 = 0, sb2 = 0;
+      // mismatch products (J - I) dI per pixel: exact integers; pf holds what goes into the float chains - a row lane's
+      // four pair sums (columns k, k+4) per run and component, a tail lane's five single products per run and component
+      float pfx[2][TAIL_LEN], pfy[2][TAIL_LEN];
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {
         const uint32_t a = win_a + (sg == 0 ? run_off0 : run_off1);
@@ -402,17 +536,58 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
         int jv[SEG_LEN];
         jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
         jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
-        jv[6] = blend<6>(t, bt, wt, wb);
+        jv[6] = blend<6>(t, bt, wt, wb); jv[7] = blend<7>(t, bt, wt, wb);
+        const uint4 tq = S.tmpl[sg][lane];
+        const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+        int sx[SEG_LEN], sy[SEG_LEN];
 #pragma unroll
         for (int k = 0; k < SEG_LEN; ++k) {
-          const int slot = sg * SEG_LEN + k;                      // 0..13: pair slot / 2 of the 128-bit loads
-          const int4 d2 = ddp[slot >> 1];
-          const int dx = (slot & 1) ? d2.z : d2.x, dy = (slot & 1) ? d2.w : d2.y;
-          sb1 += jv[k] * dx; sb2 += jv[k] * dy;
+          const int4 d2 = ddl[sg * DD_RUN + ((k >> 1) < 3 ? 32 * (k >> 1) : 96)];
+          const int dx = (k & 1) ? d2.z : d2.x, dy = (k & 1) ? d2.w : d2.y;
+          const int ti = (k & 1) ? (int)tw[k >> 1] >> 16 : (int)(short)(tw[k >> 1] & 0xffffu);
+          const int diff = jv[k] - ti;
+          sx[k] = diff * dx; sy[k] = diff * dy;         // |diff| <= 8160, |d| <= 4080
+        }
+        if (row_lane) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { pfx[sg][k] = (float)(sx[k] + sx[k + 4]); pfy[sg][k] = (float)(sy[k] + sy[k + 4]); }   // pmaddwd + cvtdq2ps
+        } else {
+#pragma unroll
+          for (int k = 0; k < TAIL_LEN; ++k) { pfx[sg][k] = (float)sx[k]; pfy[sg][k] = (float)sy[k]; }
         }
       }
-      float b1 = __fmul_rn((float)(warp_sum_wide(sb1) - C1), FLT_SCALE);
-      float b2 = __fmul_rn((float)(warp_sum_wide(sb2) - C2), FLT_SCALE);
+      if (row_lane) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          *reinterpret_cast<float2*>(&S.u.region.simd[k][2 * lane]) = make_float2(pfx[0][k], pfx[1][k]);
+          *reinterpret_cast<float2*>(&S.u.region.simd[4 + k][2 * lane]) = make_float2(pfy[0][k], pfy[1][k]);
+        }
+      } else {
+        const int e = 2 * TAIL_LEN * (lane - WIN);
+        const float ox[2 * TAIL_LEN] = {pfx[0][0], pfx[0][1], pfx[0][2], pfx[0][3], pfx[0][4], pfx[1][0], pfx[1][1], pfx[1][2], pfx[1][3], pfx[1][4]};
+        const float oy[2 * TAIL_LEN] = {pfy[0][0], pfy[0][1], pfy[0][2], pfy[0][3], pfy[0][4], pfy[1][0], pfy[1][1], pfy[1][2], pfy[1][3], pfy[1][4]};
+#pragma unroll
+        for (int i = 0; i < TAIL_LEN; ++i) {
+          if (e + 2 * i < CH_TAIL) {           // lane 31's dead row supplies the zeros 105..107; 108, 109 do not exist
+            *reinterpret_cast<float2*>(&S.u.region.tail[0][e + 2 * i]) = make_float2(ox[2 * i], ox[2 * i + 1]);
+            *reinterpret_cast<float2*>(&S.u.region.tail[1][e + 2 * i]) = make_float2(oy[2 * i], oy[2 * i + 1]);
+          }
+        }
+      }
+      __syncwarp();
+      // the ten dependent chains: lanes 0..3 x / 4..7 y of the SIMD lanes (42 additions), lanes 8, 9 the scalar tails (105)
+      float ch = 0.f;
+      if (lane < 10) {
+        ch = ordered_sum<CH_SIMD / 4>(chain, 0.f);
+        if (lane >= 8) ch = ordered_sum<(CH_TAIL - CH_SIMD) / 4>(chain + CH_SIMD / 4, ch);
+      }
+      const float lanes4 = reduce_lanes4(ch);
+      const float ib1 = __fadd_rn(__shfl_sync(0xffffffffu, ch, 8), __shfl_sync(0xffffffffu, lanes4, 0));
+      const float ib2 = __fadd_rn(__shfl_sync(0xffffffffu, ch, 9), __shfl_sync(0xffffffffu, lanes4, 4));
+      __syncwarp();
+      LK_DBG((float)j, ib1, ib2, nx, ny);
+      float b1 = __fmul_rn(ib1, FLT_SCALE);
+      float b2 = __fmul_rn(ib2, FLT_SCALE);
       float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -432,20 +607,20 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
       if (!(ex == ex) || !(ey == ey) || jx < -WIN || jx >= cols || jy < -WIN || jy >= rows) {
         status = 0;
       } else {
-        if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG - DER)) {
+        if (!staged || jx < rx0 || jx > rx0 + (REG - DER) || jy < ry0 || jy > ry0 + (REG_H - DER)) {
           __syncwarp();
-          rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN;
+          rx0 = jx - REG_MARGIN; ry0 = jy - REG_MARGIN_Y;
           if (kRoi) {
             const int4 wn = *reinterpret_cast<const int4*>(S.win);
-            if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG, rows, wn.z, wn.w))) S.left = 1;
+            if (lane == 0 && (!footprint_inside(rx0, rx0 + REG, cols, wn.x, wn.y) || !footprint_inside(ry0, ry0 + REG_H, rows, wn.z, wn.w))) S.left = 1;
           }
-          rxo = stage_footprint<REG, REG, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
+          rxo = stage_footprint<REG, REG_H, 9, REG_PITCH>(S.u.region.px, imgJ, cols, rows, pitchJ, rx0, ry0, lane);
           stage_wait();
         }
         Weights wj = make_weights(__fsub_rn(ex, (float)jx), __fsub_rn(ey, (float)jy));
-        const uint32_t wt = (uint32_t)wj.w00 | ((uint32_t)wj.w01 << 16), wb = (uint32_t)wj.w10 | ((uint32_t)wj.w11 << 16);
+        const uint32_t wt = ((uint32_t)wj.w00 & 0xffffu) | ((uint32_t)wj.w01 << 16), wb = ((uint32_t)wj.w10 & 0xffffu) | ((uint32_t)wj.w11 << 16);
         const uint32_t win_a = region_a + (jy - ry0) * REG_PITCH + (jx - rx0) + rxo;
-        int sabs = 0;
+        int sabs = 0;          // sum of |diff| <= 441 * 8160 < 2^24: exact in OpenCV's float accumulator whatever the order
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
           if (seg_row[sg] >= WIN) continue;
@@ -454,14 +629,16 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
           int jv[SEG_LEN];
           jv[0] = blend<0>(t, bt, wt, wb); jv[1] = blend<1>(t, bt, wt, wb); jv[2] = blend<2>(t, bt, wt, wb);
           jv[3] = blend<3>(t, bt, wt, wb); jv[4] = blend<4>(t, bt, wt, wb); jv[5] = blend<5>(t, bt, wt, wb);
-          jv[6] = blend<6>(t, bt, wt, wb);
+          jv[6] = blend<6>(t, bt, wt, wb); jv[7] = blend<7>(t, bt, wt, wb);
+          const uint4 tq = S.tmpl[sg][lane];
+          const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
 #pragma unroll
           for (int k = 0; k < SEG_LEN; ++k) {
-            int diff = jv[k] - S.tmpl[lane * PIX_PER_LANE + sg * SEG_LEN + k];
-            sabs += diff < 0 ? -diff : diff;
+            const int diff = jv[k] - ((k & 1) ? (int)tw[k >> 1] >> 16 : (int)(short)(tw[k >> 1] & 0xffffu));
+            if (row_lane || k < TAIL_LEN) sabs += diff < 0 ? -diff : diff;
           }
         }
-        err = __fmul_rn((float)warp_sum_wide(sabs), 1.f / (float)(32 * WIN * WIN));
+        err = __fdiv_rn((float)warp_sum_wide(sabs), (float)(32 * WIN * WIN));      // `errval * 1.f / (32 * w * h)`
       }
     }
   }
@@ -575,6 +752,22 @@ __global__ void lk_merge_kernel(const float* __restrict__ tracked, const uint8_t
 }
 
 }  // namespace
+
+#ifdef AGT_LK_DEBUG
+extern "C" int agt_lk_debug_set(int gid) {
+  int zero = 0;
+  cudaMemcpyToSymbol(g_lk_dbg_gid, &gid, sizeof(int));
+  return (int)cudaMemcpyToSymbol(g_lk_dbg_n, &zero, sizeof(int));
+}
+extern "C" int agt_lk_debug_get(float* host, int cap) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_lk_dbg_n, sizeof(int));
+  if (n > cap) n = cap;
+  cudaMemcpyFromSymbol(host, g_lk_dbg, sizeof(float) * n);
+  return n;
+}
+#endif
 
 extern "C" int agt_lk_merge(agt_ctx* ctx, const float* d_tracked_pts, const uint8_t* d_status, const uint8_t* d_prev_valid,
                             float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int32_t* d_tracked_tags, int batch, int n_pts) {

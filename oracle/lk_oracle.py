@@ -118,6 +118,38 @@ def _pad_deriv(d):
     return cv.copyMakeBorder(d, WIN, WIN, WIN, WIN, cv.BORDER_CONSTANT, value=0).astype(np.int32)
 
 
+
+def _seq_sum_f32(values: np.ndarray) -> np.float32:
+    """Left-to-right float32 sum (one rounding per addition), as a scalar `acc += v` loop in C produces."""
+    v = np.ascontiguousarray(values, dtype=np.float32).ravel()
+    return np.add.accumulate(v, dtype=np.float32)[-1] if v.size else np.float32(0)
+
+
+SIMD_W = (WIN // 8) * 8          # 16: columns handled eight at a time by OpenCV's 128-bit loop; 16..20 are the scalar tail
+
+
+def _tensor_sum_f32(p: np.ndarray) -> np.float32:
+    """Float32 sum of a (21,21) integer product plane in the order lkpyramid.cpp adds it up (SSE build):
+    four float lanes take columns k, k+4, k+8, k+12 of every row (one add each, rows top to bottom), the
+    lanes are reduced as (l0+l2)+(l1+l3), columns 16..20 are added one by one into a scalar float, and the
+    lane sum is added to that scalar last."""
+    f = p.astype(np.float32)                                   # products < 2^24: exact
+    lanes = [_seq_sum_f32(f[:, k:SIMD_W:4]) for k in range(4)]
+    simd = np.float32(np.float32(lanes[0] + lanes[2]) + np.float32(lanes[1] + lanes[3]))
+    return np.float32(_seq_sum_f32(f[:, SIMD_W:]) + simd)
+
+
+def _mismatch_sum_f32(p: np.ndarray) -> np.float32:
+    """Float32 sum of diff*dI over the window in lkpyramid.cpp's order: within each group of eight columns the
+    products of columns (k, k+4) are added exactly (pmaddwd, int32), converted to float and added to lane k's
+    accumulator (group 0 then group 1, rows top to bottom); result = tail + ((l0+l2)+(l1+l3)), the tail being the
+    one-by-one float sum of columns 16..20."""
+    pairs = (p[:, 0:SIMD_W].reshape(WIN, SIMD_W // 8, 2, 4).sum(axis=2)).astype(np.float32)   # (21, 2, 4)
+    lanes = [_seq_sum_f32(pairs[:, :, k]) for k in range(4)]
+    simd = np.float32(np.float32(lanes[0] + lanes[2]) + np.float32(lanes[1] + lanes[3]))
+    return np.float32(_seq_sum_f32(p[:, SIMD_W:].astype(np.float32)) + simd)
+
+
 def lk_np(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, levels: int = MAX_LEVEL + 1):
     """Restatement of calcOpticalFlowPyrLK defaults, one point at a time."""
     f32 = np.float32
@@ -157,9 +189,9 @@ def lk_np(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, levels: int = MAX_
                           + sd[y0 + 1:y0 + WIN + 1, x0:x0 + WIN] * w10 + sd[y0 + 1:y0 + WIN + 1, x0 + 1:x0 + WIN + 1] * w11,
                           W_BITS)
             dix, diy = dt[..., 0].astype(np.int64), dt[..., 1].astype(np.int64)
-            a11 = f32(f32((dix * dix).sum()) * FLT_SCALE)
-            a12 = f32(f32((dix * diy).sum()) * FLT_SCALE)
-            a22 = f32(f32((diy * diy).sum()) * FLT_SCALE)
+            a11 = f32(_tensor_sum_f32(dix * dix) * FLT_SCALE)
+            a12 = f32(_tensor_sum_f32(dix * diy) * FLT_SCALE)
+            a22 = f32(_tensor_sum_f32(diy * diy) * FLT_SCALE)
             d = f32(a11 * a22 - a12 * a12)
             min_eig = f32((a22 + a11 - np.sqrt(f32((a11 - a22) * (a11 - a22) + f32(4.0) * a12 * a12))) / f32(2 * WIN * WIN))
             if min_eig < MIN_EIG or d < np.finfo(np.float32).eps:
@@ -181,8 +213,8 @@ def lk_np(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, levels: int = MAX_
                 diff = _descale(sj[y1:y1 + WIN, x1:x1 + WIN] * w00 + sj[y1:y1 + WIN, x1 + 1:x1 + WIN + 1] * w01
                                 + sj[y1 + 1:y1 + WIN + 1, x1:x1 + WIN] * w10 + sj[y1 + 1:y1 + WIN + 1, x1 + 1:x1 + WIN + 1] * w11,
                                 W_BITS - 5) - tmpl
-                b1 = f32(f32((diff.astype(np.int64) * dix).sum()) * FLT_SCALE)
-                b2 = f32(f32((diff.astype(np.int64) * diy).sum()) * FLT_SCALE)
+                b1 = f32(_mismatch_sum_f32(diff.astype(np.int64) * dix) * FLT_SCALE)
+                b2 = f32(_mismatch_sum_f32(diff.astype(np.int64) * diy) * FLT_SCALE)
                 dx = f32(f32(a12 * b2 - a22 * b1) * d)
                 dy = f32(f32(a12 * b1 - a11 * b2) * d)
                 nx, ny = nx + dx, ny + dy
@@ -207,5 +239,5 @@ def lk_np(prev: np.ndarray, nxt: np.ndarray, pts: np.ndarray, levels: int = MAX_
                 diff = _descale(sj[y1:y1 + WIN, x1:x1 + WIN] * w00 + sj[y1:y1 + WIN, x1 + 1:x1 + WIN + 1] * w01
                                 + sj[y1 + 1:y1 + WIN + 1, x1:x1 + WIN] * w10 + sj[y1 + 1:y1 + WIN + 1, x1 + 1:x1 + WIN + 1] * w11,
                                 W_BITS - 5) - tmpl
-                err[p] = f32(np.abs(diff).sum()) * f32(1.0 / (32 * WIN * WIN))
+                err[p] = f32(np.abs(diff).sum()) / f32(32 * WIN * WIN)      # `errval * 1.f / (32 * w * h)`: a float division
     return out, status, err

@@ -2,9 +2,11 @@
 import math
 
 import numpy as np
+from pathlib import Path
 
 from accurate_aprilgroup_tracking_b200 import synth
 
+ROOT = Path(__file__).resolve().parent.parent
 ROT_TOL = 1e-4                       # rad   (BASELINE.json north_star)
 TRANS_TOL = 1e-3 * synth.TAG_SIZE    # 1e-3 of the tag size = 20 um
 FLOW_TOL = 0.01                      # px
