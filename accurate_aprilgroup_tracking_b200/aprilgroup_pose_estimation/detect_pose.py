@@ -13,9 +13,21 @@ reference names but does not yet contain can be switched on:
 
 Both default to False, which reproduces the reference's behaviour frame by frame,
 including the in-place write of solvePnP into the guess arrays and the resulting
-aliasing of ``extrinsic_guess`` and ``prev_transform``.  Tag detection, undistortion,
+aliasing of ``extrinsic_guess`` and ``prev_transform``.  The frame ingest runs on the
+device as well: ``process_frame`` is cv.undistort + crop (and keeps the gray image of the
+result, computed in the same pass, for ``_detect_and_get_pose``), the gray conversion of
+any other BGR frame is ``agt_bgr_to_gray`` - both bit-exact against cv2.  Tag detection,
 capture and drawing are outside the accelerated path and keep using whatever
 ``apriltag`` / ``cv2`` modules the host has, exactly like the reference.
+
+Cameras.  The reference passes (mtx, dist) to solvePnP / projectPoints even though the
+frame it detects on has been undistorted and cropped by ``process_frame`` (detect_pose.py:
+509-526 with :611-619); that is reproduced as it is.  Dense refinement reads pixels, so it
+needs the camera the pixels were formed by: for a frame that came out of ``process_frame``
+that is the new camera matrix of cv.getOptimalNewCameraMatrix with the principal point moved
+by the crop offset and no distortion; for a frame handed in directly it is (mtx, no
+distortion).  A distorted frame handed in directly cannot be refined and raises - it is
+never skipped silently.
 """
 import json
 from copy import deepcopy
@@ -65,6 +77,9 @@ class PoseDetector(TransformHelper, Draw):
         self._agt = agt_cv.default_context() if device == 0 else agt_cv.HostContext(device)   # raises without a B200
         self._gray = None
         self._prev_gray = None
+        self._gray_mtx = None          # pinhole camera matrix of the pixels in self._gray (None: they are distorted)
+        self._ingest = None            # (frame returned by process_frame, its gray image, its pinhole camera matrix)
+        self._und_cache = {}           # (width, height) -> (new camera matrix, roi) of cv.getOptimalNewCameraMatrix
         self._prev_corners: List[Tuple[int, np.ndarray]] = []
         self._frame_corners: List[Tuple[int, np.ndarray]] = []
         try:
@@ -239,9 +254,11 @@ class PoseDetector(TransformHelper, Draw):
 
     def _refine_in_place(self, transformation) -> None:
         """Stage 3: dense photometric refinement; the result replaces the PnP pose inside the same arrays."""
-        if self.dist is not None and np.any(np.asarray(self.dist) != 0):
-            return          # frames reaching this point are undistorted by process_frame(); K is then not self.mtx
-        ok, rvec, tvec, _, _ = self._agt.refine_pose(self._gray, transformation[0], transformation[1], self.mtx)
+        if self._gray_mtx is None:
+            raise ValueError("use_dense_refine: this frame carries lens distortion (dist != 0) and did not come out of "
+                             "process_frame(); dense refinement needs undistorted pixels - pass frames through process_frame() "
+                             "first, as the reference's capture loop does (detect_pose.py:678)")
+        ok, rvec, tvec, _, _ = self._agt.refine_pose(self._gray, transformation[0], transformation[1], self._gray_mtx)
         if ok:
             transformation[0].reshape(-1)[:] = rvec.reshape(-1)
             transformation[1].reshape(-1)[:] = tvec.reshape(-1)
@@ -249,24 +266,43 @@ class PoseDetector(TransformHelper, Draw):
     # ------------------------------------------------------------------------------------
     # per-frame entry points (detect_pose.py:147-183, 576-619)
     # ------------------------------------------------------------------------------------
+    def _has_distortion(self) -> bool:
+        return self.dist is not None and bool(np.any(np.asarray(self.dist) != 0))
+
+    def _set_gray(self, frame: np.ndarray) -> np.ndarray:
+        """Gray image of the frame (detect_pose.py:602) and the pinhole camera its pixels were formed by."""
+        if self._ingest is not None and frame is self._ingest[0]:
+            gray, mtx = self._ingest[1], self._ingest[2]           # undistorted + converted in one pass by process_frame
+        else:
+            gray = self._agt.bgr_to_gray(frame) if frame.ndim == 3 else frame
+            mtx = None if self._has_distortion() else self.mtx
+        self._prev_gray, self._gray, self._gray_mtx = self._gray, gray, mtx
+        return gray
+
     def _detect_and_get_pose(self, frame: np.ndarray) -> None:
         self.img = frame
         height, width = frame.shape[:2]
         self.draw_frame = np.zeros(shape=[height, width, 3], dtype=np.uint8)
-        gray = bgr_to_gray(frame) if frame.ndim == 3 else frame
-        self._prev_gray, self._gray = self._gray, gray
+        gray = self._set_gray(frame)
         imgpoints_arr, objpoints_arr, tag_ids = self._obtain_detections(gray)
         if self.use_lk and len(imgpoints_arr) < MIN_TAGS:
             imgpoints_arr, objpoints_arr, tag_ids = self._track_lost_tags(imgpoints_arr, objpoints_arr, tag_ids)
         self._estimate_pose(imgpoints_arr, objpoints_arr)
 
     def undistort_frame(self, frame: np.ndarray) -> np.ndarray:
-        import cv2 as cv          # frame ingest is the step before the path
+        """detect_pose.py:147-183: cv.getOptimalNewCameraMatrix (host, 3x3 algebra, once per frame size), then cv.undistort +
+        crop on the device; the gray image of the result comes out of the same pass and waits for _detect_and_get_pose."""
         height, width = frame.shape[:2]
-        new_mtx, roi = cv.getOptimalNewCameraMatrix(self.mtx, self.dist, (width, height), 1, (width, height))
-        dst = cv.undistort(frame, self.mtx, self.dist, None, new_mtx)
-        x, y, w, h = roi
-        return dst[y:y + h, x:x + w]
+        if (width, height) not in self._und_cache:
+            import cv2 as cv
+            self._und_cache[(width, height)] = cv.getOptimalNewCameraMatrix(self.mtx, self.dist, (width, height), 1, (width, height))
+        new_mtx, roi = self._und_cache[(width, height)]
+        out, gray = self._agt.undistort_frame(frame, self.mtx, self.dist, new_mtx, roi)
+        pinhole = np.array(new_mtx, dtype=np.float64)
+        pinhole[0, 2] -= roi[0]
+        pinhole[1, 2] -= roi[1]
+        self._ingest = (out, gray, pinhole)
+        return out
 
     def process_frame(self, frame: np.ndarray) -> np.ndarray:
         return self.undistort_frame(frame) if self.dist is not None else frame

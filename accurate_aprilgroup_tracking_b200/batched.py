@@ -32,8 +32,15 @@ class BatchedPoseDetector:
 
     def __init__(self, ctx: AgtContext, n_streams: int, width: int, height: int, obj_pts: np.ndarray,
                  enhance_ape: bool = True, use_lk: bool = True, use_dense_refine: bool = True, levels: int = 4,
-                 use_graphs: bool = True):
+                 use_graphs: bool = True, tag_ids=None):
+        """``obj_pts`` [4T,3]: the group's corners in JSON key order (``PoseDetector.all_objpts``); ``tag_ids``: the ids in the
+        same order (``list(PoseDetector.extrinsics)``), default 0..T-1 - ``pack`` puts detections where their object points are."""
         t = ctx.torch
+        if obj_pts.shape[0] % 4:
+            raise ValueError("obj_pts must hold four corners per tag")
+        self.tag_pos = tag_positions(range(obj_pts.shape[0] // 4) if tag_ids is None else tag_ids)
+        if len(self.tag_pos) * 4 != obj_pts.shape[0]:
+            raise ValueError(f"{len(self.tag_pos)} tag ids for {obj_pts.shape[0] // 4} tags of object points")
         self.ctx, self.n, self.enhance_ape = ctx, int(n_streams), enhance_ape
         self.use_lk, self.use_dense_refine = use_lk, use_dense_refine
         self.n_pts = int(obj_pts.shape[0])
@@ -58,6 +65,12 @@ class BatchedPoseDetector:
         self.kernels_per_step = 0
         if use_dense_refine and ctx._model is None:
             ctx.set_synthetic_model()
+        self._epoch = getattr(ctx, "config_epoch", 0)
+
+    def pack(self, dets_per_stream):
+        """Detections [(tag_id, corners (4,2)), ...] per stream -> the (img_pts, valid, n_tags) arrays ``step`` takes, indexed by
+        the tags' positions in the group (KeyError for an id the group does not have)."""
+        return pack_detections(dets_per_stream, self.tag_pos)
 
     def reset(self):
         """Forget all stream state (fresh streams); captured graphs stay valid because the buffers are reused."""
@@ -130,6 +143,12 @@ class BatchedPoseDetector:
         self.in_img.copy_(ctx._dev(img_pts, t.float32))
         self.in_valid.copy_(ctx._dev(valid, t.uint8))
         self.in_ntags.copy_(ctx._dev(n_tags, t.int32))
+        if self._epoch != getattr(ctx, "config_epoch", 0):
+            # set_camera / set_model since the graphs were captured: they hold the camera by value and the model's pointers,
+            # so replaying them would silently keep the old ones - drop them and capture again
+            self._graphs = [None] * self.SLOTS
+            self._outs = [None] * self.SLOTS
+            self._epoch = getattr(ctx, "config_epoch", 0)
         if self.use_graphs and self._graphs[slot] is not None:
             self._graphs[slot].replay()
             out = self._outs[slot]
@@ -150,15 +169,40 @@ class BatchedPoseDetector:
         return out
 
 
-def pack_detections(dets_per_stream, n_tags_total: int = synth.NUM_TAGS):
-    """[(tag_id, corners (4,2)), ...] per stream -> (img_pts [S,4T,2] f32, valid [S,4T] u8, n_tags [S] i32)."""
+def tag_positions(tag_ids) -> dict:
+    """tag id -> position of the tag in the group, i.e. in the JSON key order that defines the corner index 4 * position + j
+    (detect_pose.py:122, :202: ``extrinsics`` is filled, and ``all_objpts`` stacked, in that order).  ``tag_ids`` is that
+    ordered sequence, e.g. ``list(PoseDetector.extrinsics)``."""
+    pos = {}
+    for k, tag in enumerate(tag_ids):
+        tag = int(tag)
+        if tag in pos:
+            raise ValueError(f"tag id {tag} appears twice in the group")
+        pos[tag] = k
+    return pos
+
+
+def pack_detections(dets_per_stream, tag_ids=None, n_tags_total: Optional[int] = None):
+    """[(tag_id, corners (4,2)), ...] per stream -> (img_pts [S,4T,2] f32, valid [S,4T] u8, n_tags [S] i32).
+
+    ``tag_ids``: the group's tag ids in JSON key order (see ``tag_positions``); a detection's corners go to the slots of its
+    tag's POSITION in that order, which is where ``all_objpts`` holds its object points (detect_pose.py:405-437 looks the
+    object points up by id, ``extrinsics[tag_id]``).  Default: ids 0..T-1 in order, the synthetic dodecahedron.  An id that is not
+    in the group raises KeyError, as the reference does (detect_pose.py:408-415 catches ValueError only)."""
+    if tag_ids is None:
+        tag_ids = range(synth.NUM_TAGS if n_tags_total is None else n_tags_total)
+    pos = tag_ids if isinstance(tag_ids, dict) else tag_positions(tag_ids)
+    total = len(pos)
+    if n_tags_total is not None and n_tags_total != total:
+        raise ValueError(f"n_tags_total={n_tags_total} but the group has {total} tags")
     s = len(dets_per_stream)
-    img = np.zeros((s, 4 * n_tags_total, 2), np.float32)
-    valid = np.zeros((s, 4 * n_tags_total), np.uint8)
+    img = np.zeros((s, 4 * total, 2), np.float32)
+    valid = np.zeros((s, 4 * total), np.uint8)
     n = np.zeros(s, np.int32)
     for i, dets in enumerate(dets_per_stream):
-        n[i] = len(dets)
         for tag, corners in dets:
-            img[i, 4 * tag:4 * tag + 4] = corners
-            valid[i, 4 * tag:4 * tag + 4] = 1
+            k = pos[int(tag)]                      # KeyError for an id outside the group
+            img[i, 4 * k:4 * k + 4] = np.asarray(corners, dtype=np.float32).reshape(4, 2)
+            valid[i, 4 * k:4 * k + 4] = 1
+        n[i] = int(valid[i].sum()) // 4            # a tag reported twice fills one slot
     return img, valid, n

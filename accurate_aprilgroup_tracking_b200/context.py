@@ -103,6 +103,7 @@ class AgtContext:
                                             d.ctypes.data_as(C.POINTER(C.c_double)) if d is not None else None, nd))
         self.mtx = np.asarray(mtx, dtype=np.float64).reshape(3, 3).copy()
         self.dist = None if dist is None else d.copy()
+        self.config_epoch = getattr(self, "config_epoch", 0) + 1      # captured CUDA graphs hold the camera by value
 
     def set_model(self, samples: np.ndarray, sample_tag: np.ndarray, normals: np.ndarray, centres: np.ndarray, pitch: float):
         s = np.ascontiguousarray(samples, dtype=np.float32)
@@ -112,6 +113,7 @@ class AgtContext:
         self._check(self.lib.agt_set_model(self.h, s.ctypes.data, tg.ctypes.data, int(s.shape[0]), n.ctypes.data,
                                            c.ctypes.data, int(n.shape[0]), float(pitch)))
         self._model = (s, tg, n, c, float(pitch))
+        self.config_epoch = getattr(self, "config_epoch", 0) + 1      # ... and the model's device pointers
 
     def set_synthetic_model(self):
         s, tg, n, c = synth.surface_model()

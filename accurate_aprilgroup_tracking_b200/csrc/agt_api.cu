@@ -30,17 +30,34 @@ int64_t layout_pyramid(agt_pyramid* p, uint8_t* base, int w, int h, int levels, 
 
 }  // namespace
 
+// Growable scratch buffers of the host entry points and of agt_refine's job list.  A CUDA graph that captured a launch reading
+// a slot holds the slot's pointer: a slot that has been handed out during a stream capture is never freed before
+// agt_destroy (growing it retires the old buffer instead), and it cannot grow DURING a capture (that would need a
+// synchronising allocation): run the sequence once eagerly at its final size first.
 int agt_scratch(agt_ctx* ctx, int slot, size_t bytes, void** out) {
   if (bytes == 0) bytes = 16;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  const bool capturing = cap == cudaStreamCaptureStatusActive;
   if (ctx->scratch_bytes[slot] < bytes) {
+    if (capturing)
+      AGT_FAIL(ctx, AGT_ERR_NOT_READY, "scratch slot %d would have to grow (%zu -> %zu bytes) during a stream capture: run the call once "
+               "outside the capture at this size first", slot, ctx->scratch_bytes[slot], bytes);
     if (ctx->scratch[slot]) {
-      AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      AGT_CUDA(ctx, cudaFree(ctx->scratch[slot]));
-      ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+      if (ctx->scratch_in_graph[slot]) {
+        if (ctx->n_retired >= (int)(sizeof(ctx->retired) / sizeof(ctx->retired[0])))
+          AGT_FAIL(ctx, AGT_ERR_NOT_READY, "too many scratch buffers kept alive for captured graphs; destroy the context and its graphs");
+        ctx->retired[ctx->n_retired++] = ctx->scratch[slot];      // a captured graph may still read it
+      } else {
+        AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        AGT_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+      }
+      ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; ctx->scratch_in_graph[slot] = 0;
     }
     AGT_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], bytes));
     ctx->scratch_bytes[slot] = bytes;
   }
+  if (capturing) ctx->scratch_in_graph[slot] = 1;
   *out = ctx->scratch[slot];
   return AGT_OK;
 }
@@ -104,6 +121,7 @@ extern "C" int agt_destroy(agt_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   for (int i = 0; i < 8; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  for (int i = 0; i < ctx->n_retired; ++i) cudaFree(ctx->retired[i]);
   if (ctx->model.samples) cudaFree(ctx->model.samples);
   if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
   if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
@@ -259,6 +277,23 @@ extern "C" int agt_pyramid_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h
     if (h_levels[l])
       AGT_CUDA(ctx, cudaMemcpy2DAsync(h_levels[l], (size_t)p.width[l], p.data[l], (size_t)p.pitch[l], (size_t)p.width[l],
                                       (size_t)p.height[l], cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  return AGT_OK;
+}
+
+extern "C" int agt_bgr_to_gray_host(agt_ctx* ctx, const uint8_t* h_bgr, int w, int h, uint8_t* h_gray) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_bgr || !h_gray || w < 1 || h < 1) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_bgr_to_gray_host: bad arguments");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t in_bytes = (size_t)w * h * 3, out_bytes = (size_t)w * h;
+  uint8_t *din, *dout;
+  int rc;
+  if ((rc = agt_scratch(ctx, 0, in_bytes, reinterpret_cast<void**>(&din)))) return rc;
+  if ((rc = agt_scratch(ctx, 1, out_bytes, reinterpret_cast<void**>(&dout)))) return rc;
+  cudaStream_t st = ctx->stream;
+  AGT_CUDA(ctx, cudaMemcpyAsync(din, h_bgr, in_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = agt_bgr_to_gray(ctx, din, w, h, (int64_t)w * 3, (int64_t)in_bytes, dout, w, (int64_t)out_bytes, 1))) return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_gray, dout, out_bytes, cudaMemcpyDeviceToHost, st));
   AGT_CUDA(ctx, cudaStreamSynchronize(st));
   return AGT_OK;
 }

@@ -57,6 +57,9 @@ struct agt_ctx {
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];
+  int scratch_in_graph[8];       // the slot's pointer was handed out during a stream capture: never freed before agt_destroy
+  void* retired[64];             // outgrown buffers a captured graph may still read
+  int n_retired;
   char err[512];
 };
 

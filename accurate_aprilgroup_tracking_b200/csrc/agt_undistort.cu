@@ -53,7 +53,7 @@ __device__ __forceinline__ void undistort_map(const agt_camera& cam, const agt_u
 __global__ void __launch_bounds__(128)
 undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__ tab, const uint8_t* __restrict__ src, int w, int h,
                       int channels, int64_t spitch, int64_t sstride, uint8_t* __restrict__ dst, int64_t dpitch, int64_t dstride,
-                      int batch) {
+                      int batch, int keep_channels) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= U.roi_w) return;
   int sx, sy;
@@ -67,6 +67,16 @@ undistort_gray_kernel(agt_camera cam, agt_undistort U, const short* __restrict__
   const int64_t o00 = (int64_t)cy0 * spitch + (int64_t)cx0 * channels, o01 = (int64_t)cy0 * spitch + (int64_t)cx1 * channels;
   const int64_t o10 = (int64_t)cy1 * spitch + (int64_t)cx0 * channels, o11 = (int64_t)cy1 * spitch + (int64_t)cx1 * channels;
   const int b0 = blockIdx.z * kFramesPerThread, b1 = min(b0 + kFramesPerThread, batch);
+  if (keep_channels) {
+    // cv::undistort alone (the frame process_frame hands back for display, detect_pose.py:611-619): the blended channels as they are
+    for (int b = b0; b < b1; ++b) {
+      const uint8_t* f = src + (int64_t)b * sstride;
+      for (int c = 0; c < channels; ++c)
+        dst[(int64_t)b * dstride + (int64_t)y * dpitch + (int64_t)x * channels + c] =
+            (uint8_t)((w00 * __ldg(f + o00 + c) + w01 * __ldg(f + o01 + c) + w10 * __ldg(f + o10 + c) + w11 * __ldg(f + o11 + c) + (1 << 14)) >> 15);
+    }
+    return;
+  }
   if (channels == 3 && cx1 == cx0 + 1 && ((spitch | sstride) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
     // interior pixel of a BGR frame: the two taps of a row are six consecutive bytes B0 G0 R0 B1 G1 R1.  Three aligned
     // word loads + two funnel shifts fetch them (half the cache wavefronts of six byte loads), one permute per channel
@@ -372,26 +382,64 @@ extern "C" int agt_undistort_to_gray(agt_ctx* ctx, const uint8_t* d_src, int w, 
     dim3 grid((ctx->und.roi_w + 127) / 128, ctx->und.roi_h, ng);
     undistort_gray_kernel<<<grid, 128, 0, ctx->stream>>>(cam, ctx->und, ctx->d_remap_tab, d_src + f0 * src_stride, w, h, channels, src_pitch,
                                                          src_stride, d_gray + f0 * dst_stride, dst_pitch, dst_stride,
-                                                         (int)(batch - f0));
+                                                         (int)(batch - f0), 0);
+    AGT_LAUNCH_CHECK(ctx);
+  }
+  return AGT_OK;
+}
+
+extern "C" int agt_undistort_frames(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int channels, int64_t src_pitch, int64_t src_stride,
+                             uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!ctx->camera_set || !ctx->undistort_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_undistort_frames: call agt_set_camera and agt_set_undistort first");
+  if (!d_src || !d_dst || batch < 0 || (channels != 1 && channels != 3) || src_pitch < (int64_t)w * channels ||
+      dst_pitch < (int64_t)ctx->und.roi_w * channels)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_undistort_frames: bad arguments");
+  if (w != ctx->und.width || h != ctx->und.height)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_undistort_frames: frame is %dx%d but agt_set_undistort was given %dx%d", w, h, ctx->und.width, ctx->und.height);
+  agt_camera cam = ctx->cam;
+  if (!cam.has_dist) { cam.k1 = cam.k2 = cam.p1 = cam.p2 = cam.k3 = 0.0; }
+  const int groups = (batch + kFramesPerThread - 1) / kFramesPerThread;
+  for (int g0 = 0; g0 < groups; g0 += 65535) {
+    const int ng = groups - g0 < 65535 ? groups - g0 : 65535;
+    const int64_t f0 = (int64_t)g0 * kFramesPerThread;
+    dim3 grid((ctx->und.roi_w + 127) / 128, ctx->und.roi_h, ng);
+    undistort_gray_kernel<<<grid, 128, 0, ctx->stream>>>(cam, ctx->und, ctx->d_remap_tab, d_src + f0 * src_stride, w, h, channels, src_pitch,
+                                                         src_stride, d_dst + f0 * dst_stride, dst_pitch, dst_stride, (int)(batch - f0), 1);
     AGT_LAUNCH_CHECK(ctx);
   }
   return AGT_OK;
 }
 
 extern "C" int agt_undistort_to_gray_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_gray) {
+  return agt_undistort_frame_host(ctx, h_src, w, h, channels, nullptr, h_gray);
+}
+
+extern "C" int agt_undistort_frame_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_frame, uint8_t* h_gray) {
   if (!ctx) return AGT_ERR_INVALID;
-  if (!ctx->undistort_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_undistort_to_gray_host: call agt_set_undistort first");
-  if (!h_src || !h_gray || w < 1 || h < 1 || (channels != 1 && channels != 3)) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_undistort_to_gray_host: bad arguments");
+  if (!ctx->undistort_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_undistort_frame_host: call agt_set_undistort first");
+  if (!h_src || (!h_gray && !h_frame) || w < 1 || h < 1 || (channels != 1 && channels != 3))
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_undistort_frame_host: bad arguments");
   AGT_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t in_bytes = (size_t)w * h * channels, out_bytes = (size_t)ctx->und.roi_w * ctx->und.roi_h;
-  uint8_t *din, *dout;
+  const size_t in_bytes = (size_t)w * h * channels, gray_bytes = (size_t)ctx->und.roi_w * ctx->und.roi_h, frame_bytes = gray_bytes * channels;
+  uint8_t *din, *dout, *dframe;
   int rc;
   if ((rc = agt_scratch(ctx, 0, in_bytes, reinterpret_cast<void**>(&din)))) return rc;
-  if ((rc = agt_scratch(ctx, 1, out_bytes, reinterpret_cast<void**>(&dout)))) return rc;
+  if ((rc = agt_scratch(ctx, 1, gray_bytes, reinterpret_cast<void**>(&dout)))) return rc;
+  if (h_frame && (rc = agt_scratch(ctx, 2, frame_bytes, reinterpret_cast<void**>(&dframe)))) return rc;
   AGT_CUDA(ctx, cudaMemcpyAsync(din, h_src, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = agt_undistort_to_gray(ctx, din, w, h, channels, (int64_t)w * channels, (int64_t)in_bytes, dout, ctx->und.roi_w, (int64_t)out_bytes, 1)))
-    return rc;
-  AGT_CUDA(ctx, cudaMemcpyAsync(h_gray, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_gray) {
+    if ((rc = agt_undistort_to_gray(ctx, din, w, h, channels, (int64_t)w * channels, (int64_t)in_bytes, dout, ctx->und.roi_w, (int64_t)gray_bytes, 1)))
+      return rc;
+    AGT_CUDA(ctx, cudaMemcpyAsync(h_gray, dout, gray_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (h_frame) {
+    if ((rc = agt_undistort_frames(ctx, din, w, h, channels, (int64_t)w * channels, (int64_t)in_bytes, dframe, (int64_t)ctx->und.roi_w * channels,
+                            (int64_t)frame_bytes, 1)))
+      return rc;
+    AGT_CUDA(ctx, cudaMemcpyAsync(h_frame, dframe, frame_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return AGT_OK;
 }

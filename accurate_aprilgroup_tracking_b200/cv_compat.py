@@ -207,6 +207,38 @@ class HostContext:
                                                         C.c_void_p(out.ctypes.data)))
         return out
 
+    def undistort_frame(self, frame, cameraMatrix, distCoeffs, newCameraMatrix, roi):
+        """The reference's undistort_frame (detect_pose.py:147-183) with ONE upload of the frame: -> (cv.undistort(frame, K, dist,
+        None, newK)[y:y+h, x:x+w], its cv.cvtColor(.., COLOR_BGR2GRAY)), both bit-exact for 8-bit frames.  The first is what
+        process_frame returns (the reference draws on it and shows it), the second is what the tracking stages read."""
+        src = np.ascontiguousarray(frame, dtype=np.uint8)
+        if src.ndim not in (2, 3) or (src.ndim == 3 and src.shape[2] != 3):
+            raise ValueError("frame must be [H,W] or [H,W,3] uint8")
+        self.use_camera(cameraMatrix, distCoeffs)
+        h, w = int(src.shape[0]), int(src.shape[1])
+        x, y, rw, rh = (int(v) for v in roi)
+        k = np.ascontiguousarray(newCameraMatrix, dtype=np.float64).reshape(9)
+        key = (k.tobytes(), w, h, x, y, rw, rh, self._cam_key)
+        if key != getattr(self, "_und_key", None):
+            self._check(self.lib.agt_set_undistort(self.h, k.ctypes.data_as(C.POINTER(C.c_double)), w, h, x, y, rw, rh))
+            self._und_key = key
+        ch = 1 if src.ndim == 2 else 3
+        out = np.empty((rh, rw) if ch == 1 else (rh, rw, 3), dtype=np.uint8)
+        gray = np.empty((rh, rw), dtype=np.uint8)
+        self._check(self.lib.agt_undistort_frame_host(self.h, C.c_void_p(src.ctypes.data), w, h, ch, C.c_void_p(out.ctypes.data),
+                                                      C.c_void_p(gray.ctypes.data)))
+        return out, gray
+
+    def bgr_to_gray(self, frame):
+        """cv.cvtColor(frame, cv.COLOR_BGR2GRAY) (detect_pose.py:602), bit-exact for 8-bit frames."""
+        src = np.ascontiguousarray(frame, dtype=np.uint8)
+        if src.ndim != 3 or src.shape[2] != 3:
+            raise ValueError("frame must be [H,W,3] uint8")
+        out = np.empty(src.shape[:2], dtype=np.uint8)
+        self._check(self.lib.agt_bgr_to_gray_host(self.h, C.c_void_p(src.ctypes.data), int(src.shape[1]), int(src.shape[0]),
+                                                  C.c_void_p(out.ctypes.data)))
+        return out
+
     def set_roi_upload(self, enable: bool) -> None:
         self._check(self.lib.agt_set_roi_upload(self.h, int(bool(enable))))
 

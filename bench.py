@@ -37,10 +37,28 @@ BYTES_PER_SAMPLE_EVAL = 36          # 16 B model record + 4 B inte
 BYTES_PER_POSE_FIXED = 156
 LK_BYTES_PER_CORNER = 5008
 PYR_BYTES_PER_1080P = 2754000
-# dram__bytes_read.sum + dram__bytes_write.sum of one dpr_kernel launch, per pose, from the ncu --set full capture
-# summarised in profiles/r01_ncu_dpr_kernel.txt (166.64 MB read + 13.44 MB written for 1024 poses of this workload with K1
-# fused into the kernel: the level-0 ROI is read from HBM, the level-1..3 ROIs it builds are written back)
-DPR_NCU_DRAM_BYTES_PER_POSE = 180.08e6 / 1024
+# Per-pose figures of one dpr_kernel launch that only a profiler can give (DRAM bytes, warp instructions issued) are NOT
+# constants of this file: they are read from the summary of the latest `ncu --set full` capture of this very command,
+# profiles/ncu_dpr_kernel.json (written by scripts/ncu_summary.py from the .ncu-rep; it records the git revision of
+# csrc/agt_dpr.cu it was taken from).  Without that file `roofline.traffic` and `roofline.issue_frac` are null.
+NCU_DPR_SUMMARY = ROOT / "profiles" / "ncu_dpr_kernel.json"
+SM_COUNT, SCHEDULERS_PER_SM = 148, 4
+
+
+def ncu_dpr_summary():
+    try:
+        return json.loads(NCU_DPR_SUMMARY.read_text())
+    except (OSError, ValueError):
+        return None
+
+
+def dpr_config(world: int, frames_per_gpu: int) -> dict:
+    """The `config` object of the headline workload - the same for the CUDA arm and the CPU (--impl reference) arm."""
+    return {"workload": "batched dense pose refinement: 1080p frames, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
+            "frames_per_gpu": frames_per_gpu,
+            "step": "K4 LM refinement to convergence with K1 fused into it (each refinement builds the region of interest of its own pyramid level from the frame, cv2.pyrDown arithmetic) + exact redo on a full pyramid of frames that left their ROI",
+            "l2": "inputs (%.1f GB of frames per GPU) are larger than L2; no flush needed" % (frames_per_gpu * CAM.width * CAM.height / 1e9),
+            "parallelism": f"frames sharded over {world} GPU(s), no collective on the path; one NCCL all-gather of the final poses of all steps"}
 
 
 def measured_peaks():
@@ -152,49 +170,59 @@ def cpu_refine(frames: np.ndarray, init: np.ndarray, workers: int, repeats: int 
     return walls, np.array([r[1] for r in res])
 
 
-def sample_frames_for_cpu(n: int, seed: int):
-    """Frames for the CPU arm: rendered by the CUDA generator when a GPU is visible (same
-    inputs as the GPU arm), else by the numpy specification of the same renderer."""
+def _render_one(args):
+    pose, seed = args
+    return synth.render(pose, CAM, seed)
+
+
+def sample_frames_for_cpu(n: int, seed: int, workers: int):
+    """Frames for the CPU arm: the numpy specification of the renderer (synth.render), in this process tree only - the CPU arm
+    must not touch the CUDA library (its record lists the native libraries the process mapped)."""
     truth, init = make_poses(n, seed)
-    try:
-        import torch
-        has_gpu = torch.cuda.is_available()
-    except Exception:
-        has_gpu = False
-    if has_gpu:
-        from accurate_aprilgroup_tracking_b200.context import AgtContext
-        ctx = AgtContext(0, CAM.mtx, None)
-        pyr = ctx.alloc_pyramid(n, CAM.width, CAM.height, 1)
-        ctx.render(pyr, truth, np.arange(n) + seed)
-        frames = pyr.frames.cpu().numpy()
-        ctx.close()
+    jobs = [(truth[i], seed + i) for i in range(n)]
+    if workers > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            frames = np.stack(pool.map(_render_one, jobs, chunksize=1))
     else:
-        frames = np.stack([synth.render(truth[i], CAM, seed + i) for i in range(n)])
+        frames = np.stack([_render_one(j) for j in jobs])
     return frames, truth, init
 
 
+def native_library_mapped() -> bool:
+    try:
+        return "libagt" in Path("/proc/self/maps").read_text()
+    except OSError:
+        return False
+
+
 def run_reference(args):
+    """CPU arm: oracle/dpr_oracle.py (there is no reference code for dense refinement) on every host core, same metric,
+    config object and step count as the CUDA arm; a step refines a bounded sample of the 4096-frame batch."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     n = max(workers * 8, 32)                       # frames per step: a bounded sample of the 4096-frame workload
-    frames, truth, init = sample_frames_for_cpu(n, 2000)
-    steps = min(args.steps, 10)                    # keep the whole run within a couple of minutes
-    walls, _ = cpu_refine(frames, init, workers, repeats=args.warmup + steps)
-    times = walls[args.warmup:]
+    frames, truth, init = sample_frames_for_cpu(n, 2000, workers)
+    steps = args.steps                             # the CUDA arm's step count (a step takes ~0.2 s on 16 cores)
+    walls, _ = cpu_refine(frames, init, workers, repeats=max(args.warmup, 1) + steps)
+    times = walls[max(args.warmup, 1):]
     total = sum(times)
     value = n * len(times) / total
+    assert not native_library_mapped(), "the CPU arm must not load libagt.so"
     line = {
         "impl": "reference", "metric": "refined poses/sec", "value": value, "unit": "poses/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched dense pose refinement, 1080p, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
-                   "frames_per_step": n, "note": "CPU oracle (numpy/OpenCV pyramid + LM); no reference code exists for this stage"},
+        "config": dpr_config(args.gpus, args.frames),
         "cpu_baseline": {"value": value, "unit": "poses/s", "cores": workers, "kind": "port",
-                         "sample": f"{n} frames per step, {workers} processes, cv2.pyrDown pyramid + oracle/dpr_oracle.py"},
+                         "sample": f"{n} frames of the batch per step (synth.render, the numpy specification of the frame generator), "
+                                   f"{workers} processes with one BLAS thread each, cv2.pyrDown pyramid + oracle/dpr_oracle.py; "
+                                   "no reference code exists for this stage"},
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "native_library_mapped": native_library_mapped(),
     }
     print(json.dumps(line), flush=True)
 
@@ -225,8 +253,13 @@ def run_gpu(args):
         nb = min(512, B - b0)
         ctx.render(pyr, truth[b0:b0 + nb], np.arange(b0, b0 + nb) + 2000 + 7919 * rank, offset=b0, batch=nb)
     d_init = torch.as_tensor(init, dtype=torch.float64, device=ctx.tdev).reshape(B, 1, 6)
-    gathered = [torch.empty((world * B, 6), dtype=torch.float64, device=ctx.tdev) for _ in range(2)] if world > 1 else None
-    pending, step_no, keep = [None], [0], [None, None]
+    # every step's poses are kept on the device ([steps][B][6] f64 per rank) and gathered ONCE, after the last step and inside
+    # the timed region: the path itself has no exchange step, and a per-step collective only coupled the
+    # ranks step by step (round 1: 5.8 % slower at 8 GPUs)
+    n_keep = max(args.steps, 1)
+    all_poses = torch.zeros((n_keep, B, 6), dtype=torch.float64, device=ctx.tdev)
+    gathered = torch.empty((world, n_keep, B, 6), dtype=torch.float64, device=ctx.tdev) if world > 1 else None
+    step_no = [0]
     torch.cuda.synchronize()
 
     redo = torch.empty(B, dtype=torch.uint8, device=ctx.tdev)
@@ -242,22 +275,13 @@ def run_gpu(args):
         ctx.build_pyramid_masked(pyr, redo)
         ctx.refine(pyr, d_init, 1, mask=redo, out=res)
         if ev: ev[2].record()
-        if world > 1:
-            # the only collective: gather the final poses.  Issued asynchronously (NCCL's own stream waits for this
-            # step's kernels) into one of two buffers, so that it travels while the next step computes; the handle of
-            # the previous step is waited for first, and the last one before the timed region ends.
-            if pending[0] is not None:
-                pending[0].wait()
-            k = step_no[0] & 1
-            step_no[0] += 1
-            keep[k] = res["pose"]                                 # keep the source alive until its gather has run
-            pending[0] = dist.all_gather_into_tensor(gathered[k], res["pose"].reshape(B, 6), async_op=True)
+        all_poses[step_no[0] % n_keep].copy_(res["pose"].reshape(B, 6))
+        step_no[0] += 1
         return res
 
     def drain():
-        if pending[0] is not None:
-            pending[0].wait()
-            pending[0] = None
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.reshape(world * n_keep * B, 6), all_poses.reshape(n_keep * B, 6))
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -265,6 +289,7 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         res = step()
     drain()
+    step_no[0] = 0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -276,13 +301,24 @@ def run_gpu(args):
     t_begin.record()
     for k in range(args.steps):
         res = step(ev[k])
-    drain()                                                       # the last gather is inside the timed region
+    drain()                                                       # the one gather of all poses is inside the timed region
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    gather_ok = True
+    if world > 1:
+        # every rank holds every rank's poses: its own block is bit-identical, and all ranks agree on a checksum of the whole
+        gather_ok = bool(torch.equal(gathered[rank], all_poses))
+        chk = gathered.sum(dim=(1, 2, 3)).clone()
+        ref = chk.clone()
+        dist.broadcast(ref, 0)
+        gather_ok = gather_ok and bool(torch.equal(chk, ref)) and bool(torch.isfinite(chk).all())
+        flag = torch.tensor([1.0 if gather_ok else 0.0], dtype=torch.float64, device=ctx.tdev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item() == 1.0)
     elapsed_ms = t_begin.elapsed_time(t_end)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=ctx.tdev)
     if world > 1:
@@ -321,6 +357,7 @@ def run_gpu(args):
     algo_bytes = float((BYTES_PER_SAMPLE_EVAL * nvalid * evals).sum() + BYTES_PER_POSE_FIXED * B)
     peak, peak_kind = measured_peaks()
     achieved = algo_bytes / (dpr_ms * 1e-3) / 1e9
+    ncu = ncu_dpr_summary()
 
     # ---- e2e through the host-buffer C-ABI entry point: every rank at once (they share the host's memory and PCIe
     #      root complexes), timed by wall clock around the blocking call, max over ranks ----
@@ -382,26 +419,34 @@ def run_gpu(args):
                "max_trans_diff_vs_gpu_m": float(np.abs(cpu_pose[:, 3:] - pose[:ns, 3:]).max())}
 
     value = B * world * args.steps / (elapsed_ms * 1e-3)
+    sm_mhz = (clocks or {}).get("sm_mhz") or None
+    roofline = {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "issue_frac": None, "peak_kind": peak_kind, "algorithmic_bytes": algo_bytes,
+                "note": "per launch of the step (setup launch + dpr_kernel including its fused pyrDown); algorithmic bytes = 36 B x valid samples x "
+                        "evaluations + 156 B per pose (SURVEY.md 8d), evaluation and sample counts returned by the kernel.  The ROI is read once (and "
+                        "its pyramid level built) into shared memory and reused by every LM evaluation, so real DRAM traffic (`traffic`) is far "
+                        "BELOW the algorithmic bytes and the kernel is bound by instruction issue: `issue_frac` = warp instructions issued / "
+                        "(148 SMs x 4 schedulers x SM clock x kernel time) is the binding roofline"}
+    if ncu is not None:
+        scale = float((nvalid * evals).sum()) / max(float(ncu.get("sample_evals", 0.0)), 1.0)      # work of this launch / work of the captured one
+        roofline["traffic"] = float(ncu["dram_bytes"]) * B / float(ncu["poses"])
+        if sm_mhz:
+            roofline["issue_frac"] = float(ncu["warp_instructions"]) * scale / (SM_COUNT * SCHEDULERS_PER_SM * sm_mhz * 1e6 * dpr_ms * 1e-3)
+        roofline["ncu"] = {k: ncu.get(k) for k in ("source", "poses", "dram_bytes", "warp_instructions", "sample_evals", "issue_active_pct",
+                                                  "kernel_ms_under_ncu", "agt_dpr_cu_sha256")}
     line = {
         "metric": "refined poses/sec", "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batched dense pose refinement: 1080p frames, 12-tag dodecahedron, 20172 surface samples, 1 hypothesis",
-                   "frames_per_gpu": B, "step": "K4 LM refinement to convergence with K1 fused into it (each refinement builds the region of interest of its own pyramid level from the frame, cv2.pyrDown arithmetic) + exact redo on a full pyramid of frames that left their ROI",
-                   "l2": "inputs (%.1f GB of frames per GPU) are larger than L2; no flush needed" % (B * CAM.width * CAM.height / 1e9),
-                   "parallelism": f"frames sharded over {world} GPU(s), no collective on the path; NCCL all-gather of final poses"},
-        "gpu_launches": int(launches),
+        "config": dpr_config(world, B),
+        "gpu_launches": int(launches), "all_ranks_hold_all_poses": gather_ok,
         "kernel_ms": {"dense_refinement_with_fused_pyramid": dpr_ms, "redo_pass": redo_ms,
                       "dense_refinement_on_built_pyramid": k4_only_ms, "full_frame_pyramid": full_pyr_ms},
         "fused_equals_built_pyramid_path": fused_equals_plain,
         "frames_redone_on_full_pyramid": n_redo,
         "lm": {"mean_evals": float(evals.mean()), "max_evals": int(evals.max()), "mean_samples": float(nvalid.mean()),
                "converged_frac": float((status == 1).mean()), "median_trans_err_vs_truth_m": float(np.median(dt))},
-        "roofline": {"bound": "hbm", "kernel": "dpr_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": DPR_NCU_DRAM_BYTES_PER_POSE * B, "peak_kind": peak_kind, "algorithmic_bytes": algo_bytes,
-                     "note": "per launch of the step (setup launch + dpr_kernel including its fused pyrDown); algorithmic bytes = 36 B x valid samples x evaluations + 156 B per pose (SURVEY.md 8d); "
-                             "traffic = ncu dram bytes (profiles/r01_ncu_dpr_kernel.txt): the ROI is read once (and its pyramid level built) into shared memory and "
-                             "reused by every LM evaluation, so the kernel is instruction-issue / latency bound, not HBM bound"},
+        "roofline": roofline,
         "pyramid_roofline": {"kernel": "pyr_down_stream_kernel (full frames, 3 levels)", "bound": "hbm",
                              "achieved": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                              "frac": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9 / peak},
@@ -683,7 +728,7 @@ def run_config1(args):
         for f in range(n):
             t0 = time.perf_counter()
             det.img = None
-            det._prev_gray, det._gray = det._gray, frames[f]
+            det._set_gray(frames[f])
             lists = det._lists_from_detections([_Det(t, c) for t, c in dets_all[f]])
             if len(lists[0]) < 2:
                 lists = det._track_lost_tags(*lists)

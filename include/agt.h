@@ -104,6 +104,13 @@ int agt_undistort_to_gray(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int 
                           int64_t src_stride, uint8_t* d_gray, int64_t dst_pitch, int64_t dst_stride, int batch);
 /* One frame from host memory: h_src[h][w][channels] -> h_gray[roi_h][roi_w]. */
 int agt_undistort_to_gray_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_gray);
+/* cv::undistort + crop alone, channels kept: d_dst[batch][roi_h][dst_pitch] = undistort(frame, K, dist, None, new_K)[roi] - the frame
+ * undistort_frame returns (detect_pose.py:174-181), which the reference goes on to draw on and display. */
+int agt_undistort_frames(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int channels, int64_t src_pitch, int64_t src_stride,
+                  uint8_t* d_dst, int64_t dst_pitch, int64_t dst_stride, int batch);
+/* process_frame (detect_pose.py:611-619) for one host frame with one upload: h_frame[roi_h][roi_w][channels] (may be NULL) as
+ * agt_undistort, h_gray[roi_h][roi_w] (may be NULL) as agt_undistort_to_gray. */
+int agt_undistort_frame_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_frame, uint8_t* h_gray);
 
 /* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
 /* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
@@ -251,6 +258,8 @@ int agt_lk_host(agt_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int 
 /* Pyramid of one host image: h_levels[l] receives level l (l >= 1), tightly packed. */
 int agt_pyramid_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int levels, uint8_t* const* h_levels);
 int agt_scharr_host(agt_ctx* ctx, const uint8_t* h_img, int w, int h, int16_t* h_out);
+/* cv.cvtColor(frame, cv.COLOR_BGR2GRAY) (detect_pose.py:602) of one host frame h_bgr[h][w][3] -> h_gray[h][w]. */
+int agt_bgr_to_gray_host(agt_ctx* ctx, const uint8_t* h_bgr, int w, int h, uint8_t* h_gray);
 /* End-to-end batched refinement from HOST frames [batch][h][w] (pinned memory
  * recommended): uploads in chunks overlapped with pyramid construction and
  * refinement, downloads poses.  h_init[batch][n_hyp][6]; outputs as agt_refine

@@ -20,8 +20,11 @@ from oracle import ape_oracle, dpr_oracle, lk_oracle
 
 
 class PipelineOracle(ape_oracle.ApeOracle):
-    def __init__(self, group, mtx, model: dpr_oracle.Model, use_lk=True, use_dense_refine=True):
-        super().__init__(group, mtx, None, True)
+    def __init__(self, group, mtx, model: dpr_oracle.Model, use_lk=True, use_dense_refine=True, dist=None):
+        """``dist``: the lens model the reference hands to solvePnP / projectPoints (detect_pose.py:509-526) - also for frames
+        that process_frame has already undistorted, a quirk of the reference that is kept.  Dense refinement reads pixels and
+        uses ``refine_mtx`` of the frame (see ``frame``), never ``dist``."""
+        super().__init__(group, mtx, dist, True)
         self.model = model
         self.use_lk, self.use_dense_refine = use_lk, use_dense_refine
         self.prev_gray: Optional[np.ndarray] = None
@@ -32,14 +35,17 @@ class PipelineOracle(ape_oracle.ApeOracle):
     def _refine(self, pose):
         """Dense refinement in place (the result lives in the same arrays solvePnP returned, dtype preserved)."""
         init = np.concatenate([np.asarray(pose[0], dtype=np.float64).ravel(), np.asarray(pose[1], dtype=np.float64).ravel()])
-        out = dpr_oracle.refine(lk_oracle.pyramid_cv(self.gray, 4), self.model, self.mtx, init)
+        out = dpr_oracle.refine(lk_oracle.pyramid_cv(self.gray, 4), self.model, self.refine_mtx, init)
         if out["status"] != dpr_oracle.ST_NONE:
             pose[0].reshape(-1)[:] = out["pose"][:3]
             pose[1].reshape(-1)[:] = out["pose"][3:]
 
-    def frame(self, gray: np.ndarray, dets: Sequence[Tuple[int, np.ndarray]]):
-        """One frame: gray (H,W) u8 + accepted detections [(tag_id, corners (4,2))]."""
+    def frame(self, gray: np.ndarray, dets: Sequence[Tuple[int, np.ndarray]], refine_mtx=None):
+        """One frame: gray (H,W) u8 + accepted detections [(tag_id, corners (4,2))].  ``refine_mtx``: pinhole camera matrix of the
+        pixels in ``gray`` when it is not ``mtx`` - for a frame undistorted and cropped by undistort_frame (detect_pose.py:147-183)
+        the new camera matrix with its principal point moved by the crop offset."""
         self.prev_gray, self.gray = self.gray, gray
+        self.refine_mtx = self.mtx if refine_mtx is None else np.asarray(refine_mtx, dtype=np.float64)
         dets = [(t, np.asarray(c, dtype=np.float64).reshape(4, 2)) for t, c in dets]
         self.tracked = 0
         if self.use_lk and len(dets) < ape_oracle.MIN_TAGS and self.prev_gray is not None and self.prev_corners:

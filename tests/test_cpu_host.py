@@ -219,3 +219,27 @@ def test_numa_binding_helpers(tmp_path, monkeypatch):
     (dev / "numa_node").write_text("-1\n")
     with sharding.on_gpu_numa_node(0, sysfs=str(tmp_path)) as node:
         assert node is None
+
+
+def test_pack_detections_maps_tag_ids_to_their_position_in_the_group():
+    """A real april_group.json has arbitrary ids in arbitrary key order: corner index = 4 * (position of the tag in the JSON)
+    + j (detect_pose.py:122, :202), and the reference looks object points up by id (detect_pose.py:405-437).  The packed
+    layout must therefore go by position, not by id (round 1 wrote to slot 4 * id)."""
+    from accurate_aprilgroup_tracking_b200.batched import pack_detections, tag_positions
+    ids = [7, 3, 42, 19]                                   # JSON key order
+    c = lambda v: np.full((4, 2), float(v)) + np.arange(8).reshape(4, 2)
+    dets = [[(42, c(420)), (7, c(70))], [(19, c(190))], []]
+    img, valid, n = pack_detections(dets, ids)
+    assert img.shape == (3, 16, 2) and valid.shape == (3, 16) and n.tolist() == [2, 1, 0]
+    assert np.array_equal(img[0, 8:12], c(420)) and np.array_equal(img[0, 0:4], c(70))       # 42 is the third tag, 7 the first
+    assert valid[0].tolist() == [1] * 4 + [0] * 4 + [1] * 4 + [0] * 4
+    assert np.array_equal(img[1, 12:16], c(190)) and valid[1].tolist() == [0] * 12 + [1] * 4
+    with pytest.raises(KeyError):                          # unknown id: the reference's extrinsics[tag_id] raises KeyError too
+        pack_detections([[(5, c(0))]], ids)
+    with pytest.raises(ValueError):
+        tag_positions([1, 2, 1])
+    # default = the synthetic dodecahedron, ids 0..11 in order
+    img, valid, n = pack_detections([[(11, c(1))]])
+    assert img.shape == (1, 48, 2) and valid[0, 44:].all() and n[0] == 1
+    # the same tag reported twice fills one slot
+    assert pack_detections([[(3, c(1)), (3, c(2))]], ids)[2][0] == 1

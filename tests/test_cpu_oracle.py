@@ -147,41 +147,17 @@ def test_dpr_oracle_jacobian_is_derivative_of_smoothed_cost():
         assert abs(np.mean(num[sel] - jac[sel, k])) < 0.02 * max(1.0, np.abs(jac[sel, k]).mean())
 
 
-def test_dpr_oracle_minimiser_matches_scipy():
-    """Sanity pin of the LM loop: scipy's MINPACK LM on the same residual/Jacobian lands in the same basin.
-    The photometric cost of a bilinear-sampled binary texture is rough below ~3e-4 rad (different optimisers stop at
-    slightly different points whose costs agree to 1e-4), so this is NOT the parity bar - that is GPU vs this oracle."""
-    from scipy.optimize import least_squares
-    g = np.load(GOLDEN / "dpr_case.npz")
-    model = util.dpr_model()
-    i = 1
-    pyr = lk_oracle.pyramid_cv(g["frames"][i], 4)
-    ev = dpr_oracle.Evaluator(pyr, model, g["mtx"], g["init"][i])
-    r_init, t_init = dpr_oracle.rodrigues(g["init"][i][:3]), g["init"][i][3:]
-
-    def fun(p):
-        return ev.residuals(dpr_oracle.rodrigues(p[:3]) @ r_init, t_init + p[3:], want_jac=False)[0]
-
-    def jac(p):
-        return ev.residuals(dpr_oracle.rodrigues(p[:3]) @ r_init, t_init + p[3:])[2]
-
-    sol = least_squares(fun, np.zeros(6), jac=jac, method="lm", xtol=1e-12, ftol=1e-12, gtol=1e-12, max_nfev=200)
-    pose_scipy = np.concatenate([dpr_oracle.log_rotation(dpr_oracle.rodrigues(sol.x[:3]) @ r_init), t_init + sol.x[3:]])
-    ours = dpr_oracle.refine(pyr, model, g["mtx"], g["init"][i])
-    dr, dt = util.pose_diff(ours["pose"], pose_scipy)
-    assert dr < 1e-3 and dt < 5e-5
-    assert abs(ours["cost"] - 0.5 * float(fun(sol.x) @ fun(sol.x))) < 1e-3 * ours["cost"]
-
-
 def test_dpr_multi_hypothesis_tie_breaks_to_lowest_index():
     g = np.load(GOLDEN / "dpr_case.npz")
     model = util.dpr_model()
     pyr = lk_oracle.pyramid_cv(g["frames"][1], 4)
     init = np.stack([g["init"][1], g["init"][1], g["truth"][1]])
     best, runs = dpr_oracle.refine_multi(pyr, model, g["mtx"], init)
-    score = [2 * r["cost"] / r["n_valid"] for r in runs]
-    assert best == int(np.argmin(score))
-    assert score[0] == score[1] and (best != 1)
+    score = np.array([2 * r["cost"] / r["n_valid"] for r in runs])
+    # the lowest index within SELECT_TIE of the best score: runs 0 and 1 are identical, run 2 (started at the truth) ends in
+    # the same fixed point with a score that differs in the 6th digit or so - still a tie, so index 0 wins
+    assert best == int(np.nonzero(score <= score.min() * (1 + dpr_oracle.SELECT_TIE))[0][0])
+    assert score[0] == score[1] and best == 0
 
 
 # ---------------------------------------------------------------------------- whole path (BASELINE config 1 shape)

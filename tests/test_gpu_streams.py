@@ -42,7 +42,7 @@ def test_batched_streams_match_single_stream_detector(ctxvga, detector_factory):
         for s in range(n_streams):
             det = singles[s]
             det.img = None
-            det._prev_gray, det._gray = det._gray, frames[s]
+            det._set_gray(frames[s])
             lists = det._lists_from_detections([_Det(t, c) for t, c in dets[s]])
             if len(lists[0]) < 2:
                 lists = det._track_lost_tags(*lists)
