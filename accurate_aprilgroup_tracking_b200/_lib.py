@@ -85,6 +85,7 @@ PROTOTYPES = {
     "agt_pyramid_host": (_I, [_VP, _VP, _I, _I, _I, C.POINTER(_VP)]),
     "agt_scharr_host": (_I, [_VP, _VP, _I, _I, _VP]),
     "agt_set_roi_upload": (_I, [_VP, _I]),
+    "agt_set_upload_threads": (_I, [_VP, _I]),
     "agt_last_h2d_bytes": (_I64, [_VP]),
     "agt_refine_host": (_I, [_VP, _VP, _I, _I, _I, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP]),
 }

@@ -1,5 +1,7 @@
 // Context lifecycle, configuration and the host-buffer entry points of libagt.so.
 #include <new>
+#include <thread>
+#include <vector>
 
 #include <stdlib.h>
 #include <chrono>
@@ -111,6 +113,10 @@ extern "C" int agt_create(int device, agt_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->stream = ctx->own_stream;
   ctx->roi_upload = 1;
+  {
+    unsigned hc = std::thread::hardware_concurrency();
+    ctx->upload_threads = hc == 0 ? 4 : (hc < 8 ? (int)hc : 8);
+  }
   *out = ctx;
   return AGT_OK;
 }
@@ -125,6 +131,8 @@ extern "C" int agt_destroy(agt_ctx* ctx) {
   if (ctx->model.samples) cudaFree(ctx->model.samples);
   if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
   if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
+  if (ctx->h_prects) cudaFreeHost(ctx->h_prects);
+  for (int k = 0; k < 2; ++k) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->ev_stage[k]) cudaEventDestroy(ctx->ev_stage[k]); }
   for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -387,6 +395,45 @@ roi_gather_kernel(const uint8_t* __restrict__ host_frames, int w, int h, const a
   }
 }
 
+// Pageable host frames (a plain numpy array): the copy engine cannot read them, and one 2-D copy per frame goes through the
+// driver's own staging at ~7 us of CPU time each.  Instead a few host threads pack the ROI rows of a chunk into a pinned
+// staging buffer (double-buffered), one cudaMemcpyAsync moves the packed chunk, and this kernel puts the rows where the
+// refinement reads them.  rect = (x0, y0, x1, y1) with x % 16 == 0, off = byte offset of the rectangle in the packed buffer.
+struct agt_pack_rect { int x0, y0, x1, y1; long long off; };
+
+__global__ void __launch_bounds__(256)
+roi_scatter_kernel(const uint8_t* __restrict__ packed, const agt_pack_rect* __restrict__ rects, uint8_t* __restrict__ dst,
+                   int64_t dst_pitch, int64_t dst_stride, int n_rects) {
+  for (int ri = blockIdx.x; ri < n_rects; ri += gridDim.x) {
+    const agt_pack_rect r = rects[ri];
+    const int cw = (r.x1 - r.x0) >> 4, rows = r.y1 - r.y0;
+    if (cw <= 0 || rows <= 0) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(packed + r.off);
+    uint8_t* out = dst + (int64_t)ri * dst_stride + (int64_t)r.y0 * dst_pitch + r.x0;
+    for (int i = threadIdx.x; i < cw * rows; i += blockDim.x) {
+      const int y = i / cw, c = i - y * cw;
+      *reinterpret_cast<uint4*>(out + (int64_t)y * dst_pitch + 16 * c) = src[i];
+    }
+  }
+}
+
+static void pack_rows(const uint8_t* h_frames, int w, int h, const int* src_frame, const agt_pack_rect* rects, int i0, int i1, uint8_t* stage) {
+  for (int i = i0; i < i1; ++i) {
+    const agt_pack_rect& r = rects[i];
+    const size_t rw = (size_t)(r.x1 - r.x0);
+    const uint8_t* src = h_frames + (int64_t)src_frame[i] * w * h + (int64_t)r.y0 * w + r.x0;
+    uint8_t* dst = stage + r.off;
+    for (int y = r.y0; y < r.y1; ++y, src += w, dst += rw) memcpy(dst, src, rw);
+  }
+}
+
+extern "C" int agt_set_upload_threads(agt_ctx* ctx, int threads) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (threads < 0 || threads > 64) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_upload_threads: 0 (one 2-D copy per frame) .. 64");
+  ctx->upload_threads = threads;
+  return AGT_OK;
+}
+
 static bool roi_rect_l0(const agt_ctx* ctx, const agt_pyramid& one, const double* init, int n_hyp, int* X0, int* Y0, int* X1,
                         int* Y1) {
   int32_t r[4];
@@ -442,6 +489,39 @@ static int refine_pass(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int 
     } else if (!roi && contiguous_ids && tight) {
       AGT_CUDA(ctx, cudaMemcpyAsync(p.data[0], h_frames + (int64_t)b0 * w * h, (size_t)nb * w * h, cudaMemcpyHostToDevice, cp));
       ctx->last_h2d_bytes += (int64_t)nb * w * h;
+    } else if (roi && ctx->upload_threads > 0 && (w & 15) == 0 && ctx->h_stage[0] != nullptr) {
+      // pageable frames: pack the chunk's ROI rows into pinned staging with a few threads, one copy, one scatter launch
+      agt_pack_rect* hr = ctx->h_prects + b0;
+      std::vector<int> src_frame((size_t)nb);
+      long long off = 0;
+      for (int i = 0; i < nb; ++i) {
+        int f = ids ? ids[b0 + i] : b0 + i;
+        src_frame[(size_t)i] = f;
+        agt_pack_rect r = {0, 0, 0, 0, off};
+        if (!roi_rect_l0(ctx, one, h_init + (int64_t)f * n_hyp * 6, n_hyp, &r.x0, &r.y0, &r.x1, &r.y1)) r.x0 = r.x1 = r.y0 = r.y1 = 0;
+        off += (long long)(r.x1 - r.x0) * (r.y1 - r.y0);
+        hr[i] = r;
+      }
+      if ((size_t)off > ctx->stage_bytes)
+        AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_refine_host: ROI rectangles of a chunk (%lld bytes) exceed the staging buffer", off);
+      // the staging buffer of this parity was last read by the copy of chunk c-2
+      if (c >= 2) AGT_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage[s]));
+      {
+        const int nt = ctx->upload_threads < nb ? ctx->upload_threads : nb;
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t)
+          pool.emplace_back(pack_rows, h_frames, w, h, src_frame.data(), hr, (int)((int64_t)nb * t / nt), (int)((int64_t)nb * (t + 1) / nt),
+                            ctx->h_stage[s]);
+        pack_rows(h_frames, w, h, src_frame.data(), hr, 0, (int)((int64_t)nb / nt), ctx->h_stage[s]);
+        for (auto& th : pool) th.join();
+      }
+      uint8_t* dpk = ctx->d_stage + (size_t)s * ctx->stage_bytes;
+      AGT_CUDA(ctx, cudaMemcpyAsync(dpk, ctx->h_stage[s], (size_t)off, cudaMemcpyHostToDevice, cp));
+      AGT_CUDA(ctx, cudaEventRecord(ctx->ev_stage[s], cp));
+      AGT_CUDA(ctx, cudaMemcpyAsync(ctx->d_prects + b0, hr, sizeof(agt_pack_rect) * nb, cudaMemcpyHostToDevice, cp));
+      roi_scatter_kernel<<<nb < 296 ? nb : 296, 256, 0, cp>>>(dpk, ctx->d_prects + b0, p.data[0], p.pitch[0], p.frame_stride[0], nb);
+      AGT_LAUNCH_CHECK(ctx);
+      ctx->last_h2d_bytes += off;
     } else {
       for (int i = 0; i < nb; ++i) {
         int f = ids ? ids[b0 + i] : b0 + i;
@@ -521,6 +601,37 @@ extern "C" int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int
       ctx->host_frames_dev = static_cast<const uint8_t*>(attr.devicePointer);     // pinned + mapped: gather by kernel
     else
       cudaGetLastError();                                                          // pageable: per-frame 2-D copies
+    if (!ctx->host_frames_dev && ctx->upload_threads > 0 && (w & 15) == 0) {
+      // pageable frames: pinned staging (2 x one chunk of the largest rectangle a refinement can ask for) + packed device twin
+      agt_pyramid one;
+      layout_pyramid(&one, nullptr, w, h, levels, 1);
+      size_t need = 0, cur = 0;
+      for (int f = 0; f < batch; ++f) {
+        int X0, Y0, X1, Y1;
+        if (roi_rect_l0(ctx, one, h_init + (int64_t)f * n_hyp * 6, n_hyp, &X0, &Y0, &X1, &Y1)) cur += (size_t)(X1 - X0) * (Y1 - Y0);
+        if ((f + 1) % chunk == 0 || f + 1 == batch) { need = cur > need ? cur : need; cur = 0; }
+      }
+      need = align_up(need + 256, 4096);
+      if (ctx->stage_bytes < need) {
+        for (int k = 0; k < 2; ++k) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); ctx->h_stage[k] = nullptr; }
+        ctx->stage_bytes = 0;
+        for (int k = 0; k < 2; ++k) AGT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stage[k]), need));
+        ctx->stage_bytes = need;
+      }
+      void* dtmp;
+      if ((rc = agt_scratch(ctx, 6, 2 * ctx->stage_bytes, &dtmp))) return rc;
+      ctx->d_stage = static_cast<uint8_t*>(dtmp);
+      if (ctx->prect_capacity < batch) {
+        if (ctx->h_prects) cudaFreeHost(ctx->h_prects);
+        ctx->h_prects = nullptr; ctx->prect_capacity = 0;
+        AGT_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_prects), sizeof(agt_pack_rect) * (size_t)batch));
+        ctx->prect_capacity = batch;
+      }
+      if ((rc = agt_scratch(ctx, 4, sizeof(agt_pack_rect) * (size_t)batch, &dtmp))) return rc;
+      ctx->d_prects = static_cast<agt_pack_rect*>(dtmp);
+      for (int k = 0; k < 2; ++k)
+        if (!ctx->ev_stage[k]) AGT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_stage[k], cudaEventDisableTiming));
+    }
     if (ctx->host_frames_dev) {
       if (ctx->rect_capacity < batch) {
         if (ctx->h_rects) cudaFreeHost(ctx->h_rects);

@@ -54,6 +54,15 @@ struct agt_ctx {
   struct agt_roi_rect* h_rects;  // pinned ROI rectangle lists (double-buffered)
   struct agt_roi_rect* d_rects;
   int rect_capacity;
+  // pageable host frames: pinned staging (double-buffered) the upload threads pack ROI rows into, and its device twin
+  int upload_threads;            // 0: one 2-D copy per frame
+  uint8_t* h_stage[2];
+  size_t stage_bytes;
+  uint8_t* d_stage;
+  cudaEvent_t ev_stage[2];
+  struct agt_pack_rect* h_prects;
+  struct agt_pack_rect* d_prects;
+  int prect_capacity;
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];

@@ -52,7 +52,7 @@ constexpr double AITKEN_COS2 = 0.64, AITKEN_QMAX = 0.75, ALPHA_MIN = 0.25, ALPHA
 // a trial pose is accepted unless the cost rises by more than this fraction (oracle/dpr_oracle.py: the Scharr gradient is not
 // the exact derivative of the bilinear interpolant, so near convergence the cost moves by ~1e-5 of itself either way; the
 // slack lets the loop contract onto J^T r = 0 instead of stalling where that noise first rejects a step)
-constexpr double ACCEPT_SLACK = 1e-3;
+constexpr double ACCEPT_SLACK = 1e-2;
 
 struct DprShared {
   // trial pose: float64 for the projection, float32 for the Jacobian
@@ -86,6 +86,10 @@ struct DprShared {
   int have_prev;
   int nc, evals, status;
 };
+
+// Two CTAs per SM: dynamic + static shared memory + the 1 KB the driver reserves per CTA must fit half of the 228 KB of an
+// SM.  (Round 2 found this the hard way: 96 bytes of new LM state left one CTA per SM and made the kernel 1.5x slower.)
+static_assert(2 * (TILE_BYTES + PB_BYTES + (int)sizeof(DprShared) + 1024) <= 233472, "dpr_kernel must keep 2 CTAs per SM");
 
 // (L2-coherent loads: with K1 fused the level image is written by this very launch, so the read-only path is out)
 __device__ __forceinline__ uint32_t ld4_global(const uint8_t* p) {
@@ -718,7 +722,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
           if (accept) {
 #pragma unroll
             for (int q = 0; q < 6; ++q) S.dprev[q] = S.dgn[q];
-            have_prev = 1;
+            have_prev = S.lam <= LAMBDA0;        // S.lam: the damping the accepted step was solved with
           } else {
             have_prev = 0;
             alpha = 1.0;
@@ -731,7 +735,10 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
 #pragma unroll
           for (int q = 0; q < 6; ++q) { A[agt_hk(q, q)] = fma(lam, A[agt_hk(q, q)], A[agt_hk(q, q)]); d[q] = -S.Hb[21 + q]; }
           if (agt_chol6_packed(A, d)) {
-            if (have_prev) {
+            if (lam > LAMBDA0) {             // damped steps are not comparable: no step-length adaptation
+              alpha = 1.0;
+              have_prev = 0;
+            } else if (have_prev) {
               // ratio of this step to the previous accepted one, in the metric of the current H
               double num = 0.0, den = 0.0, dd = 0.0;
 #pragma unroll

@@ -242,6 +242,10 @@ class HostContext:
     def set_roi_upload(self, enable: bool) -> None:
         self._check(self.lib.agt_set_roi_upload(self.h, int(bool(enable))))
 
+    def set_upload_threads(self, threads: int) -> None:
+        """Host threads that pack the rectangles of PAGEABLE frames into pinned staging (0: one 2-D copy per frame)."""
+        self._check(self.lib.agt_set_upload_threads(self.h, int(threads)))
+
     def last_h2d_bytes(self) -> int:
         return int(self.lib.agt_last_h2d_bytes(self.h))
 

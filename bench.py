@@ -396,8 +396,48 @@ def run_gpu(args):
                "host_numa_node": numa,
                "note": "agt_refine_host on pinned host frames (allocated on the NUMA node of the rank's GPU when the host exposes one: host_numa_node), all ranks concurrently, max over ranks; per frame only the "
                        "rectangle the refinement can read is copied (frames that leave it are redone from the full frame)"}
+        # the same call on PAGEABLE frames (what a numpy caller holds): host threads pack each chunk's rectangles into pinned
+        # staging, one copy per chunk (agt_set_upload_threads); next to it the one-2-D-copy-per-frame path it replaces
+        if world == 1 and psutil.virtual_memory().available > B * CAM.width * CAM.height + (8 << 30):
+            hp = np.array(hf)                                        # pageable copy
+            legs = {}
+            for label, threads in (("staged", None), ("copy_per_frame", 0)):
+                if threads is not None:
+                    hctx.set_upload_threads(threads)
+                outp = hctx.refine_poses(hp, init, CAM.mtx)         # warm-up (allocates the staging buffers)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    outp = hctx.refine_poses(hp, init, CAM.mtx)
+                legs[label] = (time.perf_counter() - t0) / 3
+                assert float(np.abs(outp["pose"].reshape(B, 6) - pose).max()) == 0.0
+            e2e["pageable"] = {"value": B / legs["staged"], "unit": "poses/s", "ms_per_step": 1e3 * legs["staged"],
+                               "h2d_bytes_per_step": int(hctx.last_h2d_bytes()),
+                               "upload_threads": min(8, os.cpu_count() or 4),
+                               "copy_per_frame_ms_per_step": 1e3 * legs["copy_per_frame"],
+                               "note": "agt_refine_host on frames in pageable host memory (a plain numpy array), same poses bit for bit"}
+            del hp
         hctx.close()
         del host_frames
+
+    # ---- BASELINE config 5 next to it, on every N the driver runs: the full pipeline (predictor -> PnP / LK fallback -> dense
+    #      refinement, one frame of every stream per step), 64 streams per GPU (weak) and 64 streams in all (strong) ----
+    streams = None
+    if not args.no_streams:
+        from accurate_aprilgroup_tracking_b200 import sharding as _sh
+        frames_s = pyr.frames[:args.cpu_sample].cpu().numpy() if (rank == 0 and not args.no_cpu) else None
+        del pyr, res, plain
+        torch.cuda.empty_cache()
+        F = 32
+        weak = streams_measure(torch, dist, world, rank, ctx, 64 * world, list(range(64 * rank, 64 * rank + 64)), F, 2)
+        torch.cuda.empty_cache()
+        strong = streams_measure(torch, dist, world, rank, ctx, 64, _sh.local_streams(64, rank, world), F, 2) if world > 1 else weak
+        streams = {"metric": "refined poses/sec (full APE+LK+DPR pipeline, BASELINE config 5)",
+                   "weak_64_streams_per_gpu": weak, "strong_64_streams": strong,
+                   "note": "one frame of every stream per step (frames of a stream are sequential: predictor and LK need the previous "
+                           "frame), CUDA graph per step, frame ingest + K1 of the next frame on a side stream; streams pinned to GPUs, one "
+                           "all-gather of all poses per sequence"}
+    else:
+        frames_s = pyr.frames[:args.cpu_sample].cpu().numpy() if (rank == 0 and not args.no_cpu) else None
 
     if rank != 0:
         if world > 1:
@@ -408,7 +448,6 @@ def run_gpu(args):
     cpu = None
     if not args.no_cpu:
         ns = args.cpu_sample
-        frames_s = pyr.frames[:ns].cpu().numpy()
         walls, cpu_pose = cpu_refine(frames_s, init[:ns], 1)
         wall = walls[0]
         dr = [2 * math.asin(min(1.0, 0.5 * np.linalg.norm(synth.rodrigues(cpu_pose[i, :3]) - synth.rodrigues(pose[i, :3]))))
@@ -452,6 +491,8 @@ def run_gpu(args):
                              "frac": PYR_BYTES_PER_1080P * B / (full_pyr_ms * 1e-3) / 1e9 / peak},
         "clocks": clocks,
     }
+    if streams is not None:
+        line["streams"] = streams
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -591,22 +632,18 @@ def run_multihyp(args):
                    "algorithmic_GBps": float((BYTES_PER_SAMPLE_EVAL * ev * nv).sum()) * args.steps / (ms * 1e-3) / 1e9}}), flush=True)
 
 
-def run_streams(args):
-    """Config 5: 64 concurrent 1080p streams, full APE + LK + DPR per frame, streams sharded s mod G."""
-    torch, dist, world, rank, local = _dist_setup()
+def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps):
+    """Config 5 on this rank's streams `mine` (global stream ids): the whole sequence `steps` times, timed on the device, max
+    over ranks.  -> dict (identical on every rank)."""
     from accurate_aprilgroup_tracking_b200 import sharding
-    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector, pack_detections
-    from accurate_aprilgroup_tracking_b200.context import AgtContext
-    ctx = AgtContext(local, CAM.mtx, None)
-    ctx.set_synthetic_model()
-    S_total, F = args.streams, args.stream_frames
-    mine = sharding.local_streams(S_total, rank, world)
-    S = len(mine)
+    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector
+    S, F = len(mine), n_frames
     trajs = [synth.trajectory(5000 + s, F) for s in mine]
     rngs = [np.random.default_rng(5000 + s) for s in mine]
     bank = ctx.alloc_pyramid(S * F, CAM.width, CAM.height, 1)           # pre-rendered frames [F][S]
     for f in range(F):
         ctx.render(bank, np.array([trajs[i][f] for i in range(S)]), np.array([1000 * s + f for s in mine]), offset=f * S, batch=S)
+    bpd = BatchedPoseDetector(ctx, S, CAM.width, CAM.height, synth.object_points())
     det_img, det_valid, det_n = [], [], []
     for f in range(F):
         dets = []
@@ -615,14 +652,11 @@ def run_streams(args):
             if (f + 3 * i) % 17 == 16:
                 d = d[:1]                                               # periodic detector dropouts exercise the LK path
             dets.append(d)
-        a, b, c = pack_detections(dets)
+        a, b, c = bpd.pack(dets)
         det_img.append(torch.as_tensor(a, device=ctx.tdev)); det_valid.append(torch.as_tensor(b, device=ctx.tdev))
         det_n.append(torch.as_tensor(c, device=ctx.tdev))
     bank_frames = bank.frames.reshape(F, S, CAM.height, CAM.width)
     holder = {}
-
-    bpd = BatchedPoseDetector(ctx, S, CAM.width, CAM.height, synth.object_points())
-
     hist = torch.zeros((S, F, 6), dtype=torch.float64, device=ctx.tdev)     # every stream's poses, frame by frame
 
     # frame ingest (device to device) and its pyramid are double-buffered: frame f+1 lands in the free slot, and K1 builds its
@@ -649,17 +683,16 @@ def run_streams(args):
             acc = out
         if world > 1:
             # NCCL: the final poses only - one all-gather of the whole sequence ([streams, frames x 6]), nothing per frame
-            holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), S_total)
+            holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), s_total)
         return acc
 
     run_sequence()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = run_sequence()
     e1.record()
     torch.cuda.synchronize()
@@ -667,21 +700,41 @@ def run_streams(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    # the steps replay CUDA graphs of the same launch sequence; the three pyrDown launches of a frame run outside the graph
-    launches = (bpd.kernels_per_step + 3) * F * args.steps
     pose = out["pose"].cpu().numpy()
     dt = np.array([np.linalg.norm(pose[i, 3:] - trajs[i][F - 1][3:]) for i in range(S)])
+    # the steps replay CUDA graphs of the same launch sequence; the three pyrDown launches of a frame run outside the graph
+    res = {"value": s_total * F * steps / (ms * 1e-3), "unit": "poses/s", "ms_per_frame_step": ms / steps / F, "ms_per_sequence": ms / steps,
+           "streams": s_total, "streams_per_gpu": S, "frames_per_stream": F, "sequences_timed": steps,
+           "gpu_launches": int((bpd.kernels_per_step + 3) * F * steps), "kernels_per_frame_step": int(bpd.kernels_per_step) + 3,
+           "cuda_graphs": True, "final_frame_median_trans_err_m": float(np.median(dt)),
+           "accepted_frac_last": float(out["accepted"].float().mean())}
+    del bank, bpd
+    return res
+
+
+def run_streams(args):
+    """Config 5: concurrent 1080p streams, full APE + LK + DPR per frame.  --stream-scaling strong: 64 streams in all, stream s
+    on GPU s mod G (BASELINE config 5); weak: 64 streams PER GPU (what a box serving more cameras than one GPU holds does)."""
+    torch, dist, world, rank, local = _dist_setup()
+    from accurate_aprilgroup_tracking_b200 import sharding
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    ctx = AgtContext(local, CAM.mtx, None)
+    ctx.set_synthetic_model()
+    weak = args.stream_scaling == "weak"
+    s_total = args.streams * world if weak else args.streams
+    mine = list(range(rank * args.streams, (rank + 1) * args.streams)) if weak else sharding.local_streams(s_total, rank, world)
+    r = streams_measure(torch, dist, world, rank, ctx, s_total, mine, args.stream_frames, args.steps)
     if rank == 0:
         print(json.dumps({
-            "metric": "refined poses/sec (full APE+LK+DPR pipeline)", "value": S_total * F * args.steps / (ms * 1e-3), "unit": "poses/s",
-            "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "64 concurrent 1080p camera streams, predictor -> PnP / LK fallback -> dense refinement per frame",
-                       "streams": S_total, "frames_per_stream": F, "step": "one pass over all frames of all streams",
-                       "parallelism": f"streams s mod {world} -> GPU; one NCCL all-gather of all poses at the end of the sequence"},
-            "gpu_launches": int(launches), "kernels_per_frame_step": int(bpd.kernels_per_step) + 3, "cuda_graphs": True,
-            "ms_per_frame_step": ms / args.steps / F,
-            "final_frame_median_trans_err_m": float(np.median(dt)), "accepted_frac_last": float(out["accepted"].float().mean())}), flush=True)
+            "metric": "refined poses/sec (full APE+LK+DPR pipeline)", "value": r["value"], "unit": "poses/s",
+            "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": r["ms_per_sequence"], "higher_is_better": True,
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+            "config": {"workload": "concurrent 1080p camera streams, predictor -> PnP / LK fallback -> dense refinement per frame",
+                       "streams": s_total, "frames_per_stream": args.stream_frames, "step": "one pass over all frames of all streams",
+                       "parallelism": (f"{args.streams} streams per GPU" if weak else f"streams s mod {world} -> GPU")
+                                      + "; one NCCL all-gather of all poses at the end of the sequence"},
+            **{k: r[k] for k in ("gpu_launches", "kernels_per_frame_step", "cuda_graphs", "ms_per_frame_step",
+                                 "final_frame_median_trans_err_m", "accepted_frac_last")}}), flush=True)
 
 
 def run_config1(args):
@@ -807,6 +860,8 @@ def main():
     ap.add_argument("--workload", default="dpr", choices=["dpr", "lk", "multihyp", "streams", "config1"])
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
+    ap.add_argument("--stream-scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-streams", action="store_true", help="skip the config-5 leg of the default line")
     args = ap.parse_args()
     if args.frames is None:
         args.frames = 8192 if args.workload == "lk" else 4096

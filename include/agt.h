@@ -269,6 +269,10 @@ int agt_bgr_to_gray_host(agt_ctx* ctx, const uint8_t* h_bgr, int w, int h, uint8
  * refinement touched pixels outside it, so results are identical to a full upload.  enable = 0
  * always uploads whole frames.  agt_last_h2d_bytes reports what the last call transferred. */
 int agt_set_roi_upload(agt_ctx* ctx, int enable);
+/* Host frames in PAGEABLE memory (a plain numpy array): `threads` host threads pack each chunk's rectangles into a pinned
+ * staging buffer that travels as one copy (default: min(8, hardware threads)); 0 = one 2-D copy per frame.  Frames in pinned,
+ * device-mapped memory are read in place by a gather kernel and need neither. */
+int agt_set_upload_threads(agt_ctx* ctx, int threads);
 int64_t agt_last_h2d_bytes(const agt_ctx* ctx);
 int agt_refine_host(agt_ctx* ctx, const uint8_t* h_frames, int w, int h, int levels, int batch,
                     const double* h_init, int n_hyp, double* h_pose, float* h_cost, int32_t* h_n_valid,
