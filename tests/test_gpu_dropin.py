@@ -230,7 +230,7 @@ def test_full_pipeline_matches_pipeline_oracle_config1(detector_factory, ctxvga)
     against the CPU composition of the three stage oracles, frame by frame, including detector dropouts."""
     from oracle import ape_oracle, pipeline_oracle
     cam = synth.CAMERA_VGA
-    n = 40
+    n = 300                                        # BASELINE config 1: the whole 300-frame sequence
     traj = synth.trajectory(1000, n)
     rng = np.random.default_rng(1000)
     pyr = ctxvga.alloc_pyramid(n, cam.width, cam.height, 1)
@@ -241,9 +241,9 @@ def test_full_pipeline_matches_pipeline_oracle_config1(detector_factory, ctxvga)
     tracked = 0
     for f in range(n):
         dets = synth.detections(traj[f], cam, rng)
-        if f in (12, 13, 27):
+        if f in (12, 13, 27) or f % 37 == 36:
             dets = dets[:1]
-        if f == 20:
+        if f in (20, 150, 151):
             dets = []
         po.frame(frames[f], dets)
         det.img = None
@@ -261,7 +261,7 @@ def test_full_pipeline_matches_pipeline_oracle_config1(detector_factory, ctxvga)
             got = np.concatenate([det.prev_transform[0].ravel(), det.prev_transform[1].ravel().astype(np.float64)])
             want = np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
             util.assert_pose_close(got, want, f"frame {f}")
-    assert tracked >= 3
+    assert tracked >= 10
 
 
 def test_distorted_camera_and_arbitrary_tag_ids_through_process_frame(tmp_path, lib_built, ctxvga):

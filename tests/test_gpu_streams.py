@@ -57,3 +57,68 @@ def test_batched_streams_match_single_stream_detector(ctxvga, detector_factory):
                 dr, dt = util.pose_diff(pose_b[s], trajs[s][f])
                 assert dr < 0.02 and dt < 2e-3
     assert tracked_total >= 2          # the LK path was exercised
+
+
+_JOBS = []          # inherited by the forked workers (2 GB of frames: not pickled)
+
+
+def _oracle_stream(index):
+    """One stream through oracle/pipeline_oracle.py (a worker process): -> per frame (accepted, pose or None, tags tracked)."""
+    from oracle import ape_oracle, pipeline_oracle
+    frames, dets, mtx = _JOBS[index]
+    po = pipeline_oracle.PipelineOracle(ape_oracle.group_from_json(synth.april_group_dict()), mtx, util.dpr_model())
+    out = []
+    for f in range(len(frames)):
+        po.frame(frames[f], dets[f])
+        pose = None if po.prev[0] is None else np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
+        out.append((po.last_accepted, pose, po.tracked))
+    return out
+
+
+def test_config5_64_streams_1080p_match_pipeline_oracle(ctx1080):
+    """BASELINE config 5 at its shape: 64 concurrent 1080p streams, 16 frames each, full APE + LK + dense refinement per frame
+    with detector dropouts (one tag left -> LK carries the rest; nothing detected -> the stream resets), the batched detector
+    against the CPU composition of the stage oracles run per stream (reference state machine + cv2 LK + dense oracle)."""
+    import multiprocessing as mp
+    import os
+    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector
+    cam = synth.CAMERA_1080P
+    n_streams, n_frames = 64, 16
+    trajs = [synth.trajectory(9000 + s, n_frames) for s in range(n_streams)]
+    rngs = [np.random.default_rng(9000 + s) for s in range(n_streams)]
+    bpd = BatchedPoseDetector(ctx1080, n_streams, cam.width, cam.height, synth.object_points())
+    frames_all = np.empty((n_frames, n_streams, cam.height, cam.width), np.uint8)
+    dets_all = []
+    got_pose, got_acc, got_tracked = [], [], []
+    for f in range(n_frames):
+        ctx1080.render(bpd.pyr[bpd.cur], np.array([trajs[s][f] for s in range(n_streams)]), np.arange(n_streams) + 1000 * f)
+        frames_all[f] = bpd.frames.cpu().numpy()
+        dets = []
+        for s in range(n_streams):
+            d = synth.detections(trajs[s][f], cam, rngs[s])
+            if (f + 3 * s) % 11 == 10:
+                d = d[:1]                       # one tag left: LK has to carry the others
+            if s % 16 == 5 and f == 7:
+                d = []                          # nothing detected: the stream loses its guess
+            dets.append(d)
+        dets_all.append(dets)
+        out = bpd.step(*bpd.pack(dets))
+        got_pose.append(out["pose"].cpu().numpy().copy())
+        got_acc.append(out["accepted"].cpu().numpy().copy())
+        got_tracked.append(out["tracked_tags"].cpu().numpy().copy())
+    _JOBS[:] = [(frames_all[:, s], [dets_all[f][s] for f in range(n_frames)], cam.mtx) for s in range(n_streams)]
+    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        want = pool.map(_oracle_stream, range(n_streams), chunksize=1)
+    _JOBS.clear()
+    n_checked = n_tracked = 0
+    for s in range(n_streams):
+        for f in range(n_frames):
+            acc, pose, tracked = want[s][f]
+            assert bool(got_acc[f][s]) == acc, (s, f)
+            assert int(got_tracked[f][s]) == tracked, (s, f)          # LK inlier set (all-four-corners rule)
+            n_tracked += tracked
+            if acc:
+                util.assert_pose_close(got_pose[f][s], pose, f"stream {s} frame {f}")
+                n_checked += 1
+    print(f"config 5: {n_checked} accepted poses of {n_streams * n_frames} checked against the pipeline oracle, {n_tracked} tags re-admitted by LK")
+    assert n_checked > 0.9 * n_streams * n_frames and n_tracked >= 50
