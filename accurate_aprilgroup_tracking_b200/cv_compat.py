@@ -186,6 +186,27 @@ class HostContext:
                 out.append(self.Scharr(l))
         return levels - 1, out
 
+    # -- corner refinement (N3, first step) ---------------------------------------------
+    def cornerSubPix(self, image, corners, winSize, zeroZone=(-1, -1), criteria=(3, 30, 0.001)):
+        """cv.cornerSubPix(image, corners, winSize, zeroZone, criteria): corners [N,1,2] / [N,2] float32 are refined IN PLACE and
+        returned, as OpenCV does.  Square windows of half-size 1..7, no zero zone, 8-bit single-channel images."""
+        if tuple(zeroZone) != (-1, -1):
+            raise ValueError("only zeroZone=(-1, -1) is implemented")
+        if winSize[0] != winSize[1]:
+            raise ValueError("only square windows are implemented")
+        img = np.ascontiguousarray(image, dtype=np.uint8)
+        if img.ndim != 2:
+            raise ValueError("image must be single-channel")
+        if not (isinstance(corners, np.ndarray) and corners.dtype == np.float32 and corners.flags.c_contiguous):
+            raise ValueError("corners must be a C-contiguous float32 array (it is refined in place)")
+        kind, count, eps = criteria
+        max_iters = int(count) if (kind & 1) else 100
+        eps = float(eps) if (kind & 2) else 0.0
+        self._check(self.lib.agt_corner_subpix_host(self.h, C.c_void_p(img.ctypes.data), int(img.shape[1]), int(img.shape[0]),
+                                                    C.c_void_p(corners.ctypes.data), int(corners.size // 2), int(winSize[0]),
+                                                    max(1, max_iters), max(eps, 0.0)))
+        return corners
+
     # -- frame ingest -------------------------------------------------------------------
     def undistort_gray(self, frame, cameraMatrix, distCoeffs, newCameraMatrix, roi):
         """cv.cvtColor(cv.undistort(frame, K, dist, None, newK)[y:y+h, x:x+w], COLOR_BGR2GRAY) in one device pass:

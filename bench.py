@@ -484,6 +484,7 @@ def run_gpu(args):
         "fused_equals_built_pyramid_path": fused_equals_plain,
         "frames_redone_on_full_pyramid": n_redo,
         "lm": {"mean_evals": float(evals.mean()), "max_evals": int(evals.max()), "mean_samples": float(nvalid.mean()),
+               "sample_evals": float((nvalid * evals).sum()),
                "converged_frac": float((status == 1).mean()), "median_trans_err_vs_truth_m": float(np.median(dt))},
         "roofline": roofline,
         "pyramid_roofline": {"kernel": "pyr_down_stream_kernel (full frames, 3 levels)", "bound": "hbm",

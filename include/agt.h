@@ -112,6 +112,17 @@ int agt_undistort_frames(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int c
  * agt_undistort, h_gray[roi_h][roi_w] (may be NULL) as agt_undistort_to_gray. */
 int agt_undistort_frame_host(agt_ctx* ctx, const uint8_t* h_src, int w, int h, int channels, uint8_t* h_frame, uint8_t* h_gray);
 
+/* ---- N3 (first step): sub-pixel corner refinement around given (predicted / tracked / detected) corners --------------------
+ * cv::cornerSubPix(gray, corners, (win, win), (-1, -1), (COUNT + EPS, max_iters, eps)) per frame of a batch - the corner
+ * refinement of OpenCV's ArUco detector, which stands in for the `refine_edges` step of the reference's apriltag detector
+ * (detect_pose.py:86-95, :368-371; that library is not vendored).  d_pts / d_out [batch][n_pts][2] float32, d_valid
+ * [batch][n_pts] (NULL = all): points that are not valid or lie outside the frame are copied through.  win = 1..7. */
+int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
+                      const uint8_t* d_valid, float* d_out, int batch, int n_pts, int win, int max_iters, double eps);
+/* One host image, corners refined in place (the OpenCV calling convention). */
+int agt_corner_subpix_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, float* h_pts, int n_pts, int win, int max_iters,
+                           double eps);
+
 /* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
 /* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
 int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,

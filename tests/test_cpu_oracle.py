@@ -257,3 +257,24 @@ def test_roi_exactness_rule_of_the_pyramid_chain():
             ay, by = window(y0, y1, h, lh, level)
             assert bx > ax and by > ay
             assert np.array_equal(a[ay:by, ax:bx], b[ay:by, ax:bx]), (level, (x0, y0, x1, y1))
+
+
+# ---------------------------------------------------------------------------- corner refinement (row N3, first step)
+def test_corner_subpix_restatement_equals_opencv():
+    from oracle import corner_oracle
+    cam = synth.CAMERA_VGA
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for s in range(4):
+        pose = synth.trajectory(600 + s, 1)[0]
+        img = synth.render(pose, cam, s)
+        true = np.concatenate([synth.project(synth.object_points()[4 * k:4 * k + 4], pose, cam) for k in synth.visible_tags(pose)])
+        pts = (true + rng.normal(0, 1.0, true.shape)).astype(np.float32)
+        for win in (3, 5):
+            a = corner_oracle.corner_subpix_cv(img, pts, win)
+            b = corner_oracle.corner_subpix_np(img, pts, win)
+            worst = max(worst, float(np.abs(a - b).max()))
+    border = np.array([[2.3, 3.1], [637.2, 476.9], [0.5, 240.0], [320.0, 0.2], [639.4, 100.0]], np.float32)
+    a, b = corner_oracle.corner_subpix_cv(img, border), corner_oracle.corner_subpix_np(img, border)
+    worst = max(worst, float(np.abs(a - b).max()))
+    assert worst <= 1e-4, worst           # float32 resampling order: identical on almost every corner

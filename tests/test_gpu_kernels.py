@@ -99,6 +99,67 @@ def test_pyramid_idempotent_constant(ctxvga):
 
 
 # ------------------------------------------------------------------------------------------
+# N3 (first step): corner refinement vs cv2.cornerSubPix
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cam_name,win", [("vga", 5), ("vga", 3), ("1080p", 5), ("1080p", 7)])
+def test_corner_subpix_matches_opencv(ctxvga, ctx1080, cam_name, win):
+    """agt_corner_subpix against cv2.cornerSubPix (the corner refinement of OpenCV's ArUco detector, which stands in for the
+    reference's apriltag `refine_edges`): predicted corners = true projections + 1 px of noise, plus points on and
+    outside the image border; tolerance 2e-3 px (the two accumulate the same float64 sums in a different order; the
+    iteration stops at 1e-3 px)."""
+    from oracle import corner_oracle
+    ctx, cam = (ctxvga, synth.CAMERA_VGA) if cam_name == "vga" else (ctx1080, synth.CAMERA_1080P)
+    n = 6
+    traj = synth.trajectory(4400, n)
+    pyr = _render(ctx, cam, traj, np.arange(n) + 4400, levels=1)
+    rng = np.random.default_rng(44)
+    obj = synth.object_points()
+    pts = np.stack([synth.project(obj, traj[i], cam) for i in range(n)]) + rng.normal(0, 1.0, (n, 48, 2))
+    extra = np.array([[2.3, 3.1], [cam.width - 2.8, cam.height - 3.1], [0.5, 240.0], [320.0, 0.2], [cam.width - 0.6, 100.0],
+                      [-5.0, 10.0], [100.0, cam.height + 3.0]], np.float32)
+    pts = np.concatenate([pts, np.broadcast_to(extra, (n,) + extra.shape)], axis=1).astype(np.float32)
+    valid = np.ones(pts.shape[:2], np.uint8)
+    valid[:, 7] = 0
+    out = ctx.corner_subpix(pyr, pts, valid, win=win).cpu().numpy()
+    frames = pyr.frames.cpu().numpy()
+    worst = worst_all = 0.0
+    moved = n_stable = n_all = 0
+    for i in range(n):
+        inside = (pts[i, :, 0] >= 0) & (pts[i, :, 0] < cam.width) & (pts[i, :, 1] >= 0) & (pts[i, :, 1] < cam.height) & (valid[i] == 1)
+        p = pts[i][inside]
+        want = corner_oracle.corner_subpix_cv(frames[i], p, win)
+        # cv2.cornerSubPix stops a linearly converging iteration at a step of 1e-3 px, and on some corners the iteration does not
+        # contract at all: there cv2's own answer moves by up to 0.5 px when the input moves by 1e-4 px.  Parity is asserted on the
+        # corners where cv2 agrees with itself under that perturbation (the large majority), and reported on all of them.
+        wobble = np.maximum(np.abs(corner_oracle.corner_subpix_cv(frames[i], np.clip(p + np.float32(1e-4), 0, None), win) - want).max(axis=1),
+                            np.abs(corner_oracle.corner_subpix_cv(frames[i], np.clip(p - np.float32(1e-4), 0, None), win) - want).max(axis=1))
+        stable = wobble < 5e-4
+        d = np.abs(out[i][inside] - want).max(axis=1)
+        worst = max(worst, float(d[stable].max()))
+        worst_all = max(worst_all, float(d.max()))
+        n_stable += int(stable.sum()); n_all += int(stable.size)
+        assert np.array_equal(out[i][~inside], pts[i][~inside])          # invalid / outside points are copied through
+        moved += int((np.abs(want - p).max(axis=1) > 0.05).sum())
+    print(f"corner_subpix {cam_name} win {win}: worst difference to cv2 {worst:.2e} px on the {n_stable} of {n_all} corners where cv2 is "
+          f"stable under a 1e-4 px perturbation ({worst_all:.2e} px on all), {moved} corners moved")
+    assert worst <= 2e-3 and moved > 100 and n_stable > 0.8 * n_all
+
+
+def test_corner_subpix_host_entry_point_refines_in_place(lib_built):
+    from accurate_aprilgroup_tracking_b200 import cv_compat
+    from oracle import corner_oracle
+    cam = synth.CAMERA_VGA
+    pose = synth.trajectory(4500, 1)[0]
+    img = synth.render(pose, cam, 7)
+    pts = (synth.project(synth.object_points(), pose, cam) + 0.7).astype(np.float32).reshape(-1, 1, 2)
+    want = corner_oracle.corner_subpix_cv(img, pts, 5)
+    got = cv_compat.default_context().cornerSubPix(img, pts, (5, 5), (-1, -1), (3, 30, 0.001))
+    assert got is pts and np.abs(pts.reshape(-1, 2) - want).max() <= 2e-3
+    with pytest.raises(ValueError):
+        cv_compat.default_context().cornerSubPix(img, pts, (5, 3))
+
+
+# ------------------------------------------------------------------------------------------
 # K2 LK vs cv2.calcOpticalFlowPyrLK
 # ------------------------------------------------------------------------------------------
 def _bits(a):
