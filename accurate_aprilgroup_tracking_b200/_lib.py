@@ -54,6 +54,7 @@ PROTOTYPES = {
     "agt_set_undistort": (_I, [_VP, C.POINTER(_D), _I, _I, _I, _I, _I, _I]),
     "agt_undistort_to_gray": (_I, [_VP, _VP, _I, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
     "agt_undistort_to_gray_host": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "agt_draw_points": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I]),
     "agt_corner_subpix": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _VP, _I, _I, _I, _I, _D]),
     "agt_corner_subpix_host": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _I, _D]),
     "agt_bgr_to_gray_host": (_I, [_VP, _VP, _I, _I, _VP]),

@@ -295,6 +295,23 @@ class AgtContext:
         return out
 
     # -- K0 ---------------------------------------------------------------------------
+    def overlay_points(self, bgr, obj_pts, poses, frame_mask=None, radius: int = 5, color=(0, 0, 255), bounds=(1280, 720)):
+        """The reference's pose overlay for a batch (detect_pose.py:441-465, draw.py:120-153): project `obj_pts` [P,3] with
+        `poses` [B,6] and stamp a filled disc on every projection into `bgr` [B,H,W,3] uint8 (device tensor, in place).
+        `bounds` is the (width, height) the reference tests the rounded centre against (hard-coded 1280 x 720 there);
+        `frame_mask` [B] uint8 selects the frames that get an overlay (the accepted ones).  -> projections [B,P,2] f64."""
+        t = self.torch
+        if not (isinstance(bgr, t.Tensor) and bgr.is_cuda and bgr.dtype == t.uint8 and bgr.dim() == 4 and bgr.shape[3] == 3 and bgr.is_contiguous()):
+            raise ValueError("bgr must be a contiguous uint8 CUDA tensor [B,H,W,3]")
+        b, h, w = int(bgr.shape[0]), int(bgr.shape[1]), int(bgr.shape[2])
+        proj = self.project(obj_pts, poses)
+        m = None if frame_mask is None else self._dev(frame_mask, t.uint8)
+        self._use_current_stream()
+        self._check(self.lib.agt_draw_points(self.h, self._p(bgr), w, h, 3 * w, 3 * w * h, self._p(proj), self._p(m) if m is not None else None,
+                                             b, int(proj.shape[1]), int(radius), int(bounds[0]), int(bounds[1]), int(color[0]), int(color[1]),
+                                             int(color[2])))
+        return proj
+
     def new_stream_state(self, n_streams: int):
         t = self.torch
         return t.zeros((n_streams, _lib.AGT_STREAM_STATE_DOUBLES), dtype=t.float64, device=self.tdev)

@@ -123,6 +123,15 @@ int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t
 int agt_corner_subpix_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, float* h_pts, int n_pts, int win, int max_iters,
                            double eps);
 
+/* ---- N4: the overlay after the path, batched (detect_pose.py:441-465 _project_draw_points; draw.py:120-153) --------------
+ * For every frame with a non-zero d_frame_mask entry (NULL = all) and every point: (x, y) = np.round(d_pts) and, if
+ * 0 <= x < bound_w and 0 <= y < bound_h (the reference tests against 1280 x 720), cv.circle(img, (x, y), radius,
+ * (blue, green, red), -1) into d_bgr[batch][h][pitch] (3 interleaved channels) - bit-identical to the cv.circle loop.
+ * d_pts [batch][n_pts][2] float64 is what agt_project writes.  The reference uses radius 5 and (0, 0, 255). */
+int agt_draw_points(agt_ctx* ctx, uint8_t* d_bgr, int w, int h, int64_t pitch, int64_t stride, const double* d_pts,
+                    const uint8_t* d_frame_mask, int batch, int n_pts, int radius, int bound_w, int bound_h, int blue, int green,
+                    int red);
+
 /* ---- K1: image pyramid + Scharr (cv::pyrDown / cv::Scharr, bit-exact) ------- */
 /* One pyrDown step on a batch: dst is ((w+1)/2) x ((h+1)/2). */
 int agt_pyr_down(agt_ctx* ctx, const uint8_t* d_src, int w, int h, int64_t src_pitch, int64_t src_stride,

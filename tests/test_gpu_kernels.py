@@ -99,6 +99,53 @@ def test_pyramid_idempotent_constant(ctxvga):
 
 
 # ------------------------------------------------------------------------------------------
+# N4: batched pose overlay vs the reference's cv.circle loop
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h", [(1280, 720), (1920, 1080), (333, 201)])
+def test_overlay_points_equal_the_cv_circle_loop(ctx1080, w, h):
+    """agt_draw_points against draw.py:144-151 run on the host: np.round, the 1280 x 720 bounds test on the centre, cv.circle(img,
+    (x, y), 5, (0, 0, 255), -1) - bit-identical frames, including discs cut by the frame border, centres outside the bounds,
+    NaN projections and masked (not accepted) frames."""
+    import cv2
+    import torch
+    rng = np.random.default_rng(w)
+    n = 5
+    cam = synth.Camera(w, h, 1400.0 * w / 1920, 1400.0 * w / 1920, w / 2.0, h / 2.0)
+    ctx = ctx1080
+    poses = synth.trajectory(5100, n)
+    poses[1, 3] += 0.9 * poses[1, 5] * (w / 2.0) / cam.fx          # object on the right border: discs cut by it, centres outside
+    poses[2, 4] -= 0.9 * poses[2, 5] * (h / 2.0) / cam.fy
+    old = (ctx.mtx.copy(), ctx.dist)
+    ctx.set_camera(cam.mtx, None)
+    try:
+        host = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+        dev = torch.from_numpy(host).to(ctx.tdev)
+        mask = np.array([1, 1, 1, 0, 1], np.uint8)
+        obj = synth.object_points()
+        proj = ctx.overlay_points(dev, obj, poses, mask).cpu().numpy()
+        want = host.copy()
+        for f in range(n):
+            if not mask[f]:
+                continue
+            for x, y in np.round(proj[f]).astype(int):
+                if 0 <= y < 720 and 0 <= x < 1280:
+                    cv2.circle(want[f], (int(x), int(y)), 5, (0, 0, 255), -1)
+        got = dev.cpu().numpy()
+        assert np.array_equal(got, want)
+        assert (got != host).any() and np.array_equal(got[3], host[3])
+        # projections are the ones cv.projectPoints gives (float32 object points on the device)
+        ref = cv2.projectPoints(obj, poses[0, :3], poses[0, 3:], cam.mtx, None)[0].reshape(-1, 2)
+        assert np.abs(proj[0] - ref).max() < 1e-2
+        # NaN poses draw nothing and do not fault
+        bad = poses.copy(); bad[0, :] = np.nan
+        dev2 = torch.from_numpy(host).to(ctx.tdev)
+        ctx.overlay_points(dev2, obj, bad, mask)
+        assert np.array_equal(dev2[0].cpu().numpy(), host[0]) and np.array_equal(dev2[1:].cpu().numpy(), got[1:])
+    finally:
+        ctx.set_camera(*old)
+
+
+# ------------------------------------------------------------------------------------------
 # N3 (first step): corner refinement vs cv2.cornerSubPix
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cam_name,win", [("vga", 5), ("vga", 3), ("1080p", 5), ("1080p", 7)])
