@@ -146,43 +146,94 @@ __device__ inline void evaluate(const agt_camera& cam, const double p[6], const 
   all_in_front = __all_sync(0xffffffffu, front);
 }
 
-// Smallest eigenvector of the symmetric 12x12 matrix M (PSD) by inverse iteration
-// on M + eps I (Cholesky).  Executed redundantly by every lane.
-__device__ inline bool smallest_eigvec12(double* M, double* v) {
+// Smallest eigenvector of the symmetric N x N matrix M (PSD, row stride N, N <= 12) by inverse iteration
+// on M + eps I (Cholesky).  Executed by one lane.
+__device__ inline bool smallest_eigvec(double* M, double* v, const int N) {
   double tr = 0.0;
-  for (int i = 0; i < 12; ++i) tr += M[i * 12 + i];
+  for (int i = 0; i < N; ++i) tr += M[i * N + i];
   double eps = 1e-13 * tr + 1e-300;
-  for (int i = 0; i < 12; ++i) M[i * 12 + i] += eps;
-  for (int j = 0; j < 12; ++j) {
-    double d = M[j * 12 + j];
-    for (int k = 0; k < j; ++k) d -= M[j * 12 + k] * M[j * 12 + k];
+  for (int i = 0; i < N; ++i) M[i * N + i] += eps;
+  for (int j = 0; j < N; ++j) {
+    double d = M[j * N + j];
+    for (int k = 0; k < j; ++k) d -= M[j * N + k] * M[j * N + k];
     if (!(d > 0.0)) return false;
     d = sqrt(d);
-    M[j * 12 + j] = d;
-    for (int i = j + 1; i < 12; ++i) {
-      double s = M[i * 12 + j];
-      for (int k = 0; k < j; ++k) s -= M[i * 12 + k] * M[j * 12 + k];
-      M[i * 12 + j] = s / d;
+    M[j * N + j] = d;
+    for (int i = j + 1; i < N; ++i) {
+      double s = M[i * N + j];
+      for (int k = 0; k < j; ++k) s -= M[i * N + k] * M[j * N + k];
+      M[i * N + j] = s / d;
     }
   }
-  for (int i = 0; i < 12; ++i) v[i] = 1.0 / sqrt(12.0) * ((i * 7 + 3) % 5 + 1);   // generic start vector
+  for (int i = 0; i < N; ++i) v[i] = 1.0 / sqrt(12.0) * ((i * 7 + 3) % 5 + 1);   // generic start vector
   for (int it = 0; it < 12; ++it) {
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < N; ++i) {
       double s = v[i];
-      for (int k = 0; k < i; ++k) s -= M[i * 12 + k] * v[k];
-      v[i] = s / M[i * 12 + i];
+      for (int k = 0; k < i; ++k) s -= M[i * N + k] * v[k];
+      v[i] = s / M[i * N + i];
     }
-    for (int i = 11; i >= 0; --i) {
+    for (int i = N - 1; i >= 0; --i) {
       double s = v[i];
-      for (int k = i + 1; k < 12; ++k) s -= M[k * 12 + i] * v[k];
-      v[i] = s / M[i * 12 + i];
+      for (int k = i + 1; k < N; ++k) s -= M[k * N + i] * v[k];
+      v[i] = s / M[i * N + i];
     }
     double n = 0.0;
-    for (int i = 0; i < 12; ++i) n += v[i] * v[i];
+    for (int i = 0; i < N; ++i) n += v[i] * v[i];
     n = 1.0 / sqrt(n);
-    for (int i = 0; i < 12; ++i) v[i] *= n;
+    for (int i = 0; i < N; ++i) v[i] *= n;
   }
   return true;
+}
+
+// Eigen-decomposition of a symmetric 3x3 matrix (cyclic Jacobi): eigenvalues w ascending, eigenvectors as the ROWS of V.
+__device__ inline void eig_sym3(const double C[6], double w[3], double V[9]) {
+  double a[9] = {C[0], C[1], C[2], C[1], C[3], C[4], C[2], C[4], C[5]};
+  double v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};          // columns are eigenvectors
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
+    if (off < 1e-300 || off < 1e-17 * (fabs(a[0]) + fabs(a[4]) + fabs(a[8]))) break;
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      if (fabs(a[p * 3 + q]) < 1e-300) continue;
+      double th = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * a[p * 3 + q]);
+      double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < 3; ++k) {                       // A <- A J
+        double akp = a[k * 3 + p], akq = a[k * 3 + q];
+        a[k * 3 + p] = c * akp - sn * akq; a[k * 3 + q] = sn * akp + c * akq;
+      }
+      for (int k = 0; k < 3; ++k) {                       // A <- J^T A
+        double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+        a[p * 3 + k] = c * apk - sn * aqk; a[q * 3 + k] = sn * apk + c * aqk;
+      }
+      for (int k = 0; k < 3; ++k) {
+        double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+        v[k * 3 + p] = c * vkp - sn * vkq; v[k * 3 + q] = sn * vkp + c * vkq;
+      }
+    }
+  }
+  int idx[3] = {0, 1, 2};
+  double d[3] = {a[0], a[4], a[8]};
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2 - i; ++j)
+      if (d[idx[j]] > d[idx[j + 1]]) { int t = idx[j]; idx[j] = idx[j + 1]; idx[j + 1] = t; }
+  for (int i = 0; i < 3; ++i) {
+    w[i] = d[idx[i]];
+    for (int k = 0; k < 3; ++k) V[i * 3 + k] = v[k * 3 + idx[i]];
+  }
+}
+
+// cv::undistortPoints for one normalised point: fixed-point iteration of the Brown-Conrady model (as OpenCV, 5 rounds suffice
+// for an initial value; the LM that follows works on the distorted pixels)
+__device__ inline void undistort_normalised(const agt_camera& cam, double& x, double& y) {
+  if (!cam.has_dist) return;
+  const double x0 = x, y0 = y;
+  for (int it = 0; it < 8; ++it) {
+    const double r2 = x * x + y * y;
+    const double icd = 1.0 / (1.0 + ((cam.k3 * r2 + cam.k2) * r2 + cam.k1) * r2);
+    const double dx = 2.0 * cam.p1 * x * y + cam.p2 * (r2 + 2.0 * x * x), dy = cam.p1 * (r2 + 2.0 * y * y) + 2.0 * cam.p2 * x * y;
+    x = (x0 - dx) * icd; y = (y0 - dy) * icd;
+  }
 }
 
 __device__ inline double det3(const double* m) {
@@ -207,6 +258,94 @@ __device__ inline void orthonormalise(double* R) {
     }
     if (diff < 1e-15) break;
   }
+}
+
+// Initial pose of a PLANAR point set from the homography plane -> normalised image (the planar branch of OpenCV's
+// cvFindExtrinsicCameraParams2): plane frame from the scatter's eigenvectors (rows of eV: the two in-plane axes are rows 2 and
+// 1, the normal row 0), Hartley-normalised DLT for H (9x9 normal matrix, smallest eigenvector), [r1 r2 t] = H up to scale,
+// r3 = r1 x r2, polar orthonormalisation, and back to the object frame.  The LM that follows only needs the right basin.
+__device__ inline bool planar_init(const agt_camera& cam, const double X[2][3], const double xn[2][2], const bool have[2], int n,
+                                   const double sum[5], const double eV[9], double* M, int lane, double p[6]) {
+  double e1[3] = {eV[6], eV[7], eV[8]}, e2[3] = {eV[3], eV[4], eV[5]};
+  double nn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+  double q[2][2], so = 0.0, si = 0.0;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const double a = X[s][0] - sum[0], b = X[s][1] - sum[1], c = X[s][2] - sum[2];
+    q[s][0] = e1[0] * a + e1[1] * b + e1[2] * c; q[s][1] = e2[0] * a + e2[1] * b + e2[2] * c;
+    if (have[s]) {
+      so += q[s][0] * q[s][0] + q[s][1] * q[s][1];
+      const double d = xn[s][0] - sum[3], e = xn[s][1] - sum[4];
+      si += d * d + e * e;
+    }
+  }
+  so = agt_warp_sum(so); si = agt_warp_sum(si);
+  if (!(so > 0.0) || !(si > 0.0)) return false;
+  const double sco = sqrt(2.0 * n / so), sci = sqrt(2.0 * n / si);
+  double acc[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+    if (have[s]) {
+      const double x = sco * q[s][0], y = sco * q[s][1], u = sci * (xn[s][0] - sum[3]), v = sci * (xn[s][1] - sum[4]);
+      const double r0[9] = {x, y, 1.0, 0.0, 0.0, 0.0, -u * x, -u * y, -u}, r1[9] = {0.0, 0.0, 0.0, x, y, 1.0, -v * x, -v * y, -v};
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = a; b < 9; ++b) acc[k++] += r0[a] * r0[b] + r1[a] * r1[b];
+    }
+#pragma unroll
+  for (int k = 0; k < 45; ++k) acc[k] = agt_warp_sum(acc[k]);
+  __syncwarp();
+  double h[9];
+  bool eig_ok = true;
+  if (lane == 0) {
+    int k = 0;
+    for (int a = 0; a < 9; ++a)
+      for (int b = a; b < 9; ++b) { M[a * 9 + b] = M[b * 9 + a] = acc[k]; ++k; }
+    eig_ok = smallest_eigvec(M, h, 9);
+  }
+  eig_ok = __shfl_sync(0xffffffffu, (int)eig_ok, 0) != 0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) h[k] = __shfl_sync(0xffffffffu, h[k], 0);
+  __syncwarp();
+  if (!eig_ok) return false;
+  // denormalise: H = Ti^-1 H' To, To = diag(sco, sco, 1), Ti^-1 = [[1/sci, 0, mu], [0, 1/sci, mv], [0, 0, 1]]
+  double H[9];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double sc = c < 2 ? sco : 1.0;
+    H[0 + c] = (h[0 + c] / sci + sum[3] * h[6 + c]) * sc;
+    H[3 + c] = (h[3 + c] / sci + sum[4] * h[6 + c]) * sc;
+    H[6 + c] = h[6 + c] * sc;
+  }
+  if (H[8] < 0.0) {                                       // the plane's origin (the centroid) lies in front of the camera
+#pragma unroll
+    for (int k = 0; k < 9; ++k) H[k] = -H[k];
+  }
+  const double n1 = sqrt(H[0] * H[0] + H[3] * H[3] + H[6] * H[6]), n2 = sqrt(H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+  if (!(n1 > 0.0) || !(n2 > 0.0)) return false;
+  const double lam = 2.0 / (n1 + n2);
+  const double r1[3] = {H[0] / n1, H[3] / n1, H[6] / n1}, r2[3] = {H[1] / n2, H[4] / n2, H[7] / n2};
+  const double r3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
+  double Rh[9] = {r1[0], r2[0], r3[0], r1[1], r2[1], r3[1], r1[2], r2[2], r3[2]};       // columns r1 r2 r3
+  orthonormalise(Rh);
+  const double th[3] = {H[2] * lam, H[5] * lam, H[8] * lam};
+  // X_cam = Rh [e1; e2; n] (X - mean) + th
+  double R[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[r * 3 + c] = Rh[r * 3 + 0] * e1[c] + Rh[r * 3 + 1] * e2[c] + Rh[r * 3 + 2] * nn[c];
+  agt_log_rotation(R, p);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) p[3 + r] = th[r] - (R[r * 3 + 0] * sum[0] + R[r * 3 + 1] * sum[1] + R[r * 3 + 2] * sum[2]);
+  bool fin = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) fin = fin && isfinite(p[k]);
+  return fin;
 }
 
 __global__ void __launch_bounds__(PNP_WARPS * 32)
@@ -243,18 +382,35 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
 #pragma unroll
     for (int k = 0; k < 6; ++k) ok = ok && isfinite(p[k]);
   } else if (ok) {
-    // ---------------- DLT initialisation (needs >= 6 points) -----------------------
-    ok = n >= 6;
-    // normalisation statistics
+    // ---------------- initial value without a guess (cv::solvePnP ITERATIVE: cvFindExtrinsicCameraParams2) --------------
+    // normalised, undistorted image points; planar object points (smallest / middle eigenvalue of their scatter < 1e-3, the
+    // rule OpenCV uses) start from a homography (>= 4 points: a single tag, a planar tag board), the others from a DLT (>= 6)
     double sum[5] = {0, 0, 0, 0, 0};
     double xn[2][2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       xn[s][0] = (U[s][0] - cam.cx) / cam.fx; xn[s][1] = (U[s][1] - cam.cy) / cam.fy;
+      undistort_normalised(cam, xn[s][0], xn[s][1]);
       if (have[s]) { sum[0] += X[s][0]; sum[1] += X[s][1]; sum[2] += X[s][2]; sum[3] += xn[s][0]; sum[4] += xn[s][1]; }
     }
 #pragma unroll
     for (int k = 0; k < 5; ++k) sum[k] = agt_warp_sum(sum[k]) / (n > 0 ? n : 1);
+    double C6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (have[s]) {
+        const double a = X[s][0] - sum[0], b = X[s][1] - sum[1], c = X[s][2] - sum[2];
+        C6[0] += a * a; C6[1] += a * b; C6[2] += a * c; C6[3] += b * b; C6[4] += b * c; C6[5] += c * c;
+      }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) C6[k] = agt_warp_sum(C6[k]);
+    double ew[3], eV[9];
+    eig_sym3(C6, ew, eV);                                 // every lane: same inputs, same result
+    const bool planar = !(ew[0] >= 1e-3 * ew[1]);
+    if (planar) {
+      ok = ok && ew[1] > 0.0 && planar_init(cam, X, xn, have, n, sum, eV, s_M[wid], lane, p);
+    } else {
+    ok = n >= 6;
     double so = 0.0, si = 0.0;
 #pragma unroll
     for (int s = 0; s < 2; ++s)
@@ -311,7 +467,7 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
     __syncwarp();
     double v[12];
     bool eig_ok = true;
-    if (lane == 0) eig_ok = smallest_eigvec12(M, v);
+    if (lane == 0) eig_ok = smallest_eigvec(M, v, 12);
     eig_ok = __shfl_sync(0xffffffffu, (int)eig_ok, 0) != 0;
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = __shfl_sync(0xffffffffu, v[k], 0);
@@ -342,6 +498,7 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
     p[3] = tt[0]; p[4] = tt[1]; p[5] = tt[2];
 #pragma unroll
     for (int k = 0; k < 6; ++k) ok = ok && isfinite(p[k]);
+    }
   }
 
   // ---------------- Levenberg-Marquardt ---------------------------------------------

@@ -474,12 +474,61 @@ def test_pnp_with_distortion(ctxvga):
 
 
 def test_pnp_too_few_points_not_ok(ctxvga):
+    cam = synth.CAMERA_VGA
     obj = synth.object_points().astype(np.float32)
-    img = np.zeros((2, 48, 2), np.float32)
-    valid = np.zeros((2, 48), np.uint8)
-    valid[0, :4] = 1                      # one tag, no guess: DLT needs >= 6 points
-    pose, ok, err, _ = ctxvga.pnp(obj, img, valid)
-    assert ok.cpu().numpy().tolist() == [0, 0]
+    pose = synth.trajectory(60, 1)[0]
+    proj = synth.project(obj, pose, cam).astype(np.float32)
+    img = np.stack([np.zeros((48, 2), np.float32), np.zeros((48, 2), np.float32), proj])
+    valid = np.zeros((3, 48), np.uint8)
+    valid[0, :4] = 1                      # four points that all project to one pixel: no homography
+    valid[2, [0, 1, 2, 3, 4]] = 1         # five points, not coplanar: the DLT needs >= 6 (cv2.solvePnP raises there)
+    pose_out, ok, err, _ = ctxvga.pnp(obj, img, valid)
+    assert ok.cpu().numpy().tolist() == [0, 0, 0]
+
+
+def test_pnp_planar_points_start_from_a_homography(ctxvga):
+    """cv.solvePnP(ITERATIVE) without a guess on coplanar object points - a single tag (4 corners), a planar tag board - takes
+    the homography branch of cvFindExtrinsicCameraParams2; so does K3 (round 1 ran the 12x12 DLT on a rank-deficient system).
+    Against cv2 on the same points, with and without lens distortion."""
+    import cv2
+    cam = synth.CAMERA_VGA
+    rng = np.random.default_rng(71)
+    s = synth.TAG_SIZE / 2
+    tag = np.array([[-s, -s, 0], [-s, s, 0], [s, s, 0], [s, -s, 0]])
+    board = np.concatenate([tag + np.array([dx, dy, 0.0]) for dx in (-0.03, 0.0, 0.03) for dy in (-0.03, 0.0, 0.03)])       # 36 points
+    tilt = synth.rodrigues(np.array([0.4, -0.3, 0.2]))
+    sets = [tag, board, board @ tilt.T + np.array([0.01, -0.02, 0.005])]       # the third: a plane that is not z = 0
+    dist = np.array([[-0.21, 0.08, 0.0006, -0.0004, -0.01]])
+    n_cases = 0
+    for d in (None, dist):
+        c = ctxvga if d is None else None
+        if d is not None:
+            from accurate_aprilgroup_tracking_b200.context import AgtContext
+            c = AgtContext(0, cam.mtx, d)
+        for pts in sets:
+            n = len(pts)
+            B = 24
+            poses = np.array([synth.random_pose(rng) for _ in range(B)])
+            poses[:, :3] *= 0.7                                       # keep the plane well inside the field of view
+            poses[:, 5] = rng.uniform(0.15, 0.35, B)
+            obj = np.zeros((48, 3), np.float32) if n <= 48 else None
+            obj[:n] = pts
+            img = np.zeros((B, 48, 2), np.float32)
+            valid = np.zeros((B, 48), np.uint8)
+            valid[:, :n] = 1
+            for b in range(B):
+                uv = cv2.projectPoints(pts, poses[b, :3], poses[b, 3:], cam.mtx, d)[0].reshape(-1, 2)
+                img[b, :n] = uv + rng.normal(0, 0.05, uv.shape)
+            got, ok, err, _ = c.pnp(obj, img, valid)
+            got, ok = got.cpu().numpy(), ok.cpu().numpy()
+            for b in range(B):
+                okc, rc, tc = cv2.solvePnP(pts.astype(np.float32), img[b, :n], cam.mtx, d, flags=cv2.SOLVEPNP_ITERATIVE)
+                assert okc and ok[b] == 1, (n, b)
+                util.assert_pose_close(got[b], np.concatenate([rc.ravel(), tc.ravel()]), f"{n} coplanar points, frame {b}, dist {d is not None}")
+                n_cases += 1
+        if d is not None:
+            c.close()
+    assert n_cases == 2 * 3 * 24
 
 
 # ------------------------------------------------------------------------------------------
