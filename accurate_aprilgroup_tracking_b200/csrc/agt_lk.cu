@@ -530,6 +530,7 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
       const uint32_t win_a = region_a + (jy - ry0) * REG_PITCH + (jx - rx0) + rxo;
       // mismatch products (J - I) dI per pixel: exact integers; pf holds what goes into the float chains - a row lane's
       // four pair sums (columns k, k+4) per run and component, a tail lane's five single products per run and component
+      // (the two runs of a lane as a rolled loop - half the code of the iteration, 32-bit stores - measured 2 % slower: 8.43 / 8.28 ms)
       float pfx[2][TAIL_LEN], pfy[2][TAIL_LEN];
 #pragma unroll
       for (int sg = 0; sg < 2; ++sg) {

@@ -64,7 +64,9 @@ _JOBS = []          # inherited by the forked workers (2 GB of frames: not pickl
 
 def _oracle_stream(index):
     """One stream through oracle/pipeline_oracle.py (a worker process): -> per frame (accepted, pose or None, tags tracked)."""
+    import cv2
     from oracle import ape_oracle, pipeline_oracle
+    cv2.setNumThreads(1)          # a forked child has none of the parent's OpenCV worker threads
     frames, dets, mtx = _JOBS[index]
     po = pipeline_oracle.PipelineOracle(ape_oracle.group_from_json(synth.april_group_dict()), mtx, util.dpr_model())
     out = []
