@@ -422,6 +422,7 @@ def run_gpu(args):
     # ---- BASELINE config 5 next to it, on every N the driver runs: the full pipeline (predictor -> PnP / LK fallback -> dense
     #      refinement, one frame of every stream per step), 64 streams per GPU (weak) and 64 streams in all (strong) ----
     streams = None
+    secondary = {}
     if not args.no_streams:
         from accurate_aprilgroup_tracking_b200 import sharding as _sh
         frames_s = pyr.frames[:args.cpu_sample].cpu().numpy() if (rank == 0 and not args.no_cpu) else None
@@ -431,6 +432,13 @@ def run_gpu(args):
         weak = streams_measure(torch, dist, world, rank, ctx, 64 * world, list(range(64 * rank, 64 * rank + 64)), F, 2)
         torch.cuda.empty_cache()
         strong = streams_measure(torch, dist, world, rank, ctx, 64, _sh.local_streams(64, rank, world), F, 2) if world > 1 else weak
+        torch.cuda.empty_cache()
+        secondary["lk"] = dict(lk_measure(torch, dist, world, rank, ctx, 8192, 3, 3), metric="tracked corners/sec (BASELINE config 3)",
+                               config=dict(LK_CONFIG, frame_pairs_per_gpu=8192))
+        torch.cuda.empty_cache()
+        secondary["multihyp"] = dict(multihyp_measure(torch, dist, world, rank, ctx, 64, 64, 3, 3),
+                                     metric="refined poses/sec, 64 hypotheses per frame (BASELINE config 4)")
+        torch.cuda.empty_cache()
         streams = {"metric": "refined poses/sec (full APE+LK+DPR pipeline, BASELINE config 5)",
                    "weak_64_streams_per_gpu": weak, "strong_64_streams": strong,
                    "note": "one frame of every stream per step (frames of a stream are sequential: predictor and LK need the previous "
@@ -494,6 +502,7 @@ def run_gpu(args):
     }
     if streams is not None:
         line["streams"] = streams
+    line.update(secondary)
     if e2e is not None:
         line["e2e"] = e2e
     if cpu is not None:
@@ -540,12 +549,8 @@ def _timed(torch, dist, world, fn, steps, warmup):
     return float(t.item())
 
 
-def run_lk(args):
-    """Config 3: pyramidal LK, 4 levels, 21x21, 48 corners per frame pair."""
-    torch, dist, world, rank, local = _dist_setup()
-    from accurate_aprilgroup_tracking_b200.context import AgtContext
-    ctx = AgtContext(local, CAM.mtx, None)
-    B = args.frames
+def lk_measure(torch, dist, world, rank, ctx, B, steps, warmup):
+    """Config 3 on this rank: B frame pairs x 48 corners.  -> dict (identical on every rank)."""
     traj = np.array([synth.trajectory(3000 + 7919 * rank + i, 2) for i in range(B)])
     pa, pb = ctx.alloc_pyramid(B, CAM.width, CAM.height, 4), ctx.alloc_pyramid(B, CAM.width, CAM.height, 4)
     for b0 in range(0, B, 512):
@@ -565,42 +570,53 @@ def run_lk(args):
         # pyramid of the new frames only where the corners can look + LK + exact redo of frames that looked outside
         holder["out"] = ctx.lk_roi(pa, pb, pts)
 
-    full_ms = _timed(torch, dist, world, step_full, args.steps, 3) / args.steps
+    full_ms = _timed(torch, dist, world, step_full, steps, 3) / steps
     l0 = ctx.launch_count()
-    ms = _timed(torch, dist, world, step, args.steps, args.warmup)
-    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + max(args.warmup, 3))
+    ms = _timed(torch, dist, world, step, steps, warmup)
+    launches = (ctx.launch_count() - l0) * steps // (steps + max(warmup, 3))
     same = all(bool(torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b))
                for a, b in zip(holder["out"][:3], holder["full"]))
     redone = int(holder["out"][4].sum())
     ctx.build_pyramid(pb)
-    lk_ms = _timed(torch, dist, world, lambda: holder.__setitem__("k", ctx.lk(pa, pb, pts)), args.steps, 3) / args.steps
-    if rank == 0:
-        out, st, err = holder["out"][:3]
-        peak, kind = measured_peaks()
-        corners = B * 48
-        ach = LK_BYTES_PER_CORNER * corners / (lk_ms * 1e-3) / 1e9
-        print(json.dumps({
-            "metric": "tracked corners/sec", "value": corners * world * args.steps / (ms * 1e-3), "unit": "corners/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32", "data": "synthetic",
-            "config": {"workload": "pyramidal LK: 4 levels, 21x21 window, 48 corners per 1080p frame pair", "frame_pairs_per_gpu": B,
-                       "step": "K1 pyramid of the new frames below the rectangles the corners can look at (32 px of flow) + K2 LK + "
-                               "exact redo on complete pyramids of frames that looked outside", "l2": "inputs larger than L2"},
-            "gpu_launches": int(launches), "kernel_ms": {"lk": lk_ms, "step_with_complete_pyramid": full_ms},
-            "roi_equals_complete_pyramid_path": same, "frames_redone_on_complete_pyramid": redone,
-            "tracked_frac": float(st.float().mean()),
-            "roofline": {"bound": "hbm", "kernel": "lk_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_kind": kind, "note": "5008 B per corner (SURVEY.md 8d); latency-bound by design"}}), flush=True)
+    lk_ms = _timed(torch, dist, world, lambda: holder.__setitem__("k", ctx.lk(pa, pb, pts)), steps, 3) / steps
+    st = holder["out"][1]
+    peak, kind = measured_peaks()
+    corners = B * 48
+    ach = LK_BYTES_PER_CORNER * corners / (lk_ms * 1e-3) / 1e9
+    res = {"value": corners * world * steps / (ms * 1e-3), "unit": "corners/s", "ms_per_step": ms / steps, "steps": steps,
+           "frame_pairs_per_gpu": B, "gpu_launches": int(launches), "kernel_ms": {"lk": lk_ms, "step_with_complete_pyramid": full_ms},
+           "roi_equals_complete_pyramid_path": same, "frames_redone_on_complete_pyramid": redone, "tracked_frac": float(st.float().mean()),
+           "roofline": {"bound": "hbm", "kernel": "lk_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_kind": kind,
+                        "note": "5008 B per corner (SURVEY.md 8d); bound by instruction issue and the dependent float32 chains that make it "
+                                "bit-identical to cv2.calcOpticalFlowPyrLK, not by bandwidth"}}
+    del pa, pb, holder
+    return res
 
 
-def run_multihyp(args):
-    """Config 4: 64 perturbed hypotheses per frame, LM to convergence, arg-min selection."""
+LK_CONFIG = {"workload": "pyramidal LK: 4 levels, 21x21 window, 48 corners per 1080p frame pair",
+             "step": "K1 pyramid of the new frames below the rectangles the corners can look at (32 px of flow) + K2 LK + "
+                     "exact redo on complete pyramids of frames that looked outside", "l2": "inputs larger than L2"}
+
+
+def run_lk(args):
+    """Config 3: pyramidal LK, 4 levels, 21x21, 48 corners per frame pair."""
     torch, dist, world, rank, local = _dist_setup()
     from accurate_aprilgroup_tracking_b200.context import AgtContext
     ctx = AgtContext(local, CAM.mtx, None)
-    ctx.set_synthetic_model()
-    H = 64
-    B = max(1, args.frames // H)
+    r = lk_measure(torch, dist, world, rank, ctx, args.frames, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "tracked corners/sec", "value": r["value"], "unit": "corners/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32", "data": "synthetic",
+            "config": dict(LK_CONFIG, frame_pairs_per_gpu=args.frames),
+            **{k: r[k] for k in ("gpu_launches", "kernel_ms", "roi_equals_complete_pyramid_path", "frames_redone_on_complete_pyramid",
+                                 "tracked_frac", "roofline")}}), flush=True)
+
+
+def multihyp_measure(torch, dist, world, rank, ctx, B, H, steps, warmup):
+    """Config 4 on this rank: B frames x H hypotheses.  -> dict."""
     rng = np.random.default_rng(4000 + rank)
     truth = np.array([synth.random_pose(rng) for _ in range(B)])
     init = truth[:, None, :] + np.concatenate([rng.normal(0, 0.03, (B, H, 3)), rng.normal(0, 0.002, (B, H, 3))], axis=2)
@@ -615,22 +631,37 @@ def run_multihyp(args):
         holder["res"], holder["best"] = res, ctx.select_best(res)
 
     l0 = ctx.launch_count()
-    ms = _timed(torch, dist, world, step, args.steps, args.warmup)
+    ms = _timed(torch, dist, world, step, steps, warmup)
     launches = ctx.launch_count() - l0
+    res, (best, bp) = holder["res"], holder["best"]
+    bp = bp.cpu().numpy()
+    ev, nv = res["evals"].double(), res["n_valid"].double()
+    dt = np.linalg.norm(bp[:, 3:] - truth[:, 3:], axis=1)
+    out = {"value": B * world * steps / (ms * 1e-3), "unit": "poses/s", "ms_per_step": ms / steps, "steps": steps, "frames_per_gpu": B,
+           "hypotheses": H, "gpu_launches": int(launches), "hypothesis_refinements_per_s": B * H * world * steps / (ms * 1e-3),
+           "lm": {"mean_evals": float(ev.mean()), "converged_frac": float((res["status"] == 1).double().mean()),
+                  "median_trans_err_vs_truth_m": float(np.median(dt)),
+                  "algorithmic_GBps": float((BYTES_PER_SAMPLE_EVAL * ev * nv).sum()) * steps / (ms * 1e-3) / 1e9}}
+    del pyr, holder
+    return out
+
+
+def run_multihyp(args):
+    """Config 4: 64 perturbed hypotheses per frame, LM to convergence, arg-min selection."""
+    torch, dist, world, rank, local = _dist_setup()
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    ctx = AgtContext(local, CAM.mtx, None)
+    ctx.set_synthetic_model()
+    H = 64
+    r = multihyp_measure(torch, dist, world, rank, ctx, max(1, args.frames // H), H, args.steps, args.warmup)
     if rank == 0:
-        res, (best, bp) = holder["res"], holder["best"]
-        bp = bp.cpu().numpy()
-        ev, nv = res["evals"].double(), res["n_valid"].double()
-        dt = np.linalg.norm(bp[:, 3:] - truth[:, 3:], axis=1)
         print(json.dumps({
-            "metric": "refined poses/sec (64 hypotheses per frame)", "value": B * world * args.steps / (ms * 1e-3), "unit": "poses/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "metric": "refined poses/sec (64 hypotheses per frame)", "value": r["value"], "unit": "poses/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "multi-hypothesis dense refinement: 64 inits per 1080p frame (0.03 rad, 2 mm), LM to convergence",
-                       "frames_per_gpu": B, "hypotheses": H},
-            "gpu_launches": int(launches), "hypothesis_refinements_per_s": B * H * world * args.steps / (ms * 1e-3),
-            "lm": {"mean_evals": float(ev.mean()), "median_trans_err_vs_truth_m": float(np.median(dt)),
-                   "algorithmic_GBps": float((BYTES_PER_SAMPLE_EVAL * ev * nv).sum()) * args.steps / (ms * 1e-3) / 1e9}}), flush=True)
+                       "frames_per_gpu": r["frames_per_gpu"], "hypotheses": H},
+            **{k: r[k] for k in ("gpu_launches", "hypothesis_refinements_per_s", "lm")}}), flush=True)
 
 
 def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps):
@@ -862,7 +893,7 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     ap.add_argument("--stream-scaling", default="strong", choices=["strong", "weak"])
-    ap.add_argument("--no-streams", action="store_true", help="skip the config-5 leg of the default line")
+    ap.add_argument("--no-streams", action="store_true", help="skip the config-3/4/5 legs of the default line")
     args = ap.parse_args()
     if args.frames is None:
         args.frames = 8192 if args.workload == "lk" else 4096
