@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 INCLUDE = PKG.parent / "include"
 LIB = CSRC / "libagt.so"
-SOURCES = ["agt_api.cu", "agt_pyramid.cu", "agt_undistort.cu", "agt_lk.cu", "agt_pnp.cu", "agt_ape.cu", "agt_dpr.cu", "agt_corner.cu", "agt_overlay.cu", "agt_render.cu"]
+SOURCES = ["agt_api.cu", "agt_pyramid.cu", "agt_undistort.cu", "agt_lk.cu", "agt_pnp.cu", "agt_ape.cu", "agt_dpr.cu", "agt_corner.cu", "agt_tags.cu", "agt_overlay.cu", "agt_render.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

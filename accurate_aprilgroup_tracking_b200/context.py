@@ -215,6 +215,46 @@ class AgtContext:
                                                b, n, int(win), int(max_iters), float(eps)))
         return out
 
+    def set_tag_family(self, codes=None):
+        """The 36-bit code words of the tag family (default tag36h11, the reference's family: detect_pose.py:87)."""
+        c = np.ascontiguousarray(synth.TAG36H11_CODES if codes is None else codes, dtype=np.uint64)
+        self._check(self.lib.agt_set_tag_family(self.h, c.ctypes.data, int(c.size)))
+        self._tag_family = int(c.size)
+
+    def decode_tags(self, pyr: Pyramid, quads, valid=None, max_hamming: int = 2):
+        """Identify the tag inside every quad: quads [B,Q,4,2] f32 (reference corner order, any rotation) ->
+        dict(id [B,Q] i32 (-1: none), rotation u8, hamming u8, margin f32)."""
+        t = self.torch
+        if getattr(self, "_tag_family", 0) == 0:
+            self.set_tag_family()
+        q = self._dev(quads, t.float32)
+        b, n = int(q.shape[0]), int(q.shape[1])
+        v = None if valid is None else self._dev(valid, t.uint8)
+        out = {"id": t.empty((b, n), dtype=t.int32, device=self.tdev), "rotation": t.empty((b, n), dtype=t.uint8, device=self.tdev),
+               "hamming": t.empty((b, n), dtype=t.uint8, device=self.tdev), "margin": t.empty((b, n), dtype=t.float32, device=self.tdev)}
+        self._use_current_stream()
+        self._check(self.lib.agt_decode_tags(self.h, self._p(pyr.levels[0]), pyr.desc.width[0], pyr.desc.height[0], pyr.desc.pitch[0],
+                                             pyr.desc.frame_stride[0], self._p(q), self._p(v) if v is not None else None, self._p(out["id"]),
+                                             self._p(out["rotation"]), self._p(out["hamming"]), self._p(out["margin"]), b, n, int(max_hamming)))
+        return out
+
+    def detect_tags(self, pyr: Pyramid, max_tags: int = 32, max_hamming: int = 2, refine_win: int = 4):
+        """Detect and identify the tags of every frame (level 0): -> dict(n [B] i32, id [B,T] i32, corners [B,T,4,2] f32 in the
+        reference's corner order, margin [B,T] f32, hamming [B,T] u8); entries beyond n[b] are undefined."""
+        t = self.torch
+        if getattr(self, "_tag_family", 0) == 0:
+            self.set_tag_family()
+        b = pyr.batch
+        out = {"n": t.empty(b, dtype=t.int32, device=self.tdev), "id": t.empty((b, max_tags), dtype=t.int32, device=self.tdev),
+               "corners": t.empty((b, max_tags, 4, 2), dtype=t.float32, device=self.tdev),
+               "margin": t.empty((b, max_tags), dtype=t.float32, device=self.tdev), "hamming": t.empty((b, max_tags), dtype=t.uint8, device=self.tdev)}
+        self._use_current_stream()
+        self._check(self.lib.agt_detect_tags(self.h, self._p(pyr.levels[0]), pyr.desc.width[0], pyr.desc.height[0], pyr.desc.pitch[0],
+                                             pyr.desc.frame_stride[0], b, int(max_tags), int(max_hamming), int(refine_win), self._p(out["n"]),
+                                             self._p(out["id"]), self._p(out["corners"]), self._p(out["margin"]), self._p(out["hamming"])))
+        out["n"].clamp_(max=max_tags)
+        return out
+
     def lk_rects(self, pyr: Pyramid, pts, valid=None, max_flow: int = 32):
         """Level-0 rectangle [B,4] i32 that tracking ``pts`` [B,P,2] can read while no corner moves more than max_flow px."""
         t = self.torch

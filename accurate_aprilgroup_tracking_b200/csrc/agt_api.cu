@@ -130,6 +130,7 @@ extern "C" int agt_destroy(agt_ctx* ctx) {
   for (int i = 0; i < ctx->n_retired; ++i) cudaFree(ctx->retired[i]);
   if (ctx->model.samples) cudaFree(ctx->model.samples);
   if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
+  if (ctx->d_tag_codes) cudaFree(ctx->d_tag_codes);
   if (ctx->h_rects) cudaFreeHost(ctx->h_rects);
   if (ctx->h_prects) cudaFreeHost(ctx->h_prects);
   for (int k = 0; k < 2; ++k) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->ev_stage[k]) cudaEventDestroy(ctx->ev_stage[k]); }

@@ -63,6 +63,8 @@ struct agt_ctx {
   struct agt_pack_rect* h_prects;
   struct agt_pack_rect* d_prects;
   int prect_capacity;
+  uint64_t* d_tag_codes;         // tag family (36-bit code words) of agt_decode_tags / agt_detect_tags
+  int n_tag_codes;
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];

@@ -1,0 +1,479 @@
+// N3: tag identification and detection on the device.
+//
+// The reference detects tags with the un-vendored swatbotics apriltag library (detect_pose.py:86-95 tag36h11; :368-371 detect;
+// :389-400 decision_margin filter, corner order of transform_helper.py:56-59).  The frozen semantics here are those of
+// oracle/tag_oracle.py, pinned to OpenCV's ArUco module (same family, DICT_APRILTAG_36h11) in the tests.
+//
+// agt_decode_tags - warp per quad: the 8x8 cells (6x6 data + black border) are sampled through the quad's homography (3x3
+// bilinear samples per cell, two cells per lane), the threshold lies half way between the darkest and the brightest cell, the
+// border may hold two wrong cells, and the 36 data bits are matched against the family over the four rotations (each lane
+// tries every 32nd code word, popcount of the xor); returns id, rotation, Hamming distance and the mean distance of the cells
+// from the threshold - the analogue of apriltag's decision_margin, which the reference compares with 50.
+#include <algorithm>
+
+#include "agt_common.cuh"
+
+namespace {
+
+constexpr int CELLS = 8;
+constexpr int TG_WARPS = 4;
+
+struct Homography { double a, b, c, d, e, f, g, h; };
+
+// unit square (s right, t down, (0,0) = top-left) -> quad given as (bottom-left, top-left, top-right, bottom-right)
+__device__ __forceinline__ Homography square_to_quad(const float* q) {
+  const double x3 = q[0], y3 = q[1], x0 = q[2], y0 = q[3], x1 = q[4], y1 = q[5], x2 = q[6], y2 = q[7];
+  const double dx1 = x1 - x2, dx2 = x3 - x2, sx = x0 - x1 + x2 - x3;
+  const double dy1 = y1 - y2, dy2 = y3 - y2, sy = y0 - y1 + y2 - y3;
+  const double den = dx1 * dy2 - dx2 * dy1;
+  Homography H;
+  H.g = (sx * dy2 - dx2 * sy) / den;
+  H.h = (dx1 * sy - sx * dy1) / den;
+  H.a = x1 - x0 + H.g * x1; H.b = x3 - x0 + H.h * x3; H.c = x0;
+  H.d = y1 - y0 + H.g * y1; H.e = y3 - y0 + H.h * y3; H.f = y0;
+  return H;
+}
+
+__global__ void __launch_bounds__(TG_WARPS * 32)
+decode_tags_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, const float* __restrict__ quads,
+                   const uint8_t* __restrict__ valid, const unsigned long long* __restrict__ codes, int n_codes, int32_t* __restrict__ id_out,
+                   uint8_t* __restrict__ rot_out, uint8_t* __restrict__ ham_out, float* __restrict__ margin_out, int n_quads, int64_t total,
+                   int max_hamming) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gid = (int64_t)blockIdx.x * TG_WARPS + (threadIdx.x >> 5);
+  if (gid >= total) return;
+  int id = -1, rot = 0, ham = 255;
+  float margin = 0.f;
+  const float* q = quads + gid * 8;
+  bool fin = true;
+  for (int k = 0; k < 8; ++k) fin = fin && isfinite(q[k]);
+  if ((valid == nullptr || valid[gid] != 0) && fin) {
+    const uint8_t* f = img + (gid / n_quads) * stride;
+    const Homography H = square_to_quad(q);
+    double m[2];
+    bool inside = true;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int cell = lane + 32 * half, r = cell >> 3, c = cell & 7;
+      double acc = 0.0;
+      for (int dt = -1; dt <= 1; ++dt)
+        for (int ds = -1; ds <= 1; ++ds) {
+          const double s = ((double)c + 0.5 + 0.25 * ds) / CELLS, t = ((double)r + 0.5 + 0.25 * dt) / CELLS;
+          const double ww = H.g * s + H.h * t + 1.0;
+          const double x = (H.a * s + H.b * t + H.c) / ww, y = (H.d * s + H.e * t + H.f) / ww;
+          const double fx0 = floor(x), fy0 = floor(y);
+          if (!(fx0 >= 0.0 && fy0 >= 0.0 && fx0 + 1.0 < (double)w && fy0 + 1.0 < (double)h)) { inside = false; continue; }
+          const int x0 = (int)fx0, y0 = (int)fy0;
+          const double ax = x - fx0, ay = y - fy0;
+          const uint8_t* p = f + (int64_t)y0 * pitch + x0;
+          acc += (1.0 - ax) * (1.0 - ay) * (double)__ldg(p) + ax * (1.0 - ay) * (double)__ldg(p + 1) +
+                 (1.0 - ax) * ay * (double)__ldg(p + pitch) + ax * ay * (double)__ldg(p + pitch + 1);
+        }
+      m[half] = acc / 9.0;
+    }
+    inside = __all_sync(0xffffffffu, inside);
+    if (inside) {
+      double lo = fmin(m[0], m[1]), hi = fmax(m[0], m[1]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+      const double thr = 0.5 * (lo + hi);
+      const unsigned b0 = __ballot_sync(0xffffffffu, m[0] > thr), b1 = __ballot_sync(0xffffffffu, m[1] > thr);
+      const unsigned long long bits = (unsigned long long)b0 | ((unsigned long long)b1 << 32);      // bit r*8+c
+      margin = (float)(agt_warp_sum(fabs(m[0] - thr) + fabs(m[1] - thr)) / 64.0);
+      const unsigned long long border = 0xFF818181818181FFull;
+      if (__popcll(bits & border) <= 2) {
+        // data word of each rotation: grid[i][j] = data[src(i, j)], row-major, first cell = most significant bit
+        unsigned long long word[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt)
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+              const int sr = rt == 0 ? i : (rt == 1 ? 5 - j : (rt == 2 ? 5 - i : j));
+              const int sc = rt == 0 ? j : (rt == 1 ? i : (rt == 2 ? 5 - j : 5 - i));
+              word[rt] = (word[rt] << 1) | ((bits >> ((sr + 1) * 8 + sc + 1)) & 1ull);
+            }
+        unsigned best = 0xffffffffu;                    // hamming << 24 | rotation << 16 | id: the oracle's tie-breaking order
+        for (int i = lane; i < n_codes; i += 32) {
+          const unsigned long long code = codes[i];
+#pragma unroll
+          for (int rt = 0; rt < 4; ++rt) {
+            const unsigned key = ((unsigned)__popcll(word[rt] ^ code) << 24) | ((unsigned)rt << 16) | (unsigned)i;
+            best = min(best, key);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        ham = (int)(best >> 24);
+        if (best != 0xffffffffu && ham <= max_hamming) { id = (int)(best & 0xffffu); rot = (int)((best >> 16) & 0xffu); }
+      }
+    }
+  }
+  if (lane == 0) {
+    id_out[gid] = id;
+    if (rot_out) rot_out[gid] = (uint8_t)rot;
+    if (ham_out) ham_out[gid] = (uint8_t)(ham > 255 ? 255 : ham);
+    if (margin_out) margin_out[gid] = margin;
+  }
+}
+
+}  // namespace
+
+extern "C" int agt_set_tag_family(agt_ctx* ctx, const uint64_t* h_codes, int n_codes) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_codes || n_codes < 1 || n_codes > 65535) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_tag_family: 1..65535 code words of 36 bits");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->d_tag_codes) { AGT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tag_codes); ctx->d_tag_codes = nullptr; }
+  AGT_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_tag_codes), sizeof(uint64_t) * (size_t)n_codes));
+  AGT_CUDA(ctx, cudaMemcpy(ctx->d_tag_codes, h_codes, sizeof(uint64_t) * (size_t)n_codes, cudaMemcpyHostToDevice));
+  ctx->n_tag_codes = n_codes;
+  return AGT_OK;
+}
+
+extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
+                               const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
+                               int n_quads, int max_hamming) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if ((int64_t)batch * n_quads == 0) return AGT_OK;
+  if (!ctx->d_tag_codes) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_decode_tags: call agt_set_tag_family first");
+  if (!d_gray || !d_quads || !d_id || batch < 0 || n_quads < 0 || w < 2 || h < 2 || pitch < w || max_hamming < 0 || max_hamming > 10)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_decode_tags: bad arguments");
+  const int64_t total = (int64_t)batch * n_quads, blocks = (total + TG_WARPS - 1) / TG_WARPS;
+  if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_decode_tags: batch too large");
+  decode_tags_kernel<<<(unsigned)blocks, TG_WARPS * 32, 0, ctx->stream>>>(d_gray, w, h, pitch, stride, d_quads, d_valid,
+                                                                          reinterpret_cast<const unsigned long long*>(ctx->d_tag_codes),
+                                                                          ctx->n_tag_codes, d_id, d_rotation, d_hamming, d_margin, n_quads, total,
+                                                                          max_hamming);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+// =====================================================================================================================
+// agt_detect_tags: quads of dark square regions -> corner refinement -> identification, for a batch of gray frames.
+//
+//   threshold   dark <=> gray < lo + 0.35 (hi - lo), lo / hi the frame's darkest / brightest pixel (a global threshold: good
+//               for evenly lit frames; an adaptive one is the open item)
+//   components  4-connected components of the dark pixels by union-find in global memory (each pixel links to its right
+//               and lower neighbour with atomicMin, then every pixel is pointed at its root)
+//   quad        per component: area, centroid; the boundary pixel farthest from the centroid (c0), the one farthest from
+//               c0 (c2), and the ones farthest from the line c0 c2 on either side (c1, c3) - the four corners of a convex
+//               quadrilateral whatever its orientation; components that are too small, touch the frame or are not
+//               quadrilateral (area far from the quad's) are dropped
+//   refine      agt_corner_subpix (cv::cornerSubPix) on the four corners, then agt_decode_tags; quads that decode to a tag
+//               are written in the reference's corner order (rolled by the decoded rotation)
+// =====================================================================================================================
+namespace {
+
+constexpr int MAX_COMPONENTS = 4096;      // per frame; what does not fit is ignored (counted)
+
+struct CompStats {
+  int area;
+  int x0, y0, x1, y1;
+  unsigned long long sx, sy;
+  unsigned long long far0, far2, side_p, side_n;      // (ordered float key << 32) | pixel index
+};
+
+__device__ __forceinline__ unsigned long long far_key(float v, int idx) {
+  return ((unsigned long long)__float_as_uint(fmaxf(v, 0.f)) << 32) | (unsigned)idx;       // non-negative floats order like integers
+}
+
+__global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, int* __restrict__ lohi) {
+  const int f = blockIdx.y;
+  const uint8_t* p = img + f * stride;
+  int lo = 255, hi = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)w * h; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = p[(i / w) * pitch + (i % w)];
+    lo = min(lo, v); hi = max(hi, v);
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
+}
+
+__device__ __forceinline__ bool is_dark(const uint8_t* img, int64_t pitch, int x, int y, int thr) { return img[(int64_t)y * pitch + x] < thr; }
+__device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
+  const int lo = lohi[2 * f], hi = lohi[2 * f + 1];
+  return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // a frame without contrast has no dark pixels
+}
+
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, const int* __restrict__ lohi,
+                                int* __restrict__ label) {
+  const int f = blockIdx.y;
+  const int thr = frame_threshold(lohi, f);
+  const int64_t n = (int64_t)w * h;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    label[f * n + i] = is_dark(img + f * stride, pitch, (int)(i % w), (int)(i / w), thr) ? (int)i : -1;
+}
+
+__device__ __forceinline__ int ccl_find(const int* L, int i) {
+  int r = i;
+  while (true) { const int p = L[r]; if (p == r) return r; r = p; }
+}
+__device__ __forceinline__ void ccl_union(int* L, int a, int b) {
+  while (true) {
+    a = ccl_find(L, a); b = ccl_find(L, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }          // link the larger root below the smaller one
+    const int old = atomicMin(&L[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+
+__global__ void ccl_merge_kernel(int w, int h, int* __restrict__ label) {
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (L[i] < 0) continue;
+    const int x = (int)(i % w), y = (int)(i / w);
+    if (x + 1 < w && L[i + 1] >= 0) ccl_union(L, (int)i, (int)i + 1);
+    if (y + 1 < h && L[i + w] >= 0) ccl_union(L, (int)i, (int)i + w);
+  }
+}
+
+__global__ void ccl_flatten_kernel(int w, int h, int* __restrict__ label) {
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (L[i] >= 0) L[i] = ccl_find(L, (int)i);      // roots keep L[r] == r; concurrent shortening of other paths is harmless
+}
+
+// roots get a component number: L[root] = -2 - number (numbers beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing)
+__global__ void ccl_number_kernel(int w, int h, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (L[i] == (int)i) {
+      const int c = atomicAdd(&n_comp[f], 1);
+      if (c < MAX_COMPONENTS) {
+        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+        s.area = 0; s.x0 = w; s.y0 = h; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
+      }
+      // written after the pass over this pixel: other pixels still read L[i] == i until the next kernel
+    }
+}
+__global__ void ccl_number_store_kernel(int w, int h, int* __restrict__ label, int* __restrict__ counter) {
+  // second pass so that no pixel sees a half-renumbered root: roots take their numbers in index order of arrival
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (L[i] == (int)i) {
+      const int c = atomicAdd(&counter[f], 1);
+      // cannot overwrite L[i] here either (other threads of THIS kernel test L[j] == j only for their own j): safe
+      L[i] = c < MAX_COMPONENTS ? -2 - c : -1;
+    }
+}
+
+__device__ __forceinline__ int comp_of(const int* L, int64_t i) {
+  const int l = L[i];
+  if (l == -1) return -1;
+  if (l <= -2) return -2 - l;                   // a root
+  const int r = L[l];
+  return r <= -2 ? -2 - r : -1;
+}
+
+__global__ void comp_stats_kernel(int w, int h, const int* __restrict__ label, CompStats* __restrict__ stats) {
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  const int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = comp_of(L, i);
+    if (c < 0) continue;
+    CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+    const int x = (int)(i % w), y = (int)(i / w);
+    atomicAdd(&s.area, 1);
+    atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
+    atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
+  }
+}
+
+__device__ __forceinline__ bool on_boundary(const int* L, int w, int h, int x, int y, int64_t i) {
+  return x == 0 || y == 0 || x == w - 1 || y == h - 1 || L[i - 1] == -1 || L[i + 1] == -1 || L[i - w] == -1 || L[i + w] == -1;
+}
+
+// pass 0: farthest boundary pixel from the centroid; pass 1: farthest from c0; pass 2: farthest from the line c0 c2 on each side
+__global__ void comp_far_kernel(int w, int h, const int* __restrict__ label, CompStats* __restrict__ stats, int pass) {
+  const int f = blockIdx.y;
+  const int64_t n = (int64_t)w * h;
+  const int* L = label + f * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = comp_of(L, i);
+    if (c < 0) continue;
+    const int x = (int)(i % w), y = (int)(i / w);
+    if (!on_boundary(L, w, h, x, y, i)) continue;
+    CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+    if (s.area < 48) continue;
+    if (pass == 0) {
+      const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
+      atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), (int)i));
+    } else if (pass == 1) {
+      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % w, y0 = p0 / w;
+      atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), (int)i));
+    } else {
+      const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
+      const int x0 = p0 % w, y0 = p0 / w, x2 = p2 % w, y2 = p2 / w;
+      const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
+      if (d > 0.f) atomicMax(&s.side_p, far_key(d, (int)i));
+      else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, (int)i));
+    }
+  }
+}
+
+// one thread per component: quadrilateral test, clockwise-on-screen order, emit
+__global__ void quad_emit_kernel(int w, int h, const int* __restrict__ n_comp, const CompStats* __restrict__ stats, float* __restrict__ quads,
+                                 uint8_t* __restrict__ quad_valid, int* __restrict__ n_quads, int max_quads) {
+  const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
+  const CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+  if (s.area < 48 || s.x0 <= 0 || s.y0 <= 0 || s.x1 >= w - 1 || s.y1 >= h - 1) return;            // too small / cut by the frame
+  if (s.far0 == 0 || s.far2 == 0 || s.side_p == 0 || s.side_n == 0) return;
+  const int p[4] = {(int)(s.far0 & 0xffffffffu), (int)(s.side_p & 0xffffffffu), (int)(s.far2 & 0xffffffffu), (int)(s.side_n & 0xffffffffu)};
+  float qx[4], qy[4];
+  for (int k = 0; k < 4; ++k) { qx[k] = (float)(p[k] % w); qy[k] = (float)(p[k] / w); }
+  // the component is the tag's black border plus the dark cells attached to it: between ~30 % (border alone) and 100 % of its quad
+  float area2 = 0.f;
+  for (int k = 0; k < 4; ++k) area2 += qx[k] * qy[(k + 1) & 3] - qx[(k + 1) & 3] * qy[k];
+  const float qa = 0.5f * fabsf(area2);
+  if (qa < 64.f || (float)s.area < 0.25f * qa || (float)s.area > 1.15f * qa) return;
+  // shortest side at least 6 px, and not a sliver
+  float smin = 1e30f, smax = 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const float dx = qx[(k + 1) & 3] - qx[k], dy = qy[(k + 1) & 3] - qy[k], l = sqrtf(dx * dx + dy * dy);
+    smin = fminf(smin, l); smax = fmaxf(smax, l);
+  }
+  if (smin < 6.f || smin < 0.08f * smax) return;
+  const int slot = atomicAdd(&n_quads[f], 1);
+  if (slot >= max_quads) return;
+  float* q = quads + ((int64_t)f * max_quads + slot) * 8;
+  // clockwise on the screen (y down) = positive shoelace sum: the reference's order BL, TL, TR, BR runs that way
+  const bool cw = area2 > 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const int j = cw ? k : (4 - k) & 3;
+    // the corner pixels are dark pixels just inside the tag: move half a pixel outwards from the centroid
+    const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
+    const float dx = qx[j] - cx, dy = qy[j] - cy, l = fmaxf(sqrtf(dx * dx + dy * dy), 1e-3f);
+    q[2 * k] = qx[j] + 0.5f * dx / l; q[2 * k + 1] = qy[j] + 0.5f * dy / l;
+  }
+  quad_valid[(int64_t)f * max_quads + slot] = 1;
+}
+
+// one thread per quad: keep the ones that decoded, in the reference's corner order
+__global__ void tags_collect_kernel(const float* __restrict__ quads, const int32_t* __restrict__ id, const uint8_t* __restrict__ rot,
+                                    const uint8_t* __restrict__ ham, const float* __restrict__ margin, const int* __restrict__ n_quads,
+                                    int max_quads, int32_t* __restrict__ out_n, int32_t* __restrict__ out_id, float* __restrict__ out_corners,
+                                    float* __restrict__ out_margin, uint8_t* __restrict__ out_ham, int max_tags) {
+  const int f = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= min(n_quads[f], max_quads)) return;
+  const int64_t g = (int64_t)f * max_quads + q;
+  if (id[g] < 0) return;
+  const int slot = atomicAdd(&out_n[f], 1);
+  if (slot >= max_tags) return;
+  const int64_t o = (int64_t)f * max_tags + slot;
+  out_id[o] = id[g];
+  if (out_margin) out_margin[o] = margin[g];
+  if (out_ham) out_ham[o] = ham[g];
+  const int r = rot[g];                                   // the quad's corner k is the tag's corner (k + r) mod 4
+  for (int k = 0; k < 4; ++k) {
+    const int src = (k - r + 4) & 3;
+    out_corners[o * 8 + 2 * k] = quads[g * 8 + 2 * src];
+    out_corners[o * 8 + 2 * k + 1] = quads[g * 8 + 2 * src + 1];
+  }
+}
+
+}  // namespace
+
+extern "C" int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
+                                 const uint8_t* d_valid, float* d_out, int batch, int n_pts, int win, int max_iters, double eps);
+
+extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch, int max_tags,
+                               int max_hamming, int refine_win, int32_t* d_n_tags, int32_t* d_ids, float* d_corners, float* d_margin,
+                               uint8_t* d_hamming) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!ctx->d_tag_codes) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_detect_tags: call agt_set_tag_family first");
+  if (!d_gray || !d_n_tags || !d_ids || !d_corners || batch < 0 || batch > 65535 || w < 16 || h < 16 || pitch < w || max_tags < 1 ||
+      max_tags > 1024 || (int64_t)w * h > 0x7fffffffLL || refine_win < 0 || refine_win > 7)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_detect_tags: bad arguments");
+  const int max_quads = 4 * max_tags < 64 ? 64 : 4 * max_tags;
+  const int64_t n = (int64_t)w * h;
+  int* label;
+  uint8_t* ws;
+  int rc;
+  if ((rc = agt_scratch(ctx, 0, sizeof(int) * (size_t)n * batch, reinterpret_cast<void**>(&label)))) return rc;
+  const size_t o_stats = 0, o_lohi = o_stats + sizeof(CompStats) * (size_t)MAX_COMPONENTS * batch, o_ncomp = o_lohi + sizeof(int) * 2 * batch,
+               o_ncomp2 = o_ncomp + sizeof(int) * batch, o_nquads = o_ncomp2 + sizeof(int) * batch,
+               o_quads = (o_nquads + sizeof(int) * batch + 63) & ~(size_t)63, o_refined = o_quads + sizeof(float) * 8 * (size_t)max_quads * batch,
+               o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
+               o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
+               o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, total = o_margin + sizeof(float) * (size_t)max_quads * batch;
+  if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
+  CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
+  int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *ncomp2 = reinterpret_cast<int*>(ws + o_ncomp2),
+      *nquads = reinterpret_cast<int*>(ws + o_nquads);
+  float *quads = reinterpret_cast<float*>(ws + o_quads), *refined = reinterpret_cast<float*>(ws + o_refined);
+  uint8_t* qvalid = ws + o_qvalid;
+  cudaStream_t st = ctx->stream;
+  // lo = 255, hi = 0 per frame; counters and validity flags zero
+  AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
+  AGT_CUDA(ctx, cudaMemsetAsync(qvalid, 0, (size_t)max_quads * batch, st));
+  AGT_CUDA(ctx, cudaMemsetAsync(d_n_tags, 0, sizeof(int32_t) * batch, st));
+  {
+    // lohi starts as (255, 0): set the lows with a tiny strided memset (2-D: 4 bytes every 8)
+    AGT_CUDA(ctx, cudaMemset2DAsync(lohi, 8, 0xff, 1, batch, st));          // low byte of lo = 255, the other bytes stay 0
+  }
+  const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 1184), (unsigned)batch);
+  frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, lohi);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, lohi, label);
+  ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, label);
+  ccl_flatten_kernel<<<grid, 256, 0, st>>>(w, h, label);
+  ccl_number_kernel<<<grid, 256, 0, st>>>(w, h, label, ncomp, stats);
+  ccl_number_store_kernel<<<grid, 256, 0, st>>>(w, h, label, ncomp2);
+  comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, label, stats);
+  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, label, stats, pass);
+  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, ncomp, stats, quads, qvalid, nquads, max_quads);
+  AGT_LAUNCH_CHECK(ctx);
+  const float* use = quads;
+  if (refine_win > 0) {
+    if ((rc = agt_corner_subpix(ctx, d_gray, w, h, pitch, stride, quads, nullptr, refined, batch, 4 * max_quads, refine_win, 30, 1e-3))) return rc;
+    use = refined;
+  }
+  if ((rc = agt_decode_tags(ctx, d_gray, w, h, pitch, stride, use, qvalid, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham,
+                            reinterpret_cast<float*>(ws + o_margin), batch, max_quads, max_hamming)))
+    return rc;
+  tags_collect_kernel<<<dim3((unsigned)((max_quads + 127) / 128), (unsigned)batch), 128, 0, st>>>(
+      use, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham, reinterpret_cast<float*>(ws + o_margin), nquads, max_quads, d_n_tags,
+      d_ids, d_corners, d_margin, d_hamming, max_tags);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_detect_tags_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, int max_tags, int max_hamming, int refine_win,
+                                    int32_t* h_n_tags, int32_t* h_ids, float* h_corners, float* h_margin, uint8_t* h_hamming) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (!h_gray || !h_n_tags || !h_ids || !h_corners || w < 16 || h < 16 || max_tags < 1 || max_tags > 1024)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_detect_tags_host: bad arguments");
+  AGT_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t *dimg, *dout;
+  int rc;
+  const size_t img_bytes = (size_t)w * h;
+  const size_t o_n = 0, o_id = 64, o_c = o_id + sizeof(int32_t) * (size_t)max_tags, o_m = o_c + sizeof(float) * 8 * (size_t)max_tags,
+               o_h = o_m + sizeof(float) * (size_t)max_tags, total = o_h + (size_t)max_tags;
+  if ((rc = agt_scratch(ctx, 2, img_bytes, reinterpret_cast<void**>(&dimg)))) return rc;
+  if ((rc = agt_scratch(ctx, 3, total, reinterpret_cast<void**>(&dout)))) return rc;
+  cudaStream_t st = ctx->stream;
+  AGT_CUDA(ctx, cudaMemcpyAsync(dimg, h_gray, img_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = agt_detect_tags(ctx, dimg, w, h, w, (int64_t)img_bytes, 1, max_tags, max_hamming, refine_win, reinterpret_cast<int32_t*>(dout + o_n),
+                            reinterpret_cast<int32_t*>(dout + o_id), reinterpret_cast<float*>(dout + o_c), reinterpret_cast<float*>(dout + o_m),
+                            dout + o_h)))
+    return rc;
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_n_tags, dout + o_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_ids, dout + o_id, sizeof(int32_t) * (size_t)max_tags, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaMemcpyAsync(h_corners, dout + o_c, sizeof(float) * 8 * (size_t)max_tags, cudaMemcpyDeviceToHost, st));
+  if (h_margin) AGT_CUDA(ctx, cudaMemcpyAsync(h_margin, dout + o_m, sizeof(float) * (size_t)max_tags, cudaMemcpyDeviceToHost, st));
+  if (h_hamming) AGT_CUDA(ctx, cudaMemcpyAsync(h_hamming, dout + o_h, (size_t)max_tags, cudaMemcpyDeviceToHost, st));
+  AGT_CUDA(ctx, cudaStreamSynchronize(st));
+  if (*h_n_tags > max_tags) *h_n_tags = max_tags;
+  return AGT_OK;
+}

@@ -207,6 +207,28 @@ class HostContext:
                                                     max(1, max_iters), max(eps, 0.0)))
         return corners
 
+    # -- tag detection (N3) --------------------------------------------------------------
+    def detect_tags(self, gray, max_tags: int = 64, max_hamming: int = 2, refine_win: int = 4):
+        """-> list of (tag_id, corners (4,2) float64 in the reference's corner order, decision margin, hamming) of a gray frame."""
+        img = np.ascontiguousarray(gray, dtype=np.uint8)
+        if img.ndim != 2:
+            raise ValueError("gray must be a single-channel image")
+        if not getattr(self, "_tag_family", False):
+            codes = np.ascontiguousarray(synth.TAG36H11_CODES, dtype=np.uint64)
+            self._check(self.lib.agt_set_tag_family(self.h, codes.ctypes.data, int(codes.size)))
+            self._tag_family = True
+        n = C.c_int32(0)
+        ids = np.zeros(max_tags, np.int32)
+        corners = np.zeros((max_tags, 4, 2), np.float32)
+        margin = np.zeros(max_tags, np.float32)
+        ham = np.zeros(max_tags, np.uint8)
+        self._check(self.lib.agt_detect_tags_host(self.h, C.c_void_p(img.ctypes.data), int(img.shape[1]), int(img.shape[0]), int(max_tags),
+                                                  int(max_hamming), int(refine_win), C.byref(n), C.c_void_p(ids.ctypes.data),
+                                                  C.c_void_p(corners.ctypes.data), C.c_void_p(margin.ctypes.data), C.c_void_p(ham.ctypes.data)))
+        k = min(int(n.value), max_tags)
+        order = np.argsort(ids[:k], kind="stable")
+        return [(int(ids[i]), corners[i].astype(np.float64), float(margin[i]), int(ham[i])) for i in order]
+
     # -- frame ingest -------------------------------------------------------------------
     def undistort_gray(self, frame, cameraMatrix, distCoeffs, newCameraMatrix, roi):
         """cv.cvtColor(cv.undistort(frame, K, dist, None, newK)[y:y+h, x:x+w], COLOR_BGR2GRAY) in one device pass:

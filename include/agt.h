@@ -123,6 +123,28 @@ int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t
 int agt_corner_subpix_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, float* h_pts, int n_pts, int win, int max_iters,
                            double eps);
 
+/* ---- N3: tag identification (detect_pose.py:368-400: which tag, its corner order, the decision-margin filter) --------------
+ * agt_set_tag_family: the family's 36-bit code words (tag36h11: 587; first data cell of the top row = most significant bit).
+ * agt_decode_tags: d_quads [batch][n_quads][4][2] float32 in the reference's corner order (transform_helper.py:56-59: bottom-left,
+ * top-left, top-right, bottom-right of the printed tag; any cyclic rotation of it is accepted) -> d_id (-1: no tag), d_rotation
+ * (the quad's first corner is the tag's corner d_rotation), d_hamming, d_margin (mean distance of the 64 cell means from the
+ * threshold: the analogue of apriltag's decision_margin).  Semantics: oracle/tag_oracle.py:decode_np. */
+int agt_set_tag_family(agt_ctx* ctx, const uint64_t* h_codes, int n_codes);
+int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
+                    const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
+                    int n_quads, int max_hamming);
+
+/* agt_detect_tags: the detector itself for a batch of gray frames (detect_pose.py:368-371 detector.detect): dark 4-connected
+ * components (global threshold per frame) -> quadrilateral fit -> agt_corner_subpix (refine_win, 0 = off) -> agt_decode_tags.
+ * Per frame up to max_tags tags: d_n_tags [batch] (may exceed max_tags: clamp), d_ids [batch][max_tags], d_corners
+ * [batch][max_tags][4][2] in the reference's corner order, d_margin / d_hamming (nullable).  The order of the tags of a frame is
+ * not defined.  Pinned to cv2.aruco.ArucoDetector (DICT_APRILTAG_36h11) in tests/: same ids, corners within a pixel. */
+int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch, int max_tags,
+                    int max_hamming, int refine_win, int32_t* d_n_tags, int32_t* d_ids, float* d_corners, float* d_margin,
+                    uint8_t* d_hamming);
+int agt_detect_tags_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, int max_tags, int max_hamming, int refine_win,
+                         int32_t* h_n_tags, int32_t* h_ids, float* h_corners, float* h_margin, uint8_t* h_hamming);
+
 /* ---- N4: the overlay after the path, batched (detect_pose.py:441-465 _project_draw_points; draw.py:120-153) --------------
  * For every frame with a non-zero d_frame_mask entry (NULL = all) and every point: (x, y) = np.round(d_pts) and, if
  * 0 <= x < bound_w and 0 <= y < bound_h (the reference tests against 1280 x 720), cv.circle(img, (x, y), radius,
