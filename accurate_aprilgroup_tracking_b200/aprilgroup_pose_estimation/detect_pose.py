@@ -16,9 +16,10 @@ including the in-place write of solvePnP into the guess arrays and the resulting
 aliasing of ``extrinsic_guess`` and ``prev_transform``.  The frame ingest runs on the
 device as well: ``process_frame`` is cv.undistort + crop (and keeps the gray image of the
 result, computed in the same pass, for ``_detect_and_get_pose``), the gray conversion of
-any other BGR frame is ``agt_bgr_to_gray`` - both bit-exact against cv2.  Tag detection,
-capture and drawing are outside the accelerated path and keep using whatever
-``apriltag`` / ``cv2`` modules the host has, exactly like the reference.
+any other BGR frame is ``agt_bgr_to_gray`` - both bit-exact against cv2.  Tag detection uses the
+host's ``apriltag`` module when there is one, exactly like the reference, and otherwise the device
+detector behind the same surface (``apriltag_gpu``: quads from dark components, cornerSubPix, tag36h11
+decoding; pinned to cv2.aruco in the tests).  Capture and drawing keep using ``cv2`` like the reference.
 
 Cameras.  The reference passes (mtx, dist) to solvePnP / projectPoints even though the
 frame it detects on has been undistorted and cropped by ``process_frame`` (detect_pose.py:
@@ -83,12 +84,13 @@ class PoseDetector(TransformHelper, Draw):
         self._prev_corners: List[Tuple[int, np.ndarray]] = []
         self._frame_corners: List[Tuple[int, np.ndarray]] = []
         try:
-            import apriltag
-            self.options = apriltag.DetectorOptions(families='tag36h11', border=1, nthreads=4, quad_decimate=1.0,
-                                                    quad_blur=0.0, refine_edges=True, refine_decode=False,
-                                                    refine_pose=True, debug=False, quad_contours=True)
+            import apriltag                      # the host's apriltag module, exactly as the reference (detect_pose.py:22)
         except ImportError:
-            self.options = None      # detector absent: _obtain_detections() raises, callers may feed detections
+            from .. import apriltag_gpu as apriltag      # not installed: the detector of csrc/agt_tags.cu behind the same surface
+        self._apriltag = apriltag
+        self.options = apriltag.DetectorOptions(families='tag36h11', border=1, nthreads=4, quad_decimate=1.0,
+                                                quad_blur=0.0, refine_edges=True, refine_decode=False,
+                                                refine_pose=True, debug=False, quad_contours=True)
         self.extrinsics = self.get_extrinsics()
         self.all_objpts = self.get_all_points(self.extrinsics)
         if use_dense_refine:
@@ -179,11 +181,7 @@ class PoseDetector(TransformHelper, Draw):
         return img_list, obj_list, ids
 
     def _obtain_detections(self, gray: np.ndarray):
-        if self.options is None:
-            raise ImportError("the 'apriltag' module is not installed: tag detection is outside the accelerated path "
-                              "(SURVEY.md section 2, row 9); install it or feed detections to _estimate_pose()")
-        import apriltag
-        detector = apriltag.Detector(self.options)
+        detector = self._apriltag.Detector(self.options)
         results, _ = detector.detect(gray, return_image=True)
         self.logger.info('Detected %d tags.', len(results))
         if not results or self.mtx is None:

@@ -66,6 +66,10 @@ class BatchedPoseDetector:
         if use_dense_refine and ctx._model is None:
             ctx.set_synthetic_model()
         self._epoch = getattr(ctx, "config_epoch", 0)
+        # the detector in front of the path (step_frames): the group's ids in JSON key order, and how many kept detections of the
+        # last step carried an id outside the group
+        self.group_ids = ctx._dev(np.array(sorted(self.tag_pos, key=self.tag_pos.get), dtype=np.int32), t.int32)
+        self.n_unknown = t.zeros(self.n, dtype=t.int32, device=dev)
 
     def pack(self, dets_per_stream):
         """Detections [(tag_id, corners (4,2)), ...] per stream -> the (img_pts, valid, n_tags) arrays ``step`` takes, indexed by
@@ -127,6 +131,25 @@ class BatchedPoseDetector:
         return {"pose": pose_out, "accepted": accepted, "error_flag": flag, "reproj_err": err,
                 "n_tags": ntg, "tracked_tags": tracked_tags, "refine": refined}
 
+    def step_frames(self, frames=None, min_margin: float = 50.0, refine_win: int = 4, max_tags: int = 32, check_ids: bool = False):
+        """Pixels in, poses out: ``_obtain_detections`` (detect_pose.py:351-439) on the device in front of ``step`` - agt_detect_tags
+        on level 0 of the current slot, the decision-margin filter and the id -> position mapping by agt_pack_detections,
+        straight into the static input buffers of the captured step; no detection ever visits the host.  ``check_ids`` reads
+        ``n_unknown`` back and raises KeyError like the reference (detect_pose.py:408-415) when a kept detection carries an id
+        the group does not have (a synchronisation: off by default, the count stays in ``self.n_unknown``)."""
+        ctx = self.ctx
+        slot = self.cur
+        if frames is not None:
+            ctx.upload_frames(self.pyr[slot], frames)
+            self._built[slot] = False
+        det = ctx.detect_tags(self.pyr[slot], max_tags=max_tags, refine_win=refine_win)
+        ctx.pack_detections(det, self.group_ids, min_margin, out=(self.in_img, self.in_valid, self.in_ntags, self.n_unknown))
+        if check_ids and int(self.n_unknown.sum().item()):
+            raise KeyError("a detected tag id is not in the group")
+        out = self.step(None, None, None)
+        out["detections"] = det
+        return out
+
     def step(self, img_pts, valid, n_tags, frames=None):
         """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),
         n_tags [S] i32 accepted detections.  ``frames`` [S,H,W] u8 is copied into the current slot
@@ -140,9 +163,10 @@ class BatchedPoseDetector:
         if not self._built[slot]:
             ctx.build_pyramid(self.pyr[slot])                # K1 (unless ingest_next built this slot during the last step)
         self._built[slot] = False                            # the caller writes the next frame into it before it is used again
-        self.in_img.copy_(ctx._dev(img_pts, t.float32))
-        self.in_valid.copy_(ctx._dev(valid, t.uint8))
-        self.in_ntags.copy_(ctx._dev(n_tags, t.int32))
+        if img_pts is not None:                              # None: step_frames has filled the input buffers on the device
+            self.in_img.copy_(ctx._dev(img_pts, t.float32))
+            self.in_valid.copy_(ctx._dev(valid, t.uint8))
+            self.in_ntags.copy_(ctx._dev(n_tags, t.int32))
         if self._epoch != getattr(ctx, "config_epoch", 0):
             # set_camera / set_model since the graphs were captured: they hold the camera by value and the model's pointers,
             # so replaying them would silently keep the old ones - drop them and capture again

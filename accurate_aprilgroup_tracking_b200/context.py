@@ -255,6 +255,22 @@ class AgtContext:
         out["n"].clamp_(max=max_tags)
         return out
 
+    def pack_detections(self, det, group_ids, min_margin: float = 50.0, out=None):
+        """A0 on the device: the dict ``detect_tags`` returns -> (img_pts [B,4T,2] f32, valid [B,4T] u8, n_tags [B] i32, n_unknown
+        [B] i32) indexed by the tags' positions in ``group_ids`` (the group's ids in JSON key order); detections with
+        margin < min_margin are dropped (detect_pose.py:389).  ``out`` = the same tuple of preallocated tensors."""
+        t = self.torch
+        g = self._dev(np.asarray(list(group_ids), dtype=np.int32), t.int32) if not hasattr(group_ids, "device") else group_ids
+        b, mt, ng = int(det["id"].shape[0]), int(det["id"].shape[1]), int(g.numel())
+        if out is None:
+            out = (t.empty((b, 4 * ng, 2), dtype=t.float32, device=self.tdev), t.empty((b, 4 * ng), dtype=t.uint8, device=self.tdev),
+                   t.empty(b, dtype=t.int32, device=self.tdev), t.empty(b, dtype=t.int32, device=self.tdev))
+        self._use_current_stream()
+        self._check(self.lib.agt_pack_detections(self.h, self._p(det["n"]), self._p(det["id"]), self._p(det["corners"]), self._p(det["margin"]),
+                                                 mt, self._p(g), ng, float(min_margin), self._p(out[0]), self._p(out[1]), self._p(out[2]),
+                                                 self._p(out[3]), b))
+        return out
+
     def lk_rects(self, pyr: Pyramid, pts, valid=None, max_flow: int = 32):
         """Level-0 rectangle [B,4] i32 that tracking ``pts`` [B,P,2] can read while no corner moves more than max_flow px."""
         t = self.torch

@@ -20,19 +20,21 @@ constexpr int CS_WARPS = 4;
 
 __global__ void __launch_bounds__(CS_WARPS * 32)
 corner_subpix_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, const float* __restrict__ pts,
-                     const uint8_t* __restrict__ valid, float* __restrict__ out, int n_pts, int64_t total, int win, int max_iters,
-                     double eps2) {
+                     const uint8_t* __restrict__ valid, const uint8_t* __restrict__ win_of, float* __restrict__ out, int n_pts, int64_t total,
+                     int win, int max_iters, double eps2) {
   __shared__ float s_patch[CS_WARPS][MAX_PATCH][MAX_PATCH + 1];
-  __shared__ float s_mask[2 * MAX_WIN + 1];
+  __shared__ float s_masks[CS_WARPS][2 * MAX_WIN + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int n = 2 * win + 1, np = n + 2;
-  if (threadIdx.x < n) {
-    const float x = (float)((int)threadIdx.x - win) / (float)win;
-    s_mask[threadIdx.x] = expf(-x * x);      // std::exp(float): correctly rounded here (checked against cv2 in the tests)
-  }
-  __syncthreads();
   const int64_t gid = (int64_t)blockIdx.x * CS_WARPS + wid;
   if (gid >= total) return;
+  if (win_of != nullptr) win = min(max((int)win_of[gid], 1), MAX_WIN);       // per-point window (the detector sizes it by the tag's cells)
+  const int n = 2 * win + 1, np = n + 2;
+  float* s_mask = s_masks[wid];
+  if (lane < n) {
+    const float x = (float)(lane - win) / (float)win;
+    s_mask[lane] = expf(-x * x);             // std::exp(float): correctly rounded here (checked against cv2 in the tests)
+  }
+  __syncwarp();
   const float tx = pts[gid * 2], ty = pts[gid * 2 + 1];
   if ((valid != nullptr && valid[gid] == 0) || !(tx >= 0.f && tx < (float)w && ty >= 0.f && ty < (float)h)) {
     if (lane == 0) { out[gid * 2] = tx; out[gid * 2 + 1] = ty; }
@@ -86,8 +88,10 @@ corner_subpix_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitc
 
 }  // namespace
 
-extern "C" int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
-                                 const uint8_t* d_valid, float* d_out, int batch, int n_pts, int win, int max_iters, double eps) {
+// d_win [batch][n_pts] (nullable): window half-size per point instead of `win`
+int agt_corner_subpix_windows(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
+                              const uint8_t* d_valid, const uint8_t* d_win, float* d_out, int batch, int n_pts, int win, int max_iters,
+                              double eps) {
   if (!ctx) return AGT_ERR_INVALID;
   if ((int64_t)batch * n_pts == 0) return AGT_OK;
   if (!d_gray || !d_pts || !d_out || batch < 0 || n_pts < 0 || w < 1 || h < 1 || pitch < w || win < 1 || win > MAX_WIN || max_iters < 1 ||
@@ -97,10 +101,15 @@ extern "C" int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int
   const int64_t total = (int64_t)batch * n_pts;
   const int64_t blocks = (total + CS_WARPS - 1) / CS_WARPS;
   if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_corner_subpix: batch too large");
-  corner_subpix_kernel<<<(unsigned)blocks, CS_WARPS * 32, 0, ctx->stream>>>(d_gray, w, h, pitch, stride, d_pts, d_valid, d_out, n_pts, total,
-                                                                            win, max_iters, eps * eps);
+  corner_subpix_kernel<<<(unsigned)blocks, CS_WARPS * 32, 0, ctx->stream>>>(d_gray, w, h, pitch, stride, d_pts, d_valid, d_win, d_out, n_pts,
+                                                                            total, win, max_iters, eps * eps);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
+}
+
+extern "C" int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
+                                 const uint8_t* d_valid, float* d_out, int batch, int n_pts, int win, int max_iters, double eps) {
+  return agt_corner_subpix_windows(ctx, d_gray, w, h, pitch, stride, d_pts, d_valid, nullptr, d_out, batch, n_pts, win, max_iters, eps);
 }
 
 extern "C" int agt_corner_subpix_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, float* h_pts, int n_pts, int win, int max_iters,

@@ -323,7 +323,8 @@ __global__ void comp_far_kernel(int w, int h, const int* __restrict__ label, Com
 
 // one thread per component: quadrilateral test, clockwise-on-screen order, emit
 __global__ void quad_emit_kernel(int w, int h, const int* __restrict__ n_comp, const CompStats* __restrict__ stats, float* __restrict__ quads,
-                                 uint8_t* __restrict__ quad_valid, int* __restrict__ n_quads, int max_quads) {
+                                 uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads, int max_quads,
+                                 int refine_win) {
   const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
   const CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
@@ -357,6 +358,15 @@ __global__ void quad_emit_kernel(int w, int h, const int* __restrict__ n_comp, c
     q[2 * k] = qx[j] + 0.5f * dx / l; q[2 * k + 1] = qy[j] + 0.5f * dy / l;
   }
   quad_valid[(int64_t)f * max_quads + slot] = 1;
+  // corner-refinement window: half a tag cell (a cell = an eighth of the side), so that the window of a small tag does not reach
+  // the corners of its inner cells (the rule of OpenCV's ArUco detector, relativeCornerRefinmentWinSize), at most refine_win
+  float mean_side = 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const float dx = qx[(k + 1) & 3] - qx[k], dy = qy[(k + 1) & 3] - qy[k];
+    mean_side += 0.25f * sqrtf(dx * dx + dy * dy);
+  }
+  const int win = min(max((int)(0.5f * mean_side / 8.f + 0.5f), 2), max(refine_win, 1));
+  for (int k = 0; k < 4; ++k) quad_win[((int64_t)f * max_quads + slot) * 4 + k] = (uint8_t)win;
 }
 
 // one thread per quad: keep the ones that decoded, in the reference's corner order
@@ -382,10 +392,56 @@ __global__ void tags_collect_kernel(const float* __restrict__ quads, const int32
   }
 }
 
+// warp per frame, lane per group position: the detection of that tag with the largest margin (a tag reported twice fills one slot)
+__global__ void pack_detections_kernel(const int32_t* __restrict__ n_det, const int32_t* __restrict__ det_id, const float* __restrict__ det_corners,
+                                       const float* __restrict__ det_margin, int max_tags, const int32_t* __restrict__ group_ids, int n_group,
+                                       float min_margin, float* __restrict__ img_pts, uint8_t* __restrict__ valid, int32_t* __restrict__ n_tags,
+                                       int32_t* __restrict__ n_unknown, int batch) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= batch) return;
+  const int nd = min(n_det[f], max_tags);
+  const int32_t* ids = det_id + (int64_t)f * max_tags;
+  const float* mg = det_margin ? det_margin + (int64_t)f * max_tags : nullptr;
+  int count = 0, matched = 0;
+  for (int pos = lane; pos < n_group; pos += 32) {
+    const int want = group_ids[pos];
+    int best = -1;
+    float best_m = 0.f, best_x = 0.f;
+    for (int k = 0; k < nd; ++k) {
+      if (ids[k] != want) continue;
+      const float m = mg ? mg[k] : min_margin;
+      if (!(m >= min_margin)) continue;                        // detect_pose.py:389: decision_margin < 50 is skipped
+      ++matched;
+      const float x = det_corners[((int64_t)f * max_tags + k) * 8];
+      if (best < 0 || m > best_m || (m == best_m && x < best_x)) { best = k; best_m = m; best_x = x; }
+    }
+    float* o = img_pts + ((int64_t)f * n_group + pos) * 8;
+    uint8_t* v = valid + ((int64_t)f * n_group + pos) * 4;
+    if (best >= 0) {
+      const float* c = det_corners + ((int64_t)f * max_tags + best) * 8;
+      for (int j = 0; j < 8; ++j) o[j] = c[j];
+      v[0] = v[1] = v[2] = v[3] = 1;
+      ++count;
+    } else {
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      v[0] = v[1] = v[2] = v[3] = 0;
+    }
+  }
+  int kept = 0;                                                // detections that pass the margin filter, whatever their id
+  for (int k = lane; k < nd; k += 32) kept += (!mg || mg[k] >= min_margin) ? 1 : 0;
+  count = __reduce_add_sync(0xffffffffu, count); matched = __reduce_add_sync(0xffffffffu, matched); kept = __reduce_add_sync(0xffffffffu, kept);
+  if (lane == 0) {
+    n_tags[f] = count;
+    if (n_unknown) n_unknown[f] = kept - matched;              // ids outside the group: the reference raises KeyError on them
+  }
+}
+
 }  // namespace
 
-extern "C" int agt_corner_subpix(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
-                                 const uint8_t* d_valid, float* d_out, int batch, int n_pts, int win, int max_iters, double eps);
+int agt_corner_subpix_windows(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_pts,
+                              const uint8_t* d_valid, const uint8_t* d_win, float* d_out, int batch, int n_pts, int win, int max_iters,
+                              double eps);
 
 extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch, int max_tags,
                                int max_hamming, int refine_win, int32_t* d_n_tags, int32_t* d_ids, float* d_corners, float* d_margin,
@@ -407,7 +463,8 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
                o_quads = (o_nquads + sizeof(int) * batch + 63) & ~(size_t)63, o_refined = o_quads + sizeof(float) * 8 * (size_t)max_quads * batch,
                o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
                o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
-               o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, total = o_margin + sizeof(float) * (size_t)max_quads * batch;
+               o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, o_win = o_margin + sizeof(float) * (size_t)max_quads * batch,
+               total = o_win + 4 * (size_t)max_quads * batch;
   if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
   CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
   int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *ncomp2 = reinterpret_cast<int*>(ws + o_ncomp2),
@@ -418,6 +475,7 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
   // lo = 255, hi = 0 per frame; counters and validity flags zero
   AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
   AGT_CUDA(ctx, cudaMemsetAsync(qvalid, 0, (size_t)max_quads * batch, st));
+  AGT_CUDA(ctx, cudaMemsetAsync(ws + o_win, 0, 4 * (size_t)max_quads * batch, st));
   AGT_CUDA(ctx, cudaMemsetAsync(d_n_tags, 0, sizeof(int32_t) * batch, st));
   {
     // lohi starts as (255, 0): set the lows with a tiny strided memset (2-D: 4 bytes every 8)
@@ -432,11 +490,15 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
   ccl_number_store_kernel<<<grid, 256, 0, st>>>(w, h, label, ncomp2);
   comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, label, stats);
   for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, label, stats, pass);
-  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, ncomp, stats, quads, qvalid, nquads, max_quads);
+  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, ncomp, stats, quads, qvalid, ws + o_win, nquads, max_quads,
+                                                                                   refine_win);
   AGT_LAUNCH_CHECK(ctx);
   const float* use = quads;
   if (refine_win > 0) {
-    if ((rc = agt_corner_subpix(ctx, d_gray, w, h, pitch, stride, quads, nullptr, refined, batch, 4 * max_quads, refine_win, 30, 1e-3))) return rc;
+    // only the corners of emitted quads (the validity flag of a quad, four times), each with its own window
+    if ((rc = agt_corner_subpix_windows(ctx, d_gray, w, h, pitch, stride, quads, ws + o_win, ws + o_win, refined, batch, 4 * max_quads,
+                                        refine_win, 30, 1e-3)))
+      return rc;
     use = refined;
   }
   if ((rc = agt_decode_tags(ctx, d_gray, w, h, pitch, stride, use, qvalid, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham,
@@ -445,6 +507,21 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
   tags_collect_kernel<<<dim3((unsigned)((max_quads + 127) / 128), (unsigned)batch), 128, 0, st>>>(
       use, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham, reinterpret_cast<float*>(ws + o_margin), nquads, max_quads, d_n_tags,
       d_ids, d_corners, d_margin, d_hamming, max_tags);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_pack_detections(agt_ctx* ctx, const int32_t* d_n_det, const int32_t* d_det_ids, const float* d_det_corners,
+                                   const float* d_det_margin, int max_tags, const int32_t* d_group_ids, int n_group, float min_margin,
+                                   float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int32_t* d_n_unknown, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!d_n_det || !d_det_ids || !d_det_corners || !d_group_ids || !d_img_pts || !d_valid || !d_n_tags || batch < 0 || max_tags < 1 ||
+      n_group < 1 || n_group > 4096)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pack_detections: bad arguments");
+  pack_detections_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, ctx->stream>>>(d_n_det, d_det_ids, d_det_corners, d_det_margin, max_tags,
+                                                                              d_group_ids, n_group, min_margin, d_img_pts, d_valid, d_n_tags,
+                                                                              d_n_unknown, batch);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

@@ -144,6 +144,15 @@ int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t p
                     uint8_t* d_hamming);
 int agt_detect_tags_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, int max_tags, int max_hamming, int refine_win,
                          int32_t* h_n_tags, int32_t* h_ids, float* h_corners, float* h_margin, uint8_t* h_hamming);
+/* A0 on the device (detect_pose.py:385-437 _obtain_detections): the output of agt_detect_tags -> the arrays the batched path
+ * takes.  Detections with d_det_margin < min_margin are dropped (detect_pose.py:389, the reference's 50; NULL margins keep all);
+ * the corners of the tag with id d_group_ids[k] (the group's ids in JSON key order, detect_pose.py:122) go to d_img_pts
+ * [batch][n_group][4][2] at position k with d_valid [batch][n_group][4] = 1, everything else is zero; a tag seen twice keeps the
+ * detection with the larger margin; d_n_tags [batch] = tags placed; d_n_unknown [batch] (nullable) = kept detections whose id is
+ * not in the group (the reference raises KeyError on those, detect_pose.py:408-415: the host wrapper does the same). */
+int agt_pack_detections(agt_ctx* ctx, const int32_t* d_n_det, const int32_t* d_det_ids, const float* d_det_corners,
+                        const float* d_det_margin, int max_tags, const int32_t* d_group_ids, int n_group, float min_margin,
+                        float* d_img_pts, uint8_t* d_valid, int32_t* d_n_tags, int32_t* d_n_unknown, int batch);
 
 /* ---- N4: the overlay after the path, batched (detect_pose.py:441-465 _project_draw_points; draw.py:120-153) --------------
  * For every frame with a non-zero d_frame_mask entry (NULL = all) and every point: (x, y) = np.round(d_pts) and, if

@@ -12,6 +12,8 @@ running the real thing here and are committed with this script:
   lk_pair.npz        cv2.calcOpticalFlowPyrLK + cv2.pyrDown + cv2.Scharr (OpenCV 4.13.0) on a rendered
                      320x240 frame pair
   dpr_case.npz       oracle/dpr_oracle.py on a rendered 320x240 frame (no reference code exists for this stage)
+  tag_case.npz       cv2.aruco.ArucoDetector (DICT_APRILTAG_36h11) on three rendered 640x480 frames: ids and corners in the
+                     reference's corner order, next to the true corners (row N3; the reference's apriltag library is absent)
 
 Versions are recorded inside each file.
 """
@@ -142,12 +144,29 @@ def make_undistort():
                         source=np.array(["cv2.getOptimalNewCameraMatrix + cv2.undistort + cv2.cvtColor, the calls of detect_pose.py:167-177, 602"]))
 
 
+def make_tags():
+    from oracle import tag_oracle
+    cam = synth.CAMERA_VGA
+    frames, poses, ids, corners, counts = [], [], [], [], []
+    for s in (700, 702, 709):
+        pose = synth.trajectory(s, 1)[0]
+        frame = synth.render(pose, cam, seed=s)
+        det = sorted(tag_oracle.detect_cv(frame), key=lambda d: d[0])
+        frames.append(frame); poses.append(pose); counts.append(len(det))
+        ids.extend(i for i, _ in det); corners.extend(c for _, c in det)
+    np.savez_compressed(GOLDEN / "tag_case.npz", frames=np.stack(frames), poses=np.array(poses), counts=np.array(counts),
+                        ids=np.array(ids, np.int32), corners=np.array(corners), mtx=cam.mtx, versions=VERSIONS,
+                        source=np.array(["cv2.aruco.ArucoDetector(DICT_APRILTAG_36h11).detectMarkers, default parameters; "
+                                         "corners rolled to the order of transform_helper.py:56-59"]))
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     make_ape()
     make_lk()
     make_dpr()
     make_undistort()
+    make_tags()
     for p in sorted(GOLDEN.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

@@ -278,3 +278,55 @@ def test_corner_subpix_restatement_equals_opencv():
     a, b = corner_oracle.corner_subpix_cv(img, border), corner_oracle.corner_subpix_np(img, border)
     worst = max(worst, float(np.abs(a - b).max()))
     assert worst <= 1e-4, worst           # float32 resampling order: identical on almost every corner
+
+
+# ---------------------------------------------------------------------------- tag identification / detection (row N3)
+def test_tag_decoder_restatement_agrees_with_aruco():
+    """decode_np (the frozen specification of agt_decode_tags) against OpenCV's ArUco module, the one implementation of the
+    tag36h11 family in the image: on every tag aruco finds, decoding aruco's own corners returns aruco's id (hamming 0,
+    rotation 0 once the corners are in the reference's order); decoding the true corners returns the true id; a quad that
+    starts at the tag's corner k comes back with rotation k; the committed aruco output (tests/golden/tag_case.npz) is
+    reproduced by the installed cv2."""
+    from oracle import tag_oracle
+    cam = synth.CAMERA_VGA
+    obj = synth.object_points()
+    g = np.load(make_golden.GOLDEN / "tag_case.npz")
+    at = 0
+    for frame, pose, cnt in zip(g["frames"], g["poses"], g["counts"]):
+        live = sorted(tag_oracle.detect_cv(frame), key=lambda d: d[0])
+        assert [i for i, _ in live] == g["ids"][at:at + cnt].tolist()
+        assert np.abs(np.array([c for _, c in live]) - g["corners"][at:at + cnt]).max() < 1e-3
+        at += cnt
+    n_aruco = 0
+    for s in range(8):
+        pose = synth.trajectory(720 + s, 1)[0]
+        img = synth.render(pose, cam, seed=s)
+        facing = set(synth.visible_tags(pose, cos_limit=0.0).tolist())          # aruco also reads tags seen at a grazing angle
+        for tag, corners in tag_oracle.detect_cv(img):
+            assert tag in facing
+            n_aruco += 1
+            assert tag_oracle.decode_np(img, corners)[:3] == (tag, 0, 0)
+            true = synth.project(obj[4 * tag:4 * tag + 4], pose, cam)
+            assert np.abs(corners - true).max() < 3.0            # aruco's corners are contour points
+            tid, rot, ham, margin = tag_oracle.decode_np(img, true)
+            assert (tid, rot, ham) == (tag, 0, 0) and margin > 50.0          # the reference's decision-margin bar
+            for k in range(1, 4):
+                assert tag_oracle.decode_np(img, np.roll(true, -k, axis=0))[:3] == (tag, k, 0)
+    assert n_aruco >= 20
+    # not a tag: a flat patch, a quad across two faces, a quad that leaves the image
+    assert tag_oracle.decode_np(img, np.array([[10, 40], [10, 10], [40, 10], [40, 40]], float))[0] == -1
+    assert tag_oracle.decode_np(img, np.array([[-5, 40], [-5, 10], [40, 10], [40, 40]], float)) == (-1, 0, 255, 0.0)
+
+
+def test_pack_detections_host_rules():
+    """The A0 rules the device kernel agt_pack_detections has to reproduce (tests/test_gpu_tags.py compares it with this
+    function): position = index of the id in the group's JSON order, unknown ids raise, a tag seen twice fills one slot."""
+    from accurate_aprilgroup_tracking_b200.batched import pack_detections
+    group = [7, 3, 11, 0]
+    c = np.arange(8, dtype=np.float32).reshape(4, 2)
+    img, valid, n = pack_detections([[(3, c), (0, c + 100)], [], [(11, c + 5), (11, c + 6)]], group)
+    assert n.tolist() == [2, 0, 1]
+    assert np.array_equal(img[0, 4:8], c) and np.array_equal(img[0, 12:16], c + 100) and valid[0].tolist() == [0] * 4 + [1] * 4 + [0] * 4 + [1] * 4
+    assert valid[2].tolist() == [0] * 8 + [1] * 4 + [0] * 4
+    with pytest.raises(KeyError):
+        pack_detections([[(5, c)]], group)
