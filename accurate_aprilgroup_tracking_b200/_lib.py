@@ -61,6 +61,8 @@ PROTOTYPES = {
     "agt_decode_tags": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I]),
     "agt_detect_tags": (_I, [_VP, _VP, _I, _I, _I64, _I64, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "agt_detect_tags_host": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "agt_detect_tags_roi": (_I, [_VP, _VP, _I, _I, _I64, _I64, _I, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "agt_track_rects": (_I, [_VP, _VP, _D, _I, _I, _I, _VP, _I]),
     "agt_pack_detections": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _VP, _I, C.c_float, _VP, _VP, _VP, _VP, _I]),
     "agt_draw_points": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I]),
     "agt_corner_subpix": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _VP, _I, _I, _I, _I, _D]),

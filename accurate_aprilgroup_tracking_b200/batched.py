@@ -70,6 +70,7 @@ class BatchedPoseDetector:
         # last step carried an id outside the group
         self.group_ids = ctx._dev(np.array(sorted(self.tag_pos, key=self.tag_pos.get), dtype=np.int32), t.int32)
         self.n_unknown = t.zeros(self.n, dtype=t.int32, device=dev)
+        self.radius = float(np.linalg.norm(np.asarray(obj_pts, dtype=np.float64), axis=1).max())      # bounding sphere of the group
 
     def pack(self, dets_per_stream):
         """Detections [(tag_id, corners (4,2)), ...] per stream -> the (img_pts, valid, n_tags) arrays ``step`` takes, indexed by
@@ -131,18 +132,25 @@ class BatchedPoseDetector:
         return {"pose": pose_out, "accepted": accepted, "error_flag": flag, "reproj_err": err,
                 "n_tags": ntg, "tracked_tags": tracked_tags, "refine": refined}
 
-    def step_frames(self, frames=None, min_margin: float = 50.0, refine_win: int = 4, max_tags: int = 32, check_ids: bool = False):
+    def step_frames(self, frames=None, min_margin: float = 50.0, refine_win: int = 4, max_tags: int = 32, check_ids: bool = False,
+                    track_window: bool = True, track_margin: int = 48):
         """Pixels in, poses out: ``_obtain_detections`` (detect_pose.py:351-439) on the device in front of ``step`` - agt_detect_tags
         on level 0 of the current slot, the decision-margin filter and the id -> position mapping by agt_pack_detections,
         straight into the static input buffers of the captured step; no detection ever visits the host.  ``check_ids`` reads
         ``n_unknown`` back and raises KeyError like the reference (detect_pose.py:408-415) when a kept detection carries an id
-        the group does not have (a synchronisation: off by default, the count stays in ``self.n_unknown``)."""
+        the group does not have (a synchronisation: off by default, the count stays in ``self.n_unknown``).  ``track_window``: a
+        stream that has a predicted or a last accepted pose is searched only around it (bounding sphere of the group + ``track_margin``
+        pixels, agt_track_rects) - a few percent of a 1080p frame; streams without a pose are searched whole."""
         ctx = self.ctx
         slot = self.cur
         if frames is not None:
             ctx.upload_frames(self.pyr[slot], frames)
             self._built[slot] = False
-        det = ctx.detect_tags(self.pyr[slot], max_tags=max_tags, refine_win=refine_win)
+        rects = None
+        if track_window:
+            # look where the object is expected: around the predicted / last accepted pose of each stream (whole frame without one)
+            rects = ctx.track_rects(self.state, self.pyr[slot].desc.width[0], self.pyr[slot].desc.height[0], self.radius, track_margin)
+        det = ctx.detect_tags(self.pyr[slot], max_tags=max_tags, refine_win=refine_win, rects=rects)
         ctx.pack_detections(det, self.group_ids, min_margin, out=(self.in_img, self.in_valid, self.in_ntags, self.n_unknown))
         if check_ids and int(self.n_unknown.sum().item()):
             raise KeyError("a detected tag id is not in the group")

@@ -238,9 +238,20 @@ class AgtContext:
                                              self._p(out["rotation"]), self._p(out["hamming"]), self._p(out["margin"]), b, n, int(max_hamming)))
         return out
 
-    def detect_tags(self, pyr: Pyramid, max_tags: int = 32, max_hamming: int = 2, refine_win: int = 4):
+    def track_rects(self, state, width: int, height: int, radius: float, margin: int = 48):
+        """Search windows [B,4] i32 (x0,y0,x1,y1) of the detector from the stream states: around the predicted (else the last
+        accepted) pose; the empty rectangle (= whole frame) for streams without one."""
+        t = self.torch
+        b = int(state.shape[0])
+        rects = t.empty((b, 4), dtype=t.int32, device=self.tdev)
+        self._use_current_stream()
+        self._check(self.lib.agt_track_rects(self.h, self._p(state), float(radius), int(margin), int(width), int(height), self._p(rects), b))
+        return rects
+
+    def detect_tags(self, pyr: Pyramid, max_tags: int = 32, max_hamming: int = 2, refine_win: int = 4, rects=None):
         """Detect and identify the tags of every frame (level 0): -> dict(n [B] i32, id [B,T] i32, corners [B,T,4,2] f32 in the
-        reference's corner order, margin [B,T] f32, hamming [B,T] u8); entries beyond n[b] are undefined."""
+        reference's corner order, margin [B,T] f32, hamming [B,T] u8); entries beyond n[b] are undefined.  ``rects`` [B,4] i32:
+        search window per frame (empty = whole frame)."""
         t = self.torch
         if getattr(self, "_tag_family", 0) == 0:
             self.set_tag_family()
@@ -249,9 +260,12 @@ class AgtContext:
                "corners": t.empty((b, max_tags, 4, 2), dtype=t.float32, device=self.tdev),
                "margin": t.empty((b, max_tags), dtype=t.float32, device=self.tdev), "hamming": t.empty((b, max_tags), dtype=t.uint8, device=self.tdev)}
         self._use_current_stream()
-        self._check(self.lib.agt_detect_tags(self.h, self._p(pyr.levels[0]), pyr.desc.width[0], pyr.desc.height[0], pyr.desc.pitch[0],
-                                             pyr.desc.frame_stride[0], b, int(max_tags), int(max_hamming), int(refine_win), self._p(out["n"]),
-                                             self._p(out["id"]), self._p(out["corners"]), self._p(out["margin"]), self._p(out["hamming"])))
+        r = None if rects is None else self._dev(rects, t.int32)
+        self._check(self.lib.agt_detect_tags_roi(self.h, self._p(pyr.levels[0]), pyr.desc.width[0], pyr.desc.height[0], pyr.desc.pitch[0],
+                                                 pyr.desc.frame_stride[0], b, self._p(r) if r is not None else None,
+                                                 int(r.shape[1]) if r is not None else 0, int(max_tags), int(max_hamming), int(refine_win),
+                                                 self._p(out["n"]), self._p(out["id"]), self._p(out["corners"]), self._p(out["margin"]),
+                                                 self._p(out["hamming"])))
         out["n"].clamp_(max=max_tags)
         return out
 

@@ -184,7 +184,43 @@ __global__ void ape_commit_kernel(double* __restrict__ state, const int32_t* __r
   }
 }
 
+// where the detector has to look in the next frame of a stream: the image of the object's bounding sphere at the predicted pose
+// (the extrinsic guess, detect_pose.py:553-566) or else at the last accepted pose, plus a margin; no pose -> the whole frame
+__global__ void track_rects_kernel(const double* __restrict__ state, agt_camera cam, double radius, int margin, int w, int h,
+                                   int32_t* __restrict__ rects, int batch) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const double* s = state + (int64_t)i * AGT_STREAM_STATE_DOUBLES;
+  const double* t = s[S_HAS_GUESS] != 0.0 ? s + S_GUESS + 3 : (s[S_HAS_PREV] != 0.0 ? s + S_PREV + 3 : nullptr);
+  int r[4] = {0, 0, 0, 0};                                   // empty rectangle: search the whole frame
+  if (t != nullptr && t[2] > 1e-6 && t[0] == t[0] && t[1] == t[1]) {
+    double ext[4];
+    for (int a = 0; a < 2; ++a) {
+      const double c = t[a], f = a == 0 ? cam.fx : cam.fy, pp = a == 0 ? cam.cx : cam.cy;
+      const double sb = fmin(radius / sqrt(c * c + t[2] * t[2]), 0.95);
+      const double al = atan2(c, t[2]), be = asin(sb);
+      ext[2 * a] = f * tan(fmax(al - be, -1.5)) + pp - margin;
+      ext[2 * a + 1] = f * tan(fmin(al + be, 1.5)) + pp + margin;
+    }
+    const int x0 = (int)fmax(floor(ext[0]), 0.0), y0 = (int)fmax(floor(ext[2]), 0.0);
+    const int x1 = (int)fmin(ceil(ext[1]) + 1.0, (double)w), y1 = (int)fmin(ceil(ext[3]) + 1.0, (double)h);
+    if (x1 > x0 && y1 > y0) { r[0] = x0; r[1] = y0; r[2] = x1; r[3] = y1; }
+  }
+  reinterpret_cast<int4*>(rects)[i] = make_int4(r[0], r[1], r[2], r[3]);
+}
+
 }  // namespace
+
+extern "C" int agt_track_rects(agt_ctx* ctx, const double* d_state, double radius, int margin, int w, int h, int32_t* d_rects, int batch) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_track_rects: no camera set");
+  if (!d_state || !d_rects || batch < 0 || !(radius > 0.0) || margin < 0 || w < 1 || h < 1 || (reinterpret_cast<uintptr_t>(d_rects) & 15) != 0)
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_track_rects: bad arguments (d_rects 16-byte aligned)");
+  track_rects_kernel<<<(batch + 127) / 128, 128, 0, ctx->stream>>>(d_state, ctx->cam, radius, margin, w, h, d_rects, batch);
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
 
 extern "C" int agt_ape_prepare(agt_ctx* ctx, const double* d_state, double* d_guess, uint8_t* d_use_guess, int batch,
                                int enhance_ape) {

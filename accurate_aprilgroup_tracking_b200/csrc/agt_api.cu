@@ -114,6 +114,13 @@ extern "C" int agt_create(int device, agt_ctx** out) {
   ctx->stream = ctx->own_stream;
   ctx->roi_upload = 1;
   {
+    // whole-frame pyramids in one pass over HBM: measured slower than the per-level launches (2.75 against 2.46 ms per 4096
+    // frames: the HBM traffic drops to the algorithmic 2.8 MB per frame, but half of the CTA's warps follow the other half and
+    // the kernel is issue-bound), so it is opt-in: AGT_K1_FUSED=1 (scripts/k1_fused_probe.py)
+    const char* e = getenv("AGT_K1_FUSED");
+    ctx->k1_fused = e && e[0] == '1';
+  }
+  {
     unsigned hc = std::thread::hardware_concurrency();
     ctx->upload_threads = hc == 0 ? 4 : (hc < 8 ? (int)hc : 8);
   }

@@ -47,6 +47,8 @@ struct agt_ctx {
   short* d_remap_tab;            // [1024][4] int16 bilinear weights of cv::remap (device)
   agt_model model;
   int64_t launches;
+  int k1_fused;                  // whole-frame pyramids in one pass (pyr_fused_kernel); AGT_K1_FUSED=0 selects the per-level launches
+  int k1_fused_per_sm;           // resident CTAs per SM of that kernel (0: not asked yet)
   int roi_upload;                // agt_refine_host uploads only the rectangle a refinement can read
   int64_t last_h2d_bytes;        // host->device bytes of the last agt_refine_host call
   int last_redo_frames;          // frames the last agt_refine_host call redid from the full frame

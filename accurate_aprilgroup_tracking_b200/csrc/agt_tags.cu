@@ -176,31 +176,48 @@ __device__ __forceinline__ unsigned long long far_key(float v, int idx) {
   return ((unsigned long long)__float_as_uint(fmaxf(v, 0.f)) << 32) | (unsigned)idx;       // non-negative floats order like integers
 }
 
-__global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, int* __restrict__ lohi) {
-  const int f = blockIdx.y;
-  const uint8_t* p = img + f * stride;
+// search window of a frame: the whole frame, or the part of it inside the frame's rectangle (x0, y0, x1, y1; an empty rectangle
+// means the whole frame).  Pixel index i of a window runs row by row over the window; labels are indexed the same way.
+struct Win { int x0, y0, ww, hh; };
+__device__ __forceinline__ Win frame_window(const int32_t* rects, int rect_stride, int f, int w, int h) {
+  Win q = {0, 0, w, h};
+  if (rects != nullptr) {
+    const int32_t* r = rects + (int64_t)f * rect_stride;
+    const int x0 = max(r[0], 0), y0 = max(r[1], 0), x1 = min(r[2], w), y1 = min(r[3], h);
+    if (x1 > x0 && y1 > y0) { q.x0 = x0; q.y0 = y0; q.ww = x1 - x0; q.hh = y1 - y0; }
+  }
+  return q;
+}
+#define AGT_WIN_ARGS const int32_t* __restrict__ rects, int rect_stride
+#define AGT_WIN_LOOP                                                                                                   \
+  const int f = blockIdx.y;                                                                                            \
+  const Win win = frame_window(rects, rect_stride, f, w, h);                                                           \
+  const int n = win.ww * win.hh;                                                                                       \
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+
+__global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
+                                    int* __restrict__ lohi) {
+  const uint8_t* p = img + blockIdx.y * stride;
   int lo = 255, hi = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)w * h; i += (int64_t)gridDim.x * blockDim.x) {
-    const int v = p[(i / w) * pitch + (i % w)];
+  AGT_WIN_LOOP {
+    const int v = p[(int64_t)(win.y0 + i / win.ww) * pitch + win.x0 + i % win.ww];
     lo = min(lo, v); hi = max(hi, v);
   }
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-  if ((threadIdx.x & 31) == 0) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
 }
 
-__device__ __forceinline__ bool is_dark(const uint8_t* img, int64_t pitch, int x, int y, int thr) { return img[(int64_t)y * pitch + x] < thr; }
 __device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
   const int lo = lohi[2 * f], hi = lohi[2 * f + 1];
   return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // a frame without contrast has no dark pixels
 }
 
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, const int* __restrict__ lohi,
-                                int* __restrict__ label) {
-  const int f = blockIdx.y;
-  const int thr = frame_threshold(lohi, f);
-  const int64_t n = (int64_t)w * h;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    label[f * n + i] = is_dark(img + f * stride, pitch, (int)(i % w), (int)(i / w), thr) ? (int)i : -1;
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
+                                const int* __restrict__ lohi, int* __restrict__ label) {
+  const uint8_t* p = img + blockIdx.y * stride;
+  const int thr = frame_threshold(lohi, blockIdx.y);
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP L[i] = p[(int64_t)(win.y0 + i / win.ww) * pitch + win.x0 + i % win.ww] < thr ? i : -1;
 }
 
 __device__ __forceinline__ int ccl_find(const int* L, int i) {
@@ -218,55 +235,46 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
   }
 }
 
-__global__ void ccl_merge_kernel(int w, int h, int* __restrict__ label) {
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP {
     if (L[i] < 0) continue;
-    const int x = (int)(i % w), y = (int)(i / w);
-    if (x + 1 < w && L[i + 1] >= 0) ccl_union(L, (int)i, (int)i + 1);
-    if (y + 1 < h && L[i + w] >= 0) ccl_union(L, (int)i, (int)i + w);
+    const int x = i % win.ww, y = i / win.ww;
+    if (x + 1 < win.ww && L[i + 1] >= 0) ccl_union(L, i, i + 1);
+    if (y + 1 < win.hh && L[i + win.ww] >= 0) ccl_union(L, i, i + win.ww);
   }
 }
 
-__global__ void ccl_flatten_kernel(int w, int h, int* __restrict__ label) {
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    if (L[i] >= 0) L[i] = ccl_find(L, (int)i);      // roots keep L[r] == r; concurrent shortening of other paths is harmless
+__global__ void ccl_flatten_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP
+    if (L[i] >= 0) L[i] = ccl_find(L, i);           // roots keep L[r] == r; concurrent shortening of other paths is harmless
 }
 
-// roots get a component number: L[root] = -2 - number (numbers beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing)
-__global__ void ccl_number_kernel(int w, int h, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    if (L[i] == (int)i) {
+// roots get a component number: L[root] = -2 - number (numbers beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing).
+// Two kernels, so that no pixel sees a half-renumbered root: the first one only resets the statistics records.
+__global__ void ccl_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP
+    if (L[i] == i) {
       const int c = atomicAdd(&n_comp[f], 1);
       if (c < MAX_COMPONENTS) {
         CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-        s.area = 0; s.x0 = w; s.y0 = h; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
+        s.area = 0; s.x0 = win.ww; s.y0 = win.hh; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
       }
-      // written after the pass over this pixel: other pixels still read L[i] == i until the next kernel
     }
 }
-__global__ void ccl_number_store_kernel(int w, int h, int* __restrict__ label, int* __restrict__ counter) {
-  // second pass so that no pixel sees a half-renumbered root: roots take their numbers in index order of arrival
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    if (L[i] == (int)i) {
+__global__ void ccl_number_store_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ counter) {
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP
+    if (L[i] == i) {
       const int c = atomicAdd(&counter[f], 1);
-      // cannot overwrite L[i] here either (other threads of THIS kernel test L[j] == j only for their own j): safe
+      // other threads of THIS kernel test L[j] == j only for their own j: overwriting L[i] here is safe
       L[i] = c < MAX_COMPONENTS ? -2 - c : -1;
     }
 }
 
-__device__ __forceinline__ int comp_of(const int* L, int64_t i) {
+__device__ __forceinline__ int comp_of(const int* L, int i) {
   const int l = L[i];
   if (l == -1) return -1;
   if (l <= -2) return -2 - l;                   // a root
@@ -274,75 +282,73 @@ __device__ __forceinline__ int comp_of(const int* L, int64_t i) {
   return r <= -2 ? -2 - r : -1;
 }
 
-__global__ void comp_stats_kernel(int w, int h, const int* __restrict__ label, CompStats* __restrict__ stats) {
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  const int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+// all coordinates of the statistics are window coordinates
+__global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats) {
+  const int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP {
     const int c = comp_of(L, i);
     if (c < 0) continue;
     CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-    const int x = (int)(i % w), y = (int)(i / w);
+    const int x = i % win.ww, y = i / win.ww;
     atomicAdd(&s.area, 1);
     atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
     atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
   }
 }
 
-__device__ __forceinline__ bool on_boundary(const int* L, int w, int h, int x, int y, int64_t i) {
-  return x == 0 || y == 0 || x == w - 1 || y == h - 1 || L[i - 1] == -1 || L[i + 1] == -1 || L[i - w] == -1 || L[i + w] == -1;
+__device__ __forceinline__ bool on_boundary(const int* L, int ww, int hh, int x, int y, int i) {
+  return x == 0 || y == 0 || x == ww - 1 || y == hh - 1 || L[i - 1] == -1 || L[i + 1] == -1 || L[i - ww] == -1 || L[i + ww] == -1;
 }
 
 // pass 0: farthest boundary pixel from the centroid; pass 1: farthest from c0; pass 2: farthest from the line c0 c2 on each side
-__global__ void comp_far_kernel(int w, int h, const int* __restrict__ label, CompStats* __restrict__ stats, int pass) {
-  const int f = blockIdx.y;
-  const int64_t n = (int64_t)w * h;
-  const int* L = label + f * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats, int pass) {
+  const int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP {
     const int c = comp_of(L, i);
     if (c < 0) continue;
-    const int x = (int)(i % w), y = (int)(i / w);
-    if (!on_boundary(L, w, h, x, y, i)) continue;
+    const int x = i % win.ww, y = i / win.ww;
+    if (!on_boundary(L, win.ww, win.hh, x, y, i)) continue;
     CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
     if (s.area < 48) continue;
     if (pass == 0) {
       const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
-      atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), (int)i));
+      atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
     } else if (pass == 1) {
-      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % w, y0 = p0 / w;
-      atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), (int)i));
+      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % win.ww, y0 = p0 / win.ww;
+      atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
     } else {
       const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
-      const int x0 = p0 % w, y0 = p0 / w, x2 = p2 % w, y2 = p2 / w;
+      const int x0 = p0 % win.ww, y0 = p0 / win.ww, x2 = p2 % win.ww, y2 = p2 / win.ww;
       const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
-      if (d > 0.f) atomicMax(&s.side_p, far_key(d, (int)i));
-      else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, (int)i));
+      if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
+      else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, i));
     }
   }
 }
 
-// one thread per component: quadrilateral test, clockwise-on-screen order, emit
-__global__ void quad_emit_kernel(int w, int h, const int* __restrict__ n_comp, const CompStats* __restrict__ stats, float* __restrict__ quads,
-                                 uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads, int max_quads,
-                                 int refine_win) {
+// one thread per component: quadrilateral test, clockwise-on-screen order, emit (frame coordinates)
+__global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_comp, const CompStats* __restrict__ stats,
+                                 float* __restrict__ quads, uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads,
+                                 int max_quads, int refine_win) {
   const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
+  const Win win = frame_window(rects, rect_stride, f, w, h);
   const CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-  if (s.area < 48 || s.x0 <= 0 || s.y0 <= 0 || s.x1 >= w - 1 || s.y1 >= h - 1) return;            // too small / cut by the frame
+  if (s.area < 48 || s.x0 <= 0 || s.y0 <= 0 || s.x1 >= win.ww - 1 || s.y1 >= win.hh - 1) return;      // too small / cut by the window
   if (s.far0 == 0 || s.far2 == 0 || s.side_p == 0 || s.side_n == 0) return;
   const int p[4] = {(int)(s.far0 & 0xffffffffu), (int)(s.side_p & 0xffffffffu), (int)(s.far2 & 0xffffffffu), (int)(s.side_n & 0xffffffffu)};
   float qx[4], qy[4];
-  for (int k = 0; k < 4; ++k) { qx[k] = (float)(p[k] % w); qy[k] = (float)(p[k] / w); }
+  for (int k = 0; k < 4; ++k) { qx[k] = (float)(p[k] % win.ww); qy[k] = (float)(p[k] / win.ww); }
   // the component is the tag's black border plus the dark cells attached to it: between ~30 % (border alone) and 100 % of its quad
   float area2 = 0.f;
   for (int k = 0; k < 4; ++k) area2 += qx[k] * qy[(k + 1) & 3] - qx[(k + 1) & 3] * qy[k];
   const float qa = 0.5f * fabsf(area2);
   if (qa < 64.f || (float)s.area < 0.25f * qa || (float)s.area > 1.15f * qa) return;
   // shortest side at least 6 px, and not a sliver
-  float smin = 1e30f, smax = 0.f;
+  float smin = 1e30f, smax = 0.f, mean_side = 0.f;
   for (int k = 0; k < 4; ++k) {
     const float dx = qx[(k + 1) & 3] - qx[k], dy = qy[(k + 1) & 3] - qy[k], l = sqrtf(dx * dx + dy * dy);
-    smin = fminf(smin, l); smax = fmaxf(smax, l);
+    smin = fminf(smin, l); smax = fmaxf(smax, l); mean_side += 0.25f * l;
   }
   if (smin < 6.f || smin < 0.08f * smax) return;
   const int slot = atomicAdd(&n_quads[f], 1);
@@ -350,23 +356,18 @@ __global__ void quad_emit_kernel(int w, int h, const int* __restrict__ n_comp, c
   float* q = quads + ((int64_t)f * max_quads + slot) * 8;
   // clockwise on the screen (y down) = positive shoelace sum: the reference's order BL, TL, TR, BR runs that way
   const bool cw = area2 > 0.f;
+  const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
   for (int k = 0; k < 4; ++k) {
     const int j = cw ? k : (4 - k) & 3;
     // the corner pixels are dark pixels just inside the tag: move half a pixel outwards from the centroid
-    const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
     const float dx = qx[j] - cx, dy = qy[j] - cy, l = fmaxf(sqrtf(dx * dx + dy * dy), 1e-3f);
-    q[2 * k] = qx[j] + 0.5f * dx / l; q[2 * k + 1] = qy[j] + 0.5f * dy / l;
+    q[2 * k] = (float)win.x0 + qx[j] + 0.5f * dx / l; q[2 * k + 1] = (float)win.y0 + qy[j] + 0.5f * dy / l;
   }
   quad_valid[(int64_t)f * max_quads + slot] = 1;
   // corner-refinement window: half a tag cell (a cell = an eighth of the side), so that the window of a small tag does not reach
   // the corners of its inner cells (the rule of OpenCV's ArUco detector, relativeCornerRefinmentWinSize), at most refine_win
-  float mean_side = 0.f;
-  for (int k = 0; k < 4; ++k) {
-    const float dx = qx[(k + 1) & 3] - qx[k], dy = qy[(k + 1) & 3] - qy[k];
-    mean_side += 0.25f * sqrtf(dx * dx + dy * dy);
-  }
-  const int win = min(max((int)(0.5f * mean_side / 8.f + 0.5f), 2), max(refine_win, 1));
-  for (int k = 0; k < 4; ++k) quad_win[((int64_t)f * max_quads + slot) * 4 + k] = (uint8_t)win;
+  const int cwin = min(max((int)(0.5f * mean_side / 8.f + 0.5f), 2), max(refine_win, 1));
+  for (int k = 0; k < 4; ++k) quad_win[((int64_t)f * max_quads + slot) * 4 + k] = (uint8_t)cwin;
 }
 
 // one thread per quad: keep the ones that decoded, in the reference's corner order
@@ -443,10 +444,11 @@ int agt_corner_subpix_windows(agt_ctx* ctx, const uint8_t* d_gray, int w, int h,
                               const uint8_t* d_valid, const uint8_t* d_win, float* d_out, int batch, int n_pts, int win, int max_iters,
                               double eps);
 
-extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch, int max_tags,
-                               int max_hamming, int refine_win, int32_t* d_n_tags, int32_t* d_ids, float* d_corners, float* d_margin,
-                               uint8_t* d_hamming) {
+extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch,
+                                   const int32_t* d_rects, int rect_stride, int max_tags, int max_hamming, int refine_win, int32_t* d_n_tags,
+                                   int32_t* d_ids, float* d_corners, float* d_margin, uint8_t* d_hamming) {
   if (!ctx) return AGT_ERR_INVALID;
+  if (d_rects != nullptr && rect_stride < 4) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_detect_tags_roi: rect_stride < 4");
   if (batch == 0) return AGT_OK;
   if (!ctx->d_tag_codes) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_detect_tags: call agt_set_tag_family first");
   if (!d_gray || !d_n_tags || !d_ids || !d_corners || batch < 0 || batch > 65535 || w < 16 || h < 16 || pitch < w || max_tags < 1 ||
@@ -481,17 +483,19 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
     // lohi starts as (255, 0): set the lows with a tiny strided memset (2-D: 4 bytes every 8)
     AGT_CUDA(ctx, cudaMemset2DAsync(lohi, 8, 0xff, 1, batch, st));          // low byte of lo = 255, the other bytes stay 0
   }
-  const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, 1184), (unsigned)batch);
-  frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, lohi);
-  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, lohi, label);
-  ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, label);
-  ccl_flatten_kernel<<<grid, 256, 0, st>>>(w, h, label);
-  ccl_number_kernel<<<grid, 256, 0, st>>>(w, h, label, ncomp, stats);
-  ccl_number_store_kernel<<<grid, 256, 0, st>>>(w, h, label, ncomp2);
-  comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, label, stats);
-  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, label, stats, pass);
-  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, ncomp, stats, quads, qvalid, ws + o_win, nquads, max_quads,
-                                                                                   refine_win);
+  // grid-stride over the pixels of each frame's window; with windows (usually a few percent of the frame) a smaller grid per frame
+  const int64_t per_frame = d_rects ? std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch) : 1184;
+  const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, per_frame), (unsigned)batch);
+  frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label);
+  ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
+  ccl_flatten_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
+  ccl_number_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp, stats);
+  ccl_number_store_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp2);
+  comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats);
+  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats, pass);
+  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
+                                                                                   nquads, max_quads, refine_win);
   AGT_LAUNCH_CHECK(ctx);
   const float* use = quads;
   if (refine_win > 0) {
@@ -509,6 +513,13 @@ extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
       d_ids, d_corners, d_margin, d_hamming, max_tags);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
+}
+
+extern "C" int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch, int max_tags,
+                               int max_hamming, int refine_win, int32_t* d_n_tags, int32_t* d_ids, float* d_corners, float* d_margin,
+                               uint8_t* d_hamming) {
+  return agt_detect_tags_roi(ctx, d_gray, w, h, pitch, stride, batch, nullptr, 0, max_tags, max_hamming, refine_win, d_n_tags, d_ids, d_corners,
+                             d_margin, d_hamming);
 }
 
 extern "C" int agt_pack_detections(agt_ctx* ctx, const int32_t* d_n_det, const int32_t* d_det_ids, const float* d_det_corners,

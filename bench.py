@@ -664,9 +664,10 @@ def run_multihyp(args):
             **{k: r[k] for k in ("gpu_launches", "hypothesis_refinements_per_s", "lm")}}), flush=True)
 
 
-def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps):
+def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps, from_pixels=False):
     """Config 5 on this rank's streams `mine` (global stream ids): the whole sequence `steps` times, timed on the device, max
-    over ranks.  -> dict (identical on every rank)."""
+    over ranks.  -> dict (identical on every rank).  from_pixels: the tag detector runs on the device in front of the path
+    (BatchedPoseDetector.step_frames: detect -> decision-margin filter -> id mapping -> APE ...) instead of detections handed in."""
     from accurate_aprilgroup_tracking_b200 import sharding
     from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector
     S, F = len(mine), n_frames
@@ -707,7 +708,7 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
                 with torch.cuda.stream(side):
                     bpd.ingest_next(bank_frames[f + 1])                 # ingest copy + K1 of the next frame
                     landed.record(side)
-            out = bpd.step(det_img[f], det_valid[f], det_n[f])
+            out = bpd.step_frames() if from_pixels else bpd.step(det_img[f], det_valid[f], det_n[f])
             hist[:, f].copy_(out["pose"])
             stepped.record(main)
             if f + 1 < F:
@@ -755,13 +756,16 @@ def run_streams(args):
     weak = args.stream_scaling == "weak"
     s_total = args.streams * world if weak else args.streams
     mine = list(range(rank * args.streams, (rank + 1) * args.streams)) if weak else sharding.local_streams(s_total, rank, world)
-    r = streams_measure(torch, dist, world, rank, ctx, s_total, mine, args.stream_frames, args.steps)
+    pixels = args.stream_input == "pixels"
+    r = streams_measure(torch, dist, world, rank, ctx, s_total, mine, args.stream_frames, args.steps, from_pixels=pixels)
     if rank == 0:
         print(json.dumps({
             "metric": "refined poses/sec (full APE+LK+DPR pipeline)", "value": r["value"], "unit": "poses/s",
             "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": r["ms_per_sequence"], "higher_is_better": True,
             "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "concurrent 1080p camera streams, predictor -> PnP / LK fallback -> dense refinement per frame",
+            "config": {"workload": ("concurrent 1080p camera streams, " + ("tag detector (search window around the predicted pose) -> " if pixels else "")
+                                    + "predictor -> PnP / LK fallback -> dense refinement per frame"),
+                       "input": "frames only (tags detected on the device)" if pixels else "frames + tag detections",
                        "streams": s_total, "frames_per_stream": args.stream_frames, "step": "one pass over all frames of all streams",
                        "parallelism": (f"{args.streams} streams per GPU" if weak else f"streams s mod {world} -> GPU")
                                       + "; one NCCL all-gather of all poses at the end of the sequence"},
@@ -893,6 +897,8 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     ap.add_argument("--stream-scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--stream-input", default="detections", choices=["detections", "pixels"],
+                    help="streams workload: tag detections handed in (BASELINE config 5), or frames only - the detector runs on the device")
     ap.add_argument("--no-streams", action="store_true", help="skip the config-3/4/5 legs of the default line")
     args = ap.parse_args()
     if args.frames is None:

@@ -144,6 +144,17 @@ int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t p
                     uint8_t* d_hamming);
 int agt_detect_tags_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, int max_tags, int max_hamming, int refine_win,
                          int32_t* h_n_tags, int32_t* h_ids, float* h_corners, float* h_margin, uint8_t* h_hamming);
+/* The detector on a search window per frame: d_rects [batch][rect_stride >= 4] int32 = x0, y0, x1, y1 in level-0 pixels (clipped to
+ * the frame; an empty rectangle = the whole frame; NULL = every frame whole).  Thresholding, components and quads see only the
+ * window (a tag cut by the window's edge is dropped like one cut by the frame); results are in frame coordinates.  In a tracking
+ * loop the window is the neighbourhood of the predicted object (agt_track_rects): a few percent of a 1080p frame. */
+int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, int batch,
+                        const int32_t* d_rects, int rect_stride, int max_tags, int max_hamming, int refine_win, int32_t* d_n_tags,
+                        int32_t* d_ids, float* d_corners, float* d_margin, uint8_t* d_hamming);
+/* Search windows from the stream states (see agt_ape_prepare): the image of a sphere of `radius` metres around the group's origin
+ * at the predicted pose (the extrinsic guess, detect_pose.py:553-566), else at the last accepted pose, grown by `margin` pixels;
+ * streams without a pose get the empty rectangle (= whole frame).  d_rects [batch][4] int32, 16-byte aligned. */
+int agt_track_rects(agt_ctx* ctx, const double* d_state, double radius, int margin, int w, int h, int32_t* d_rects, int batch);
 /* A0 on the device (detect_pose.py:385-437 _obtain_detections): the output of agt_detect_tags -> the arrays the batched path
  * takes.  Detections with d_det_margin < min_margin are dropped (detect_pose.py:389, the reference's 50; NULL margins keep all);
  * the corners of the tag with id d_group_ids[k] (the group's ids in JSON key order, detect_pose.py:122) go to d_img_pts

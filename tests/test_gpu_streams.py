@@ -59,25 +59,30 @@ def test_batched_streams_match_single_stream_detector(ctxvga, detector_factory):
     assert tracked_total >= 2          # the LK path was exercised
 
 
-_JOBS = []          # inherited by the forked workers (2 GB of frames: not pickled)
-
-
-def _oracle_stream(index):
-    """One stream through oracle/pipeline_oracle.py (a worker process): -> per frame (accepted, pose or None, tags tracked)."""
+def _oracle_stream(job):
+    """One stream through oracle/pipeline_oracle.py (a worker process): -> per frame (accepted, pose or None, tags tracked).
+    The workers are SPAWNED (a fork of a process that holds a CUDA context and the BLAS / OpenCV thread pools can deadlock in the
+    child) and map the frames from a file instead of receiving 2 GB through a pipe."""
     import cv2
     from oracle import ape_oracle, pipeline_oracle
-    cv2.setNumThreads(1)          # a forked child has none of the parent's OpenCV worker threads
-    frames, dets, mtx = _JOBS[index]
+    cv2.setNumThreads(1)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)                      # one BLAS thread per worker: 16 workers do not fight over 16 x 16 threads
+    except Exception:
+        pass
+    path, stream, dets, mtx = job
+    frames = np.load(path, mmap_mode="r")[:, stream]
     po = pipeline_oracle.PipelineOracle(ape_oracle.group_from_json(synth.april_group_dict()), mtx, util.dpr_model())
     out = []
     for f in range(len(frames)):
-        po.frame(frames[f], dets[f])
+        po.frame(np.ascontiguousarray(frames[f]), dets[f])
         pose = None if po.prev[0] is None else np.concatenate([po.prev[0].ravel(), po.prev[1].ravel().astype(np.float64)])
         out.append((po.last_accepted, pose, po.tracked))
     return out
 
 
-def test_config5_64_streams_1080p_match_pipeline_oracle(ctx1080):
+def test_config5_64_streams_1080p_match_pipeline_oracle(ctx1080, tmp_path):
     """BASELINE config 5 at its shape: 64 concurrent 1080p streams, 16 frames each, full APE + LK + dense refinement per frame
     with detector dropouts (one tag left -> LK carries the rest; nothing detected -> the stream resets), the batched detector
     against the CPU composition of the stage oracles run per stream (reference state machine + cv2 LK + dense oracle)."""
@@ -108,10 +113,13 @@ def test_config5_64_streams_1080p_match_pipeline_oracle(ctx1080):
         got_pose.append(out["pose"].cpu().numpy().copy())
         got_acc.append(out["accepted"].cpu().numpy().copy())
         got_tracked.append(out["tracked_tags"].cpu().numpy().copy())
-    _JOBS[:] = [(frames_all[:, s], [dets_all[f][s] for f in range(n_frames)], cam.mtx) for s in range(n_streams)]
-    with mp.get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
-        want = pool.map(_oracle_stream, range(n_streams), chunksize=1)
-    _JOBS.clear()
+    path = str(tmp_path / "config5_frames.npy")
+    np.save(path, frames_all)
+    del frames_all
+    jobs = [(path, s, [dets_all[f][s] for f in range(n_frames)], cam.mtx) for s in range(n_streams)]
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
+        want = pool.map_async(_oracle_stream, jobs, chunksize=1).get(timeout=1200)      # a stuck worker fails the test, not the run
+    os.remove(path)
     n_checked = n_tracked = 0
     for s in range(n_streams):
         for f in range(n_frames):

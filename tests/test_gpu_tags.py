@@ -200,11 +200,16 @@ def test_stream_pipeline_from_pixels(ctx1080):
     n_streams, n_frames = 8, 8
     trajs = [synth.trajectory(8200 + s, n_frames) for s in range(n_streams)]
     bpd = BatchedPoseDetector(ctx1080, n_streams, cam.width, cam.height, OBJ)
+    whole = BatchedPoseDetector(ctx1080, n_streams, cam.width, cam.height, OBJ)
     n_acc, worst = 0, [0.0, 0.0]
     for f in range(n_frames):
         poses = np.array([trajs[s][f] for s in range(n_streams)])
         ctx1080.render(bpd.pyr[bpd.cur], poses, np.arange(n_streams) + 50 * f)
+        whole.frames.copy_(bpd.frames)
+        ref = whole.step_frames(track_window=False)                         # the whole frame searched in every step
         out = bpd.step_frames(check_ids=True)
+        assert np.array_equal(ref["accepted"].cpu().numpy(), out["accepted"].cpu().numpy())
+        assert np.abs(ref["n_tags"].cpu().numpy() - out["n_tags"].cpu().numpy()).max() <= 1        # the threshold comes from the window
         acc, pose, ntg = out["accepted"].cpu().numpy(), out["pose"].cpu().numpy(), out["n_tags"].cpu().numpy()
         assert (ntg >= 2).all()
         for s in range(n_streams):
@@ -215,3 +220,46 @@ def test_stream_pipeline_from_pixels(ctx1080):
                 assert dr < 5e-3 and dt < 1e-3, (f, s, dr, dt)       # the photometric estimate on noisy 8-bit frames, far views included
     print(f"pixels -> poses, {n_streams} streams x {n_frames} frames: {n_acc} accepted, worst {worst[0]:.2e} rad {worst[1]:.2e} m from the truth")
     assert n_acc >= n_streams * (n_frames - 1)
+
+
+def test_detect_tags_in_search_windows(ctx1080):
+    """agt_detect_tags_roi: a window around the object finds the tags the whole-frame search finds (same ids, corners within half
+    a pixel: the threshold is taken from the window), an empty rectangle means the whole frame, a window that cuts a tag drops it,
+    and agt_track_rects places the window around the predicted pose of a stream (whole frame for a stream without a pose)."""
+    cam = synth.CAMERA_1080P
+    n = 6
+    pyr, poses, frames = _render(ctx1080, cam, range(760, 760 + n))
+    t = ctx1080.torch
+    full = {k: v.cpu().numpy() for k, v in ctx1080.detect_tags(pyr).items()}
+    radius = float(np.linalg.norm(OBJ, axis=1).max())
+    state = ctx1080.new_stream_state(n)
+    st = state.cpu().numpy()
+    st[:, 0] = 1.0; st[:, 1:7] = poses                       # has_prev, prev pose (layout: csrc/agt_ape.cu)
+    st[1, 7] = 1.0; st[1, 8:14] = poses[1]                   # stream 1 also has a guess
+    st[2, 0] = 0.0                                           # stream 2 has no pose at all
+    state.copy_(t.tensor(st, device=state.device))
+    rects = ctx1080.track_rects(state, cam.width, cam.height, radius, 32)
+    r = rects.cpu().numpy()
+    assert r[2].tolist() == [0, 0, 0, 0]
+    for f in (0, 1, 3, 4, 5):
+        pts = synth.project(OBJ, poses[f], cam)
+        assert r[f, 0] <= max(pts[:, 0].min() - 30, 0) and r[f, 1] <= max(pts[:, 1].min() - 30, 0)
+        assert r[f, 2] >= min(pts[:, 0].max() + 30, cam.width) and r[f, 3] >= min(pts[:, 1].max() + 30, cam.height)
+        assert (r[f, 2] - r[f, 0]) * (r[f, 3] - r[f, 1]) < 0.25 * cam.width * cam.height
+    roi = {k: v.cpu().numpy() for k, v in ctx1080.detect_tags(pyr, rects=rects).items()}
+    for f in range(n):
+        a = {int(full["id"][f, j]): full["corners"][f, j] for j in range(full["n"][f])}
+        b = {int(roi["id"][f, j]): roi["corners"][f, j] for j in range(roi["n"][f])}
+        assert set(a) == set(b), (f, sorted(a), sorted(b))
+        for i in a:
+            assert np.abs(a[i] - b[i]).max() < 0.5, (f, i, np.abs(a[i] - b[i]).max())
+        if f == 2:
+            assert all(np.array_equal(a[i], b[i]) for i in a)                      # whole frame either way: identical
+    # a window that cuts through the object: only tags that lie entirely inside it, none invented
+    cut = r.copy()
+    cx = synth.project(np.zeros((1, 3)), poses[0], cam)[0]
+    cut[0, 2] = int(cx[0])
+    part = {k: v.cpu().numpy() for k, v in ctx1080.detect_tags(pyr, rects=cut).items()}
+    ids0 = [int(i) for i in part["id"][0, :part["n"][0]]]
+    assert set(ids0) < set(int(i) for i in full["id"][0, :full["n"][0]])
+    assert all(part["corners"][0, j, :, 0].max() < cut[0, 2] for j in range(part["n"][0]))
