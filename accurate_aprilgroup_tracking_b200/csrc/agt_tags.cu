@@ -189,22 +189,28 @@ __device__ __forceinline__ Win frame_window(const int32_t* rects, int rect_strid
   return q;
 }
 #define AGT_WIN_ARGS const int32_t* __restrict__ rects, int rect_stride
+// A warp takes 32 consecutive pixels of a window row at a time (x = 32 chunk + lane; i = y ww + x indexes the labels): no division
+// per pixel, coalesced loads, and the lanes of a warp see one horizontal run of pixels.
 #define AGT_WIN_LOOP                                                                                                   \
   const int f = blockIdx.y;                                                                                            \
   const Win win = frame_window(rects, rect_stride, f, w, h);                                                           \
-  const int n = win.ww * win.hh;                                                                                       \
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  const int lane = threadIdx.x & 31, chunks = (win.ww + 31) >> 5, items = chunks * win.hh;                              \
+  for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = item / chunks, x = (item - y * chunks) * 32 + lane, i = y * win.ww + x; \
+       item < items;                                                                                                   \
+       item += gridDim.x * (blockDim.x >> 5), y = item / chunks, x = (item - y * chunks) * 32 + lane, i = y * win.ww + x)
 
 __global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
                                     int* __restrict__ lohi) {
   const uint8_t* p = img + blockIdx.y * stride;
   int lo = 255, hi = 0;
   AGT_WIN_LOOP {
-    const int v = p[(int64_t)(win.y0 + i / win.ww) * pitch + win.x0 + i % win.ww];
-    lo = min(lo, v); hi = max(hi, v);
+    if (x < win.ww) {
+      const int v = p[(int64_t)(win.y0 + y) * pitch + win.x0 + x];
+      lo = min(lo, v); hi = max(hi, v);
+    }
   }
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * blockIdx.y], lo); atomicMax(&lohi[2 * blockIdx.y + 1], hi); }
 }
 
 __device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
@@ -212,12 +218,22 @@ __device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
   return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // a frame without contrast has no dark pixels
 }
 
+// labels start as the first pixel of the pixel's horizontal run inside its 32-pixel chunk (one ballot), so a run is already one
+// tree of depth 1 and the merge pass has to join runs, not pixels
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
                                 const int* __restrict__ lohi, int* __restrict__ label) {
   const uint8_t* p = img + blockIdx.y * stride;
   const int thr = frame_threshold(lohi, blockIdx.y);
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP L[i] = p[(int64_t)(win.y0 + i / win.ww) * pitch + win.x0 + i % win.ww] < thr ? i : -1;
+  AGT_WIN_LOOP {
+    const bool dark = x < win.ww && p[(int64_t)(win.y0 + y) * pitch + win.x0 + x] < thr;
+    const unsigned m = __ballot_sync(0xffffffffu, dark);
+    if (x < win.ww) {
+      const unsigned zeros_below = ~m & ((1u << lane) - 1u);
+      const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;           // first lane of this lane's run
+      L[i] = dark ? i - lane + run0 : -1;
+    }
+  }
 }
 
 __device__ __forceinline__ int ccl_find(const int* L, int i) {
@@ -235,41 +251,34 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
   }
 }
 
+// joins: a run with the run to its left across a chunk boundary, and a run with the run above it - once per pair of runs (at
+// the first column where both are dark), not once per pixel
 __global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
   int* L = label + (int64_t)blockIdx.y * w * h;
   AGT_WIN_LOOP {
-    if (L[i] < 0) continue;
-    const int x = i % win.ww, y = i / win.ww;
-    if (x + 1 < win.ww && L[i + 1] >= 0) ccl_union(L, i, i + 1);
-    if (y + 1 < win.hh && L[i + win.ww] >= 0) ccl_union(L, i, i + win.ww);
+    if (x >= win.ww || L[i] < 0) continue;
+    if (lane == 0 && x > 0 && L[i - 1] >= 0) ccl_union(L, i, i - 1);
+    if (y > 0 && L[i - win.ww] >= 0 && (x == 0 || L[i - 1] < 0 || L[i - win.ww - 1] < 0)) ccl_union(L, i, i - win.ww);
   }
 }
 
 __global__ void ccl_flatten_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
   int* L = label + (int64_t)blockIdx.y * w * h;
   AGT_WIN_LOOP
-    if (L[i] >= 0) L[i] = ccl_find(L, i);           // roots keep L[r] == r; concurrent shortening of other paths is harmless
+    if (x < win.ww && L[i] >= 0) L[i] = ccl_find(L, i);     // roots keep L[r] == r; concurrent shortening of other paths is harmless
 }
 
 // roots get a component number: L[root] = -2 - number (numbers beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing).
-// Two kernels, so that no pixel sees a half-renumbered root: the first one only resets the statistics records.
+// Other threads of this kernel test L[j] == j only for their own j, so overwriting L[i] here is safe.
 __global__ void ccl_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
   int* L = label + (int64_t)blockIdx.y * w * h;
   AGT_WIN_LOOP
-    if (L[i] == i) {
+    if (x < win.ww && L[i] == i) {
       const int c = atomicAdd(&n_comp[f], 1);
       if (c < MAX_COMPONENTS) {
         CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
         s.area = 0; s.x0 = win.ww; s.y0 = win.hh; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
       }
-    }
-}
-__global__ void ccl_number_store_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ counter) {
-  int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP
-    if (L[i] == i) {
-      const int c = atomicAdd(&counter[f], 1);
-      // other threads of THIS kernel test L[j] == j only for their own j: overwriting L[i] here is safe
       L[i] = c < MAX_COMPONENTS ? -2 - c : -1;
     }
 }
@@ -282,17 +291,29 @@ __device__ __forceinline__ int comp_of(const int* L, int i) {
   return r <= -2 ? -2 - r : -1;
 }
 
-// all coordinates of the statistics are window coordinates
+// all coordinates of the statistics are window coordinates.  The 32 pixels of a warp lie in one row and mostly in one component:
+// when every dark lane has the same component, the warp adds its totals with one set of atomics
 __global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats) {
   const int* L = label + (int64_t)blockIdx.y * w * h;
   AGT_WIN_LOOP {
-    const int c = comp_of(L, i);
-    if (c < 0) continue;
-    CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-    const int x = i % win.ww, y = i / win.ww;
-    atomicAdd(&s.area, 1);
-    atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
-    atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
+    const int c = x < win.ww ? comp_of(L, i) : -1;
+    const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
+    if (m == 0) continue;
+    const int lead = __ffs(m) - 1, c0 = __shfl_sync(0xffffffffu, c, lead);
+    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
+      const int cnt = __popc(m), sumx = __reduce_add_sync(0xffffffffu, c >= 0 ? x : 0);
+      if (lane == lead) {
+        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c0];
+        atomicAdd(&s.area, cnt);
+        atomicAdd(&s.sx, (unsigned long long)sumx); atomicAdd(&s.sy, (unsigned long long)y * cnt);
+        atomicMin(&s.x0, x); atomicMax(&s.x1, x - lane + 31 - __clz(m)); atomicMin(&s.y0, y); atomicMax(&s.y1, y);
+      }
+    } else if (c >= 0) {
+      CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+      atomicAdd(&s.area, 1);
+      atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
+      atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
+    }
   }
 }
 
@@ -304,9 +325,9 @@ __device__ __forceinline__ bool on_boundary(const int* L, int ww, int hh, int x,
 __global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats, int pass) {
   const int* L = label + (int64_t)blockIdx.y * w * h;
   AGT_WIN_LOOP {
+    if (x >= win.ww) continue;
     const int c = comp_of(L, i);
     if (c < 0) continue;
-    const int x = i % win.ww, y = i / win.ww;
     if (!on_boundary(L, win.ww, win.hh, x, y, i)) continue;
     CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
     if (s.area < 48) continue;
@@ -491,7 +512,6 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
   ccl_flatten_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
   ccl_number_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp, stats);
-  ccl_number_store_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp2);
   comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats);
   for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats, pass);
   quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
