@@ -189,24 +189,35 @@ __device__ __forceinline__ Win frame_window(const int32_t* rects, int rect_strid
   return q;
 }
 #define AGT_WIN_ARGS const int32_t* __restrict__ rects, int rect_stride
-// A warp takes 32 consecutive pixels of a window row at a time (x = 32 chunk + lane; i = y ww + x indexes the labels): no division
-// per pixel, coalesced loads, and the lanes of a warp see one horizontal run of pixels.
-#define AGT_WIN_LOOP                                                                                                   \
+// A warp takes 32 consecutive pixels of a window row at a time (item = row * chunks + chunk, x = 32 chunk + lane; i = y ww + x
+// indexes the labels): no division per pixel, coalesced loads, and the lanes of a warp see one horizontal run of pixels.  These
+// passes are bound by the latency of their loads, so a warp takes U consecutive items per trip and issues the loads of all of them
+// before it uses any (`base` is warp-uniform: ballots and shuffles inside the loop are safe).
+struct WinItem { int x, y, i; bool in; };
+__device__ __forceinline__ WinItem win_item(int item, int items, int chunks, int ww, int lane) {
+  WinItem r;
+  r.y = item / chunks; r.x = (item - r.y * chunks) * 32 + lane; r.i = r.y * ww + r.x; r.in = item < items && r.x < ww;
+  return r;
+}
+#define AGT_WIN_LOOP_U(U)                                                                                              \
   const int f = blockIdx.y;                                                                                            \
   const Win win = frame_window(rects, rect_stride, f, w, h);                                                           \
   const int lane = threadIdx.x & 31, chunks = (win.ww + 31) >> 5, items = chunks * win.hh;                              \
-  for (int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), y = item / chunks, x = (item - y * chunks) * 32 + lane, i = y * win.ww + x; \
-       item < items;                                                                                                   \
-       item += gridDim.x * (blockDim.x >> 5), y = item / chunks, x = (item - y * chunks) * 32 + lane, i = y * win.ww + x)
+  const int warp_step = gridDim.x * (blockDim.x >> 5) * (U);                                                           \
+  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (U); base < items; base += warp_step)
 
 __global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
                                     int* __restrict__ lohi) {
   const uint8_t* p = img + blockIdx.y * stride;
   int lo = 255, hi = 0;
-  AGT_WIN_LOOP {
-    if (x < win.ww) {
-      const int v = p[(int64_t)(win.y0 + y) * pitch + win.x0 + x];
-      lo = min(lo, v); hi = max(hi, v);
+  AGT_WIN_LOOP_U(4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const WinItem t = win_item(base + k, items, chunks, win.ww, lane);
+      if (t.in) {
+        const int v = p[(int64_t)(win.y0 + t.y) * pitch + win.x0 + t.x];
+        lo = min(lo, v); hi = max(hi, v);
+      }
     }
   }
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
@@ -225,20 +236,31 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
   const uint8_t* p = img + blockIdx.y * stride;
   const int thr = frame_threshold(lohi, blockIdx.y);
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP {
-    const bool dark = x < win.ww && p[(int64_t)(win.y0 + y) * pitch + win.x0 + x] < thr;
-    const unsigned m = __ballot_sync(0xffffffffu, dark);
-    if (x < win.ww) {
-      const unsigned zeros_below = ~m & ((1u << lane) - 1u);
-      const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;           // first lane of this lane's run
-      L[i] = dark ? i - lane + run0 : -1;
+  AGT_WIN_LOOP_U(4) {
+    WinItem t[4];
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      t[k] = win_item(base + k, items, chunks, win.ww, lane);
+      v[k] = t[k].in ? (int)p[(int64_t)(win.y0 + t[k].y) * pitch + win.x0 + t[k].x] : 256;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool dark = v[k] < thr;
+      const unsigned m = __ballot_sync(0xffffffffu, dark);
+      if (t[k].in) {
+        const unsigned zeros_below = ~m & ((1u << lane) - 1u);
+        const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;           // first lane of this lane's run
+        L[t[k].i] = dark ? t[k].i - lane + run0 : -1;
+      }
     }
   }
 }
 
+// a root is a pixel that points at itself, or - once ccl_flatten_number_kernel has been there - holds a negative component code
 __device__ __forceinline__ int ccl_find(const int* L, int i) {
   int r = i;
-  while (true) { const int p = L[r]; if (p == r) return r; r = p; }
+  while (true) { const int p = L[r]; if (p == r || p < 0) return r; r = p; }
 }
 __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
   while (true) {
@@ -252,97 +274,187 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
 }
 
 // joins: a run with the run to its left across a chunk boundary, and a run with the run above it - once per pair of runs (at
-// the first column where both are dark), not once per pixel
+// the first column where both are dark), not once per pixel.  Only the sign of a label is looked at here (dark or not: that
+// never changes), the labels of the left neighbours come from the neighbouring lane.
 __global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP {
-    if (x >= win.ww || L[i] < 0) continue;
-    if (lane == 0 && x > 0 && L[i - 1] >= 0) ccl_union(L, i, i - 1);
-    if (y > 0 && L[i - win.ww] >= 0 && (x == 0 || L[i - 1] < 0 || L[i - win.ww - 1] < 0)) ccl_union(L, i, i - win.ww);
+  AGT_WIN_LOOP_U(2) {
+    WinItem t[2];
+    int me[2], up[2], lf0[2], ul0[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      t[k] = win_item(base + k, items, chunks, win.ww, lane);
+      me[k] = t[k].in ? L[t[k].i] : -1;
+      up[k] = t[k].in && t[k].y > 0 ? L[t[k].i - win.ww] : -1;
+      const bool edge = lane == 0 && t[k].in && t[k].x > 0;
+      lf0[k] = edge ? L[t[k].i - 1] : -1;
+      ul0[k] = edge && t[k].y > 0 ? L[t[k].i - win.ww - 1] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int lf = __shfl_up_sync(0xffffffffu, me[k], 1), ul = __shfl_up_sync(0xffffffffu, up[k], 1);
+      if (lane == 0) { lf = lf0[k]; ul = ul0[k]; }
+      if (me[k] < 0) continue;
+      if (lane == 0 && lf >= 0) ccl_union(L, t[k].i, t[k].i - 1);
+      if (up[k] >= 0 && (lf < 0 || ul < 0)) ccl_union(L, t[k].i, t[k].i - win.ww);
+    }
   }
 }
 
-__global__ void ccl_flatten_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
+// every dark pixel is pointed at its root, and a root gets a component number on the spot: L[root] = -2 - number (numbers
+// beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing).  A thread that walks through a root another thread has just
+// numbered sees a negative value there and stops: ccl_find.
+__global__ void ccl_flatten_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP
-    if (x < win.ww && L[i] >= 0) L[i] = ccl_find(L, i);     // roots keep L[r] == r; concurrent shortening of other paths is harmless
-}
-
-// roots get a component number: L[root] = -2 - number (numbers beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing).
-// Other threads of this kernel test L[j] == j only for their own j, so overwriting L[i] here is safe.
-__global__ void ccl_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
-  int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP
-    if (x < win.ww && L[i] == i) {
-      const int c = atomicAdd(&n_comp[f], 1);
-      if (c < MAX_COMPONENTS) {
-        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-        s.area = 0; s.x0 = win.ww; s.y0 = win.hh; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
-      }
-      L[i] = c < MAX_COMPONENTS ? -2 - c : -1;
+  AGT_WIN_LOOP_U(2) {
+    WinItem t[2];
+    int me[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      t[k] = win_item(base + k, items, chunks, win.ww, lane);
+      me[k] = t[k].in ? L[t[k].i] : -1;
     }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (me[k] < 0) continue;
+      const int i = t[k].i;
+      if (me[k] == i) {
+        const int c = atomicAdd(&n_comp[f], 1);
+        if (c < MAX_COMPONENTS) {
+          CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+          s.area = 0; s.x0 = win.ww; s.y0 = win.hh; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
+        }
+        L[i] = c < MAX_COMPONENTS ? -2 - c : -1;
+      } else {
+        const int r = ccl_find(L, me[k]);
+        if (r != me[k]) L[i] = r;
+      }
+    }
+  }
 }
 
-__device__ __forceinline__ int comp_of(const int* L, int i) {
-  const int l = L[i];
+// before comp_stats_kernel: a root holds its code, every other dark pixel the index of its root
+__device__ __forceinline__ int comp_of(const int* L, int l) {
   if (l == -1) return -1;
   if (l <= -2) return -2 - l;                   // a root
   const int r = L[l];
   return r <= -2 ? -2 - r : -1;
 }
+// after comp_stats_kernel every pixel of a numbered component holds the code itself
+__device__ __forceinline__ int comp_code(int l) { return l <= -2 ? -2 - l : -1; }
 
 // all coordinates of the statistics are window coordinates.  The 32 pixels of a warp lie in one row and mostly in one component:
-// when every dark lane has the same component, the warp adds its totals with one set of atomics
-__global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats) {
-  const int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP {
-    const int c = x < win.ww ? comp_of(L, i) : -1;
-    const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
-    if (m == 0) continue;
-    const int lead = __ffs(m) - 1, c0 = __shfl_sync(0xffffffffu, c, lead);
-    if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
-      const int cnt = __popc(m), sumx = __reduce_add_sync(0xffffffffu, c >= 0 ? x : 0);
-      if (lane == lead) {
-        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c0];
-        atomicAdd(&s.area, cnt);
-        atomicAdd(&s.sx, (unsigned long long)sumx); atomicAdd(&s.sy, (unsigned long long)y * cnt);
-        atomicMin(&s.x0, x); atomicMax(&s.x1, x - lane + 31 - __clz(m)); atomicMin(&s.y0, y); atomicMax(&s.y1, y);
+// when every dark lane has the same component, the warp adds its totals with one set of atomics.  Every pixel is relabelled with
+// the code of its component, so that the later passes need one load per pixel (nobody else reads the label of a pixel that is
+// not a root for anything but its sign).
+__global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, CompStats* __restrict__ stats) {
+  int* L = label + (int64_t)blockIdx.y * w * h;
+  AGT_WIN_LOOP_U(2) {
+    WinItem t[2];
+    int me[2], cc[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      t[k] = win_item(base + k, items, chunks, win.ww, lane);
+      me[k] = t[k].in ? L[t[k].i] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) cc[k] = comp_of(L, me[k]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int c = cc[k], x = t[k].x, y = t[k].y;
+      const unsigned m = __ballot_sync(0xffffffffu, c >= 0);
+      if (m == 0) continue;
+      if (c >= 0 && me[k] >= 0) L[t[k].i] = -2 - c;
+      const int lead = __ffs(m) - 1, c0 = __shfl_sync(0xffffffffu, c, lead);
+      if (__all_sync(0xffffffffu, c < 0 || c == c0)) {
+        const int cnt = __popc(m), sumx = __reduce_add_sync(0xffffffffu, c >= 0 ? x : 0);
+        if (lane == lead) {
+          CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c0];
+          atomicAdd(&s.area, cnt);
+          atomicAdd(&s.sx, (unsigned long long)sumx); atomicAdd(&s.sy, (unsigned long long)y * cnt);
+          atomicMin(&s.x0, x); atomicMax(&s.x1, x - lane + 31 - __clz(m)); atomicMin(&s.y0, y); atomicMax(&s.y1, y);
+        }
+      } else if (c >= 0) {
+        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+        atomicAdd(&s.area, 1);
+        atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
+        atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
       }
-    } else if (c >= 0) {
-      CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-      atomicAdd(&s.area, 1);
-      atomicAdd(&s.sx, (unsigned long long)x); atomicAdd(&s.sy, (unsigned long long)y);
-      atomicMin(&s.x0, x); atomicMin(&s.y0, y); atomicMax(&s.x1, x); atomicMax(&s.y1, y);
     }
   }
 }
 
-__device__ __forceinline__ bool on_boundary(const int* L, int ww, int hh, int x, int y, int i) {
-  return x == 0 || y == 0 || x == ww - 1 || y == hh - 1 || L[i - 1] == -1 || L[i + 1] == -1 || L[i - ww] == -1 || L[i + ww] == -1;
+// The quadrilateral of a component comes from its boundary pixels (a dark pixel with a background pixel, or the edge of the
+// window, next to it) in three passes - 0: farthest from the centroid (c0); 1: farthest from c0 (c2); 2: farthest from the line
+// c0 c2 on each side.  Pass 0 scans the window and lists the boundary pixels of components of at least 48 pixels; passes 1 and 2
+// read that list (a few thousand entries per frame) unless it overflowed.
+constexpr int FAR_LIST_CAP = 32768;       // entries per frame
+
+__device__ __forceinline__ void far_update(CompStats& s, int pass, int x, int y, int i, int ww) {
+  if (pass == 1) {
+    const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % ww, y0 = p0 / ww;
+    atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
+  } else {
+    const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
+    const int x0 = p0 % ww, y0 = p0 / ww, x2 = p2 % ww, y2 = p2 / ww;
+    const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
+    if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
+    else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, i));
+  }
 }
 
-// pass 0: farthest boundary pixel from the centroid; pass 1: farthest from c0; pass 2: farthest from the line c0 c2 on each side
-__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats, int pass) {
+__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats, int pass,
+                                int* __restrict__ n_list, int2* __restrict__ list) {
   const int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP {
-    if (x >= win.ww) continue;
-    const int c = comp_of(L, i);
-    if (c < 0) continue;
-    if (!on_boundary(L, win.ww, win.hh, x, y, i)) continue;
-    CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-    if (s.area < 48) continue;
-    if (pass == 0) {
-      const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
-      atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
-    } else if (pass == 1) {
-      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % win.ww, y0 = p0 / win.ww;
-      atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
-    } else {
-      const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
-      const int x0 = p0 % win.ww, y0 = p0 / win.ww, x2 = p2 % win.ww, y2 = p2 / win.ww;
-      const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
-      if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
-      else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, i));
+  if (pass > 0 && n_list[blockIdx.y] <= FAR_LIST_CAP) {
+    const int n = n_list[blockIdx.y];
+    const Win win = frame_window(rects, rect_stride, blockIdx.y, w, h);
+    const int2* E = list + (int64_t)blockIdx.y * FAR_LIST_CAP;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int2 ic = E[e];
+      far_update(stats[(int64_t)blockIdx.y * MAX_COMPONENTS + ic.y], pass, ic.x % win.ww, ic.x / win.ww, ic.x, win.ww);
+    }
+    return;
+  }
+  AGT_WIN_LOOP_U(2) {
+    WinItem t[2];
+    int me[2], up[2], dn[2], lf0[2], rt0[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      t[k] = win_item(base + k, items, chunks, win.ww, lane);
+      me[k] = t[k].in ? L[t[k].i] : -1;
+      up[k] = t[k].in && t[k].y > 0 ? L[t[k].i - win.ww] : -1;
+      dn[k] = t[k].in && t[k].y < win.hh - 1 ? L[t[k].i + win.ww] : -1;
+      lf0[k] = lane == 0 && t[k].in && t[k].x > 0 ? L[t[k].i - 1] : -1;
+      rt0[k] = lane == 31 && t[k].in && t[k].x < win.ww - 1 ? L[t[k].i + 1] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int lf = __shfl_up_sync(0xffffffffu, me[k], 1), rt = __shfl_down_sync(0xffffffffu, me[k], 1);
+      if (lane == 0) lf = lf0[k];
+      if (lane == 31) rt = rt0[k];
+      const int c = comp_code(me[k]), x = t[k].x, y = t[k].y, i = t[k].i;
+      // (a neighbour outside the window reads as background: the edge of the window is a boundary)
+      bool hit = c >= 0 && (lf == -1 || rt == -1 || up[k] == -1 || dn[k] == -1);
+      CompStats* s = nullptr;
+      if (hit) {
+        s = &stats[(int64_t)f * MAX_COMPONENTS + c];
+        hit = s->area >= 48;
+      }
+      if (pass == 0) {
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0) continue;
+        int pos = 0;
+        if (lane == __ffs(m) - 1) pos = atomicAdd(&n_list[f], __popc(m));
+        pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+        if (hit) {
+          if (pos < FAR_LIST_CAP) list[(int64_t)f * FAR_LIST_CAP + pos] = make_int2(i, c);
+          const float cx = (float)((double)s->sx / s->area), cy = (float)((double)s->sy / s->area);
+          atomicMax(&s->far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
+        }
+      } else if (hit) {
+        far_update(*s, pass, x, y, i, win.ww);
+      }
     }
   }
 }
@@ -487,13 +599,14 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
                o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
                o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
                o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, o_win = o_margin + sizeof(float) * (size_t)max_quads * batch,
-               total = o_win + 4 * (size_t)max_quads * batch;
+               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, total = o_list + sizeof(int2) * (size_t)FAR_LIST_CAP * batch;
   if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
   CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
-  int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *ncomp2 = reinterpret_cast<int*>(ws + o_ncomp2),
+  int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *nlist = reinterpret_cast<int*>(ws + o_ncomp2),
       *nquads = reinterpret_cast<int*>(ws + o_nquads);
   float *quads = reinterpret_cast<float*>(ws + o_quads), *refined = reinterpret_cast<float*>(ws + o_refined);
   uint8_t* qvalid = ws + o_qvalid;
+  int2* far_list = reinterpret_cast<int2*>(ws + o_list);
   cudaStream_t st = ctx->stream;
   // lo = 255, hi = 0 per frame; counters and validity flags zero
   AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
@@ -510,10 +623,9 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
   ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label);
   ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
-  ccl_flatten_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
-  ccl_number_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp, stats);
+  ccl_flatten_number_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp, stats);
   comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats);
-  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats, pass);
+  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats, pass, nlist, far_list);
   quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
                                                                                    nquads, max_quads, refine_win);
   AGT_LAUNCH_CHECK(ctx);
