@@ -177,49 +177,92 @@ __device__ __forceinline__ unsigned long long far_key(float v, int idx) {
 }
 
 // search window of a frame: the whole frame, or the part of it inside the frame's rectangle (x0, y0, x1, y1; an empty rectangle
-// means the whole frame).  Pixel index i of a window runs row by row over the window; labels are indexed the same way.
+// means the whole frame; the left edge is moved to a multiple of 16 pixels so that rows can be read as aligned words).  Pixel
+// index i of a window runs row by row over the window; labels are indexed the same way.
 struct Win { int x0, y0, ww, hh; };
 __device__ __forceinline__ Win frame_window(const int32_t* rects, int rect_stride, int f, int w, int h) {
   Win q = {0, 0, w, h};
   if (rects != nullptr) {
     const int32_t* r = rects + (int64_t)f * rect_stride;
-    const int x0 = max(r[0], 0), y0 = max(r[1], 0), x1 = min(r[2], w), y1 = min(r[3], h);
+    const int x0 = max(r[0], 0) & ~15, y0 = max(r[1], 0), x1 = min(r[2], w), y1 = min(r[3], h);
     if (x1 > x0 && y1 > y0) { q.x0 = x0; q.y0 = y0; q.ww = x1 - x0; q.hh = y1 - y0; }
   }
   return q;
 }
 #define AGT_WIN_ARGS const int32_t* __restrict__ rects, int rect_stride
-// A warp takes 32 consecutive pixels of a window row at a time (item = row * chunks + chunk, x = 32 chunk + lane; i = y ww + x
-// indexes the labels): no division per pixel, coalesced loads, and the lanes of a warp see one horizontal run of pixels.  These
-// passes are bound by the latency of their loads, so a warp takes U consecutive items per trip and issues the loads of all of them
-// before it uses any (`base` is warp-uniform: ballots and shuffles inside the loop are safe).
-struct WinItem { int x, y, i; bool in; };
-__device__ __forceinline__ WinItem win_item(int item, int items, int chunks, int ww, int lane) {
-  WinItem r;
-  r.y = item / chunks; r.x = (item - r.y * chunks) * 32 + lane; r.i = r.y * ww + r.x; r.in = item < items && r.x < ww;
-  return r;
-}
-#define AGT_WIN_LOOP_U(U)                                                                                              \
+
+// Layout of the component passes.  A window row is cut into 32-pixel items (item = row * chunks + chunk); ccl_init_kernel
+// writes one mask word per item (bit b = pixel 32 chunk + b is dark) and appends the non-empty items (a few percent of a frame,
+// 10-15 % of a search window) to a list.  Every later pass runs a warp per list entry, lane = pixel: which neighbours are dark
+// is bit arithmetic on the mask words of the neighbouring items, labels are read and written at dark pixels only.
+#define AGT_WARP_SETUP                                                                                                 \
   const int f = blockIdx.y;                                                                                            \
   const Win win = frame_window(rects, rect_stride, f, w, h);                                                           \
-  const int lane = threadIdx.x & 31, chunks = (win.ww + 31) >> 5, items = chunks * win.hh;                              \
-  const int warp_step = gridDim.x * (blockDim.x >> 5) * (U);                                                           \
-  for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (U); base < items; base += warp_step)
+  const int lane = threadIdx.x & 31, chunks = (win.ww + 31) >> 5;                                                      \
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+struct Entry { int item, y, ch, x, i; unsigned m; bool dark; };
+__device__ __forceinline__ Entry load_entry(const int2* __restrict__ E, int e, int n, int chunks, int ww, int lane) {
+  Entry t;
+  const int2 v = e < n ? E[e] : make_int2(0, 0);
+  t.item = v.x; t.m = (unsigned)v.y;
+  t.y = t.item / chunks; t.ch = t.item - t.y * chunks; t.x = t.ch * 32 + lane; t.i = t.y * ww + t.x;
+  t.dark = (t.m >> lane) & 1u;
+  return t;
+}
+
+// four pixels of a row as one word (x counts from the left edge of the window; pixels beyond the window read as 0)
+__device__ __forceinline__ uint32_t load_px4(const uint8_t* __restrict__ row, int x, int ww, bool aligned) {
+  if (aligned) return *reinterpret_cast<const uint32_t*>(row + x);
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (x + k < ww) v |= (uint32_t)row[x + k] << (8 * k);
+  return v;
+}
 
 __global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
                                     int* __restrict__ lohi) {
   const uint8_t* p = img + blockIdx.y * stride;
-  int lo = 255, hi = 0;
-  AGT_WIN_LOOP_U(4) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
+  AGT_WARP_SETUP
+  (void)chunks;
+  const int gchunks = (win.ww + 127) >> 7, gitems = gchunks * win.hh;
+  uint32_t lo4 = 0xffffffffu, hi4 = 0u;
+  if (aligned && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (pitch & 15) == 0 && (win.x0 & 15) == 0) {
+    // sixteen pixels per lane: a warp reads 512 pixels of a row per load
+    const int wch = (win.ww + 511) >> 9, witems = wch * win.hh;
+    for (int base = warp0 * 2; base < witems; base += nwarps * 2) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const WinItem t = win_item(base + k, items, chunks, win.ww, lane);
-      if (t.in) {
-        const int v = p[(int64_t)(win.y0 + t.y) * pitch + win.x0 + t.x];
-        lo = min(lo, v); hi = max(hi, v);
+      for (int k = 0; k < 2; ++k) {
+        const int g = base + k, y = g / wch, x = (g - y * wch) * 512 + 16 * lane;
+        if (g < witems && x < win.ww) {
+          const uint4 v = *reinterpret_cast<const uint4*>(p + (int64_t)(win.y0 + y) * pitch + win.x0 + x);
+          const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int nv = min(4, win.ww - x - 4 * j);
+            if (nv <= 0) continue;
+            const uint32_t inv = nv < 4 ? 0xffffffffu << (8 * nv) : 0u;
+            lo4 = __vminu4(lo4, q[j] | inv); hi4 = __vmaxu4(hi4, q[j] & ~inv);
+          }
+        }
+      }
+    }
+  } else {
+    for (int base = warp0 * 4; base < gitems; base += nwarps * 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int g = base + k, y = g / gchunks, x = (g - y * gchunks) * 128 + 4 * lane;
+        if (g < gitems && x < win.ww) {
+          const uint32_t v = load_px4(p + (int64_t)(win.y0 + y) * pitch + win.x0, x, win.ww, aligned);
+          const int nv = min(4, win.ww - x);
+          const uint32_t inv = nv < 4 ? 0xffffffffu << (8 * nv) : 0u;
+          lo4 = __vminu4(lo4, v | inv); hi4 = __vmaxu4(hi4, v & ~inv);
+        }
       }
     }
   }
+  int lo = min(min(lo4 & 0xff, (lo4 >> 8) & 0xff), min((lo4 >> 16) & 0xff, lo4 >> 24));
+  int hi = max(max(hi4 & 0xff, (hi4 >> 8) & 0xff), max((hi4 >> 16) & 0xff, hi4 >> 24));
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
   if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * blockIdx.y], lo); atomicMax(&lohi[2 * blockIdx.y + 1], hi); }
 }
@@ -229,30 +272,60 @@ __device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
   return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // a frame without contrast has no dark pixels
 }
 
-// labels start as the first pixel of the pixel's horizontal run inside its 32-pixel chunk (one ballot), so a run is already one
-// tree of depth 1 and the merge pass has to join runs, not pixels
+// Threshold, mask words, list of non-empty items, first labels.  A warp reads 128 pixels of a row (four per lane); the eight
+// lanes of an item put their dark bits together.  A dark pixel's label starts as the first pixel of its horizontal run inside
+// the item, so a run is already one tree of depth 1 and the merge pass has to join runs, not pixels.
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
-                                const int* __restrict__ lohi, int* __restrict__ label) {
+                                const int* __restrict__ lohi, int* __restrict__ label, uint32_t* __restrict__ mask, int64_t mask_stride,
+                                int* __restrict__ n_entries, int2* __restrict__ entries, int* __restrict__ entry_of) {
   const uint8_t* p = img + blockIdx.y * stride;
+  const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
   const int thr = frame_threshold(lohi, blockIdx.y);
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP_U(4) {
-    WinItem t[4];
-    int v[4];
+  uint32_t* M = mask + blockIdx.y * mask_stride;
+  int2* E = entries + blockIdx.y * mask_stride;
+  int* P = entry_of + blockIdx.y * mask_stride;        // position of a non-empty item in the list
+  AGT_WARP_SETUP
+  const int gchunks = (win.ww + 127) >> 7, gitems = gchunks * win.hh;
+  const int sub = lane & 7, q = lane >> 3;
+  for (int base = warp0 * 2; base < gitems; base += nwarps * 2) {
+    uint32_t v[2];
+    int yy[2], gc[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      t[k] = win_item(base + k, items, chunks, win.ww, lane);
-      v[k] = t[k].in ? (int)p[(int64_t)(win.y0 + t[k].y) * pitch + win.x0 + t[k].x] : 256;
+    for (int k = 0; k < 2; ++k) {
+      const int g = base + k;
+      yy[k] = g / gchunks; gc[k] = g - yy[k] * gchunks;
+      const int x = gc[k] * 128 + 4 * lane;
+      v[k] = g < gitems && x < win.ww ? load_px4(p + (int64_t)(win.y0 + yy[k]) * pitch + win.x0, x, win.ww, aligned) : 0xffffffffu;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool dark = v[k] < thr;
-      const unsigned m = __ballot_sync(0xffffffffu, dark);
-      if (t[k].in) {
-        const unsigned zeros_below = ~m & ((1u << lane) - 1u);
-        const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;           // first lane of this lane's run
-        L[t[k].i] = dark ? t[k].i - lane + run0 : -1;
+    for (int k = 0; k < 2; ++k) {
+      const int x = gc[k] * 128 + 4 * lane;
+      unsigned nib = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) nib |= (x + b < win.ww && (int)((v[k] >> (8 * b)) & 0xffu) < thr) ? 1u << b : 0u;
+      if (base + k >= gitems) nib = 0;
+      unsigned m = nib << (4 * sub);
+      m |= __shfl_xor_sync(0xffffffffu, m, 1); m |= __shfl_xor_sync(0xffffffffu, m, 2); m |= __shfl_xor_sync(0xffffffffu, m, 4);
+      const int ch = gc[k] * 4 + q;
+      if (base + k >= gitems || ch >= chunks) continue;
+      const int item = yy[k] * chunks + ch;
+      if (sub == 0) {
+        M[item] = m;
+        if (m != 0) {
+          const int pos = atomicAdd(&n_entries[f], 1);
+          E[pos] = make_int2(item, (int)m);
+          P[item] = pos;
+        }
       }
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (nib >> b & 1u) {
+          const int bit = 4 * sub + b;
+          const unsigned zeros_below = ~m & ((1u << bit) - 1u);
+          const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;         // first pixel of this pixel's run
+          L[yy[k] * win.ww + ch * 32 + bit] = yy[k] * win.ww + ch * 32 + run0;
+        }
     }
   }
 }
@@ -273,30 +346,200 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
   }
 }
 
-// joins: a run with the run to its left across a chunk boundary, and a run with the run above it - once per pair of runs (at
-// the first column where both are dark), not once per pixel.  Only the sign of a label is looked at here (dark or not: that
-// never changes), the labels of the left neighbours come from the neighbouring lane.
-__global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label) {
+// Components of a frame in one CTA, in shared memory.  The unit is a run: a maximal row of dark pixels inside one item (a few
+// hundred to a few thousand per search window).  Runs are numbered by a prefix sum over the list entries, joined - with the run
+// left of them in the neighbouring item, with the runs above them - by union-find on a table in shared memory (the chains a tall
+// component builds are walked at shared-memory latency: the same walk through global memory was three quarters of the
+// detector's component time), roots get their component number, and every dark pixel is written once, with the final code of
+// its component.  A frame with more entries or runs than the tables hold is flagged and goes through ccl_merge_kernel and
+// ccl_flatten_number_kernel instead (which return at once for every other frame).
+constexpr int RUNS_THREADS = 512, RUNS_ENT_CAP = 8 * RUNS_THREADS, RUNS_RUN_CAP = 12 * RUNS_THREADS;
+
+// find with path halving: every node on the way is pointed at its grandparent.  Safe next to concurrent unions - a node that is
+// not a root never becomes one again and is written by nobody but such walks, and any ancestor is a valid parent.
+__device__ __forceinline__ int run_find(int* parent, int i) {
+  int r = i, p = parent[r];
+  while (p != r) {
+    const int g = parent[p];
+    if (g != p) parent[r] = g;
+    r = p; p = g;
+  }
+  return r;
+}
+__device__ __forceinline__ void run_union(int* parent, int a, int b) {
+  while (true) {
+    a = run_find(parent, a); b = run_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(&parent[a], b);
+    if (old == a) return;
+    a = old;
+  }
+}
+// index, inside its item, of the run that holds bit b (starts = the first bits of the item's runs)
+__device__ __forceinline__ int run_index(unsigned starts, int b) { return __popc(starts & ((2u << b) - 1u)) - 1; }
+
+__global__ void __launch_bounds__(RUNS_THREADS, 1)
+ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint32_t* __restrict__ mask, int64_t mask_stride,
+                const int* __restrict__ n_entries, const int2* __restrict__ entries, const int* __restrict__ entry_of, int* __restrict__ n_comp,
+                CompStats* __restrict__ stats, uint8_t* __restrict__ overflow) {
+  __shared__ int s_parent[RUNS_RUN_CAP];
+  __shared__ int s_base[RUNS_ENT_CAP];
+  __shared__ int s_warp[RUNS_THREADS / 32];
+  __shared__ int s_total;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const Win win = frame_window(rects, rect_stride, f, w, h);
+  const int chunks = (win.ww + 31) >> 5;
+  int* L = label + (int64_t)f * w * h;
+  const uint32_t* M = mask + f * mask_stride;
+  const int2* E = entries + f * mask_stride;
+  const int* P = entry_of + f * mask_stride;
+  const int n = n_entries[f];
+  if (n > RUNS_ENT_CAP) { if (tid == 0) overflow[f] = 1; return; }
+  // ---- runs per entry, exclusive prefix sum (eight consecutive entries per thread)
+  int cnt[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = tid * 8 + k;
+    const unsigned m = e < n ? (unsigned)E[e].y : 0u;
+    cnt[k] = __popc(m & ~(m << 1));
+    sum += cnt[k];
+  }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = lane < RUNS_THREADS / 32 ? s_warp[lane] : 0, iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    if (lane < RUNS_THREADS / 32) s_warp[lane] = iv - v;
+    if (lane == RUNS_THREADS / 32 - 1) s_total = iv;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (total > RUNS_RUN_CAP) { if (tid == 0) overflow[f] = 1; return; }
+  {
+    int run = s_warp[wid] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s_base[tid * 8 + k] = run; run += cnt[k]; }
+  }
+  for (int r = tid; r < total; r += RUNS_THREADS) s_parent[r] = r;
+  __syncthreads();
+  // ---- joins, a thread per entry
+  for (int e = tid; e < n; e += RUNS_THREADS) {
+    const int2 v = E[e];
+    const int item = v.x, y = item / chunks, ch = item - y * chunks;
+    const unsigned m = (unsigned)v.y;
+    const unsigned up = y > 0 ? M[item - chunks] : 0u, lw = ch > 0 ? M[item - 1] : 0u, ulw = ch > 0 && y > 0 ? M[item - chunks - 1] : 0u;
+    const unsigned starts = m & ~(m << 1), base = (unsigned)s_base[e];
+    if ((m & 1u) && (lw >> 31)) {
+      const int pl = P[item - 1];
+      run_union(s_parent, (int)base, s_base[pl] + __popc(lw & ~(lw << 1)) - 1);          // the last run of the item on the left
+    }
+    unsigned join = m & up & ~(((m << 1) | (lw >> 31)) & ((up << 1) | (ulw >> 31)));      // first column where a run meets a run above
+    if (join) {
+      const int ub = s_base[P[item - chunks]];
+      const unsigned ustarts = up & ~(up << 1);
+      while (join) {
+        const int b = __ffs(join) - 1;
+        join &= join - 1;
+        run_union(s_parent, (int)base + run_index(starts, b), ub + run_index(ustarts, b));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- roots, component numbers, codes
+  int root[RUNS_RUN_CAP / RUNS_THREADS];
+#pragma unroll
+  for (int k = 0; k < RUNS_RUN_CAP / RUNS_THREADS; ++k) {
+    const int r = tid + k * RUNS_THREADS;
+    root[k] = r < total ? run_find(s_parent, r) : -1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RUNS_RUN_CAP / RUNS_THREADS; ++k) {
+    const int r = tid + k * RUNS_THREADS;
+    if (r < total && root[k] == r) {
+      const int c = atomicAdd(&n_comp[f], 1);
+      if (c < MAX_COMPONENTS) {
+        CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+        s.area = 0; s.x0 = win.ww; s.y0 = win.hh; s.x1 = -1; s.y1 = -1; s.sx = 0; s.sy = 0; s.far0 = 0; s.far2 = 0; s.side_p = 0; s.side_n = 0;
+      }
+      s_parent[r] = c < MAX_COMPONENTS ? -2 - c : -1;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RUNS_RUN_CAP / RUNS_THREADS; ++k) {
+    const int r = tid + k * RUNS_THREADS;
+    if (r < total && root[k] != r) s_parent[r] = s_parent[root[k]];
+  }
+  __syncthreads();
+  // ---- statistics of the components, a thread per entry: a run adds its length, its coordinate sums and its extent
+  for (int e = tid; e < n; e += RUNS_THREADS) {
+    const int2 v = E[e];
+    const int y = v.x / chunks, xb = (v.x - y * chunks) * 32;
+    unsigned mm = (unsigned)v.y;
+    int r = s_base[e];
+    while (mm) {
+      const int a = __ffs(mm) - 1;
+      const unsigned t = mm >> a;
+      const int len = t == 0xffffffffu ? 32 : __ffs(~t) - 1;
+      mm &= ~((len == 32 ? 0xffffffffu : (1u << len) - 1u) << a);
+      const int code = s_parent[r++];
+      if (code <= -2) {
+        CompStats& st = stats[(int64_t)f * MAX_COMPONENTS + (-2 - code)];
+        const int xa = xb + a;
+        atomicAdd(&st.area, len);
+        atomicAdd(&st.sx, (unsigned long long)(len * xa + len * (len - 1) / 2)); atomicAdd(&st.sy, (unsigned long long)y * len);
+        atomicMin(&st.x0, xa); atomicMax(&st.x1, xa + len - 1); atomicMin(&st.y0, y); atomicMax(&st.y1, y);
+      }
+    }
+  }
+  // ---- every dark pixel gets the code of its component: a warp fetches 32 entries at once and goes through them
+  for (int e0 = wid * 32; e0 < n; e0 += RUNS_THREADS) {
+    const int2 mine = e0 + lane < n ? E[e0 + lane] : make_int2(0, 0);
+    const int my_base = e0 + lane < n ? s_base[e0 + lane] : 0;
+    const int cnt = min(32, n - e0);
+    for (int j = 0; j < cnt; ++j) {
+      const int item = __shfl_sync(0xffffffffu, mine.x, j), base = __shfl_sync(0xffffffffu, my_base, j);
+      const unsigned m = (unsigned)__shfl_sync(0xffffffffu, mine.y, j);
+      if (m >> lane & 1u) {
+        const int y = item / chunks, ch = item - y * chunks;
+        L[y * win.ww + ch * 32 + lane] = s_parent[base + run_index(m & ~(m << 1), lane)];
+      }
+    }
+  }
+}
+
+// joins: a run with the run to its left across an item boundary, and a run with the run above it - once per pair of runs (at
+// the first column where both are dark), not once per pixel
+__global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                 const int* __restrict__ n_entries, const int2* __restrict__ entries, const uint8_t* __restrict__ overflow) {
+  if (!overflow[blockIdx.y]) return;
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP_U(2) {
-    WinItem t[2];
-    int me[2], up[2], lf0[2], ul0[2];
+  const uint32_t* M = mask + blockIdx.y * mask_stride;
+  const int2* E = entries + blockIdx.y * mask_stride;
+  AGT_WARP_SETUP
+  const int n = n_entries[f];
+  for (int e = warp0 * 2; e < n; e += nwarps * 2) {
+    Entry t[2];
+    unsigned up[2], lw[2], ulw[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      t[k] = win_item(base + k, items, chunks, win.ww, lane);
-      me[k] = t[k].in ? L[t[k].i] : -1;
-      up[k] = t[k].in && t[k].y > 0 ? L[t[k].i - win.ww] : -1;
-      const bool edge = lane == 0 && t[k].in && t[k].x > 0;
-      lf0[k] = edge ? L[t[k].i - 1] : -1;
-      ul0[k] = edge && t[k].y > 0 ? L[t[k].i - win.ww - 1] : -1;
+      t[k] = load_entry(E, e + k, n, chunks, win.ww, lane);
+      up[k] = t[k].y > 0 ? M[t[k].item - chunks] : 0u;
+      lw[k] = t[k].ch > 0 ? M[t[k].item - 1] : 0u;
+      ulw[k] = t[k].ch > 0 && t[k].y > 0 ? M[t[k].item - chunks - 1] : 0u;
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      int lf = __shfl_up_sync(0xffffffffu, me[k], 1), ul = __shfl_up_sync(0xffffffffu, up[k], 1);
-      if (lane == 0) { lf = lf0[k]; ul = ul0[k]; }
-      if (me[k] < 0) continue;
-      if (lane == 0 && lf >= 0) ccl_union(L, t[k].i, t[k].i - 1);
-      if (up[k] >= 0 && (lf < 0 || ul < 0)) ccl_union(L, t[k].i, t[k].i - win.ww);
+      const unsigned m = t[k].m, left_m = (m << 1) | (lw[k] >> 31), left_u = (up[k] << 1) | (ulw[k] >> 31);
+      const unsigned join_up = m & up[k] & ~(left_m & left_u);
+      if (lane == 0 && (m & 1u) && (lw[k] >> 31)) ccl_union(L, t[k].i, t[k].i - 1);
+      if (join_up >> lane & 1u) ccl_union(L, t[k].i, t[k].i - win.ww);
     }
   }
 }
@@ -304,15 +547,21 @@ __global__ void ccl_merge_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ l
 // every dark pixel is pointed at its root, and a root gets a component number on the spot: L[root] = -2 - number (numbers
 // beyond MAX_COMPONENTS are dropped: L[root] = -1 marks nothing).  A thread that walks through a root another thread has just
 // numbered sees a negative value there and stops: ccl_find.
-__global__ void ccl_flatten_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, int* __restrict__ n_comp, CompStats* __restrict__ stats) {
+__global__ void ccl_flatten_number_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const int* __restrict__ n_entries,
+                                          const int2* __restrict__ entries, int64_t mask_stride, int* __restrict__ n_comp, CompStats* __restrict__ stats,
+                                          const uint8_t* __restrict__ overflow) {
+  if (!overflow[blockIdx.y]) return;
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP_U(2) {
-    WinItem t[2];
+  const int2* E = entries + blockIdx.y * mask_stride;
+  AGT_WARP_SETUP
+  const int n = n_entries[f];
+  for (int e = warp0 * 2; e < n; e += nwarps * 2) {
+    Entry t[2];
     int me[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      t[k] = win_item(base + k, items, chunks, win.ww, lane);
-      me[k] = t[k].in ? L[t[k].i] : -1;
+      t[k] = load_entry(E, e + k, n, chunks, win.ww, lane);
+      me[k] = t[k].dark ? L[t[k].i] : -1;
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -346,16 +595,22 @@ __device__ __forceinline__ int comp_code(int l) { return l <= -2 ? -2 - l : -1; 
 // all coordinates of the statistics are window coordinates.  The 32 pixels of a warp lie in one row and mostly in one component:
 // when every dark lane has the same component, the warp adds its totals with one set of atomics.  Every pixel is relabelled with
 // the code of its component, so that the later passes need one load per pixel (nobody else reads the label of a pixel that is
-// not a root for anything but its sign).
-__global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, CompStats* __restrict__ stats) {
+// not a root).
+__global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const int* __restrict__ n_entries,
+                                  const int2* __restrict__ entries, int64_t mask_stride, CompStats* __restrict__ stats,
+                                  const uint8_t* __restrict__ overflow) {
+  if (!overflow[blockIdx.y]) return;                   // ccl_runs_kernel has added up the runs already
   int* L = label + (int64_t)blockIdx.y * w * h;
-  AGT_WIN_LOOP_U(2) {
-    WinItem t[2];
+  const int2* E = entries + blockIdx.y * mask_stride;
+  AGT_WARP_SETUP
+  const int n = n_entries[f];
+  for (int e = warp0 * 2; e < n; e += nwarps * 2) {
+    Entry t[2];
     int me[2], cc[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      t[k] = win_item(base + k, items, chunks, win.ww, lane);
-      me[k] = t[k].in ? L[t[k].i] : -1;
+      t[k] = load_entry(E, e + k, n, chunks, win.ww, lane);
+      me[k] = t[k].dark ? L[t[k].i] : -1;
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) cc[k] = comp_of(L, me[k]);
@@ -386,75 +641,57 @@ __global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ 
 
 // The quadrilateral of a component comes from its boundary pixels (a dark pixel with a background pixel, or the edge of the
 // window, next to it) in three passes - 0: farthest from the centroid (c0); 1: farthest from c0 (c2); 2: farthest from the line
-// c0 c2 on each side.  Pass 0 scans the window and lists the boundary pixels of components of at least 48 pixels; passes 1 and 2
-// read that list (a few thousand entries per frame) unless it overflowed.
-constexpr int FAR_LIST_CAP = 32768;       // entries per frame
-
-__device__ __forceinline__ void far_update(CompStats& s, int pass, int x, int y, int i, int ww) {
-  if (pass == 1) {
-    const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % ww, y0 = p0 / ww;
-    atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
-  } else {
-    const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
-    const int x0 = p0 % ww, y0 = p0 / ww, x2 = p2 % ww, y2 = p2 / ww;
-    const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
-    if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
-    else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, i));
+// c0 c2 on each side.  boundary_list_kernel (a thread per entry, mask arithmetic only) lists the boundary pixels of a frame;
+// the three passes run a thread per listed pixel.
+__global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                     const int* __restrict__ n_entries, const int2* __restrict__ entries, int* __restrict__ n_list, int* __restrict__ list) {
+  const int f = blockIdx.y;
+  const Win win = frame_window(rects, rect_stride, f, w, h);
+  const int chunks = (win.ww + 31) >> 5, n = n_entries[f];
+  const uint32_t* M = mask + f * mask_stride;
+  const int2* E = entries + f * mask_stride;
+  int* P = list + (int64_t)f * w * h;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int2 v = E[e];
+    const int item = v.x, y = item / chunks, ch = item - y * chunks;
+    const unsigned m = (unsigned)v.y;
+    const unsigned up = y > 0 ? M[item - chunks] : 0u, dn = y < win.hh - 1 ? M[item + chunks] : 0u;
+    const unsigned lw = ch > 0 ? M[item - 1] : 0u, rw = ch < chunks - 1 ? M[item + 1] : 0u;
+    // (a neighbour outside the window reads as background: the edge of the window is a boundary)
+    unsigned bm = m & ~(((m << 1) | (lw >> 31)) & ((m >> 1) | (rw << 31)) & up & dn);
+    if (bm == 0) continue;
+    int pos = atomicAdd(&n_list[f], __popc(bm));
+    const int i0 = y * win.ww + ch * 32;
+    while (bm) { P[pos++] = i0 + __ffs(bm) - 1; bm &= bm - 1; }
   }
 }
 
-__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, CompStats* __restrict__ stats, int pass,
-                                int* __restrict__ n_list, int2* __restrict__ list) {
-  const int* L = label + (int64_t)blockIdx.y * w * h;
-  if (pass > 0 && n_list[blockIdx.y] <= FAR_LIST_CAP) {
-    const int n = n_list[blockIdx.y];
-    const Win win = frame_window(rects, rect_stride, blockIdx.y, w, h);
-    const int2* E = list + (int64_t)blockIdx.y * FAR_LIST_CAP;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-      const int2 ic = E[e];
-      far_update(stats[(int64_t)blockIdx.y * MAX_COMPONENTS + ic.y], pass, ic.x % win.ww, ic.x / win.ww, ic.x, win.ww);
-    }
-    return;
-  }
-  AGT_WIN_LOOP_U(2) {
-    WinItem t[2];
-    int me[2], up[2], dn[2], lf0[2], rt0[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      t[k] = win_item(base + k, items, chunks, win.ww, lane);
-      me[k] = t[k].in ? L[t[k].i] : -1;
-      up[k] = t[k].in && t[k].y > 0 ? L[t[k].i - win.ww] : -1;
-      dn[k] = t[k].in && t[k].y < win.hh - 1 ? L[t[k].i + win.ww] : -1;
-      lf0[k] = lane == 0 && t[k].in && t[k].x > 0 ? L[t[k].i - 1] : -1;
-      rt0[k] = lane == 31 && t[k].in && t[k].x < win.ww - 1 ? L[t[k].i + 1] : -1;
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      int lf = __shfl_up_sync(0xffffffffu, me[k], 1), rt = __shfl_down_sync(0xffffffffu, me[k], 1);
-      if (lane == 0) lf = lf0[k];
-      if (lane == 31) rt = rt0[k];
-      const int c = comp_code(me[k]), x = t[k].x, y = t[k].y, i = t[k].i;
-      // (a neighbour outside the window reads as background: the edge of the window is a boundary)
-      bool hit = c >= 0 && (lf == -1 || rt == -1 || up[k] == -1 || dn[k] == -1);
-      CompStats* s = nullptr;
-      if (hit) {
-        s = &stats[(int64_t)f * MAX_COMPONENTS + c];
-        hit = s->area >= 48;
-      }
-      if (pass == 0) {
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (m == 0) continue;
-        int pos = 0;
-        if (lane == __ffs(m) - 1) pos = atomicAdd(&n_list[f], __popc(m));
-        pos = __shfl_sync(0xffffffffu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
-        if (hit) {
-          if (pos < FAR_LIST_CAP) list[(int64_t)f * FAR_LIST_CAP + pos] = make_int2(i, c);
-          const float cx = (float)((double)s->sx / s->area), cy = (float)((double)s->sy / s->area);
-          atomicMax(&s->far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
-        }
-      } else if (hit) {
-        far_update(*s, pass, x, y, i, win.ww);
-      }
+__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, const int* __restrict__ n_list,
+                                const int* __restrict__ list, CompStats* __restrict__ stats, int pass) {
+  const int f = blockIdx.y;
+  const Win win = frame_window(rects, rect_stride, f, w, h);
+  const int* L = label + (int64_t)f * w * h;
+  const int* P = list + (int64_t)f * w * h;
+  const int n = n_list[f], ww = win.ww;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int i = P[e], c = comp_code(L[i]);
+    if (c < 0) continue;
+    CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
+    const int area = s.area;
+    if (area < 48) continue;
+    const int y = i / ww, x = i - y * ww;
+    if (pass == 0) {
+      const float cx = (float)((double)s.sx / area), cy = (float)((double)s.sy / area);
+      atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
+    } else if (pass == 1) {
+      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % ww, y0 = p0 / ww;
+      atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
+    } else {
+      const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
+      const int x0 = p0 % ww, y0 = p0 / ww, x2 = p2 % ww, y2 = p2 / ww;
+      const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
+      if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
+      else if (d < 0.f) atomicMax(&s.side_n, far_key(-d, i));
     }
   }
 }
@@ -588,25 +825,31 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
       max_tags > 1024 || (int64_t)w * h > 0x7fffffffLL || refine_win < 0 || refine_win > 7)
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_detect_tags: bad arguments");
   const int max_quads = 4 * max_tags < 64 ? 64 : 4 * max_tags;
-  const int64_t n = (int64_t)w * h;
+  const int64_t n = (int64_t)w * h, mask_stride = (int64_t)((w + 31) / 32) * h;
   int* label;
   uint8_t* ws;
   int rc;
   if ((rc = agt_scratch(ctx, 0, sizeof(int) * (size_t)n * batch, reinterpret_cast<void**>(&label)))) return rc;
   const size_t o_stats = 0, o_lohi = o_stats + sizeof(CompStats) * (size_t)MAX_COMPONENTS * batch, o_ncomp = o_lohi + sizeof(int) * 2 * batch,
-               o_ncomp2 = o_ncomp + sizeof(int) * batch, o_nquads = o_ncomp2 + sizeof(int) * batch,
+               o_nlist = o_ncomp + sizeof(int) * batch, o_nent = o_nlist + sizeof(int) * batch, o_over = o_nent + sizeof(int) * batch, o_nquads = (o_over + (size_t)batch + 3) & ~(size_t)3,
                o_quads = (o_nquads + sizeof(int) * batch + 63) & ~(size_t)63, o_refined = o_quads + sizeof(float) * 8 * (size_t)max_quads * batch,
                o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
                o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
                o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, o_win = o_margin + sizeof(float) * (size_t)max_quads * batch,
-               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, total = o_list + sizeof(int2) * (size_t)FAR_LIST_CAP * batch;
+               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int) * (size_t)n * batch,
+               o_ent = (o_mask + sizeof(uint32_t) * (size_t)mask_stride * batch + 63) & ~(size_t)63, o_pos = o_ent + sizeof(int2) * (size_t)mask_stride * batch,
+               total = o_pos + sizeof(int) * (size_t)mask_stride * batch;
   if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
   CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
-  int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *nlist = reinterpret_cast<int*>(ws + o_ncomp2),
+  int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *nlist = reinterpret_cast<int*>(ws + o_nlist), *nent = reinterpret_cast<int*>(ws + o_nent),
       *nquads = reinterpret_cast<int*>(ws + o_nquads);
   float *quads = reinterpret_cast<float*>(ws + o_quads), *refined = reinterpret_cast<float*>(ws + o_refined);
   uint8_t* qvalid = ws + o_qvalid;
-  int2* far_list = reinterpret_cast<int2*>(ws + o_list);
+  int* far_list = reinterpret_cast<int*>(ws + o_list);
+  int2* entries = reinterpret_cast<int2*>(ws + o_ent);
+  uint32_t* mask = reinterpret_cast<uint32_t*>(ws + o_mask);
+  int* entry_of = reinterpret_cast<int*>(ws + o_pos);
+  uint8_t* overflow = ws + o_over;
   cudaStream_t st = ctx->stream;
   // lo = 255, hi = 0 per frame; counters and validity flags zero
   AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
@@ -620,12 +863,17 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   // grid-stride over the pixels of each frame's window; with windows (usually a few percent of the frame) a smaller grid per frame
   const int64_t per_frame = d_rects ? std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch) : 1184;
   const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, per_frame), (unsigned)batch);
+  // the passes over the list of non-empty items / boundary pixels: sized for the dark part of a frame, whatever the window
+  const dim3 grid_ne((unsigned)std::min<int64_t>((n + 255) / 256, std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch)), (unsigned)batch);
   frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
-  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label);
-  ccl_merge_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label);
-  ccl_flatten_number_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, ncomp, stats);
-  comp_stats_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats);
-  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid, 256, 0, st>>>(w, h, d_rects, rect_stride, label, stats, pass, nlist, far_list);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label, mask, mask_stride, nent, entries, entry_of);
+  ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
+                                                           overflow);
+  ccl_merge_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow);
+  ccl_flatten_number_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, ncomp, stats, overflow);
+  comp_stats_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, stats, overflow);
+  boundary_list_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, mask, mask_stride, nent, entries, nlist, far_list);
+  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nlist, far_list, stats, pass);
   quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
                                                                                    nquads, max_quads, refine_win);
   AGT_LAUNCH_CHECK(ctx);

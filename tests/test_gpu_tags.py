@@ -263,3 +263,31 @@ def test_detect_tags_in_search_windows(ctx1080):
     ids0 = [int(i) for i in part["id"][0, :part["n"][0]]]
     assert set(ids0) < set(int(i) for i in full["id"][0, :full["n"][0]])
     assert all(part["corners"][0, j, :, 0].max() < cut[0, 2] for j in range(part["n"][0]))
+
+
+def test_detect_tags_cluttered_frame_takes_the_global_memory_path(ctx1080):
+    """A frame with more dark runs than the shared-memory tables of ccl_runs_kernel hold (here: two thousand dark bars around the
+    object, > 20 000 non-empty 32-pixel items) is labelled by the global-memory union-find instead.  The bars are components of
+    their own, darkest / brightest pixel are unchanged, so the tags and their corners must come out exactly as on the clean frame."""
+    cam = synth.CAMERA_1080P
+    pyr, poses, frames = _render(ctx1080, cam, [700, 701, 702])
+    clean = {k: v.cpu().numpy() for k, v in ctx1080.detect_tags(pyr).items()}
+    cluttered = frames.copy()
+    yy, xx = np.mgrid[0:cam.height, 0:cam.width]
+    bars = ((yy % 16) < 6) & ((xx % 64) < 40)
+    for f in range(len(frames)):
+        pts = synth.project(OBJ, poses[f], cam)
+        c, r = pts.mean(axis=0), np.abs(pts - pts.mean(axis=0)).max() + 80
+        away = (np.abs(xx - c[0]) > r) | (np.abs(yy - c[1]) > r)
+        cluttered[f][bars & away] = frames[f].min()
+        items = (cluttered[f] < int(frames[f].min()) + 0.35 * (int(frames[f].max()) - int(frames[f].min()))).reshape(cam.height, -1, 32).any(axis=2)
+        assert items.sum() > 20000
+    p2 = ctx1080.alloc_pyramid(len(frames), cam.width, cam.height, 1)
+    ctx1080.upload_frames(p2, cluttered)
+    out = {k: v.cpu().numpy() for k, v in ctx1080.detect_tags(p2).items()}
+    assert clean["n"].min() >= 3
+    for f in range(len(frames)):
+        a = {int(clean["id"][f, j]): clean["corners"][f, j] for j in range(clean["n"][f])}
+        b = {int(out["id"][f, j]): out["corners"][f, j] for j in range(out["n"][f])}
+        assert set(a) == set(b), (f, sorted(a), sorted(b))
+        assert all(np.array_equal(a[i], b[i]) for i in a), f
