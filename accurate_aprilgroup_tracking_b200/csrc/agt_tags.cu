@@ -350,9 +350,10 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
 // hundred to a few thousand per search window).  Runs are numbered by a prefix sum over the list entries, joined - with the run
 // left of them in the neighbouring item, with the runs above them - by union-find on a table in shared memory (the chains a tall
 // component builds are walked at shared-memory latency: the same walk through global memory was three quarters of the
-// detector's component time), roots get their component number, and every dark pixel is written once, with the final code of
-// its component.  A frame with more entries or runs than the tables hold is flagged and goes through ccl_merge_kernel and
-// ccl_flatten_number_kernel instead (which return at once for every other frame).
+// detector's component time) and roots get their component number.  What leaves the kernel is the component code of every run:
+// no pixel label is written or read on this path.  A frame with more entries or runs than the tables hold is flagged and goes
+// through ccl_merge_kernel, ccl_flatten_number_kernel and comp_stats_kernel instead (which return at once for every other
+// frame) and carries its codes in the pixel labels.
 constexpr int RUNS_THREADS = 512, RUNS_ENT_CAP = 8 * RUNS_THREADS, RUNS_RUN_CAP = 12 * RUNS_THREADS;
 
 // find with path halving: every node on the way is pointed at its grandparent.  Safe next to concurrent unions - a node that is
@@ -382,7 +383,7 @@ __device__ __forceinline__ int run_index(unsigned starts, int b) { return __popc
 __global__ void __launch_bounds__(RUNS_THREADS, 1)
 ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint32_t* __restrict__ mask, int64_t mask_stride,
                 const int* __restrict__ n_entries, const int2* __restrict__ entries, const int* __restrict__ entry_of, int* __restrict__ n_comp,
-                CompStats* __restrict__ stats, uint8_t* __restrict__ overflow) {
+                CompStats* __restrict__ stats, uint8_t* __restrict__ overflow, int* __restrict__ run_code, int* __restrict__ ent_base) {
   __shared__ int s_parent[RUNS_RUN_CAP];
   __shared__ int s_base[RUNS_ENT_CAP];
   __shared__ int s_warp[RUNS_THREADS / 32];
@@ -477,41 +478,9 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint3
     if (r < total && root[k] != r) s_parent[r] = s_parent[root[k]];
   }
   __syncthreads();
-  // ---- statistics of the components, a thread per entry: a run adds its length, its coordinate sums and its extent
-  for (int e = tid; e < n; e += RUNS_THREADS) {
-    const int2 v = E[e];
-    const int y = v.x / chunks, xb = (v.x - y * chunks) * 32;
-    unsigned mm = (unsigned)v.y;
-    int r = s_base[e];
-    while (mm) {
-      const int a = __ffs(mm) - 1;
-      const unsigned t = mm >> a;
-      const int len = t == 0xffffffffu ? 32 : __ffs(~t) - 1;
-      mm &= ~((len == 32 ? 0xffffffffu : (1u << len) - 1u) << a);
-      const int code = s_parent[r++];
-      if (code <= -2) {
-        CompStats& st = stats[(int64_t)f * MAX_COMPONENTS + (-2 - code)];
-        const int xa = xb + a;
-        atomicAdd(&st.area, len);
-        atomicAdd(&st.sx, (unsigned long long)(len * xa + len * (len - 1) / 2)); atomicAdd(&st.sy, (unsigned long long)y * len);
-        atomicMin(&st.x0, xa); atomicMax(&st.x1, xa + len - 1); atomicMin(&st.y0, y); atomicMax(&st.y1, y);
-      }
-    }
-  }
-  // ---- every dark pixel gets the code of its component: a warp fetches 32 entries at once and goes through them
-  for (int e0 = wid * 32; e0 < n; e0 += RUNS_THREADS) {
-    const int2 mine = e0 + lane < n ? E[e0 + lane] : make_int2(0, 0);
-    const int my_base = e0 + lane < n ? s_base[e0 + lane] : 0;
-    const int cnt = min(32, n - e0);
-    for (int j = 0; j < cnt; ++j) {
-      const int item = __shfl_sync(0xffffffffu, mine.x, j), base = __shfl_sync(0xffffffffu, my_base, j);
-      const unsigned m = (unsigned)__shfl_sync(0xffffffffu, mine.y, j);
-      if (m >> lane & 1u) {
-        const int y = item / chunks, ch = item - y * chunks;
-        L[y * win.ww + ch * 32 + lane] = s_parent[base + run_index(m & ~(m << 1), lane)];
-      }
-    }
-  }
+  // ---- hand-over to boundary_list_kernel: the code of every run and the first run of every entry
+  for (int r = tid; r < total; r += RUNS_THREADS) run_code[(int64_t)f * RUNS_RUN_CAP + r] = s_parent[r];
+  for (int e = tid; e < n; e += RUNS_THREADS) ent_base[(int64_t)f * RUNS_ENT_CAP + e] = s_base[e];
 }
 
 // joins: a run with the run to its left across an item boundary, and a run with the run above it - once per pair of runs (at
@@ -643,38 +612,67 @@ __global__ void comp_stats_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ 
 // window, next to it) in three passes - 0: farthest from the centroid (c0); 1: farthest from c0 (c2); 2: farthest from the line
 // c0 c2 on each side.  boundary_list_kernel (a thread per entry, mask arithmetic only) lists the boundary pixels of a frame;
 // the three passes run a thread per listed pixel.
-__global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, int64_t mask_stride,
-                                     const int* __restrict__ n_entries, const int2* __restrict__ entries, int* __restrict__ n_list, int* __restrict__ list) {
+__global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                     const int* __restrict__ n_entries, const int2* __restrict__ entries, const uint8_t* __restrict__ overflow,
+                                     const int* __restrict__ run_code, const int* __restrict__ ent_base, CompStats* __restrict__ stats,
+                                     int* __restrict__ n_list, int2* __restrict__ list) {
   const int f = blockIdx.y;
   const Win win = frame_window(rects, rect_stride, f, w, h);
   const int chunks = (win.ww + 31) >> 5, n = n_entries[f];
+  const bool by_label = overflow[f] != 0;
+  const int* L = label + (int64_t)f * w * h;
   const uint32_t* M = mask + f * mask_stride;
   const int2* E = entries + f * mask_stride;
-  int* P = list + (int64_t)f * w * h;
+  const int* code = run_code + (int64_t)f * RUNS_RUN_CAP;
+  int2* P = list + (int64_t)f * w * h;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const int2 v = E[e];
     const int item = v.x, y = item / chunks, ch = item - y * chunks;
     const unsigned m = (unsigned)v.y;
     const unsigned up = y > 0 ? M[item - chunks] : 0u, dn = y < win.hh - 1 ? M[item + chunks] : 0u;
     const unsigned lw = ch > 0 ? M[item - 1] : 0u, rw = ch < chunks - 1 ? M[item + 1] : 0u;
+    const int base = by_label ? 0 : ent_base[(int64_t)f * RUNS_ENT_CAP + e];
+    const int xb = ch * 32, i0 = y * win.ww + xb;
     // (a neighbour outside the window reads as background: the edge of the window is a boundary)
-    unsigned bm = m & ~(((m << 1) | (lw >> 31)) & ((m >> 1) | (rw << 31)) & up & dn);
-    if (bm == 0) continue;
-    int pos = atomicAdd(&n_list[f], __popc(bm));
-    const int i0 = y * win.ww + ch * 32;
-    while (bm) { P[pos++] = i0 + __ffs(bm) - 1; bm &= bm - 1; }
+    const unsigned bm = m & ~(((m << 1) | (lw >> 31)) & ((m >> 1) | (rw << 31)) & up & dn);
+    int pos = bm ? atomicAdd(&n_list[f], __popc(bm)) : 0;
+    // run by run: the component's statistics (length, coordinate sums, extent) and the boundary pixels of the run
+    unsigned mm = m;
+    int r = 0;
+    while (mm) {
+      const int a = __ffs(mm) - 1;
+      const unsigned t = mm >> a;
+      const int len = t == 0xffffffffu ? 32 : __ffs(~t) - 1;
+      const unsigned bits = (len == 32 ? 0xffffffffu : (1u << len) - 1u) << a;
+      mm &= ~bits;
+      if (by_label) {                                  // statistics came from comp_stats_kernel, codes sit in the labels
+        unsigned bb = bm & bits;
+        while (bb) { const int b = __ffs(bb) - 1; bb &= bb - 1; P[pos++] = make_int2(i0 + b, comp_code(L[i0 + b])); }
+        continue;
+      }
+      const int c = comp_code(code[base + r++]);
+      if (c >= 0) {
+        CompStats& st = stats[(int64_t)f * MAX_COMPONENTS + c];
+        const int xa = xb + a;
+        atomicAdd(&st.area, len);
+        atomicAdd(&st.sx, (unsigned long long)(len * xa + len * (len - 1) / 2)); atomicAdd(&st.sy, (unsigned long long)y * len);
+        atomicMin(&st.x0, xa); atomicMax(&st.x1, xa + len - 1); atomicMin(&st.y0, y); atomicMax(&st.y1, y);
+      }
+      unsigned bb = bm & bits;
+      while (bb) { const int b = __ffs(bb) - 1; bb &= bb - 1; P[pos++] = make_int2(i0 + b, c); }
+    }
   }
 }
 
-__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ label, const int* __restrict__ n_list,
-                                const int* __restrict__ list, CompStats* __restrict__ stats, int pass) {
+__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_list, const int2* __restrict__ list,
+                                CompStats* __restrict__ stats, int pass) {
   const int f = blockIdx.y;
   const Win win = frame_window(rects, rect_stride, f, w, h);
-  const int* L = label + (int64_t)f * w * h;
-  const int* P = list + (int64_t)f * w * h;
+  const int2* P = list + (int64_t)f * w * h;
   const int n = n_list[f], ww = win.ww;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int i = P[e], c = comp_code(L[i]);
+    const int2 ic = P[e];
+    const int i = ic.x, c = ic.y;
     if (c < 0) continue;
     CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
     const int area = s.area;
@@ -836,20 +834,22 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
                o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
                o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
                o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, o_win = o_margin + sizeof(float) * (size_t)max_quads * batch,
-               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int) * (size_t)n * batch,
+               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int2) * (size_t)n * batch,
                o_ent = (o_mask + sizeof(uint32_t) * (size_t)mask_stride * batch + 63) & ~(size_t)63, o_pos = o_ent + sizeof(int2) * (size_t)mask_stride * batch,
-               total = o_pos + sizeof(int) * (size_t)mask_stride * batch;
+               o_rcode = o_pos + sizeof(int) * (size_t)mask_stride * batch, o_ebase = o_rcode + sizeof(int) * (size_t)RUNS_RUN_CAP * batch,
+               total = o_ebase + sizeof(int) * (size_t)RUNS_ENT_CAP * batch;
   if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
   CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
   int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *nlist = reinterpret_cast<int*>(ws + o_nlist), *nent = reinterpret_cast<int*>(ws + o_nent),
       *nquads = reinterpret_cast<int*>(ws + o_nquads);
   float *quads = reinterpret_cast<float*>(ws + o_quads), *refined = reinterpret_cast<float*>(ws + o_refined);
   uint8_t* qvalid = ws + o_qvalid;
-  int* far_list = reinterpret_cast<int*>(ws + o_list);
+  int2* far_list = reinterpret_cast<int2*>(ws + o_list);
   int2* entries = reinterpret_cast<int2*>(ws + o_ent);
   uint32_t* mask = reinterpret_cast<uint32_t*>(ws + o_mask);
   int* entry_of = reinterpret_cast<int*>(ws + o_pos);
   uint8_t* overflow = ws + o_over;
+  int *run_code = reinterpret_cast<int*>(ws + o_rcode), *ent_base = reinterpret_cast<int*>(ws + o_ebase);
   cudaStream_t st = ctx->stream;
   // lo = 255, hi = 0 per frame; counters and validity flags zero
   AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
@@ -868,12 +868,13 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
   ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label, mask, mask_stride, nent, entries, entry_of);
   ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
-                                                           overflow);
+                                                           overflow, run_code, ent_base);
   ccl_merge_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow);
   ccl_flatten_number_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, ncomp, stats, overflow);
   comp_stats_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, stats, overflow);
-  boundary_list_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, mask, mask_stride, nent, entries, nlist, far_list);
-  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nlist, far_list, stats, pass);
+  boundary_list_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow, run_code, ent_base, stats,
+                                                nlist, far_list);
+  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, nlist, far_list, stats, pass);
   quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
                                                                                    nquads, max_quads, refine_win);
   AGT_LAUNCH_CHECK(ctx);
