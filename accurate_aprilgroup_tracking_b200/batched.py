@@ -201,6 +201,88 @@ class BatchedPoseDetector:
         return out
 
 
+class StreamGroups:
+    """The streams of one GPU as G independent ``BatchedPoseDetector``s, each with its own context (its own camera and group, if
+    the cameras differ), CUDA stream and ingest stream; the host drives the groups in turn from one thread.
+
+    Streams are independent (the reference runs one ``PoseDetector`` per camera) and the kernels work frame by frame, so every
+    stream gets exactly the arithmetic of the single batch: poses and accept decisions are bit-identical (tested).  What it is
+    NOT is a way to more poses per second on one camera model: a frame-step is one dependent chain of latency-bound kernels whose
+    length hardly depends on the batch (64 streams 0.33 ms, 32 streams 0.32 ms), so G groups of S/G streams in flight finish no
+    sooner than one batch of S, and the ~0.1 ms of host work per group-step binds from G = 4 on (measured on B200, 64 streams x
+    1080p, `bench.py --workload streams --stream-groups G`: 195 / 199 / 134 / 78 thousand poses/s at G = 1 / 2 / 4 / 8).  Use it
+    for groups of cameras that differ (resolution, calibration, tag group), not for speed."""
+
+    def __init__(self, contexts, n_streams: int, width: int, height: int, obj_pts: np.ndarray, **kw):
+        if not contexts:
+            raise ValueError("at least one context")
+        g = len(contexts)
+        if n_streams < g:
+            raise ValueError(f"{n_streams} streams cannot fill {g} groups")
+        t = contexts[0].torch
+        self.torch, self.n, self.g = t, int(n_streams), g
+        bounds = [round(k * n_streams / g) for k in range(g + 1)]
+        self.slices = [slice(bounds[k], bounds[k + 1]) for k in range(g)]
+        self.dets = [BatchedPoseDetector(c, sl.stop - sl.start, width, height, obj_pts, **kw) for c, sl in zip(contexts, self.slices)]
+        dev = contexts[0].tdev
+        self.mains = [t.cuda.Stream(dev) for _ in range(g)]
+        self.sides = [t.cuda.Stream(dev) for _ in range(g)]
+        self.landed = [t.cuda.Event() for _ in range(g)]
+        self.stepped = [t.cuda.Event() for _ in range(g)]
+        self._joined = t.cuda.Event()
+
+    def reset(self):
+        for d in self.dets:
+            d.reset()
+
+    def fork(self):
+        """The groups' streams wait for what has been queued on the current stream (e.g. the frames of the first step)."""
+        self._joined.record(self.torch.cuda.current_stream())
+        for m, ev in zip(self.mains, self.stepped):
+            m.wait_event(self._joined)
+            ev.record(m)
+
+    def join(self):
+        """The current stream waits for every group."""
+        cur = self.torch.cuda.current_stream()
+        for m in self.mains:
+            ev = self.torch.cuda.Event()
+            ev.record(m)
+            cur.wait_event(ev)
+
+    def load(self, frames):
+        """frames [S,H,W] -> the current slot of every group (on the current stream; call ``fork`` afterwards)."""
+        for d, sl in zip(self.dets, self.slices):
+            d.frames.copy_(frames[sl])
+
+    def step(self, img_pts=None, valid=None, n_tags=None, next_frames=None, pose_out=None, accepted_out=None, **frames_kw):
+        """One frame of every stream.  Detections as for ``BatchedPoseDetector.step`` ([S,...] arrays, sliced per group), or none
+        at all: the detector runs on the device (``step_frames``).  ``next_frames`` [S,H,W]: the frames of the following step,
+        ingested (copy + K1) on each group's side stream under the step in flight.  ``pose_out`` [S,6] / ``accepted_out`` [S]:
+        receive the poses and the accept flags (on the groups' streams: ``join`` before reading them elsewhere).
+        Returns the groups' output dicts (buffers of the captured graphs, valid on the group's stream until its slot comes round)."""
+        t = self.torch
+        outs = []
+        for k, (d, sl) in enumerate(zip(self.dets, self.slices)):
+            main, side = self.mains[k], self.sides[k]
+            with t.cuda.stream(main):
+                if next_frames is not None:
+                    side.wait_event(self.stepped[k])                 # the free slot was last read by the previous step
+                    with t.cuda.stream(side):
+                        d.ingest_next(next_frames[sl])
+                        self.landed[k].record(side)
+                out = d.step_frames(**frames_kw) if img_pts is None else d.step(img_pts[sl], valid[sl], n_tags[sl])
+                if pose_out is not None:
+                    pose_out[sl].copy_(out["pose"])
+                if accepted_out is not None:
+                    accepted_out[sl].copy_(out["accepted"].reshape(-1))
+                self.stepped[k].record(main)
+                if next_frames is not None:
+                    main.wait_event(self.landed[k])
+            outs.append(out)
+        return outs
+
+
 def tag_positions(tag_ids) -> dict:
     """tag id -> position of the tag in the group, i.e. in the JSON key order that defines the corner index 4 * position + j
     (detect_pose.py:122, :202: ``extrinsics`` is filled, and ``all_objpts`` stacked, in that order).  ``tag_ids`` is that

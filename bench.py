@@ -664,7 +664,7 @@ def run_multihyp(args):
             **{k: r[k] for k in ("gpu_launches", "hypothesis_refinements_per_s", "lm")}}), flush=True)
 
 
-def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps, from_pixels=False):
+def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, steps, from_pixels=False, groups=1):
     """Config 5 on this rank's streams `mine` (global stream ids): the whole sequence `steps` times, timed on the device, max
     over ranks.  -> dict (identical on every rank).  from_pixels: the tag detector runs on the device in front of the path
     (BatchedPoseDetector.step_frames: detect -> decision-margin filter -> id mapping -> APE ...) instead of detections handed in."""
@@ -719,6 +719,35 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
             holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), s_total)
         return acc
 
+    if groups > 1:
+        # the streams of this GPU as `groups` independent batches in flight at once (batched.StreamGroups): same poses, the
+        # latency-bound chains of the groups overlap
+        from accurate_aprilgroup_tracking_b200.batched import StreamGroups
+        from accurate_aprilgroup_tracking_b200.context import AgtContext
+        del bpd
+        gctx = [AgtContext(ctx.device, CAM.mtx, None) for _ in range(groups)]
+        for c in gctx:
+            c.set_synthetic_model()
+        sg = StreamGroups(gctx, S, CAM.width, CAM.height, synth.object_points())
+        bpd = sg.dets[0]
+        det_img_t, det_valid_t, det_n_t = torch.stack(det_img), torch.stack(det_valid), torch.stack(det_n)
+        acc_last = torch.zeros(S, dtype=torch.int32, device=ctx.tdev)
+
+        def run_sequence():                                             # noqa: F811
+            sg.reset()
+            sg.load(bank_frames[0])
+            sg.fork()
+            for f in range(F):
+                nxt = bank_frames[f + 1] if f + 1 < F else None
+                if from_pixels:
+                    sg.step(next_frames=nxt, pose_out=hist[:, f], accepted_out=acc_last)
+                else:
+                    sg.step(det_img_t[f], det_valid_t[f], det_n_t[f], next_frames=nxt, pose_out=hist[:, f], accepted_out=acc_last)
+            sg.join()
+            if world > 1:
+                holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), s_total)
+            return {"pose": hist[:, F - 1], "accepted": acc_last}
+
     run_sequence()
     torch.cuda.synchronize()
     if world > 1:
@@ -739,7 +768,8 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
     res = {"value": s_total * F * steps / (ms * 1e-3), "unit": "poses/s", "ms_per_frame_step": ms / steps / F, "ms_per_sequence": ms / steps,
            "streams": s_total, "streams_per_gpu": S, "frames_per_stream": F, "sequences_timed": steps,
            "gpu_launches": int((bpd.kernels_per_step + 3) * F * steps), "kernels_per_frame_step": int(bpd.kernels_per_step) + 3,
-           "cuda_graphs": True, "final_frame_median_trans_err_m": float(np.median(dt)),
+           "cuda_graphs": True, "stream_groups": int(groups), "pose_checksum": float(hist.sum().item()),
+           "final_frame_median_trans_err_m": float(np.median(dt)),
            "accepted_frac_last": float(out["accepted"].float().mean())}
     del bank, bpd
     return res
@@ -757,7 +787,8 @@ def run_streams(args):
     s_total = args.streams * world if weak else args.streams
     mine = list(range(rank * args.streams, (rank + 1) * args.streams)) if weak else sharding.local_streams(s_total, rank, world)
     pixels = args.stream_input == "pixels"
-    r = streams_measure(torch, dist, world, rank, ctx, s_total, mine, args.stream_frames, args.steps, from_pixels=pixels)
+    r = streams_measure(torch, dist, world, rank, ctx, s_total, mine, args.stream_frames, args.steps, from_pixels=pixels,
+                        groups=args.stream_groups)
     if rank == 0:
         print(json.dumps({
             "metric": "refined poses/sec (full APE+LK+DPR pipeline)", "value": r["value"], "unit": "poses/s",
@@ -769,7 +800,7 @@ def run_streams(args):
                        "streams": s_total, "frames_per_stream": args.stream_frames, "step": "one pass over all frames of all streams",
                        "parallelism": (f"{args.streams} streams per GPU" if weak else f"streams s mod {world} -> GPU")
                                       + "; one NCCL all-gather of all poses at the end of the sequence"},
-            **{k: r[k] for k in ("gpu_launches", "kernels_per_frame_step", "cuda_graphs", "ms_per_frame_step",
+            **{k: r[k] for k in ("gpu_launches", "kernels_per_frame_step", "cuda_graphs", "stream_groups", "pose_checksum", "ms_per_frame_step",
                                  "final_frame_median_trans_err_m", "accepted_frac_last")}}), flush=True)
 
 
@@ -897,6 +928,8 @@ def main():
     ap.add_argument("--streams", type=int, default=64)
     ap.add_argument("--stream-frames", type=int, default=64)
     ap.add_argument("--stream-scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--stream-groups", type=int, default=1,
+                    help="streams of a GPU as this many independent batches in flight at once (batched.StreamGroups)")
     ap.add_argument("--stream-input", default="detections", choices=["detections", "pixels"],
                     help="streams workload: tag detections handed in (BASELINE config 5), or frames only - the detector runs on the device")
     ap.add_argument("--no-streams", action="store_true", help="skip the config-3/4/5 legs of the default line")

@@ -132,3 +132,69 @@ def test_config5_64_streams_1080p_match_pipeline_oracle(ctx1080, tmp_path):
                 n_checked += 1
     print(f"config 5: {n_checked} accepted poses of {n_streams * n_frames} checked against the pipeline oracle, {n_tracked} tags re-admitted by LK")
     assert n_checked > 0.9 * n_streams * n_frames and n_tracked >= 50
+
+
+@pytest.mark.parametrize("from_pixels", [False, True])
+def test_stream_groups_equal_the_single_batch(ctxvga, from_pixels):
+    """batched.StreamGroups (the streams of a GPU as independent batches in flight on their own CUDA streams, frame ingest of the
+    next step on side streams) against one BatchedPoseDetector over all streams: same frames, same detections with dropouts
+    (or none at all: the detector on the device) -> every pose of every frame bit-identical, same accept decisions; graphs are
+    captured on the way (more than two steps)."""
+    import torch
+    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector, StreamGroups, pack_detections
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    cam = synth.CAMERA_VGA
+    n_streams, n_frames, groups = 10, 9, 3
+    trajs = [synth.trajectory(8100 + s, n_frames) for s in range(n_streams)]
+    rngs = [np.random.default_rng(8100 + s) for s in range(n_streams)]
+    bank = ctxvga.alloc_pyramid(n_streams * n_frames, cam.width, cam.height, 1)
+    for f in range(n_frames):
+        ctxvga.render(bank, np.array([trajs[s][f] for s in range(n_streams)]), np.arange(n_streams) + 100 * f, offset=f * n_streams,
+                      batch=n_streams)
+    frames = bank.frames.reshape(n_frames, n_streams, cam.height, cam.width)
+    dets = []
+    for f in range(n_frames):
+        row = []
+        for s in range(n_streams):
+            d = synth.detections(trajs[s][f], cam, rngs[s])
+            if (f + 2 * s) % 7 == 6:
+                d = d[:1]
+            row.append(d)
+        dets.append([torch.as_tensor(a, device=ctxvga.tdev) for a in pack_detections(row)])
+
+    single = BatchedPoseDetector(ctxvga, n_streams, cam.width, cam.height, synth.object_points())
+    ref_pose = torch.zeros((n_frames, n_streams, 6), dtype=torch.float64, device=ctxvga.tdev)
+    ref_acc = []
+    for f in range(n_frames):
+        single.frames.copy_(frames[f])
+        out = single.step_frames() if from_pixels else single.step(*dets[f])
+        ref_pose[f].copy_(out["pose"])
+        ref_acc.append(out["accepted"].clone())
+
+    ctxs = [AgtContext(0, cam.mtx, None) for _ in range(groups)]
+    for c in ctxs:
+        c.set_synthetic_model()
+    sg = StreamGroups(ctxs, n_streams, cam.width, cam.height, synth.object_points())
+    assert [sl.stop - sl.start for sl in sg.slices] == [3, 4, 3]
+    got_pose = torch.zeros_like(ref_pose)
+    for rep in range(2):                                  # the second pass replays the captured graphs from a reset state
+        sg.reset()
+        sg.load(frames[0])
+        sg.fork()
+        accs = torch.zeros((n_frames, n_streams), dtype=torch.int32, device=ctxvga.tdev)
+        for f in range(n_frames):
+            nxt = frames[f + 1] if f + 1 < n_frames else None
+            if from_pixels:
+                sg.step(next_frames=nxt, pose_out=got_pose[f], accepted_out=accs[f])
+            else:
+                sg.step(*dets[f], next_frames=nxt, pose_out=got_pose[f], accepted_out=accs[f])
+        sg.join()
+        torch.cuda.synchronize()
+        for f in range(n_frames):
+            a = accs[f]
+            assert torch.equal(a.cpu() != 0, ref_acc[f].reshape(-1).cpu() != 0), (rep, f)
+            ok = (a != 0).cpu().numpy()
+            assert np.array_equal(got_pose[f].cpu().numpy()[ok], ref_pose[f].cpu().numpy()[ok]), (rep, f)
+        assert sum(int(x.sum()) for x in ref_acc) >= n_frames * n_streams * 0.8
+    for c in ctxs:
+        c.close()
