@@ -82,6 +82,7 @@ PROTOTYPES = {
     "agt_lk_rects": (_I, [_VP, _PYR, _VP, _VP, _I, _I, _VP, _I, _I]),
     "agt_lk_roi": (_I, [_VP, _PYR, _PYR, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I]),
     "agt_pnp": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),
+    "agt_streams_front": (_I, [_VP] * 11 + [_I] + [_VP] * 6 + [_I, _I]),
     "agt_project": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_prepare": (_I, [_VP, _VP, _VP, _VP, _I, _I]),
     "agt_ape_update": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I]),

@@ -6,11 +6,12 @@ the reference's per-stream state (detect_pose.py:74-78) kept in device memory.  
 
   K1  agt_build_pyramid    pyramid of the new frames (outside the captured sequence: ``ingest_next`` lets the caller run
                            it, with the frame ingest, on a side stream while the previous step refines)
-  K2  agt_lk + agt_lk_merge  streams with < 2 detected tags re-admit the tags whose four corners
-                           were tracked from the previous frame (the inlier set is LK status == 1)
-  K0  agt_ape_prepare      extrinsic guess from the predictor state        (detect_pose.py:508)
-  K3  agt_pnp              batched solvePnP + mean reprojection error      (detect_pose.py:509-538)
-  K4  agt_accept_gate + agt_refine   dense refinement of the poses that pass the 2 px gate (masked)
+  K2  agt_lk_fallback      streams with < 2 detected tags track the corners of the previous accepted frame
+  --  agt_streams_front    ONE launch, a warp per stream: re-admit the tags whose four corners were tracked (agt_lk_merge: the
+                           inlier set is LK status == 1), extrinsic guess from the predictor state (agt_ape_prepare,
+                           detect_pose.py:508), K3 batched solvePnP + mean reprojection error (detect_pose.py:509-538), and the
+                           2 px gate that masks the refinement (agt_accept_gate)
+  K4  agt_refine           dense refinement of the poses that pass the gate
   K0  agt_ape_commit       accept / reset rules, velocity FIFOs, predictor (detect_pose.py:539-574) with the refined
                            pose, and the hand-over of the accepted frame's corners to the next LK step
 
@@ -108,24 +109,24 @@ class BatchedPoseDetector:
         """One frame of every stream: fixed launch sequence over static buffers (graph-capturable)."""
         ctx, t = self.ctx, self.ctx.torch
         cur, prv = self.pyr[slot], self.pyr[(slot - 1) % self.SLOTS]
-        img, val, ntg = self.in_img.clone(), self.in_valid.clone(), self.in_ntags.clone()
-        tracked_tags = None
+        # The detections of the frame are merged in place in the static input buffers (every step fills them anew before its graph
+        # runs); K2 only tracks frames with < 2 detected tags, and on the very first frame prev_valid is all zero, so nothing can be
+        # re-admitted from the (not yet written) previous slot.
+        img, val = self.in_img, self.in_valid
+        nxt = st = None
         if self.use_lk:
-            # K2: only frames with < 2 detected tags are tracked; on the very first frame prev_valid is all zero,
-            # so nothing can be re-admitted from the (not yet written) previous slot
-            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntg)
-            tracked_tags = t.empty(self.n, dtype=t.int32, device=ctx.tdev)
-            ctx.lk_merge(nxt, st, self.prev_valid, img, val, ntg, tracked_tags)
-        guess, use = ctx.ape_prepare(self.state, self.enhance_ape)               # K0
-        pose, ok, err, iters = ctx.pnp(self.obj, img, val, guess, use)            # K3
+            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=self.in_ntags)                                  # K2
+        # merge + K0 (guess from the state records) + K3 + accept gate: the frame's warp does them all in one launch
+        fr = ctx.streams_front(self.obj, self.state, self.enhance_ape, img, val, self.in_ntags, tracked=nxt, lk_status=st,
+                               prev_valid=self.prev_valid if self.use_lk else None, want_gate=self.use_dense_refine)
+        pose, ok, err, ntg, tracked_tags = fr["pose"], fr["ok"], fr["err"], fr["n_tags"], fr["tracked_tags"]
         refined = None
         if self.use_dense_refine:
-            gate = ctx.accept_gate(ok, err, ntg)                                  # only poses the reference accepts
             out = {k: t.empty((self.n, 1) + ((6,) if k == "pose" else ()), dtype=d, device=ctx.tdev)
                    for k, d in (("pose", t.float64), ("cost", t.float32), ("n_valid", t.int32), ("evals", t.int32),
                                 ("left_roi", t.uint8))}
-            out["status"] = t.zeros((self.n, 1), dtype=t.uint8, device=ctx.tdev)  # masked frames keep status 0: pose unused
-            refined = ctx.refine(cur, pose.reshape(self.n, 1, 6), 1, mask=gate, out=out)   # K4
+            out["status"] = fr["status"]                                          # masked frames keep status 0: pose unused
+            refined = ctx.refine(cur, pose.reshape(self.n, 1, 6), 1, mask=fr["gate"], out=out)   # K4
         # K0 with the refined pose where there is one; the corners of the accepted frame feed the next LK step
         accepted, flag, pose_out = ctx.ape_commit(self.state, ntg, pose, ok, err, refined, img, val, self.prev_pts,
                                                   self.prev_valid, self.enhance_ape)

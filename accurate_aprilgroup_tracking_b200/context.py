@@ -355,6 +355,25 @@ class AgtContext:
                                      self._p(ok), self._p(err), self._p(iters), b, p))
         return pose, ok, err, iters
 
+    def streams_front(self, obj, state, enhance_ape, img, valid, n_tags_in, tracked=None, lk_status=None, prev_valid=None,
+                      want_gate=True):
+        """agt_streams_front: lk_merge (when ``tracked`` is given) -> ape_prepare -> pnp -> accept_gate in one launch, on device tensors.
+        ``img`` [B,P,2] f32 / ``valid`` [B,P] u8 are merged in place.  -> dict(pose, ok, err, iters, n_tags, tracked_tags, gate, status)."""
+        t = self.torch
+        b, p = int(img.shape[0]), int(img.shape[1])
+        o = {"pose": t.empty((b, 6), dtype=t.float64, device=self.tdev), "ok": t.empty(b, dtype=t.uint8, device=self.tdev),
+             "err": t.empty(b, dtype=t.float32, device=self.tdev), "iters": t.empty(b, dtype=t.int32, device=self.tdev),
+             "n_tags": t.empty(b, dtype=t.int32, device=self.tdev),
+             "tracked_tags": t.empty(b, dtype=t.int32, device=self.tdev) if tracked is not None else None,
+             "gate": t.empty(b, dtype=t.uint8, device=self.tdev) if want_gate else None,
+             "status": t.empty((b, 1), dtype=t.uint8, device=self.tdev) if want_gate else None}
+        self._use_current_stream()
+        self._check(self.lib.agt_streams_front(self.h, self._p(obj), self._p(tracked), self._p(lk_status), self._p(prev_valid), self._p(img),
+                                               self._p(valid), self._p(n_tags_in), self._p(o["n_tags"]), self._p(o["tracked_tags"]),
+                                               self._p(state), 1 if enhance_ape else 0, self._p(o["pose"]), self._p(o["ok"]), self._p(o["err"]),
+                                               self._p(o["iters"]), self._p(o["gate"]), self._p(o["status"]), b, p))
+        return o
+
     def project(self, obj_pts, poses):
         t = self.torch
         obj = self._dev(obj_pts, t.float32)

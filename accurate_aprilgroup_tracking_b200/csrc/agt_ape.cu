@@ -19,6 +19,7 @@ namespace {
 
 enum { S_HAS_PREV = 0, S_PREV = 1, S_HAS_GUESS = 7, S_GUESS = 8, S_ALIAS = 14, S_T32 = 15, S_NVEL = 16, S_RV0 = 17,
        S_TV0 = 26, S_RV1 = 29, S_TV1 = 38 };
+static_assert(S_HAS_GUESS == AGT_STATE_HAS_GUESS && S_GUESS == AGT_STATE_GUESS, "agt_common.cuh: state record slots");
 
 __device__ inline void mat3_mul(const double* A, const double* B, double* C) {      // C = A B
   for (int r = 0; r < 3; ++r)

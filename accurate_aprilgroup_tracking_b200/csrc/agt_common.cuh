@@ -262,3 +262,6 @@ __device__ __forceinline__ long long agt_warp_sum(long long v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// slots of a stream's state record (layout: agt_ape.cu) that other translation units read
+constexpr int AGT_STATE_HAS_GUESS = 7, AGT_STATE_GUESS = 8;

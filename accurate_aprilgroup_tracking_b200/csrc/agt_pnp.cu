@@ -348,14 +348,61 @@ __device__ inline bool planar_init(const agt_camera& cam, const double X[2][3], 
   return fin;
 }
 
+// The stream pipeline's steps around the PnP of a frame, done by the frame's own warp in the same launch (agt_streams_front; a
+// frame-step is a chain of dependent launches, and five of them were one-warp-per-frame bookkeeping):
+//   before: agt_lk_merge (re-admit the tags whose four corners LK tracked, detect_pose.py stage 2) and agt_ape_prepare (the
+//           extrinsic guess of the stream's state record, detect_pose.py:508)
+//   after:  agt_accept_gate (detect_pose.py:494, 533, 539) and the reset of the refinement status of the frame
+struct PnpFront {
+  const float* tracked; const uint8_t* status; const uint8_t* prev_valid;       // LK results; tracked == nullptr: no merge
+  float* img; uint8_t* valid;                                                   // the frame's corners, merged in place
+  const int32_t* n_tags_in; int32_t* n_tags_out; int32_t* tracked_tags;
+  const double* state; int enhance;
+  uint8_t* gate; uint8_t* refine_status;                                        // nullable
+};
+
+template <bool kFront>
 __global__ void __launch_bounds__(PNP_WARPS * 32)
-pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restrict__ img, const uint8_t* __restrict__ valid,
+pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restrict__ img_in, const uint8_t* __restrict__ valid_in,
            const double* __restrict__ guess, const uint8_t* __restrict__ use_guess, double* __restrict__ pose_out,
-           uint8_t* __restrict__ ok_out, float* __restrict__ err_out, int32_t* __restrict__ iters_out, int n_pts, int batch) {
+           uint8_t* __restrict__ ok_out, float* __restrict__ err_out, int32_t* __restrict__ iters_out, int n_pts, int batch,
+           PnpFront F) {
   __shared__ double s_M[PNP_WARPS][144];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int f = blockIdx.x * PNP_WARPS + wid;
   if (f >= batch) return;
+
+  // (the merged corners are read back through the pointers they were written through, not through a read-only path)
+  const float* img = kFront ? F.img : img_in;
+  const uint8_t* valid = kFront ? F.valid : valid_in;
+  int n_tags = 0;
+  if (kFront) {
+    n_tags = F.n_tags_in[f];
+    if (F.tracked != nullptr) {                            // agt_lk_merge: lane = tag
+      const int tags = n_pts >> 2, before = n_tags;
+      bool det = false;
+      if (lane < tags) {
+        const int64_t base = ((int64_t)f * tags + lane) * 4;
+        det = F.valid[base] && F.valid[base + 1] && F.valid[base + 2] && F.valid[base + 3];
+        if (!det && before < 2) {
+          bool ok4 = true;
+          for (int j = 0; j < 4; ++j) ok4 = ok4 && F.prev_valid[base + j] != 0 && F.status[base + j] == 1;
+          if (ok4) {
+            for (int j = 0; j < 4; ++j) {
+              F.img[(base + j) * 2] = F.tracked[(base + j) * 2];
+              F.img[(base + j) * 2 + 1] = F.tracked[(base + j) * 2 + 1];
+              F.valid[base + j] = 1;
+            }
+            det = true;
+          }
+        }
+      }
+      n_tags = __popc(__ballot_sync(0xffffffffu, det));
+      if (lane == 0 && F.tracked_tags != nullptr) F.tracked_tags[f] = n_tags - before;
+      __syncwarp();
+    }
+    if (lane == 0) F.n_tags_out[f] = n_tags;
+  }
 
   double X[2][3], U[2][2];
   bool have[2];
@@ -375,10 +422,13 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
 
   double p[6];
   bool ok = n >= 4;
-  bool guessed = use_guess != nullptr && guess != nullptr && use_guess[f] != 0;
+  // (front: agt_ape_prepare - the guess is the one of the stream's state record, detect_pose.py:508)
+  const double* gsrc = kFront ? F.state + (int64_t)f * AGT_STREAM_STATE_DOUBLES + AGT_STATE_GUESS : guess + (int64_t)f * 6;
+  bool guessed = kFront ? (F.enhance != 0 && F.state[(int64_t)f * AGT_STREAM_STATE_DOUBLES + AGT_STATE_HAS_GUESS] != 0.0)
+                        : (use_guess != nullptr && guess != nullptr && use_guess[f] != 0);
   if (guessed) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) p[k] = guess[(int64_t)f * 6 + k];
+    for (int k = 0; k < 6; ++k) p[k] = gsrc[k];
 #pragma unroll
     for (int k = 0; k < 6; ++k) ok = ok && isfinite(p[k]);
   } else if (ok) {
@@ -571,8 +621,13 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
 #pragma unroll
     for (int a = 0; a < 6; ++a) pose_out[(int64_t)f * 6 + a] = ok ? p[a] : 0.0;
     ok_out[f] = ok ? 1 : 0;
-    err_out[f] = ok && n > 0 ? __fdiv_rn(total, (float)n) : 0.f;
+    const float err = ok && n > 0 ? __fdiv_rn(total, (float)n) : 0.f;
+    err_out[f] = err;
     if (iters_out) iters_out[f] = iters;
+    if (kFront) {
+      if (F.gate != nullptr) F.gate[f] = ok && err < 2.0f && n_tags >= 2 ? 1 : 0;      // agt_accept_gate
+      if (F.refine_status != nullptr) F.refine_status[f] = 0;                         // masked frames keep status 0
+    }
   }
 }
 
@@ -610,8 +665,30 @@ extern "C" int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_
   if (n_pts < 1 || n_pts > AGT_MAX_POINTS) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_pnp: n_pts must be 1..%d", AGT_MAX_POINTS);
   if (batch == 0) return AGT_OK;
   int blocks = (batch + PNP_WARPS - 1) / PNP_WARPS;
-  pnp_kernel<<<blocks, PNP_WARPS * 32, 0, ctx->stream>>>(ctx->cam, d_obj_pts, d_img_pts, d_valid, d_guess, d_use_guess,
-                                                         d_pose, d_ok, d_reproj_err, d_iters, n_pts, batch);
+  pnp_kernel<false><<<blocks, PNP_WARPS * 32, 0, ctx->stream>>>(ctx->cam, d_obj_pts, d_img_pts, d_valid, d_guess, d_use_guess,
+                                                                d_pose, d_ok, d_reproj_err, d_iters, n_pts, batch, PnpFront{});
+  AGT_LAUNCH_CHECK(ctx);
+  return AGT_OK;
+}
+
+extern "C" int agt_streams_front(agt_ctx* ctx, const float* d_obj_pts, const float* d_tracked_pts, const uint8_t* d_lk_status,
+                                 const uint8_t* d_prev_valid, float* d_img_pts, uint8_t* d_valid, const int32_t* d_n_tags_in,
+                                 int32_t* d_n_tags, int32_t* d_tracked_tags, const double* d_state, int enhance_ape, double* d_pose,
+                                 uint8_t* d_ok, float* d_reproj_err, int32_t* d_iters, uint8_t* d_gate, uint8_t* d_refine_status, int batch,
+                                 int n_pts) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (batch == 0) return AGT_OK;
+  if (!ctx->camera_set) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_streams_front: call agt_set_camera first");
+  if (!d_obj_pts || !d_img_pts || !d_valid || !d_n_tags_in || !d_n_tags || !d_state || !d_pose || !d_ok || !d_reproj_err || batch < 0 ||
+      n_pts < 4 || (n_pts & 3) || n_pts > AGT_MAX_POINTS || (d_tracked_pts != nullptr && (!d_lk_status || !d_prev_valid)))
+    AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_streams_front: bad arguments");
+  PnpFront F;
+  F.tracked = d_tracked_pts; F.status = d_lk_status; F.prev_valid = d_prev_valid; F.img = d_img_pts; F.valid = d_valid;
+  F.n_tags_in = d_n_tags_in; F.n_tags_out = d_n_tags; F.tracked_tags = d_tracked_tags; F.state = d_state; F.enhance = enhance_ape;
+  F.gate = d_gate; F.refine_status = d_refine_status;
+  int blocks = (batch + PNP_WARPS - 1) / PNP_WARPS;
+  pnp_kernel<true><<<blocks, PNP_WARPS * 32, 0, ctx->stream>>>(ctx->cam, d_obj_pts, nullptr, nullptr, nullptr, nullptr, d_pose, d_ok,
+                                                               d_reproj_err, d_iters, n_pts, batch, F);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }

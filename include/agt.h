@@ -240,6 +240,16 @@ int agt_pnp(agt_ctx* ctx, const float* d_obj_pts, const float* d_img_pts, const 
 /* cv::projectPoints: d_out[batch][n_pts][2] float64. */
 int agt_project(agt_ctx* ctx, const float* d_obj_pts, const double* d_pose, double* d_out, int batch, int n_pts);
 
+/* The stream pipeline's one-warp-per-frame steps around K3 in ONE launch (a frame-step is a chain of dependent launches):
+ * agt_lk_merge (d_tracked_pts NULL: skipped) -> agt_ape_prepare (the guess is read from the state records, detect_pose.py:508)
+ * -> agt_pnp -> agt_accept_gate (d_gate, may be NULL; detect_pose.py:494, 533, 539) and d_refine_status[batch] = 0 (may be NULL).
+ * d_img_pts / d_valid are merged in place; d_n_tags_in[batch] is read, d_n_tags[batch] written (they may be the same array).
+ * Same arithmetic, frame by frame, as the separate calls. */
+int agt_streams_front(agt_ctx* ctx, const float* d_obj_pts, const float* d_tracked_pts, const uint8_t* d_lk_status,
+                      const uint8_t* d_prev_valid, float* d_img_pts, uint8_t* d_valid, const int32_t* d_n_tags_in, int32_t* d_n_tags,
+                      int32_t* d_tracked_tags, const double* d_state, int enhance_ape, double* d_pose, uint8_t* d_ok,
+                      float* d_reproj_err, int32_t* d_iters, uint8_t* d_gate, uint8_t* d_refine_status, int batch, int n_pts);
+
 /* ---- K0: per-stream APE state machine + motion predictor --------------------- */
 /* State of one camera stream as detect_pose.py:74-78 keeps it (prev_transform,
  * extrinsic_guess, 2-deep velocity FIFOs) plus the aliasing flags needed to
