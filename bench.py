@@ -433,6 +433,9 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         strong = streams_measure(torch, dist, world, rank, ctx, 64, _sh.local_streams(64, rank, world), F, 2) if world > 1 else weak
         torch.cuda.empty_cache()
+        # the same 64 streams per GPU from pixels alone: the tag detector (N3) runs on the device in front of the path
+        pixels = streams_measure(torch, dist, world, rank, ctx, 64 * world, list(range(64 * rank, 64 * rank + 64)), F, 2, from_pixels=True)
+        torch.cuda.empty_cache()
         secondary["lk"] = dict(lk_measure(torch, dist, world, rank, ctx, 8192, 3, 3), metric="tracked corners/sec (BASELINE config 3)",
                                config=dict(LK_CONFIG, frame_pairs_per_gpu=8192))
         torch.cuda.empty_cache()
@@ -440,10 +443,11 @@ def run_gpu(args):
                                      metric="refined poses/sec, 64 hypotheses per frame (BASELINE config 4)")
         torch.cuda.empty_cache()
         streams = {"metric": "refined poses/sec (full APE+LK+DPR pipeline, BASELINE config 5)",
-                   "weak_64_streams_per_gpu": weak, "strong_64_streams": strong,
+                   "weak_64_streams_per_gpu": weak, "strong_64_streams": strong, "weak_64_streams_per_gpu_from_pixels": pixels,
                    "note": "one frame of every stream per step (frames of a stream are sequential: predictor and LK need the previous "
                            "frame), CUDA graph per step, frame ingest + K1 of the next frame on a side stream; streams pinned to GPUs, one "
-                           "all-gather of all poses per sequence"}
+                           "all-gather of all poses per sequence; from_pixels: no detections are handed in, agt_detect_tags_roi finds the "
+                           "tags on a window around each stream's predicted pose and agt_pack_detections filters and maps them on the device"}
     else:
         frames_s = pyr.frames[:args.cpu_sample].cpu().numpy() if (rank == 0 and not args.no_cpu) else None
 
