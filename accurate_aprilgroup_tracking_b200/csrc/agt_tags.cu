@@ -152,8 +152,9 @@ extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
 //
 //   threshold   dark <=> gray < lo + 0.35 (hi - lo), lo / hi the frame's darkest / brightest pixel (a global threshold: good
 //               for evenly lit frames; an adaptive one is the open item)
-//   components  4-connected components of the dark pixels by union-find in global memory (each pixel links to its right
-//               and lower neighbour with atomicMin, then every pixel is pointed at its root)
+//   components  4-connected components of the dark pixels: a mask word per 32-pixel item and a list of the non-empty items,
+//               union-find over the runs of a frame in shared memory (ccl_runs_kernel; cluttered frames: union-find over
+//               the pixels in global memory)
 //   quad        per component: area, centroid; the boundary pixel farthest from the centroid (c0), the one farthest from
 //               c0 (c2), and the ones farthest from the line c0 c2 on either side (c1, c3) - the four corners of a convex
 //               quadrilateral whatever its orientation; components that are too small, touch the frame or are not
@@ -381,7 +382,7 @@ __device__ __forceinline__ void run_union(int* parent, int a, int b) {
 __device__ __forceinline__ int run_index(unsigned starts, int b) { return __popc(starts & ((2u << b) - 1u)) - 1; }
 
 __global__ void __launch_bounds__(RUNS_THREADS, 1)
-ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint32_t* __restrict__ mask, int64_t mask_stride,
+ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, int64_t mask_stride,
                 const int* __restrict__ n_entries, const int2* __restrict__ entries, const int* __restrict__ entry_of, int* __restrict__ n_comp,
                 CompStats* __restrict__ stats, uint8_t* __restrict__ overflow, int* __restrict__ run_code, int* __restrict__ ent_base) {
   __shared__ int s_parent[RUNS_RUN_CAP];
@@ -391,7 +392,6 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, int* __restrict__ label, const uint3
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Win win = frame_window(rects, rect_stride, f, w, h);
   const int chunks = (win.ww + 31) >> 5;
-  int* L = label + (int64_t)f * w * h;
   const uint32_t* M = mask + f * mask_stride;
   const int2* E = entries + f * mask_stride;
   const int* P = entry_of + f * mask_stride;
@@ -867,7 +867,7 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   const dim3 grid_ne((unsigned)std::min<int64_t>((n + 255) / 256, std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch)), (unsigned)batch);
   frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
   ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label, mask, mask_stride, nent, entries, entry_of);
-  ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
+  ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
                                                            overflow, run_code, ent_base);
   ccl_merge_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow);
   ccl_flatten_number_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, ncomp, stats, overflow);
