@@ -121,6 +121,13 @@ extern "C" int agt_create(int device, agt_ctx** out) {
     ctx->k1_fused = e && e[0] == '1';
   }
   {
+    // LK of a small batch (a frame-step of the stream pipeline) is a wait for the slowest corner: a warp per pyramid level
+    // (lk_levels_kernel) halves that latency; large batches are throughput-bound and keep one warp per corner.  A machine-full
+    // of corners in the level-parallel layout = 4 x 8 CTAs of four warps per SM.
+    const char* e = getenv("AGT_LK_SPLIT_MAX");
+    ctx->lk_split_max = e ? atoi(e) : 8 * ctx->sm_count;
+  }
+  {
     unsigned hc = std::thread::hardware_concurrency();
     ctx->upload_threads = hc == 0 ? 4 : (hc < 8 ? (int)hc : 8);
   }

@@ -49,6 +49,7 @@ struct agt_ctx {
   int64_t launches;
   int k1_fused;                  // whole-frame pyramids in one pass (pyr_fused_kernel); AGT_K1_FUSED=0 selects the per-level launches
   int k1_fused_per_sm;           // resident CTAs per SM of that kernel (0: not asked yet)
+  int lk_split_max;              // agt_lk of at most this many corners runs a warp per pyramid level (AGT_LK_SPLIT_MAX; 0: never)
   int roi_upload;                // agt_refine_host uploads only the rectangle a refinement can read
   int64_t last_h2d_bytes;        // host->device bytes of the last agt_refine_host call
   int last_redo_frames;          // frames the last agt_refine_host call redid from the full frame

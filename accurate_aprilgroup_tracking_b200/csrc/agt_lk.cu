@@ -274,13 +274,19 @@ __device__ __noinline__ void scharr_cut_window(WarpSmem& S, int ix, int iy, int 
   }
 }
 
-template <bool kRoi>
+// kSplit (lk_levels_kernel, small batches): one warp per pyramid LEVEL of the corner.  What a level prepares - template
+// footprint, Scharr window, bilinear template, structure tensor - depends on the corner alone, not on the flow, and is half
+// of a corner's instructions: the warps of a CTA prepare all levels at once, then the search runs level by level, each warp
+// taking the flow of the level above over from shared memory (handover / publish: a chain of CTA barriers).  The arithmetic
+// of every level is the code below either way, so the results are bit-identical.
+template <bool kRoi, bool kSplit = false>
 __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int64_t gid, const agt_pyramid& prev, const agt_pyramid& next,
                                           const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                                           uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts,
                                           const int32_t* __restrict__ skip_if_tags_ge2, const int32_t* __restrict__ rects_prev,
                                           const int32_t* __restrict__ rects_next, int rect_stride, const uint8_t* __restrict__ mask,
-                                          uint8_t* __restrict__ left_roi_out) {
+                                          uint8_t* __restrict__ left_roi_out, const int my_level = 0, float* s_flow = nullptr) {
+  static_assert(!(kRoi && kSplit), "the level-parallel variant is for complete pyramids");
   const int frame = (int)(gid / n_pts);
   if (mask != nullptr && mask[frame] == 0) return;
   // region-of-interest rectangles: element k of the previous / next pyramid's rectangle lives in lane k / 4 + k (one
@@ -304,22 +310,40 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
   int status = 1;
   float err = 0.f;
   const int top = prev.levels - 1;
+  // level-parallel variant: barrier k (k = 1 .. top + 1) lies between the search of level top + 1 - k and that of the level below
+  auto cta_barrier = [] { asm volatile("bar.sync 1;" ::: "memory"); };
+  auto handover = [&](int level, float px0, float py0, float& nx, float& ny) {
+    if (!kSplit) return;
+    for (int l = top; l > level; --l) cta_barrier();
+    if (level == top) { nx = px0; ny = py0; } else { nx = __fmul_rn(s_flow[0], 2.f); ny = __fmul_rn(s_flow[1], 2.f); }
+    outx = nx; outy = ny;
+  };
+  auto publish = [&](int level) {
+    if (!kSplit) return;
+    if (lane == 0) { s_flow[0] = outx; s_flow[1] = outy; }
+    for (int l = level; l >= 0; --l) cta_barrier();
+  };
 
-  for (int level = top; level >= 0; --level) {
+  for (int level = kSplit ? my_level : top; level >= (kSplit ? my_level : 0); --level) {
     const int cols = prev.width[level], rows = prev.height[level];
     const uint8_t* imgI = prev.data[level] + (int64_t)frame * prev.frame_stride[level];
     const uint8_t* imgJ = next.data[level] + (int64_t)frame * next.frame_stride[level];
     const int64_t pitchI = prev.pitch[level], pitchJ = next.pitch[level];
     const float sc = (float)(1.0 / (double)(1 << level));
     float px = __fmul_rn(ptx, sc), py = __fmul_rn(pty, sc);
-    float nx, ny;
-    if (level == top) { nx = px; ny = py; } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
-    outx = nx; outy = ny;
+    const float px0 = px, py0 = py;
+    float nx = 0.f, ny = 0.f;
+    if (!kSplit) {
+      if (level == top) { nx = px; ny = py; } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
+      outx = nx; outy = ny;
+    }
     px = __fsub_rn(px, 10.f); py = __fsub_rn(py, 10.f);
     const int ix = (int)floorf(px), iy = (int)floorf(py);
     // also rejects NaN / huge coordinates (the float->int conversion saturates)
     if (!(px == px) || !(py == py) || ix < -WIN || ix >= cols || iy < -WIN || iy >= rows) {
       if (level == 0) { status = 0; err = 0.f; }
+      handover(level, px0, py0, nx, ny);
+      publish(level);
       continue;
     }
     if (kRoi) {
@@ -489,9 +513,12 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
     float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * WIN * WIN));
     if ((double)minEig < 1e-4 || D < 1.1920928955078125e-7f) {
       if (level == 0) status = 0;
+      handover(level, px0, py0, nx, ny);
+      publish(level);
       continue;
     }
     D = __fdiv_rn(1.f, D);
+    handover(level, px0, py0, nx, ny);       // (level-parallel variant: wait for the flow of the level above)
     __syncwarp();      // the scratch of the tensor sums is dead: the region buffer and the search scratch may overwrite it
     // zero padding of the search chains (elements 42, 43 of the eight lane chains; the tail's comes from lane 31's dead row)
     if (lane < 8) *reinterpret_cast<float2*>(&S.u.region.simd[lane][CH_SIMD - 2]) = make_float2(0.f, 0.f);
@@ -644,8 +671,9 @@ __device__ __forceinline__ void lk_corner(WarpSmem& S, const int lane, const int
         err = __fdiv_rn((float)warp_sum_wide(sabs), (float)(32 * WIN * WIN));      // `errval * 1.f / (32 * w * h)`
       }
     }
+    publish(level);
   }
-  if (lane == 0) {
+  if (lane == 0 && (!kSplit || my_level == 0)) {
     next_pts[gid * 2] = outx;
     next_pts[gid * 2 + 1] = outy;
     status_out[gid] = (uint8_t)status;
@@ -686,6 +714,19 @@ lk_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts
                     rects_next, rect_stride, mask, left_roi_out);
     __syncwarp();
   }
+}
+
+// Small batches (the stream pipeline tracks a few hundred corners per step, and waits for them): a CTA per corner, a warp per
+// pyramid level - see lk_corner<kRoi, kSplit>.  Same outputs as lk_kernel bit for bit, about half its latency.
+__global__ void __launch_bounds__(AGT_MAX_LEVELS * 32)
+lk_levels_kernel(agt_pyramid prev, agt_pyramid next, const float* __restrict__ prev_pts, float* __restrict__ next_pts,
+                 uint8_t* __restrict__ status_out, float* __restrict__ err_out, int n_pts, const int32_t* __restrict__ skip_if_tags_ge2) {
+  extern __shared__ __align__(16) uint8_t lk_smem_raw[];      // one WarpSmem per level
+  __shared__ float s_flow[2];
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(lk_smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  lk_corner<false, true>(smem[wid], lane, (int64_t)blockIdx.x, prev, next, prev_pts, next_pts, status_out, err_out, n_pts, skip_if_tags_ge2,
+                         nullptr, nullptr, 0, nullptr, nullptr, prev.levels - 1 - wid, s_flow);
 }
 
 // Level-0 rectangle (x0,y0,x1,y1; x multiples of 16) that covers what tracking the points of one frame can read when no
@@ -844,6 +885,15 @@ static int lk_impl(agt_ctx* ctx, const agt_pyramid* prev, const agt_pyramid* nex
   if (total == 0) return AGT_OK;
   int64_t blocks = (total + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   if (blocks > 0x7fffffffLL) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_lk: batch too large");
+  // (agt_lk_fallback skips the frames that kept their detections - nearly all: their CTAs leave at once - so it may be 8 x larger)
+  if (!d_rects_prev && !d_rects_next && !d_mask && prev->levels > 1 && total <= (int64_t)ctx->lk_split_max * (d_n_tags ? 8 : 1)) {
+    // few corners (a frame-step of the stream pipeline): the caller waits for the slowest corner, so a warp per level
+    const int smem = prev->levels * (int)sizeof(WarpSmem);
+    lk_levels_kernel<<<(unsigned)total, prev->levels * 32, smem, ctx->stream>>>(*prev, *next, d_prev_pts, d_next_pts, d_status, d_err, n_pts,
+                                                                              d_n_tags);
+    AGT_LAUNCH_CHECK(ctx);
+    return AGT_OK;
+  }
   const bool stride = d_mask != nullptr && blocks > 8LL * ctx->sm_count;
   if (stride) blocks = 8LL * ctx->sm_count;      // warps stride over the corners
   const bool roi = d_rects_prev || d_rects_next;

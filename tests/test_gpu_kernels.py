@@ -317,6 +317,34 @@ def test_lk_config3_sweep_512_pairs_every_corner(ctx1080):
     assert n_bits == 0, f"{n_bits} tracked corners are not bit-identical to OpenCV (worst {worst} px)"
 
 
+@pytest.mark.parametrize("levels", [4, 3, 2])
+def test_lk_level_parallel_equals_warp_per_corner(lib_built, levels, monkeypatch):
+    """Small batches run lk_levels_kernel (a warp per pyramid level, the levels' setups in parallel, the searches chained through
+    shared memory); large ones lk_kernel (a warp per corner).  Same code per level: points, status and error must be bit-identical,
+    with and without the fallback rule (frames with >= 2 tags skipped), corners outside the frame and NaNs included."""
+    from accurate_aprilgroup_tracking_b200.context import AgtContext
+    cam = synth.CAMERA_VGA
+    n = 5
+    traj = synth.trajectory(3300, n + 1)
+    obj = synth.object_points()
+    pts = np.stack([synth.project(obj, traj[i], cam) for i in range(n)]).astype(np.float32)
+    pts[0, 0] = [-40, -40]; pts[1, 1] = [np.nan, 3]; pts[2, 2] = [639.7, 479.2]; pts[3, 3] = [2000, 100]
+    n_tags = np.array([0, 2, 1, 5, 0], np.int32)
+    got = {}
+    for label, limit in (("levels", "100000"), ("corner", "0")):
+        monkeypatch.setenv("AGT_LK_SPLIT_MAX", limit)
+        ctx = AgtContext(0, cam.mtx, None)
+        prev = _render(ctx, cam, traj[:-1], np.arange(n) + 3300, levels=levels)
+        nxt = _render(ctx, cam, traj[1:], np.arange(n) + 3301, levels=levels)
+        a = [x.cpu().numpy() for x in ctx.lk(prev, nxt, pts)]
+        b = [x.cpu().numpy() for x in ctx.lk(prev, nxt, pts, n_tags=ctx._dev(n_tags, ctx.torch.int32))]
+        got[label] = a + b
+        ctx.close()
+    for x, y in zip(got["levels"], got["corner"]):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert got["levels"][1].sum() > 100 and (got["levels"][4][[1, 3]] == 0).all()
+
+
 def test_lk_textureless_all_lost(ctxvga):
     pyr_a = ctxvga.alloc_pyramid(1, 640, 480, 4)
     pyr_b = ctxvga.alloc_pyramid(1, 640, 480, 4)
