@@ -53,9 +53,13 @@ class BatchedPoseDetector:
         self.state = ctx.new_stream_state(self.n)
         dev = ctx.tdev
         # static buffers: the per-step work is a fixed launch sequence, captured once per pyramid slot into a CUDA graph
-        self.in_img = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
-        self.in_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
-        self.in_ntags = t.zeros(self.n, dtype=t.int32, device=dev)
+        # (the three inputs of a step are views of ONE buffer, so that a caller who holds them packed - ``pack_inputs`` - pays one
+        # copy per step instead of three)
+        nb_img, nb_nt, nb_val = 8 * self.n * self.n_pts, 4 * self.n, self.n * self.n_pts
+        self.in_all = t.zeros(nb_img + nb_nt + nb_val, dtype=t.uint8, device=dev)
+        self.in_img = self.in_all[:nb_img].view(t.float32).view(self.n, self.n_pts, 2)
+        self.in_ntags = self.in_all[nb_img:nb_img + nb_nt].view(t.int32)
+        self.in_valid = self.in_all[nb_img + nb_nt:].view(self.n, self.n_pts)
         self.prev_pts = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
         self.prev_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
         self.use_graphs = use_graphs
@@ -77,6 +81,19 @@ class BatchedPoseDetector:
         """Detections [(tag_id, corners (4,2)), ...] per stream -> the (img_pts, valid, n_tags) arrays ``step`` takes, indexed by
         the tags' positions in the group (KeyError for an id the group does not have)."""
         return pack_detections(dets_per_stream, self.tag_pos)
+
+    def pack_inputs(self, img_pts, valid, n_tags, pin: bool = False):
+        """(img_pts [S,P,2], valid [S,P], n_tags [S]) -> one uint8 tensor in the layout of the step's input buffer (host tensor,
+        pinned on request, for numpy inputs; device tensor for device inputs): ``step(packed)`` then costs one copy."""
+        t = self.ctx.torch
+        parts = []
+        for a, dt in ((img_pts, t.float32), (n_tags, t.int32), (valid, t.uint8)):
+            x = a if isinstance(a, t.Tensor) else t.as_tensor(np.ascontiguousarray(a))
+            parts.append(x.to(dt).contiguous().reshape(-1).view(t.uint8))
+        packed = t.cat(parts)
+        if packed.numel() != self.in_all.numel():
+            raise ValueError("inputs do not have this detector's shape")
+        return packed.pin_memory() if pin and not packed.is_cuda else packed
 
     def reset(self):
         """Forget all stream state (fresh streams); captured graphs stay valid because the buffers are reused."""
@@ -159,9 +176,9 @@ class BatchedPoseDetector:
         out["detections"] = det
         return out
 
-    def step(self, img_pts, valid, n_tags, frames=None):
+    def step(self, img_pts, valid=None, n_tags=None, frames=None):
         """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),
-        n_tags [S] i32 accepted detections.  ``frames`` [S,H,W] u8 is copied into the current slot
+        n_tags [S] i32 accepted detections - or ``step(packed)`` with the tensor ``pack_inputs`` made of them.  ``frames`` [S,H,W] u8 is copied into the current slot
         unless the caller wrote ``self.frames`` directly.  Returns a dict of device tensors (valid until the slot
         comes round again when CUDA graphs are in use: the graph of a slot reuses its output buffers)."""
         ctx, t = self.ctx, self.ctx.torch
@@ -172,7 +189,9 @@ class BatchedPoseDetector:
         if not self._built[slot]:
             ctx.build_pyramid(self.pyr[slot])                # K1 (unless ingest_next built this slot during the last step)
         self._built[slot] = False                            # the caller writes the next frame into it before it is used again
-        if img_pts is not None:                              # None: step_frames has filled the input buffers on the device
+        if img_pts is not None and valid is None:            # the three inputs packed by ``pack_inputs``: one copy
+            self.in_all.copy_(img_pts, non_blocking=True)
+        elif img_pts is not None:                            # None: step_frames has filled the input buffers on the device
             self.in_img.copy_(ctx._dev(img_pts, t.float32))
             self.in_valid.copy_(ctx._dev(valid, t.uint8))
             self.in_ntags.copy_(ctx._dev(n_tags, t.int32))

@@ -681,7 +681,7 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
     for f in range(F):
         ctx.render(bank, np.array([trajs[i][f] for i in range(S)]), np.array([1000 * s + f for s in mine]), offset=f * S, batch=S)
     bpd = BatchedPoseDetector(ctx, S, CAM.width, CAM.height, synth.object_points())
-    det_img, det_valid, det_n = [], [], []
+    det_img, det_valid, det_n, det_packed = [], [], [], []
     for f in range(F):
         dets = []
         for i in range(S):
@@ -692,6 +692,7 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
         a, b, c = bpd.pack(dets)
         det_img.append(torch.as_tensor(a, device=ctx.tdev)); det_valid.append(torch.as_tensor(b, device=ctx.tdev))
         det_n.append(torch.as_tensor(c, device=ctx.tdev))
+        det_packed.append(bpd.pack_inputs(det_img[-1], det_valid[-1], det_n[-1]))      # one copy per step instead of three
     bank_frames = bank.frames.reshape(F, S, CAM.height, CAM.width)
     holder = {}
     hist = torch.zeros((S, F, 6), dtype=torch.float64, device=ctx.tdev)     # every stream's poses, frame by frame
@@ -712,7 +713,7 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
                 with torch.cuda.stream(side):
                     bpd.ingest_next(bank_frames[f + 1])                 # ingest copy + K1 of the next frame
                     landed.record(side)
-            out = bpd.step_frames() if from_pixels else bpd.step(det_img[f], det_valid[f], det_n[f])
+            out = bpd.step_frames() if from_pixels else bpd.step(det_packed[f])
             hist[:, f].copy_(out["pose"])
             stepped.record(main)
             if f + 1 < F:
