@@ -208,7 +208,11 @@ class BatchedPoseDetector:
             # two steps have run eagerly (lazy one-time setup is done): capture this slot and replay it
             g = t.cuda.CUDAGraph()
             t.cuda.synchronize(ctx.tdev)
-            with t.cuda.graph(g):
+            # captured on the caller's stream when that is not the default one, so that the kernel nodes take its priority: a
+            # caller that runs the steps on a high-priority stream keeps the latency-bound chain ahead of the bandwidth-bound
+            # ingest (copy + K1) it overlaps with
+            cur = t.cuda.current_stream(ctx.tdev)
+            with t.cuda.graph(g, stream=None if cur == t.cuda.default_stream(ctx.tdev) else cur):
                 out = self._body(slot)
             g.replay()
             self._graphs[slot], self._outs[slot] = g, out

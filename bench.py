@@ -708,7 +708,12 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
         bpd.frames.copy_(bank_frames[0])
         stepped.record(main)
         for f in range(F):
-            if f + 1 < F:
+            if f + 1 < F and os.environ.get("AGT_BENCH_SERIAL_INGEST") == "1":     # (probe: no overlap, the chain alone)
+                bpd.ingest_next(bank_frames[f + 1])
+                landed.record(main)
+            elif f + 1 < F and os.environ.get("AGT_BENCH_SERIAL_INGEST") == "2":   # (probe: no ingest at all - stale frames)
+                landed.record(main)
+            elif f + 1 < F:
                 side.wait_event(stepped)                                # the free slot was last read by step f-1
                 with torch.cuda.stream(side):
                     bpd.ingest_next(bank_frames[f + 1])                 # ingest copy + K1 of the next frame
@@ -753,16 +758,20 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
                 holder["all"] = sharding.gather_stream_poses(hist.reshape(S, F * 6), s_total)
             return {"pose": hist[:, F - 1], "accepted": acc_last}
 
-    run_sequence()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        out = run_sequence()
-    e1.record()
-    torch.cuda.synchronize()
+    # the steps run on a high-priority stream (the ingest of the next frame on a normal one): the latency-bound chain of a step
+    # is not held up by the bandwidth-bound copy + K1 it overlaps with
+    hp = torch.cuda.Stream(priority=-1) if os.environ.get("AGT_BENCH_STREAM_PRIORITY", "1") == "1" else torch.cuda.current_stream()
+    with torch.cuda.stream(hp):
+        run_sequence()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = run_sequence()
+        e1.record()
+        torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.tdev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
