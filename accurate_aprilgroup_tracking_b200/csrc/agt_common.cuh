@@ -210,6 +210,15 @@ __device__ __forceinline__ double agt_rsqrt_newton(double d) {
   return y;
 }
 
+// 1/d in float64: MUFU.RCP64H seed + two Newton steps (d finite, non-zero, normal)
+__device__ __forceinline__ double agt_rcp_newton(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+  for (int it = 0; it < 2; ++it) y = fma(fma(-d, y, 1.0), y, y);
+  return y;
+}
+
 // index of H(p, q), p <= q, in the packed upper triangle stored by rows
 __host__ __device__ constexpr int agt_hk(int p, int q) { return p * 6 - p * (p - 1) / 2 + (q - p); }
 

@@ -206,6 +206,27 @@ struct __align__(16) DprJob {
 };
 static_assert(sizeof(DprJob) == 128, "DprJob layout");
 
+// tag k passes the visibility test at the pose (Rc, tc): its normal makes less than 75 degrees with the ray to its centre
+__device__ __forceinline__ bool dpr_tag_visible(const agt_model& model, const double Rc[9], const double tc[3], int k) {
+  double c[3], n[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    c[i] = Rc[i * 3] * model.centres[k][0] + Rc[i * 3 + 1] * model.centres[k][1] + Rc[i * 3 + 2] * model.centres[k][2] + tc[i];
+    n[i] = Rc[i * 3] * model.normals[k][0] + Rc[i * 3 + 1] * model.normals[k][1] + Rc[i * 3 + 2] * model.normals[k][2];
+  }
+  const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  const double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
+  return d > COS_VISIBLE;
+}
+
+__device__ __forceinline__ void dpr_fill_job(DprJob& j, const agt_dpr_plan& plan, uint32_t active, const double Rc[9]) {
+  j.level = plan.level; j.rx0 = plan.rx0; j.ry0 = plan.ry0; j.rx1 = plan.rx1; j.ry1 = plan.ry1;
+  j.tx0 = plan.tx0; j.ty0 = plan.ty0; j.tw = plan.tw; j.th = plan.th; j.active = active; j.pad[0] = j.pad[1] = 0;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) j.R[i] = Rc[i];
+  j.pad2 = 0.0;
+}
+
 __global__ void dpr_prep_kernel(agt_pyramid pyr, agt_camera cam, agt_model model, const double* __restrict__ init, int n_hyp,
                                 const uint8_t* __restrict__ mask, DprJob* __restrict__ jobs, int64_t n_jobs) {
   const int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,24 +238,31 @@ __global__ void dpr_prep_kernel(agt_pyramid pyr, agt_camera cam, agt_model model
   agt_rodrigues(r0, Rc);
   const agt_dpr_plan plan = agt_make_dpr_plan(cam, model.pitch, model.radius, tc, pyr.width, pyr.height, pyr.levels);
   uint32_t active = 0;
-  for (int k = 0; k < model.n_tags; ++k) {
-    double c[3], n[3];
-    for (int i = 0; i < 3; ++i) {
-      c[i] = Rc[i * 3] * model.centres[k][0] + Rc[i * 3 + 1] * model.centres[k][1] + Rc[i * 3 + 2] * model.centres[k][2] + tc[i];
-      n[i] = Rc[i * 3] * model.normals[k][0] + Rc[i * 3 + 1] * model.normals[k][1] + Rc[i * 3 + 2] * model.normals[k][2];
-    }
-    const double cn = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-    const double d = -(n[0] * c[0] + n[1] * c[1] + n[2] * c[2]) / cn;
-    if (d > COS_VISIBLE) active |= 1u << k;
-  }
+  for (int k = 0; k < model.n_tags; ++k)
+    if (dpr_tag_visible(model, Rc, tc, k)) active |= 1u << k;
   DprJob j;
-  j.level = plan.level; j.rx0 = plan.rx0; j.ry0 = plan.ry0; j.rx1 = plan.rx1; j.ry1 = plan.ry1;
-  j.tx0 = plan.tx0; j.ty0 = plan.ty0; j.tw = plan.tw; j.th = plan.th; j.active = active; j.pad[0] = j.pad[1] = 0;
-  for (int i = 0; i < 9; ++i) j.R[i] = Rc[i];
-  j.pad2 = 0.0;
+  dpr_fill_job(j, plan, active, Rc);
   jobs[job] = j;
 }
 
+// The same setup by one warp of the refinement's own CTA (cluster launches: a batch smaller than the machine is a chain of
+// dependent launches per frame-step, and a setup launch of its own is a tenth of that chain): every lane derives the rotation
+// and the ROI plan, lane k tests tag k, lane 0 writes the record.  Every CTA of a cluster arrives at the same record.
+__device__ __forceinline__ void dpr_prep_warp(const agt_pyramid& pyr, const agt_camera& cam, const agt_model& model,
+                                              const double* __restrict__ p0, DprJob* out, int lane) {
+  const double r0[3] = {p0[0], p0[1], p0[2]}, tc[3] = {p0[3], p0[4], p0[5]};
+  double Rc[9];
+  agt_rodrigues(r0, Rc);
+  const agt_dpr_plan plan = agt_make_dpr_plan(cam, model.pitch, model.radius, tc, pyr.width, pyr.height, pyr.levels);
+  uint32_t active = 0;
+  for (int k0 = 0; k0 < model.n_tags; k0 += 32) {
+    const int k = k0 + lane;
+    const bool vis = k < model.n_tags && dpr_tag_visible(model, Rc, tc, k < model.n_tags ? k : 0);
+    active |= __ballot_sync(0xffffffffu, vis) << k0;
+  }
+  if (lane == 0) dpr_fill_job(*out, plan, active, Rc);
+  __syncwarp();
+}
 // BORDER_REFLECT_101 index: in range almost always, the general fold otherwise
 __device__ __forceinline__ int reflect101(int i, int n) { return (unsigned)i < (unsigned)n ? i : agt_reflect101(i, n); }
 
@@ -361,8 +389,21 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   double* const Rc = S.Pc; double* const tc = S.Pc + 9;
 
   // ---- the plan of this refinement (dpr_prep_kernel), read by every thread so that staging starts at once --------
-  const int4* jw = reinterpret_cast<const int4*>(jobs + job);
-  const int4 ja = __ldg(jw), jb = __ldg(jw + 1), jc = __ldg(jw + 2);
+  const DprJob* jp = jobs + job;
+  int4 ja, jb, jc;
+  if (kCluster > 1 && jobs == nullptr) {
+    // no setup launch: warp 0 builds the record in the (still unused) pyramid scratch; it is consumed before the first barrier
+    // below, after which the scratch is free again
+    DprJob* sj = reinterpret_cast<DprJob*>(s_tile + TILE_BYTES);
+    if (wid == 0) dpr_prep_warp(pyr, cam, model, init + job * 6, sj, lane);
+    __syncthreads();
+    jp = sj;
+    const int4* jw = reinterpret_cast<const int4*>(sj);
+    ja = jw[0]; jb = jw[1]; jc = jw[2];
+  } else {
+    const int4* jw = reinterpret_cast<const int4*>(jp);
+    ja = __ldg(jw); jb = __ldg(jw + 1); jc = __ldg(jw + 2);
+  }
   const int lvl = ja.x;
   const bool build_level = fuse_pyramid != 0 && lvl > 0;
   auto stage_tile = [&]() {
@@ -399,7 +440,7 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
   if (tid == 0) {
     S.cc = 0.0; S.lam = LAMBDA0; S.nc = 0; S.evals = 0; S.status = AGT_DPR_MAX_EVALS; S.alpha = 1.0; S.have_prev = 0;
     const double* p0 = init + job * 6;
-    const DprJob* J = jobs + job;
+    const DprJob* J = jp;
 #pragma unroll
     for (int i = 0; i < 9; ++i) Rc[i] = J->R[i];
     tc[0] = p0[3]; tc[1] = p0[4]; tc[2] = p0[5];
@@ -909,11 +950,15 @@ static int refine_impl(agt_ctx* ctx, const agt_pyramid* pyr, const double* d_ini
     if (rc) return rc;
     d_jobs = static_cast<DprJob*>(pj);
   }
-  dpr_prep_kernel<<<(unsigned)((jobs + 127) / 128), 128, 0, ctx->stream>>>(*pyr, ctx->cam, ctx->model, d_init, n_hyp, d_mask, d_jobs, jobs);
-  AGT_LAUNCH_CHECK(ctx);
   int cluster = 1;
   const int64_t slots = 2LL * ctx->sm_count;
   while (cluster < 8 && jobs * (cluster * 2) <= slots) cluster *= 2;
+  if (cluster == 1) {
+    dpr_prep_kernel<<<(unsigned)((jobs + 127) / 128), 128, 0, ctx->stream>>>(*pyr, ctx->cam, ctx->model, d_init, n_hyp, d_mask, d_jobs, jobs);
+    AGT_LAUNCH_CHECK(ctx);
+  } else {
+    d_jobs = nullptr;                    // cluster launches derive the setup record in the kernel (dpr_prep_warp)
+  }
   if (cluster == 1) {
     dpr_kernel<1><<<(unsigned)jobs, DPR_THREADS, TILE_BYTES + PB_BYTES, ctx->stream>>>(*pyr, ctx->cam, ctx->model.samples, ctx->model, d_init,
                                                                          n_hyp, d_mask, d_pose, d_cost, d_n_valid, d_evals, d_status,

@@ -27,7 +27,7 @@ struct Proj {
 __device__ __forceinline__ Proj project_point(const agt_camera& cam, double X, double Y, double Z) {
   Proj p;
   p.ok = Z > 1e-9;
-  double iz = p.ok ? 1.0 / Z : 1.0;
+  double iz = p.ok ? agt_rcp_newton(Z) : 1.0;
   double x = X * iz, y = Y * iz;
   double dxx = 1.0, dxy = 0.0, dyx = 0.0, dyy = 1.0, xd = x, yd = y;
   if (cam.has_dist) {
@@ -49,25 +49,45 @@ __device__ __forceinline__ Proj project_point(const agt_camera& cam, double X, d
   return p;
 }
 
-// dR/dr_i for i=0..2 (row-major 3x3 each): (r_i [r]x + [r x (I-R) e_i]x) R / theta^2
-__device__ inline void rodrigues_jacobian(const double r[3], const double R[9], double dR[3][9]) {
-  double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+// R(r) and dR/dr_i for i=0..2 (row-major 3x3 each): dR/dr_i = [a_i]x R with a_i = (r_i r + r x (I-R) e_i) / theta^2.
+// One warp runs one frame, so a launch lasts as long as its longest chain of dependent float64 operations: theta comes
+// from a Newton-refined reciprocal square root (no sqrt, no division: 1/theta and 1/theta^2 fall out of it), the skew
+// products are written out (no multiplications by the zeros of [a]x).
+__device__ __forceinline__ void rodrigues_with_jacobian(const double r[3], double R[9], double dR[3][9]) {
+  const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  if (th2 < 1e-20) {                                       // R = I + [r]x, dR/dr_i = [e_i]x
+    R[0] = 1; R[1] = -r[2]; R[2] = r[1];
+    R[3] = r[2]; R[4] = 1; R[5] = -r[0];
+    R[6] = -r[1]; R[7] = r[0]; R[8] = 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dR[i][k] = 0.0;
+    dR[0][5] = -1; dR[0][7] = 1; dR[1][2] = 1; dR[1][6] = -1; dR[2][1] = -1; dR[2][3] = 1;
+    return;
+  }
+  const double ith = agt_rsqrt_newton(th2), th = th2 * ith, ith2 = ith * ith;
+  const double kx = r[0] * ith, ky = r[1] * ith, kz = r[2] * ith;
+  double sn, c;
+  sincos(th, &sn, &c);
+  const double c1 = 1.0 - c;
+  R[0] = c + c1 * kx * kx;       R[1] = c1 * kx * ky - sn * kz; R[2] = c1 * kx * kz + sn * ky;
+  R[3] = c1 * ky * kx + sn * kz; R[4] = c + c1 * ky * ky;       R[5] = c1 * ky * kz - sn * kx;
+  R[6] = c1 * kz * kx - sn * ky; R[7] = c1 * kz * ky + sn * kx; R[8] = c + c1 * kz * kz;
+#pragma unroll
   for (int i = 0; i < 3; ++i) {
-    double a[3];
-    if (th2 < 1e-20) {
-      a[0] = i == 0; a[1] = i == 1; a[2] = i == 2;          // dR/dr_i = [e_i]x
-      double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
-      for (int k = 0; k < 9; ++k) dR[i][k] = K[k];
-      continue;
-    }
     // v = (I - R) e_i
-    double v[3] = {(i == 0) - R[0 + i], (i == 1) - R[3 + i], (i == 2) - R[6 + i]};
-    double c[3] = {r[1] * v[2] - r[2] * v[1], r[2] * v[0] - r[0] * v[2], r[0] * v[1] - r[1] * v[0]};
-    a[0] = (r[i] * r[0] + c[0]) / th2; a[1] = (r[i] * r[1] + c[1]) / th2; a[2] = (r[i] * r[2] + c[2]) / th2;
-    double K[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
-    for (int rr = 0; rr < 3; ++rr)
-      for (int cc = 0; cc < 3; ++cc)
-        dR[i][rr * 3 + cc] = K[rr * 3 + 0] * R[0 + cc] + K[rr * 3 + 1] * R[3 + cc] + K[rr * 3 + 2] * R[6 + cc];
+    const double v[3] = {(i == 0) - R[0 + i], (i == 1) - R[3 + i], (i == 2) - R[6 + i]};
+    const double ri = r[i] * ith2;
+    const double a0 = fma(ri, r[0], (r[1] * v[2] - r[2] * v[1]) * ith2);
+    const double a1 = fma(ri, r[1], (r[2] * v[0] - r[0] * v[2]) * ith2);
+    const double a2 = fma(ri, r[2], (r[0] * v[1] - r[1] * v[0]) * ith2);
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      dR[i][0 + cc] = a1 * R[6 + cc] - a2 * R[3 + cc];
+      dR[i][3 + cc] = a2 * R[0 + cc] - a0 * R[6 + cc];
+      dR[i][6 + cc] = a0 * R[3 + cc] - a1 * R[0 + cc];
+    }
   }
 }
 
@@ -79,14 +99,14 @@ struct Normal {
 
 // Evaluate cost and normal equations at pose p for this lane's (<= 2) points and reduce over the warp.
 __device__ inline void evaluate(const agt_camera& cam, const double p[6], const double X[2][3], const double U[2][2],
-                                const bool have[2], Normal& out, bool& all_in_front) {
+                                const bool have[2], Normal& out, bool& all_in_front, float nrm[2]) {
   double R[9], dR[3][9];
-  agt_rodrigues(p, R);
-  rodrigues_jacobian(p, R, dR);
+  rodrigues_with_jacobian(p, R, dR);
   double acc[28];
 #pragma unroll
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
   bool front = true;
+  nrm[0] = nrm[1] = 0.f;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (!have[s]) continue;
@@ -97,6 +117,10 @@ __device__ inline void evaluate(const agt_camera& cam, const double p[6], const 
     Proj pr = project_point(cam, Xc, Yc, Zc);
     front = front && pr.ok;
     double e[2] = {pr.u - U[s][0], pr.v - U[s][1]};
+    {   // this point's term of the reference's mean reprojection error (transform_helper.py:106-119), in float32 like the reference
+      const float du = __fsub_rn((float)U[s][0], (float)pr.u), dv = __fsub_rn((float)U[s][1], (float)pr.v);
+      nrm[s] = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
+    }
     double J[2][6];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -553,43 +577,67 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
 
   // ---------------- Levenberg-Marquardt ---------------------------------------------
   int iters = 0;
+  float nrm[2] = {0.f, 0.f};            // per-point reprojection error of the pose in p (set by the evaluation that produced it)
   if (ok) {
+    // One evaluation site: the loop body is "evaluate the trial pose, decide, solve for the next trial" (the first trial is the
+    // initial value and is always taken) - the evaluation is the bulk of the kernel's code and is instantiated once.
     Normal cur, tri;
     bool front;
-    evaluate(cam, p, X, U, have, cur, front);
-    double lam = 1e-3;
-    for (iters = 0; iters < PNP_MAX_ITERS; ++iters) {
-      double A[21], b[6];                          // packed upper triangle, solved in registers
+    float tnrm[2];
+    double lam = 1e-3, dmax = 0.0;
+    double q[6];
 #pragma unroll
-      for (int k = 0; k < 21; ++k) A[k] = cur.H[k];
+    for (int a = 0; a < 6; ++a) q[a] = p[a];
+    bool first = true;
+    while (true) {
+      evaluate(cam, q, X, U, have, tri, front, tnrm);
+      bool stop = false;
+      if (first) {
+        cur = tri;
+        nrm[0] = tnrm[0]; nrm[1] = tnrm[1];
+        first = false;
+      } else {
+        if (front && tri.c < cur.c) {
 #pragma unroll
-      for (int a = 0; a < 6; ++a) { A[agt_hk(a, a)] *= (1.0 + lam); b[a] = -cur.g[a]; }
-      if (!agt_chol6_packed(A, b)) {
-        lam *= 10.0;
-        if (lam > 1e12) { ok = false; break; }
-        continue;
+          for (int a = 0; a < 6; ++a) p[a] = q[a];
+          cur = tri;
+          nrm[0] = tnrm[0]; nrm[1] = tnrm[1];
+          lam = fmax(lam * 0.1, 1e-15);
+          // an accepted step below 1e-9 (rad / m) ends the loop: the steps shrink at least by the damping factor (<= 1e-3, a tenth of
+          // it per accepted step), so what is left is below 1e-12 - four orders of magnitude under the distance to cv::solvePnP,
+          // which itself stops at a relative change of 1.2e-7.  (1e-11 bought one more evaluation per frame and nothing else.)
+          stop = dmax < 1e-9;
+        } else {
+          lam *= 10.0;
+          // a rejected step below 1e-8: the gradient is rounding noise, p is the minimiser to float64 accuracy.  (The bound was
+          // 1e-10: one frame in eight then spent six or seven more evaluations raising the damping until a 1e-9 step had shrunk
+          // below it - and a 64-frame launch lasts as long as its slowest frame: 10-11 evaluations instead of 5.)
+          stop = dmax < 1e-8 || lam > 1e12;
+        }
+        ++iters;
       }
-      double q[6], dmax = 0.0;
+      if (stop || iters >= PNP_MAX_ITERS) break;
+      // next trial: damped normal equations, solved in registers (packed upper triangle); a failed factorisation raises the damping
+      double b[6];
+      while (true) {
+        double A[21];
+#pragma unroll
+        for (int k = 0; k < 21; ++k) A[k] = cur.H[k];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) { A[agt_hk(a, a)] *= (1.0 + lam); b[a] = -cur.g[a]; }
+        if (agt_chol6_packed(A, b)) break;
+        lam *= 10.0;
+        ++iters;
+        if (lam > 1e12) { ok = false; break; }
+        if (iters >= PNP_MAX_ITERS) break;
+      }
+      if (!ok || iters >= PNP_MAX_ITERS) break;
+      dmax = 0.0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) { q[a] = p[a] + b[a]; dmax = fmax(dmax, fabs(b[a])); }
-      evaluate(cam, q, X, U, have, tri, front);
-      if (front && tri.c < cur.c) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) p[a] = q[a];
-        cur = tri;
-        lam = fmax(lam * 0.1, 1e-15);
-        // an accepted step below 1e-9 (rad / m) ends the loop: the steps shrink at least by the damping factor (<= 1e-3, a tenth of
-        // it per accepted step), so what is left is below 1e-12 - four orders of magnitude under the distance to cv::solvePnP,
-        // which itself stops at a relative change of 1.2e-7.  (1e-11 bought one more evaluation per frame and nothing else.)
-        if (dmax < 1e-9) { ++iters; break; }
-      } else {
-        lam *= 10.0;
-        if (dmax < 1e-10 || lam > 1e12) { ++iters; break; }
-      }
     }
     // keep the rotation vector in OpenCV's range (angle <= pi)
-    double th = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
-    if (th > 3.14159265358979323846) {
+    if (p[0] * p[0] + p[1] * p[1] + p[2] * p[2] > 3.14159265358979323846 * 3.14159265358979323846) {
       double R[9];
       agt_rodrigues(p, R);
       agt_log_rotation(R, p);
@@ -599,26 +647,13 @@ pnp_kernel(agt_camera cam, const float* __restrict__ obj, const float* __restric
   }
 
   // ---------------- epilogue: mean reprojection error as transform_helper.py:106-119 ----
-  float nrm[2] = {0.f, 0.f};
-  if (ok) {
-    double R[9];
-    agt_rodrigues(p, R);
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (have[s]) {
-        double Xc = R[0] * X[s][0] + R[1] * X[s][1] + R[2] * X[s][2] + p[3];
-        double Yc = R[3] * X[s][0] + R[4] * X[s][1] + R[5] * X[s][2] + p[4];
-        double Zc = R[6] * X[s][0] + R[7] * X[s][1] + R[8] * X[s][2] + p[5];
-        Proj pr = project_point(cam, Xc, Yc, Zc);
-        float du = __fsub_rn((float)U[s][0], (float)pr.u), dv = __fsub_rn((float)U[s][1], (float)pr.v);
-        nrm[s] = __fsqrt_rn(__fadd_rn(__fmul_rn(du, du), __fmul_rn(dv, dv)));
-      }
-  }
+  // (the per-point terms come from the evaluation of the final pose: same projection, no second pass)
+  if (!ok) nrm[0] = nrm[1] = 0.f;
   float total = 0.f;
-  for (int q = 0; q < n_pts; ++q) {
-    float v0 = __shfl_sync(0xffffffffu, q < 32 ? nrm[0] : nrm[1], q & 31);
-    int hv = __shfl_sync(0xffffffffu, (int)(q < 32 ? have[0] : have[1]), q & 31);
-    if (hv) total = __fadd_rn(total, v0);
+  const unsigned hm0 = __ballot_sync(0xffffffffu, have[0]), hm1 = __ballot_sync(0xffffffffu, have[1]);
+  for (int q = 0; q < n_pts; ++q) {                     // point order, one rounding per addition (Python's sum())
+    const float v0 = __shfl_sync(0xffffffffu, q < 32 ? nrm[0] : nrm[1], q & 31);
+    if (((q < 32 ? hm0 : hm1) >> (q & 31)) & 1u) total = __fadd_rn(total, v0);
   }
   if (lane == 0) {
 #pragma unroll

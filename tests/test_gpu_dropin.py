@@ -160,7 +160,8 @@ def test_refine_host_roi_upload_is_exact(host, ctxvga):
     host.refine_poses(np.full_like(frames, 255), init, cam.mtx)
     l0 = host.launch_count()
     pin = host.refine_poses(pinned.numpy(), init, cam.mtx)
-    assert host.launch_count() - l0 >= 3          # gather + setup + refinement with its fused pyrDown (+ redo pass)
+    assert host.launch_count() - l0 >= 2          # gather + refinement with its fused pyrDown (a batch this small runs as clusters,
+                                                  # which derive their setup record themselves) (+ redo pass)
     for key in ("pose", "cost", "n_valid", "evals", "status"):
         assert np.array_equal(pin[key], full[key]), key
     assert host.last_h2d_bytes() == roi_bytes

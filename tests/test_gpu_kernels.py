@@ -559,6 +559,59 @@ def test_pnp_planar_points_start_from_a_homography(ctxvga):
     assert n_cases == 2 * 3 * 24
 
 
+def test_reprojection_gate_near_the_threshold(ctxvga):
+    """A3 at the 2 px boundary (detect_pose.py:539 with transform_helper.py:98-121): one corner per frame is pushed off by a
+    ramp of offsets so that the mean reprojection error of the solved pose sweeps through 2.0 px; the device error must agree
+    with cv2.solvePnP + the reference's error formula to 1e-4 px there, and the gate must decide as the reference does on
+    every frame whose reference error is further than that from the threshold."""
+    import cv2
+    from oracle import ape_oracle
+    cam = synth.CAMERA_VGA
+    n = 240
+    obj, img, valid, truth = _pnp_inputs(cam, n, 4242, noise=0.05)
+    ntags = (valid.reshape(n, 12, 4).sum(axis=2) == 4).sum(axis=1).astype(np.int32)
+    rng = np.random.default_rng(11)
+    guess = truth + np.concatenate([rng.normal(0, 0.01, (n, 3)), rng.normal(0, 0.001, (n, 3))], axis=1)
+
+    def ref_error(i, pts):
+        m = valid[i] == 1
+        r0, t0 = guess[i, :3].reshape(3, 1).copy(), guess[i, 3:].reshape(3, 1).copy()
+        okr, r, t = cv2.solvePnP(obj[m], pts[m], cam.mtx, None, r0, t0, True, flags=cv2.SOLVEPNP_ITERATIVE)
+        assert okr
+        return ape_oracle.mean_reprojection_error(obj[m], pts[m], r, t, cam.mtx, None)
+
+    for i in range(n):
+        # offset of one corner, found by bisection on the reference, that leaves a mean error of 2.0 +- 0.1 px (a ramp over the batch)
+        target = ape_oracle.MAX_MEAN_ERROR + (i - n / 2 + 0.5) / n * 0.2
+        m0 = np.flatnonzero(valid[i])[0]
+        ang = rng.uniform(0, 2 * np.pi)
+        u = np.array([np.cos(ang), np.sin(ang)], np.float32)
+        lo, hi = 0.0, 200.0
+        for _ in range(30):
+            mid = 0.5 * (lo + hi)
+            pts = img[i].copy()
+            pts[m0] += np.float32(mid) * u
+            if ref_error(i, pts) < target:
+                lo = mid
+            else:
+                hi = mid
+        img[i, m0] += np.float32(0.5 * (lo + hi)) * u
+    pose, ok, err, _ = ctxvga.pnp(obj, img, valid, guess, np.ones(n, np.uint8))
+    gate = ctxvga.accept_gate(ok, err, ctxvga._dev(ntags, ctxvga.torch.int32)).cpu().numpy()
+    ok, err = ok.cpu().numpy(), err.cpu().numpy()
+    assert ok.all()
+    e_ref = np.array([ref_error(i, img[i]) for i in range(n)])
+    tol = 1e-4
+    assert np.abs(err - e_ref).max() < tol, np.abs(err - e_ref).max()
+    near = np.abs(e_ref - ape_oracle.MAX_MEAN_ERROR) < 0.05
+    assert near.sum() >= 10 and (e_ref[near] < 2.0).any() and (e_ref[near] > 2.0).any(), "the sweep missed the threshold"
+    decided = np.abs(e_ref - ape_oracle.MAX_MEAN_ERROR) > tol
+    want = (e_ref < ape_oracle.MAX_MEAN_ERROR) & (ntags >= ape_oracle.MIN_TAGS)
+    assert np.array_equal(gate[decided] != 0, want[decided])
+    print("gate sweep: errors", e_ref.min(), "..", e_ref.max(), "within 0.05 px of the threshold:", int(near.sum()),
+          "max |err - ref|", np.abs(err - e_ref).max())
+
+
 # ------------------------------------------------------------------------------------------
 # K3 + K0: the APE state machine over whole streams vs the reference restatement
 # ------------------------------------------------------------------------------------------
