@@ -55,11 +55,16 @@ class BatchedPoseDetector:
         # static buffers: the per-step work is a fixed launch sequence, captured once per pyramid slot into a CUDA graph
         # (the three inputs of a step are views of ONE buffer, so that a caller who holds them packed - ``pack_inputs`` - pays one
         # copy per step instead of three)
+        # One input buffer per frame slot: the inputs of the step after the coming one can be put in place (``detect_next``) while
+        # the step in flight still reads its own.
         nb_img, nb_nt, nb_val = 8 * self.n * self.n_pts, 4 * self.n, self.n * self.n_pts
-        self.in_all = t.zeros(nb_img + nb_nt + nb_val, dtype=t.uint8, device=dev)
-        self.in_img = self.in_all[:nb_img].view(t.float32).view(self.n, self.n_pts, 2)
-        self.in_ntags = self.in_all[nb_img:nb_img + nb_nt].view(t.int32)
-        self.in_valid = self.in_all[nb_img + nb_nt:].view(self.n, self.n_pts)
+        self._in = []
+        for _ in range(self.SLOTS):
+            buf = t.zeros(nb_img + nb_nt + nb_val, dtype=t.uint8, device=dev)
+            self._in.append((buf, buf[:nb_img].view(t.float32).view(self.n, self.n_pts, 2), buf[nb_img:nb_img + nb_nt].view(t.int32),
+                             buf[nb_img + nb_nt:].view(self.n, self.n_pts)))
+        self._rects_next = t.zeros((self.n, 4), dtype=t.int32, device=dev)      # search windows of the next frame (next_windows)
+        self._det_done = None                                                     # event: the last detection issued has finished
         self.prev_pts = t.zeros((self.n, self.n_pts, 2), dtype=t.float32, device=dev)
         self.prev_valid = t.zeros((self.n, self.n_pts), dtype=t.uint8, device=dev)
         self.use_graphs = use_graphs
@@ -76,6 +81,23 @@ class BatchedPoseDetector:
         self.group_ids = ctx._dev(np.array(sorted(self.tag_pos, key=self.tag_pos.get), dtype=np.int32), t.int32)
         self.n_unknown = t.zeros(self.n, dtype=t.int32, device=dev)
         self.radius = float(np.linalg.norm(np.asarray(obj_pts, dtype=np.float64), axis=1).max())      # bounding sphere of the group
+
+    # the input buffers of the coming step
+    @property
+    def in_all(self):
+        return self._in[self.cur][0]
+
+    @property
+    def in_img(self):
+        return self._in[self.cur][1]
+
+    @property
+    def in_ntags(self):
+        return self._in[self.cur][2]
+
+    @property
+    def in_valid(self):
+        return self._in[self.cur][3]
 
     def pack(self, dets_per_stream):
         """Detections [(tag_id, corners (4,2)), ...] per stream -> the (img_pts, valid, n_tags) arrays ``step`` takes, indexed by
@@ -113,12 +135,19 @@ class BatchedPoseDetector:
         (on another stream, ordered after the previous step) while that step runs."""
         return self.pyr[(self.cur + 1) % self.SLOTS].frames
 
-    def ingest_next(self, frames) -> None:
+    def ingest_next(self, frames, build: bool = True) -> None:
         """Put the frame of the step after the coming one into its slot and build its pyramid (K1), on the current stream:
         neither is read by the coming step, so with a side stream (ordered after the previous step; the coming-but-one step
         ordered after it) the bandwidth-bound ingest runs under the latency-bound refinement of the step in flight."""
         slot = (self.cur + 1) % self.SLOTS
         self.ctx.upload_frames(self.pyr[slot], frames)
+        if build:
+            self.build_next()
+
+    def build_next(self) -> None:
+        """K1 of the frame in the next slot (the second half of ``ingest_next(frames, build=False)``: a caller that also runs
+        ``detect_next``, which reads level 0 only, can put the two on different streams)."""
+        slot = (self.cur + 1) % self.SLOTS
         self.ctx.build_pyramid(self.pyr[slot])
         self._built[slot] = True
 
@@ -129,12 +158,12 @@ class BatchedPoseDetector:
         # The detections of the frame are merged in place in the static input buffers (every step fills them anew before its graph
         # runs); K2 only tracks frames with < 2 detected tags, and on the very first frame prev_valid is all zero, so nothing can be
         # re-admitted from the (not yet written) previous slot.
-        img, val = self.in_img, self.in_valid
+        _, img, ntags_in, val = self._in[slot]
         nxt = st = None
         if self.use_lk:
-            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=self.in_ntags)                                  # K2
+            nxt, st, _ = ctx.lk(prv, cur, self.prev_pts, n_tags=ntags_in)                                       # K2
         # merge + K0 (guess from the state records) + K3 + accept gate: the frame's warp does them all in one launch
-        fr = ctx.streams_front(self.obj, self.state, self.enhance_ape, img, val, self.in_ntags, tracked=nxt, lk_status=st,
+        fr = ctx.streams_front(self.obj, self.state, self.enhance_ape, img, val, ntags_in, tracked=nxt, lk_status=st,
                                prev_valid=self.prev_valid if self.use_lk else None, want_gate=self.use_dense_refine)
         pose, ok, err, ntg, tracked_tags = fr["pose"], fr["ok"], fr["err"], fr["n_tags"], fr["tracked_tags"]
         refined = None
@@ -168,13 +197,44 @@ class BatchedPoseDetector:
         if track_window:
             # look where the object is expected: around the predicted / last accepted pose of each stream (whole frame without one)
             rects = ctx.track_rects(self.state, self.pyr[slot].desc.width[0], self.pyr[slot].desc.height[0], self.radius, track_margin)
-        det = ctx.detect_tags(self.pyr[slot], max_tags=max_tags, refine_win=refine_win, rects=rects)
-        ctx.pack_detections(det, self.group_ids, min_margin, out=(self.in_img, self.in_valid, self.in_ntags, self.n_unknown))
+        det = self._detect_into(slot, rects, min_margin, refine_win, max_tags)
         if check_ids and int(self.n_unknown.sum().item()):
             raise KeyError("a detected tag id is not in the group")
         out = self.step(None, None, None)
         out["detections"] = det
         return out
+
+    def next_windows(self, track_margin: int = 64) -> None:
+        """First half of the pipelined detector (``detect_next``): the search windows of the frame AFTER the coming one, from the
+        stream states as they are now - call it on the stream the steps run on, before the coming step (whose commit moves the
+        states).  The pose predicted for the coming frame stands in for the one after it, so the margin is wider than
+        ``step_frames``' (the object moves twice as far)."""
+        pyr = self.pyr[self.cur]
+        self.ctx.track_rects(self.state, pyr.desc.width[0], pyr.desc.height[0], self.radius, track_margin, out=self._rects_next)
+
+    def detect_next(self, min_margin: float = 50.0, refine_win: int = 4, max_tags: int = 32, track_window: bool = True) -> None:
+        """Second half: detect the tags of the frame in the next slot (``ingest_next`` / ``next_frames`` put it there) inside the
+        windows ``next_windows`` left, and pack them into that slot's input buffers - on the current stream, which the caller orders
+        after ``next_windows`` and after the step that last read the slot.  Nothing the step in flight reads is touched, so the
+        detector of frame f+1 runs under the PnP / refinement chain of frame f; the step for f+1 is then ``step(None)``."""
+        slot = (self.cur + 1) % self.SLOTS
+        self._detect_into(slot, self._rects_next if track_window else None, min_margin, refine_win, max_tags)
+
+    def _detect_into(self, slot, rects, min_margin, refine_win, max_tags):
+        """Detector + decision-margin filter + id mapping of the frame in ``slot`` into that slot's input buffers, on the current
+        stream.  The detector's workspace belongs to the context, so two detections never overlap: each waits for the one issued
+        before it, whatever streams they were issued on (``step_frames`` on the step's stream, ``detect_next`` on a side stream)."""
+        t = self.ctx.torch
+        cur = t.cuda.current_stream(self.ctx.tdev)
+        if self._det_done is not None:
+            cur.wait_event(self._det_done)
+        else:
+            self._det_done = t.cuda.Event()
+        _, img, ntags_in, val = self._in[slot]
+        det = self.ctx.detect_tags(self.pyr[slot], max_tags=max_tags, refine_win=refine_win, rects=rects)
+        self.ctx.pack_detections(det, self.group_ids, min_margin, out=(img, val, ntags_in, self.n_unknown))
+        self._det_done.record(cur)
+        return det
 
     def step(self, img_pts, valid=None, n_tags=None, frames=None):
         """img_pts [S,P,2] f32, valid [S,P] u8 (corner-level; all four corners of a detected tag set),

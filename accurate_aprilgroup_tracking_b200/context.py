@@ -238,12 +238,12 @@ class AgtContext:
                                              self._p(out["rotation"]), self._p(out["hamming"]), self._p(out["margin"]), b, n, int(max_hamming)))
         return out
 
-    def track_rects(self, state, width: int, height: int, radius: float, margin: int = 48):
+    def track_rects(self, state, width: int, height: int, radius: float, margin: int = 48, out=None):
         """Search windows [B,4] i32 (x0,y0,x1,y1) of the detector from the stream states: around the predicted (else the last
-        accepted) pose; the empty rectangle (= whole frame) for streams without one."""
+        accepted) pose; the empty rectangle (= whole frame) for streams without one.  ``out``: preallocated [B,4] i32."""
         t = self.torch
         b = int(state.shape[0])
-        rects = t.empty((b, 4), dtype=t.int32, device=self.tdev)
+        rects = t.empty((b, 4), dtype=t.int32, device=self.tdev) if out is None else out
         self._use_current_stream()
         self._check(self.lib.agt_track_rects(self.h, self._p(state), float(radius), int(margin), int(width), int(height), self._p(rects), b))
         return rects

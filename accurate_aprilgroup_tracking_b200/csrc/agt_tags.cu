@@ -13,6 +13,15 @@
 
 #include "agt_common.cuh"
 
+// Iteration cap of the detector's corner refinement (stop rule: a step below 1e-3 px or this many iterations).  A corner of a
+// tag converges in 3-6 iterations; what runs longer is the corner of a quadrilateral that is no tag, or a corner bouncing
+// between two float32 positions - and the launch lasts as long as its slowest corner.  With 10 the ids and corners of the probe
+// frames are unchanged (scripts/tag_detect_probe.py) and the pass takes 32 instead of 57 us; cv2.aruco's own refinement stops
+// far earlier (cornerRefinementMinAccuracy 0.1 px).
+#ifndef AGT_TAG_SUBPIX_ITERS
+#define AGT_TAG_SUBPIX_ITERS 10
+#endif
+
 namespace {
 
 constexpr int CELLS = 8;
@@ -882,7 +891,7 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   if (refine_win > 0) {
     // only the corners of emitted quads (the validity flag of a quad, four times), each with its own window
     if ((rc = agt_corner_subpix_windows(ctx, d_gray, w, h, pitch, stride, quads, ws + o_win, ws + o_win, refined, batch, 4 * max_quads,
-                                        refine_win, 30, 1e-3)))
+                                        refine_win, AGT_TAG_SUBPIX_ITERS, 1e-3)))
       return rc;
     use = refined;
   }

@@ -699,7 +699,12 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
 
     # frame ingest (device to device) and its pyramid are double-buffered: frame f+1 lands in the free slot, and K1 builds its
     # pyramid, on a side stream while the latency-bound rest of step f runs
-    side, landed, stepped = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+    # from pixels: the detector of frame f+1 (search windows from the states before step f) runs on the side stream as well, under the
+    # chain of step f, and K1 of frame f+1 - which the detector does not read - on a third stream.  The detector is then the longest
+    # chain of the step (0.28 ms next to the refinement chain and K1, 0.19 ms alone), so its stream gets the high priority too.
+    pipelined = from_pixels and os.environ.get("AGT_BENCH_PIPELINED_DETECT", "1") == "1"
+    side, landed, stepped = torch.cuda.Stream(priority=-1 if pipelined else 0), torch.cuda.Event(), torch.cuda.Event()
+    third, prepared, copied, built = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def run_sequence():
         bpd.reset()
@@ -713,16 +718,36 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
                 landed.record(main)
             elif f + 1 < F and os.environ.get("AGT_BENCH_SERIAL_INGEST") == "2":   # (probe: no ingest at all - stale frames)
                 landed.record(main)
+            elif f + 1 < F and pipelined:
+                bpd.next_windows()                                      # where to look in frame f+1: from the states before step f
+                prepared.record(main)
+                side.wait_event(stepped)                                # the free slot was last read by step f-1
+                side.wait_event(prepared)
+                with torch.cuda.stream(side):
+                    bpd.ingest_next(bank_frames[f + 1], build=False)    # ingest copy of the next frame
+                    copied.record(side)
+                    bpd.detect_next()                                   # its tags, into the input buffers of its slot
+                    landed.record(side)
+                k1s = third if os.environ.get("AGT_BENCH_K1_THIRD", "1") == "1" else side
+                k1s.wait_event(copied)
+                with torch.cuda.stream(k1s):
+                    bpd.build_next()                                    # K1 of the next frame
+                    built.record(k1s)
             elif f + 1 < F:
                 side.wait_event(stepped)                                # the free slot was last read by step f-1
                 with torch.cuda.stream(side):
                     bpd.ingest_next(bank_frames[f + 1])                 # ingest copy + K1 of the next frame
                     landed.record(side)
-            out = bpd.step_frames() if from_pixels else bpd.step(det_packed[f])
+            if pipelined and f > 0:
+                out = bpd.step(None)                                    # detections are in place (detect_next of the last iteration)
+            else:
+                out = bpd.step_frames() if from_pixels else bpd.step(det_packed[f])
             hist[:, f].copy_(out["pose"])
             stepped.record(main)
             if f + 1 < F:
                 main.wait_event(landed)
+                if pipelined:
+                    main.wait_event(built)
             acc = out
         if world > 1:
             # NCCL: the final poses only - one all-gather of the whole sequence ([streams, frames x 6]), nothing per frame
@@ -782,7 +807,8 @@ def streams_measure(torch, dist, world, rank, ctx, s_total, mine, n_frames, step
     res = {"value": s_total * F * steps / (ms * 1e-3), "unit": "poses/s", "ms_per_frame_step": ms / steps / F, "ms_per_sequence": ms / steps,
            "streams": s_total, "streams_per_gpu": S, "frames_per_stream": F, "sequences_timed": steps,
            "gpu_launches": int((bpd.kernels_per_step + 3) * F * steps), "kernels_per_frame_step": int(bpd.kernels_per_step) + 3,
-           "cuda_graphs": True, "stream_groups": int(groups), "pose_checksum": float(hist.sum().item()),
+           "cuda_graphs": True, "stream_groups": int(groups), "detector_one_frame_ahead": bool(pipelined),
+           "pose_checksum": float(hist.sum().item()),
            "final_frame_median_trans_err_m": float(np.median(dt)),
            "accepted_frac_last": float(out["accepted"].float().mean())}
     del bank, bpd
@@ -814,7 +840,7 @@ def run_streams(args):
                        "streams": s_total, "frames_per_stream": args.stream_frames, "step": "one pass over all frames of all streams",
                        "parallelism": (f"{args.streams} streams per GPU" if weak else f"streams s mod {world} -> GPU")
                                       + "; one NCCL all-gather of all poses at the end of the sequence"},
-            **{k: r[k] for k in ("gpu_launches", "kernels_per_frame_step", "cuda_graphs", "stream_groups", "pose_checksum", "ms_per_frame_step",
+            **{k: r[k] for k in ("gpu_launches", "kernels_per_frame_step", "cuda_graphs", "stream_groups", "detector_one_frame_ahead", "pose_checksum", "ms_per_frame_step",
                                  "final_frame_median_trans_err_m", "accepted_frac_last")}}), flush=True)
 
 

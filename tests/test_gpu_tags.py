@@ -222,6 +222,67 @@ def test_stream_pipeline_from_pixels(ctx1080):
     assert n_acc >= n_streams * (n_frames - 1)
 
 
+def test_stream_pipeline_with_the_detector_one_frame_ahead(ctx1080):
+    """next_windows / detect_next: the detector of frame f+1 runs on a side stream (K1 on a third) under the chain of frame f, its
+    search windows taken from the stream states before step f.  Same decisions as the in-line detector (step_frames) and poses
+    within a small fraction of the tolerance of it (the windows, and with them the detector's threshold, differ slightly), eagerly
+    and from replayed graphs."""
+    from accurate_aprilgroup_tracking_b200.batched import BatchedPoseDetector
+    cam = synth.CAMERA_1080P
+    t = ctx1080.torch
+    n_streams, n_frames = 8, 10
+    trajs = [synth.trajectory(8300 + s, n_frames) for s in range(n_streams)]
+    bank = ctx1080.alloc_pyramid(n_streams * n_frames, cam.width, cam.height, 1)
+    for f in range(n_frames):
+        ctx1080.render(bank, np.array([trajs[s][f] for s in range(n_streams)]), np.arange(n_streams) + 50 * f, offset=f * n_streams, batch=n_streams)
+    frames = bank.frames.reshape(n_frames, n_streams, cam.height, cam.width)
+    inline = BatchedPoseDetector(ctx1080, n_streams, cam.width, cam.height, OBJ)
+    ref = []
+    for f in range(n_frames):
+        inline.frames.copy_(frames[f])
+        o = inline.step_frames()
+        ref.append((o["accepted"].cpu().numpy().copy(), o["pose"].cpu().numpy().copy(), o["n_tags"].cpu().numpy().copy()))
+    bpd = BatchedPoseDetector(ctx1080, n_streams, cam.width, cam.height, OBJ)
+    main = t.cuda.current_stream()
+    side, third = t.cuda.Stream(), t.cuda.Stream()
+    stepped, prepared, copied, landed, built = (t.cuda.Event() for _ in range(5))
+    bpd.frames.copy_(frames[0])
+    stepped.record(main)
+    n_acc, worst = 0, [0.0, 0.0]
+    for f in range(n_frames):
+        if f + 1 < n_frames:
+            bpd.next_windows()
+            prepared.record(main)
+            side.wait_event(stepped); side.wait_event(prepared)
+            with t.cuda.stream(side):
+                bpd.ingest_next(frames[f + 1], build=False)
+                copied.record(side)
+                bpd.detect_next()
+                landed.record(side)
+            third.wait_event(copied)
+            with t.cuda.stream(third):
+                bpd.build_next()
+                built.record(third)
+        out = bpd.step_frames() if f == 0 else bpd.step(None)
+        acc, pose, ntg = out["accepted"].cpu().numpy().copy(), out["pose"].cpu().numpy().copy(), out["n_tags"].cpu().numpy().copy()
+        stepped.record(main)
+        if f + 1 < n_frames:
+            main.wait_event(landed); main.wait_event(built)
+        assert np.array_equal(acc, ref[f][0]), f
+        assert np.abs(ntg - ref[f][2]).max() <= 1, f
+        for s in range(n_streams):
+            if acc[s]:
+                n_acc += 1
+                dr, dt = util.pose_diff(pose[s], ref[f][1][s])
+                worst = [max(worst[0], dr), max(worst[1], dt)]
+                assert dr < 2e-5 and dt < 4e-6, (f, s, dr, dt)        # a fifth of the parity tolerance
+    t.cuda.synchronize()
+    assert all(g is not None for g in bpd._graphs)                  # the later steps were graph replays
+    print(f"detector one frame ahead, {n_streams} streams x {n_frames} frames: {n_acc} accepted, worst {worst[0]:.2e} rad {worst[1]:.2e} m "
+          f"from the in-line detector")
+    assert n_acc >= n_streams * (n_frames - 1)
+
+
 def test_detect_tags_in_search_windows(ctx1080):
     """agt_detect_tags_roi: a window around the object finds the tags the whole-frame search finds (same ids, corners within half
     a pixel: the threshold is taken from the window), an empty rectangle means the whole frame, a window that cuts a tag drops it,
