@@ -30,7 +30,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int DPR_THREADS = 256;
+#ifndef AGT_DPR_THREADS
+#define AGT_DPR_THREADS 256      // (A/B builds: scripts/build_variant.py -DAGT_DPR_THREADS=...)
+#endif
+constexpr int DPR_THREADS = AGT_DPR_THREADS;
 constexpr int DPR_WARPS = DPR_THREADS / 32;
 constexpr int TILE_ROWS = AGT_DPR_TILE_ROWS;
 constexpr int TILE_PITCH = AGT_DPR_TILE_PITCH;
@@ -501,7 +504,8 @@ dpr_kernel(agt_pyramid pyr, agt_camera cam, const float4* __restrict__ samples, 
         const bool stream = L == 1 && (sw & 15) == 0 && sw >= 16 && sh >= 4 && (dw & 7) == 0 && (sp & 15) == 0 && (dp & 7) == 0 &&
                             (reinterpret_cast<uintptr_t>(simg) & 15) == 0 && (reinterpret_cast<uintptr_t>(dimg) & 7) == 0;
         if (stream) {
-          constexpr int kQ = 3;                                        // rows in flight per warp: 8 warps x 7 x 544 B of ring
+          constexpr int kQ = DPR_WARPS > 8 ? 2 : 3;                    // rows in flight per warp: 8 warps x 7 x 544 B of ring
+          static_assert(DPR_WARPS * (kQ + 4) * 544 <= PB_BYTES, "ring of the streaming pyrDown");
           const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_scratch) + wid * ((kQ + 4) * 544);
           const int xo1 = min(dw, (x1 + 7) & ~7);
           const int per = (y1 - y0 + DPR_WARPS - 1) / DPR_WARPS;
