@@ -58,6 +58,7 @@ PROTOTYPES = {
     "agt_undistort_to_gray": (_I, [_VP, _VP, _I, _I, _I, _I64, _I64, _VP, _I64, _I64, _I]),
     "agt_undistort_to_gray_host": (_I, [_VP, _VP, _I, _I, _I, _VP]),
     "agt_set_tag_family": (_I, [_VP, _VP, _I]),
+    "agt_set_tag_threshold": (_I, [_VP, _I]),
     "agt_decode_tags": (_I, [_VP, _VP, _I, _I, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I]),
     "agt_detect_tags": (_I, [_VP, _VP, _I, _I, _I64, _I64, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "agt_detect_tags_host": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),

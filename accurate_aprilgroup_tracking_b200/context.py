@@ -221,6 +221,14 @@ class AgtContext:
         self._check(self.lib.agt_set_tag_family(self.h, c.ctypes.data, int(c.size)))
         self._tag_family = int(c.size)
 
+    TAG_THRESHOLDS = {"auto": 0, "window": 1, "local": 2}
+
+    def set_tag_threshold(self, mode="auto"):
+        """What the detector's threshold takes as white: "window" = the brightest pixel of a frame's search window, "local" = the
+        brightest pixel of the 3 x 3 tiles of 32 x 32 pixels around the pixel (frames lit unevenly; the reference's apriltag
+        library thresholds adaptively), "auto" = local for whole frames, window for search windows."""
+        self._check(self.lib.agt_set_tag_threshold(self.h, self.TAG_THRESHOLDS[mode] if isinstance(mode, str) else int(mode)))
+
     def decode_tags(self, pyr: Pyramid, quads, valid=None, max_hamming: int = 2):
         """Identify the tag inside every quad: quads [B,Q,4,2] f32 (reference corner order, any rotation) ->
         dict(id [B,Q] i32 (-1: none), rotation u8, hamming u8, margin f32)."""

@@ -68,6 +68,7 @@ struct agt_ctx {
   int prect_capacity;
   uint64_t* d_tag_codes;         // tag family (36-bit code words) of agt_decode_tags / agt_detect_tags
   int n_tag_codes;
+  int tag_threshold;             // agt_set_tag_threshold: 0 auto, 1 one threshold per search window, 2 local white level
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];

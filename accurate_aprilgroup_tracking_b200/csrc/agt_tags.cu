@@ -138,6 +138,13 @@ extern "C" int agt_set_tag_family(agt_ctx* ctx, const uint64_t* h_codes, int n_c
   return AGT_OK;
 }
 
+extern "C" int agt_set_tag_threshold(agt_ctx* ctx, int mode) {
+  if (!ctx) return AGT_ERR_INVALID;
+  if (mode < 0 || mode > 2) AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_set_tag_threshold: mode 0 (auto), 1 (per window) or 2 (local white level)");
+  ctx->tag_threshold = mode;
+  return AGT_OK;
+}
+
 extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
                                const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
                                int n_quads, int max_hamming) {
@@ -159,8 +166,13 @@ extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
 // =====================================================================================================================
 // agt_detect_tags: quads of dark square regions -> corner refinement -> identification, for a batch of gray frames.
 //
-//   threshold   dark <=> gray < lo + 0.35 (hi - lo), lo / hi the frame's darkest / brightest pixel (a global threshold: good
-//               for evenly lit frames; an adaptive one is the open item)
+//   threshold   dark <=> gray < lo + 0.35 (hi - lo).  lo = the darkest pixel of the search window.  hi = the brightest pixel of
+//               the window (one threshold per window: a tracking window is a few hundred pixels wide, which is local already),
+//               or - whole frames, agt_set_tag_threshold - the brightest pixel of the 3 x 3 tiles of 32 x 32 pixels around the
+//               pixel: the local white level.  Uneven lighting is a smooth gain on the scene: it moves white by its full
+//               factor and black by next to nothing, so the threshold follows white and keeps the window's black.  (Taking
+//               lo from the neighbourhood as well - the adaptive threshold of the CPU detectors - turns mid-gray background
+//               next to a white quiet zone into dark frames around every tag that the later passes would have to discard.)
 //   components  4-connected components of the dark pixels: a mask word per 32-pixel item and a list of the non-empty items,
 //               union-find over the runs of a frame in shared memory (ccl_runs_kernel; cluttered frames: union-find over
 //               the pixels in global memory)
@@ -277,20 +289,59 @@ __global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int 
   if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * blockIdx.y], lo); atomicMax(&lohi[2 * blockIdx.y + 1], hi); }
 }
 
-__device__ __forceinline__ int frame_threshold(const int* lohi, int f) {
-  const int lo = lohi[2 * f], hi = lohi[2 * f + 1];
-  return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // a frame without contrast has no dark pixels
+__device__ __forceinline__ int threshold_of(int lo, int hi) {
+  return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // no contrast, no dark pixels
+}
+__device__ __forceinline__ int frame_threshold(const int* lohi, int f) { return threshold_of(lohi[2 * f], lohi[2 * f + 1]); }
+
+// Local white level: the brightest pixel of every 32 x 32 tile of a window (tile (ty, tx) = rows 32 ty.., item tx of the row), and
+// the window's darkest / brightest pixel as frame_minmax_kernel leaves them.  A warp takes four tiles of a tile row: 128 pixels
+// of a row per load, the eight lanes of a tile put their maxima together.
+constexpr int TILE = 32;
+__global__ void tile_max_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
+                                int* __restrict__ lohi, uint8_t* __restrict__ tile_hi, int64_t tile_stride) {
+  const uint8_t* p = img + blockIdx.y * stride;
+  const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
+  AGT_WARP_SETUP
+  uint8_t* T = tile_hi + f * tile_stride;
+  const int gchunks = (win.ww + 127) >> 7, trows = (win.hh + TILE - 1) / TILE;
+  uint32_t wlo4 = 0xffffffffu, whi4 = 0u;
+  for (int g = warp0; g < gchunks * trows; g += nwarps) {
+    const int ty = g / gchunks, gc = g - ty * gchunks, x = gc * 128 + 4 * lane;
+    uint32_t lo4 = 0xffffffffu, hi4 = 0u;
+    if (x < win.ww) {
+      const int nv = min(4, win.ww - x);
+      const uint32_t inv = nv < 4 ? 0xffffffffu << (8 * nv) : 0u;
+      const int y1 = min(win.hh, (ty + 1) * TILE);
+#pragma unroll 8
+      for (int y = ty * TILE; y < y1; ++y) {
+        const uint32_t v = load_px4(p + (int64_t)(win.y0 + y) * pitch + win.x0, x, win.ww, aligned);
+        lo4 = __vminu4(lo4, v | inv); hi4 = __vmaxu4(hi4, v & ~inv);
+      }
+    }
+    wlo4 = __vminu4(wlo4, lo4); whi4 = __vmaxu4(whi4, hi4);
+    hi4 = __vmaxu4(hi4, __shfl_xor_sync(0xffffffffu, hi4, 1)); hi4 = __vmaxu4(hi4, __shfl_xor_sync(0xffffffffu, hi4, 2));
+    hi4 = __vmaxu4(hi4, __shfl_xor_sync(0xffffffffu, hi4, 4));
+    const int tx = gc * 4 + (lane >> 3);
+    if ((lane & 7) == 0 && tx < chunks) T[ty * chunks + tx] = (uint8_t)max(max(hi4 & 0xff, (hi4 >> 8) & 0xff), max((hi4 >> 16) & 0xff, hi4 >> 24));
+  }
+  int lo = min(min(wlo4 & 0xff, (wlo4 >> 8) & 0xff), min((wlo4 >> 16) & 0xff, wlo4 >> 24));
+  int hi = max(max(whi4 & 0xff, (whi4 >> 8) & 0xff), max((whi4 >> 16) & 0xff, whi4 >> 24));
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0 && lo <= hi) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
 }
 
 // Threshold, mask words, list of non-empty items, first labels.  A warp reads 128 pixels of a row (four per lane); the eight
 // lanes of an item put their dark bits together.  A dark pixel's label starts as the first pixel of its horizontal run inside
 // the item, so a run is already one tree of depth 1 and the merge pass has to join runs, not pixels.
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
-                                const int* __restrict__ lohi, int* __restrict__ label, uint32_t* __restrict__ mask, int64_t mask_stride,
+                                const int* __restrict__ lohi, const uint8_t* __restrict__ tile_hi, int64_t tile_stride,
+                                int* __restrict__ label, uint32_t* __restrict__ mask, int64_t mask_stride,
                                 int* __restrict__ n_entries, int2* __restrict__ entries, int* __restrict__ entry_of) {
   const uint8_t* p = img + blockIdx.y * stride;
   const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
-  const int thr = frame_threshold(lohi, blockIdx.y);
+  const int frame_thr = frame_threshold(lohi, blockIdx.y), frame_lo = lohi[2 * blockIdx.y];
+  const uint8_t* T = tile_hi ? tile_hi + blockIdx.y * tile_stride : nullptr;
   int* L = label + (int64_t)blockIdx.y * w * h;
   uint32_t* M = mask + blockIdx.y * mask_stride;
   int2* E = entries + blockIdx.y * mask_stride;
@@ -311,6 +362,17 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int x = gc[k] * 128 + 4 * lane;
+      int thr = frame_thr;
+      if (T != nullptr) {
+        // local white level: the brightest of the 3 x 3 tiles around the item's tile, one neighbour per lane of the item
+        const int trows = (win.hh + TILE - 1) / TILE, ty = min(yy[k], win.hh - 1) / TILE, tx = min(gc[k] * 4 + q, chunks - 1);
+        const int dy = sub / 3 - 1, dx = sub - (sub / 3) * 3 - 1;                  // sub 0..7: eight neighbours; sub 0 adds (+1, +1)
+        int hi = T[min(max(ty + dy, 0), trows - 1) * chunks + min(max(tx + dx, 0), chunks - 1)];
+        if (sub == 0) hi = max(hi, (int)T[min(ty + 1, trows - 1) * chunks + min(tx + 1, chunks - 1)]);
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 4));
+        thr = threshold_of(frame_lo, hi);
+      }
       unsigned nib = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) nib |= (x + b < win.ww && (int)((v[k] >> (8 * b)) & 0xffu) < thr) ? 1u << b : 0u;
@@ -833,6 +895,9 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
     AGT_FAIL(ctx, AGT_ERR_INVALID, "agt_detect_tags: bad arguments");
   const int max_quads = 4 * max_tags < 64 ? 64 : 4 * max_tags;
   const int64_t n = (int64_t)w * h, mask_stride = (int64_t)((w + 31) / 32) * h;
+  const int64_t tile_stride = ((int64_t)((w + 31) / 32) * ((h + TILE - 1) / TILE) + 63) & ~(int64_t)63;
+  // whole frames take the local white level, search windows one threshold each (agt_set_tag_threshold overrides)
+  const bool local = ctx->tag_threshold == 2 || (ctx->tag_threshold == 0 && d_rects == nullptr);
   int* label;
   uint8_t* ws;
   int rc;
@@ -846,7 +911,7 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
                o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int2) * (size_t)n * batch,
                o_ent = (o_mask + sizeof(uint32_t) * (size_t)mask_stride * batch + 63) & ~(size_t)63, o_pos = o_ent + sizeof(int2) * (size_t)mask_stride * batch,
                o_rcode = o_pos + sizeof(int) * (size_t)mask_stride * batch, o_ebase = o_rcode + sizeof(int) * (size_t)RUNS_RUN_CAP * batch,
-               total = o_ebase + sizeof(int) * (size_t)RUNS_ENT_CAP * batch;
+               o_tiles = o_ebase + sizeof(int) * (size_t)RUNS_ENT_CAP * batch, total = o_tiles + (size_t)tile_stride * batch;
   if ((rc = agt_scratch(ctx, 1, total, reinterpret_cast<void**>(&ws)))) return rc;
   CompStats* stats = reinterpret_cast<CompStats*>(ws + o_stats);
   int *lohi = reinterpret_cast<int*>(ws + o_lohi), *ncomp = reinterpret_cast<int*>(ws + o_ncomp), *nlist = reinterpret_cast<int*>(ws + o_nlist), *nent = reinterpret_cast<int*>(ws + o_nent),
@@ -874,8 +939,11 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, per_frame), (unsigned)batch);
   // the passes over the list of non-empty items / boundary pixels: sized for the dark part of a frame, whatever the window
   const dim3 grid_ne((unsigned)std::min<int64_t>((n + 255) / 256, std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch)), (unsigned)batch);
-  frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
-  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, label, mask, mask_stride, nent, entries, entry_of);
+  uint8_t* tiles = local ? ws + o_tiles : nullptr;
+  if (local) tile_max_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride);
+  else frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride, label, mask, mask_stride, nent,
+                                       entries, entry_of);
   ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
                                                            overflow, run_code, ent_base);
   ccl_merge_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow);

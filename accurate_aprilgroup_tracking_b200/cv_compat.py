@@ -208,6 +208,11 @@ class HostContext:
         return corners
 
     # -- tag detection (N3) --------------------------------------------------------------
+    def set_tag_threshold(self, mode="auto"):
+        """"auto" / "window" / "local": see Context.set_tag_threshold (a whole frame, which is what detect_tags takes, uses the
+        local white level unless told otherwise)."""
+        self._check(self.lib.agt_set_tag_threshold(self.h, {"auto": 0, "window": 1, "local": 2}[mode] if isinstance(mode, str) else int(mode)))
+
     def detect_tags(self, gray, max_tags: int = 64, max_hamming: int = 2, refine_win: int = 4):
         """-> list of (tag_id, corners (4,2) float64 in the reference's corner order, decision margin, hamming) of a gray frame."""
         img = np.ascontiguousarray(gray, dtype=np.uint8)

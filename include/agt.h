@@ -135,7 +135,7 @@ int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t p
                     int n_quads, int max_hamming);
 
 /* agt_detect_tags: the detector itself for a batch of gray frames (detect_pose.py:368-371 detector.detect): dark 4-connected
- * components (global threshold per frame) -> quadrilateral fit -> agt_corner_subpix (refine_win, 0 = off) -> agt_decode_tags.
+ * components (dark = below darkest + 0.35 x (white - darkest); see agt_set_tag_threshold) -> quadrilateral fit -> agt_corner_subpix (refine_win, 0 = off) -> agt_decode_tags.
  * Per frame up to max_tags tags: d_n_tags [batch] (may exceed max_tags: clamp), d_ids [batch][max_tags], d_corners
  * [batch][max_tags][4][2] in the reference's corner order, d_margin / d_hamming (nullable).  The order of the tags of a frame is
  * not defined.  Pinned to cv2.aruco.ArucoDetector (DICT_APRILTAG_36h11) in tests/: same ids, corners within a pixel. */
@@ -144,6 +144,10 @@ int agt_detect_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t p
                     uint8_t* d_hamming);
 int agt_detect_tags_host(agt_ctx* ctx, const uint8_t* h_gray, int w, int h, int max_tags, int max_hamming, int refine_win,
                          int32_t* h_n_tags, int32_t* h_ids, float* h_corners, float* h_margin, uint8_t* h_hamming);
+/* What "white" is in the detector's threshold (the reference's apriltag library thresholds adaptively, detect_pose.py:86-95 leaves
+ * its defaults): mode 1 = the brightest pixel of the frame's search window, mode 2 = the brightest pixel of the 3 x 3 tiles of
+ * 32 x 32 pixels around the pixel (frames lit unevenly), mode 0 (default) = 2 for whole frames, 1 for search windows. */
+int agt_set_tag_threshold(agt_ctx* ctx, int mode);
 /* The detector on a search window per frame: d_rects [batch][rect_stride >= 4] int32 = x0, y0, x1, y1 in level-0 pixels (clipped to
  * the frame; an empty rectangle = the whole frame; NULL = every frame whole).  Thresholding, components and quads see only the
  * window (a tag cut by the window's edge is dropped like one cut by the frame); results are in frame coordinates.  In a tracking

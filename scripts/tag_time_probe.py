@@ -14,7 +14,10 @@ st = state.cpu().numpy(); st[:, 0] = 1.0; st[:, 1:7] = poses
 state.copy_(torch.tensor(st, device=state.device))
 radius = float(np.linalg.norm(synth.object_points(), axis=1).max())
 rects = ctx.track_rects(state, cam.width, cam.height, radius, 48)
-for which, r in (("window", rects), ("whole", None)):
+modes = (("window", rects, "auto"), ("whole", None, "auto")) if len(sys.argv) < 2 else \
+    (("window", rects, "window"), ("window, local white level", rects, "local"), ("whole, one threshold", None, "window"), ("whole, local white level", None, "local"))
+for which, r, mode in modes:
+    ctx.set_tag_threshold(mode)
     for _ in range(3): det = ctx.detect_tags(pyr, rects=r)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
