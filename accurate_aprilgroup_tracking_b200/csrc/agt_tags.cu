@@ -232,6 +232,11 @@ __device__ __forceinline__ Entry load_entry(const int2* __restrict__ E, int e, i
   return t;
 }
 
+// rows of the window can be read as 16-byte words (the window's left edge is a multiple of 16 pixels by construction)
+__device__ __forceinline__ bool rows_aligned16(const uint8_t* p, int64_t pitch, const Win& win) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (pitch & 15) == 0 && (win.x0 & 15) == 0;
+}
+
 // four pixels of a row as one word (x counts from the left edge of the window; pixels beyond the window read as 0)
 __device__ __forceinline__ uint32_t load_px4(const uint8_t* __restrict__ row, int x, int ww, bool aligned) {
   if (aligned) return *reinterpret_cast<const uint32_t*>(row + x);
@@ -286,13 +291,15 @@ __global__ void frame_minmax_kernel(const uint8_t* __restrict__ img, int w, int 
   int lo = min(min(lo4 & 0xff, (lo4 >> 8) & 0xff), min((lo4 >> 16) & 0xff, lo4 >> 24));
   int hi = max(max(hi4 & 0xff, (hi4 >> 8) & 0xff), max((hi4 >> 16) & 0xff, hi4 >> 24));
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&lohi[2 * blockIdx.y], lo); atomicMax(&lohi[2 * blockIdx.y + 1], hi); }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMax(&lohi[2 * blockIdx.y], 255 - lo); atomicMax(&lohi[2 * blockIdx.y + 1], hi); }
 }
 
 __device__ __forceinline__ int threshold_of(int lo, int hi) {
   return hi - lo < 40 ? -1 : lo + (35 * (hi - lo)) / 100;              // no contrast, no dark pixels
 }
-__device__ __forceinline__ int frame_threshold(const int* lohi, int f) { return threshold_of(lohi[2 * f], lohi[2 * f + 1]); }
+// lohi[2 f] = 255 - the darkest pixel, lohi[2 f + 1] = the brightest: both grow from zeroed memory by atomicMax
+__device__ __forceinline__ int frame_lo(const int* lohi, int f) { return 255 - lohi[2 * f]; }
+__device__ __forceinline__ int frame_threshold(const int* lohi, int f) { return threshold_of(frame_lo(lohi, f), lohi[2 * f + 1]); }
 
 // Local white level: the brightest pixel of every 32 x 32 tile of a window (tile (ty, tx) = rows 32 ty.., item tx of the row), and
 // the window's darkest / brightest pixel as frame_minmax_kernel leaves them.  A warp takes four tiles of a tile row: 128 pixels
@@ -306,6 +313,31 @@ __global__ void tile_max_kernel(const uint8_t* __restrict__ img, int w, int h, i
   uint8_t* T = tile_hi + f * tile_stride;
   const int gchunks = (win.ww + 127) >> 7, trows = (win.hh + TILE - 1) / TILE;
   uint32_t wlo4 = 0xffffffffu, whi4 = 0u;
+  if (rows_aligned16(p, pitch, win)) {
+    // sixteen pixels per lane: a warp takes 512 pixels of a tile row, two lanes make a tile
+    const int wch = (win.ww + 511) >> 9;
+    for (int g = warp0; g < wch * trows; g += nwarps) {
+      const int ty = g / wch, c = g - ty * wch, x = c * 512 + 16 * lane;
+      uint32_t lo4 = 0xffffffffu, hi4 = 0u;
+      if (x < win.ww) {
+        uint32_t inv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const int nv = min(4, max(win.ww - x - 4 * j, 0)); inv[j] = nv < 4 ? 0xffffffffu << (8 * nv) : 0u; }
+        const uint8_t* row = p + (int64_t)(win.y0 + ty * TILE) * pitch + win.x0 + x;
+        const int ny = min(win.hh, (ty + 1) * TILE) - ty * TILE;
+#pragma unroll 4
+        for (int y = 0; y < ny; ++y) {
+          const uint4 v = *reinterpret_cast<const uint4*>(row + (int64_t)y * pitch);
+          lo4 = __vminu4(lo4, __vminu4(__vminu4(v.x | inv[0], v.y | inv[1]), __vminu4(v.z | inv[2], v.w | inv[3])));
+          hi4 = __vmaxu4(hi4, __vmaxu4(__vmaxu4(v.x & ~inv[0], v.y & ~inv[1]), __vmaxu4(v.z & ~inv[2], v.w & ~inv[3])));
+        }
+      }
+      wlo4 = __vminu4(wlo4, lo4); whi4 = __vmaxu4(whi4, hi4);
+      hi4 = __vmaxu4(hi4, __shfl_xor_sync(0xffffffffu, hi4, 1));
+      const int tx = c * 16 + (lane >> 1);
+      if ((lane & 1) == 0 && tx < chunks) T[ty * chunks + tx] = (uint8_t)max(max(hi4 & 0xff, (hi4 >> 8) & 0xff), max((hi4 >> 16) & 0xff, hi4 >> 24));
+    }
+  } else
   for (int g = warp0; g < gchunks * trows; g += nwarps) {
     const int ty = g / gchunks, gc = g - ty * gchunks, x = gc * 128 + 4 * lane;
     uint32_t lo4 = 0xffffffffu, hi4 = 0u;
@@ -328,7 +360,7 @@ __global__ void tile_max_kernel(const uint8_t* __restrict__ img, int w, int h, i
   int lo = min(min(wlo4 & 0xff, (wlo4 >> 8) & 0xff), min((wlo4 >> 16) & 0xff, wlo4 >> 24));
   int hi = max(max(whi4 & 0xff, (whi4 >> 8) & 0xff), max((whi4 >> 16) & 0xff, whi4 >> 24));
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-  if (lane == 0 && lo <= hi) { atomicMin(&lohi[2 * f], lo); atomicMax(&lohi[2 * f + 1], hi); }
+  if (lane == 0 && lo <= hi) { atomicMax(&lohi[2 * f], 255 - lo); atomicMax(&lohi[2 * f + 1], hi); }
 }
 
 // Threshold, mask words, list of non-empty items, first labels.  A warp reads 128 pixels of a row (four per lane); the eight
@@ -340,13 +372,71 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
                                 int* __restrict__ n_entries, int2* __restrict__ entries, int* __restrict__ entry_of) {
   const uint8_t* p = img + blockIdx.y * stride;
   const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
-  const int frame_thr = frame_threshold(lohi, blockIdx.y), frame_lo = lohi[2 * blockIdx.y];
+  const int frame_thr = frame_threshold(lohi, blockIdx.y), black = frame_lo(lohi, blockIdx.y);
   const uint8_t* T = tile_hi ? tile_hi + blockIdx.y * tile_stride : nullptr;
   int* L = label + (int64_t)blockIdx.y * w * h;
   uint32_t* M = mask + blockIdx.y * mask_stride;
   int2* E = entries + blockIdx.y * mask_stride;
   int* P = entry_of + blockIdx.y * mask_stride;        // position of a non-empty item in the list
   AGT_WARP_SETUP
+  if (rows_aligned16(p, pitch, win)) {
+    // Sixteen pixels per lane, two lanes per item; a warp takes 512 pixels of INIT_ROWS (1-16) consecutive rows: the threshold of an item
+    // (nine tile maxima with the local white level) is formed once for those rows, the rows' loads do not depend on each other.
+    // Dark bits of four pixels: per-byte compare, then the bytes' top bits gathered by one multiplication.
+    const int wch = (win.ww + 511) >> 9, half = lane & 1;
+    int INIT_ROWS = 16;                                  // a divisor of TILE; fewer rows per warp where that leaves warps without work
+    while (INIT_ROWS > 1 && wch * ((win.hh + INIT_ROWS - 1) / INIT_ROWS) < nwarps) INIT_ROWS >>= 1;
+    const int rgroups = (win.hh + INIT_ROWS - 1) / INIT_ROWS;
+    for (int g = warp0; g < wch * rgroups; g += nwarps) {
+      const int rg = g / wch, c = g - rg * wch, x = c * 512 + 16 * lane, ch = c * 16 + (lane >> 1);
+      int thr = frame_thr;
+      if (T != nullptr) {
+        const int trows = (win.hh + TILE - 1) / TILE, ty = rg * INIT_ROWS / TILE, tx = min(ch, chunks - 1);
+        int hi = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {                                              // neighbours 0, 2, 4, 6, 8 / 1, 3, 5, 7 of the 3 x 3
+          const int nb = min(2 * k + half, 8), dy = nb / 3 - 1, dx = nb - (nb / 3) * 3 - 1;
+          hi = max(hi, (int)T[min(max(ty + dy, 0), trows - 1) * chunks + min(max(tx + dx, 0), chunks - 1)]);
+        }
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+        thr = threshold_of(black, hi);
+      }
+      const uint32_t thr4 = (uint32_t)max(thr, 0) * 0x01010101u;
+      const int nv = min(16, win.ww - x);
+      const uint32_t keep = nv >= 16 ? 0xffffu : (nv <= 0 ? 0u : (1u << nv) - 1u);
+      const uint8_t* row = p + (int64_t)(win.y0 + rg * INIT_ROWS) * pitch + win.x0 + x;
+      const int ny = min(win.hh, (rg + 1) * INIT_ROWS) - rg * INIT_ROWS;
+#pragma unroll 4
+      for (int yo = 0; yo < ny; ++yo) {
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (nv > 0) v = *reinterpret_cast<const uint4*>(row + (int64_t)yo * pitch);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        unsigned m16 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m16 |= (((__vcmpltu4(w4[j], thr4) & 0x80808080u) * 0x00204081u) >> 28) << (4 * j);
+        m16 &= keep;
+        const unsigned other = __shfl_xor_sync(0xffffffffu, m16, 1);
+        const unsigned m = half ? (other | (m16 << 16)) : (m16 | (other << 16));
+        const int y = rg * INIT_ROWS + yo, item = y * chunks + ch;
+        if (!half && ch < chunks) {
+          M[item] = m;
+          if (m != 0) {
+            const int pos = atomicAdd(&n_entries[f], 1);
+            E[pos] = make_int2(item, (int)m);
+            P[item] = pos;
+          }
+        }
+        unsigned mine = ch < chunks ? m & (half ? 0xffff0000u : 0x0000ffffu) : 0u;
+        while (mine) {
+          const int bit = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const unsigned zeros_below = ~m & ((1u << bit) - 1u);
+          L[y * win.ww + ch * 32 + bit] = y * win.ww + ch * 32 + (zeros_below ? 32 - __clz(zeros_below) : 0);
+        }
+      }
+    }
+    return;
+  }
   const int gchunks = (win.ww + 127) >> 7, gitems = gchunks * win.hh;
   const int sub = lane & 7, q = lane >> 3;
   for (int base = warp0 * 2; base < gitems; base += nwarps * 2) {
@@ -371,7 +461,7 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
         if (sub == 0) hi = max(hi, (int)T[min(ty + 1, trows - 1) * chunks + min(tx + 1, chunks - 1)]);
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 4));
-        thr = threshold_of(frame_lo, hi);
+        thr = threshold_of(black, hi);
       }
       unsigned nib = 0;
 #pragma unroll
@@ -735,13 +825,11 @@ __global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const int* __re
   }
 }
 
-__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_list, const int2* __restrict__ list,
-                                CompStats* __restrict__ stats, int pass) {
-  const int f = blockIdx.y;
-  const Win win = frame_window(rects, rect_stride, f, w, h);
-  const int2* P = list + (int64_t)f * w * h;
-  const int n = n_list[f], ww = win.ww;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+// one pass of the quadrilateral fit over boundary pixels e0, e0 + stride, ... of frame f (pass 0: farthest from the centroid,
+// 1: farthest from that pixel, 2: farthest from the line through the two, on either side).  The keys of the previous pass are
+// read past the L1 (they were written by atomics)
+__device__ __forceinline__ void far_pass(int f, int ww, const int2* __restrict__ P, int n, CompStats* __restrict__ stats, int pass, int e0, int stride) {
+  for (int e = e0; e < n; e += stride) {
     const int2 ic = P[e];
     const int i = ic.x, c = ic.y;
     if (c < 0) continue;
@@ -753,10 +841,10 @@ __global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restric
       const float cx = (float)((double)s.sx / area), cy = (float)((double)s.sy / area);
       atomicMax(&s.far0, far_key((x - cx) * (x - cx) + (y - cy) * (y - cy), i));
     } else if (pass == 1) {
-      const int p0 = (int)(s.far0 & 0xffffffffu), x0 = p0 % ww, y0 = p0 / ww;
+      const int p0 = (int)(__ldcg(&s.far0) & 0xffffffffu), x0 = p0 % ww, y0 = p0 / ww;
       atomicMax(&s.far2, far_key((float)((x - x0) * (x - x0) + (y - y0) * (y - y0)), i));
     } else {
-      const int p0 = (int)(s.far0 & 0xffffffffu), p2 = (int)(s.far2 & 0xffffffffu);
+      const int p0 = (int)(__ldcg(&s.far0) & 0xffffffffu), p2 = (int)(__ldcg(&s.far2) & 0xffffffffu);
       const int x0 = p0 % ww, y0 = p0 / ww, x2 = p2 % ww, y2 = p2 / ww;
       const float d = (float)((x2 - x0) * (y - y0) - (y2 - y0) * (x - x0));       // twice the signed area of (c0, c2, p)
       if (d > 0.f) atomicMax(&s.side_p, far_key(d, i));
@@ -765,24 +853,30 @@ __global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restric
   }
 }
 
-// one thread per component: quadrilateral test, clockwise-on-screen order, emit (frame coordinates)
-__global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_comp, const CompStats* __restrict__ stats,
-                                 float* __restrict__ quads, uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads,
-                                 int max_quads, int refine_win) {
-  const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
+__global__ void comp_far_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_list, const int2* __restrict__ list,
+                                CompStats* __restrict__ stats, int pass) {
+  const int f = blockIdx.y;
   const Win win = frame_window(rects, rect_stride, f, w, h);
-  const CompStats& s = stats[(int64_t)f * MAX_COMPONENTS + c];
-  if (s.area < 48 || s.x0 <= 0 || s.y0 <= 0 || s.x1 >= win.ww - 1 || s.y1 >= win.hh - 1) return;      // too small / cut by the window
-  if (s.far0 == 0 || s.far2 == 0 || s.side_p == 0 || s.side_n == 0) return;
-  const int p[4] = {(int)(s.far0 & 0xffffffffu), (int)(s.side_p & 0xffffffffu), (int)(s.far2 & 0xffffffffu), (int)(s.side_n & 0xffffffffu)};
+  far_pass(f, win.ww, list + (int64_t)f * w * h, n_list[f], stats, pass, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// component c of frame f: quadrilateral test, clockwise-on-screen order, emit (frame coordinates)
+__device__ __forceinline__ void emit_quad(int f, int c, const Win win, const CompStats* __restrict__ stats, float* __restrict__ quads,
+                                          uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads,
+                                          int max_quads, int refine_win) {
+  const CompStats* sp = stats + (int64_t)f * MAX_COMPONENTS + c;
+  const int s_area = sp->area;
+  if (s_area < 48 || sp->x0 <= 0 || sp->y0 <= 0 || sp->x1 >= win.ww - 1 || sp->y1 >= win.hh - 1) return;      // too small / cut by the window
+  const unsigned long long far0 = __ldcg(&sp->far0), far2 = __ldcg(&sp->far2), side_p = __ldcg(&sp->side_p), side_n = __ldcg(&sp->side_n);
+  if (far0 == 0 || far2 == 0 || side_p == 0 || side_n == 0) return;
+  const int p[4] = {(int)(far0 & 0xffffffffu), (int)(side_p & 0xffffffffu), (int)(far2 & 0xffffffffu), (int)(side_n & 0xffffffffu)};
   float qx[4], qy[4];
   for (int k = 0; k < 4; ++k) { qx[k] = (float)(p[k] % win.ww); qy[k] = (float)(p[k] / win.ww); }
   // the component is the tag's black border plus the dark cells attached to it: between ~30 % (border alone) and 100 % of its quad
   float area2 = 0.f;
   for (int k = 0; k < 4; ++k) area2 += qx[k] * qy[(k + 1) & 3] - qx[(k + 1) & 3] * qy[k];
   const float qa = 0.5f * fabsf(area2);
-  if (qa < 64.f || (float)s.area < 0.25f * qa || (float)s.area > 1.15f * qa) return;
+  if (qa < 64.f || (float)s_area < 0.25f * qa || (float)s_area > 1.15f * qa) return;
   // shortest side at least 6 px, and not a sliver
   float smin = 1e30f, smax = 0.f, mean_side = 0.f;
   for (int k = 0; k < 4; ++k) {
@@ -795,7 +889,7 @@ __global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restri
   float* q = quads + ((int64_t)f * max_quads + slot) * 8;
   // clockwise on the screen (y down) = positive shoelace sum: the reference's order BL, TL, TR, BR runs that way
   const bool cw = area2 > 0.f;
-  const float cx = (float)((double)s.sx / s.area), cy = (float)((double)s.sy / s.area);
+  const float cx = (float)((double)sp->sx / s_area), cy = (float)((double)sp->sy / s_area);
   for (int k = 0; k < 4; ++k) {
     const int j = cw ? k : (4 - k) & 3;
     // the corner pixels are dark pixels just inside the tag: move half a pixel outwards from the centroid
@@ -807,6 +901,16 @@ __global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restri
   // the corners of its inner cells (the rule of OpenCV's ArUco detector, relativeCornerRefinmentWinSize), at most refine_win
   const int cwin = min(max((int)(0.5f * mean_side / 8.f + 0.5f), 2), max(refine_win, 1));
   for (int k = 0; k < 4; ++k) quad_win[((int64_t)f * max_quads + slot) * 4 + k] = (uint8_t)cwin;
+}
+
+// one thread per component; the first thread of a frame also clears the frame's tag counter (tags_collect_kernel counts into it)
+__global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_comp, const CompStats* __restrict__ stats,
+                                 float* __restrict__ quads, uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads,
+                                 int max_quads, int refine_win, int32_t* __restrict__ out_n) {
+  const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) out_n[f] = 0;
+  if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
+  emit_quad(f, c, frame_window(rects, rect_stride, f, w, h), stats, quads, quad_valid, quad_win, n_quads, max_quads, refine_win);
 }
 
 // one thread per quad: keep the ones that decoded, in the reference's corner order
@@ -904,11 +1008,12 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   if ((rc = agt_scratch(ctx, 0, sizeof(int) * (size_t)n * batch, reinterpret_cast<void**>(&label)))) return rc;
   const size_t o_stats = 0, o_lohi = o_stats + sizeof(CompStats) * (size_t)MAX_COMPONENTS * batch, o_ncomp = o_lohi + sizeof(int) * 2 * batch,
                o_nlist = o_ncomp + sizeof(int) * batch, o_nent = o_nlist + sizeof(int) * batch, o_over = o_nent + sizeof(int) * batch, o_nquads = (o_over + (size_t)batch + 3) & ~(size_t)3,
-               o_quads = (o_nquads + sizeof(int) * batch + 63) & ~(size_t)63, o_refined = o_quads + sizeof(float) * 8 * (size_t)max_quads * batch,
-               o_qvalid = o_refined + sizeof(float) * 8 * (size_t)max_quads * batch, o_id = (o_qvalid + (size_t)max_quads * batch + 63) & ~(size_t)63,
+               o_qvalid = o_nquads + sizeof(int) * batch, o_win = o_qvalid + (size_t)max_quads * batch,             // everything up to here starts as zero
+               o_quads = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_refined = o_quads + sizeof(float) * 8 * (size_t)max_quads * batch,
+               o_id = (o_refined + sizeof(float) * 8 * (size_t)max_quads * batch + 63) & ~(size_t)63,
                o_rot = o_id + sizeof(int32_t) * (size_t)max_quads * batch, o_ham = o_rot + (size_t)max_quads * batch,
-               o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63, o_win = o_margin + sizeof(float) * (size_t)max_quads * batch,
-               o_list = (o_win + 4 * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int2) * (size_t)n * batch,
+               o_margin = (o_ham + (size_t)max_quads * batch + 63) & ~(size_t)63,
+               o_list = (o_margin + sizeof(float) * (size_t)max_quads * batch + 63) & ~(size_t)63, o_mask = o_list + sizeof(int2) * (size_t)n * batch,
                o_ent = (o_mask + sizeof(uint32_t) * (size_t)mask_stride * batch + 63) & ~(size_t)63, o_pos = o_ent + sizeof(int2) * (size_t)mask_stride * batch,
                o_rcode = o_pos + sizeof(int) * (size_t)mask_stride * batch, o_ebase = o_rcode + sizeof(int) * (size_t)RUNS_RUN_CAP * batch,
                o_tiles = o_ebase + sizeof(int) * (size_t)RUNS_ENT_CAP * batch, total = o_tiles + (size_t)tile_stride * batch;
@@ -925,17 +1030,13 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   uint8_t* overflow = ws + o_over;
   int *run_code = reinterpret_cast<int*>(ws + o_rcode), *ent_base = reinterpret_cast<int*>(ws + o_ebase);
   cudaStream_t st = ctx->stream;
-  // lo = 255, hi = 0 per frame; counters and validity flags zero
+  // one memset: darkest / brightest pixel (stored so that both start as 0), counters, overflow flags, validity flags and
+  // refinement windows of the quads; the tag counters are cleared by the quad emission
   AGT_CUDA(ctx, cudaMemsetAsync(ws + o_lohi, 0, o_quads - o_lohi, st));
-  AGT_CUDA(ctx, cudaMemsetAsync(qvalid, 0, (size_t)max_quads * batch, st));
-  AGT_CUDA(ctx, cudaMemsetAsync(ws + o_win, 0, 4 * (size_t)max_quads * batch, st));
-  AGT_CUDA(ctx, cudaMemsetAsync(d_n_tags, 0, sizeof(int32_t) * batch, st));
-  {
-    // lohi starts as (255, 0): set the lows with a tiny strided memset (2-D: 4 bytes every 8)
-    AGT_CUDA(ctx, cudaMemset2DAsync(lohi, 8, 0xff, 1, batch, st));          // low byte of lo = 255, the other bytes stay 0
-  }
   // grid-stride over the pixels of each frame's window; with windows (usually a few percent of the frame) a smaller grid per frame
-  const int64_t per_frame = d_rects ? std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch) : 1184;
+  // (whole frames: 32 CTAs per SM over the batch - a grid sized for one frame, times 64 frames, spent its time launching CTAs
+  // that had nothing to do: 174 + 188 us for min/max + threshold of 64 1080p frames)
+  const int64_t per_frame = std::max<int64_t>(16, (int64_t)(d_rects ? 8 : 32) * ctx->sm_count / batch);
   const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, per_frame), (unsigned)batch);
   // the passes over the list of non-empty items / boundary pixels: sized for the dark part of a frame, whatever the window
   const dim3 grid_ne((unsigned)std::min<int64_t>((n + 255) / 256, std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch)), (unsigned)batch);
@@ -951,9 +1052,11 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   comp_stats_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, stats, overflow);
   boundary_list_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow, run_code, ent_base, stats,
                                                 nlist, far_list);
+  // (the three passes and the emission of a frame by one CTA - one launch instead of four - measured slower: 33.6 against 27.8 us
+  // per 64 windows, the passes of a frame become one chain of dependent loads and atomics)
   for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, nlist, far_list, stats, pass);
   quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
-                                                                                   nquads, max_quads, refine_win);
+                                                                                   nquads, max_quads, refine_win, d_n_tags);
   AGT_LAUNCH_CHECK(ctx);
   const float* use = quads;
   if (refine_win > 0) {
