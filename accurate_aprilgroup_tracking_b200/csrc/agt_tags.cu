@@ -43,11 +43,16 @@ __device__ __forceinline__ Homography square_to_quad(const float* q) {
   return H;
 }
 
+// where the detector wants the quads that decode to a tag: per frame a counter and max_tags slots (out_n == NULL: nowhere)
+struct TagSink {
+  int32_t* out_n; int32_t* out_id; float* out_corners; float* out_margin; uint8_t* out_ham; int max_tags;
+};
+
 __global__ void __launch_bounds__(TG_WARPS * 32)
 decode_tags_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, const float* __restrict__ quads,
                    const uint8_t* __restrict__ valid, const unsigned long long* __restrict__ codes, int n_codes, int32_t* __restrict__ id_out,
                    uint8_t* __restrict__ rot_out, uint8_t* __restrict__ ham_out, float* __restrict__ margin_out, int n_quads, int64_t total,
-                   int max_hamming) {
+                   int max_hamming, const TagSink sink) {
   const int lane = threadIdx.x & 31;
   const int64_t gid = (int64_t)blockIdx.x * TG_WARPS + (threadIdx.x >> 5);
   if (gid >= total) return;
@@ -68,8 +73,8 @@ decode_tags_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch,
       for (int dt = -1; dt <= 1; ++dt)
         for (int ds = -1; ds <= 1; ++ds) {
           const double s = ((double)c + 0.5 + 0.25 * ds) / CELLS, t = ((double)r + 0.5 + 0.25 * dt) / CELLS;
-          const double ww = H.g * s + H.h * t + 1.0;
-          const double x = (H.a * s + H.b * t + H.c) / ww, y = (H.d * s + H.e * t + H.f) / ww;
+          const double iw = 1.0 / (H.g * s + H.h * t + 1.0);
+          const double x = (H.a * s + H.b * t + H.c) * iw, y = (H.d * s + H.e * t + H.f) * iw;
           const double fx0 = floor(x), fy0 = floor(y);
           if (!(fx0 >= 0.0 && fy0 >= 0.0 && fx0 + 1.0 < (double)w && fy0 + 1.0 < (double)h)) { inside = false; continue; }
           const int x0 = (int)fx0, y0 = (int)fy0;
@@ -123,6 +128,21 @@ decode_tags_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch,
     if (ham_out) ham_out[gid] = (uint8_t)(ham > 255 ? 255 : ham);
     if (margin_out) margin_out[gid] = margin;
   }
+  if (sink.out_n != nullptr && id >= 0) {
+    // the detector's list of tags, corners in the reference's order: the quad's corner k is the tag's corner (k + rot) mod 4
+    const int64_t f = gid / n_quads;
+    int slot = lane == 0 ? atomicAdd(&sink.out_n[f], 1) : 0;
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < sink.max_tags) {
+      const int64_t o = f * sink.max_tags + slot;
+      if (lane < 8) sink.out_corners[o * 8 + lane] = q[2 * (((lane >> 1) - rot + 4) & 3) + (lane & 1)];
+      if (lane == 0) {
+        sink.out_id[o] = id;
+        if (sink.out_margin) sink.out_margin[o] = margin;
+        if (sink.out_ham) sink.out_ham[o] = (uint8_t)ham;
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -145,9 +165,9 @@ extern "C" int agt_set_tag_threshold(agt_ctx* ctx, int mode) {
   return AGT_OK;
 }
 
-extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
-                               const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
-                               int n_quads, int max_hamming) {
+static int decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
+                       const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
+                       int n_quads, int max_hamming, const TagSink& sink) {
   if (!ctx) return AGT_ERR_INVALID;
   if ((int64_t)batch * n_quads == 0) return AGT_OK;
   if (!ctx->d_tag_codes) AGT_FAIL(ctx, AGT_ERR_NOT_READY, "agt_decode_tags: call agt_set_tag_family first");
@@ -158,9 +178,16 @@ extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h
   decode_tags_kernel<<<(unsigned)blocks, TG_WARPS * 32, 0, ctx->stream>>>(d_gray, w, h, pitch, stride, d_quads, d_valid,
                                                                           reinterpret_cast<const unsigned long long*>(ctx->d_tag_codes),
                                                                           ctx->n_tag_codes, d_id, d_rotation, d_hamming, d_margin, n_quads, total,
-                                                                          max_hamming);
+                                                                          max_hamming, sink);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
+}
+
+extern "C" int agt_decode_tags(agt_ctx* ctx, const uint8_t* d_gray, int w, int h, int64_t pitch, int64_t stride, const float* d_quads,
+                               const uint8_t* d_valid, int32_t* d_id, uint8_t* d_rotation, uint8_t* d_hamming, float* d_margin, int batch,
+                               int n_quads, int max_hamming) {
+  return decode_tags(ctx, d_gray, w, h, pitch, stride, d_quads, d_valid, d_id, d_rotation, d_hamming, d_margin, batch, n_quads, max_hamming,
+                     TagSink{nullptr, nullptr, nullptr, nullptr, nullptr, 0});
 }
 
 // =====================================================================================================================
@@ -903,7 +930,7 @@ __device__ __forceinline__ void emit_quad(int f, int c, const Win win, const Com
   for (int k = 0; k < 4; ++k) quad_win[((int64_t)f * max_quads + slot) * 4 + k] = (uint8_t)cwin;
 }
 
-// one thread per component; the first thread of a frame also clears the frame's tag counter (tags_collect_kernel counts into it)
+// one thread per component; the first thread of a frame also clears the frame's tag counter (decode_tags_kernel counts into it)
 __global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_comp, const CompStats* __restrict__ stats,
                                  float* __restrict__ quads, uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win, int* __restrict__ n_quads,
                                  int max_quads, int refine_win, int32_t* __restrict__ out_n) {
@@ -911,29 +938,6 @@ __global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restri
   if (c == 0) out_n[f] = 0;
   if (c >= min(n_comp[f], MAX_COMPONENTS)) return;
   emit_quad(f, c, frame_window(rects, rect_stride, f, w, h), stats, quads, quad_valid, quad_win, n_quads, max_quads, refine_win);
-}
-
-// one thread per quad: keep the ones that decoded, in the reference's corner order
-__global__ void tags_collect_kernel(const float* __restrict__ quads, const int32_t* __restrict__ id, const uint8_t* __restrict__ rot,
-                                    const uint8_t* __restrict__ ham, const float* __restrict__ margin, const int* __restrict__ n_quads,
-                                    int max_quads, int32_t* __restrict__ out_n, int32_t* __restrict__ out_id, float* __restrict__ out_corners,
-                                    float* __restrict__ out_margin, uint8_t* __restrict__ out_ham, int max_tags) {
-  const int f = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= min(n_quads[f], max_quads)) return;
-  const int64_t g = (int64_t)f * max_quads + q;
-  if (id[g] < 0) return;
-  const int slot = atomicAdd(&out_n[f], 1);
-  if (slot >= max_tags) return;
-  const int64_t o = (int64_t)f * max_tags + slot;
-  out_id[o] = id[g];
-  if (out_margin) out_margin[o] = margin[g];
-  if (out_ham) out_ham[o] = ham[g];
-  const int r = rot[g];                                   // the quad's corner k is the tag's corner (k + r) mod 4
-  for (int k = 0; k < 4; ++k) {
-    const int src = (k - r + 4) & 3;
-    out_corners[o * 8 + 2 * k] = quads[g * 8 + 2 * src];
-    out_corners[o * 8 + 2 * k + 1] = quads[g * 8 + 2 * src + 1];
-  }
 }
 
 // warp per frame, lane per group position: the detection of that tag with the largest margin (a tag reported twice fills one slot)
@@ -1066,12 +1070,11 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
       return rc;
     use = refined;
   }
-  if ((rc = agt_decode_tags(ctx, d_gray, w, h, pitch, stride, use, qvalid, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham,
-                            reinterpret_cast<float*>(ws + o_margin), batch, max_quads, max_hamming)))
+  // identification; the quads that decode go straight to the caller's list (no collection pass)
+  if ((rc = decode_tags(ctx, d_gray, w, h, pitch, stride, use, qvalid, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham,
+                        reinterpret_cast<float*>(ws + o_margin), batch, max_quads, max_hamming,
+                        TagSink{d_n_tags, d_ids, d_corners, d_margin, d_hamming, max_tags})))
     return rc;
-  tags_collect_kernel<<<dim3((unsigned)((max_quads + 127) / 128), (unsigned)batch), 128, 0, st>>>(
-      use, reinterpret_cast<int32_t*>(ws + o_id), ws + o_rot, ws + o_ham, reinterpret_cast<float*>(ws + o_margin), nquads, max_quads, d_n_tags,
-      d_ids, d_corners, d_margin, d_hamming, max_tags);
   AGT_LAUNCH_CHECK(ctx);
   return AGT_OK;
 }
