@@ -825,6 +825,8 @@ __global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const int* __re
     const unsigned bm = m & ~(((m << 1) | (lw >> 31)) & ((m >> 1) | (rw << 31)) & up & dn);
     int pos = bm ? atomicAdd(&n_list[f], __popc(bm)) : 0;
     // run by run: the component's statistics (length, coordinate sums, extent) and the boundary pixels of the run
+    // (adding the statistics up in ccl_runs_kernel with shared-memory atomics instead was measured: that kernel 20 -> 47 us, this
+    // one 30 -> 19 us per 64 windows - one CTA's atomics on a border's seven words are slower than the whole grid's at the L2)
     unsigned mm = m;
     int r = 0;
     while (mm) {
