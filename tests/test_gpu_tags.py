@@ -420,3 +420,27 @@ def test_detect_tags_under_uneven_lighting(ctx1080):
     assert missing <= 2, missing
     with pytest.raises(Exception):
         ctx1080.set_tag_threshold(7)
+
+
+@pytest.mark.parametrize("mode", ["local", "window"])
+def test_detect_tags_on_frames_of_odd_size(ctx1080, mode):
+    """Frames whose rows cannot be read as 16-byte words (a 1915 x 1077 crop, as process_frame's undistort + crop produces them:
+    SURVEY.md 8c) take the four-pixels-per-lane forms of the tile / min-max / threshold passes: same tags as on the full frame,
+    corners shifted by the crop's offset."""
+    from accurate_aprilgroup_tracking_b200 import cv_compat
+    cam = synth.CAMERA_1080P
+    pyr, poses, frames = _render(ctx1080, cam, [770, 771, 772, 773])
+    host = cv_compat.default_context()
+    host.set_tag_threshold(mode)
+    try:
+        n_tags = 0
+        for f in range(len(frames)):
+            full = {i: c for i, c, _, _ in host.detect_tags(frames[f])}
+            crop = {i: c for i, c, _, _ in host.detect_tags(np.ascontiguousarray(frames[f][3:, 5:]))}
+            assert set(full) == set(crop) and len(full) >= 2, (f, sorted(full), sorted(crop))
+            n_tags += len(full)
+            for i in full:
+                assert np.abs(crop[i] + np.array([5.0, 3.0]) - full[i]).max() < 0.05, (f, i)
+        assert n_tags >= 12
+    finally:
+        host.set_tag_threshold("auto")
