@@ -155,11 +155,13 @@ def test_refine_host_roi_upload_is_exact(host, ctxvga):
         assert np.array_equal(roi[key], full[key]), key
     assert roi_bytes < 0.6 * full_bytes, (roi_bytes, full_bytes)
     # pinned host frames take the gather-kernel path (one launch per chunk instead of one 2-D copy per frame)
-    import torch
-    pinned = torch.from_numpy(frames).pin_memory()
+    from accurate_aprilgroup_tracking_b200 import cv_compat
+    pinned = cv_compat.pinned_frames(frames.shape)              # an ordinary numpy array, in page-locked memory
+    assert isinstance(pinned, np.ndarray) and pinned.dtype == np.uint8
+    pinned[...] = frames
     host.refine_poses(np.full_like(frames, 255), init, cam.mtx)
     l0 = host.launch_count()
-    pin = host.refine_poses(pinned.numpy(), init, cam.mtx)
+    pin = host.refine_poses(pinned, init, cam.mtx)
     assert host.launch_count() - l0 >= 2          # gather + refinement with its fused pyrDown (a batch this small runs as clusters,
                                                   # which derive their setup record themselves) (+ redo pass)
     for key in ("pose", "cost", "n_valid", "evals", "status"):
