@@ -1046,6 +1046,9 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   const dim3 grid((unsigned)std::min<int64_t>((n + 255) / 256, per_frame), (unsigned)batch);
   // the passes over the list of non-empty items / boundary pixels: sized for the dark part of a frame, whatever the window
   const dim3 grid_ne((unsigned)std::min<int64_t>((n + 255) / 256, std::max<int64_t>(16, (int64_t)8 * ctx->sm_count / batch)), (unsigned)batch);
+  // (both passes of a frame by one CTA of 1024 threads - one launch, tile maxima in shared memory, the second read from the L2 -
+  // measured slower: 48 against 13 + 21 us per 64 windows, 293 against 57 + 80 us per 64 whole frames; the threshold pass is
+  // instruction work - dark bits, runs, first labels - that one SM per frame does not get through)
   uint8_t* tiles = local ? ws + o_tiles : nullptr;
   if (local) tile_max_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride);
   else frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
