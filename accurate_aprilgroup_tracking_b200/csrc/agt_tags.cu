@@ -390,18 +390,17 @@ __global__ void tile_max_kernel(const uint8_t* __restrict__ img, int w, int h, i
   if (lane == 0 && lo <= hi) { atomicMax(&lohi[2 * f], 255 - lo); atomicMax(&lohi[2 * f + 1], hi); }
 }
 
-// Threshold, mask words, list of non-empty items, first labels.  A warp reads 128 pixels of a row (four per lane); the eight
-// lanes of an item put their dark bits together.  A dark pixel's label starts as the first pixel of its horizontal run inside
-// the item, so a run is already one tree of depth 1 and the merge pass has to join runs, not pixels.
+// Threshold, mask words, list of non-empty items.  A warp reads 128 pixels of a row (four per lane); the eight lanes of an item put
+// their dark bits together (rows readable as 16-byte words: sixteen pixels per lane, two lanes per item).  No pixel labels are
+// written here: the common path works on runs (ccl_runs_kernel), and a frame that overflows its tables gets its labels there.
 __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, int64_t pitch, int64_t stride, AGT_WIN_ARGS,
                                 const int* __restrict__ lohi, const uint8_t* __restrict__ tile_hi, int64_t tile_stride,
-                                int* __restrict__ label, uint32_t* __restrict__ mask, int64_t mask_stride,
+                                uint32_t* __restrict__ mask, int64_t mask_stride,
                                 int* __restrict__ n_entries, int2* __restrict__ entries, int* __restrict__ entry_of) {
   const uint8_t* p = img + blockIdx.y * stride;
   const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3) == 0 && (pitch & 3) == 0;
   const int frame_thr = frame_threshold(lohi, blockIdx.y), black = frame_lo(lohi, blockIdx.y);
   const uint8_t* T = tile_hi ? tile_hi + blockIdx.y * tile_stride : nullptr;
-  int* L = label + (int64_t)blockIdx.y * w * h;
   uint32_t* M = mask + blockIdx.y * mask_stride;
   int2* E = entries + blockIdx.y * mask_stride;
   int* P = entry_of + blockIdx.y * mask_stride;        // position of a non-empty item in the list
@@ -453,13 +452,6 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
             P[item] = pos;
           }
         }
-        unsigned mine = ch < chunks ? m & (half ? 0xffff0000u : 0x0000ffffu) : 0u;
-        while (mine) {
-          const int bit = __ffs(mine) - 1;
-          mine &= mine - 1;
-          const unsigned zeros_below = ~m & ((1u << bit) - 1u);
-          L[y * win.ww + ch * 32 + bit] = y * win.ww + ch * 32 + (zeros_below ? 32 - __clz(zeros_below) : 0);
-        }
       }
     }
     return;
@@ -507,14 +499,6 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int w, int h, i
           P[item] = pos;
         }
       }
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (nib >> b & 1u) {
-          const int bit = 4 * sub + b;
-          const unsigned zeros_below = ~m & ((1u << bit) - 1u);
-          const int run0 = zeros_below ? 32 - __clz(zeros_below) : 0;         // first pixel of this pixel's run
-          L[yy[k] * win.ww + ch * 32 + bit] = yy[k] * win.ww + ch * 32 + run0;
-        }
     }
   }
 }
@@ -572,7 +556,8 @@ __device__ __forceinline__ int run_index(unsigned starts, int b) { return __popc
 __global__ void __launch_bounds__(RUNS_THREADS, 1)
 ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, int64_t mask_stride,
                 const int* __restrict__ n_entries, const int2* __restrict__ entries, const int* __restrict__ entry_of, int* __restrict__ n_comp,
-                CompStats* __restrict__ stats, uint8_t* __restrict__ overflow, int* __restrict__ run_code, int* __restrict__ ent_base) {
+                CompStats* __restrict__ stats, uint8_t* __restrict__ overflow, int* __restrict__ run_code, int* __restrict__ ent_base,
+                int* __restrict__ label) {
   __shared__ int s_parent[RUNS_RUN_CAP];
   __shared__ int s_base[RUNS_ENT_CAP];
   __shared__ int s_warp[RUNS_THREADS / 32];
@@ -584,7 +569,26 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, i
   const int2* E = entries + f * mask_stride;
   const int* P = entry_of + f * mask_stride;
   const int n = n_entries[f];
-  if (n > RUNS_ENT_CAP) { if (tid == 0) overflow[f] = 1; return; }
+  // A frame that does not fit the tables goes through the pixel-level union-find (ccl_merge_kernel ...), which wants every dark
+  // pixel labelled with the first pixel of its run inside the item - a run is then one tree of depth 1 and the merge pass joins
+  // runs, not pixels.  Only such frames pay for those labels.
+  auto overflow_exit = [&]() {
+    int* L = label + (int64_t)f * w * h;
+    for (int e = tid; e < n; e += RUNS_THREADS) {
+      const int2 v = E[e];
+      const int y = v.x / chunks, i0 = y * win.ww + (v.x - y * chunks) * 32;
+      const unsigned m = (unsigned)v.y;
+      unsigned mm = m;
+      while (mm) {
+        const int bit = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const unsigned zeros_below = ~m & ((1u << bit) - 1u);
+        L[i0 + bit] = i0 + (zeros_below ? 32 - __clz(zeros_below) : 0);
+      }
+    }
+    if (tid == 0) overflow[f] = 1;
+  };
+  if (n > RUNS_ENT_CAP) { overflow_exit(); return; }
   // ---- runs per entry, exclusive prefix sum (eight consecutive entries per thread)
   int cnt[8], sum = 0;
 #pragma unroll
@@ -608,7 +612,7 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, i
   }
   __syncthreads();
   const int total = s_total;
-  if (total > RUNS_RUN_CAP) { if (tid == 0) overflow[f] = 1; return; }
+  if (total > RUNS_RUN_CAP) { overflow_exit(); return; }
   {
     int run = s_warp[wid] + incl - sum;
 #pragma unroll
@@ -1052,10 +1056,10 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   uint8_t* tiles = local ? ws + o_tiles : nullptr;
   if (local) tile_max_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride);
   else frame_minmax_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi);
-  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride, label, mask, mask_stride, nent,
-                                       entries, entry_of);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(d_gray, w, h, pitch, stride, d_rects, rect_stride, lohi, tiles, tile_stride, mask, mask_stride, nent, entries,
+                                       entry_of);
   ccl_runs_kernel<<<(unsigned)batch, RUNS_THREADS, 0, st>>>(w, h, d_rects, rect_stride, mask, mask_stride, nent, entries, entry_of, ncomp, stats,
-                                                           overflow, run_code, ent_base);
+                                                           overflow, run_code, ent_base, label);
   ccl_merge_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow);
   ccl_flatten_number_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, ncomp, stats, overflow);
   comp_stats_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, stats, overflow);
