@@ -817,17 +817,27 @@ __global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const int* __re
   const int2* E = entries + f * mask_stride;
   const int* code = run_code + (int64_t)f * RUNS_RUN_CAP;
   int2* P = list + (int64_t)f * w * h;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int2 v = E[e];
+  const int lane = threadIdx.x & 31;
+  for (int e0 = blockIdx.x * blockDim.x + threadIdx.x - lane; e0 < n; e0 += gridDim.x * blockDim.x) {      // (uniform across a warp)
+    const int e = e0 + lane;
+    const bool act = e < n;
+    const int2 v = act ? E[e] : make_int2(0, 0);
     const int item = v.x, y = item / chunks, ch = item - y * chunks;
     const unsigned m = (unsigned)v.y;
-    const unsigned up = y > 0 ? M[item - chunks] : 0u, dn = y < win.hh - 1 ? M[item + chunks] : 0u;
-    const unsigned lw = ch > 0 ? M[item - 1] : 0u, rw = ch < chunks - 1 ? M[item + 1] : 0u;
-    const int base = by_label ? 0 : ent_base[(int64_t)f * RUNS_ENT_CAP + e];
+    const unsigned up = act && y > 0 ? M[item - chunks] : 0u, dn = act && y < win.hh - 1 ? M[item + chunks] : 0u;
+    const unsigned lw = act && ch > 0 ? M[item - 1] : 0u, rw = act && ch < chunks - 1 ? M[item + 1] : 0u;
+    const int base = by_label || !act ? 0 : ent_base[(int64_t)f * RUNS_ENT_CAP + e];
     const int xb = ch * 32, i0 = y * win.ww + xb;
     // (a neighbour outside the window reads as background: the edge of the window is a boundary)
     const unsigned bm = m & ~(((m << 1) | (lw >> 31)) & ((m >> 1) | (rw << 31)) & up & dn);
-    int pos = bm ? atomicAdd(&n_list[f], __popc(bm)) : 0;
+    // room in the list for the boundary pixels of the warp's 32 items by one addition
+    const int cnt = __popc(bm);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int pos = lane == 0 && total > 0 ? atomicAdd(&n_list[f], total) : 0;
+    pos = __shfl_sync(0xffffffffu, pos, 0) + incl - cnt;
     // run by run: the component's statistics (length, coordinate sums, extent) and the boundary pixels of the run
     // (adding the statistics up in ccl_runs_kernel with shared-memory atomics instead was measured: that kernel 20 -> 47 us, this
     // one 30 -> 19 us per 64 windows - one CTA's atomics on a border's seven words are slower than the whole grid's at the L2)
@@ -850,7 +860,11 @@ __global__ void boundary_list_kernel(int w, int h, AGT_WIN_ARGS, const int* __re
         const int xa = xb + a;
         atomicAdd(&st.area, len);
         atomicAdd(&st.sx, (unsigned long long)(len * xa + len * (len - 1) / 2)); atomicAdd(&st.sy, (unsigned long long)y * len);
-        atomicMin(&st.x0, xa); atomicMax(&st.x1, xa + len - 1); atomicMin(&st.y0, y); atomicMax(&st.y1, y);
+        // the extent only ever grows: look first (past the L1), most runs lie inside what is there already
+        if (xa < __ldcg(&st.x0)) atomicMin(&st.x0, xa);
+        if (xa + len - 1 > __ldcg(&st.x1)) atomicMax(&st.x1, xa + len - 1);
+        if (y < __ldcg(&st.y0)) atomicMin(&st.y0, y);
+        if (y > __ldcg(&st.y1)) atomicMax(&st.y1, y);
       }
       unsigned bb = bm & bits;
       while (bb) { const int b = __ffs(bb) - 1; bb &= bb - 1; P[pos++] = make_int2(i0 + b, c); }
