@@ -128,6 +128,10 @@ extern "C" int agt_create(int device, agt_ctx** out) {
     ctx->lk_split_max = e ? atoi(e) : 8 * ctx->sm_count;
   }
   {
+    const char* e = getenv("AGT_TAG_SEPARATE_PASSES");
+    ctx->tag_separate_passes = e ? atoi(e) : 0;
+  }
+  {
     unsigned hc = std::thread::hardware_concurrency();
     ctx->upload_threads = hc == 0 ? 4 : (hc < 8 ? (int)hc : 8);
   }

@@ -69,6 +69,7 @@ struct agt_ctx {
   uint64_t* d_tag_codes;         // tag family (36-bit code words) of agt_decode_tags / agt_detect_tags
   int n_tag_codes;
   int tag_threshold;             // agt_set_tag_threshold: 0 auto, 1 one threshold per search window, 2 local white level
+  int tag_separate_passes;       // AGT_TAG_SEPARATE_PASSES=1: the quadrilateral passes as launches of their own even for batches (A/B)
   // scratch device memory owned by the context (host entry points)
   void* scratch[8];
   size_t scratch_bytes[8];

@@ -9,6 +9,7 @@
 // border may hold two wrong cells, and the 36 data bits are matched against the family over the four rotations (each lane
 // tries every 32nd code word, popcount of the xor); returns id, rotation, Hamming distance and the mean distance of the cells
 // from the threshold - the analogue of apriltag's decision_margin, which the reference compares with 50.
+#include <cooperative_groups.h>
 #include <algorithm>
 
 #include "agt_common.cuh"
@@ -960,6 +961,31 @@ __global__ void quad_emit_kernel(int w, int h, AGT_WIN_ARGS, const int* __restri
   emit_quad(f, c, frame_window(rects, rect_stride, f, w, h), stats, quads, quad_valid, quad_win, n_quads, max_quads, refine_win);
 }
 
+// Batches: the three passes and the emission of a frame by one thread-block cluster - a cluster barrier between the passes
+// instead of a kernel boundary (four launches of 6-8 us, most of it ramp, tail and the first dependent loads, for microseconds
+// of work): 23.4 against 28 us per 64 windows.  Measured and dropped: one CTA per frame (33.6 us: too few threads for the work),
+// the boundary list in the same cluster kernel with 512 threads per CTA (53 against 20 + 23 us).
+constexpr int FIT_CLUSTER = 8, FIT_THREADS = 256;
+__global__ void __launch_bounds__(FIT_THREADS)
+quad_fit_cluster_kernel(int w, int h, AGT_WIN_ARGS, const int* __restrict__ n_list, const int2* __restrict__ list, const int* __restrict__ n_comp,
+                        CompStats* __restrict__ stats, float* __restrict__ quads, uint8_t* __restrict__ quad_valid, uint8_t* __restrict__ quad_win,
+                        int* __restrict__ n_quads, int max_quads, int refine_win, int32_t* __restrict__ out_n) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int f = blockIdx.x / FIT_CLUSTER, rank = blockIdx.x % FIT_CLUSTER, t = rank * FIT_THREADS + threadIdx.x;
+  const Win win = frame_window(rects, rect_stride, f, w, h);
+  const int2* P = list + (int64_t)f * w * h;
+  const int n = n_list[f];
+  if (t == 0) out_n[f] = 0;
+  for (int pass = 0; pass < 3; ++pass) {
+    far_pass(f, win.ww, P, n, stats, pass, t, FIT_CLUSTER * FIT_THREADS);
+    __threadfence();
+    cluster.sync();
+  }
+  const int nc = min(n_comp[f], MAX_COMPONENTS);
+  for (int c = t; c < nc; c += FIT_CLUSTER * FIT_THREADS) emit_quad(f, c, win, stats, quads, quad_valid, quad_win, n_quads, max_quads, refine_win);
+}
+
 // warp per frame, lane per group position: the detection of that tag with the largest margin (a tag reported twice fills one slot)
 __global__ void pack_detections_kernel(const int32_t* __restrict__ n_det, const int32_t* __restrict__ det_id, const float* __restrict__ det_corners,
                                        const float* __restrict__ det_margin, int max_tags, const int32_t* __restrict__ group_ids, int n_group,
@@ -1079,11 +1105,25 @@ extern "C" int agt_detect_tags_roi(agt_ctx* ctx, const uint8_t* d_gray, int w, i
   comp_stats_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, nent, entries, mask_stride, stats, overflow);
   boundary_list_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, label, mask, mask_stride, nent, entries, overflow, run_code, ent_base, stats,
                                                 nlist, far_list);
-  // (the three passes and the emission of a frame by one CTA - one launch instead of four - measured slower: 33.6 against 27.8 us
-  // per 64 windows, the passes of a frame become one chain of dependent loads and atomics)
-  for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, nlist, far_list, stats, pass);
-  quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid, ws + o_win,
-                                                                                   nquads, max_quads, refine_win, d_n_tags);
+  if (batch >= 8 && ctx->tag_separate_passes == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)batch * FIT_CLUSTER);
+    cfg.blockDim = dim3(FIT_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = FIT_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int* c_nlist = nlist; const int2* c_list = far_list; const int* c_ncomp = ncomp;
+    uint8_t* qwin = ws + o_win;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, quad_fit_cluster_kernel, w, h, d_rects, rect_stride, c_nlist, c_list, c_ncomp, stats, quads,
+                                             qvalid, qwin, nquads, max_quads, refine_win, d_n_tags);
+    if (e != cudaSuccess) AGT_FAIL(ctx, AGT_ERR_CUDA, "agt_detect_tags: cluster launch failed: %s", cudaGetErrorString(e));
+  } else {
+    for (int pass = 0; pass < 3; ++pass) comp_far_kernel<<<grid_ne, 256, 0, st>>>(w, h, d_rects, rect_stride, nlist, far_list, stats, pass);
+    quad_emit_kernel<<<dim3(MAX_COMPONENTS / 128, (unsigned)batch), 128, 0, st>>>(w, h, d_rects, rect_stride, ncomp, stats, quads, qvalid,
+                                                                                     ws + o_win, nquads, max_quads, refine_win, d_n_tags);
+  }
   AGT_LAUNCH_CHECK(ctx);
   const float* use = quads;
   if (refine_win > 0) {
