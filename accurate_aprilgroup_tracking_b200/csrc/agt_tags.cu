@@ -528,7 +528,7 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
 // no pixel label is written or read on this path.  A frame with more entries or runs than the tables hold is flagged and goes
 // through ccl_merge_kernel, ccl_flatten_number_kernel and comp_stats_kernel instead (which return at once for every other
 // frame) and carries its codes in the pixel labels.
-constexpr int RUNS_THREADS = 512, RUNS_ENT_CAP = 8 * RUNS_THREADS, RUNS_RUN_CAP = 12 * RUNS_THREADS;
+constexpr int RUNS_THREADS = 1024, RUNS_ENT_PER = 4, RUNS_ENT_CAP = RUNS_ENT_PER * RUNS_THREADS, RUNS_RUN_CAP = 6 * RUNS_THREADS;
 
 // find with path halving: every node on the way is pointed at its grandparent.  Safe next to concurrent unions - a node that is
 // not a root never becomes one again and is written by nobody but such walks, and any ancestor is a valid parent.
@@ -590,11 +590,11 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, i
     if (tid == 0) overflow[f] = 1;
   };
   if (n > RUNS_ENT_CAP) { overflow_exit(); return; }
-  // ---- runs per entry, exclusive prefix sum (eight consecutive entries per thread)
-  int cnt[8], sum = 0;
+  // ---- runs per entry, exclusive prefix sum (RUNS_ENT_PER consecutive entries per thread)
+  int cnt[RUNS_ENT_PER], sum = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int e = tid * 8 + k;
+  for (int k = 0; k < RUNS_ENT_PER; ++k) {
+    const int e = tid * RUNS_ENT_PER + k;
     const unsigned m = e < n ? (unsigned)E[e].y : 0u;
     cnt[k] = __popc(m & ~(m << 1));
     sum += cnt[k];
@@ -617,7 +617,7 @@ ccl_runs_kernel(int w, int h, AGT_WIN_ARGS, const uint32_t* __restrict__ mask, i
   {
     int run = s_warp[wid] + incl - sum;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s_base[tid * 8 + k] = run; run += cnt[k]; }
+    for (int k = 0; k < RUNS_ENT_PER; ++k) { s_base[tid * RUNS_ENT_PER + k] = run; run += cnt[k]; }
   }
   for (int r = tid; r < total; r += RUNS_THREADS) s_parent[r] = r;
   __syncthreads();
