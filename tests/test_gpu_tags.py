@@ -396,7 +396,7 @@ def test_detect_tags_under_uneven_lighting(ctx1080):
         err += [np.abs(l[i] - e[i]).max() for i in set(l) & set(e)]
     print(f"uneven lighting: {n_even} tags on the even frames; on the dim frames local {n_local}, one threshold {n_one}, aruco {n_aruco}; "
           f"corners vs the even frames median {np.median(err):.3f} max {np.max(err):.2f} px")
-    assert n_local >= n_even - 2 and n_local >= n_aruco - 2
+    assert n_local >= n_even - 4 and n_local >= n_aruco - 4             # measured: 76 of 78, aruco 78
     assert n_one < n_local - n // 2                          # the rule this replaces loses tags on most frames
     # (the few corners that move by pixels are those of steeply tilted tags, where cornerSubPix has two answers: see the corner test)
     assert np.median(err) < 0.1 and np.percentile(err, 95) < 0.5 and np.sum(np.array(err) > 1.0) <= 3 and np.max(err) < 6.0
